@@ -1,0 +1,875 @@
+/*
+ * oracle/bsalign_oracle.c -- TEST INFRASTRUCTURE ONLY. Never linked into, imported by or executed from
+ * the product path (bsalign_b200/); only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline /
+ * --impl reference legs may load it.
+ *
+ * A plain scalar C restatement of the reference's banded striped DP hot path, written in LINEAR band
+ * coordinates (band position p = 0..bw-1; the reference's SSE lane j owns the "running block"
+ * p in [j*W, (j+1)*W), W = bw/16).  Every int8 operation saturates exactly where the SSE code
+ * saturates (adds/subs_epi8), so the output is bit-identical to the reference's SSE4.2 build.
+ *
+ * Parity status: PINNED.  tests/test_oracle_vs_ref.py compares every function here against the
+ * unmodified reference compiled into oracle/_ref/libbsref.so (see oracle/ref_harness.c), and
+ * tests/golden/ holds vectors generated from that build (tests/golden/make_golden.py) plus the README
+ * example (README.md:36-42).
+ *
+ * Citations are into /root/reference/bsalign.h unless stated otherwise.
+ */
+#include <stdint.h>
+#include <stdlib.h>
+#include <string.h>
+#include <pthread.h>
+
+#define BSO_LANES 16                 /* WORDSIZE of the SSE4.2 build, bsalign.h:142 */
+#define BSO_EPI8_MIN (-63)           /* SEQALIGN_SCORE_EPI8_MIN, bsalign.h:56 */
+#define BSO_EPI8_MAX (63)            /* SEQALIGN_SCORE_EPI8_MAX, bsalign.h:57 */
+#define BSO_SCORE_MIN (-536870911)   /* SEQALIGN_SCORE_MIN = -(INT32_MAX >> 2), bsalign.h:58 */
+#define BSO_MODE_GLOBAL 0
+#define BSO_MODE_OVERLAP 1
+#define BSO_MODE_EXTEND 2
+
+#define BSO_ERR_RANGE 1   /* a score lookup left the band (the reference would read out of bounds) */
+#define BSO_ERR_LOOP  2   /* traceback found no consistent predecessor (the reference would spin forever) */
+#define BSO_ERR_CIGCAP 4  /* cigar buffer too small */
+#define BSO_ERR_REFBUG 8  /* input reaches a reference code path that corrupts its own scratch memory (edit row_movx, bsalign.h:704-713) */
+
+static inline int8_t sat8(int v){ return (int8_t)(v > 127 ? 127 : (v < -128 ? -128 : v)); }
+static inline int8_t adds8(int8_t a, int8_t b){ return sat8((int)a + (int)b); }
+static inline int8_t subs8(int8_t a, int8_t b){ return sat8((int)a - (int)b); }
+static inline int8_t max8(int8_t a, int8_t b){ return a > b ? a : b; }
+
+/* bsalign.h:2084-2092 */
+int bso_epi8_piecewise(int8_t go1, int8_t ge1, int8_t go2, int8_t ge2, int bw){
+	if(go2 < go1 && ge2 > ge1 && go2 + ge2 < go1 + ge1 && (go1 - go2) / (ge1 - ge2) < bw) return 2;
+	return go1 ? 1 : 0;
+}
+
+typedef struct {
+	int8_t *u, *e, *q;  /* linear band order */
+	int32_t *ub;        /* 17 ints: ub[0] = H just left of u[0]; ub[j] = H at band pos j*W-1 */
+} bso_row_t;
+
+typedef struct {
+	uint32_t qlen, tlen, bw, W;
+	int pw, mode;
+	const uint8_t *qseq, *tseq;
+	const int8_t *mtx;
+	int8_t go1, ge1, go2, ge2;
+	int8_t smax, smin;
+	/* trace: row y lives at index y+1 (row -1 = init row, bsalign.h:3922) */
+	int8_t *U, *E, *Q;
+	int32_t *UB;    /* (tlen+1) * 17 */
+	int32_t *begs;  /* tlen+1, begs[0] is row -1 */
+	int err;
+} bso_epi8_t;
+
+static inline bso_row_t bso_trace_row(bso_epi8_t *a, int64_t y){
+	bso_row_t r;
+	r.u = a->U + (y + 1) * (int64_t)a->bw;
+	r.e = a->E ? a->E + (y + 1) * (int64_t)a->bw : NULL;
+	r.q = a->Q ? a->Q + (y + 1) * (int64_t)a->bw : NULL;
+	r.ub = a->UB + (y + 1) * 17;
+	return r;
+}
+
+/* bsalign.h:2094-2140: row -1 */
+static void bso_row_init(bso_epi8_t *a, bso_row_t r, int8_t max_nt, int8_t min_nt){
+	uint32_t p, j, W = a->W, bw = a->bw;
+	int32_t blk[BSO_LANES], s;
+	int two = (a->go2 < a->go1 && a->ge2 > a->ge1 && a->go2 + a->ge2 < a->go1 + a->ge1 && (a->go1 - a->go2) / (a->ge1 - a->ge2) < (int)bw);
+	if(a->mode == BSO_MODE_GLOBAL || a->mode == BSO_MODE_EXTEND){
+		int8_t ext = two ? a->ge2 : a->ge1;
+		for(p=0;p<bw;p++) r.u[p] = ext;
+		for(j=0;j<BSO_LANES;j++) blk[j] = ext * (int)W;
+		r.u[0] = (int8_t)(a->go1 + a->ge1 + min_nt - max_nt);
+		blk[0] += r.u[0] - ext;
+		if(two){
+			uint32_t xp = (uint32_t)((a->go2 - a->go1) / (a->ge1 - a->ge2));
+			for(p=1;p<xp&&p<bw;p++){ /* the reference has no p<bw guard: xp >= bw writes past the row */
+				r.u[p] = a->ge1;
+				blk[p / W] += a->ge1 - a->ge2;
+			}
+		}
+		s = max_nt - min_nt;
+		for(j=0;j<BSO_LANES;j++){ r.ub[j] = s; s += blk[j]; }
+		r.ub[BSO_LANES] = s;
+	} else {
+		memset(r.u, 0, bw);
+		memset(r.ub, 0, 17 * sizeof(int32_t));
+	}
+	if(two){
+		memset(r.e, BSO_EPI8_MIN, bw);
+		memset(r.q, BSO_EPI8_MIN, bw);
+	} else if(a->go1){
+		memset(r.e, BSO_EPI8_MIN, bw);
+	}
+}
+
+/* bsalign.h:3187-3197: absolute H at band position pos of a row */
+static int bso_getscore(bso_epi8_t *a, bso_row_t r, int64_t pos){
+	uint32_t W = a->W, j, i, k;
+	int s;
+	if(pos < 0 || pos >= (int64_t)a->bw){ a->err |= BSO_ERR_RANGE; return BSO_SCORE_MIN; }
+	j = pos / W; i = pos % W;
+	s = r.ub[j];
+	for(k=0;k<=i;k++) s += r.u[j * W + k];
+	return s;
+}
+
+/* bsalign.h:2244-2392: realign the previous row to a band that starts m cells further right */
+static void bso_row_shift(bso_epi8_t *a, bso_row_t src, bso_row_t dst, uint32_t m, int8_t nt_max, int8_t nt_min){
+	uint32_t W = a->W, bw = a->bw, p, j, cyc, mov;
+	int32_t sums[BSO_LANES];
+	int pw = a->pw;
+	if(m >= bw){ /* :2253-2259 */
+		memset(dst.u, 0, bw);
+		if(pw) memset(dst.e, 0, bw);
+		if(pw == 2) memset(dst.q, 0, bw);
+		for(j=0;j<=BSO_LANES;j++) dst.ub[j] = BSO_SCORE_MIN;
+		return;
+	}
+	if(m == 0){ /* :2260-2269 */
+		memcpy(dst.u, src.u, bw);
+		if(pw) memcpy(dst.e, src.e, bw);
+		if(pw == 2) memcpy(dst.q, src.q, bw);
+		memcpy(dst.ub, src.ub, 17 * sizeof(int32_t));
+		return;
+	}
+	cyc = m / W; mov = m % W;
+	/* the byte shuffles of :2271-2345 amount to dst[p] = src[p + m], zero filled past the old band */
+	for(p=0;p<bw;p++){
+		int in = (p + m < bw);
+		dst.u[p] = in ? src.u[p + m] : 0;
+		if(pw) dst.e[p] = in ? src.e[p + m] : 0;
+		if(pw == 2) dst.q[p] = in ? src.q[p + m] : 0;
+	}
+	/* :2310-2331, :2350-2355: block anchors; sums[j] = old ub[j] + first `mov` cells of old block j */
+	for(j=0;j<BSO_LANES;j++){
+		sums[j] = src.ub[j];
+		for(p=0;p<mov;p++) sums[j] += src.u[j * W + p];
+	}
+	for(j=0;j+cyc<BSO_LANES;j++) dst.ub[j] = sums[j + cyc];
+	for(j=BSO_LANES-cyc;j<=BSO_LANES;j++) dst.ub[j] = src.ub[BSO_LANES];
+	/* :2357-2389: synthesize the overhang (cells the old band did not cover) */
+	{
+		uint32_t i0 = bw - m, d;
+		int c;
+		if(pw == 2){
+			d = (uint32_t)((a->go1 - a->go2) / (a->ge2 - a->ge1));
+			c = (nt_min < a->go2 + a->ge2 ? nt_min : a->go2 + a->ge2) - 1 - nt_max + (a->go2 + a->ge2);
+		} else {
+			d = bw + 1;
+			c = (nt_min < a->go1 + a->ge1 ? nt_min : a->go1 + a->ge1) - 1 - nt_max + (a->go1 + a->ge1);
+		}
+		dst.u[i0] = (int8_t)c;
+		/* c accumulates the overhang values; every block end crossed adds the running total to its anchor */
+		for(p=i0+1;p<=bw;p++){
+			if(p % W == 0){ /* crossed the end of block p/W - 1 */
+				dst.ub[p / W] += c;
+			}
+			if(p == bw) break;
+			{
+				int8_t g = (p < i0 + d) ? a->ge1 : a->ge2;
+				dst.u[p] = g;
+				c += g;
+			}
+		}
+	}
+}
+
+/* score of aligning query position x against target base tb: the query-profile entry (:2166-2191) */
+static inline int8_t bso_prof(bso_epi8_t *a, uint32_t x, uint8_t tb){
+	return x < a->qlen ? a->mtx[a->qseq[x] * 4 + tb] : BSO_EPI8_MIN;
+}
+
+/* :2639-2652: carry the block-exit F of lane j-1 into lane j, extended across whole blocks */
+static void bso_fpen(bso_epi8_t *a, const int8_t fend[BSO_LANES], const int32_t *ub, int8_t ge, int8_t fin[BSO_LANES]){
+	int j, s, t;
+	fin[0] = BSO_EPI8_MIN;
+	for(j=1;j<BSO_LANES;j++) fin[j] = fend[j - 1];
+	t = (int)a->W * ge;
+	s = t + fin[0] - (ub[1] - ub[0]);
+	for(j=1;j<BSO_LANES;j++){
+		if(fin[j] < s) fin[j] = (int8_t)s;
+		s = t + fin[j] - (ub[j + 1] - ub[j]);
+	}
+}
+
+/*
+ * One DP row (bsalign.h:2727-2793 linear, :2885-2960 affine, :3084-3179 two-piece, tail :2618-2636).
+ * prev = previous row already shifted to this row's band; out = new row.  Returns nothing; out.ub[0]
+ * is H(rbeg, y).
+ */
+static void bso_row_cal(bso_epi8_t *a, uint32_t rbeg, uint8_t tb, bso_row_t prev, bso_row_t out, int rh){
+	uint32_t W = a->W, j, i, p;
+	int pw = a->pw;
+	int8_t GE = a->ge1, GOE = (int8_t)(a->go1 + a->ge1), GP = a->ge2, GQP = (int8_t)(a->go2 + a->ge2);
+	int8_t GOQ = subs8(GOE, GQP);
+	int8_t fend[BSO_LANES], gend[BSO_LANES], fin[BSO_LANES], gin[BSO_LANES], vt[BSO_LANES];
+	int h0, t0;
+	/* cell 0 of the band: the diagonal predecessor H(rbeg-1, y-1) is outside the stored row (:2899-2907) */
+	h0 = (rh - prev.ub[0]) + bso_prof(a, rbeg, tb);
+	if(pw == 0) t0 = prev.u[0] + GE;
+	else if(pw == 1) t0 = prev.u[0] + prev.e[0];
+	else t0 = prev.u[0] + (prev.e[0] > prev.q[0] ? prev.e[0] : prev.q[0]);
+	if(h0 >= t0){ if(h0 > BSO_EPI8_MAX) h0 = BSO_EPI8_MAX; }
+	else h0 = BSO_EPI8_MIN;
+	/* pass 1: F (and G) leaving every running block when nothing enters it */
+	for(j=0;j<BSO_LANES;j++){
+		int8_t f = BSO_EPI8_MIN, g = BSO_EPI8_MIN, h, u, e, q;
+		for(i=0;i<W;i++){
+			p = j * W + i;
+			h = (p == 0) ? (int8_t)h0 : bso_prof(a, rbeg + p, tb);
+			u = prev.u[p];
+			if(pw == 0){
+				e = adds8(u, GE);
+				h = max8(e, h); h = max8(f, h);
+				f = subs8(adds8(h, GE), u);
+			} else if(pw == 1){
+				e = adds8(prev.e[p], u);
+				h = max8(e, h); h = max8(f, h);
+				f = adds8(f, GE); h = adds8(h, GOE); f = max8(f, h); f = subs8(f, u);
+			} else {
+				e = adds8(prev.e[p], u); q = adds8(prev.q[p], u);
+				h = max8(e, h); h = max8(q, h); h = max8(f, h); h = max8(g, h);
+				f = adds8(f, GE); h = adds8(h, GOE); f = max8(f, h); f = subs8(f, u);
+				g = adds8(g, GP); h = subs8(h, GOQ); g = max8(g, h); g = subs8(g, u);
+			}
+		}
+		fend[j] = f; gend[j] = g;
+	}
+	bso_fpen(a, fend, prev.ub, GE, fin);
+	if(pw == 2) bso_fpen(a, gend, prev.ub, GP, gin);
+	/* pass 2: the real row */
+	for(j=0;j<BSO_LANES;j++){
+		int8_t f = fin[j], g = (pw == 2) ? gin[j] : 0, h = 0, u = 0, e, q, v = 0, z;
+		for(i=0;i<W;i++){
+			p = j * W + i;
+			z = (p == 0) ? (int8_t)h0 : bso_prof(a, rbeg + p, tb);
+			u = prev.u[p];
+			if(pw == 0){
+				e = adds8(u, GE);
+				h = max8(e, z); h = max8(f, h);
+				out.u[p] = subs8(h, v);
+				v = subs8(h, u);
+				f = subs8(adds8(h, GE), u);
+			} else if(pw == 1){
+				e = adds8(prev.e[p], u);
+				h = max8(e, z); h = max8(f, h);
+				out.u[p] = subs8(h, v);
+				v = subs8(h, u);
+				e = adds8(e, GE); e = subs8(e, h); e = max8(e, GOE);
+				out.e[p] = e;
+				f = adds8(f, GE); h = adds8(h, GOE); f = max8(f, h); f = subs8(f, u);
+			} else {
+				e = adds8(prev.e[p], u);
+				h = max8(e, z);
+				q = adds8(prev.q[p], u);
+				h = max8(q, h); h = max8(f, h); h = max8(g, h);
+				out.u[p] = subs8(h, v);
+				v = subs8(h, u);
+				e = adds8(e, GE); e = subs8(e, h); e = max8(e, GOE);
+				out.e[p] = e;
+				q = adds8(q, GP); q = subs8(q, h); q = max8(q, GQP);
+				out.q[p] = q;
+				f = adds8(f, GE); h = adds8(h, GOE); f = max8(f, h); f = subs8(f, u);
+				g = adds8(g, GP); h = subs8(h, GOQ); g = max8(g, h); g = subs8(g, u);
+			}
+		}
+		/* the SSE code leaves h biased by the gap-open constant after the loop and removes it (:2958, :3177) */
+		if(pw == 1) h = subs8(h, GOE);
+		else if(pw == 2) h = subs8(h, GQP);
+		vt[j] = subs8(h, u); /* V = H(x,y) - H(x,y-1) of the block's last cell (:2622) */
+	}
+	/* tail (:2618-2636): new anchors; first cell of every block still lacks the V of its left neighbour */
+	for(j=1;j<=BSO_LANES;j++) out.ub[j] = prev.ub[j] + vt[j - 1];
+	for(j=1;j<BSO_LANES;j++) out.u[j * W] = subs8(out.u[j * W], vt[j - 1]);
+	out.ub[0] = prev.ub[0] + out.u[0];
+	out.u[0] = 0;
+}
+
+/* bsalign.h:3213-3291: arg-max of a row with the SSE reduction's tie-break order */
+static uint32_t bso_row_max(bso_epi8_t *a, bso_row_t r, int *max_score){
+	uint32_t W = a->W, j, c, i, nchunk = (W + 31) / 32, best_lane, best_chunk, x, y, pos;
+	int32_t Max[BSO_LANES], Scr[BSO_LANES];
+	uint32_t Idx[BSO_LANES];
+	int umax, uscr;
+	for(j=0;j<BSO_LANES;j++){ Max[j] = BSO_SCORE_MIN; Scr[j] = r.ub[j]; Idx[j] = j; }
+	for(c=0;c<nchunk;c++){
+		uint32_t lo = c * 32, hi = lo + 32 < W ? lo + 32 : W;
+		for(j=0;j<BSO_LANES;j++){
+			int run = 0, mx = -32767, h; /* int16 lanes in the reference; |run| <= 32*128 never saturates */
+			for(i=lo;i<hi;i++){ run += r.u[j * W + i]; if(run > mx) mx = run; }
+			h = Scr[j] + mx;
+			if(h > Max[j]){ Max[j] = h; Idx[j] = j | (c << 8); }
+			Scr[j] += run;
+		}
+	}
+	/* lanes j, j+4, j+8, j+12 are folded pairwise keeping the lower lane on ties (:3264-3266) */
+	for(j=0;j<4;j++){
+		int32_t m0 = Max[j], m1 = Max[j + 8];
+		uint32_t i0 = Idx[j], i1 = Idx[j + 8];
+		if(Max[j + 4] > m0){ m0 = Max[j + 4]; i0 = Idx[j + 4]; }
+		if(Max[j + 12] > m1){ m1 = Max[j + 12]; i1 = Idx[j + 12]; }
+		if(m1 > m0){ m0 = m1; i0 = i1; }
+		Max[j] = m0; Idx[j] = i0;
+	}
+	*max_score = Max[0]; x = 0;
+	for(j=1;j<4;j++) if(Max[j] > *max_score){ *max_score = Max[j]; x = j; }
+	best_lane = Idx[x] & 0xFF; best_chunk = Idx[x] >> 8;
+	x = best_chunk * 32; y = (best_chunk + 1) * 32 < W ? (best_chunk + 1) * 32 : W;
+	pos = x; umax = BSO_SCORE_MIN; uscr = 0;
+	for(;x<y;x++){
+		uscr += r.u[best_lane * W + x];
+		if(uscr > umax){ pos = x; umax = uscr; }
+	}
+	return best_lane * W + pos;
+}
+
+/* bsalign.h:3331-3349 */
+static int bso_band_mov(bso_epi8_t *a, const int32_t *ub, uint32_t tidx, uint32_t qoff){
+	uint32_t W = a->W, i;
+	int noisy = 0;
+	uint32_t nz;
+	if(tidx <= W * BSO_LANES / 4) return 0;
+	if(qoff + W * BSO_LANES >= a->qlen) return 0;
+	for(i=1;i<=BSO_LANES;i++) noisy += ub[i] < ub[i - 1] ? ub[i - 1] - ub[i] : ub[i] - ub[i - 1];
+	nz = ((uint32_t)(noisy / BSO_LANES)) / W * BSO_LANES / 2; /* int / u4i promotes to unsigned in the reference */
+	noisy = (int)(16u > nz ? 16u : nz);
+	if(ub[0] + noisy < ub[BSO_LANES]) return 2;
+	if(ub[0] > ub[BSO_LANES] + noisy) return 0;
+	return 1;
+}
+
+typedef struct { uint32_t *buf; uint32_t cap, n; uint32_t run; int on; } bso_cig_t;
+
+/* bsalign.h:409-417 */
+static void bso_cig_push(bso_epi8_t *a, bso_cig_t *cg, uint32_t op, uint32_t sz){
+	if(op == (cg->run & 0xf)){ cg->run += sz << 4; return; }
+	if(cg->run){
+		if(cg->on){ if(cg->n < cg->cap) cg->buf[cg->n] = cg->run; else if(a) a->err |= BSO_ERR_CIGCAP; }
+		cg->n++;
+	}
+	cg->run = sz << 4 | op;
+}
+static void bso_cig_flush(bso_epi8_t *a, bso_cig_t *cg){
+	if(cg->run){
+		if(cg->on){ if(cg->n < cg->cap) cg->buf[cg->n] = cg->run; else if(a) a->err |= BSO_ERR_CIGCAP; }
+		cg->n++;
+	}
+	cg->run = 0;
+}
+
+/* H(col, row) from the trace (bsalign.h:3199-3202) */
+static int bso_mtx_score(bso_epi8_t *a, int64_t row, int64_t col){
+	if(row < -1 || row >= (int64_t)a->tlen){ a->err |= BSO_ERR_RANGE; return BSO_SCORE_MIN; }
+	return bso_getscore(a, bso_trace_row(a, row), col - a->begs[row + 1]);
+}
+
+/* bsalign.h:3667-3702 and :3704-3852: traceback by re-deriving each step from score differences */
+static void bso_backcal(bso_epi8_t *a, int32_t *rs, bso_cig_t *cg){
+	int qb = rs[2], tb = rs[4]; /* inclusive end cell */
+	int mat = 0, mis = 0, ins = 0, del = 0, aln = 0;
+	int Hcur, Hprev = 0, pend = 0, prior = 0, bw = (int)a->bw, pw = a->pw;
+	int64_t guard = 0, guard_max = 8 * ((int64_t)a->qlen + a->tlen) + 64;
+	rs[2] = qb + 1; rs[4] = tb + 1;
+	Hcur = bso_mtx_score(a, tb, qb);
+	while(1){
+		if(++guard > guard_max){ a->err |= BSO_ERR_LOOP; break; }
+		if((pend & 0xf) == 2 || (pend & 0xf) == 4){ /* inside a deletion run (piece 1: op 2, piece 2: op 4) */
+			int len = pend >> 4, cost;
+			Hprev = bso_mtx_score(a, tb, qb);
+			cost = ((pend & 0xf) == 2) ? a->go1 + len * a->ge1 : a->go2 + len * a->ge2;
+			if(Hprev + cost == Hcur){
+				bso_cig_push(a, cg, 2, len);
+				del += len; aln += len;
+				Hcur = Hprev; pend = 0;
+			} else {
+				pend += 1 << 4; tb--;
+				continue;
+			}
+		}
+		if(qb < 0 || tb < 0) break;
+		if(qb == a->begs[tb]){ /* begs[] is shifted by one: this is the band start of row tb-1 (:3761) */
+			if(qb){
+				Hprev = a->UB[(int64_t)tb * 17]; /* ub[0] of row tb-1 */
+				prior = 0;
+			} else if(a->mode == BSO_MODE_OVERLAP || tb == 0) Hprev = 0;
+			else if(pw < 2) Hprev = a->go1 + a->ge1 * tb;
+			else { int c1 = a->go1 + a->ge1 * tb, c2 = a->go2 + a->ge2 * tb; Hprev = c1 > c2 ? c1 : c2; }
+		} else if(qb - a->begs[tb] <= bw){
+			Hprev = bso_mtx_score(a, tb - 1, qb - 1);
+		} /* else: right of row tb-1's band; the reference reads past the row but never uses the value (:3671) */
+		{
+			int x = qb - a->begs[tb], bt, s, h;
+			int8_t u = 0, e = 0, q = 0;
+			if(x >= 0 && x < bw){
+				bso_row_t r = bso_trace_row(a, tb - 1);
+				u = r.u[x]; e = r.e ? r.e[x] : (int8_t)(a->go1 + a->ge1); q = r.q ? r.q[x] : 0;
+			}
+			s = a->mtx[a->qseq[qb] * 4 + a->tseq[tb]];
+			h = Hcur - Hprev;
+			if(x > bw) bt = 1;
+			else if(x == bw) bt = (h == s) ? 0 : 1;
+			else if(prior){
+				if(h == s) bt = 0;
+				else if(h == u + e) bt = 2;
+				else if(pw == 2 && h == u + q) bt = 4;
+				else bt = 1;
+			} else {
+				if(h == u + e) bt = 2;
+				else if(pw == 2 && h == u + q) bt = 4;
+				else if(h == s) bt = 0;
+				else bt = 1;
+			}
+			prior = 1;
+			if(bt == 0){
+				if(a->qseq[qb] == a->tseq[tb]) mat++; else mis++;
+				qb--; tb--; aln++;
+				bso_cig_push(a, cg, 0, 1);
+				Hcur = Hprev;
+			} else if(bt == 1){
+				if(qb <= 0){
+					bso_cig_push(a, cg, 1, 1);
+					Hcur = Hprev;
+					qb--; ins++; aln++;
+				} else {
+					int sz, t, Hl;
+					for(sz=1;sz+a->begs[tb + 1]<=qb;sz++){
+						t = a->go1 + sz * a->ge1;
+						if(pw == 2){ int t2 = a->go2 + sz * a->ge2; if(t2 > t) t = t2; }
+						Hl = bso_mtx_score(a, tb, qb - sz);
+						if(Hl + t == Hcur){
+							bso_cig_push(a, cg, 1, sz);
+							Hcur = Hl; qb -= sz; ins += sz; aln += sz;
+							break;
+						}
+					}
+					/* no match: the reference re-enters the same state forever; the guard above ends it */
+				}
+			} else {
+				pend = (1 << 4) | bt;
+				tb--;
+				continue;
+			}
+		}
+	}
+	if(a->mode == BSO_MODE_OVERLAP){
+		bso_cig_flush(a, cg);
+	} else {
+		uint32_t op = 0, sz = 0;
+		if(qb >= 0){ op = 1; sz = qb + 1; ins += sz; qb = -1; }
+		else if(tb >= 0){ op = 2; sz = tb + 1; del += sz; tb = -1; }
+		aln += sz;
+		bso_cig_push(a, cg, op, sz);
+		bso_cig_flush(a, cg);
+	}
+	rs[1] = qb + 1; rs[3] = tb + 1;
+	rs[5] = mat; rs[6] = mis; rs[7] = ins; rs[8] = del; rs[9] = aln;
+	if(cg->on){ /* :3850 */
+		uint32_t i, n = cg->n < cg->cap ? cg->n : cg->cap;
+		for(i=0;i<n/2;i++){ uint32_t t = cg->buf[i]; cg->buf[i] = cg->buf[n - 1 - i]; cg->buf[n - 1 - i] = t; }
+	}
+}
+
+/*
+ * bsalign.h:3854-4050.  result = {score,qb,qe,tb,te,mat,mis,ins,del,aln}.  Returns error flags (0 = ok).
+ * dump_* (optional) receive per-row band offsets, anchors and linear u/e/q rows for debugging.
+ */
+int bso_epi8_pairwise_ex(const uint8_t *qseq, uint32_t qlen, const uint8_t *tseq, uint32_t tlen, int mode, uint32_t bandwidth,
+		const int8_t mtx[16], int8_t go1, int8_t ge1, int8_t go2, int8_t ge2,
+		int32_t *rs, uint32_t *cigar, uint32_t cigar_cap, uint32_t *ncigar,
+		int32_t *dump_begs, int32_t *dump_ub, int8_t *dump_u, int8_t *dump_e, int8_t *dump_q){
+	bso_epi8_t A, *a = &A;
+	bso_row_t prev, tmp, cur;
+	bso_cig_t cg;
+	uint32_t i, bw, rbeg, mov;
+	int k, rh, rbx, rby, rbz, score, max_score;
+	int8_t *scratch;
+	int32_t tub[17];
+	memset(a, 0, sizeof(A));
+	memset(rs, 0, 10 * sizeof(int32_t));
+	if(ncigar) *ncigar = 0;
+	if(qlen == 0 || tlen == 0) return 0; /* the reference has no guard here; callers never pass empties */
+	bw = bandwidth ? bandwidth : qlen;
+	bw = (bw + BSO_LANES - 1) / BSO_LANES * BSO_LANES;
+	a->qlen = qlen; a->tlen = tlen; a->bw = bw; a->W = bw / BSO_LANES; a->mode = mode & 3;
+	a->qseq = qseq; a->tseq = tseq; a->mtx = mtx; a->go1 = go1; a->ge1 = ge1; a->go2 = go2; a->ge2 = ge2;
+	a->pw = bso_epi8_piecewise(go1, ge1, go2, ge2, bw);
+	a->smax = -127; a->smin = 127;
+	for(k=0;k<16;k++){ if(mtx[k] > a->smax) a->smax = mtx[k]; if(mtx[k] < a->smin) a->smin = mtx[k]; }
+	a->U = malloc((size_t)bw * (tlen + 1));
+	a->E = a->pw ? malloc((size_t)bw * (tlen + 1)) : NULL;
+	a->Q = a->pw == 2 ? malloc((size_t)bw * (tlen + 1)) : NULL;
+	a->UB = malloc(sizeof(int32_t) * 17 * (size_t)(tlen + 1));
+	a->begs = malloc(sizeof(int32_t) * (size_t)(tlen + 1));
+	scratch = malloc((size_t)bw * 3);
+	tmp.u = scratch; tmp.e = scratch + bw; tmp.q = scratch + 2 * (size_t)bw; tmp.ub = tub;
+	prev = bso_trace_row(a, -1);
+	bso_row_init(a, prev, a->smax, a->smin);
+	a->begs[0] = 0;
+	rs[0] = BSO_SCORE_MIN;
+	rbeg = 0; mov = 0;
+	for(i=0;i<tlen;i++){
+		uint8_t tb = tseq[i];
+		if(mov && rbeg + bw < qlen){
+			int lim = (int)qlen - (int)(rbeg + bw);
+			if(lim < 0) lim = 0;
+			if((uint32_t)lim < mov) mov = (uint32_t)lim;
+			rbeg += mov;
+			rh = bso_getscore(a, prev, (int64_t)mov - 1);
+		} else {
+			mov = 0;
+			if(rbeg) rh = BSO_SCORE_MIN;
+			else if(a->mode == BSO_MODE_OVERLAP || i == 0) rh = 0;
+			else if(a->pw < 2) rh = (int)((uint32_t)go1 + (uint32_t)ge1 * i);
+			else {
+				uint32_t c1 = (uint32_t)go1 + (uint32_t)ge1 * i, c2 = (uint32_t)go2 + (uint32_t)ge2 * i; /* unsigned compare, :3944 */
+				rh = (int)(c1 > c2 ? c1 : c2);
+			}
+		}
+		bso_row_shift(a, prev, tmp, mov, a->smax, a->smin);
+		cur = bso_trace_row(a, i);
+		bso_row_cal(a, rbeg, tb, tmp, cur, rh);
+		rbx = bso_band_mov(a, cur.ub, i, rbeg);
+		if(a->mode == BSO_MODE_GLOBAL){
+			int tq = (int)(tlen / qlen);
+			rbz = 2 * (tq > 1 ? tq : 1);
+			rby = (int)((1.0 * i / tlen) * qlen);
+			if((int64_t)rbeg + rbz * (int64_t)(tlen - i - 1) + (int64_t)bw <= (int64_t)(uint32_t)(qlen + (uint32_t)rbz - 1)){
+				uint32_t rem = tlen - i - 1;
+				mov = 1 + ((qlen - (rbeg + bw)) / (rem > 1 ? rem : 1));
+			} else if((int)rbeg < rby - (int)bw){
+				mov = rbx + 1;
+			} else if((int)rbeg > rby){
+				mov = rbx - 1 > 0 ? rbx - 1 : 0;
+			} else mov = rbx;
+		} else mov = rbx;
+		a->begs[i + 1] = rbeg;
+		if(a->mode != BSO_MODE_GLOBAL && rbeg + bw >= qlen){
+			score = bso_getscore(a, cur, (int64_t)qlen - 1 - rbeg);
+			if(score > rs[0]){ rs[0] = score; rs[2] = qlen - 1; rs[4] = i; }
+		}
+		prev = cur;
+	}
+	if(a->mode == BSO_MODE_GLOBAL){
+		rs[0] = bso_getscore(a, prev, (int64_t)qlen - 1 - rbeg);
+		rs[2] = qlen - 1; rs[4] = tlen - 1;
+	} else {
+		uint32_t rmax = bso_row_max(a, prev, &max_score);
+		if(max_score > rs[0]){ rs[0] = max_score; rs[2] = rbeg + rmax; rs[4] = tlen - 1; }
+	}
+	if(dump_begs){
+		for(i=0;i<tlen;i++){
+			dump_begs[i] = a->begs[i + 1];
+			memcpy(dump_ub + (size_t)i * 17, a->UB + (size_t)(i + 1) * 17, 17 * sizeof(int32_t));
+			memcpy(dump_u + (size_t)i * bw, a->U + (size_t)(i + 1) * bw, bw);
+			if(dump_e){ if(a->E) memcpy(dump_e + (size_t)i * bw, a->E + (size_t)(i + 1) * bw, bw); else memset(dump_e + (size_t)i * bw, 0, bw); }
+			if(dump_q){ if(a->Q) memcpy(dump_q + (size_t)i * bw, a->Q + (size_t)(i + 1) * bw, bw); else memset(dump_q + (size_t)i * bw, 0, bw); }
+		}
+	}
+	cg.buf = cigar; cg.cap = cigar_cap; cg.n = 0; cg.run = 0; cg.on = cigar != NULL;
+	bso_backcal(a, rs, &cg);
+	if(ncigar) *ncigar = cg.n;
+	free(a->U); free(a->E); free(a->Q); free(a->UB); free(a->begs); free(scratch);
+	return a->err;
+}
+
+int bso_epi8_pairwise(const uint8_t *qseq, uint32_t qlen, const uint8_t *tseq, uint32_t tlen, int mode, uint32_t bandwidth,
+		const int8_t mtx[16], int8_t go1, int8_t ge1, int8_t go2, int8_t ge2,
+		int32_t *rs, uint32_t *cigar, uint32_t cigar_cap, uint32_t *ncigar){
+	return bso_epi8_pairwise_ex(qseq, qlen, tseq, tlen, mode, bandwidth, mtx, go1, ge1, go2, ge2, rs, cigar, cigar_cap, ncigar, NULL, NULL, NULL, NULL, NULL);
+}
+
+/* ------------------------------------------------------------------------------------------------
+ * Batch runners (pthread pool over independent pairs) -- same argument layout as oracle/ref_harness.c
+ * ------------------------------------------------------------------------------------------------ */
+int bso_edit_pairwise(const uint8_t *qseq, uint32_t qlen, const uint8_t *tseq, uint32_t tlen, int mode, uint32_t bandwidth,
+		int32_t *rs, uint32_t *cigar, uint32_t cigar_cap, uint32_t *ncigar);
+
+typedef struct {
+	int kind;
+	uint64_t n;
+	const uint8_t *seqs;
+	const uint64_t *qoff, *toff;
+	const uint32_t *qlen, *tlen;
+	int mode;
+	uint32_t bandwidth;
+	const int8_t *matrix;
+	int8_t go1, ge1, go2, ge2;
+	int32_t *results;
+	uint32_t *cigars;
+	const uint64_t *cgoff;
+	uint32_t *ncigar;
+	volatile uint64_t next;
+	int repeat;
+	volatile int err;
+	int32_t *errs;
+} bso_job_t;
+
+static void* bso_worker(void *arg){
+	bso_job_t *job = (bso_job_t*)arg;
+	uint64_t i, j;
+	int r, err = 0;
+	while(1){
+		i = __sync_fetch_and_add(&job->next, 16);
+		if(i >= job->n) break;
+		for(j=i;j<i+16&&j<job->n;j++){
+			uint32_t *cg = (job->cigars && job->cgoff) ? job->cigars + job->cgoff[j] : NULL;
+			uint32_t cap = (job->cigars && job->cgoff) ? (uint32_t)(job->cgoff[j + 1] - job->cgoff[j]) : 0;
+			uint32_t ncg = 0;
+			int perr = 0;
+			for(r=0;r<job->repeat;r++){
+				if(job->kind == 0){
+					perr |= bso_epi8_pairwise(job->seqs + job->qoff[j], job->qlen[j], job->seqs + job->toff[j], job->tlen[j], job->mode, job->bandwidth,
+						job->matrix, job->go1, job->ge1, job->go2, job->ge2, job->results + j * 10, cg, cap, &ncg);
+				} else {
+					perr |= bso_edit_pairwise(job->seqs + job->qoff[j], job->qlen[j], job->seqs + job->toff[j], job->tlen[j], job->mode, job->bandwidth,
+						job->results + j * 10, cg, cap, &ncg);
+				}
+			}
+			err |= perr;
+			if(job->errs) job->errs[j] = perr;
+			if(job->ncigar) job->ncigar[j] = ncg;
+		}
+	}
+	if(err) __sync_fetch_and_or(&job->err, err);
+	return NULL;
+}
+
+static int bso_run(bso_job_t *job, int nthreads){
+	pthread_t *tids;
+	int i;
+	if(nthreads < 1) nthreads = 1;
+	if(job->repeat < 1) job->repeat = 1;
+	job->next = 0; job->err = 0;
+	if(nthreads == 1){ bso_worker(job); return job->err; }
+	tids = malloc(sizeof(pthread_t) * nthreads);
+	for(i=0;i<nthreads;i++) pthread_create(tids + i, NULL, bso_worker, job);
+	for(i=0;i<nthreads;i++) pthread_join(tids[i], NULL);
+	free(tids);
+	return job->err;
+}
+
+int bso_epi8_batch_ex(uint64_t n, const uint8_t *seqs, const uint64_t *qoff, const uint32_t *qlen, const uint64_t *toff, const uint32_t *tlen,
+		int mode, uint32_t bandwidth, const int8_t matrix[16], int8_t go1, int8_t ge1, int8_t go2, int8_t ge2,
+		int32_t *results, uint32_t *cigars, const uint64_t *cgoff, uint32_t *ncigar, int nthreads, int repeat, int32_t *errs){
+	bso_job_t job;
+	memset(&job, 0, sizeof(job));
+	job.kind = 0; job.n = n; job.seqs = seqs; job.qoff = qoff; job.qlen = qlen; job.toff = toff; job.tlen = tlen;
+	job.mode = mode; job.bandwidth = bandwidth; job.matrix = matrix; job.go1 = go1; job.ge1 = ge1; job.go2 = go2; job.ge2 = ge2;
+	job.results = results; job.cigars = cigars; job.cgoff = cgoff; job.ncigar = ncigar; job.repeat = repeat; job.errs = errs;
+	return bso_run(&job, nthreads);
+}
+
+int bso_epi8_batch(uint64_t n, const uint8_t *seqs, const uint64_t *qoff, const uint32_t *qlen, const uint64_t *toff, const uint32_t *tlen,
+		int mode, uint32_t bandwidth, const int8_t matrix[16], int8_t go1, int8_t ge1, int8_t go2, int8_t ge2,
+		int32_t *results, uint32_t *cigars, const uint64_t *cgoff, uint32_t *ncigar, int nthreads, int repeat){
+	return bso_epi8_batch_ex(n, seqs, qoff, qlen, toff, tlen, mode, bandwidth, matrix, go1, ge1, go2, ge2, results, cigars, cgoff, ncigar, nthreads, repeat, NULL);
+}
+
+int bso_edit_batch_ex(uint64_t n, const uint8_t *seqs, const uint64_t *qoff, const uint32_t *qlen, const uint64_t *toff, const uint32_t *tlen,
+		int mode, uint32_t bandwidth, int32_t *results, uint32_t *cigars, const uint64_t *cgoff, uint32_t *ncigar, int nthreads, int repeat, int32_t *errs);
+
+int bso_edit_batch(uint64_t n, const uint8_t *seqs, const uint64_t *qoff, const uint32_t *qlen, const uint64_t *toff, const uint32_t *tlen,
+		int mode, uint32_t bandwidth, int32_t *results, uint32_t *cigars, const uint64_t *cgoff, uint32_t *ncigar, int nthreads, int repeat){
+	return bso_edit_batch_ex(n, seqs, qoff, qlen, toff, tlen, mode, bandwidth, results, cigars, cgoff, ncigar, nthreads, repeat, NULL);
+}
+
+int bso_edit_batch_ex(uint64_t n, const uint8_t *seqs, const uint64_t *qoff, const uint32_t *qlen, const uint64_t *toff, const uint32_t *tlen,
+		int mode, uint32_t bandwidth, int32_t *results, uint32_t *cigars, const uint64_t *cgoff, uint32_t *ncigar, int nthreads, int repeat, int32_t *errs){
+	bso_job_t job;
+	memset(&job, 0, sizeof(job));
+	job.kind = 1; job.errs = errs; job.n = n; job.seqs = seqs; job.qoff = qoff; job.qlen = qlen; job.toff = toff; job.tlen = tlen;
+	job.mode = mode; job.bandwidth = bandwidth;
+	job.results = results; job.cigars = cigars; job.cgoff = cgoff; job.ncigar = ncigar; job.repeat = repeat;
+	return bso_run(&job, nthreads);
+}
+
+
+/* ------------------------------------------------------------------------------------------------
+ * Edit-distance kernel (bsalign.h:612-1206), restated per cell.
+ *
+ * The reference keeps u(x,y) = H(x,y) - H(x-1,y) in two bit-planes (minus, plus) of 64-bit words,
+ * striped over 64 lanes, and resolves the left-to-right dependency with a re-pass loop that stops at the
+ * exact fix-point (bsalign.h:784-809).  That fix-point is the plain sequential recurrence
+ *     h  = (q[x] != t[y]) && u(x,y-1) != -1 && v(x-1,y) != -1      (h = H(x,y) - H(x-1,y-1), 0 or 1)
+ *     u' = h - v(x-1,y),   v' = h - u(x,y-1)
+ * with v = +1 entering the band's first cell (0 in OVERLAP mode), which is what is evaluated here.
+ * ------------------------------------------------------------------------------------------------ */
+typedef struct {
+	uint32_t qlen, tlen, bw, W;
+	int mode;
+	const uint8_t *qseq, *tseq;
+	int8_t *U;       /* (tlen+1) rows of bw cells; row 0 is the init row (all +1), row y+1 is target row y */
+	uint32_t *begs;  /* tlen+1; begs[y+1] = band start of row y */
+	int err;
+} bso_edit_t;
+
+static inline int bso_edit_u(bso_edit_t *a, int64_t trow, int64_t pos){
+	if(pos < 0 || pos >= (int64_t)a->bw || trow < 0 || trow > (int64_t)a->tlen){ a->err |= BSO_ERR_RANGE; return 0; }
+	return a->U[trow * (int64_t)a->bw + pos];
+}
+
+/* bsalign.h:813-963: arg-min of the last row with the SSE code's block/chunk tie-break order (EXTEND only) */
+static int bso_edit_rowmin(bso_edit_t *a, int sbeg0, const int8_t *u, uint32_t *whence){
+	uint32_t W = a->W, blk, l, ib, ie, i, pmin = 0;
+	int sbeg = sbeg0, smin = sbeg0;
+	for(blk=0;blk<4;blk++){
+		int tot[16], mm[16], cand[16], sc;
+		uint32_t pp[16], st;
+		for(l=0;l<16;l++){
+			const int8_t *lane = u + (size_t)(blk * 16 + l) * W;
+			int hh = 0;
+			mm[l] = 0; pp[l] = 0;
+			for(ib=0;ib<W;ib=ie){
+				int h = 0, m = 0, d;
+				uint32_t pz = 0;
+				ie = ib + 124 < W ? ib + 124 : W;
+				for(i=ib;i<ie;i++){
+					h += lane[i];
+					if(m > h){ m = h; pz = i - ib; }
+				}
+				d = hh + m;
+				if(mm[l] > d){ mm[l] = d; pp[l] = pz + ib; }
+				hh += h;
+			}
+			tot[l] = hh;
+		}
+		for(l=0;l<16;l++){ cand[l] = sbeg + mm[l]; sbeg += tot[l]; }
+		sc = cand[0]; st = 0;
+		for(l=1;l<16;l++) if(sc > cand[l]){ sc = cand[l]; st = l; }
+		if(sc >= smin) continue;
+		smin = sc;
+		pmin = (blk * 16 + st) * W + pp[st];
+	}
+	if(whence) *whence = pmin;
+	return smin;
+}
+
+/* bsalign.h:1046-1206 (driver), :653-721 (row init / shift), :766-810 (row), :965-1044 (backtrace) */
+int bso_edit_pairwise(const uint8_t *qseq, uint32_t qlen, const uint8_t *tseq, uint32_t tlen, int mode, uint32_t bandwidth,
+		int32_t *rs, uint32_t *cigar, uint32_t cigar_cap, uint32_t *ncigar){
+	bso_edit_t A, *a = &A;
+	bso_cig_t cg;
+	uint32_t i, p, bw, q64, rbeg = 0, prev_beg = 0;
+	int type = mode & 3, sbeg = 0, smin = 0x7FFFFFFF, rx, ry, srow;
+	int8_t *prev, *cur, *tmp;
+	memset(rs, 0, 10 * sizeof(int32_t));
+	if(ncigar) *ncigar = 0;
+	if(qlen == 0 || tlen == 0) return 0; /* :1051-1054 */
+	q64 = (qlen + 63) / 64 * 64;
+	if(type == BSO_MODE_OVERLAP || type == BSO_MODE_EXTEND) bw = q64; /* :1055-1067 */
+	else {
+		bw = (bandwidth + 63) / 64 * 64;
+		if(bw == 0 || bw > qlen) bw = q64;
+		if(bw < qlen && bw < ((qlen + tlen - 1) / tlen) + 1) bw = ((qlen + tlen - 1) / tlen + 1 + 63) / 64 * 64;
+	}
+	if(bw > q64) return BSO_ERR_RANGE; /* qlen % 64 == 0 with a tiny target: the reference's band start underflows (:1114) */
+	memset(a, 0, sizeof(A));
+	a->qlen = qlen; a->tlen = tlen; a->bw = bw; a->W = bw / 64; a->mode = type; a->qseq = qseq; a->tseq = tseq;
+	a->U = malloc((size_t)bw * (tlen + 1));
+	a->begs = malloc(sizeof(uint32_t) * (size_t)(tlen + 1));
+	tmp = malloc(bw);
+	memset(a->U, 1, bw); /* init row: u = +1 everywhere (:653-656) */
+	a->begs[0] = 0;
+	rx = qlen - 1; ry = tlen - 1;
+	for(i=0;i<tlen;i++){
+		uint32_t movx;
+		int v;
+		prev = a->U + (size_t)i * bw;
+		cur = a->U + (size_t)(i + 1) * bw;
+		if(type == BSO_MODE_OVERLAP || type == BSO_MODE_EXTEND) rbeg = 0;
+		else { /* fixed diagonal band (:1112-1114) */
+			rbeg = (uint32_t)(((uint64_t)i * qlen) / tlen);
+			rbeg = (rbeg < bw / 2) ? 0 : rbeg - bw / 2;
+			if(rbeg + bw > q64) rbeg = q64 - bw;
+		}
+		a->begs[i + 1] = rbeg;
+		movx = rbeg - prev_beg;
+		/* shift (:658-721): sbeg follows H(rbeg-1, y) */
+		if(type == BSO_MODE_OVERLAP){
+			sbeg = 0;
+			memcpy(tmp, prev, bw);
+		} else {
+			uint32_t mv = movx < bw ? movx : bw;
+			/* bsalign.h:704-713 offsets its destination pointers twice when the shift spans whole 64-lane
+			 * cycles plus a remainder; the reference then computes on stale scratch words.  Out of domain. */
+			if(movx < bw && movx >= a->W && movx % a->W) a->err |= BSO_ERR_REFBUG;
+			for(p=0;p<mv;p++) sbeg += prev[p];
+			sbeg++;
+			for(p=0;p<bw;p++) tmp[p] = (p + movx < bw) ? prev[p + movx] : 1;
+		}
+		/* the row */
+		v = (type == BSO_MODE_OVERLAP) ? 0 : 1;
+		for(p=0;p<bw;p++){
+			uint32_t x = rbeg + p;
+			int match = (x < qlen) && (qseq[x] == tseq[i]);
+			int u = tmp[p];
+			int h = (!match && u != -1 && v != -1) ? 1 : 0;
+			cur[p] = (int8_t)(h - v);
+			v = h - u;
+		}
+		if(type == BSO_MODE_OVERLAP || type == BSO_MODE_EXTEND){ /* :1124-1139: H(qlen-1, i) */
+			srow = sbeg;
+			for(p=0;p<bw&&rbeg+p<qlen;p++) srow += cur[p];
+			if(srow < smin){ smin = srow; rx = qlen - 1; ry = i; }
+		}
+		prev_beg = rbeg;
+	}
+	cur = a->U + (size_t)tlen * bw;
+	if(type == BSO_MODE_EXTEND){
+		uint32_t k = 0;
+		srow = bso_edit_rowmin(a, sbeg, cur, &k);
+		if(srow < smin){ smin = srow; rx = k; ry = tlen - 1; }
+	}
+	/* backtrace (:965-1044) */
+	{
+		int x = rx, y = ry, mat = 0, mis = 0, ins = 0, del = 0;
+		uint32_t op;
+		int64_t guard = 0;
+		cg.buf = cigar; cg.cap = cigar_cap; cg.n = 0; cg.run = 0; cg.on = cigar != NULL;
+		rs[2] = x + 1; rs[4] = y + 1;
+		while(x >= 0 && y >= 0){
+			if(++guard > 4 * ((int64_t)qlen + tlen) + 64){ a->err |= BSO_ERR_LOOP; break; }
+			if(qseq[x] == tseq[y]){ mat++; op = 0; x--; y--; }
+			else if(bso_edit_u(a, y + 1, (int64_t)x - a->begs[y + 1]) == 1){ ins++; op = 1; x--; }
+			else if(bso_edit_u(a, y, (int64_t)x - a->begs[y]) == -1){ del++; op = 2; y--; }
+			else { mis++; op = 0; x--; y--; }
+			/* :1009-1014 is the same run-length merge as bso_cig_push with length 1 */
+			if(op == (cg.run & 0xf)) cg.run += 0x10;
+			else { bso_cig_flush(NULL, &cg); cg.run = 0x10 | op; }
+		}
+		rs[1] = x + 1; rs[3] = y + 1;
+		if(rs[1]){
+			op = 1;
+			if(op == (cg.run & 0xf)) cg.run += 0x10 * (uint32_t)rs[1];
+			else { bso_cig_flush(NULL, &cg); cg.run = (0x10 * (uint32_t)rs[1]) | op; }
+			ins += rs[1]; rs[1] = 0;
+		}
+		if((type == BSO_MODE_GLOBAL || type == BSO_MODE_EXTEND) && rs[3]){
+			op = 2;
+			if(op == (cg.run & 0xf)) cg.run += 0x10 * (uint32_t)rs[3];
+			else { bso_cig_flush(NULL, &cg); cg.run = (0x10 * (uint32_t)rs[3]) | op; }
+			del += rs[3]; rs[3] = 0;
+		}
+		rs[5] = mat; rs[6] = mis; rs[7] = ins; rs[8] = del; rs[9] = mat + mis + ins + del;
+		bso_cig_flush(NULL, &cg);
+		if(cg.on){
+			uint32_t n = cg.n < cg.cap ? cg.n : cg.cap, k;
+			if(cg.n > cg.cap) a->err |= BSO_ERR_CIGCAP;
+			for(k=0;k<n/2;k++){ uint32_t t = cg.buf[k]; cg.buf[k] = cg.buf[n - 1 - k]; cg.buf[n - 1 - k] = t; }
+		}
+		if(ncigar) *ncigar = cg.n;
+	}
+	/* score (:1189-1203) */
+	if(type == BSO_MODE_OVERLAP) rs[0] = smin + rs[4] - rs[3];
+	else if(type == BSO_MODE_EXTEND) rs[0] = smin;
+	else {
+		int sc = sbeg;
+		for(p=0;p<bw&&rbeg+p<qlen;p++) sc += cur[p];
+		rs[0] = sc;
+	}
+	free(a->U); free(a->begs); free(tmp);
+	return a->err;
+}
