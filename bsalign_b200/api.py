@@ -1,0 +1,252 @@
+"""Host-side mirror of the reference's pairwise API on top of libbsalign_b200.so (C ABI: include/bsalign_b200.h).
+
+Names, argument meaning and result layout follow the reference (ruanjue/bsalign):
+  banded_striped_epi8_seqalign_pairwise   bsalign.h:3854 / :399
+  striped_seqedit_pairwise                bsalign.h:1046 / :232
+  banded_striped_epi8_seqalign_set_score_matrix  bsalign.h:323
+  seqalign_cigar2alnstr                   bsalign.h:531
+plus the batch forms a GPU needs.  There is NO CPU fallback: a missing library or device raises.
+"""
+import ctypes
+import os
+
+import numpy as np
+
+from .synth import PairBatch
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libbsalign_b200.so")
+
+SEQALIGN_MODE_GLOBAL = 0   # bsalign.h:30
+SEQALIGN_MODE_OVERLAP = 1  # bsalign.h:31
+SEQALIGN_MODE_EXTEND = 2   # bsalign.h:32
+
+ST_RANGE, ST_LOOP, ST_CIGCAP, ST_REFBUG, ST_EMPTY = 1, 2, 4, 8, 16
+
+RESULT_FIELDS = ("score", "qb", "qe", "tb", "te", "mat", "mis", "ins", "del", "aln")  # seqalign_result_t, bsalign.h:213-218
+
+_P = ctypes.c_void_p
+_I8 = ctypes.c_int8
+
+
+class Timing(ctypes.Structure):
+    _fields_ = [("h2d_ms", ctypes.c_float), ("forward_ms", ctypes.c_float), ("traceback_ms", ctypes.c_float),
+                ("d2h_ms", ctypes.c_float), ("total_ms", ctypes.c_float),
+                ("forward_launches", ctypes.c_uint32), ("traceback_launches", ctypes.c_uint32),
+                ("other_launches", ctypes.c_uint32), ("waves", ctypes.c_uint32),
+                ("cells", ctypes.c_uint64), ("trace_bytes", ctypes.c_uint64),
+                ("h2d_bytes", ctypes.c_uint64), ("d2h_bytes", ctypes.c_uint64)]
+
+    def as_dict(self):
+        return {k: getattr(self, k) for k, _ in self._fields_}
+
+
+_lib = None
+
+
+def lib():
+    """Load the CUDA library; fail loudly when it has not been built (python __graft_entry__.py build)."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise RuntimeError("bsalign_b200: %s is missing - build it with `python -c 'import __graft_entry__ as g; g.build()'`; "
+                               "there is no CPU fallback" % LIB_PATH)
+        L = ctypes.CDLL(LIB_PATH)
+        L.bsb200_create.restype = _P
+        L.bsb200_create.argtypes = [ctypes.c_int, ctypes.c_uint64]
+        L.bsb200_destroy.argtypes = [_P]
+        L.bsb200_last_error.restype = ctypes.c_char_p
+        L.bsb200_last_error.argtypes = [_P]
+        L.bsb200_version.restype = ctypes.c_char_p
+        L.bsb200_get_timing.argtypes = [_P, ctypes.POINTER(Timing)]
+        L.bsb200_batch_upload.restype = _P
+        L.bsb200_batch_upload.argtypes = [_P, ctypes.c_int, ctypes.c_uint64, _P, _P, _P, _P, _P, ctypes.c_int, ctypes.c_uint32, _P,
+                                          _I8, _I8, _I8, _I8, ctypes.c_int]
+        L.bsb200_batch_run.argtypes = [_P, _P]
+        L.bsb200_batch_sync.argtypes = [_P]
+        L.bsb200_batch_fetch.argtypes = [_P, _P, _P, _P, _P, _P, _P]
+        L.bsb200_batch_free.argtypes = [_P, _P]
+        L.bsb200_epi8_pairwise_batch.argtypes = [_P, ctypes.c_uint64, _P, _P, _P, _P, _P, ctypes.c_int, ctypes.c_uint32, _P,
+                                                 _I8, _I8, _I8, _I8, _P, _P, _P, _P, _P]
+        L.bsb200_edit_pairwise_batch.argtypes = [_P, ctypes.c_uint64, _P, _P, _P, _P, _P, ctypes.c_int, ctypes.c_uint32,
+                                                 _P, _P, _P, _P, _P]
+        L.bsb200_epi8_bandwidth.restype = ctypes.c_uint32
+        L.bsb200_epi8_bandwidth.argtypes = [ctypes.c_uint32, ctypes.c_uint32]
+        L.bsb200_edit_bandwidth.restype = ctypes.c_uint32
+        L.bsb200_edit_bandwidth.argtypes = [ctypes.c_uint32, ctypes.c_uint32, ctypes.c_int, ctypes.c_uint32]
+        _lib = L
+    return _lib
+
+
+def _ptr(a):
+    if a is None:
+        return None
+    if isinstance(a, int):
+        return ctypes.c_void_p(a)
+    return a.ctypes.data_as(_P)
+
+
+def cigar_offsets(batch):
+    """Per-pair capacity qlen+tlen+2 words (an alignment never has more runs than columns)."""
+    cap = batch.qlen.astype(np.uint64) + batch.tlen.astype(np.uint64) + np.uint64(2)
+    off = np.zeros(batch.n + 1, dtype=np.uint64)
+    np.cumsum(cap, out=off[1:])
+    return off
+
+
+class Context:
+    """One CUDA device + stream (bsb200_ctx)."""
+
+    def __init__(self, device=0, trace_budget_bytes=0):
+        self._lib = lib()
+        self._h = self._lib.bsb200_create(int(device), int(trace_budget_bytes))
+        if not self._h:
+            raise RuntimeError("bsalign_b200: cannot create a context on CUDA device %d (no GPU?); there is no CPU fallback" % device)
+        self.device = device
+
+    def close(self):
+        if self._h:
+            self._lib.bsb200_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _check(self, rc, what):
+        if rc != 0:
+            raise RuntimeError("%s failed: %s" % (what, self._lib.bsb200_last_error(self._h).decode()))
+
+    def timing(self):
+        t = Timing()
+        self._lib.bsb200_get_timing(self._h, ctypes.byref(t))
+        return t.as_dict()
+
+    # ---- one-shot batch calls (host buffers in, host buffers out) ---------------------------------
+    def epi8_batch(self, batch, mode, bandwidth, matrix, gapo1, gape1, gapo2=0, gape2=0, want_cigar=True, out=None):
+        n = batch.n
+        m = np.ascontiguousarray(matrix, dtype=np.int8)
+        res, cg, off, ncg, st = out if out is not None else _alloc_out(batch, want_cigar)
+        rc = self._lib.bsb200_epi8_pairwise_batch(self._h, n, _ptr(batch.seqs), _ptr(batch.qoff), _ptr(batch.qlen), _ptr(batch.toff), _ptr(batch.tlen),
+                                                  int(mode), int(bandwidth), _ptr(m), gapo1, gape1, gapo2, gape2,
+                                                  _ptr(res), _ptr(cg), _ptr(off), _ptr(ncg), _ptr(st))
+        self._check(rc, "bsb200_epi8_pairwise_batch")
+        return BatchResult(res, cg, off, ncg, st)
+
+    def edit_batch(self, batch, mode, bandwidth, want_cigar=True, out=None):
+        n = batch.n
+        res, cg, off, ncg, st = out if out is not None else _alloc_out(batch, want_cigar)
+        rc = self._lib.bsb200_edit_pairwise_batch(self._h, n, _ptr(batch.seqs), _ptr(batch.qoff), _ptr(batch.qlen), _ptr(batch.toff), _ptr(batch.tlen),
+                                                  int(mode), int(bandwidth), _ptr(res), _ptr(cg), _ptr(off), _ptr(ncg), _ptr(st))
+        self._check(rc, "bsb200_edit_pairwise_batch")
+        return BatchResult(res, cg, off, ncg, st)
+
+    # ---- staged form: inputs stay resident in HBM between runs -------------------------------------
+    def upload(self, kind, batch, mode, bandwidth, matrix=None, gaps=(0, 0, 0, 0), want_cigar=True):
+        m = np.ascontiguousarray(matrix if matrix is not None else np.zeros(16), dtype=np.int8)
+        h = self._lib.bsb200_batch_upload(self._h, 0 if kind == "epi8" else 1, batch.n, _ptr(batch.seqs), _ptr(batch.qoff), _ptr(batch.qlen),
+                                          _ptr(batch.toff), _ptr(batch.tlen), int(mode), int(bandwidth), _ptr(m),
+                                          gaps[0], gaps[1], gaps[2], gaps[3], 1 if want_cigar else 0)
+        if not h:
+            raise RuntimeError("bsb200_batch_upload failed: %s" % self._lib.bsb200_last_error(self._h).decode())
+        return ResidentBatch(self, h, batch, want_cigar)
+
+
+def _alloc_out(batch, want_cigar):
+    n = batch.n
+    res = np.zeros((n, 10), dtype=np.int32)
+    off = cigar_offsets(batch) if want_cigar else None
+    cg = np.zeros(int(off[-1]) if want_cigar else 0, dtype=np.uint32) if want_cigar else None
+    ncg = np.zeros(n, dtype=np.uint32)
+    st = np.zeros(n, dtype=np.int32)
+    return res, cg, off, ncg, st
+
+
+class BatchResult:
+    def __init__(self, results, cigar_arena, cigar_off, ncigar, status):
+        self.results = results      # (n, 10) int32, columns = RESULT_FIELDS
+        self.cigar_arena = cigar_arena
+        self.cigar_off = cigar_off
+        self.ncigar = ncigar
+        self.status = status
+
+    def cigar(self, i):
+        o = int(self.cigar_off[i])
+        return self.cigar_arena[o:o + int(self.ncigar[i])]
+
+    def cigars(self):
+        return [self.cigar(i) for i in range(len(self.ncigar))]
+
+
+class ResidentBatch:
+    def __init__(self, ctx, handle, batch, want_cigar):
+        self.ctx, self._h, self.batch, self.want_cigar = ctx, handle, batch, want_cigar
+
+    def run(self):
+        self.ctx._check(self.ctx._lib.bsb200_batch_run(self.ctx._h, self._h), "bsb200_batch_run")
+
+    def fetch(self, out=None):
+        res, cg, off, ncg, st = out if out is not None else _alloc_out(self.batch, self.want_cigar)
+        rc = self.ctx._lib.bsb200_batch_fetch(self.ctx._h, self._h, _ptr(res), _ptr(cg), _ptr(off), _ptr(ncg), _ptr(st))
+        self.ctx._check(rc, "bsb200_batch_fetch")
+        return BatchResult(res, cg, off, ncg, st)
+
+    def free(self):
+        if self._h:
+            self.ctx._lib.bsb200_batch_free(self.ctx._h, self._h)
+            self._h = None
+
+
+# ---- reference-named single-pair functions --------------------------------------------------------
+_default_ctx = None
+
+
+def default_context():
+    global _default_ctx
+    if _default_ctx is None:
+        _default_ctx = Context(0)
+    return _default_ctx
+
+
+def banded_striped_epi8_seqalign_set_score_matrix(mat, mis):
+    """bsalign.h:323: matrix[i] = mis if the two 2-bit codes of i differ else mat."""
+    return np.array([mis if ((i ^ (i >> 2)) & 3) else mat for i in range(16)], dtype=np.int8)
+
+
+def _single(batchfn, qseq, tseq, *args):
+    b = PairBatch.from_lists([(qseq, tseq)])
+    r = batchfn(b, *args)
+    rs = dict(zip(RESULT_FIELDS, (int(v) for v in r.results[0])))
+    return rs, r.cigar(0).copy(), int(r.status[0])
+
+
+def banded_striped_epi8_seqalign_pairwise(qseq, tseq, mode, bandwidth, matrix, gapo1, gape1, gapo2, gape2, ctx=None):
+    """Same arguments as bsalign.h:399 without mempool/verbose.  Returns (result dict, cigar words, status)."""
+    ctx = ctx or default_context()
+    return _single(ctx.epi8_batch, qseq, tseq, mode, bandwidth, matrix, gapo1, gape1, gapo2, gape2)
+
+
+def striped_seqedit_pairwise(qseq, tseq, mode, bandwidth, ctx=None):
+    """Same arguments as bsalign.h:232 without mempool/verbose."""
+    ctx = ctx or default_context()
+    return _single(ctx.edit_batch, qseq, tseq, mode, bandwidth)
+
+
+def seqalign_cigar2alnstr(qseq, tseq, rs, cigars):
+    """bsalign.h:531-582: three strings (query row, target row, match row) of the alignment."""
+    x, y = rs["qb"], rs["tb"]
+    a, b, c = [], [], []
+    for w in cigars:
+        op, ln = int(w) & 0xF, int(w) >> 4
+        for _ in range(ln):
+            if op == 0:
+                qa, ta = "ACGTN"[qseq[x]], "ACGTN"[tseq[y]]
+                a.append(qa); b.append(ta); c.append("|" if qseq[x] == tseq[y] else "*")
+                x += 1; y += 1
+            elif op == 1:
+                a.append("ACGTN"[qseq[x]]); b.append("-"); c.append("-"); x += 1
+            elif op == 2:
+                a.append("-"); b.append("ACGTN"[tseq[y]]); c.append("-"); y += 1
+    return "".join(a), "".join(b), "".join(c)

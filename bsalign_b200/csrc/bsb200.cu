@@ -1,0 +1,540 @@
+// bsb200.cu -- host side of libbsalign_b200.so: the C ABI declared in include/bsalign_b200.h.
+//
+// Plans a batch (per-pair band width, heaviest-first work order, waves that fit the HBM trace budget),
+// moves packed inputs to the device, launches the sm_100a kernels of epi8_kernels.cuh / edit_kernels.cuh
+// on one stream and brings results + run-length CIGARs back.  No CPU fallback exists: every entry point
+// fails with an error string when CUDA is unavailable.
+#include "../../include/bsalign_b200.h"
+#include "epi8_kernels.cuh"
+#include "edit_kernels.cuh"
+
+#include <algorithm>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <numeric>
+#include <string>
+#include <vector>
+
+using namespace bsb200;
+
+#define BSB_VERSION "bsalign_b200 0.1 (sm_100a)"
+
+struct DevBuf {
+	void *p = nullptr; size_t cap = 0;
+	cudaError_t reserve(size_t n){
+		if(n <= cap) return cudaSuccess;
+		if(p) cudaFree(p);
+		p = nullptr; cap = 0;
+		size_t want = n + n / 8 + 256;
+		cudaError_t e = cudaMalloc(&p, want);
+		if(e == cudaSuccess) cap = want;
+		return e;
+	}
+	void release(){ if(p) cudaFree(p); p = nullptr; cap = 0; }
+	template<class T> T *as() const { return (T*)p; }
+};
+
+struct HostBuf { // pinned staging
+	void *p = nullptr; size_t cap = 0;
+	cudaError_t reserve(size_t n){
+		if(n <= cap) return cudaSuccess;
+		if(p) cudaFreeHost(p);
+		p = nullptr; cap = 0;
+		size_t want = n + n / 8 + 256;
+		cudaError_t e = cudaMallocHost(&p, want);
+		if(e == cudaSuccess) cap = want;
+		return e;
+	}
+	void release(){ if(p) cudaFreeHost(p); p = nullptr; cap = 0; }
+	template<class T> T *as() const { return (T*)p; }
+};
+
+struct bsb200_ctx {
+	int device = 0;
+	int num_sms = 0;
+	size_t smem_optin = 0;
+	cudaStream_t stream = nullptr;
+	cudaEvent_t ev[8] = {};
+	uint64_t trace_budget = 0;
+	std::string err;
+	bsb200_timing_t timing = {};
+	DevBuf trace;       // shared by all batches of this context (one batch runs at a time)
+	DevBuf counter;
+};
+
+struct Wave { uint32_t beg, end; uint64_t trace_bytes; };
+
+struct bsb200_batch {
+	int kind = 0;
+	uint64_t n = 0;
+	int mode = 0; uint32_t bandwidth = 0;
+	int8_t mtx[16] = {}; int8_t go1 = 0, ge1 = 0, go2 = 0, ge2 = 0;
+	int pw = 0; int want_cigar = 1;
+	uint32_t max_bw = 16, max_q64 = 64;
+	std::vector<uint8_t> empty;
+	uint64_t cells = 0, trace_bytes = 0, cig_words = 0;
+	std::vector<Wave> waves;
+	std::vector<uint32_t> order;
+	std::vector<uint64_t> trace_off, cig_off;
+	DevBuf d_seqs, d_qoff, d_toff, d_qlen, d_tlen, d_order, d_trace_off, d_results, d_status, d_ncigar, d_cig_raw, d_cig_off, d_cig_dense, d_dense_off, d_dense_total, d_block_rows;
+	HostBuf h_results, h_status, h_ncigar, h_dense_off, h_dense, h_total;
+	size_t seq_bytes = 0;
+	bool ran = false;
+};
+
+static int fail(bsb200_ctx *ctx, const char *what, cudaError_t e){
+	char buf[512];
+	snprintf(buf, sizeof(buf), "%s: %s", what, e == cudaSuccess ? "invalid argument" : cudaGetErrorString(e));
+	if(ctx) ctx->err = buf;
+	return -1;
+}
+#define CK(call) do { cudaError_t _e = (call); if(_e != cudaSuccess) return fail(ctx, #call, _e); } while(0)
+#define CKP(call) do { cudaError_t _e = (call); if(_e != cudaSuccess){ fail(ctx, #call, _e); return nullptr; } } while(0)
+
+extern "C" const char *bsb200_version(void){ return BSB_VERSION; }
+
+extern "C" int bsb200_device_count(void){
+	int n = 0;
+	if(cudaGetDeviceCount(&n) != cudaSuccess) return 0;
+	return n;
+}
+
+extern "C" bsb200_ctx *bsb200_create(int device, uint64_t trace_budget_bytes){
+	int n = 0;
+	if(cudaGetDeviceCount(&n) != cudaSuccess || n == 0 || device < 0 || device >= n){
+		fprintf(stderr, "bsalign_b200: no usable CUDA device %d (count %d); this library has no CPU fallback\n", device, n);
+		return nullptr;
+	}
+	bsb200_ctx *ctx = new bsb200_ctx();
+	ctx->device = device;
+	if(cudaSetDevice(device) != cudaSuccess){ delete ctx; return nullptr; }
+	cudaDeviceProp prop;
+	cudaGetDeviceProperties(&prop, device);
+	ctx->num_sms = prop.multiProcessorCount;
+	ctx->smem_optin = prop.sharedMemPerBlockOptin;
+	cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking);
+	for(auto &e : ctx->ev) cudaEventCreate(&e);
+	ctx->trace_budget = trace_budget_bytes;
+	return ctx;
+}
+
+extern "C" void bsb200_destroy(bsb200_ctx *ctx){
+	if(!ctx) return;
+	cudaSetDevice(ctx->device);
+	cudaStreamSynchronize(ctx->stream);
+	ctx->trace.release(); ctx->counter.release();
+	for(auto &e : ctx->ev) cudaEventDestroy(e);
+	cudaStreamDestroy(ctx->stream);
+	delete ctx;
+}
+
+extern "C" const char *bsb200_last_error(bsb200_ctx *ctx){ return ctx ? ctx->err.c_str() : "null context"; }
+extern "C" void bsb200_get_timing(bsb200_ctx *ctx, bsb200_timing_t *out){ if(ctx && out) *out = ctx->timing; }
+
+extern "C" uint32_t bsb200_epi8_bandwidth(uint32_t qlen, uint32_t bandwidth){
+	uint32_t bw = bandwidth ? bandwidth : qlen; // bsalign.h:3861-3862
+	return (bw + 15) / 16 * 16;
+}
+
+extern "C" uint32_t bsb200_edit_bandwidth(uint32_t qlen, uint32_t tlen, int mode, uint32_t bandwidth){
+	return edit_bandwidth(qlen, tlen, mode, bandwidth);
+}
+
+void bsb200_batch_free(bsb200_ctx *ctx, bsb200_batch *b);
+
+extern "C" bsb200_batch *bsb200_batch_upload(bsb200_ctx *ctx, int kind, uint64_t n, const uint8_t *seqs,
+		const uint64_t *qoff, const uint32_t *qlen, const uint64_t *toff, const uint32_t *tlen,
+		int mode, uint32_t bandwidth, const int8_t matrix[16], int8_t go1, int8_t ge1, int8_t go2, int8_t ge2, int want_cigar){
+	if(!ctx) return nullptr;
+	ctx->err.clear();
+	if(n >= 0xFFFFFFF0ull || (n && (!seqs || !qoff || !qlen || !toff || !tlen)) || (kind == 0 && !matrix) || kind < 0 || kind > 1){
+		fail(ctx, "bsb200_batch_upload", cudaSuccess); return nullptr;
+	}
+	cudaSetDevice(ctx->device);
+	bsb200_batch *b = new bsb200_batch();
+	b->kind = kind; b->n = n; b->mode = mode & 3; b->bandwidth = bandwidth; b->want_cigar = want_cigar;
+	if(kind == 0){
+		memcpy(b->mtx, matrix, 16); b->go1 = go1; b->ge1 = ge1; b->go2 = go2; b->ge2 = ge2;
+		b->pw = epi8_piecewise(go1, ge1, go2, ge2, 16);
+	}
+	// ---- plan: per-pair band, trace footprint, heaviest-first order, waves ---------------------------
+	std::vector<uint64_t> work(n), tbytes(n);
+	size_t seq_end = 0;
+	b->max_bw = kind == 0 ? 16 : 64;
+	b->empty.assign(n, 0);
+	b->order.clear(); b->order.reserve(n);
+	for(uint64_t i=0;i<n;i++){
+		uint32_t bw;
+		seq_end = std::max<size_t>(seq_end, std::max<size_t>(qoff[i] + qlen[i], toff[i] + tlen[i]));
+		if(qlen[i] == 0 || tlen[i] == 0){ b->empty[i] = 1; work[i] = 0; tbytes[i] = 0; continue; } // bsalign.h:1051-1054
+		if(kind == 0){
+			bw = bsb200_epi8_bandwidth(qlen[i], bandwidth);
+			tbytes[i] = ((uint64_t)bw * (b->pw + 1) + kMetaInts * 4) * ((uint64_t)tlen[i] + 1);
+			tbytes[i] = (tbytes[i] + 15) / 16 * 16;
+			b->cells += (uint64_t)std::min<uint32_t>(bw, (qlen[i] + 15) / 16 * 16) * tlen[i];
+			b->trace_bytes += ((uint64_t)bw * (b->pw + 1) + 84) * tlen[i];
+		} else {
+			bw = edit_bandwidth(qlen[i], tlen[i], mode, bandwidth);
+			b->cells += (uint64_t)bw * tlen[i];
+			b->trace_bytes += ((uint64_t)bw / 4 + 4) * tlen[i];
+			b->max_q64 = std::max<uint32_t>(b->max_q64, (qlen[i] + 63) / 64 * 64);
+		}
+		work[i] = (uint64_t)bw * tlen[i];
+		b->max_bw = std::max(b->max_bw, bw);
+		b->order.push_back((uint32_t)i);
+	}
+	b->seq_bytes = seq_end;
+	const uint32_t nact = (uint32_t)b->order.size();
+	if(kind == 0) std::stable_sort(b->order.begin(), b->order.end(), [&](uint32_t x, uint32_t y){ return work[x] > work[y]; });
+	else std::stable_sort(b->order.begin(), b->order.end(), [&](uint32_t x, uint32_t y){ return tlen[x] > tlen[y]; });
+	uint64_t budget = ctx->trace_budget;
+	if(budget == 0){
+		size_t fr = 0, tot = 0;
+		cudaMemGetInfo(&fr, &tot);
+		budget = (uint64_t)((fr + ctx->trace.cap) * 0.80);
+	}
+	b->trace_off.assign(n + 1, 0);
+	b->cig_off.assign(n + 1, 0);
+	std::vector<uint32_t> block_rows;
+	if(kind == 0){
+		Wave w = {0, 0, 0};
+		for(uint32_t k=0;k<nact;k++){
+			uint32_t i = b->order[k];
+			if(tbytes[i] > budget){ ctx->err = "a single pair needs more traceback memory than the budget"; delete b; return nullptr; }
+			if(w.trace_bytes + tbytes[i] > budget && w.end > w.beg){
+				b->waves.push_back(w);
+				w.beg = w.end; w.trace_bytes = 0;
+			}
+			b->trace_off[i] = w.trace_bytes;
+			w.trace_bytes += tbytes[i];
+			w.end = k + 1;
+		}
+		if(w.end > w.beg) b->waves.push_back(w);
+	} else {
+		// 32 consecutive pairs (one warp) share an interleaved trace block sized by the longest target in it
+		const uint32_t WB = b->max_bw / 64;
+		const uint32_t nblk = (nact + 31) / 32;
+		block_rows.assign(nblk + 1, 0);
+		Wave w = {0, 0, 0};
+		for(uint32_t bk=0;bk<nblk;bk++){
+			uint32_t lo = bk * 32, hi = std::min<uint32_t>(lo + 32, nact), mt = 0;
+			for(uint32_t k=lo;k<hi;k++) mt = std::max(mt, tlen[b->order[k]]);
+			uint64_t R = (uint64_t)mt + 1;
+			uint64_t bytes = R * WB * 2 * 32 * 8 + R * 32 * 4;
+			if(bytes > budget){ ctx->err = "a single block of pairs needs more traceback memory than the budget"; delete b; return nullptr; }
+			if(w.trace_bytes + bytes > budget && w.end > w.beg){
+				b->waves.push_back(w);
+				w.beg = w.end; w.trace_bytes = 0;
+			}
+			block_rows[bk] = (uint32_t)R;
+			b->trace_off[bk] = w.trace_bytes;
+			w.trace_bytes += bytes;
+			w.end = hi;
+		}
+		if(w.end > w.beg) b->waves.push_back(w);
+	}
+	if(want_cigar){
+		for(uint64_t i=0;i<n;i++) b->cig_off[i + 1] = b->cig_off[i] + ((qlen[i] && tlen[i]) ? (uint64_t)qlen[i] + tlen[i] + 2 : 0);
+		b->cig_words = b->cig_off[n];
+	}
+	// ---- device buffers + H2D ---------------------------------------------------------------------------
+	uint64_t max_wave = 0;
+	for(auto &w : b->waves) max_wave = std::max(max_wave, w.trace_bytes);
+	cudaError_t e = cudaSuccess;
+	auto R = [&](cudaError_t x){ if(e == cudaSuccess) e = x; };
+	R(b->d_seqs.reserve(seq_end + 16)); R(b->d_qoff.reserve(n * 8 + 8)); R(b->d_toff.reserve(n * 8 + 8));
+	R(b->d_qlen.reserve(n * 4 + 4)); R(b->d_tlen.reserve(n * 4 + 4)); R(b->d_order.reserve(n * 4 + 4));
+	R(b->d_trace_off.reserve(n * 8 + 8)); R(b->d_results.reserve(n * 40 + 40)); R(b->d_status.reserve(n * 4 + 4));
+	R(b->d_ncigar.reserve(n * 4 + 4)); R(b->d_dense_off.reserve(n * 8 + 8)); R(b->d_dense_total.reserve(16));
+	if(want_cigar){ R(b->d_cig_raw.reserve(b->cig_words * 4 + 16)); R(b->d_cig_off.reserve((n + 1) * 8)); R(b->d_cig_dense.reserve(b->cig_words * 4 + 16)); }
+	R(ctx->trace.reserve(max_wave + 256)); R(ctx->counter.reserve(256));
+	if(kind == 1) R(b->d_block_rows.reserve(block_rows.size() * 4 + 16));
+	if(e != cudaSuccess){ fail(ctx, "device allocation", e); bsb200_batch_free(ctx, b); return nullptr; }
+	cudaStream_t st = ctx->stream;
+	cudaEventRecord(ctx->ev[0], st);
+	if(n){
+		R(cudaMemcpyAsync(b->d_seqs.p, seqs, seq_end, cudaMemcpyHostToDevice, st));
+		R(cudaMemcpyAsync(b->d_qoff.p, qoff, n * 8, cudaMemcpyHostToDevice, st));
+		R(cudaMemcpyAsync(b->d_toff.p, toff, n * 8, cudaMemcpyHostToDevice, st));
+		R(cudaMemcpyAsync(b->d_qlen.p, qlen, n * 4, cudaMemcpyHostToDevice, st));
+		R(cudaMemcpyAsync(b->d_tlen.p, tlen, n * 4, cudaMemcpyHostToDevice, st));
+		if(nact) R(cudaMemcpyAsync(b->d_order.p, b->order.data(), (size_t)nact * 4, cudaMemcpyHostToDevice, st));
+		if(kind == 1 && !block_rows.empty()) R(cudaMemcpyAsync(b->d_block_rows.p, block_rows.data(), block_rows.size() * 4, cudaMemcpyHostToDevice, st));
+		R(cudaMemcpyAsync(b->d_trace_off.p, b->trace_off.data(), n * 8, cudaMemcpyHostToDevice, st));
+		if(want_cigar) R(cudaMemcpyAsync(b->d_cig_off.p, b->cig_off.data(), (n + 1) * 8, cudaMemcpyHostToDevice, st));
+	}
+	cudaEventRecord(ctx->ev[1], st);
+	R(cudaStreamSynchronize(st)); // order/trace_off are host vectors owned by b, but seqs belong to the caller
+	if(e != cudaSuccess){ fail(ctx, "host to device copy", e); bsb200_batch_free(ctx, b); return nullptr; }
+	float ms = 0; cudaEventElapsedTime(&ms, ctx->ev[0], ctx->ev[1]);
+	ctx->timing = bsb200_timing_t();
+	ctx->timing.h2d_ms = ms;
+	ctx->timing.h2d_bytes = seq_end + n * (8 + 8 + 4 + 4 + 4 + 8) + (want_cigar ? (n + 1) * 8 : 0);
+	ctx->timing.cells = b->cells;
+	ctx->timing.trace_bytes = b->trace_bytes;
+	ctx->timing.waves = (uint32_t)b->waves.size();
+	return b;
+}
+
+template<int PW>
+static int launch_epi8_forward(bsb200_ctx *ctx, const Epi8Args &a, uint32_t npairs){
+	int threads = kFwdThreads;
+	while(threads >= 32 && (size_t)(threads / kGroup) * a.group_smem > ctx->smem_optin) threads >>= 1;
+	if(threads < 32){ ctx->err = "band too wide for the shared-memory row buffers"; return -1; }
+	size_t smem = (size_t)(threads / kGroup) * a.group_smem;
+	CK(cudaFuncSetAttribute(epi8_forward_kernel<PW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+	int per_sm = 1;
+	CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, epi8_forward_kernel<PW>, threads, smem));
+	if(per_sm < 1) per_sm = 1;
+	uint32_t groups = threads / kGroup;
+	uint32_t grid = std::min<uint32_t>((npairs + groups - 1) / groups, (uint32_t)(ctx->num_sms * per_sm));
+	if(grid == 0) grid = 1;
+	epi8_forward_kernel<PW><<<grid, threads, smem, ctx->stream>>>(a);
+	CK(cudaGetLastError());
+	return 0;
+}
+
+template<int WR>
+static int launch_edit_t(bsb200_ctx *ctx, const EditArgs &a){
+	int threads = kEditThreads;
+	size_t per_thread = (size_t)a.nQW * 16;
+	while(threads > 32 && per_thread * threads > ctx->smem_optin) threads >>= 1;
+	if(per_thread * threads > ctx->smem_optin){ ctx->err = "query too long for the shared-memory bit-planes of the edit kernel"; return -1; }
+	size_t smem = per_thread * threads;
+	CK(cudaFuncSetAttribute(edit_kernel<WR>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+	uint32_t grid = (a.npairs + threads - 1) / threads;
+	edit_kernel<WR><<<grid, threads, smem, ctx->stream>>>(a);
+	CK(cudaGetLastError());
+	return 0;
+}
+
+static int launch_edit(bsb200_ctx *ctx, const EditArgs &a){
+	if(a.WB <= 1) return launch_edit_t<1>(ctx, a);
+	if(a.WB <= 2) return launch_edit_t<2>(ctx, a);
+	if(a.WB <= 4) return launch_edit_t<4>(ctx, a);
+	if(a.WB <= 8) return launch_edit_t<8>(ctx, a);
+	if(a.WB <= 16) return launch_edit_t<16>(ctx, a);
+	if(a.WB <= 256) return launch_edit_t<256>(ctx, a);
+	ctx->err = "edit band wider than 16384 cells is not supported";
+	return -1;
+}
+
+extern "C" int bsb200_batch_run(bsb200_ctx *ctx, bsb200_batch *b){
+	if(!ctx || !b) return -1;
+	ctx->err.clear();
+	cudaSetDevice(ctx->device);
+	cudaStream_t st = ctx->stream;
+	ctx->timing.forward_launches = ctx->timing.traceback_launches = ctx->timing.other_launches = 0;
+	float fwd_ms = 0, bt_ms = 0;
+	std::vector<cudaEvent_t> evs;
+	if(b->n == 0 || b->waves.empty()){ if(b->n){ cudaMemsetAsync(b->d_results.p, 0, b->n * 40, st); cudaMemsetAsync(b->d_status.p, 0, b->n * 4, st); cudaMemsetAsync(b->d_ncigar.p, 0, b->n * 4, st); cudaMemsetAsync(b->d_dense_off.p, 0, b->n * 8, st); cudaMemsetAsync(b->d_dense_total.p, 0, 16, st); cudaStreamSynchronize(st);} b->ran = true; return 0; }
+	CK(cudaMemsetAsync(b->d_results.p, 0, b->n * 40, st));
+	CK(cudaMemsetAsync(b->d_status.p, 0, b->n * 4, st));
+	CK(cudaMemsetAsync(b->d_ncigar.p, 0, b->n * 4, st));
+	CK(cudaMemsetAsync(b->d_dense_total.p, 0, 16, st));
+	CK(cudaMemsetAsync(b->d_dense_off.p, 0, b->n * 8, st));
+	// three events per wave: [start, forward done, traceback done]
+	evs.resize(b->waves.size() * 3);
+	for(auto &e : evs) CK(cudaEventCreate(&e));
+	for(size_t wi=0;wi<b->waves.size();wi++){
+		const Wave &w = b->waves[wi];
+		uint32_t np = w.end - w.beg;
+		CK(cudaMemsetAsync(ctx->counter.p, 0, 16, st));
+		CK(cudaEventRecord(evs[wi * 3 + 0], st));
+		if(b->kind == 0){
+			Epi8Args a;
+			a.seqs = b->d_seqs.as<uint8_t>(); a.qoff = b->d_qoff.as<uint64_t>(); a.toff = b->d_toff.as<uint64_t>();
+			a.qlen = b->d_qlen.as<uint32_t>(); a.tlen = b->d_tlen.as<uint32_t>();
+			a.order = b->d_order.as<uint32_t>() + w.beg; a.npairs = np; a.counter = ctx->counter.as<unsigned int>();
+			a.trace = ctx->trace.as<uint8_t>(); a.trace_off = b->d_trace_off.as<uint64_t>();
+			a.results = b->d_results.as<int32_t>(); a.status = b->d_status.as<int32_t>();
+			a.bandwidth = b->bandwidth; a.max_bw = b->max_bw;
+			a.group_smem = (uint32_t)(((size_t)b->max_bw * (b->pw + 2) + (kMetaInts * 2) * 4 + 32 + 32 * 4 + 15) / 16 * 16);
+			a.mode = b->mode; memcpy(a.mtx, b->mtx, 16); a.go1 = b->go1; a.ge1 = b->ge1; a.go2 = b->go2; a.ge2 = b->ge2;
+			a.smax = -127; a.smin = 127;
+			for(int k=0;k<16;k++){ a.smax = std::max(a.smax, b->mtx[k]); a.smin = std::min(a.smin, b->mtx[k]); }
+			int rc = b->pw == 2 ? launch_epi8_forward<2>(ctx, a, np) : (b->pw == 1 ? launch_epi8_forward<1>(ctx, a, np) : launch_epi8_forward<0>(ctx, a, np));
+			if(rc) return rc;
+			ctx->timing.forward_launches++;
+			CK(cudaEventRecord(evs[wi * 3 + 1], st));
+			Epi8BtArgs t;
+			t.seqs = a.seqs; t.qoff = a.qoff; t.toff = a.toff; t.qlen = a.qlen; t.tlen = a.tlen; t.order = a.order; t.npairs = np;
+			t.trace = a.trace; t.trace_off = a.trace_off; t.results = a.results; t.status = a.status;
+			t.cigars = b->want_cigar ? b->d_cig_raw.as<uint32_t>() : nullptr; t.cig_off = b->d_cig_off.as<uint64_t>();
+			t.dense = b->want_cigar ? b->d_cig_dense.as<uint32_t>() : nullptr; t.dense_off = b->d_dense_off.as<uint64_t>();
+			t.dense_total = b->d_dense_total.as<unsigned long long>();
+			t.ncigar = b->d_ncigar.as<uint32_t>();
+			t.bandwidth = b->bandwidth; t.mode = b->mode; t.pw = b->pw; memcpy(t.mtx, b->mtx, 16);
+			t.go1 = b->go1; t.ge1 = b->ge1; t.go2 = b->go2; t.ge2 = b->ge2;
+			epi8_backcal_kernel<<<(np + 127) / 128, 128, 0, st>>>(t);
+			CK(cudaGetLastError());
+			ctx->timing.traceback_launches++;
+		} else {
+			EditArgs a;
+			a.seqs = b->d_seqs.as<uint8_t>(); a.qoff = b->d_qoff.as<uint64_t>(); a.toff = b->d_toff.as<uint64_t>();
+			a.qlen = b->d_qlen.as<uint32_t>(); a.tlen = b->d_tlen.as<uint32_t>();
+			a.order = b->d_order.as<uint32_t>() + w.beg; a.npairs = np;
+			a.trace = ctx->trace.as<uint8_t>();
+			a.block_off = b->d_trace_off.as<uint64_t>() + w.beg / 32; a.block_rows = b->d_block_rows.as<uint32_t>() + w.beg / 32;
+			a.results = b->d_results.as<int32_t>(); a.status = b->d_status.as<int32_t>();
+			a.cigars = b->want_cigar ? b->d_cig_raw.as<uint32_t>() : nullptr; a.cig_off = b->d_cig_off.as<uint64_t>();
+			a.dense = b->want_cigar ? b->d_cig_dense.as<uint32_t>() : nullptr; a.dense_off = b->d_dense_off.as<uint64_t>();
+			a.dense_total = b->d_dense_total.as<unsigned long long>(); a.ncigar = b->d_ncigar.as<uint32_t>();
+			a.mode = b->mode; a.bandwidth = b->bandwidth; a.WB = b->max_bw / 64; a.nQW = b->max_q64 / 64 + 2;
+			int rc = launch_edit(ctx, a);
+			if(rc) return rc;
+			ctx->timing.forward_launches++;
+			CK(cudaEventRecord(evs[wi * 3 + 1], st));
+		}
+		CK(cudaEventRecord(evs[wi * 3 + 2], st));
+	}
+	CK(cudaStreamSynchronize(st));
+	for(size_t wi=0;wi<b->waves.size();wi++){
+		float m1 = 0, m2 = 0;
+		cudaEventElapsedTime(&m1, evs[wi * 3 + 0], evs[wi * 3 + 1]);
+		cudaEventElapsedTime(&m2, evs[wi * 3 + 1], evs[wi * 3 + 2]);
+		fwd_ms += m1; bt_ms += m2;
+	}
+	for(auto &e : evs) cudaEventDestroy(e);
+	ctx->timing.forward_ms = fwd_ms; ctx->timing.traceback_ms = bt_ms;
+	ctx->timing.other_launches = 5 + (uint32_t)b->waves.size();
+	b->ran = true;
+	return 0;
+}
+
+extern "C" int bsb200_batch_sync(bsb200_ctx *ctx){
+	if(!ctx) return -1;
+	CK(cudaStreamSynchronize(ctx->stream));
+	return 0;
+}
+
+extern "C" int bsb200_batch_fetch(bsb200_ctx *ctx, bsb200_batch *b, bsb200_result_t *results,
+		uint32_t *cigars, const uint64_t *cgoff, uint32_t *ncigar, int32_t *status){
+	if(!ctx || !b || !b->ran) return fail(ctx, "bsb200_batch_fetch before run", cudaSuccess);
+	ctx->err.clear();
+	cudaSetDevice(ctx->device);
+	cudaStream_t st = ctx->stream;
+	uint64_t n = b->n;
+	if(n == 0) return 0;
+	const bool cg = b->want_cigar && cigars && cgoff;
+	CK(b->h_results.reserve(n * 40)); CK(b->h_status.reserve(n * 4)); CK(b->h_ncigar.reserve(n * 4)); CK(b->h_total.reserve(16));
+	cudaEventRecord(ctx->ev[2], st);
+	CK(cudaMemcpyAsync(b->h_results.p, b->d_results.p, n * 40, cudaMemcpyDeviceToHost, st));
+	CK(cudaMemcpyAsync(b->h_status.p, b->d_status.p, n * 4, cudaMemcpyDeviceToHost, st));
+	CK(cudaMemcpyAsync(b->h_ncigar.p, b->d_ncigar.p, n * 4, cudaMemcpyDeviceToHost, st));
+	uint64_t d2h = n * 48;
+	uint64_t total = 0;
+	if(cg){
+		CK(b->h_dense_off.reserve(n * 8));
+		CK(cudaMemcpyAsync(b->h_dense_off.p, b->d_dense_off.p, n * 8, cudaMemcpyDeviceToHost, st));
+		CK(cudaMemcpyAsync(b->h_total.p, b->d_dense_total.p, 8, cudaMemcpyDeviceToHost, st));
+		CK(cudaStreamSynchronize(st));
+		total = *b->h_total.as<unsigned long long>();
+		CK(b->h_dense.reserve(total * 4 + 16));
+		if(total) CK(cudaMemcpyAsync(b->h_dense.p, b->d_cig_dense.p, total * 4, cudaMemcpyDeviceToHost, st));
+		d2h += n * 8 + 8 + total * 4;
+	}
+	cudaEventRecord(ctx->ev[3], st);
+	CK(cudaStreamSynchronize(st));
+	float ms = 0; cudaEventElapsedTime(&ms, ctx->ev[2], ctx->ev[3]);
+	ctx->timing.d2h_ms = ms; ctx->timing.d2h_bytes = d2h;
+	{ int32_t *hs0 = b->h_status.as<int32_t>(); for(uint64_t i=0;i<n;i++) if(b->empty[i]) hs0[i] |= BSB200_ST_EMPTY; }
+	if(results) memcpy(results, b->h_results.p, n * 40);
+	if(status) memcpy(status, b->h_status.p, n * 4);
+	const uint32_t *hn = b->h_ncigar.as<uint32_t>();
+	if(ncigar) memcpy(ncigar, hn, n * 4);
+	if(cg){
+		const uint64_t *doff = b->h_dense_off.as<uint64_t>();
+		const uint32_t *dense = b->h_dense.as<uint32_t>();
+		int32_t *hs = b->h_status.as<int32_t>();
+		for(uint64_t i=0;i<n;i++){
+			uint64_t cap = cgoff[i + 1] - cgoff[i];
+			uint64_t k = hn[i];
+			if(k > cap){ k = cap; if(status) status[i] |= BSB200_ST_CIGCAP; hs[i] |= BSB200_ST_CIGCAP; }
+			if(k) memcpy(cigars + cgoff[i], dense + doff[i], k * 4);
+		}
+	}
+	return 0;
+}
+
+extern "C" void bsb200_batch_free(bsb200_ctx *ctx, bsb200_batch *b){
+	if(!b) return;
+	if(ctx){ cudaSetDevice(ctx->device); cudaStreamSynchronize(ctx->stream); }
+	DevBuf *ds[] = {&b->d_seqs, &b->d_qoff, &b->d_toff, &b->d_qlen, &b->d_tlen, &b->d_order, &b->d_trace_off, &b->d_results, &b->d_status,
+		&b->d_ncigar, &b->d_cig_raw, &b->d_cig_off, &b->d_cig_dense, &b->d_dense_off, &b->d_dense_total, &b->d_block_rows};
+	for(auto d : ds) d->release();
+	HostBuf *hs[] = {&b->h_results, &b->h_status, &b->h_ncigar, &b->h_dense_off, &b->h_dense, &b->h_total};
+	for(auto h : hs) h->release();
+	delete b;
+}
+
+static int run_whole(bsb200_ctx *ctx, int kind, uint64_t n, const uint8_t *seqs,
+		const uint64_t *qoff, const uint32_t *qlen, const uint64_t *toff, const uint32_t *tlen,
+		int mode, uint32_t bandwidth, const int8_t *matrix, int8_t go1, int8_t ge1, int8_t go2, int8_t ge2,
+		bsb200_result_t *results, uint32_t *cigars, const uint64_t *cgoff, uint32_t *ncigar, int32_t *status){
+	if(!ctx) return -1;
+	bsb200_batch *b = bsb200_batch_upload(ctx, kind, n, seqs, qoff, qlen, toff, tlen, mode, bandwidth, matrix, go1, ge1, go2, ge2, cigars && cgoff);
+	if(!b) return -1;
+	int rc = bsb200_batch_run(ctx, b);
+	if(rc == 0) rc = bsb200_batch_fetch(ctx, b, results, cigars, cgoff, ncigar, status);
+	bsb200_timing_t tm = ctx->timing;
+	bsb200_batch_free(ctx, b);
+	tm.total_ms = tm.h2d_ms + tm.forward_ms + tm.traceback_ms + tm.d2h_ms;
+	ctx->timing = tm;
+	return rc;
+}
+
+extern "C" int bsb200_epi8_pairwise_batch(bsb200_ctx *ctx, uint64_t n, const uint8_t *seqs,
+		const uint64_t *qoff, const uint32_t *qlen, const uint64_t *toff, const uint32_t *tlen,
+		int mode, uint32_t bandwidth, const int8_t matrix[16], int8_t go1, int8_t ge1, int8_t go2, int8_t ge2,
+		bsb200_result_t *results, uint32_t *cigars, const uint64_t *cgoff, uint32_t *ncigar, int32_t *status){
+	return run_whole(ctx, 0, n, seqs, qoff, qlen, toff, tlen, mode, bandwidth, matrix, go1, ge1, go2, ge2, results, cigars, cgoff, ncigar, status);
+}
+
+extern "C" int bsb200_edit_pairwise_batch(bsb200_ctx *ctx, uint64_t n, const uint8_t *seqs,
+		const uint64_t *qoff, const uint32_t *qlen, const uint64_t *toff, const uint32_t *tlen,
+		int mode, uint32_t bandwidth,
+		bsb200_result_t *results, uint32_t *cigars, const uint64_t *cgoff, uint32_t *ncigar, int32_t *status){
+	return run_whole(ctx, 1, n, seqs, qoff, qlen, toff, tlen, mode, bandwidth, nullptr, 0, 0, 0, 0, results, cigars, cgoff, ncigar, status);
+}
+
+static int run_single(bsb200_ctx *ctx, int kind, const uint8_t *qseq, uint32_t qlen, const uint8_t *tseq, uint32_t tlen,
+		int mode, uint32_t bandwidth, const int8_t *matrix, int8_t go1, int8_t ge1, int8_t go2, int8_t ge2,
+		bsb200_result_t *result, uint32_t *cigar, uint32_t cigar_cap, uint32_t *ncigar, int32_t *status){
+	std::vector<uint8_t> seqs((size_t)qlen + tlen + 1);
+	if(qlen) memcpy(seqs.data(), qseq, qlen);
+	if(tlen) memcpy(seqs.data() + qlen, tseq, tlen);
+	uint64_t qoff = 0, toff = qlen, cgoff[2] = {0, cigar_cap};
+	return run_whole(ctx, kind, 1, seqs.data(), &qoff, &qlen, &toff, &tlen, mode, bandwidth, matrix, go1, ge1, go2, ge2,
+		result, cigar, cigar ? cgoff : nullptr, ncigar, status);
+}
+
+extern "C" int bsb200_epi8_pairwise(bsb200_ctx *ctx, const uint8_t *qseq, uint32_t qlen, const uint8_t *tseq, uint32_t tlen,
+		int mode, uint32_t bandwidth, const int8_t matrix[16], int8_t go1, int8_t ge1, int8_t go2, int8_t ge2,
+		bsb200_result_t *result, uint32_t *cigar, uint32_t cigar_cap, uint32_t *ncigar, int32_t *status){
+	return run_single(ctx, 0, qseq, qlen, tseq, tlen, mode, bandwidth, matrix, go1, ge1, go2, ge2, result, cigar, cigar_cap, ncigar, status);
+}
+
+extern "C" int bsb200_edit_pairwise(bsb200_ctx *ctx, const uint8_t *qseq, uint32_t qlen, const uint8_t *tseq, uint32_t tlen,
+		int mode, uint32_t bandwidth,
+		bsb200_result_t *result, uint32_t *cigar, uint32_t cigar_cap, uint32_t *ncigar, int32_t *status){
+	return run_single(ctx, 1, qseq, qlen, tseq, tlen, mode, bandwidth, nullptr, 0, 0, 0, 0, result, cigar, cigar_cap, ncigar, status);
+}
+
+// ---- development aid: copy one pair's raw traceback block (epi8) back to the host -------------------
+// Layout: (tlen+1) rows of (pw+1)*bw bytes in band-circular order (slot = x % bw), then (tlen+1) anchor
+// records of 20 ints {ub[17], rbeg, 0, 0}.  Valid after bsb200_batch_run for single-wave batches.
+extern "C" int64_t bsb200_debug_trace(bsb200_ctx *ctx, bsb200_batch *b, uint64_t pair, uint8_t *out, uint64_t cap, uint32_t *bw_out, int *pw_out){
+	if(!ctx || !b || b->kind != 0 || pair >= b->n || b->waves.size() != 1 || b->empty[pair]) return -1;
+	std::vector<uint32_t> ql(1), tl(1);
+	cudaMemcpy(ql.data(), b->d_qlen.as<uint32_t>() + pair, 4, cudaMemcpyDeviceToHost);
+	cudaMemcpy(tl.data(), b->d_tlen.as<uint32_t>() + pair, 4, cudaMemcpyDeviceToHost);
+	uint32_t bw = bsb200_epi8_bandwidth(ql[0], b->bandwidth);
+	uint64_t bytes = ((uint64_t)bw * (b->pw + 1) + kMetaInts * 4) * ((uint64_t)tl[0] + 1);
+	if(bytes > cap) return -(int64_t)bytes;
+	if(cudaMemcpy(out, ctx->trace.as<uint8_t>() + b->trace_off[pair], bytes, cudaMemcpyDeviceToHost) != cudaSuccess) return -1;
+	if(bw_out) *bw_out = bw;
+	if(pw_out) *pw_out = b->pw;
+	return (int64_t)bytes;
+}

@@ -1,0 +1,118 @@
+/*
+ * bsalign_b200.h -- C ABI of libbsalign_b200.so: the B200 (sm_100a) implementation of bsalign's banded
+ * striped DP hot path.  Plain pointers and sizes only; no CUDA, torch or reference types cross this line.
+ *
+ * The reference (ruanjue/bsalign) is a header-only C library: its "FFI" for this path is the pair of
+ * static-inline entry points
+ *     banded_striped_epi8_seqalign_pairwise   bsalign.h:3854  (declared bsalign.h:399)
+ *     striped_seqedit_pairwise                bsalign.h:1046  (declared bsalign.h:232)
+ * which align ONE pair per call on one CPU thread.  A GPU only pays off on batches, so the boundary is a
+ * batch form of those two calls (same argument meaning, one entry per pair) plus a single-pair
+ * convenience wrapper with the reference's argument list.  include/bsalign_b200_compat.h re-bodies the
+ * reference's own function names on top of this ABI.
+ *
+ * Conventions shared with the reference:
+ *   - sequences: one base per byte, values 0..3 (bsalign.h:399 `u1i *qseq`; dna.h:662 never emits 4)
+ *   - mode: SEQALIGN_MODE_GLOBAL 0 / OVERLAP 1 / EXTEND 2 (bsalign.h:30-38); flag bits are ignored here
+ *     (QPROF, CIGRESV are handled by the compat header on the host side)
+ *   - bandwidth 0 = full band; rounded up to 16 (epi8, bsalign.h:3861-3862) / the 64-multiple rule of
+ *     bsalign.h:1055-1067 (edit)
+ *   - matrix[q*4+t] int8 (bsalign.h:323), gap penalties are NEGATIVE int8 (main.c:284-288)
+ *   - result: the 10 ints of seqalign_result_t (bsalign.h:213-218)
+ *   - cigar words: len<<4 | op, op 0=M 1=I 2=D (bsalign.h:61-69, 401-417), query-start to query-end order
+ *
+ * Per-pair status flags (0 = the result is bit-identical to the reference's SSE4.2 build):
+ */
+#ifndef BSALIGN_B200_H
+#define BSALIGN_B200_H
+
+#include <stdint.h>
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define BSB200_ST_RANGE   1  /* a traceback score lookup left the stored band: the reference reads out of bounds here */
+#define BSB200_ST_LOOP    2  /* no consistent traceback predecessor: the reference never terminates here (bsalign.h:3798-3814) */
+#define BSB200_ST_CIGCAP  4  /* cigar capacity given by the caller was too small; cigar truncated, counts still exact */
+#define BSB200_ST_REFBUG  8  /* edit band shift hits the reference's scratch-corrupting path (bsalign.h:704-713); result follows the intended algorithm */
+#define BSB200_ST_EMPTY  16  /* qlen==0 or tlen==0: all-zero result (bsalign.h:1051-1054) */
+
+/* same field order as seqalign_result_t, bsalign.h:213-218 */
+typedef struct {
+	int32_t score;
+	int32_t qb, qe;
+	int32_t tb, te;
+	int32_t mat, mis, ins, del, aln;
+} bsb200_result_t;
+
+typedef struct bsb200_ctx bsb200_ctx;
+
+/* kernel-time accounting of the last *_run / *_batch call, CUDA events on the context's stream */
+typedef struct {
+	float h2d_ms, forward_ms, traceback_ms, d2h_ms, total_ms;
+	uint32_t forward_launches, traceback_launches, other_launches, waves;
+	uint64_t cells;            /* nominal band cells = sum over pairs of bw_eff * tlen */
+	uint64_t trace_bytes;      /* algorithmic bytes written by the forward kernel(s) */
+	uint64_t h2d_bytes, d2h_bytes;
+} bsb200_timing_t;
+
+/* ---- context ------------------------------------------------------------------------------------ */
+/* device: CUDA ordinal.  trace_budget_bytes: cap for the traceback store per wave (0 = 80% of free HBM). */
+bsb200_ctx *bsb200_create(int device, uint64_t trace_budget_bytes);
+void bsb200_destroy(bsb200_ctx *ctx);
+const char *bsb200_last_error(bsb200_ctx *ctx);   /* "" when the last call succeeded */
+int bsb200_device_count(void);
+const char *bsb200_version(void);
+void bsb200_get_timing(bsb200_ctx *ctx, bsb200_timing_t *out);
+
+/* ---- 8-bit affine / 2-piece banded alignment: replaces banded_striped_epi8_seqalign_pairwise ------ */
+/*
+ * One call = n independent pairs.  seqs is one arena; pair i is query seqs[qoff[i] .. +qlen[i]) and
+ * target seqs[toff[i] .. +tlen[i]).  results[n]; ncigar[n] (may be NULL); cigars is a caller arena where
+ * pair i owns words [cgoff[i], cgoff[i+1]) (both may be NULL: counts only, like cigars==NULL in
+ * bsalign.h:3713); status[n] may be NULL.  All pointers are HOST pointers.  Returns 0, or <0 on a CUDA /
+ * argument error (message via bsb200_last_error).
+ */
+int bsb200_epi8_pairwise_batch(bsb200_ctx *ctx, uint64_t n, const uint8_t *seqs,
+		const uint64_t *qoff, const uint32_t *qlen, const uint64_t *toff, const uint32_t *tlen,
+		int mode, uint32_t bandwidth, const int8_t matrix[16], int8_t gapo1, int8_t gape1, int8_t gapo2, int8_t gape2,
+		bsb200_result_t *results, uint32_t *cigars, const uint64_t *cgoff, uint32_t *ncigar, int32_t *status);
+
+/* Reference argument list for ONE pair (bsalign.h:399 minus mempool/verbose); cigar_cap words at cigar. */
+int bsb200_epi8_pairwise(bsb200_ctx *ctx, const uint8_t *qseq, uint32_t qlen, const uint8_t *tseq, uint32_t tlen,
+		int mode, uint32_t bandwidth, const int8_t matrix[16], int8_t gapo1, int8_t gape1, int8_t gapo2, int8_t gape2,
+		bsb200_result_t *result, uint32_t *cigar, uint32_t cigar_cap, uint32_t *ncigar, int32_t *status);
+
+/* ---- 2-bit-plane edit distance: replaces striped_seqedit_pairwise --------------------------------- */
+int bsb200_edit_pairwise_batch(bsb200_ctx *ctx, uint64_t n, const uint8_t *seqs,
+		const uint64_t *qoff, const uint32_t *qlen, const uint64_t *toff, const uint32_t *tlen,
+		int mode, uint32_t bandwidth,
+		bsb200_result_t *results, uint32_t *cigars, const uint64_t *cgoff, uint32_t *ncigar, int32_t *status);
+
+int bsb200_edit_pairwise(bsb200_ctx *ctx, const uint8_t *qseq, uint32_t qlen, const uint8_t *tseq, uint32_t tlen,
+		int mode, uint32_t bandwidth,
+		bsb200_result_t *result, uint32_t *cigar, uint32_t cigar_cap, uint32_t *ncigar, int32_t *status);
+
+/* ---- staged form (inputs resident in HBM): upload once, run the kernels many times, fetch ---------- */
+typedef struct bsb200_batch bsb200_batch;
+/* kind: 0 = epi8, 1 = edit.  matrix/gaps are ignored for kind 1. */
+bsb200_batch *bsb200_batch_upload(bsb200_ctx *ctx, int kind, uint64_t n, const uint8_t *seqs,
+		const uint64_t *qoff, const uint32_t *qlen, const uint64_t *toff, const uint32_t *tlen,
+		int mode, uint32_t bandwidth, const int8_t matrix[16], int8_t gapo1, int8_t gape1, int8_t gapo2, int8_t gape2,
+		int want_cigar);
+int bsb200_batch_run(bsb200_ctx *ctx, bsb200_batch *b);       /* kernels only; asynchronous on the context stream */
+int bsb200_batch_sync(bsb200_ctx *ctx);                       /* wait for the stream */
+int bsb200_batch_fetch(bsb200_ctx *ctx, bsb200_batch *b, bsb200_result_t *results,
+		uint32_t *cigars, const uint64_t *cgoff, uint32_t *ncigar, int32_t *status);
+void bsb200_batch_free(bsb200_ctx *ctx, bsb200_batch *b);
+
+/* nominal band width the kernels use for one pair (the GCUPS denominator) */
+uint32_t bsb200_epi8_bandwidth(uint32_t qlen, uint32_t bandwidth);
+uint32_t bsb200_edit_bandwidth(uint32_t qlen, uint32_t tlen, int mode, uint32_t bandwidth);
+
+#ifdef __cplusplus
+}
+#endif
+#endif
