@@ -1,0 +1,319 @@
+#!/usr/bin/env python
+"""bench.py -- GCUPS of the banded striped DP hot path on N B200s (contract: see the task's section 4).
+
+One "step" = one pass of the hot path over one batch of synthetic pairs.  Default workload is
+BASELINE.json configs[1] ("c2": 100k pairs, 1 kb x 1 kb, global, 8-bit affine, full band) per GPU;
+with N > 1 every rank aligns its own shard of the same shape (independent pairs, no data-path
+collective; "scaling": "weak").
+
+  value : whole-job GCUPS with inputs resident in HBM (kernels only, CUDA events on the library stream)
+  e2e   : same metric through the host-buffer C-ABI call (pinned host inputs -> H2D -> kernels -> D2H)
+  roofline / cpu_baseline / clocks / gpu_launches: see DESIGN.md section 6
+
+--impl reference times the reference's own CPU implementation (oracle/_ref/libbsref.so, the unmodified
+headers; falls back to the oracle port when that was not built) on all host cores over a bounded sample.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+import numpy as np
+
+WORKLOADS = {
+    # name: (kind, pairs per GPU, qlen, error model, mode, bandwidth, description)
+    "c2": dict(kind="epi8", pairs=100000, qlen=1000, err=(0.03, 0.03, 0.04), mode=0, bandwidth=0,
+               desc="BASELINE configs[1]: 100k pairs 1kb x 1kb, global 8-bit affine, bandwidth=0 (full)"),
+    "c3": dict(kind="epi8", pairs=10000, qlen=10000, err="ont12", mode=1, bandwidth=512,
+               desc="BASELINE configs[2]: 10k pairs 10kb x 10kb ONT-like, overlap, band 512"),
+    "c4": dict(kind="edit", pairs=1000000, qlen=300, err=(0.02, 0.02, 0.02), mode=0, bandwidth=64,
+               desc="BASELINE configs[3]: 1M pairs 300bp x 300bp, 2-bit edit, band 64"),
+    "g10k": dict(kind="epi8", pairs=512, qlen=10000, err=(0.03, 0.03, 0.04), mode=0, bandwidth=0,
+                 desc="north_star target: 10kb x 10kb global, full band"),
+}
+MATRIX = (2, -6)
+GAPS = (-3, -2, 0, 0)
+
+
+def make_batch(w, seed, pairs):
+    from bsalign_b200 import synth
+    err = synth.ont_like(0.12) if w["err"] == "ont12" else w["err"]
+    return synth.make_pairs(pairs, w["qlen"], seed, *err)
+
+
+def nominal_cells(w, batch):
+    """bw_eff * tlen per pair."""
+    q = batch.qlen.astype(np.int64)
+    t = batch.tlen.astype(np.int64)
+    if w["kind"] == "epi8":
+        bw = np.where(w["bandwidth"] == 0, q, w["bandwidth"])
+        bw = (bw + 15) // 16 * 16
+        bw = np.minimum(bw, (q + 15) // 16 * 16)
+    else:  # bsalign.h:1055-1067
+        q64 = (q + 63) // 64 * 64
+        if w["mode"] in (1, 2):
+            bw = q64
+        else:
+            bw = np.full_like(q, (w["bandwidth"] + 63) // 64 * 64)
+            bw = np.where((bw == 0) | (bw > q), q64, bw)
+            need = (q + t - 1) // np.maximum(t, 1) + 1
+            bw = np.where((bw < q) & (bw < need), (need + 63) // 64 * 64, bw)
+    return int((bw * t).sum())
+
+
+class ClockSampler:
+    """nvidia-smi clocks + throttle reasons sampled during the timed region (B200_PROFILING.md)."""
+
+    Q = "index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown," \
+        "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, device):
+        self.device, self.proc, self.lines = device, None, []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.device), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits", "-lms", "200"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], None, set()
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1])); mx = float(f[2])
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def cpu_reference_run(w, batch, nthreads, repeat=1):
+    """Reference CPU implementation (or the oracle port) over `batch` on `nthreads` host threads; seconds."""
+    import checkers as ck
+    from bsalign_b200 import synth
+    kind = "reference" if ck.have_ref() else "port"
+    fn = ck.ref_batch if kind == "reference" else ck.oracle_batch
+    mtx = synth.score_matrix(*MATRIX)
+    res, _, _ = fn(w["kind"], batch, w["mode"], w["bandwidth"], mtx, GAPS, nthreads=nthreads, repeat=repeat, want_cigar=True)
+    return ck.last_call_seconds, kind, res  # the C call only: results + cigars written to caller arenas
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS))
+    ap.add_argument("--pairs", type=int, default=0, help="pairs per GPU (default: the workload's)")
+    ap.add_argument("--cpu-sample", type=int, default=0, help="pairs in the CPU baseline sample (default: sized for ~10-20 s)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--check", type=int, default=0, help="verify this many pairs of the last step against the oracle")
+    args = ap.parse_args()
+
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    w = WORKLOADS[args.workload]
+    pairs = args.pairs or w["pairs"]
+    ncores = os.cpu_count() or 1
+
+    # ------------------------------------------------------------------ reference arm (CPU) -----------
+    if args.impl == "reference":
+        if rank != 0:
+            return
+        # bounded sample: sized from the survey's single-core rates so one step is a few seconds on all cores
+        per_core_gcups = {"c2": 2.3, "c3": 1.5, "c4": 1.1, "g10k": 2.1}[args.workload]
+        one = make_batch(w, 999, 8)
+        cells_per_pair = nominal_cells(w, one) / one.n
+        sample = args.cpu_sample or int(max(ncores, min(pairs, 4.0 * per_core_gcups * 1e9 * ncores / cells_per_pair)))
+        batch = make_batch(w, 1000, sample)
+        cells = nominal_cells(w, batch)
+        for _ in range(args.warmup):
+            cpu_reference_run(w, batch.subset(np.arange(min(sample, ncores * 4))), ncores)
+        kind, dt = "port", 0.0
+        for _ in range(args.steps):
+            d, kind, _ = cpu_reference_run(w, batch, ncores)
+            dt += d / args.steps
+        val = cells / dt / 1e9
+        sample_desc = "%d pairs of the %s shape per step, %d host threads" % (sample, args.workload, ncores)
+        print(json.dumps({
+            "impl": "reference", "metric": "GCUPS", "value": val, "unit": "GCUPS (1e9 band cells/s)", "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "int8" if w["kind"] == "epi8" else "u64 bit-planes", "data": "synthetic",
+            "config": {"workload": "%s: %s" % (args.workload, w["desc"]), "pairs_per_step": sample, "matrix": MATRIX, "gaps": GAPS},
+            "cpu_baseline": {"value": val, "unit": "GCUPS", "cores": ncores, "kind": kind, "sample": sample_desc},
+            "e2e": {"value": val, "unit": "GCUPS", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        }))
+        return
+
+    # ------------------------------------------------------------------ our arm (GPU) -----------------
+    import torch
+    import torch.distributed as dist
+    from bsalign_b200 import api, synth
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the product path has no CPU fallback (use --impl reference for the CPU arm)")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(x):
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def sum_over_ranks(x):
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        return float(t.item())
+
+    mtx = synth.score_matrix(*MATRIX)
+    batch = make_batch(w, 1000 + rank, pairs)          # this rank's shard
+    cells = nominal_cells(w, batch)
+    # pinned host copies of the inputs for the e2e leg
+    pin = lambda a: torch.from_numpy(a).pin_memory().numpy()
+    hb = synth.PairBatch.__new__(synth.PairBatch)
+    hb.seqs, hb.qoff, hb.qlen, hb.toff, hb.tlen = pin(batch.seqs), pin(batch.qoff), pin(batch.qlen), pin(batch.toff), pin(batch.tlen)
+    ctx = api.Context(local_rank)
+    out = api._alloc_out(hb, True)
+
+    def one_e2e():
+        if w["kind"] == "epi8":
+            return ctx.epi8_batch(hb, w["mode"], w["bandwidth"], mtx, *GAPS, out=out)
+        return ctx.edit_batch(hb, w["mode"], w["bandwidth"], out=out)
+
+    # ---- kernel-only leg: inputs resident in HBM --------------------------------------------------
+    rb = ctx.upload(w["kind"], hb, w["mode"], w["bandwidth"], mtx, GAPS, want_cigar=True)
+    for _ in range(args.warmup):
+        rb.run()
+    sampler = ClockSampler(local_rank)
+    barrier()
+    sampler.start()
+    dev_ms = fwd_ms = bt_ms = 0.0
+    fwd_launches = bt_launches = 0
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        rb.run()
+        tm = ctx.timing()
+        dev_ms += tm["run_ms"]; fwd_ms += tm["forward_ms"]; bt_ms += tm["traceback_ms"]
+        fwd_launches += tm["forward_launches"]; bt_launches += tm["traceback_launches"]
+    barrier()
+    wall = time.perf_counter() - t0
+    clocks = sampler.stop()
+    trace_bytes, waves = tm["trace_bytes"], tm["waves"]
+    last = rb.fetch(out=out)
+    rb.free()
+    step_ms = max_over_ranks(dev_ms / args.steps)
+    total_cells = sum_over_ranks(cells)
+    value = total_cells / (step_ms * 1e-3) / 1e9
+
+    # ---- e2e leg: host buffers through the C-ABI call ---------------------------------------------
+    for _ in range(min(args.warmup, 3)):
+        one_e2e()
+    barrier()
+    t0 = time.perf_counter()
+    h2d = d2h = 0
+    for _ in range(args.steps):
+        r = one_e2e()
+        tm2 = ctx.timing()
+        h2d, d2h = tm2["h2d_bytes"], tm2["d2h_bytes"]
+    barrier()
+    e2e_ms = max_over_ranks((time.perf_counter() - t0) / args.steps * 1e3)
+    e2e_val = total_cells / (e2e_ms * 1e-3) / 1e9
+    checksum = int(r.results[:, 0].astype(np.int64).sum())
+    assert checksum == int(last.results[:, 0].astype(np.int64).sum()), "e2e and resident runs disagree"
+    bad_status = int((r.status != 0).sum())
+
+    # ---- optional parity spot check ------------------------------------------------------------------
+    checked = None
+    if args.check:
+        import checkers as ck
+        idx = np.linspace(0, batch.n - 1, args.check).astype(np.int64)
+        sub = batch.subset(idx)
+        exp, ecg, _ = ck.oracle_batch(w["kind"], sub, w["mode"], w["bandwidth"], mtx, GAPS, nthreads=ncores)
+        ok = all(np.array_equal(r.results[i], exp[k]) and np.array_equal(r.cigar(i), ecg[k]) for k, i in enumerate(idx))
+        checked = {"pairs": int(args.check), "bit_exact": bool(ok)}
+
+    # ---- roofline of the dominant kernel (forward): algorithmic trace bytes / its event time ---------
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    peak = float(peaks.get("hbm_gbs", 6650.0))
+    achieved = trace_bytes * args.steps / (fwd_ms * 1e-3) / 1e9 if fwd_ms > 0 else 0.0
+    roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                "peak_source": "measured (MEASURED_PEAKS.json)" if peaks else "fallback (B200_PROFILING.md)",
+                "traffic": None, "kernel": "epi8_forward_kernel" if w["kind"] == "epi8" else "edit_kernel",
+                "algorithmic_bytes_per_step": int(trace_bytes), "kernel_ms_per_step": fwd_ms / args.steps,
+                "traceback_ms_per_step": bt_ms / args.steps, "waves_per_step": waves}
+
+    # ---- CPU baseline on this box's host cores (rank 0, N=1 only) ------------------------------------
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        per_core = {"c2": 2.3, "c3": 1.5, "c4": 1.1, "g10k": 2.1}[args.workload]
+        sample = args.cpu_sample or int(max(ncores, min(pairs, 12.0 * per_core * 1e9 * ncores / (cells / batch.n))))
+        sub = batch.subset(np.arange(sample))
+        scells = nominal_cells(w, sub)
+        cpu_reference_run(w, sub.subset(np.arange(min(sample, 2 * ncores))), ncores)
+        dt, kind, cres = cpu_reference_run(w, sub, ncores)
+        same = bool(np.array_equal(cres, r.results[:sample]))
+        cpu = {"value": scells / dt / 1e9, "unit": "GCUPS", "cores": ncores, "kind": kind,
+               "sample": "first %d pairs of the same batch, %d host threads, %.1f s" % (sample, ncores, dt),
+               "results_equal_gpu": same}
+
+    if rank == 0:
+        print(json.dumps({
+            "metric": "GCUPS", "value": value, "unit": "GCUPS (1e9 band cells/s)", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": step_ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "int8" if w["kind"] == "epi8" else "u64 bit-planes", "data": "synthetic",
+            "config": {"workload": "%s: %s" % (args.workload, w["desc"]), "pairs_per_gpu": pairs, "matrix": MATRIX, "gaps": GAPS,
+                       "l2": "inputs (%.0f MB) and the %.1f GB traceback store written per step both exceed the 126 MB L2" % (batch.seqs.nbytes / 1e6, trace_bytes / 1e9),
+                       "timing": "CUDA events on the library stream; max over ranks", "wall_ms_per_step": wall / args.steps * 1e3},
+            "e2e": {"value": e2e_val, "unit": "GCUPS", "ms_per_step": e2e_ms, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h)},
+            "gpu_launches": int(fwd_launches + bt_launches),
+            "roofline": roofline, "cpu_baseline": cpu, "clocks": clocks,
+            "parity": {"nonzero_status_pairs": bad_status, "score_checksum": checksum, "checked": checked},
+        }))
+    ctx.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

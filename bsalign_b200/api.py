@@ -35,7 +35,8 @@ class Timing(ctypes.Structure):
                 ("forward_launches", ctypes.c_uint32), ("traceback_launches", ctypes.c_uint32),
                 ("other_launches", ctypes.c_uint32), ("waves", ctypes.c_uint32),
                 ("cells", ctypes.c_uint64), ("trace_bytes", ctypes.c_uint64),
-                ("h2d_bytes", ctypes.c_uint64), ("d2h_bytes", ctypes.c_uint64)]
+                ("h2d_bytes", ctypes.c_uint64), ("d2h_bytes", ctypes.c_uint64),
+                ("run_ms", ctypes.c_float), ("reserved", ctypes.c_uint32)]
 
     def as_dict(self):
         return {k: getattr(self, k) for k, _ in self._fields_}

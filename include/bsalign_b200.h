@@ -56,6 +56,8 @@ typedef struct {
 	uint64_t cells;            /* nominal band cells = sum over pairs of bw_eff * tlen */
 	uint64_t trace_bytes;      /* algorithmic bytes written by the forward kernel(s) */
 	uint64_t h2d_bytes, d2h_bytes;
+	float run_ms;              /* whole bsb200_batch_run: first memset to last kernel, one event pair */
+	uint32_t reserved;
 } bsb200_timing_t;
 
 /* ---- context ------------------------------------------------------------------------------------ */

@@ -25,6 +25,7 @@ def build_oracle():
 
 _oracle = None
 _ref = None
+last_call_seconds = 0.0  # wall time of the most recent C call made by run_batch (excludes numpy/python packing)
 
 
 def oracle():
@@ -66,7 +67,10 @@ def run_batch(lib, prefix, kind, batch, mode, bandwidth, mtx=None, gaps=(0, 0, 0
     off = cigar_caps(batch) if want_cigar else None
     arena = np.zeros(int(off[-1]), dtype=np.uint32) if want_cigar else None
     ncg = np.zeros(n, dtype=np.uint32)
+    global last_call_seconds
+    import time as _time
     fn = getattr(lib, "%s_%s_batch%s" % (prefix, kind, "" if errs is None else "_ex"))
+    _t0 = _time.perf_counter()
     if kind == "epi8":
         m = np.ascontiguousarray(mtx, dtype=np.int8)
         rc = fn(ctypes.c_uint64(n), _ptr(batch.seqs), _ptr(batch.qoff), _ptr(batch.qlen), _ptr(batch.toff), _ptr(batch.tlen),
@@ -76,6 +80,7 @@ def run_batch(lib, prefix, kind, batch, mode, bandwidth, mtx=None, gaps=(0, 0, 0
         rc = fn(ctypes.c_uint64(n), _ptr(batch.seqs), _ptr(batch.qoff), _ptr(batch.qlen), _ptr(batch.toff), _ptr(batch.tlen),
                 ctypes.c_int(mode), ctypes.c_uint32(bandwidth),
                 _ptr(res), _ptr(arena), _ptr(off), _ptr(ncg), ctypes.c_int(nthreads), ctypes.c_int(repeat), *extra)
+    last_call_seconds = _time.perf_counter() - _t0
     cigs = split_cigars(arena, off, ncg) if want_cigar else None
     return res, cigs, rc
 
