@@ -5,7 +5,9 @@
 // on one stream and brings results + run-length CIGARs back.  No CPU fallback exists: every entry point
 // fails with an error string when CUDA is unavailable.
 #include "../../include/bsalign_b200.h"
-#include "epi8_kernels.cuh"
+#include "common.cuh"
+#include "epi8_forward.cuh"
+#include "epi8_backcal.cuh"
 #include "edit_kernels.cuh"
 
 #include <algorithm>
@@ -170,7 +172,7 @@ extern "C" bsb200_batch *bsb200_batch_upload(bsb200_ctx *ctx, int kind, uint64_t
 		if(qlen[i] == 0 || tlen[i] == 0){ b->empty[i] = 1; work[i] = 0; tbytes[i] = 0; continue; } // bsalign.h:1051-1054
 		if(kind == 0){
 			bw = bsb200_epi8_bandwidth(qlen[i], bandwidth);
-			tbytes[i] = ((uint64_t)bw * (b->pw + 1) + kMetaInts * 4) * ((uint64_t)tlen[i] + 1);
+			tbytes[i] = ((uint64_t)8 * epi8_region_bytes(bw / 16) * (b->pw + 1) + kMetaInts * 4) * ((uint64_t)tlen[i] + 1);
 			tbytes[i] = (tbytes[i] + 15) / 16 * 16;
 			b->cells += (uint64_t)std::min<uint32_t>(bw, (qlen[i] + 15) / 16 * 16) * tlen[i];
 			b->trace_bytes += ((uint64_t)bw * (b->pw + 1) + 84) * tlen[i];
@@ -277,20 +279,20 @@ extern "C" bsb200_batch *bsb200_batch_upload(bsb200_ctx *ctx, int kind, uint64_t
 	return b;
 }
 
-template<int PW>
+template<int PW, bool FAST>
 static int launch_epi8_forward(bsb200_ctx *ctx, const Epi8Args &a, uint32_t npairs){
 	int threads = kFwdThreads;
 	while(threads >= 32 && (size_t)(threads / kGroup) * a.group_smem > ctx->smem_optin) threads >>= 1;
 	if(threads < 32){ ctx->err = "band too wide for the shared-memory row buffers"; return -1; }
 	size_t smem = (size_t)(threads / kGroup) * a.group_smem;
-	CK(cudaFuncSetAttribute(epi8_forward_kernel<PW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+	CK(cudaFuncSetAttribute(epi8_forward_kernel<PW, FAST>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
 	int per_sm = 1;
-	CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, epi8_forward_kernel<PW>, threads, smem));
+	CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, epi8_forward_kernel<PW, FAST>, threads, smem));
 	if(per_sm < 1) per_sm = 1;
 	uint32_t groups = threads / kGroup;
 	uint32_t grid = std::min<uint32_t>((npairs + groups - 1) / groups, (uint32_t)(ctx->num_sms * per_sm));
 	if(grid == 0) grid = 1;
-	epi8_forward_kernel<PW><<<grid, threads, smem, ctx->stream>>>(a);
+	epi8_forward_kernel<PW, FAST><<<grid, threads, smem, ctx->stream>>>(a);
 	CK(cudaGetLastError());
 	return 0;
 }
@@ -350,12 +352,18 @@ extern "C" int bsb200_batch_run(bsb200_ctx *ctx, bsb200_batch *b){
 			a.order = b->d_order.as<uint32_t>() + w.beg; a.npairs = np; a.counter = ctx->counter.as<unsigned int>();
 			a.trace = ctx->trace.as<uint8_t>(); a.trace_off = b->d_trace_off.as<uint64_t>();
 			a.results = b->d_results.as<int32_t>(); a.status = b->d_status.as<int32_t>();
-			a.bandwidth = b->bandwidth; a.max_bw = b->max_bw;
-			a.group_smem = (uint32_t)(((size_t)b->max_bw * (b->pw + 2) + (kMetaInts * 2) * 4 + 32 + 32 * 4 + 15) / 16 * 16);
+			a.bandwidth = b->bandwidth; a.max_S = epi8_region_bytes(b->max_bw / 16);
+			// arrays u,(e),(q),selectors of 8 regions each + anchors, scratch; odd multiple of 32 B so the four groups of a warp start on different banks
+			a.group_smem = (uint32_t)(((size_t)8 * a.max_S * (b->pw + 2) + (kMetaInts * 2) * 4 + 32 + 32 * 4 + 31) / 32 * 32);
+			if((a.group_smem / 32) % 2 == 0) a.group_smem += 32;
 			a.mode = b->mode; memcpy(a.mtx, b->mtx, 16); a.go1 = b->go1; a.ge1 = b->ge1; a.go2 = b->go2; a.ge2 = b->ge2;
 			a.smax = -127; a.smin = 127;
 			for(int k=0;k<16;k++){ a.smax = std::max(a.smax, b->mtx[k]); a.smin = std::min(a.smin, b->mtx[k]); }
-			int rc = b->pw == 2 ? launch_epi8_forward<2>(ctx, a, np) : (b->pw == 1 ? launch_epi8_forward<1>(ctx, a, np) : launch_epi8_forward<0>(ctx, a, np));
+			// all gap costs <= 0 (the normal case): saturation bounds that cannot bind are dropped (epi8_forward.cuh)
+			const bool fast = b->ge1 <= 0 && (int8_t)(b->go1 + b->ge1) <= 0 && (b->pw < 2 || (b->ge2 <= 0 && (int8_t)(b->go2 + b->ge2) <= 0));
+			int rc;
+			if(fast) rc = b->pw == 2 ? launch_epi8_forward<2, true>(ctx, a, np) : (b->pw == 1 ? launch_epi8_forward<1, true>(ctx, a, np) : launch_epi8_forward<0, true>(ctx, a, np));
+			else rc = b->pw == 2 ? launch_epi8_forward<2, false>(ctx, a, np) : (b->pw == 1 ? launch_epi8_forward<1, false>(ctx, a, np) : launch_epi8_forward<0, false>(ctx, a, np));
 			if(rc) return rc;
 			ctx->timing.forward_launches++;
 			CK(cudaEventRecord(evs[wi * 3 + 1], st));
@@ -526,7 +534,7 @@ extern "C" int bsb200_edit_pairwise(bsb200_ctx *ctx, const uint8_t *qseq, uint32
 }
 
 // ---- development aid: copy one pair's raw traceback block (epi8) back to the host -------------------
-// Layout: (tlen+1) rows of (pw+1)*bw bytes in band-circular order (slot = x % bw), then (tlen+1) anchor
+// Layout: (tlen+1) rows of (pw+1) array images (8 regions of S bytes, see common.cuh), then (tlen+1) anchor
 // records of 20 ints {ub[17], rbeg, 0, 0}.  Valid after bsb200_batch_run for single-wave batches.
 extern "C" int64_t bsb200_debug_trace(bsb200_ctx *ctx, bsb200_batch *b, uint64_t pair, uint8_t *out, uint64_t cap, uint32_t *bw_out, int *pw_out){
 	if(!ctx || !b || b->kind != 0 || pair >= b->n || b->waves.size() != 1 || b->empty[pair]) return -1;
@@ -534,7 +542,7 @@ extern "C" int64_t bsb200_debug_trace(bsb200_ctx *ctx, bsb200_batch *b, uint64_t
 	cudaMemcpy(ql.data(), b->d_qlen.as<uint32_t>() + pair, 4, cudaMemcpyDeviceToHost);
 	cudaMemcpy(tl.data(), b->d_tlen.as<uint32_t>() + pair, 4, cudaMemcpyDeviceToHost);
 	uint32_t bw = bsb200_epi8_bandwidth(ql[0], b->bandwidth);
-	uint64_t bytes = ((uint64_t)bw * (b->pw + 1) + kMetaInts * 4) * ((uint64_t)tl[0] + 1);
+	uint64_t bytes = ((uint64_t)8 * epi8_region_bytes(bw / 16) * (b->pw + 1) + kMetaInts * 4) * ((uint64_t)tl[0] + 1);
 	if(bytes > cap) return -(int64_t)bytes;
 	if(cudaMemcpy(out, ctx->trace.as<uint8_t>() + b->trace_off[pair], bytes, cudaMemcpyDeviceToHost) != cudaSuccess) return -1;
 	if(bw_out) *bw_out = bw;

@@ -1,0 +1,57 @@
+// common.cuh -- constants and small device helpers shared by the bsalign_b200 kernels.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace bsb200 {
+
+constexpr int kGroup = 8;             // threads per pair in the epi8 forward kernel
+constexpr int kLanes = 16;            // SSE lanes of the reference build (WORDSIZE, bsalign.h:142)
+constexpr int kMetaInts = 20;         // per-row anchors: ub[17], rbeg, 2 pad  (80 B, bsalign.h:3878)
+constexpr int kScoreMin = -536870911; // SEQALIGN_SCORE_MIN, bsalign.h:58
+constexpr int kEpi8Min = -63;         // SEQALIGN_SCORE_EPI8_MIN, bsalign.h:56
+constexpr int kEpi8Max = 63;
+
+// ---- s16x2 helpers: two int8 lanes per register ------------------------------------------------------
+__device__ __forceinline__ uint32_t pk(int lo, int hi){ return (uint32_t)(lo & 0xffff) | ((uint32_t)hi << 16); }
+__device__ __forceinline__ uint32_t pk1(int v){ return pk(v, v); }
+// raw PRMT: selector nibble 8|i replicates the sign of byte i (__byte_perm() masks that bit away)
+__device__ __forceinline__ uint32_t prmt(uint32_t a, uint32_t b, uint32_t sel){ uint32_t d; asm("prmt.b32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(sel)); return d; }
+__device__ __forceinline__ int lo16(uint32_t v){ return (int)(short)(v & 0xffff); }
+__device__ __forceinline__ int hi16(uint32_t v){ return (int)(short)(v >> 16); }
+__device__ __forceinline__ int clamp8(int v){ return max(-128, min(127, v)); }
+
+__host__ __device__ __forceinline__ int epi8_piecewise(int go1, int ge1, int go2, int ge2, int bw){
+	if(go2 < go1 && ge2 > ge1 && go2 + ge2 < go1 + ge1 && (go1 - go2) / (ge1 - ge2) < bw) return 2; // bsalign.h:2084-2092
+	return go1 ? 1 : 0;
+}
+
+// Row image layout shared by the forward kernel, the HBM trace and the traceback kernel: per array
+// (u, e, q) eight regions of S bytes, region t = byte pairs (lane 2t, lane 2t+1) for steps 0..W-1.
+__host__ __device__ __forceinline__ uint32_t epi8_region_bytes(uint32_t W){ return (2 * W + 15) / 16 * 16; }
+// byte offset of band position p (lane j = p / W, step i = p % W) inside one array image
+__host__ __device__ __forceinline__ uint32_t epi8_cell_offset(uint32_t S, uint32_t j, uint32_t i){ return (j >> 1) * S + 2 * i + (j & 1); }
+
+struct CigarSink {
+	uint32_t *buf; uint32_t cap, n, run; int err;
+	__device__ __forceinline__ void put(uint32_t w){ if(buf){ if(n < cap) buf[n] = w; else err |= 4; } n++; }
+	__device__ __forceinline__ void push(uint32_t op, uint32_t sz){ // bsalign.h:409-417
+		if(op == (run & 0xf)){ run += sz << 4; return; }
+		if(run) put(run);
+		run = sz << 4 | op;
+	}
+	__device__ __forceinline__ void flush(){ if(run) put(run); run = 0; }
+};
+
+// The walk emits operations end-to-start; the final cigar is their reverse (bsalign.h:3850, :1042).  Each pair
+// reserves its exact length in one dense arena so that only real cigar words travel back over PCIe.
+__device__ __forceinline__ void emit_dense(const CigarSink &cg, uint32_t *dense, uint64_t *dense_off, unsigned long long *dense_total, uint32_t *ncigar, uint32_t pair){
+	if(ncigar) ncigar[pair] = cg.n;
+	if(!cg.buf || !dense) return;
+	uint32_t n = cg.n < cg.cap ? cg.n : cg.cap;
+	unsigned long long off = atomicAdd(dense_total, (unsigned long long)n);
+	dense_off[pair] = off;
+	for(uint32_t i=0;i<n;i++) dense[off + i] = cg.buf[n - 1 - i];
+}
+
+} // namespace bsb200

@@ -12,7 +12,7 @@
 // one contiguous 256-byte line per plane.  Forward sweep and backtrace are fused in one kernel: the
 // trace of a pair is still L2-resident when its own thread walks it back.
 #pragma once
-#include <cuda_runtime.h>
+#include "common.cuh"
 #include <stdint.h>
 
 namespace bsb200 {

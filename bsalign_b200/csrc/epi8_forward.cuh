@@ -1,0 +1,592 @@
+// epi8_forward.cuh -- sm_100a forward kernel of the 8-bit banded DP (replaces bsalign.h:2094-3349, 3854-4045).
+//
+// Parallel decomposition:
+//   * The reference's SSE word has 16 int8 lanes; lane j walks the "running block" of band positions
+//     [j*W, (j+1)*W) sequentially, twice per row (pass 1: block-exit F; pass 2: the row).  To stay
+//     bit-exact under int8 saturation that dependency structure is kept: one GROUP of 8 threads per pair,
+//     each thread owning two SSE lanes packed as s16x2 in one register, so the native VIADDMNMX.S16x2 /
+//     VIMNMX3.S16x2 instructions process two cells per issue with the saturation bounds of the SSE code.
+//   * Row state lives in shared memory in a lane-pair layout: thread t owns one contiguous 16-byte aligned
+//     region per array holding (lane 2t, lane 2t+1) byte pairs for its W steps, so the hot loops move 8
+//     steps per 128-bit LDS/STS.  The same image is what is streamed to the HBM traceback store.
+//   * The query profile of the reference (64 B per position) is replaced by a 2-byte PRMT selector per
+//     step: one PRMT against the target base's matrix column yields both lanes' substitution scores.
+//   * Four groups share a warp and run the row loop in lock step; groups fetch pairs from an atomic
+//     counter (persistent scheduling, heaviest pairs first).
+//   * FAST=true drops saturation bounds that provably cannot bind when all gap costs are <= 0 (the normal
+//     case); FAST=false keeps every bound of the SSE code.  Both are bit-exact on their domain.
+#pragma once
+#include "common.cuh"
+
+namespace bsb200 {
+
+constexpr int kFwdThreads = 128;     // 16 groups per CTA
+
+struct Epi8Args {
+	const uint8_t *seqs;
+	const uint64_t *qoff, *toff;
+	const uint32_t *qlen, *tlen;
+	const uint32_t *order;       // pair indices of this wave, heaviest first
+	uint32_t npairs;             // pairs in this wave
+	unsigned int *counter;       // work-stealing counter (zeroed before launch)
+	uint8_t *trace;              // traceback arena
+	const uint64_t *trace_off;   // per pair: byte offset of its block in the arena
+	int32_t *results;            // per pair 10 ints; forward writes score/qe/te
+	int32_t *status;             // per pair flags
+	uint32_t bandwidth;          // requested (0 = full)
+	uint32_t max_S;              // largest per-thread region (bytes) in the batch (smem sizing)
+	uint32_t group_smem;         // bytes of shared memory per group
+	int mode;
+	int8_t mtx[16];
+	int8_t go1, ge1, go2, ge2;
+	int8_t smax, smin;
+};
+
+// ---- saturating s16x2 arithmetic ------------------------------------------------------------------------
+constexpr uint32_t kLO = 0xff80ff80u, kHI = 0x007f007fu, kONE = 0x00010001u;
+__device__ __forceinline__ uint32_t sadd(uint32_t a, uint32_t b){ return __vmins2(__viaddmax_s16x2(a, b, kLO), kHI); }   // adds_epi8
+__device__ __forceinline__ uint32_t sadd_lo(uint32_t a, uint32_t b){ return __viaddmax_s16x2(a, b, kLO); }             // upper bound cannot bind
+// a - b with both bounds, given cb = ~b:  max(a + ~b, -129) + 1 = max(a - b, -128)
+__device__ __forceinline__ uint32_t ssubc(uint32_t a, uint32_t cb){ return __viaddmin_s16x2(__viaddmax_s16x2(a, cb, 0xff7fff7fu), kONE, kHI); }  // subs_epi8
+__device__ __forceinline__ uint32_t smax(uint32_t a, uint32_t b){ return __vmaxs2(a, b); }
+__device__ __forceinline__ uint32_t smax3(uint32_t a, uint32_t b, uint32_t c){ return __vimax3_s16x2(a, b, c); }
+
+// entry k (0..7) of a 16-byte chunk: (lane A byte, lane B byte) -> sign-extended s16x2
+template<int K> __device__ __forceinline__ uint32_t ent(const uint4 &c){
+	const uint32_t w = (K >> 1) == 0 ? c.x : (K >> 1) == 1 ? c.y : (K >> 1) == 2 ? c.z : c.w;
+	return prmt(w, 0u, (K & 1) ? 0xB3A2u : 0x9180u);
+}
+template<int K> __device__ __forceinline__ uint32_t ent_sel(const uint4 &c){
+	const uint32_t w = (K >> 1) == 0 ? c.x : (K >> 1) == 1 ? c.y : (K >> 1) == 2 ? c.z : c.w;
+	return (K & 1) ? (w >> 16) : w;   // PRMT reads only bits 15:0 of its selector
+}
+// low bytes of the two halves of ve (even entry) and vo (odd entry) -> one output word
+__device__ __forceinline__ uint32_t pack2(uint32_t ve, uint32_t vo){ return prmt(ve, vo, 0x6420u); }
+
+// PRMT selector that fetches (sext S[cA], sext S[cB]) from {column word, 0xC1C1C1C1}; code 4 = past the query end (-63)
+__device__ __forceinline__ uint32_t zsel(uint32_t cA, uint32_t cB){ return cA | ((8u | cA) << 4) | (cB << 8) | ((8u | cB) << 12); }
+
+struct RowState { uint32_t f, g, h, u, nv; };
+
+// one DP step for the thread's two lanes.  PASS2=false: only the F/G chain (pass 1).
+template<int PW, bool FAST, bool PASS2>
+__device__ __forceinline__ void dp_step(RowState &s, uint32_t u, uint32_t e, uint32_t q, uint32_t z,
+		uint32_t GE, uint32_t GOE, uint32_t GP, uint32_t GQP, uint32_t NGOQ, uint32_t &un, uint32_t &en, uint32_t &qn){
+	uint32_t ev, qv = 0, h;
+	if(PW == 0) ev = FAST ? sadd_lo(u, GE) : sadd(u, GE);
+	else ev = FAST ? sadd_lo(e, u) : sadd(e, u);
+	if(PW == 2){
+		qv = FAST ? sadd_lo(q, u) : sadd(q, u);
+		h = smax(smax3(ev, z, qv), smax(s.f, s.g));
+	} else h = smax3(ev, z, s.f);
+	const uint32_t cu = ~u;
+	if(PASS2){
+		const uint32_t ch = ~h;
+		un = sadd(h, s.nv);                                                    // u(x,y) = h - v(x-1,y)
+		s.nv = __viaddmin_s16x2(__viaddmax_s16x2(u, ch, kLO), kONE, 0x00800080u);  // -(subs(h,u)) = clamp(u - h, -127, 128)
+		if(PW >= 1){
+			if(FAST){
+				uint32_t x = sadd_lo(ev, GE);
+				en = __vadd2(__viaddmax_s16x2(x, ch, __vsub2(GOE, kONE)), kONE);       // max(x - h, goe)
+			} else en = smax(ssubc(sadd(ev, GE), ch), GOE);
+		}
+		if(PW == 2){
+			if(FAST){
+				uint32_t x = sadd_lo(qv, GP);
+				qn = __vadd2(__viaddmax_s16x2(x, ch, __vsub2(GQP, kONE)), kONE);
+			} else qn = smax(ssubc(sadd(qv, GP), ch), GQP);
+		}
+		s.u = u;
+	}
+	if(PW == 0){
+		s.h = h;
+		s.f = ssubc(FAST ? sadd_lo(h, GE) : sadd(h, GE), cu);
+	} else {
+		uint32_t y = FAST ? sadd_lo(h, GOE) : sadd(h, GOE);
+		uint32_t f1 = FAST ? __viaddmax_s16x2(s.f, GE, y) : smax(sadd(s.f, GE), y);
+		s.f = ssubc(f1, cu);
+		if(PW == 2){
+			y = sadd(y, NGOQ);
+			uint32_t g1 = FAST ? __viaddmax_s16x2(s.g, GP, y) : smax(sadd(s.g, GP), y);
+			s.g = ssubc(g1, cu);
+		}
+		s.h = y; // the SSE code leaves h biased by the gap-open constant after the loop (:2958, :3177)
+	}
+}
+
+// sum of entries [0, count) of lane j of a row image, spread over the group's threads
+__device__ __forceinline__ int group_lane_sum(const int8_t *img, uint32_t S, uint32_t j, uint32_t count, int t){
+	const unsigned gm = 0xffu << ((threadIdx.x & 31) & 24);
+	const int8_t *p = img + (size_t)(j >> 1) * S + (j & 1);
+	int s = 0;
+	for(uint32_t k=t;k<count;k+=kGroup) s += p[2 * k];
+	s += __shfl_xor_sync(gm, s, 1);
+	s += __shfl_xor_sync(gm, s, 2);
+	s += __shfl_xor_sync(gm, s, 4);
+	return s;
+}
+// absolute H at band position pos (bsalign.h:3187-3197)
+__device__ __forceinline__ int group_getscore(const int8_t *sU, const int32_t *sUB, uint32_t S, uint32_t W, uint32_t pos, int t){
+	uint32_t j = pos / W, i = pos - j * W;
+	return sUB[j] + group_lane_sum(sU, S, j, i + 1, t);
+}
+
+template<int PW, bool FAST>
+__global__ void __launch_bounds__(kFwdThreads) epi8_forward_kernel(const Epi8Args a){
+	extern __shared__ __align__(16) uint8_t smem_raw[];
+	const int lane = threadIdx.x & 31;
+	const int t = lane & 7;
+	const unsigned gmask = 0xffu << (lane & 24);
+	const int A = 2 * t, B = A + 1;
+	const uint32_t IMG = 8u * a.max_S;              // bytes per array image in shared memory
+	uint8_t *gs = smem_raw + (size_t)(threadIdx.x >> 3) * a.group_smem;
+	int8_t *sU = (int8_t*)gs;
+	int8_t *sE = sU + IMG;
+	int8_t *sQ = sE + (PW >= 1 ? IMG : 0);
+	uint8_t *sC = (uint8_t*)(sQ + (PW == 2 ? IMG : 0));   // PRMT selectors, 2 bytes per step
+	int32_t *sUB = (int32_t*)(sC + IMG);            // kMetaInts ints: ub[17], rbeg
+	int32_t *sTmp = sUB + kMetaInts;                // 20 ints scratch
+	int8_t *sF = (int8_t*)(sTmp + kMetaInts);       // 16 fend, 16 gend
+	int32_t *sRM = (int32_t*)(sF + 32);             // 32 ints scratch for row_max
+
+	const int mode = a.mode & 3;
+	const int go1 = a.go1, ge1 = a.ge1, go2 = a.go2, ge2 = a.ge2;
+	const int GOEi = (int8_t)(go1 + ge1), GQPi = (int8_t)(go2 + ge2);
+	const uint32_t GE = pk1(ge1), GOE = pk1(GOEi), GP = pk1(ge2), GQP = pk1(GQPi);
+	const uint32_t NGOE = pk1(-GOEi), NGOQ = pk1(-clamp8(GOEi - GQPi)), NGQP = pk1(-GQPi);
+	// matrix columns: colw[tb] holds mtx[0*4+tb], mtx[1*4+tb], mtx[2*4+tb], mtx[3*4+tb] as bytes
+	uint32_t colw[4];
+	#pragma unroll
+	for(int c=0;c<4;c++) colw[c] = (uint32_t)(uint8_t)a.mtx[c] | ((uint32_t)(uint8_t)a.mtx[4 + c] << 8) | ((uint32_t)(uint8_t)a.mtx[8 + c] << 16) | ((uint32_t)(uint8_t)a.mtx[12 + c] << 24);
+
+	bool have = false, done = false;
+	uint32_t pair = 0, qlen = 1, tlen = 1, bw = 16, W = 1, S = 16, row = 0, rbeg = 0, mov = 0;
+	const uint8_t *qs = a.seqs, *ts = a.seqs;
+	uint8_t *tr = a.trace;       // this pair's trace block (row -1 first)
+	int32_t *meta = nullptr;     // this pair's anchors block
+	uint32_t RS = 16;            // bytes per trace row
+	uint32_t tb_next = 0;
+	int best = kScoreMin, best_qe = 0, best_te = 0, stflag = 0;
+	// this thread's regions
+	int8_t *rU = sU, *rE = sE, *rQ = sQ; uint8_t *rC = sC;
+
+	// selector of query position x for this pair
+	#define QCODE(x) ((x) < qlen ? (uint32_t)qs[(x)] : 4u)
+
+	while(true){
+		if(!have && !done){
+			uint32_t idx = 0;
+			if(t == 0) idx = atomicAdd(a.counter, 1u);
+			idx = __shfl_sync(gmask, idx, lane & 24);
+			if(idx >= a.npairs) done = true;
+			else {
+				pair = a.order[idx];
+				qlen = a.qlen[pair]; tlen = a.tlen[pair];
+				qs = a.seqs + a.qoff[pair]; ts = a.seqs + a.toff[pair];
+				bw = a.bandwidth ? a.bandwidth : qlen;
+				bw = (bw + kLanes - 1) / kLanes * kLanes;
+				W = bw / kLanes;
+				S = epi8_region_bytes(W);
+				RS = 8u * S * (PW + 1);
+				tr = a.trace + a.trace_off[pair];
+				meta = (int32_t*)(tr + (size_t)RS * (tlen + 1));
+				rU = sU + (size_t)t * S; rE = sE + (size_t)t * S; rQ = sQ + (size_t)t * S; rC = sC + (size_t)t * S;
+				row = 0; rbeg = 0; mov = 0;
+				best = kScoreMin; best_qe = 0; best_te = 0; stflag = 0;
+				have = true;
+				tb_next = ts[0];
+				// ---- row -1 (bsalign.h:2094-2140) ----------------------------------------------------------
+				const bool two = (PW == 2);
+				const bool glob = (mode == 0 || mode == 2);
+				const int ext = two ? ge2 : ge1;
+				const int u0 = (int8_t)(go1 + ge1 + a.smin - a.smax);
+				const uint32_t xp = two ? (uint32_t)((go2 - go1) / (ge1 - ge2)) : 0;
+				for(uint32_t i=0;i<S/2;i++){
+					uint32_t pA = A * W + i, pB = B * W + i;
+					int vA = 0, vB = 0;
+					if(glob){
+						vA = (pA == 0) ? u0 : ((two && pA < xp) ? ge1 : ext);
+						vB = (two && pB < xp) ? ge1 : ext;
+					}
+					if(i >= W){ vA = 0; vB = 0; }
+					rU[2 * i] = (int8_t)vA; rU[2 * i + 1] = (int8_t)vB;
+					if(PW >= 1){ rE[2 * i] = kEpi8Min; rE[2 * i + 1] = kEpi8Min; }
+					if(PW == 2){ rQ[2 * i] = kEpi8Min; rQ[2 * i + 1] = kEpi8Min; }
+					*(uint16_t*)(rC + 2 * i) = (uint16_t)(i < W ? zsel(QCODE(pA), QCODE(pB)) : zsel(4, 4));
+				}
+				for(int j=t;j<=kLanes;j+=kGroup){
+					int s = 0;
+					if(glob){
+						int64_t n = (int64_t)j * W; // cells [0, n)
+						s = a.smax - a.smin;
+						if(n > 0){
+							s += u0;
+							int64_t n1 = 0; // cells holding ge1 among [1, n)
+							if(two){ n1 = (int64_t)xp - 1; if(n1 > n - 1) n1 = n - 1; if(n1 < 0) n1 = 0; }
+							s += (int)(n1 * ge1 + (n - 1 - n1) * ext);
+						}
+					}
+					sUB[j] = s;
+				}
+				if(t == 0){ sUB[17] = 0; sUB[18] = 0; sUB[19] = 0; }
+			}
+		}
+		if(__all_sync(0xffffffffu, done)) break;
+		__syncwarp();
+		if(have && row == 0){
+			// store row -1 to the trace (backcal may walk into it, bsalign.h:3922)
+			const uint32_t nch = RS / 16 / (PW + 1);
+			for(uint32_t c=t;c<nch;c+=kGroup){
+				*(uint4*)(tr + 16 * c) = *(const uint4*)(sU + 16 * c);
+				if(PW >= 1) *(uint4*)(tr + 8 * S + 16 * c) = *(const uint4*)(sE + 16 * c);
+				if(PW == 2) *(uint4*)(tr + 16 * S + 16 * c) = *(const uint4*)(sQ + 16 * c);
+			}
+			if(t < 5) *(uint4*)(meta + 4 * t) = *(const uint4*)(sUB + 4 * t);
+		}
+		__syncwarp();
+
+		// =============================== one DP row ================================================
+		const uint32_t tb = tb_next;
+		if(have && row + 1 < tlen) tb_next = ts[row + 1];
+		int rh;
+		if(mov && rbeg + bw < qlen){ // bsalign.h:3932-3946
+			int lim = (int)qlen - (int)(rbeg + bw); if(lim < 0) lim = 0;
+			if((uint32_t)lim < mov) mov = (uint32_t)lim;
+		} else mov = 0;
+		if(mov){
+			rh = (mov - 1 < bw) ? group_getscore(sU, sUB, S, W, mov - 1, t) : kScoreMin;
+			if(mov - 1 >= bw) stflag |= 1;
+		} else {
+			if(rbeg) rh = kScoreMin;
+			else if(mode == 1 || row == 0) rh = 0;
+			else if(PW < 2) rh = (int)((uint32_t)go1 + (uint32_t)ge1 * row);
+			else { uint32_t c1 = (uint32_t)go1 + (uint32_t)ge1 * row, c2 = (uint32_t)go2 + (uint32_t)ge2 * row; rh = (int)(c1 > c2 ? c1 : c2); }
+		}
+		// ---- band shift (bsalign.h:2244-2392) ----------------------------------------------------------
+		if(mov){
+			if(mov >= bw){
+				for(uint32_t i=0;i<S/2;i++){
+					uint32_t xA = rbeg + mov + A * W + i, xB = xA + W;
+					*(uint16_t*)(rU + 2 * i) = 0;
+					if(PW >= 1) *(uint16_t*)(rE + 2 * i) = 0;
+					if(PW == 2) *(uint16_t*)(rQ + 2 * i) = 0;
+					*(uint16_t*)(rC + 2 * i) = (uint16_t)(i < W ? zsel(QCODE(xA), QCODE(xB)) : zsel(4, 4));
+				}
+				for(int j=t;j<=kLanes;j+=kGroup) sUB[j] = kScoreMin;
+				rbeg += mov;
+			} else {
+				const uint32_t cyc = mov / W, mr = mov - cyc * W;
+				// anchors of the old row advanced by the first mr cells of each block (:2310-2331)
+				for(int j=t;j<kLanes;j+=kGroup){
+					const int8_t *p = sU + (size_t)(j >> 1) * S + (j & 1);
+					int s = sUB[j];
+					for(uint32_t k=0;k<mr;k++) s += p[2 * k];
+					sTmp[j] = s;
+				}
+				const int ub16 = sUB[kLanes];
+				// overhang parameters (:2357-2369)
+				uint32_t d; int c;
+				if(PW == 2){ d = (uint32_t)((go1 - go2) / (ge2 - ge1)); c = min((int)a.smin, go2 + ge2) - 1 - a.smax + (go2 + ge2); }
+				else { d = bw + 1; c = min((int)a.smin, go1 + ge1) - 1 - a.smax + (go1 + ge1); }
+				const uint32_t i0 = bw - mov;   // first band position the old row does not cover
+				if(cyc == 0 && mr <= 8){
+					// fast path: the thread's byte-pair stream slides down by mr entries; the last mr entries come
+					// from (own lane B, right neighbour's lane A) or, for the last lane, from the synthesized overhang
+					uint4 fU = *(const uint4*)rU, fE = make_uint4(0, 0, 0, 0), fQ = fE, fC = *(const uint4*)rC;
+					if(PW >= 1) fE = *(const uint4*)rE;
+					if(PW == 2) fQ = *(const uint4*)rQ;
+					uint4 nU, nE = fE, nQ = fQ, nC;
+					nU.x = __shfl_down_sync(gmask, fU.x, 1, kGroup); nU.y = __shfl_down_sync(gmask, fU.y, 1, kGroup);
+					nU.z = __shfl_down_sync(gmask, fU.z, 1, kGroup); nU.w = __shfl_down_sync(gmask, fU.w, 1, kGroup);
+					nC.x = __shfl_down_sync(gmask, fC.x, 1, kGroup); nC.y = __shfl_down_sync(gmask, fC.y, 1, kGroup);
+					nC.z = __shfl_down_sync(gmask, fC.z, 1, kGroup); nC.w = __shfl_down_sync(gmask, fC.w, 1, kGroup);
+					if(PW >= 1){
+						nE.x = __shfl_down_sync(gmask, fE.x, 1, kGroup); nE.y = __shfl_down_sync(gmask, fE.y, 1, kGroup);
+						nE.z = __shfl_down_sync(gmask, fE.z, 1, kGroup); nE.w = __shfl_down_sync(gmask, fE.w, 1, kGroup);
+					}
+					if(PW == 2){
+						nQ.x = __shfl_down_sync(gmask, fQ.x, 1, kGroup); nQ.y = __shfl_down_sync(gmask, fQ.y, 1, kGroup);
+						nQ.z = __shfl_down_sync(gmask, fQ.z, 1, kGroup); nQ.w = __shfl_down_sync(gmask, fQ.w, 1, kGroup);
+					}
+					__syncwarp(gmask);
+					const uint32_t nW = S / 4, ws = (2 * mr) / 4, bb = ((2 * mr) & 3) * 8;
+					auto slide = [&](uint32_t *r){
+						uint32_t lo = r[ws < nW ? ws : nW - 1];
+						for(uint32_t w=0;w<nW;w++){
+							uint32_t nx = w + ws + 1; if(nx >= nW) nx = nW - 1;
+							uint32_t hi = r[nx];
+							r[w] = __funnelshift_r(lo, hi, bb);
+							lo = hi;
+						}
+					};
+					slide((uint32_t*)rU); slide((uint32_t*)rC);
+					if(PW >= 1) slide((uint32_t*)rE);
+					if(PW == 2) slide((uint32_t*)rQ);
+					// entry k of a saved first chunk: byte pair (A, B)
+					auto pairA = [](const uint4 &c4, uint32_t k){ uint32_t w = (k >> 1) == 0 ? c4.x : (k >> 1) == 1 ? c4.y : (k >> 1) == 2 ? c4.z : c4.w; return (w >> ((k & 1) * 16)) & 0xffu; };
+					auto pairB = [](const uint4 &c4, uint32_t k){ uint32_t w = (k >> 1) == 0 ? c4.x : (k >> 1) == 1 ? c4.y : (k >> 1) == 2 ? c4.z : c4.w; return (w >> ((k & 1) * 16 + 8)) & 0xffu; };
+					for(uint32_t k=0;k<mr;k++){
+						const uint32_t i = W - mr + k;
+						uint32_t uB, eB = 0, qB = 0, cB;
+						if(t == 7){ // overhang cell k (:2370-2389)
+							uB = (uint32_t)(uint8_t)(int8_t)(k == 0 ? c : (k < d ? ge1 : ge2));
+							cB = QCODE(rbeg + bw + k);
+						} else {
+							uB = pairA(nU, k); eB = pairA(nE, k); qB = pairA(nQ, k);
+							uint32_t sel = (k & 1) ? (((k >> 1) == 0 ? nC.x : (k >> 1) == 1 ? nC.y : (k >> 1) == 2 ? nC.z : nC.w) >> 16) : ((k >> 1) == 0 ? nC.x : (k >> 1) == 1 ? nC.y : (k >> 1) == 2 ? nC.z : nC.w);
+							cB = sel & 7u;          // lane A code of the neighbour's entry
+						}
+						uint32_t selo = (k & 1) ? (((k >> 1) == 0 ? fC.x : (k >> 1) == 1 ? fC.y : (k >> 1) == 2 ? fC.z : fC.w) >> 16) : ((k >> 1) == 0 ? fC.x : (k >> 1) == 1 ? fC.y : (k >> 1) == 2 ? fC.z : fC.w);
+						uint32_t cA = (selo >> 8) & 7u; // own lane B code becomes lane A
+						rU[2 * i] = (int8_t)pairB(fU, k); rU[2 * i + 1] = (int8_t)uB;
+						if(PW >= 1){ rE[2 * i] = (int8_t)pairB(fE, k); rE[2 * i + 1] = (int8_t)eB; }
+						if(PW == 2){ rQ[2 * i] = (int8_t)pairB(fQ, k); rQ[2 * i + 1] = (int8_t)qB; }
+						*(uint16_t*)(rC + 2 * i) = (uint16_t)zsel(cA, cB);
+					}
+				} else {
+					// general path (rare: global mode hurrying to the end): gather from the previous row's image in
+					// the HBM trace, which this group finished writing in the previous iteration
+					__syncwarp(gmask);
+					const uint8_t *pimg = tr + (size_t)RS * row; // image of row-1
+					for(uint32_t i=0;i<W;i++){
+						#pragma unroll
+						for(int ln=0;ln<2;ln++){
+							uint32_t P = (uint32_t)(A + ln) * W + i + mov;
+							int uv, ev_ = 0, qv_ = 0;
+							if(P < bw){
+								uint32_t jo = P / W, io = P - jo * W;
+								size_t off = (size_t)(jo >> 1) * S + 2 * io + (jo & 1);
+								uv = (int8_t)pimg[off];
+								if(PW >= 1) ev_ = (int8_t)pimg[8 * S + off];
+								if(PW == 2) qv_ = (int8_t)pimg[16 * S + off];
+							} else {
+								uint32_t k = P - bw;
+								uv = (int8_t)(k == 0 ? c : (k < d ? ge1 : ge2));
+							}
+							rU[2 * i + ln] = (int8_t)uv;
+							if(PW >= 1) rE[2 * i + ln] = (int8_t)ev_;
+							if(PW == 2) rQ[2 * i + ln] = (int8_t)qv_;
+						}
+						uint32_t xA = rbeg + mov + A * W + i;
+						*(uint16_t*)(rC + 2 * i) = (uint16_t)zsel(QCODE(xA), QCODE(xA + W));
+					}
+				}
+				__syncwarp(gmask);
+				for(int j=t;j<=kLanes;j+=kGroup){
+					int v = (j + cyc < (uint32_t)kLanes) ? sTmp[j + cyc] : ub16;
+					// block ends crossed by the overhang add the running overhang total (:2372-2389)
+					uint32_t P = (uint32_t)j * W;
+					if(j >= 1 && P > i0){
+						uint32_t k = P - i0; // overhang cells in [i0, P)
+						uint32_t n1 = (k - 1 < d - 1) ? k - 1 : d - 1;
+						v += c + (int)n1 * ge1 + (int)(k - 1 - n1) * ge2;
+					}
+					sUB[j] = v;
+				}
+				rbeg += mov;
+			}
+		}
+		__syncwarp();
+
+		// ---- cell 0 (bsalign.h:2899-2907) -----------------------------------------------------------
+		const uint32_t T32 = colw[tb & 3];
+		int h0;
+		{
+			int z0 = (int)(int8_t)prmt(T32, 0xC1C1C1C1u, (uint32_t)sC[0] & 7u);
+			int u0 = sU[0], t0;
+			h0 = (rh - sUB[0]) + z0;
+			if(PW == 0) t0 = u0 + ge1;
+			else if(PW == 1) t0 = u0 + sE[0];
+			else t0 = u0 + max((int)sE[0], (int)sQ[0]);
+			if(h0 >= t0){ if(h0 > kEpi8Max) h0 = kEpi8Max; } else h0 = kEpi8Min;
+		}
+		const uint32_t zmask = t == 0 ? 0xffff0000u : 0xffffffffu, zor = t == 0 ? (uint32_t)(h0 & 0xffff) : 0u;
+		const uint32_t nchunk = (W + 7) / 8;
+
+		// ---- pass 1: F (G) leaving every running block with nothing entering ------------------------
+		RowState st; st.f = pk1(kEpi8Min); st.g = pk1(kEpi8Min); st.h = 0; st.u = 0; st.nv = 0;
+		{
+			uint32_t dum0, dum1, dum2;
+			for(uint32_t c=0;c<nchunk;c++){
+				const uint4 cu4 = *(const uint4*)(rU + 16 * c), cs4 = *(const uint4*)(rC + 16 * c);
+				uint4 ce4 = cu4, cq4 = cu4;
+				if(PW >= 1) ce4 = *(const uint4*)(rE + 16 * c);
+				if(PW == 2) cq4 = *(const uint4*)(rQ + 16 * c);
+				const uint32_t left = W - 8 * c;
+				#define P1STEP(K) { if((K) == 0 || left > (K)){ \
+					uint32_t z = prmt(T32, 0xC1C1C1C1u, ent_sel<K>(cs4)); \
+					if((K) == 0 && c == 0) z = (z & zmask) | zor; \
+					dp_step<PW, FAST, false>(st, ent<K>(cu4), ent<K>(ce4), ent<K>(cq4), z, GE, GOE, GP, GQP, NGOQ, dum0, dum1, dum2); } }
+				P1STEP(0) P1STEP(1) P1STEP(2) P1STEP(3) P1STEP(4) P1STEP(5) P1STEP(6) P1STEP(7)
+				#undef P1STEP
+			}
+		}
+		sF[A] = (int8_t)lo16(st.f); sF[B] = (int8_t)hi16(st.f);
+		if(PW == 2){ sF[16 + A] = (int8_t)lo16(st.g); sF[16 + B] = (int8_t)hi16(st.g); }
+		__syncwarp();
+		// ---- F penetration (bsalign.h:2639-2652): exact 16-step scalar scan, every thread redundantly ---
+		{
+			int finA = kEpi8Min, finB = kEpi8Min, ginA = kEpi8Min, ginB = kEpi8Min;
+			int tW = (int)W * ge1, tW2 = (int)W * ge2;
+			int ubp = sUB[0], ubn = sUB[1];
+			int s = tW + kEpi8Min - (ubn - ubp), s2 = tW2 + kEpi8Min - (ubn - ubp);
+			#pragma unroll
+			for(int j=1;j<kLanes;j++){
+				int fj = sF[j - 1];
+				if(fj < s) fj = (int)(int8_t)s;
+				int gj = 0;
+				if(PW == 2){ gj = sF[16 + j - 1]; if(gj < s2) gj = (int)(int8_t)s2; }
+				if(j == A){ finA = fj; ginA = gj; }
+				if(j == B){ finB = fj; ginB = gj; }
+				ubp = ubn; ubn = sUB[j + 1];
+				s = tW + fj - (ubn - ubp);
+				if(PW == 2) s2 = tW2 + gj - (ubn - ubp);
+			}
+			st.f = pk(finA, finB); st.g = pk(ginA, ginB);
+		}
+		// ---- pass 2: the row, written in place (bsalign.h:2934-2957 etc.) ------------------------------
+		uint32_t unew0 = 0;
+		st.nv = 0; st.h = 0; st.u = 0;
+		for(uint32_t c=0;c<nchunk;c++){
+			const uint4 cu4 = *(const uint4*)(rU + 16 * c), cs4 = *(const uint4*)(rC + 16 * c);
+			uint4 ce4 = cu4, cq4 = cu4;
+			if(PW >= 1) ce4 = *(const uint4*)(rE + 16 * c);
+			if(PW == 2) cq4 = *(const uint4*)(rQ + 16 * c);
+			const uint32_t left = W - 8 * c;
+			uint32_t un[8], en[8], qn[8];
+			#pragma unroll
+			for(int k=0;k<8;k++){ un[k] = 0; en[k] = 0; qn[k] = 0; }
+			#define P2STEP(K) { if((K) == 0 || left > (K)){ \
+				uint32_t z = prmt(T32, 0xC1C1C1C1u, ent_sel<K>(cs4)); \
+				if((K) == 0 && c == 0) z = (z & zmask) | zor; \
+				dp_step<PW, FAST, true>(st, ent<K>(cu4), ent<K>(ce4), ent<K>(cq4), z, GE, GOE, GP, GQP, NGOQ, un[K], en[K], qn[K]); } }
+			P2STEP(0) P2STEP(1) P2STEP(2) P2STEP(3) P2STEP(4) P2STEP(5) P2STEP(6) P2STEP(7)
+			#undef P2STEP
+			if(c == 0) unew0 = un[0];
+			*(uint4*)(rU + 16 * c) = make_uint4(pack2(un[0], un[1]), pack2(un[2], un[3]), pack2(un[4], un[5]), pack2(un[6], un[7]));
+			if(PW >= 1) *(uint4*)(rE + 16 * c) = make_uint4(pack2(en[0], en[1]), pack2(en[2], en[3]), pack2(en[4], en[5]), pack2(en[6], en[7]));
+			if(PW == 2) *(uint4*)(rQ + 16 * c) = make_uint4(pack2(qn[0], qn[1]), pack2(qn[2], qn[3]), pack2(qn[4], qn[5]), pack2(qn[6], qn[7]));
+		}
+		// ---- tail (bsalign.h:2618-2636) ------------------------------------------------------------------
+		{
+			uint32_t h = st.h;
+			if(PW == 1) h = sadd(h, NGOE);
+			else if(PW == 2) h = sadd(h, NGQP);
+			const uint32_t vt = ssubc(h, ~st.u);
+			int vtA = lo16(vt), vtB = hi16(vt);
+			int vprev = __shfl_up_sync(0xffffffffu, vtB, 1, kGroup);
+			if(t == 0) vprev = 0;
+			int uA = clamp8(lo16(unew0) - vprev);
+			int uB = clamp8(hi16(unew0) - vtA);
+			__syncwarp();
+			sUB[A + 1] += vtA;
+			sUB[B + 1] += vtB;
+			if(t == 0){ sUB[0] += uA; uA = 0; sUB[17] = (int32_t)rbeg; }
+			rU[0] = (int8_t)uA;
+			rU[1] = (int8_t)uB;
+		}
+		__syncwarp();
+		// ---- stream the finished row to the traceback store ---------------------------------------------
+		if(have){
+			uint8_t *dst = tr + (size_t)RS * (row + 1);
+			const uint32_t nch = S / 2; // 16-byte chunks per array image (8 regions of S bytes)
+			for(uint32_t c=t;c<nch;c+=kGroup){
+				*(uint4*)(dst + 16 * c) = *(const uint4*)(sU + 16 * c);
+				if(PW >= 1) *(uint4*)(dst + 8 * S + 16 * c) = *(const uint4*)(sE + 16 * c);
+				if(PW == 2) *(uint4*)(dst + 16 * S + 16 * c) = *(const uint4*)(sQ + 16 * c);
+			}
+			if(t < 5) *(uint4*)(meta + (size_t)kMetaInts * (row + 1) + 4 * t) = *(const uint4*)(sUB + 4 * t);
+		}
+		// ---- adaptive band steering (bsalign.h:3331-3349, 4005-4021) -------------------------------------
+		{
+			int rbx = 0;
+			if(!(row <= W * kLanes / 4) && !(rbeg + W * kLanes >= qlen)){
+				int noisy = 0, p0 = sUB[0];
+				const int ub0 = p0;
+				#pragma unroll
+				for(int j=1;j<=kLanes;j++){ int p1 = sUB[j]; noisy += p1 < p0 ? p0 - p1 : p1 - p0; p0 = p1; }
+				uint32_t nz = ((uint32_t)(noisy / kLanes)) / W * kLanes / 2;
+				noisy = (int)(16u > nz ? 16u : nz);
+				if(ub0 + noisy < p0) rbx = 2;
+				else if(ub0 > p0 + noisy) rbx = 0;
+				else rbx = 1;
+			}
+			if(mode == 0){
+				int tq = (int)(tlen / qlen);
+				int rbz = 2 * (tq > 1 ? tq : 1);
+				int rby = (int)((1.0 * row / tlen) * qlen);
+				if((int64_t)rbeg + rbz * (int64_t)(tlen - row - 1) + (int64_t)bw <= (int64_t)(uint32_t)(qlen + (uint32_t)rbz - 1)){
+					uint32_t rem = tlen - row - 1;
+					mov = 1 + ((qlen - (rbeg + bw)) / (rem > 1 ? rem : 1));
+				} else if((int)rbeg < rby - (int)bw) mov = rbx + 1;
+				else if((int)rbeg > rby) mov = rbx - 1 > 0 ? rbx - 1 : 0;
+				else mov = rbx;
+			} else mov = rbx;
+		}
+		// ---- end-point candidates (bsalign.h:4022-4045) ---------------------------------------------------
+		if(mode != 0 && rbeg + bw >= qlen){
+			int sc = group_getscore(sU, sUB, S, W, qlen - 1 - rbeg, t);
+			if(sc > best){ best = sc; best_qe = (int)qlen - 1; best_te = (int)row; }
+		}
+		row++;
+		if(have && row == tlen){
+			if(mode == 0){
+				uint32_t pos = qlen - 1 - rbeg;
+				if(pos < bw) best = group_getscore(sU, sUB, S, W, pos, t);
+				else { best = kScoreMin; stflag |= 1; }
+				best_qe = (int)qlen - 1; best_te = (int)tlen - 1;
+			} else {
+				// row_max with the SSE reduction's tie-break order (bsalign.h:3213-3291)
+				const uint32_t nck = (W + 31) / 32;
+				#pragma unroll
+				for(int which=0;which<2;which++){
+					int j = which ? B : A;
+					const int8_t *p = rU + which;
+					int Max = kScoreMin, Scr = sUB[j]; uint32_t Idx = (uint32_t)j;
+					for(uint32_t c=0;c<nck;c++){
+						uint32_t lo = c * 32, hi = lo + 32 < W ? lo + 32 : W;
+						int run = 0, mx = -32767;
+						for(uint32_t i=lo;i<hi;i++){ run += p[2 * i]; if(run > mx) mx = run; }
+						int hh = Scr + mx;
+						if(hh > Max){ Max = hh; Idx = (uint32_t)j | (c << 8); }
+						Scr += run;
+					}
+					sRM[j] = Max; sRM[16 + j] = (int)Idx;
+				}
+				__syncwarp(gmask);
+				int M4[4]; uint32_t I4[4];
+				#pragma unroll
+				for(int j=0;j<4;j++){
+					int m0 = sRM[j], m1 = sRM[j + 8];
+					uint32_t i0 = (uint32_t)sRM[16 + j], i1 = (uint32_t)sRM[16 + j + 8];
+					if(sRM[j + 4] > m0){ m0 = sRM[j + 4]; i0 = (uint32_t)sRM[16 + j + 4]; }
+					if(sRM[j + 12] > m1){ m1 = sRM[j + 12]; i1 = (uint32_t)sRM[16 + j + 12]; }
+					if(m1 > m0){ m0 = m1; i0 = i1; }
+					M4[j] = m0; I4[j] = i0;
+				}
+				int max_score = M4[0]; uint32_t bi = I4[0];
+				#pragma unroll
+				for(int j=1;j<4;j++) if(M4[j] > max_score){ max_score = M4[j]; bi = I4[j]; }
+				if(max_score > best){
+					uint32_t bl = bi & 0xff, bc = bi >> 8;
+					uint32_t x = bc * 32, y = (bc + 1) * 32 < W ? (bc + 1) * 32 : W;
+					const int8_t *p = sU + (size_t)(bl >> 1) * S + (bl & 1);
+					uint32_t pos = x; int umax = kScoreMin, uscr = 0;
+					for(;x<y;x++){ uscr += p[2 * x]; if(uscr > umax){ pos = x; umax = uscr; } }
+					best = max_score; best_qe = (int)(rbeg + bl * W + pos); best_te = (int)tlen - 1;
+				}
+				__syncwarp(gmask);
+			}
+			if(t == 0){
+				int32_t *rs = a.results + (size_t)pair * 10;
+				rs[0] = best; rs[2] = best_qe; rs[4] = best_te;
+				a.status[pair] = stflag;
+			}
+			have = false;
+		}
+		if(!have) mov = 0;
+	}
+	#undef QCODE
+}
+
+} // namespace bsb200

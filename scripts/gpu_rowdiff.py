@@ -19,8 +19,12 @@ def rowdiff(ctx, q, t, mode, bw_req, mtx, gaps, maxshow=3):
     assert nbytes > 0, nbytes
     bw, pw = bw.value, pw.value
     tlen = len(t)
-    RS = bw * (pw + 1)
-    rows = buf[:RS * (tlen + 1)].reshape(tlen + 1, pw + 1, bw).view(np.int8)
+    W = bw // 16
+    S = (2 * W + 15) // 16 * 16
+    RS = 8 * S * (pw + 1)
+    rows = buf[:RS * (tlen + 1)].reshape(tlen + 1, pw + 1, 8 * S).view(np.int8)
+    pp = np.arange(bw); jj = pp // W; ii = pp % W
+    idx = (jj >> 1) * S + 2 * ii + (jj & 1)
     meta = buf[RS * (tlen + 1):RS * (tlen + 1) + 80 * (tlen + 1)].view(np.int32).reshape(tlen + 1, 20)
     res, begs, ub, u, e, qq = ck.rows_dump(ck.oracle(), "bso_epi8_pairwise_ex", q, t, mode, bw_req, mtx, gaps,
                                            extra_args=(None, ctypes.c_uint32(0), None))
@@ -29,7 +33,6 @@ def rowdiff(ctx, q, t, mode, bw_req, mtx, gaps, maxshow=3):
     shown = 0
     for y in range(tlen):
         gb = int(meta[y + 1, 17]); gub = meta[y + 1, :17]
-        idx = (gb + np.arange(bw)) % bw
         gu = rows[y + 1, 0][idx]
         ge = rows[y + 1, 1][idx] if pw >= 1 else None
         gq = rows[y + 1, 2][idx] if pw == 2 else None
@@ -51,3 +54,7 @@ if __name__ == "__main__":
     b = synth.make_pairs(1, 100, seed=5)
     rowdiff(ctx, b.query(0), b.target(0), 0, 32, m, (-3, -2, 0, 0))
     rowdiff(ctx, b.query(0), b.target(0), 1, 0, m, (-3, -2, 0, 0))
+    b = synth.make_pairs(1, 400, seed=6)
+    rowdiff(ctx, b.query(0), b.target(0), 1, 64, m, (-3, -2, -8, -1))
+    rowdiff(ctx, b.query(0), b.target(0)[:150], 0, 64, m, (-3, -2, 0, 0))
+    rowdiff(ctx, b.query(0), b.target(0), 0, 48, synth.score_matrix(30, -40), (-40, -20, 0, 0))
