@@ -172,7 +172,7 @@ extern "C" bsb200_batch *bsb200_batch_upload(bsb200_ctx *ctx, int kind, uint64_t
 		if(qlen[i] == 0 || tlen[i] == 0){ b->empty[i] = 1; work[i] = 0; tbytes[i] = 0; continue; } // bsalign.h:1051-1054
 		if(kind == 0){
 			bw = bsb200_epi8_bandwidth(qlen[i], bandwidth);
-			tbytes[i] = ((uint64_t)8 * epi8_region_bytes(bw / 16) * (b->pw + 1) + kMetaInts * 4) * ((uint64_t)tlen[i] + 1);
+			tbytes[i] = ((uint64_t)epi8_image_bytes(bw / 16) * (b->pw + 1) + kMetaInts * 4) * ((uint64_t)tlen[i] + 1);
 			tbytes[i] = (tbytes[i] + 15) / 16 * 16;
 			b->cells += (uint64_t)std::min<uint32_t>(bw, (qlen[i] + 15) / 16 * 16) * tlen[i];
 			b->trace_bytes += ((uint64_t)bw * (b->pw + 1) + 84) * tlen[i];
@@ -352,10 +352,10 @@ extern "C" int bsb200_batch_run(bsb200_ctx *ctx, bsb200_batch *b){
 			a.order = b->d_order.as<uint32_t>() + w.beg; a.npairs = np; a.counter = ctx->counter.as<unsigned int>();
 			a.trace = ctx->trace.as<uint8_t>(); a.trace_off = b->d_trace_off.as<uint64_t>();
 			a.results = b->d_results.as<int32_t>(); a.status = b->d_status.as<int32_t>();
-			a.bandwidth = b->bandwidth; a.max_S = epi8_region_bytes(b->max_bw / 16);
-			// arrays u,(e),(q),selectors of 8 regions each + anchors, scratch; odd multiple of 32 B so the four groups of a warp start on different banks
-			a.group_smem = (uint32_t)(((size_t)8 * a.max_S * (b->pw + 2) + (kMetaInts * 2) * 4 + 32 + 32 * 4 + 31) / 32 * 32);
-			if((a.group_smem / 32) % 2 == 0) a.group_smem += 32;
+			a.bandwidth = b->bandwidth; a.max_img = epi8_image_bytes(b->max_bw / 16);
+			// images of u,(e),(q) and the selectors + anchors and scratch; 32 bytes past a multiple of 128 so the four
+			// groups of a warp keep their small per-group words (anchors, F hand-over) on different banks
+			a.group_smem = (uint32_t)(((size_t)a.max_img * (b->pw + 2) + (kMetaInts * 2) * 4 + 32 + 32 * 4 + 127) / 128 * 128 + 32);
 			a.mode = b->mode; memcpy(a.mtx, b->mtx, 16); a.go1 = b->go1; a.ge1 = b->ge1; a.go2 = b->go2; a.ge2 = b->ge2;
 			a.smax = -127; a.smin = 127;
 			for(int k=0;k<16;k++){ a.smax = std::max(a.smax, b->mtx[k]); a.smin = std::min(a.smin, b->mtx[k]); }
@@ -542,7 +542,7 @@ extern "C" int64_t bsb200_debug_trace(bsb200_ctx *ctx, bsb200_batch *b, uint64_t
 	cudaMemcpy(ql.data(), b->d_qlen.as<uint32_t>() + pair, 4, cudaMemcpyDeviceToHost);
 	cudaMemcpy(tl.data(), b->d_tlen.as<uint32_t>() + pair, 4, cudaMemcpyDeviceToHost);
 	uint32_t bw = bsb200_epi8_bandwidth(ql[0], b->bandwidth);
-	uint64_t bytes = ((uint64_t)8 * epi8_region_bytes(bw / 16) * (b->pw + 1) + kMetaInts * 4) * ((uint64_t)tl[0] + 1);
+	uint64_t bytes = ((uint64_t)epi8_image_bytes(bw / 16) * (b->pw + 1) + kMetaInts * 4) * ((uint64_t)tl[0] + 1);
 	if(bytes > cap) return -(int64_t)bytes;
 	if(cudaMemcpy(out, ctx->trace.as<uint8_t>() + b->trace_off[pair], bytes, cudaMemcpyDeviceToHost) != cudaSuccess) return -1;
 	if(bw_out) *bw_out = bw;

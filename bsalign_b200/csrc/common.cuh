@@ -26,11 +26,13 @@ __host__ __device__ __forceinline__ int epi8_piecewise(int go1, int ge1, int go2
 	return go1 ? 1 : 0;
 }
 
-// Row image layout shared by the forward kernel, the HBM trace and the traceback kernel: per array
-// (u, e, q) eight regions of S bytes, region t = byte pairs (lane 2t, lane 2t+1) for steps 0..W-1.
-__host__ __device__ __forceinline__ uint32_t epi8_region_bytes(uint32_t W){ return (2 * W + 15) / 16 * 16; }
+// Row image layout shared by the forward kernel, the HBM trace and the traceback kernel.  One array (u, e or q)
+// of a row is ceil(W/8) chunks of 128 bytes; chunk c holds, for each of the 8 threads t of the group, 16 bytes =
+// the byte pairs (lane 2t, lane 2t+1) of steps 8c..8c+7.  A group's 128-bit access to one chunk therefore covers
+// all 32 shared-memory banks exactly once, and the image is what is streamed to HBM unchanged.
+__host__ __device__ __forceinline__ uint32_t epi8_image_bytes(uint32_t W){ return (W + 7) / 8 * 128; }
 // byte offset of band position p (lane j = p / W, step i = p % W) inside one array image
-__host__ __device__ __forceinline__ uint32_t epi8_cell_offset(uint32_t S, uint32_t j, uint32_t i){ return (j >> 1) * S + 2 * i + (j & 1); }
+__host__ __device__ __forceinline__ uint32_t epi8_cell_offset(uint32_t j, uint32_t i){ return (i >> 3) * 128 + (j >> 1) * 16 + (i & 7) * 2 + (j & 1); }
 
 struct CigarSink {
 	uint32_t *buf; uint32_t cap, n, run; int err;

@@ -30,13 +30,13 @@ struct Epi8BtArgs {
 };
 
 struct TraceView {
-	const uint8_t *tr; const int32_t *meta; uint32_t bw, W, S, RS; int tlen;
+	const uint8_t *tr; const int32_t *meta; uint32_t bw, W, IB, RS; int tlen;
 	__device__ __forceinline__ int beg(int row) const { return meta[(size_t)kMetaInts * (row + 1) + 17]; }
 	__device__ __forceinline__ int ub(int row, int j) const { return meta[(size_t)kMetaInts * (row + 1) + j]; }
 	// array arr (0 u, 1 e, 2 q) of the cell at band position p of a row
 	__device__ __forceinline__ int cell(int row, int arr, uint32_t p) const {
 		uint32_t j = p / W, i = p - j * W;
-		return (int)(int8_t)tr[(size_t)RS * (row + 1) + (size_t)arr * 8 * S + epi8_cell_offset(S, j, i)];
+		return (int)(int8_t)tr[(size_t)RS * (row + 1) + (size_t)arr * IB + epi8_cell_offset(j, i)];
 	}
 	// H(col,row) = anchor of the lane + its u cells up to col (bsalign.h:3187-3202); sets err when the lookup leaves the band
 	__device__ int score(int row, int col, int &err) const {
@@ -45,16 +45,22 @@ struct TraceView {
 		if(pos < 0 || pos >= (int64_t)bw){ err |= 1; return kScoreMin; }
 		uint32_t j = (uint32_t)pos / W, n = (uint32_t)pos - j * W + 1;
 		int s = ub(row, j);
-		// the lane's cells sit at stride 2 in its region: dp4a with a 0/1 mask adds two of them per word
-		const uint8_t *r = tr + (size_t)RS * (row + 1) + (size_t)(j >> 1) * S;
+		// the lane's cells are every other byte of its thread's 16 bytes per chunk: dp4a with a 0/1 mask adds two per word
+		const uint8_t *r = tr + (size_t)RS * (row + 1) + (size_t)(j >> 1) * 16;
 		const int mk = (j & 1) ? 0x01000100 : 0x00010001;
-		uint32_t w = 0;
-		for(;n>=8;n-=8,w+=4){
-			int4 v = *(const int4*)(r + 4 * w);
+		for(;n>=8;n-=8,r+=128){
+			int4 v = *(const int4*)r;
 			s = __dp4a(v.x, mk, s); s = __dp4a(v.y, mk, s); s = __dp4a(v.z, mk, s); s = __dp4a(v.w, mk, s);
 		}
-		for(;n>=2;n-=2,w++) s = __dp4a(*(const int*)(r + 4 * w), mk, s);
-		if(n) s = __dp4a(*(const int*)(r + 4 * w), mk & 0x0000ffff, s);
+		if(n){
+			int4 v = *(const int4*)r;
+			int w[4] = {v.x, v.y, v.z, v.w};
+			#pragma unroll
+			for(int k=0;k<4;k++){
+				if(n >= 2u * k + 2) s = __dp4a(w[k], mk, s);
+				else if(n == 2u * k + 1) s = __dp4a(w[k], mk & 0x0000ffff, s);
+			}
+		}
 		return s;
 	}
 };
@@ -71,7 +77,7 @@ __global__ void __launch_bounds__(128) epi8_backcal_kernel(const Epi8BtArgs a){
 	TraceView tv;
 	tv.bw = a.bandwidth ? a.bandwidth : (uint32_t)qlen;
 	tv.bw = (tv.bw + kLanes - 1) / kLanes * kLanes;
-	tv.W = tv.bw / kLanes; tv.S = epi8_region_bytes(tv.W); tv.RS = 8u * tv.S * (pw + 1); tv.tlen = tlen;
+	tv.W = tv.bw / kLanes; tv.IB = epi8_image_bytes(tv.W); tv.RS = tv.IB * (pw + 1); tv.tlen = tlen;
 	tv.tr = a.trace + a.trace_off[pair];
 	tv.meta = (const int32_t*)(tv.tr + (size_t)tv.RS * (tlen + 1));
 	const int bw = (int)tv.bw;

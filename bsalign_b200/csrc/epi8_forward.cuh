@@ -6,9 +6,10 @@
 //     bit-exact under int8 saturation that dependency structure is kept: one GROUP of 8 threads per pair,
 //     each thread owning two SSE lanes packed as s16x2 in one register, so the native VIADDMNMX.S16x2 /
 //     VIMNMX3.S16x2 instructions process two cells per issue with the saturation bounds of the SSE code.
-//   * Row state lives in shared memory in a lane-pair layout: thread t owns one contiguous 16-byte aligned
-//     region per array holding (lane 2t, lane 2t+1) byte pairs for its W steps, so the hot loops move 8
-//     steps per 128-bit LDS/STS.  The same image is what is streamed to the HBM traceback store.
+//   * Row state lives in shared memory in a lane-pair layout: per array, chunk c holds for each thread t 16
+//     bytes = the (lane 2t, lane 2t+1) byte pairs of steps 8c..8c+7, so the hot loops move 8 steps per 128-bit
+//     LDS/STS and a group's access to a chunk touches every bank once (no conflicts).  The same image is what
+//     is streamed to the HBM traceback store.
 //   * The query profile of the reference (64 B per position) is replaced by a 2-byte PRMT selector per
 //     step: one PRMT against the target base's matrix column yields both lanes' substitution scores.
 //   * Four groups share a warp and run the row loop in lock step; groups fetch pairs from an atomic
@@ -34,7 +35,7 @@ struct Epi8Args {
 	int32_t *results;            // per pair 10 ints; forward writes score/qe/te
 	int32_t *status;             // per pair flags
 	uint32_t bandwidth;          // requested (0 = full)
-	uint32_t max_S;              // largest per-thread region (bytes) in the batch (smem sizing)
+	uint32_t max_img;            // largest array image (bytes) in the batch (smem sizing)
 	uint32_t group_smem;         // bytes of shared memory per group
 	int mode;
 	int8_t mtx[16];
@@ -115,20 +116,19 @@ __device__ __forceinline__ void dp_step(RowState &s, uint32_t u, uint32_t e, uin
 }
 
 // sum of entries [0, count) of lane j of a row image, spread over the group's threads
-__device__ __forceinline__ int group_lane_sum(const int8_t *img, uint32_t S, uint32_t j, uint32_t count, int t){
+__device__ __forceinline__ int group_lane_sum(const int8_t *img, uint32_t j, uint32_t count, int t){
 	const unsigned gm = 0xffu << ((threadIdx.x & 31) & 24);
-	const int8_t *p = img + (size_t)(j >> 1) * S + (j & 1);
 	int s = 0;
-	for(uint32_t k=t;k<count;k+=kGroup) s += p[2 * k];
+	for(uint32_t k=t;k<count;k+=kGroup) s += img[epi8_cell_offset(j, k)];
 	s += __shfl_xor_sync(gm, s, 1);
 	s += __shfl_xor_sync(gm, s, 2);
 	s += __shfl_xor_sync(gm, s, 4);
 	return s;
 }
 // absolute H at band position pos (bsalign.h:3187-3197)
-__device__ __forceinline__ int group_getscore(const int8_t *sU, const int32_t *sUB, uint32_t S, uint32_t W, uint32_t pos, int t){
+__device__ __forceinline__ int group_getscore(const int8_t *sU, const int32_t *sUB, uint32_t W, uint32_t pos, int t){
 	uint32_t j = pos / W, i = pos - j * W;
-	return sUB[j] + group_lane_sum(sU, S, j, i + 1, t);
+	return sUB[j] + group_lane_sum(sU, j, i + 1, t);
 }
 
 template<int PW, bool FAST>
@@ -138,7 +138,7 @@ __global__ void __launch_bounds__(kFwdThreads) epi8_forward_kernel(const Epi8Arg
 	const int t = lane & 7;
 	const unsigned gmask = 0xffu << (lane & 24);
 	const int A = 2 * t, B = A + 1;
-	const uint32_t IMG = 8u * a.max_S;              // bytes per array image in shared memory
+	const uint32_t IMG = a.max_img;                 // bytes reserved per array image in shared memory
 	uint8_t *gs = smem_raw + (size_t)(threadIdx.x >> 3) * a.group_smem;
 	int8_t *sU = (int8_t*)gs;
 	int8_t *sE = sU + IMG;
@@ -160,15 +160,17 @@ __global__ void __launch_bounds__(kFwdThreads) epi8_forward_kernel(const Epi8Arg
 	for(int c=0;c<4;c++) colw[c] = (uint32_t)(uint8_t)a.mtx[c] | ((uint32_t)(uint8_t)a.mtx[4 + c] << 8) | ((uint32_t)(uint8_t)a.mtx[8 + c] << 16) | ((uint32_t)(uint8_t)a.mtx[12 + c] << 24);
 
 	bool have = false, done = false;
-	uint32_t pair = 0, qlen = 1, tlen = 1, bw = 16, W = 1, S = 16, row = 0, rbeg = 0, mov = 0;
+	uint32_t pair = 0, qlen = 1, tlen = 1, bw = 16, W = 1, IB = 128, row = 0, rbeg = 0, mov = 0;
 	const uint8_t *qs = a.seqs, *ts = a.seqs;
 	uint8_t *tr = a.trace;       // this pair's trace block (row -1 first)
 	int32_t *meta = nullptr;     // this pair's anchors block
 	uint32_t RS = 16;            // bytes per trace row
 	uint32_t tb_next = 0;
 	int best = kScoreMin, best_qe = 0, best_te = 0, stflag = 0;
-	// this thread's regions
-	int8_t *rU = sU, *rE = sE, *rQ = sQ; uint8_t *rC = sC;
+	// this thread's 16 bytes inside chunk 0 of every array; chunk c is 128*c bytes further
+	int8_t *const rU = sU + 16 * t, *const rE = sE + 16 * t, *const rQ = sQ + 16 * t; uint8_t *const rC = sC + 16 * t;
+	// byte offset, relative to rU/rE/rQ/rC, of the thread's own step i (lane A; lane B is the next byte)
+	#define TOFF(i) ((((i) >> 3) << 7) + (((i) & 7) << 1))
 
 	// selector of query position x for this pair
 	#define QCODE(x) ((x) < qlen ? (uint32_t)qs[(x)] : 4u)
@@ -186,11 +188,10 @@ __global__ void __launch_bounds__(kFwdThreads) epi8_forward_kernel(const Epi8Arg
 				bw = a.bandwidth ? a.bandwidth : qlen;
 				bw = (bw + kLanes - 1) / kLanes * kLanes;
 				W = bw / kLanes;
-				S = epi8_region_bytes(W);
-				RS = 8u * S * (PW + 1);
+				IB = epi8_image_bytes(W);
+				RS = IB * (PW + 1);
 				tr = a.trace + a.trace_off[pair];
 				meta = (int32_t*)(tr + (size_t)RS * (tlen + 1));
-				rU = sU + (size_t)t * S; rE = sE + (size_t)t * S; rQ = sQ + (size_t)t * S; rC = sC + (size_t)t * S;
 				row = 0; rbeg = 0; mov = 0;
 				best = kScoreMin; best_qe = 0; best_te = 0; stflag = 0;
 				have = true;
@@ -201,7 +202,7 @@ __global__ void __launch_bounds__(kFwdThreads) epi8_forward_kernel(const Epi8Arg
 				const int ext = two ? ge2 : ge1;
 				const int u0 = (int8_t)(go1 + ge1 + a.smin - a.smax);
 				const uint32_t xp = two ? (uint32_t)((go2 - go1) / (ge1 - ge2)) : 0;
-				for(uint32_t i=0;i<S/2;i++){
+				for(uint32_t i=0;i<IB/16;i++){
 					uint32_t pA = A * W + i, pB = B * W + i;
 					int vA = 0, vB = 0;
 					if(glob){
@@ -209,10 +210,10 @@ __global__ void __launch_bounds__(kFwdThreads) epi8_forward_kernel(const Epi8Arg
 						vB = (two && pB < xp) ? ge1 : ext;
 					}
 					if(i >= W){ vA = 0; vB = 0; }
-					rU[2 * i] = (int8_t)vA; rU[2 * i + 1] = (int8_t)vB;
-					if(PW >= 1){ rE[2 * i] = kEpi8Min; rE[2 * i + 1] = kEpi8Min; }
-					if(PW == 2){ rQ[2 * i] = kEpi8Min; rQ[2 * i + 1] = kEpi8Min; }
-					*(uint16_t*)(rC + 2 * i) = (uint16_t)(i < W ? zsel(QCODE(pA), QCODE(pB)) : zsel(4, 4));
+					rU[TOFF(i)] = (int8_t)vA; rU[TOFF(i) + 1] = (int8_t)vB;
+					if(PW >= 1){ rE[TOFF(i)] = kEpi8Min; rE[TOFF(i) + 1] = kEpi8Min; }
+					if(PW == 2){ rQ[TOFF(i)] = kEpi8Min; rQ[TOFF(i) + 1] = kEpi8Min; }
+					*(uint16_t*)(rC + TOFF(i)) = (uint16_t)(i < W ? zsel(QCODE(pA), QCODE(pB)) : zsel(4, 4));
 				}
 				for(int j=t;j<=kLanes;j+=kGroup){
 					int s = 0;
@@ -235,11 +236,11 @@ __global__ void __launch_bounds__(kFwdThreads) epi8_forward_kernel(const Epi8Arg
 		__syncwarp();
 		if(have && row == 0){
 			// store row -1 to the trace (backcal may walk into it, bsalign.h:3922)
-			const uint32_t nch = RS / 16 / (PW + 1);
+			const uint32_t nch = IB / 16;
 			for(uint32_t c=t;c<nch;c+=kGroup){
 				*(uint4*)(tr + 16 * c) = *(const uint4*)(sU + 16 * c);
-				if(PW >= 1) *(uint4*)(tr + 8 * S + 16 * c) = *(const uint4*)(sE + 16 * c);
-				if(PW == 2) *(uint4*)(tr + 16 * S + 16 * c) = *(const uint4*)(sQ + 16 * c);
+				if(PW >= 1) *(uint4*)(tr + IB + 16 * c) = *(const uint4*)(sE + 16 * c);
+				if(PW == 2) *(uint4*)(tr + 2 * IB + 16 * c) = *(const uint4*)(sQ + 16 * c);
 			}
 			if(t < 5) *(uint4*)(meta + 4 * t) = *(const uint4*)(sUB + 4 * t);
 		}
@@ -254,7 +255,7 @@ __global__ void __launch_bounds__(kFwdThreads) epi8_forward_kernel(const Epi8Arg
 			if((uint32_t)lim < mov) mov = (uint32_t)lim;
 		} else mov = 0;
 		if(mov){
-			rh = (mov - 1 < bw) ? group_getscore(sU, sUB, S, W, mov - 1, t) : kScoreMin;
+			rh = (mov - 1 < bw) ? group_getscore(sU, sUB, W, mov - 1, t) : kScoreMin;
 			if(mov - 1 >= bw) stflag |= 1;
 		} else {
 			if(rbeg) rh = kScoreMin;
@@ -265,12 +266,12 @@ __global__ void __launch_bounds__(kFwdThreads) epi8_forward_kernel(const Epi8Arg
 		// ---- band shift (bsalign.h:2244-2392) ----------------------------------------------------------
 		if(mov){
 			if(mov >= bw){
-				for(uint32_t i=0;i<S/2;i++){
+				for(uint32_t i=0;i<IB/16;i++){
 					uint32_t xA = rbeg + mov + A * W + i, xB = xA + W;
-					*(uint16_t*)(rU + 2 * i) = 0;
-					if(PW >= 1) *(uint16_t*)(rE + 2 * i) = 0;
-					if(PW == 2) *(uint16_t*)(rQ + 2 * i) = 0;
-					*(uint16_t*)(rC + 2 * i) = (uint16_t)(i < W ? zsel(QCODE(xA), QCODE(xB)) : zsel(4, 4));
+					*(uint16_t*)(rU + TOFF(i)) = 0;
+					if(PW >= 1) *(uint16_t*)(rE + TOFF(i)) = 0;
+					if(PW == 2) *(uint16_t*)(rQ + TOFF(i)) = 0;
+					*(uint16_t*)(rC + TOFF(i)) = (uint16_t)(i < W ? zsel(QCODE(xA), QCODE(xB)) : zsel(4, 4));
 				}
 				for(int j=t;j<=kLanes;j+=kGroup) sUB[j] = kScoreMin;
 				rbeg += mov;
@@ -278,9 +279,8 @@ __global__ void __launch_bounds__(kFwdThreads) epi8_forward_kernel(const Epi8Arg
 				const uint32_t cyc = mov / W, mr = mov - cyc * W;
 				// anchors of the old row advanced by the first mr cells of each block (:2310-2331)
 				for(int j=t;j<kLanes;j+=kGroup){
-					const int8_t *p = sU + (size_t)(j >> 1) * S + (j & 1);
 					int s = sUB[j];
-					for(uint32_t k=0;k<mr;k++) s += p[2 * k];
+					for(uint32_t k=0;k<mr;k++) s += sU[epi8_cell_offset(j, k)];
 					sTmp[j] = s;
 				}
 				const int ub16 = sUB[kLanes];
@@ -309,19 +309,22 @@ __global__ void __launch_bounds__(kFwdThreads) epi8_forward_kernel(const Epi8Arg
 						nQ.z = __shfl_down_sync(gmask, fQ.z, 1, kGroup); nQ.w = __shfl_down_sync(gmask, fQ.w, 1, kGroup);
 					}
 					__syncwarp(gmask);
-					const uint32_t nW = S / 4, ws = (2 * mr) / 4, bb = ((2 * mr) & 3) * 8;
-					auto slide = [&](uint32_t *r){
-						uint32_t lo = r[ws < nW ? ws : nW - 1];
+					// the thread's stream is 4 words per chunk; word w lives at chunk w/4, offset 4*(w%4)
+					const uint32_t nW = IB / 32, ws = (2 * mr) / 4, bb = ((2 * mr) & 3) * 8;
+					#define WOFF(w) ((((w) >> 2) << 7) + (((w) & 3) << 2))
+					auto slide = [&](uint8_t *r){
+						uint32_t lo = *(const uint32_t*)(r + WOFF(ws < nW ? ws : nW - 1));
 						for(uint32_t w=0;w<nW;w++){
 							uint32_t nx = w + ws + 1; if(nx >= nW) nx = nW - 1;
-							uint32_t hi = r[nx];
-							r[w] = __funnelshift_r(lo, hi, bb);
+							uint32_t hi = *(const uint32_t*)(r + WOFF(nx));
+							*(uint32_t*)(r + WOFF(w)) = __funnelshift_r(lo, hi, bb);
 							lo = hi;
 						}
 					};
-					slide((uint32_t*)rU); slide((uint32_t*)rC);
-					if(PW >= 1) slide((uint32_t*)rE);
-					if(PW == 2) slide((uint32_t*)rQ);
+					#undef WOFF
+					slide((uint8_t*)rU); slide((uint8_t*)rC);
+					if(PW >= 1) slide((uint8_t*)rE);
+					if(PW == 2) slide((uint8_t*)rQ);
 					// entry k of a saved first chunk: byte pair (A, B)
 					auto pairA = [](const uint4 &c4, uint32_t k){ uint32_t w = (k >> 1) == 0 ? c4.x : (k >> 1) == 1 ? c4.y : (k >> 1) == 2 ? c4.z : c4.w; return (w >> ((k & 1) * 16)) & 0xffu; };
 					auto pairB = [](const uint4 &c4, uint32_t k){ uint32_t w = (k >> 1) == 0 ? c4.x : (k >> 1) == 1 ? c4.y : (k >> 1) == 2 ? c4.z : c4.w; return (w >> ((k & 1) * 16 + 8)) & 0xffu; };
@@ -338,10 +341,10 @@ __global__ void __launch_bounds__(kFwdThreads) epi8_forward_kernel(const Epi8Arg
 						}
 						uint32_t selo = (k & 1) ? (((k >> 1) == 0 ? fC.x : (k >> 1) == 1 ? fC.y : (k >> 1) == 2 ? fC.z : fC.w) >> 16) : ((k >> 1) == 0 ? fC.x : (k >> 1) == 1 ? fC.y : (k >> 1) == 2 ? fC.z : fC.w);
 						uint32_t cA = (selo >> 8) & 7u; // own lane B code becomes lane A
-						rU[2 * i] = (int8_t)pairB(fU, k); rU[2 * i + 1] = (int8_t)uB;
-						if(PW >= 1){ rE[2 * i] = (int8_t)pairB(fE, k); rE[2 * i + 1] = (int8_t)eB; }
-						if(PW == 2){ rQ[2 * i] = (int8_t)pairB(fQ, k); rQ[2 * i + 1] = (int8_t)qB; }
-						*(uint16_t*)(rC + 2 * i) = (uint16_t)zsel(cA, cB);
+						rU[TOFF(i)] = (int8_t)pairB(fU, k); rU[TOFF(i) + 1] = (int8_t)uB;
+						if(PW >= 1){ rE[TOFF(i)] = (int8_t)pairB(fE, k); rE[TOFF(i) + 1] = (int8_t)eB; }
+						if(PW == 2){ rQ[TOFF(i)] = (int8_t)pairB(fQ, k); rQ[TOFF(i) + 1] = (int8_t)qB; }
+						*(uint16_t*)(rC + TOFF(i)) = (uint16_t)zsel(cA, cB);
 					}
 				} else {
 					// general path (rare: global mode hurrying to the end): gather from the previous row's image in
@@ -355,20 +358,20 @@ __global__ void __launch_bounds__(kFwdThreads) epi8_forward_kernel(const Epi8Arg
 							int uv, ev_ = 0, qv_ = 0;
 							if(P < bw){
 								uint32_t jo = P / W, io = P - jo * W;
-								size_t off = (size_t)(jo >> 1) * S + 2 * io + (jo & 1);
+								size_t off = epi8_cell_offset(jo, io);
 								uv = (int8_t)pimg[off];
-								if(PW >= 1) ev_ = (int8_t)pimg[8 * S + off];
-								if(PW == 2) qv_ = (int8_t)pimg[16 * S + off];
+								if(PW >= 1) ev_ = (int8_t)pimg[IB + off];
+								if(PW == 2) qv_ = (int8_t)pimg[2 * IB + off];
 							} else {
 								uint32_t k = P - bw;
 								uv = (int8_t)(k == 0 ? c : (k < d ? ge1 : ge2));
 							}
-							rU[2 * i + ln] = (int8_t)uv;
-							if(PW >= 1) rE[2 * i + ln] = (int8_t)ev_;
-							if(PW == 2) rQ[2 * i + ln] = (int8_t)qv_;
+							rU[TOFF(i) + ln] = (int8_t)uv;
+							if(PW >= 1) rE[TOFF(i) + ln] = (int8_t)ev_;
+							if(PW == 2) rQ[TOFF(i) + ln] = (int8_t)qv_;
 						}
 						uint32_t xA = rbeg + mov + A * W + i;
-						*(uint16_t*)(rC + 2 * i) = (uint16_t)zsel(QCODE(xA), QCODE(xA + W));
+						*(uint16_t*)(rC + TOFF(i)) = (uint16_t)zsel(QCODE(xA), QCODE(xA + W));
 					}
 				}
 				__syncwarp(gmask);
@@ -408,10 +411,10 @@ __global__ void __launch_bounds__(kFwdThreads) epi8_forward_kernel(const Epi8Arg
 		{
 			uint32_t dum0, dum1, dum2;
 			for(uint32_t c=0;c<nchunk;c++){
-				const uint4 cu4 = *(const uint4*)(rU + 16 * c), cs4 = *(const uint4*)(rC + 16 * c);
+				const uint4 cu4 = *(const uint4*)(rU + 128 * c), cs4 = *(const uint4*)(rC + 128 * c);
 				uint4 ce4 = cu4, cq4 = cu4;
-				if(PW >= 1) ce4 = *(const uint4*)(rE + 16 * c);
-				if(PW == 2) cq4 = *(const uint4*)(rQ + 16 * c);
+				if(PW >= 1) ce4 = *(const uint4*)(rE + 128 * c);
+				if(PW == 2) cq4 = *(const uint4*)(rQ + 128 * c);
 				const uint32_t left = W - 8 * c;
 				#define P1STEP(K) { if((K) == 0 || left > (K)){ \
 					uint32_t z = prmt(T32, 0xC1C1C1C1u, ent_sel<K>(cs4)); \
@@ -448,10 +451,10 @@ __global__ void __launch_bounds__(kFwdThreads) epi8_forward_kernel(const Epi8Arg
 		uint32_t unew0 = 0;
 		st.nv = 0; st.h = 0; st.u = 0;
 		for(uint32_t c=0;c<nchunk;c++){
-			const uint4 cu4 = *(const uint4*)(rU + 16 * c), cs4 = *(const uint4*)(rC + 16 * c);
+			const uint4 cu4 = *(const uint4*)(rU + 128 * c), cs4 = *(const uint4*)(rC + 128 * c);
 			uint4 ce4 = cu4, cq4 = cu4;
-			if(PW >= 1) ce4 = *(const uint4*)(rE + 16 * c);
-			if(PW == 2) cq4 = *(const uint4*)(rQ + 16 * c);
+			if(PW >= 1) ce4 = *(const uint4*)(rE + 128 * c);
+			if(PW == 2) cq4 = *(const uint4*)(rQ + 128 * c);
 			const uint32_t left = W - 8 * c;
 			uint32_t un[8], en[8], qn[8];
 			#pragma unroll
@@ -463,9 +466,9 @@ __global__ void __launch_bounds__(kFwdThreads) epi8_forward_kernel(const Epi8Arg
 			P2STEP(0) P2STEP(1) P2STEP(2) P2STEP(3) P2STEP(4) P2STEP(5) P2STEP(6) P2STEP(7)
 			#undef P2STEP
 			if(c == 0) unew0 = un[0];
-			*(uint4*)(rU + 16 * c) = make_uint4(pack2(un[0], un[1]), pack2(un[2], un[3]), pack2(un[4], un[5]), pack2(un[6], un[7]));
-			if(PW >= 1) *(uint4*)(rE + 16 * c) = make_uint4(pack2(en[0], en[1]), pack2(en[2], en[3]), pack2(en[4], en[5]), pack2(en[6], en[7]));
-			if(PW == 2) *(uint4*)(rQ + 16 * c) = make_uint4(pack2(qn[0], qn[1]), pack2(qn[2], qn[3]), pack2(qn[4], qn[5]), pack2(qn[6], qn[7]));
+			*(uint4*)(rU + 128 * c) = make_uint4(pack2(un[0], un[1]), pack2(un[2], un[3]), pack2(un[4], un[5]), pack2(un[6], un[7]));
+			if(PW >= 1) *(uint4*)(rE + 128 * c) = make_uint4(pack2(en[0], en[1]), pack2(en[2], en[3]), pack2(en[4], en[5]), pack2(en[6], en[7]));
+			if(PW == 2) *(uint4*)(rQ + 128 * c) = make_uint4(pack2(qn[0], qn[1]), pack2(qn[2], qn[3]), pack2(qn[4], qn[5]), pack2(qn[6], qn[7]));
 		}
 		// ---- tail (bsalign.h:2618-2636) ------------------------------------------------------------------
 		{
@@ -489,11 +492,11 @@ __global__ void __launch_bounds__(kFwdThreads) epi8_forward_kernel(const Epi8Arg
 		// ---- stream the finished row to the traceback store ---------------------------------------------
 		if(have){
 			uint8_t *dst = tr + (size_t)RS * (row + 1);
-			const uint32_t nch = S / 2; // 16-byte chunks per array image (8 regions of S bytes)
+			const uint32_t nch = IB / 16; // 16-byte pieces per array image
 			for(uint32_t c=t;c<nch;c+=kGroup){
 				*(uint4*)(dst + 16 * c) = *(const uint4*)(sU + 16 * c);
-				if(PW >= 1) *(uint4*)(dst + 8 * S + 16 * c) = *(const uint4*)(sE + 16 * c);
-				if(PW == 2) *(uint4*)(dst + 16 * S + 16 * c) = *(const uint4*)(sQ + 16 * c);
+				if(PW >= 1) *(uint4*)(dst + IB + 16 * c) = *(const uint4*)(sE + 16 * c);
+				if(PW == 2) *(uint4*)(dst + 2 * IB + 16 * c) = *(const uint4*)(sQ + 16 * c);
 			}
 			if(t < 5) *(uint4*)(meta + (size_t)kMetaInts * (row + 1) + 4 * t) = *(const uint4*)(sUB + 4 * t);
 		}
@@ -525,14 +528,14 @@ __global__ void __launch_bounds__(kFwdThreads) epi8_forward_kernel(const Epi8Arg
 		}
 		// ---- end-point candidates (bsalign.h:4022-4045) ---------------------------------------------------
 		if(mode != 0 && rbeg + bw >= qlen){
-			int sc = group_getscore(sU, sUB, S, W, qlen - 1 - rbeg, t);
+			int sc = group_getscore(sU, sUB, W, qlen - 1 - rbeg, t);
 			if(sc > best){ best = sc; best_qe = (int)qlen - 1; best_te = (int)row; }
 		}
 		row++;
 		if(have && row == tlen){
 			if(mode == 0){
 				uint32_t pos = qlen - 1 - rbeg;
-				if(pos < bw) best = group_getscore(sU, sUB, S, W, pos, t);
+				if(pos < bw) best = group_getscore(sU, sUB, W, pos, t);
 				else { best = kScoreMin; stflag |= 1; }
 				best_qe = (int)qlen - 1; best_te = (int)tlen - 1;
 			} else {
@@ -546,7 +549,7 @@ __global__ void __launch_bounds__(kFwdThreads) epi8_forward_kernel(const Epi8Arg
 					for(uint32_t c=0;c<nck;c++){
 						uint32_t lo = c * 32, hi = lo + 32 < W ? lo + 32 : W;
 						int run = 0, mx = -32767;
-						for(uint32_t i=lo;i<hi;i++){ run += p[2 * i]; if(run > mx) mx = run; }
+						for(uint32_t i=lo;i<hi;i++){ run += p[TOFF(i)]; if(run > mx) mx = run; }
 						int hh = Scr + mx;
 						if(hh > Max){ Max = hh; Idx = (uint32_t)j | (c << 8); }
 						Scr += run;
@@ -570,9 +573,8 @@ __global__ void __launch_bounds__(kFwdThreads) epi8_forward_kernel(const Epi8Arg
 				if(max_score > best){
 					uint32_t bl = bi & 0xff, bc = bi >> 8;
 					uint32_t x = bc * 32, y = (bc + 1) * 32 < W ? (bc + 1) * 32 : W;
-					const int8_t *p = sU + (size_t)(bl >> 1) * S + (bl & 1);
 					uint32_t pos = x; int umax = kScoreMin, uscr = 0;
-					for(;x<y;x++){ uscr += p[2 * x]; if(uscr > umax){ pos = x; umax = uscr; } }
+					for(;x<y;x++){ uscr += sU[epi8_cell_offset(bl, x)]; if(uscr > umax){ pos = x; umax = uscr; } }
 					best = max_score; best_qe = (int)(rbeg + bl * W + pos); best_te = (int)tlen - 1;
 				}
 				__syncwarp(gmask);
@@ -587,6 +589,7 @@ __global__ void __launch_bounds__(kFwdThreads) epi8_forward_kernel(const Epi8Arg
 		if(!have) mov = 0;
 	}
 	#undef QCODE
+	#undef TOFF
 }
 
 } // namespace bsb200

@@ -20,11 +20,11 @@ def rowdiff(ctx, q, t, mode, bw_req, mtx, gaps, maxshow=3):
     bw, pw = bw.value, pw.value
     tlen = len(t)
     W = bw // 16
-    S = (2 * W + 15) // 16 * 16
-    RS = 8 * S * (pw + 1)
-    rows = buf[:RS * (tlen + 1)].reshape(tlen + 1, pw + 1, 8 * S).view(np.int8)
+    IB = (W + 7) // 8 * 128
+    RS = IB * (pw + 1)
+    rows = buf[:RS * (tlen + 1)].reshape(tlen + 1, pw + 1, IB).view(np.int8)
     pp = np.arange(bw); jj = pp // W; ii = pp % W
-    idx = (jj >> 1) * S + 2 * ii + (jj & 1)
+    idx = (ii >> 3) * 128 + (jj >> 1) * 16 + (ii & 7) * 2 + (jj & 1)
     meta = buf[RS * (tlen + 1):RS * (tlen + 1) + 80 * (tlen + 1)].view(np.int32).reshape(tlen + 1, 20)
     res, begs, ub, u, e, qq = ck.rows_dump(ck.oracle(), "bso_epi8_pairwise_ex", q, t, mode, bw_req, mtx, gaps,
                                            extra_args=(None, ctypes.c_uint32(0), None))
