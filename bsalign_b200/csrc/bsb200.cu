@@ -357,6 +357,7 @@ extern "C" int bsb200_batch_run(bsb200_ctx *ctx, bsb200_batch *b){
 			// groups of a warp keep their small per-group words (anchors, F hand-over) on different banks
 			a.group_smem = (uint32_t)(((size_t)a.max_img * (b->pw + 2) + (kMetaInts * 2) * 4 + 32 + 32 * 4 + 127) / 128 * 128 + 32);
 			a.mode = b->mode; memcpy(a.mtx, b->mtx, 16); a.go1 = b->go1; a.ge1 = b->ge1; a.go2 = b->go2; a.ge2 = b->ge2;
+			a.all_ones = 0xffffffffu;
 			a.smax = -127; a.smin = 127;
 			for(int k=0;k<16;k++){ a.smax = std::max(a.smax, b->mtx[k]); a.smin = std::min(a.smin, b->mtx[k]); }
 			// all gap costs <= 0 (the normal case): saturation bounds that cannot bind are dropped (epi8_forward.cuh)

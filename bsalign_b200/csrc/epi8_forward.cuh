@@ -41,6 +41,7 @@ struct Epi8Args {
 	int8_t mtx[16];
 	int8_t go1, ge1, go2, ge2;
 	int8_t smax, smin;
+	uint32_t all_ones;           // 0xffffffff, passed at run time so that ~x can be issued as IMAD on the otherwise idle FMA pipe
 };
 
 // ---- saturating s16x2 arithmetic ------------------------------------------------------------------------
@@ -69,10 +70,13 @@ __device__ __forceinline__ uint32_t zsel(uint32_t cA, uint32_t cB){ return cA | 
 
 struct RowState { uint32_t f, g, h, u, nv; };
 
+// ~x = x * 0xffffffff + 0xffffffff (mod 2^32): an IMAD, i.e. FMA pipe, leaving the saturated ALU pipe to the DPX ops
+__device__ __forceinline__ uint32_t not_fma(uint32_t x, uint32_t m1){ return x * m1 + m1; }
+
 // one DP step for the thread's two lanes.  PASS2=false: only the F/G chain (pass 1).
 template<int PW, bool FAST, bool PASS2>
 __device__ __forceinline__ void dp_step(RowState &s, uint32_t u, uint32_t e, uint32_t q, uint32_t z,
-		uint32_t GE, uint32_t GOE, uint32_t GP, uint32_t GQP, uint32_t NGOQ, uint32_t &un, uint32_t &en, uint32_t &qn){
+		uint32_t GE, uint32_t GOE, uint32_t GP, uint32_t GQP, uint32_t NGOQ, uint32_t M1, uint32_t &un, uint32_t &en, uint32_t &qn){
 	uint32_t ev, qv = 0, h;
 	if(PW == 0) ev = FAST ? sadd_lo(u, GE) : sadd(u, GE);
 	else ev = FAST ? sadd_lo(e, u) : sadd(e, u);
@@ -80,21 +84,21 @@ __device__ __forceinline__ void dp_step(RowState &s, uint32_t u, uint32_t e, uin
 		qv = FAST ? sadd_lo(q, u) : sadd(q, u);
 		h = smax(smax3(ev, z, qv), smax(s.f, s.g));
 	} else h = smax3(ev, z, s.f);
-	const uint32_t cu = ~u;
+	const uint32_t cu = not_fma(u, M1);
 	if(PASS2){
-		const uint32_t ch = ~h;
+		const uint32_t ch = not_fma(h, M1);
 		un = sadd(h, s.nv);                                                    // u(x,y) = h - v(x-1,y)
 		s.nv = __viaddmin_s16x2(__viaddmax_s16x2(u, ch, kLO), kONE, 0x00800080u);  // -(subs(h,u)) = clamp(u - h, -127, 128)
 		if(PW >= 1){
 			if(FAST){
-				uint32_t x = sadd_lo(ev, GE);
-				en = __vadd2(__viaddmax_s16x2(x, ch, __vsub2(GOE, kONE)), kONE);       // max(x - h, goe)
+				uint32_t x1 = __viaddmax_s16x2(ev, __vadd2(GE, kONE), 0xff81ff81u);   // adds(ev, ge) + 1
+				en = __viaddmax_s16x2(x1, ch, GOE);                                   // max(x - h, goe): (x+1) + ~h = x - h
 			} else en = smax(ssubc(sadd(ev, GE), ch), GOE);
 		}
 		if(PW == 2){
 			if(FAST){
-				uint32_t x = sadd_lo(qv, GP);
-				qn = __vadd2(__viaddmax_s16x2(x, ch, __vsub2(GQP, kONE)), kONE);
+				uint32_t x1 = __viaddmax_s16x2(qv, __vadd2(GP, kONE), 0xff81ff81u);
+				qn = __viaddmax_s16x2(x1, ch, GQP);
 			} else qn = smax(ssubc(sadd(qv, GP), ch), GQP);
 		}
 		s.u = u;
@@ -153,6 +157,7 @@ __global__ void __launch_bounds__(kFwdThreads) epi8_forward_kernel(const Epi8Arg
 	const int go1 = a.go1, ge1 = a.ge1, go2 = a.go2, ge2 = a.ge2;
 	const int GOEi = (int8_t)(go1 + ge1), GQPi = (int8_t)(go2 + ge2);
 	const uint32_t GE = pk1(ge1), GOE = pk1(GOEi), GP = pk1(ge2), GQP = pk1(GQPi);
+	const uint32_t M1 = a.all_ones;
 	const uint32_t NGOE = pk1(-GOEi), NGOQ = pk1(-clamp8(GOEi - GQPi)), NGQP = pk1(-GQPi);
 	// matrix columns: colw[tb] holds mtx[0*4+tb], mtx[1*4+tb], mtx[2*4+tb], mtx[3*4+tb] as bytes
 	uint32_t colw[4];
@@ -404,25 +409,28 @@ __global__ void __launch_bounds__(kFwdThreads) epi8_forward_kernel(const Epi8Arg
 			if(h0 >= t0){ if(h0 > kEpi8Max) h0 = kEpi8Max; } else h0 = kEpi8Min;
 		}
 		const uint32_t zmask = t == 0 ? 0xffff0000u : 0xffffffffu, zor = t == 0 ? (uint32_t)(h0 & 0xffff) : 0u;
-		const uint32_t nchunk = (W + 7) / 8;
+		const uint32_t nchunk = (W + 7) / 8, nfull = W / 8;
 
 		// ---- pass 1: F (G) leaving every running block with nothing entering ------------------------
+		// (full chunks run without per-step guards; a ragged last chunk, W % 8 != 0, takes the guarded copy)
 		RowState st; st.f = pk1(kEpi8Min); st.g = pk1(kEpi8Min); st.h = 0; st.u = 0; st.nv = 0;
 		{
 			uint32_t dum0, dum1, dum2;
-			for(uint32_t c=0;c<nchunk;c++){
-				const uint4 cu4 = *(const uint4*)(rU + 128 * c), cs4 = *(const uint4*)(rC + 128 * c);
-				uint4 ce4 = cu4, cq4 = cu4;
-				if(PW >= 1) ce4 = *(const uint4*)(rE + 128 * c);
-				if(PW == 2) cq4 = *(const uint4*)(rQ + 128 * c);
-				const uint32_t left = W - 8 * c;
-				#define P1STEP(K) { if((K) == 0 || left > (K)){ \
-					uint32_t z = prmt(T32, 0xC1C1C1C1u, ent_sel<K>(cs4)); \
-					if((K) == 0 && c == 0) z = (z & zmask) | zor; \
-					dp_step<PW, FAST, false>(st, ent<K>(cu4), ent<K>(ce4), ent<K>(cq4), z, GE, GOE, GP, GQP, NGOQ, dum0, dum1, dum2); } }
-				P1STEP(0) P1STEP(1) P1STEP(2) P1STEP(3) P1STEP(4) P1STEP(5) P1STEP(6) P1STEP(7)
-				#undef P1STEP
-			}
+			#define P1STEP(K, LEFT) { if((K) < (LEFT)){ \
+				uint32_t z = prmt(T32, 0xC1C1C1C1u, ent_sel<K>(cs4)); \
+				if((K) == 0 && c == 0) z = (z & zmask) | zor; \
+				dp_step<PW, FAST, false>(st, ent<K>(cu4), ent<K>(ce4), ent<K>(cq4), z, GE, GOE, GP, GQP, NGOQ, M1, dum0, dum1, dum2); } }
+			#define P1CHUNK(LEFT) { \
+				const uint4 cu4 = *(const uint4*)(rU + 128 * c), cs4 = *(const uint4*)(rC + 128 * c); \
+				uint4 ce4 = cu4, cq4 = cu4; \
+				if(PW >= 1) ce4 = *(const uint4*)(rE + 128 * c); \
+				if(PW == 2) cq4 = *(const uint4*)(rQ + 128 * c); \
+				P1STEP(0, LEFT) P1STEP(1, LEFT) P1STEP(2, LEFT) P1STEP(3, LEFT) P1STEP(4, LEFT) P1STEP(5, LEFT) P1STEP(6, LEFT) P1STEP(7, LEFT) }
+			uint32_t c = 0;
+			for(;c<nfull;c++) P1CHUNK(8u)
+			if(c < nchunk){ const uint32_t left = W - 8 * c; P1CHUNK(left) }
+			#undef P1CHUNK
+			#undef P1STEP
 		}
 		sF[A] = (int8_t)lo16(st.f); sF[B] = (int8_t)hi16(st.f);
 		if(PW == 2){ sF[16 + A] = (int8_t)lo16(st.g); sF[16 + B] = (int8_t)hi16(st.g); }
@@ -450,25 +458,28 @@ __global__ void __launch_bounds__(kFwdThreads) epi8_forward_kernel(const Epi8Arg
 		// ---- pass 2: the row, written in place (bsalign.h:2934-2957 etc.) ------------------------------
 		uint32_t unew0 = 0;
 		st.nv = 0; st.h = 0; st.u = 0;
-		for(uint32_t c=0;c<nchunk;c++){
-			const uint4 cu4 = *(const uint4*)(rU + 128 * c), cs4 = *(const uint4*)(rC + 128 * c);
-			uint4 ce4 = cu4, cq4 = cu4;
-			if(PW >= 1) ce4 = *(const uint4*)(rE + 128 * c);
-			if(PW == 2) cq4 = *(const uint4*)(rQ + 128 * c);
-			const uint32_t left = W - 8 * c;
-			uint32_t un[8], en[8], qn[8];
-			#pragma unroll
-			for(int k=0;k<8;k++){ un[k] = 0; en[k] = 0; qn[k] = 0; }
-			#define P2STEP(K) { if((K) == 0 || left > (K)){ \
+		{
+			#define P2STEP(K, LEFT) { if((K) < (LEFT)){ \
 				uint32_t z = prmt(T32, 0xC1C1C1C1u, ent_sel<K>(cs4)); \
 				if((K) == 0 && c == 0) z = (z & zmask) | zor; \
-				dp_step<PW, FAST, true>(st, ent<K>(cu4), ent<K>(ce4), ent<K>(cq4), z, GE, GOE, GP, GQP, NGOQ, un[K], en[K], qn[K]); } }
-			P2STEP(0) P2STEP(1) P2STEP(2) P2STEP(3) P2STEP(4) P2STEP(5) P2STEP(6) P2STEP(7)
+				dp_step<PW, FAST, true>(st, ent<K>(cu4), ent<K>(ce4), ent<K>(cq4), z, GE, GOE, GP, GQP, NGOQ, M1, un[K], en[K], qn[K]); } }
+			#define P2CHUNK(LEFT, RAGGED) { \
+				const uint4 cu4 = *(const uint4*)(rU + 128 * c), cs4 = *(const uint4*)(rC + 128 * c); \
+				uint4 ce4 = cu4, cq4 = cu4; \
+				if(PW >= 1) ce4 = *(const uint4*)(rE + 128 * c); \
+				if(PW == 2) cq4 = *(const uint4*)(rQ + 128 * c); \
+				uint32_t un[8], en[8], qn[8]; \
+				if(RAGGED){ _Pragma("unroll") for(int k=0;k<8;k++){ un[k] = 0; en[k] = 0; qn[k] = 0; } } \
+				P2STEP(0, LEFT) P2STEP(1, LEFT) P2STEP(2, LEFT) P2STEP(3, LEFT) P2STEP(4, LEFT) P2STEP(5, LEFT) P2STEP(6, LEFT) P2STEP(7, LEFT) \
+				if(c == 0) unew0 = un[0]; \
+				*(uint4*)(rU + 128 * c) = make_uint4(pack2(un[0], un[1]), pack2(un[2], un[3]), pack2(un[4], un[5]), pack2(un[6], un[7])); \
+				if(PW >= 1) *(uint4*)(rE + 128 * c) = make_uint4(pack2(en[0], en[1]), pack2(en[2], en[3]), pack2(en[4], en[5]), pack2(en[6], en[7])); \
+				if(PW == 2) *(uint4*)(rQ + 128 * c) = make_uint4(pack2(qn[0], qn[1]), pack2(qn[2], qn[3]), pack2(qn[4], qn[5]), pack2(qn[6], qn[7])); }
+			uint32_t c = 0;
+			for(;c<nfull;c++) P2CHUNK(8u, false)
+			if(c < nchunk){ const uint32_t left = W - 8 * c; P2CHUNK(left, true) }
+			#undef P2CHUNK
 			#undef P2STEP
-			if(c == 0) unew0 = un[0];
-			*(uint4*)(rU + 128 * c) = make_uint4(pack2(un[0], un[1]), pack2(un[2], un[3]), pack2(un[4], un[5]), pack2(un[6], un[7]));
-			if(PW >= 1) *(uint4*)(rE + 128 * c) = make_uint4(pack2(en[0], en[1]), pack2(en[2], en[3]), pack2(en[4], en[5]), pack2(en[6], en[7]));
-			if(PW == 2) *(uint4*)(rQ + 128 * c) = make_uint4(pack2(qn[0], qn[1]), pack2(qn[2], qn[3]), pack2(qn[4], qn[5]), pack2(qn[6], qn[7]));
 		}
 		// ---- tail (bsalign.h:2618-2636) ------------------------------------------------------------------
 		{
