@@ -1,0 +1,95 @@
+/*
+ * bsalign_b200_compat.h -- GNU-C drop-in for the two pairwise entry points of ruanjue/bsalign, re-bodied on
+ * top of libbsalign_b200.so (C ABI: bsalign_b200.h).
+ *
+ * Usage in a program that already uses the reference library (README.md:51-80 of the reference):
+ *
+ *     #include "bsalign.h"                 // the reference's own header: types, cigar helpers, printing
+ *     #include "bsalign_b200_compat.h"     // after it
+ *     ...
+ *     rs = b200_banded_striped_epi8_seqalign_pairwise(qseq, qlen, tseq, tlen, mempool, cigars,
+ *                                                     mode, bandwidth, matrix, gapo1, gape1, gapo2, gape2, verbose);
+ *
+ * or compile with -DBSALIGN_B200_OVERRIDE to have the reference NAMES themselves routed to the GPU
+ * (the macros below rename every later use of the two functions).  Signatures, the by-value
+ * seqalign_result_t, the u4v cigar vector (cleared, or appended to under SEQALIGN_MODE_CIGRESV) and the
+ * "all-zero result for an empty edit input" rule are the reference's (bsalign.h:399, :232, :3713-3719,
+ * :1051-1054).  `mempool` is accepted and ignored: scratch lives in HBM.  `verbose` is ignored.
+ * Programmer errors keep the reference's behaviour: message on stderr + abort().
+ *
+ * One pair per call pays a host<->device round trip; throughput needs the batch entry points of
+ * bsalign_b200.h (see INTEGRATION.md for the main.c loop rewritten on top of them).
+ */
+#ifndef BSALIGN_B200_COMPAT_H
+#define BSALIGN_B200_COMPAT_H
+
+#include "bsalign_b200.h"
+
+#ifndef BAND_STRIPED_DNA_SEQ_ALIGNMENT_RJ_H
+#error "include the reference's bsalign.h before bsalign_b200_compat.h"
+#endif
+
+static bsb200_ctx *bsalign_b200_default_ctx(void){
+	static bsb200_ctx *ctx = NULL;
+	if(ctx == NULL){
+		ctx = bsb200_create(0, 0);
+		if(ctx == NULL){
+			fflush(stdout); fprintf(stderr, " -- bsalign_b200: no CUDA device, and there is no CPU fallback in %s -- %s:%d --\n", __FUNCTION__, __FILE__, __LINE__); fflush(stderr);
+			abort();
+		}
+	}
+	return ctx;
+}
+
+static inline void bsalign_b200_take_cigars(u4v *cigars, int mode, const uint32_t *buf, uint32_t n){
+	uint32_t i;
+	if(cigars == NULL) return;
+	if(!(mode & SEQALIGN_MODE_CIGRESV)) clear_u4v(cigars);
+	for(i=0;i<n;i++) push_u4v(cigars, buf[i]);
+}
+
+static inline seqalign_result_t b200_banded_striped_epi8_seqalign_pairwise(u1i *qseq, u4i qlen, u1i *tseq, u4i tlen, b1v *mempool, u4v *cigars,
+		int mode, u4i bandwidth, b1i matrix[16], b1i gapo1, b1i gape1, b1i gapo2, b1i gape2, int verbose){
+	seqalign_result_t rs;
+	bsb200_result_t r;
+	uint32_t *buf, n = 0;
+	int32_t st = 0;
+	UNUSED(mempool); UNUSED(verbose);
+	buf = cigars? (uint32_t*)malloc(sizeof(uint32_t) * ((size_t)qlen + tlen + 2)) : NULL;
+	if(bsb200_epi8_pairwise(bsalign_b200_default_ctx(), qseq, qlen, tseq, tlen, seqalign_mode_type(mode), bandwidth, (const int8_t*)matrix,
+			gapo1, gape1, gapo2, gape2, &r, buf, qlen + tlen + 2, &n, &st)){
+		fflush(stdout); fprintf(stderr, " -- bsalign_b200: %s in %s -- %s:%d --\n", bsb200_last_error(bsalign_b200_default_ctx()), __FUNCTION__, __FILE__, __LINE__); fflush(stderr);
+		abort();
+	}
+	rs.score = r.score; rs.qb = r.qb; rs.qe = r.qe; rs.tb = r.tb; rs.te = r.te;
+	rs.mat = r.mat; rs.mis = r.mis; rs.ins = r.ins; rs.del = r.del; rs.aln = r.aln;
+	bsalign_b200_take_cigars(cigars, mode, buf, n);
+	if(buf) free(buf);
+	return rs;
+}
+
+static inline seqalign_result_t b200_striped_seqedit_pairwise(u1i *qseq, u4i qlen, u1i *tseq, u4i tlen, int mode, u4i bandwidth, b1v *mempool, u4v *cigars, int verbose){
+	seqalign_result_t rs;
+	bsb200_result_t r;
+	uint32_t *buf, n = 0;
+	int32_t st = 0;
+	UNUSED(mempool); UNUSED(verbose);
+	if(qlen == 0 || tlen == 0){ memset(&rs, 0, sizeof(seqalign_result_t)); return rs; } /* bsalign.h:1051-1054 */
+	buf = cigars? (uint32_t*)malloc(sizeof(uint32_t) * ((size_t)qlen + tlen + 2)) : NULL;
+	if(bsb200_edit_pairwise(bsalign_b200_default_ctx(), qseq, qlen, tseq, tlen, seqalign_mode_type(mode), bandwidth, &r, buf, qlen + tlen + 2, &n, &st)){
+		fflush(stdout); fprintf(stderr, " -- bsalign_b200: %s in %s -- %s:%d --\n", bsb200_last_error(bsalign_b200_default_ctx()), __FUNCTION__, __FILE__, __LINE__); fflush(stderr);
+		abort();
+	}
+	rs.score = r.score; rs.qb = r.qb; rs.qe = r.qe; rs.tb = r.tb; rs.te = r.te;
+	rs.mat = r.mat; rs.mis = r.mis; rs.ins = r.ins; rs.del = r.del; rs.aln = r.aln;
+	bsalign_b200_take_cigars(cigars, mode, buf, n);
+	if(buf) free(buf);
+	return rs;
+}
+
+#ifdef BSALIGN_B200_OVERRIDE
+#define banded_striped_epi8_seqalign_pairwise b200_banded_striped_epi8_seqalign_pairwise
+#define striped_seqedit_pairwise b200_striped_seqedit_pairwise
+#endif
+
+#endif

@@ -112,14 +112,17 @@ def rows_dump(lib, fname, q, t, mode, bandwidth, mtx, gaps, extra_args=()):
     return res, begs, ub, u, e, qq
 
 
-def forked(fn, *args, **kw):
-    """Run fn in a forked child so that a crash of the checker (the reference reads out of bounds on some
-    adversarial inputs) is reported as None instead of killing the test process."""
+def forked(fn, *args, timeout_s=120, **kw):
+    """Run fn in a forked child so that a crash or a hang of the checker (the reference reads out of bounds, or
+    never leaves its traceback loop, on some adversarial inputs) is reported as None instead of taking the
+    test process with it."""
     import pickle
+    import signal
     r, w = os.pipe()
     pid = os.fork()
     if pid == 0:
         os.close(r)
+        signal.alarm(int(timeout_s))
         try:
             data = pickle.dumps(fn(*args, **kw))
             with os.fdopen(w, "wb") as f:

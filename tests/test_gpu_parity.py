@@ -1,0 +1,188 @@
+"""GPU parity tests (-m gpu): the CUDA path, called through the C ABI (bsalign_b200.api -> libbsalign_b200.so),
+against the oracle on the same seeded inputs, against the committed golden vectors, and - at BASELINE.json's
+batch shapes - through size-independent properties.  Bar: bit-exact (score, coordinates, counts, CIGAR words)."""
+import os
+
+import numpy as np
+import pytest
+
+import checkers as ck
+from bsalign_b200 import api, synth
+from test_oracle import load_golden, golden_cases, _random_pairs
+
+pytestmark = pytest.mark.gpu
+
+M26 = synth.score_matrix(2, -6)
+
+
+@pytest.fixture(scope="module")
+def ctx():
+    c = api.Context(0)
+    yield c
+    c.close()
+
+
+def assert_same(got, exp_res, exp_cigs, errs=None, tag=""):
+    gc = got.cigars()
+    for i in range(len(exp_res)):
+        if errs is not None and errs[i]:
+            assert got.status[i] != 0, (tag, i, "oracle flags reference-UB but the GPU status is clean")
+            continue
+        assert got.status[i] == 0, (tag, i, int(got.status[i]))
+        assert np.array_equal(got.results[i], exp_res[i]), (tag, i, got.results[i], exp_res[i])
+        assert np.array_equal(gc[i], exp_cigs[i]), (tag, i)
+
+
+@pytest.mark.parametrize("gaps", [(-3, -2, 0, 0), (0, -2, 0, 0), (-3, -2, -8, -1)], ids=["affine", "linear", "twopiece"])
+@pytest.mark.parametrize("mode", [0, 1, 2], ids=["global", "overlap", "extend"])
+def test_epi8_matches_oracle(ctx, mode, gaps):
+    for bw in (0, 16, 64, 128):
+        b = synth.make_pairs(48, 300, seed=mode * 100 + bw)
+        exp, ecg, _ = ck.oracle_batch("epi8", b, mode, bw, M26, gaps)
+        assert_same(ctx.epi8_batch(b, mode, bw, M26, *gaps), exp, ecg, tag=(mode, bw, gaps))
+
+
+@pytest.mark.parametrize("mode", [0, 1, 2], ids=["global", "overlap", "extend"])
+def test_edit_matches_oracle(ctx, mode):
+    for bw in (0, 64, 128, 256):
+        b = synth.make_pairs(128, 300, seed=7 + mode * 10 + bw, p_sub=0.02, p_ins=0.02, p_del=0.02)
+        exp, ecg, _ = ck.oracle_batch("edit", b, mode, bw)
+        assert_same(ctx.edit_batch(b, mode, bw), exp, ecg, tag=(mode, bw))
+
+
+def test_golden_vectors(ctx):
+    z, batch = load_golden("epi8_golden.npz")
+    n = 0
+    for ci, cfg, valid, res, cigs in golden_cases(z, "epi8"):
+        mode, bw, M, X, go1, ge1, go2, ge2 = cfg
+        got = ctx.epi8_batch(batch, mode, bw, synth.score_matrix(M, X), go1, ge1, go2, ge2)
+        gc = got.cigars()
+        for i in np.nonzero(valid)[0]:
+            assert np.array_equal(got.results[i], res[i]) and np.array_equal(gc[i], cigs[i]), (cfg, int(i))
+            n += 1
+    z, batch = load_golden("edit_golden.npz")
+    for ci, cfg, valid, res, cigs in golden_cases(z, "edit"):
+        got = ctx.edit_batch(batch, cfg[0], cfg[1])
+        gc = got.cigars()
+        for i in np.nonzero(valid)[0]:
+            assert np.array_equal(got.results[i], res[i]) and np.array_equal(gc[i], cigs[i]), (cfg, int(i))
+            n += 1
+    assert n > 1200
+
+
+def test_readme_example(ctx):
+    z = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "readme_pair.npz"))
+    rs, cg, st = api.banded_striped_epi8_seqalign_pairwise(z["q"], z["t"], api.SEQALIGN_MODE_OVERLAP, int(z["bandwidth"]),
+                                                           api.banded_striped_epi8_seqalign_set_score_matrix(2, -2), -4, -2, 0, 0, ctx=ctx)
+    assert st == 0 and rs["score"] == 128 and rs["mat"] == 71 and rs["mis"] == 4
+    assert np.array_equal(cg, z["cig"]) and [rs[k] for k in api.RESULT_FIELDS] == list(z["res"])
+
+
+def test_baseline_config_shapes(ctx):
+    """configs[0] (single 1 kb pair, global, band 128), config 2/3/4 shapes at oracle-sized counts."""
+    b = synth.make_pairs(1, 1000, seed=42)
+    exp, ecg, _ = ck.oracle_batch("epi8", b, 0, 128, M26, (-3, -2, 0, 0))
+    assert_same(ctx.epi8_batch(b, 0, 128, M26, -3, -2, 0, 0), exp, ecg, tag="c1")
+    b = synth.make_pairs(200, 1000, seed=1000)
+    exp, ecg, _ = ck.oracle_batch("epi8", b, 0, 0, M26, (-3, -2, 0, 0), nthreads=8)
+    assert_same(ctx.epi8_batch(b, 0, 0, M26, -3, -2, 0, 0), exp, ecg, tag="c2")
+    b = synth.make_pairs(12, 10000, 2000, *synth.ont_like(0.12))
+    exp, ecg, _ = ck.oracle_batch("epi8", b, 1, 512, M26, (-3, -2, 0, 0), nthreads=8)
+    assert_same(ctx.epi8_batch(b, 1, 512, M26, -3, -2, 0, 0), exp, ecg, tag="c3")
+    b = synth.make_pairs(3000, 300, 3000, 0.02, 0.02, 0.02)
+    exp, ecg, _ = ck.oracle_batch("edit", b, 0, 64, nthreads=8)
+    assert_same(ctx.edit_batch(b, 0, 64), exp, ecg, tag="c4")
+
+
+def test_adversarial_and_reference_ub_flags(ctx):
+    """Tiny, ragged, unrelated, long-indel and homopolymer pairs with odd bands and saturating scores.  Pairs on
+    which the reference reads out of bounds / never terminates must come back flagged, all others bit-exact."""
+    rng = np.random.default_rng(5)
+    params = [((2, -6), (-3, -2, 0, 0)), ((2, -6), (-3, -2, -8, -1)), ((30, -40), (-40, -20, 0, 0)), ((5, -4), (-10, -1, 0, 0)), ((1, -1), (0, -1, 0, 0))]
+    for it in range(10):
+        b = _random_pairs(rng, 32, *[(1, 17), (20, 120), (100, 500), (300, 900)][it % 4], 0.2)
+        (Mv, Xv), gaps = params[it % len(params)]
+        mtx = synth.score_matrix(Mv, Xv)
+        for mode in (0, 1, 2):
+            bw = int(rng.choice([0, 16, 48, 128, 1024]))
+            errs = np.zeros(b.n, np.int32)
+            exp, ecg, _ = ck.oracle_batch("epi8", b, mode, bw, mtx, gaps, errs=errs)
+            assert_same(ctx.epi8_batch(b, mode, bw, mtx, *gaps), exp, ecg, errs=errs, tag=("epi8", it, mode, bw))
+            bwe = int(rng.choice([0, 1, 64, 192]))
+            errs = np.zeros(b.n, np.int32)
+            exp, ecg, _ = ck.oracle_batch("edit", b, mode, bwe, errs=errs)
+            assert_same(ctx.edit_batch(b, mode, bwe), exp, ecg, errs=errs, tag=("edit", it, mode, bwe))
+
+
+def test_empty_pairs_and_mixed_lengths(ctx):
+    pairs = [(np.zeros(0, np.uint8), np.array([1, 2, 3], np.uint8)), (np.array([0, 1, 2, 3] * 20, np.uint8), np.array([0, 1, 2, 3] * 19, np.uint8)),
+             (np.array([2], np.uint8), np.zeros(0, np.uint8)), (np.array([1], np.uint8), np.array([1], np.uint8))]
+    b = synth.PairBatch.from_lists(pairs)
+    for kind in ("epi8", "edit"):
+        exp, ecg, _ = ck.oracle_batch(kind, b, 0, 0, M26, (-3, -2, 0, 0))
+        got = ctx.epi8_batch(b, 0, 0, M26, -3, -2, 0, 0) if kind == "epi8" else ctx.edit_batch(b, 0, 0)
+        assert got.status[0] == api.ST_EMPTY and got.status[2] == api.ST_EMPTY and not got.results[0].any()
+        for i in (1, 3):
+            assert np.array_equal(got.results[i], exp[i]) and np.array_equal(got.cigar(i), ecg[i])
+
+
+def test_waves_and_single_pair_api_agree(ctx):
+    """A trace budget that forces several waves, and the single-pair entry point, give the one-wave answer."""
+    b = synth.make_pairs(300, 400, seed=77)
+    one = ctx.epi8_batch(b, 0, 0, M26, -3, -2, 0, 0)
+    small = api.Context(0, trace_budget_bytes=40 << 20)
+    many = small.epi8_batch(b, 0, 0, M26, -3, -2, 0, 0)
+    assert small.timing()["waves"] > 1
+    assert np.array_equal(one.results, many.results) and np.array_equal(one.ncigar, many.ncigar)
+    assert all(np.array_equal(x, y) for x, y in zip(one.cigars(), many.cigars()))
+    small.close()
+    rs, cg, st = api.banded_striped_epi8_seqalign_pairwise(b.query(5), b.target(5), 0, 0, M26, -3, -2, 0, 0, ctx=ctx)
+    assert [rs[k] for k in api.RESULT_FIELDS] == list(one.results[5]) and np.array_equal(cg, one.cigar(5))
+
+
+def cigar_score(q, t, res, cig, mtx, go, ge):
+    """Affine score of the path a CIGAR describes (global): independent of the DP."""
+    x, y, s = int(res[1]), int(res[3]), 0
+    for w in cig:
+        op, ln = int(w) & 15, int(w) >> 4
+        if op == 0:
+            s += int(mtx[q[x:x + ln].astype(np.int64) * 4 + t[y:y + ln]].sum()); x += ln; y += ln
+        elif op == 1:
+            s += go + ge * ln; x += ln
+        else:
+            s += go + ge * ln; y += ln
+    return s, x, y
+
+
+def test_full_size_properties(ctx):
+    """BASELINE config 2 shape at 20k pairs (beyond what the oracle finishes in seconds): every CIGAR must be a
+    complete global path whose affine score equals the reported score, counts must add up, and a second run must
+    reproduce the first bit for bit.  Config 4 shape at 200k pairs: edit score = mismatches + indels."""
+    b = synth.make_pairs(20000, 1000, seed=1234)
+    r1 = ctx.epi8_batch(b, 0, 0, M26, -3, -2, 0, 0)
+    r2 = ctx.epi8_batch(b, 0, 0, M26, -3, -2, 0, 0)
+    assert np.array_equal(r1.results, r2.results) and np.array_equal(r1.cigar_arena, r2.cigar_arena)
+    res = r1.results
+    assert not r1.status.any()
+    assert np.array_equal(res[:, 9], res[:, 5] + res[:, 6] + res[:, 7] + res[:, 8])
+    assert np.array_equal(res[:, 2] - res[:, 1], res[:, 5] + res[:, 6] + res[:, 7])
+    assert np.array_equal(res[:, 4] - res[:, 3], res[:, 5] + res[:, 6] + res[:, 8])
+    assert (res[:, 1] == 0).all() and (res[:, 3] == 0).all() and np.array_equal(res[:, 2], b.qlen.astype(np.int32)) and np.array_equal(res[:, 4], b.tlen.astype(np.int32))
+    for i in range(0, b.n, 97):
+        s, x, y = cigar_score(b.query(i), b.target(i), res[i], r1.cigar(i), M26, -3, -2)
+        assert (s, x, y) == (int(res[i, 0]), int(b.qlen[i]), int(b.tlen[i])), i
+    sub = np.arange(0, b.n, 400)
+    exp, ecg, _ = ck.oracle_batch("epi8", b.subset(sub), 0, 0, M26, (-3, -2, 0, 0), nthreads=8)
+    for k, i in enumerate(sub):
+        assert np.array_equal(res[i], exp[k]) and np.array_equal(r1.cigar(i), ecg[k])
+    b = synth.make_pairs(200000, 300, seed=4321, p_sub=0.02, p_ins=0.02, p_del=0.02)
+    e1 = ctx.edit_batch(b, 0, 64)
+    res = e1.results
+    assert not e1.status.any()
+    assert np.array_equal(res[:, 0], res[:, 6] + res[:, 7] + res[:, 8])
+    assert np.array_equal(res[:, 2] - res[:, 1], res[:, 5] + res[:, 6] + res[:, 7])
+    assert np.array_equal(res[:, 4] - res[:, 3], res[:, 5] + res[:, 6] + res[:, 8])
+    sub = np.arange(0, b.n, 2000)
+    exp, ecg, _ = ck.oracle_batch("edit", b.subset(sub), 0, 64, nthreads=8)
+    for k, i in enumerate(sub):
+        assert np.array_equal(res[i], exp[k]) and np.array_equal(e1.cigar(i), ecg[k])
