@@ -210,7 +210,7 @@ def main():
     hb = synth.PairBatch.__new__(synth.PairBatch)
     hb.seqs, hb.qoff, hb.qlen, hb.toff, hb.tlen = pin(batch.seqs), pin(batch.qoff), pin(batch.qlen), pin(batch.toff), pin(batch.tlen)
     ctx = api.Context(local_rank)
-    out = api._alloc_out(hb, True)
+    out = tuple(pin(a) if a is not None else None for a in api._alloc_out(hb, True))   # pinned result / cigar arenas
 
     def one_e2e():
         if w["kind"] == "epi8":
@@ -248,10 +248,13 @@ def main():
     barrier()
     t0 = time.perf_counter()
     h2d = d2h = 0
+    e2e_parts = {"h2d_ms": 0.0, "run_ms": 0.0, "d2h_ms": 0.0}
     for _ in range(args.steps):
         r = one_e2e()
         tm2 = ctx.timing()
         h2d, d2h = tm2["h2d_bytes"], tm2["d2h_bytes"]
+        for k in e2e_parts:
+            e2e_parts[k] += tm2[k] / args.steps
     barrier()
     e2e_ms = max_over_ranks((time.perf_counter() - t0) / args.steps * 1e3)
     e2e_val = total_cells / (e2e_ms * 1e-3) / 1e9
@@ -305,7 +308,8 @@ def main():
             "config": {"workload": "%s: %s" % (args.workload, w["desc"]), "pairs_per_gpu": pairs, "matrix": MATRIX, "gaps": GAPS,
                        "l2": "inputs (%.0f MB) and the %.1f GB traceback store written per step both exceed the 126 MB L2" % (batch.seqs.nbytes / 1e6, trace_bytes / 1e9),
                        "timing": "CUDA events on the library stream; max over ranks", "wall_ms_per_step": wall / args.steps * 1e3},
-            "e2e": {"value": e2e_val, "unit": "GCUPS", "ms_per_step": e2e_ms, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h)},
+            "e2e": {"value": e2e_val, "unit": "GCUPS", "ms_per_step": e2e_ms, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
+                    "device_parts_ms": e2e_parts, "host_planning_and_scatter_ms": e2e_ms - sum(e2e_parts.values())},
             "gpu_launches": int(fwd_launches + bt_launches),
             "roofline": roofline, "cpu_baseline": cpu, "clocks": clocks,
             "parity": {"nonzero_status_pairs": bad_status, "score_checksum": checksum, "checked": checked},

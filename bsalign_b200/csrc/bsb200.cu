@@ -63,6 +63,10 @@ struct bsb200_ctx {
 	bsb200_timing_t timing = {};
 	DevBuf trace;       // shared by all batches of this context (one batch runs at a time)
 	DevBuf counter;
+	// allocations of finished batches are parked here and handed to the next batch (cudaMalloc/cudaFree and pinned
+	// allocations cost more than the kernels of a small batch)
+	DevBuf dev_cache[16];
+	HostBuf host_cache[8];
 };
 
 struct Wave { uint32_t beg, end; uint64_t trace_bytes; };
@@ -126,6 +130,8 @@ extern "C" void bsb200_destroy(bsb200_ctx *ctx){
 	cudaSetDevice(ctx->device);
 	cudaStreamSynchronize(ctx->stream);
 	ctx->trace.release(); ctx->counter.release();
+	for(auto &d : ctx->dev_cache) d.release();
+	for(auto &h : ctx->host_cache) h.release();
 	for(auto &e : ctx->ev) cudaEventDestroy(e);
 	cudaStreamDestroy(ctx->stream);
 	delete ctx;
@@ -155,6 +161,13 @@ extern "C" bsb200_batch *bsb200_batch_upload(bsb200_ctx *ctx, int kind, uint64_t
 	}
 	cudaSetDevice(ctx->device);
 	bsb200_batch *b = new bsb200_batch();
+	{
+		DevBuf *ds[] = {&b->d_seqs, &b->d_qoff, &b->d_toff, &b->d_qlen, &b->d_tlen, &b->d_order, &b->d_trace_off, &b->d_results, &b->d_status,
+			&b->d_ncigar, &b->d_cig_raw, &b->d_cig_off, &b->d_cig_dense, &b->d_dense_off, &b->d_dense_total, &b->d_block_rows};
+		for(int k=0;k<16;k++){ *ds[k] = ctx->dev_cache[k]; ctx->dev_cache[k] = DevBuf(); }
+		HostBuf *hs[] = {&b->h_results, &b->h_status, &b->h_ncigar, &b->h_dense_off, &b->h_dense, &b->h_total};
+		for(int k=0;k<6;k++){ *hs[k] = ctx->host_cache[k]; ctx->host_cache[k] = HostBuf(); }
+	}
 	b->kind = kind; b->n = n; b->mode = mode & 3; b->bandwidth = bandwidth; b->want_cigar = want_cigar;
 	if(kind == 0){
 		memcpy(b->mtx, matrix, 16); b->go1 = go1; b->ge1 = ge1; b->go2 = go2; b->ge2 = ge2;
@@ -188,8 +201,26 @@ extern "C" bsb200_batch *bsb200_batch_upload(bsb200_ctx *ctx, int kind, uint64_t
 	}
 	b->seq_bytes = seq_end;
 	const uint32_t nact = (uint32_t)b->order.size();
-	if(kind == 0) std::stable_sort(b->order.begin(), b->order.end(), [&](uint32_t x, uint32_t y){ return work[x] > work[y]; });
-	else std::stable_sort(b->order.begin(), b->order.end(), [&](uint32_t x, uint32_t y){ return tlen[x] > tlen[y]; });
+	{
+		// heaviest first (epi8: band cells; edit: target length, so the 32 pairs of a warp finish together); counting
+		// sort when the key range is small, else one sort of packed (key, index) words
+		uint64_t kmax = 0;
+		std::vector<uint64_t> key(nact);
+		for(uint32_t k=0;k<nact;k++){ uint32_t i = b->order[k]; key[k] = kind == 0 ? work[i] : (uint64_t)tlen[i]; kmax = std::max(kmax, key[k]); }
+		if(kmax < (1u << 22)){
+			std::vector<uint32_t> cnt(kmax + 2, 0);
+			for(uint32_t k=0;k<nact;k++) cnt[kmax - key[k] + 1]++;
+			for(uint64_t v=1;v<cnt.size();v++) cnt[v] += cnt[v - 1];
+			std::vector<uint32_t> sorted(nact);
+			for(uint32_t k=0;k<nact;k++) sorted[cnt[kmax - key[k]]++] = b->order[k];
+			b->order.swap(sorted);
+		} else {
+			std::vector<std::pair<uint64_t, uint32_t>> kv(nact);
+			for(uint32_t k=0;k<nact;k++) kv[k] = std::make_pair(~key[k], b->order[k]);
+			std::sort(kv.begin(), kv.end());
+			for(uint32_t k=0;k<nact;k++) b->order[k] = kv[k].second;
+		}
+	}
 	uint64_t budget = ctx->trace_budget;
 	if(budget == 0){
 		size_t fr = 0, tot = 0;
@@ -203,7 +234,7 @@ extern "C" bsb200_batch *bsb200_batch_upload(bsb200_ctx *ctx, int kind, uint64_t
 		Wave w = {0, 0, 0};
 		for(uint32_t k=0;k<nact;k++){
 			uint32_t i = b->order[k];
-			if(tbytes[i] > budget){ ctx->err = "a single pair needs more traceback memory than the budget"; delete b; return nullptr; }
+			if(tbytes[i] > budget){ ctx->err = "a single pair needs more traceback memory than the budget"; bsb200_batch_free(ctx, b); return nullptr; }
 			if(w.trace_bytes + tbytes[i] > budget && w.end > w.beg){
 				b->waves.push_back(w);
 				w.beg = w.end; w.trace_bytes = 0;
@@ -224,7 +255,7 @@ extern "C" bsb200_batch *bsb200_batch_upload(bsb200_ctx *ctx, int kind, uint64_t
 			for(uint32_t k=lo;k<hi;k++) mt = std::max(mt, tlen[b->order[k]]);
 			uint64_t R = (uint64_t)mt + 1;
 			uint64_t bytes = R * WB * 2 * 32 * 8 + R * 32 * 4;
-			if(bytes > budget){ ctx->err = "a single block of pairs needs more traceback memory than the budget"; delete b; return nullptr; }
+			if(bytes > budget){ ctx->err = "a single block of pairs needs more traceback memory than the budget"; bsb200_batch_free(ctx, b); return nullptr; }
 			if(w.trace_bytes + bytes > budget && w.end > w.beg){
 				b->waves.push_back(w);
 				w.beg = w.end; w.trace_bytes = 0;
@@ -432,7 +463,7 @@ extern "C" int bsb200_batch_fetch(bsb200_ctx *ctx, bsb200_batch *b, bsb200_resul
 	const bool cg = b->want_cigar && cigars && cgoff;
 	CK(b->h_results.reserve(n * 40)); CK(b->h_status.reserve(n * 4)); CK(b->h_ncigar.reserve(n * 4)); CK(b->h_total.reserve(16));
 	cudaEventRecord(ctx->ev[2], st);
-	CK(cudaMemcpyAsync(b->h_results.p, b->d_results.p, n * 40, cudaMemcpyDeviceToHost, st));
+	CK(cudaMemcpyAsync(results ? (void*)results : b->h_results.p, b->d_results.p, n * 40, cudaMemcpyDeviceToHost, st));
 	CK(cudaMemcpyAsync(b->h_status.p, b->d_status.p, n * 4, cudaMemcpyDeviceToHost, st));
 	CK(cudaMemcpyAsync(b->h_ncigar.p, b->d_ncigar.p, n * 4, cudaMemcpyDeviceToHost, st));
 	uint64_t d2h = n * 48;
@@ -452,7 +483,6 @@ extern "C" int bsb200_batch_fetch(bsb200_ctx *ctx, bsb200_batch *b, bsb200_resul
 	float ms = 0; cudaEventElapsedTime(&ms, ctx->ev[2], ctx->ev[3]);
 	ctx->timing.d2h_ms = ms; ctx->timing.d2h_bytes = d2h;
 	{ int32_t *hs0 = b->h_status.as<int32_t>(); for(uint64_t i=0;i<n;i++) if(b->empty[i]) hs0[i] |= BSB200_ST_EMPTY; }
-	if(results) memcpy(results, b->h_results.p, n * 40);
 	if(status) memcpy(status, b->h_status.p, n * 4);
 	const uint32_t *hn = b->h_ncigar.as<uint32_t>();
 	if(ncigar) memcpy(ncigar, hn, n * 4);
@@ -475,9 +505,14 @@ extern "C" void bsb200_batch_free(bsb200_ctx *ctx, bsb200_batch *b){
 	if(ctx){ cudaSetDevice(ctx->device); cudaStreamSynchronize(ctx->stream); }
 	DevBuf *ds[] = {&b->d_seqs, &b->d_qoff, &b->d_toff, &b->d_qlen, &b->d_tlen, &b->d_order, &b->d_trace_off, &b->d_results, &b->d_status,
 		&b->d_ncigar, &b->d_cig_raw, &b->d_cig_off, &b->d_cig_dense, &b->d_dense_off, &b->d_dense_total, &b->d_block_rows};
-	for(auto d : ds) d->release();
 	HostBuf *hs[] = {&b->h_results, &b->h_status, &b->h_ncigar, &b->h_dense_off, &b->h_dense, &b->h_total};
-	for(auto h : hs) h->release();
+	if(ctx){ // park the allocations for the next batch (a cache slot that is still occupied keeps the larger buffer)
+		for(int k=0;k<16;k++){ if(ctx->dev_cache[k].cap < ds[k]->cap){ ctx->dev_cache[k].release(); ctx->dev_cache[k] = *ds[k]; } else ds[k]->release(); }
+		for(int k=0;k<6;k++){ if(ctx->host_cache[k].cap < hs[k]->cap){ ctx->host_cache[k].release(); ctx->host_cache[k] = *hs[k]; } else hs[k]->release(); }
+	} else {
+		for(auto d : ds) d->release();
+		for(auto h : hs) h->release();
+	}
 	delete b;
 }
 

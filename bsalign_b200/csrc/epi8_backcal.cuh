@@ -39,9 +39,11 @@ struct TraceView {
 		return (int)(int8_t)tr[(size_t)RS * (row + 1) + (size_t)arr * IB + epi8_cell_offset(j, i)];
 	}
 	// H(col,row) = anchor of the lane + its u cells up to col (bsalign.h:3187-3202); sets err when the lookup leaves the band
-	__device__ int score(int row, int col, int &err) const {
+	__device__ int score(int row, int col, int &err) const { return score_at(row, (row >= -1 && row < tlen) ? beg(row) : 0, col, err); }
+	// same with the row's band offset supplied by the caller (the walk keeps the offsets of rows tb, tb-1, tb-2 in registers)
+	__device__ int score_at(int row, int rbeg, int col, int &err) const {
 		if(row < -1 || row >= tlen){ err |= 1; return kScoreMin; }
-		int64_t pos = (int64_t)col - beg(row);
+		int64_t pos = (int64_t)col - rbeg;
 		if(pos < 0 || pos >= (int64_t)bw){ err |= 1; return kScoreMin; }
 		uint32_t j = (uint32_t)pos / W, n = (uint32_t)pos - j * W + 1;
 		int s = ub(row, j);
@@ -91,56 +93,58 @@ __global__ void __launch_bounds__(128) epi8_backcal_kernel(const Epi8BtArgs a){
 	int Hcur, Hprev = 0, pend = 0, prior = 0;
 	int64_t guard = 0; const int64_t guard_max = 8 * ((int64_t)qlen + tlen) + 64;
 	const int qe = qb + 1, te = tb + 1;
-	Hcur = tv.score(tb, qb, err);
+	// band offsets of rows tb, tb-1, tb-2: the one for tb-2 is requested a full step before it is needed, which
+	// takes the anchor record out of the dependent-load chain of a step
+	int b0 = tv.beg(tb), b1 = tb >= 0 ? tv.beg(tb - 1) : 0, b2 = tb >= 1 ? tv.beg(tb - 2) : 0;
+	#define ROW_UP() { tb--; b0 = b1; b1 = b2; b2 = tb >= 1 ? tv.beg(tb - 2) : 0; }
+	Hcur = tv.score_at(tb, b0, qb, err);
 	while(true){
 		if(++guard > guard_max){ err |= 2; break; }
 		if((pend & 0xf) == 2 || (pend & 0xf) == 4){
 			int len = pend >> 4;
-			Hprev = tv.score(tb, qb, err);
+			Hprev = tv.score_at(tb, b0, qb, err);
 			int cost = ((pend & 0xf) == 2) ? go1 + len * ge1 : go2 + len * ge2;
 			if(Hprev + cost == Hcur){
 				cg.push(2, len);
 				del += len; aln += len;
 				Hcur = Hprev; pend = 0;
-			} else { pend += 1 << 4; tb--; continue; }
+			} else { pend += 1 << 4; ROW_UP(); continue; }
 		}
 		if(qb < 0 || tb < 0) break;
-		const int pbeg = tv.beg(tb - 1);
+		const int pbeg = b1;
 		if(qb == pbeg){
 			if(qb){ Hprev = tv.ub(tb - 1, 0); prior = 0; }
 			else if(mode == 1 || tb == 0) Hprev = 0;
 			else if(pw < 2) Hprev = go1 + ge1 * tb;
 			else Hprev = max(go1 + ge1 * tb, go2 + ge2 * tb);
 		} else if(qb - pbeg <= bw){
-			Hprev = tv.score(tb - 1, qb - 1, err);
+			Hprev = tv.score_at(tb - 1, b1, qb - 1, err);
 		}
 		{
 			const int x = qb - pbeg;
-			int bt, u = 0, e = 0, q = 0;
-			if(x >= 0 && x < bw){
-				u = tv.cell(tb - 1, 0, (uint32_t)x);
-				e = pw >= 1 ? tv.cell(tb - 1, 1, (uint32_t)x) : (int)(int8_t)(go1 + ge1);
-				q = pw == 2 ? tv.cell(tb - 1, 2, (uint32_t)x) : 0;
-			}
 			const int s = a.mtx[qs[qb] * 4 + ts[tb]];
 			const int h = Hcur - Hprev;
+			int bt;
 			if(x > bw) bt = 1;
 			else if(x == bw) bt = (h == s) ? 0 : 1;
-			else if(prior){
-				if(h == s) bt = 0;
-				else if(h == u + e) bt = 2;
-				else if(pw == 2 && h == u + q) bt = 4;
-				else bt = 1;
-			} else {
+			else if(prior && h == s) bt = 0;    // the common step: no need to look at the cell above
+			else {
+				int u = 0, e = 0, q = 0;
+				if(x >= 0 && x < bw){
+					u = tv.cell(tb - 1, 0, (uint32_t)x);
+					e = pw >= 1 ? tv.cell(tb - 1, 1, (uint32_t)x) : (int)(int8_t)(go1 + ge1);
+					q = pw == 2 ? tv.cell(tb - 1, 2, (uint32_t)x) : 0;
+				}
 				if(h == u + e) bt = 2;
 				else if(pw == 2 && h == u + q) bt = 4;
-				else if(h == s) bt = 0;
+				else if(!prior && h == s) bt = 0;
 				else bt = 1;
 			}
 			prior = 1;
 			if(bt == 0){
 				if(qs[qb] == ts[tb]) mat++; else mis++;
-				qb--; tb--; aln++;
+				qb--; aln++;
+				ROW_UP();
 				cg.push(0, 1);
 				Hcur = Hprev;
 			} else if(bt == 1){
@@ -149,11 +153,11 @@ __global__ void __launch_bounds__(128) epi8_backcal_kernel(const Epi8BtArgs a){
 					Hcur = Hprev;
 					qb--; ins++; aln++;
 				} else {
-					const int cbeg = tv.beg(tb);
+					const int cbeg = b0;
 					for(int sz=1;sz+cbeg<=qb;sz++){
 						int tt = go1 + sz * ge1;
 						if(pw == 2) tt = max(tt, go2 + sz * ge2);
-						int Hl = tv.score(tb, qb - sz, err);
+						int Hl = tv.score_at(tb, b0, qb - sz, err);
 						if(Hl + tt == Hcur){
 							cg.push(1, sz);
 							Hcur = Hl; qb -= sz; ins += sz; aln += sz;
@@ -163,11 +167,12 @@ __global__ void __launch_bounds__(128) epi8_backcal_kernel(const Epi8BtArgs a){
 				}
 			} else {
 				pend = (1 << 4) | bt;
-				tb--;
+				ROW_UP();
 				continue;
 			}
 		}
 	}
+	#undef ROW_UP
 	if(mode == 1) cg.flush();
 	else {
 		uint32_t op = 0, sz = 0;
