@@ -57,11 +57,13 @@ struct bsb200_ctx {
 	int num_sms = 0;
 	size_t smem_optin = 0;
 	cudaStream_t stream = nullptr;
+	cudaStream_t stream_bt = nullptr;   // traceback kernels run here, concurrently with the next wave's forward kernel
 	cudaEvent_t ev[8] = {};
 	uint64_t trace_budget = 0;
 	std::string err;
 	bsb200_timing_t timing = {};
-	DevBuf trace;       // shared by all batches of this context (one batch runs at a time)
+	DevBuf trace;       // traceback arena, even waves (shared by all batches of this context; one batch runs at a time)
+	DevBuf trace2;      // odd waves
 	DevBuf counter;
 	// allocations of finished batches are parked here and handed to the next batch (cudaMalloc/cudaFree and pinned
 	// allocations cost more than the kernels of a small batch)
@@ -120,6 +122,7 @@ extern "C" bsb200_ctx *bsb200_create(int device, uint64_t trace_budget_bytes){
 	ctx->num_sms = prop.multiProcessorCount;
 	ctx->smem_optin = prop.sharedMemPerBlockOptin;
 	cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking);
+	{ int lo = 0, hi = 0; cudaDeviceGetStreamPriorityRange(&lo, &hi); cudaStreamCreateWithPriority(&ctx->stream_bt, cudaStreamNonBlocking, hi); }
 	for(auto &e : ctx->ev) cudaEventCreate(&e);
 	ctx->trace_budget = trace_budget_bytes;
 	return ctx;
@@ -129,11 +132,12 @@ extern "C" void bsb200_destroy(bsb200_ctx *ctx){
 	if(!ctx) return;
 	cudaSetDevice(ctx->device);
 	cudaStreamSynchronize(ctx->stream);
-	ctx->trace.release(); ctx->counter.release();
+	ctx->trace.release(); ctx->trace2.release(); ctx->counter.release();
 	for(auto &d : ctx->dev_cache) d.release();
 	for(auto &h : ctx->host_cache) h.release();
 	for(auto &e : ctx->ev) cudaEventDestroy(e);
 	cudaStreamDestroy(ctx->stream);
+	cudaStreamDestroy(ctx->stream_bt);
 	delete ctx;
 }
 
@@ -225,12 +229,14 @@ extern "C" bsb200_batch *bsb200_batch_upload(bsb200_ctx *ctx, int kind, uint64_t
 	if(budget == 0){
 		size_t fr = 0, tot = 0;
 		cudaMemGetInfo(&fr, &tot);
-		budget = (uint64_t)((fr + ctx->trace.cap) * 0.80);
+		budget = (uint64_t)((fr + ctx->trace.cap + ctx->trace2.cap) * 0.80);
 	}
 	b->trace_off.assign(n + 1, 0);
 	b->cig_off.assign(n + 1, 0);
 	std::vector<uint32_t> block_rows;
 	if(kind == 0){
+		// as few waves as the trace budget allows: a wave must keep every SM's groups busy, and splitting further to
+		// overlap the traceback with the next forward sweep cost more (idle groups, co-scheduling) than it hid
 		Wave w = {0, 0, 0};
 		for(uint32_t k=0;k<nact;k++){
 			uint32_t i = b->order[k];
@@ -368,20 +374,22 @@ extern "C" int bsb200_batch_run(bsb200_ctx *ctx, bsb200_batch *b){
 	CK(cudaMemsetAsync(b->d_ncigar.p, 0, b->n * 4, st));
 	CK(cudaMemsetAsync(b->d_dense_total.p, 0, 16, st));
 	CK(cudaMemsetAsync(b->d_dense_off.p, 0, b->n * 8, st));
-	// three events per wave: [start, forward done, traceback done]
-	evs.resize(b->waves.size() * 3);
+	// four events per wave: [forward start, forward done, traceback start, traceback done]
+	evs.resize(b->waves.size() * 4);
 	for(auto &e : evs) CK(cudaEventCreate(&e));
+	cudaStream_t sb = st; // (ctx->stream_bt is kept for experiments with concurrent traceback)
 	for(size_t wi=0;wi<b->waves.size();wi++){
 		const Wave &w = b->waves[wi];
 		uint32_t np = w.end - w.beg;
+		uint8_t *arena = ctx->trace.as<uint8_t>();
 		CK(cudaMemsetAsync(ctx->counter.p, 0, 16, st));
-		CK(cudaEventRecord(evs[wi * 3 + 0], st));
+		CK(cudaEventRecord(evs[wi * 4 + 0], st));
 		if(b->kind == 0){
 			Epi8Args a;
 			a.seqs = b->d_seqs.as<uint8_t>(); a.qoff = b->d_qoff.as<uint64_t>(); a.toff = b->d_toff.as<uint64_t>();
 			a.qlen = b->d_qlen.as<uint32_t>(); a.tlen = b->d_tlen.as<uint32_t>();
 			a.order = b->d_order.as<uint32_t>() + w.beg; a.npairs = np; a.counter = ctx->counter.as<unsigned int>();
-			a.trace = ctx->trace.as<uint8_t>(); a.trace_off = b->d_trace_off.as<uint64_t>();
+			a.trace = arena; a.trace_off = b->d_trace_off.as<uint64_t>();
 			a.results = b->d_results.as<int32_t>(); a.status = b->d_status.as<int32_t>();
 			a.bandwidth = b->bandwidth; a.max_img = epi8_image_bytes(b->max_bw / 16);
 			// images of u,(e),(q) and the selectors + anchors and scratch; 32 bytes past a multiple of 128 so the four
@@ -398,7 +406,9 @@ extern "C" int bsb200_batch_run(bsb200_ctx *ctx, bsb200_batch *b){
 			else rc = b->pw == 2 ? launch_epi8_forward<2, false>(ctx, a, np) : (b->pw == 1 ? launch_epi8_forward<1, false>(ctx, a, np) : launch_epi8_forward<0, false>(ctx, a, np));
 			if(rc) return rc;
 			ctx->timing.forward_launches++;
-			CK(cudaEventRecord(evs[wi * 3 + 1], st));
+			CK(cudaEventRecord(evs[wi * 4 + 1], st));
+			// traceback of this wave on the second stream, behind its forward kernel
+			CK(cudaEventRecord(evs[wi * 4 + 2], sb));
 			Epi8BtArgs t;
 			t.seqs = a.seqs; t.qoff = a.qoff; t.toff = a.toff; t.qlen = a.qlen; t.tlen = a.tlen; t.order = a.order; t.npairs = np;
 			t.trace = a.trace; t.trace_off = a.trace_off; t.results = a.results; t.status = a.status;
@@ -408,9 +418,10 @@ extern "C" int bsb200_batch_run(bsb200_ctx *ctx, bsb200_batch *b){
 			t.ncigar = b->d_ncigar.as<uint32_t>();
 			t.bandwidth = b->bandwidth; t.mode = b->mode; t.pw = b->pw; memcpy(t.mtx, b->mtx, 16);
 			t.go1 = b->go1; t.ge1 = b->ge1; t.go2 = b->go2; t.ge2 = b->ge2;
-			epi8_backcal_kernel<<<(np + 127) / 128, 128, 0, st>>>(t);
+			epi8_backcal_kernel<<<(np + 63) / 64, 64, 0, sb>>>(t);
 			CK(cudaGetLastError());
 			ctx->timing.traceback_launches++;
+			CK(cudaEventRecord(evs[wi * 4 + 3], sb));
 		} else {
 			EditArgs a;
 			a.seqs = b->d_seqs.as<uint8_t>(); a.qoff = b->d_qoff.as<uint64_t>(); a.toff = b->d_toff.as<uint64_t>();
@@ -426,17 +437,18 @@ extern "C" int bsb200_batch_run(bsb200_ctx *ctx, bsb200_batch *b){
 			int rc = launch_edit(ctx, a);
 			if(rc) return rc;
 			ctx->timing.forward_launches++;
-			CK(cudaEventRecord(evs[wi * 3 + 1], st));
+			CK(cudaEventRecord(evs[wi * 4 + 1], st));
+			CK(cudaEventRecord(evs[wi * 4 + 2], st));
+			CK(cudaEventRecord(evs[wi * 4 + 3], st));
 		}
-		CK(cudaEventRecord(evs[wi * 3 + 2], st));
 	}
 	CK(cudaEventRecord(ctx->ev[5], st));
 	CK(cudaStreamSynchronize(st));
 	{ float rm = 0; cudaEventElapsedTime(&rm, ctx->ev[4], ctx->ev[5]); ctx->timing.run_ms = rm; }
 	for(size_t wi=0;wi<b->waves.size();wi++){
 		float m1 = 0, m2 = 0;
-		cudaEventElapsedTime(&m1, evs[wi * 3 + 0], evs[wi * 3 + 1]);
-		cudaEventElapsedTime(&m2, evs[wi * 3 + 1], evs[wi * 3 + 2]);
+		cudaEventElapsedTime(&m1, evs[wi * 4 + 0], evs[wi * 4 + 1]);
+		cudaEventElapsedTime(&m2, evs[wi * 4 + 2], evs[wi * 4 + 3]);
 		fwd_ms += m1; bt_ms += m2;
 	}
 	for(auto &e : evs) cudaEventDestroy(e);

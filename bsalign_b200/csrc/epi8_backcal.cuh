@@ -50,17 +50,23 @@ struct TraceView {
 		// the lane's cells are every other byte of its thread's 16 bytes per chunk: dp4a with a 0/1 mask adds two per word
 		const uint8_t *r = tr + (size_t)RS * (row + 1) + (size_t)(j >> 1) * 16;
 		const int mk = (j & 1) ? 0x01000100 : 0x00010001;
-		for(;n>=8;n-=8,r+=128){
-			int4 v = *(const int4*)r;
-			s = __dp4a(v.x, mk, s); s = __dp4a(v.y, mk, s); s = __dp4a(v.z, mk, s); s = __dp4a(v.w, mk, s);
-		}
-		if(n){
-			int4 v = *(const int4*)r;
-			int w[4] = {v.x, v.y, v.z, v.w};
+		// all chunk loads of a round are issued before the first sum so that a lookup costs one memory round trip
+		// per 8 chunks (64 steps of the lane) instead of one per chunk
+		const uint32_t nch = (n + 7) >> 3;
+		for(uint32_t c0=0;c0<nch;c0+=8){
+			int4 v[8];
 			#pragma unroll
-			for(int k=0;k<4;k++){
-				if(n >= 2u * k + 2) s = __dp4a(w[k], mk, s);
-				else if(n == 2u * k + 1) s = __dp4a(w[k], mk & 0x0000ffff, s);
+			for(int k=0;k<8;k++) if(c0 + k < nch) v[k] = *(const int4*)(r + 128 * (c0 + k));
+			#pragma unroll
+			for(int k=0;k<8;k++){
+				if(c0 + k >= nch) break;
+				const uint32_t left = n - 8 * (c0 + k); // entries of this chunk that count (>= 1)
+				const int w[4] = {v[k].x, v[k].y, v[k].z, v[k].w};
+				#pragma unroll
+				for(int q=0;q<4;q++){
+					if(left >= 2u * q + 2) s = __dp4a(w[q], mk, s);
+					else if(left == 2u * q + 1) s = __dp4a(w[q], mk & 0x0000ffff, s);
+				}
 			}
 		}
 		return s;
