@@ -40,6 +40,56 @@ struct TraceView {
 	}
 	// H(col,row) = anchor of the lane + its u cells up to col (bsalign.h:3187-3202); sets err when the lookup leaves the band
 	__device__ int score(int row, int col, int &err) const { return score_at(row, (row >= -1 && row < tlen) ? beg(row) : 0, col, err); }
+	// ---- split lookup: `begin` only computes addresses and issues the loads (anchor + up to 8 chunks), `finish` sums.
+	// Between the two the caller issues its other loads, so that one walk step costs a single memory round trip.
+	struct Pending { const uint8_t *r; int4 v[8]; int ub; uint32_t n; int mk; };
+	__device__ __forceinline__ void begin(Pending &p, bool need, int row, int rbeg, int col, int &err) const {
+		int64_t pos = (int64_t)col - rbeg;
+		bool ok = need && row >= -1 && row < tlen && pos >= 0 && pos < (int64_t)bw;
+		if(need && !ok) err |= 1;
+		uint32_t up = ok ? (uint32_t)pos : 0u, j = up / W;
+		int rw = ok ? row : -1;
+		p.n = ok ? up - j * W + 1 : 0u;
+		p.ub = ok ? ub(rw, j) : kScoreMin;
+		p.r = tr + (size_t)RS * (rw + 1) + (size_t)(j >> 1) * 16;
+		p.mk = (j & 1) ? 0x01000100 : 0x00010001;
+		const uint32_t nch = (p.n + 7) >> 3;
+		#pragma unroll
+		for(int k=0;k<8;k++) p.v[k] = (uint32_t)k < nch ? *(const int4*)(p.r + 128 * k) : make_int4(0, 0, 0, 0);
+	}
+	__device__ __forceinline__ int finish(const Pending &p) const {
+		int s = p.ub;
+		const uint32_t nch = (p.n + 7) >> 3;
+		#pragma unroll
+		for(int k=0;k<8;k++){
+			if((uint32_t)k < nch){
+				const uint32_t left = p.n - 8 * k;
+				const int w[4] = {p.v[k].x, p.v[k].y, p.v[k].z, p.v[k].w};
+				#pragma unroll
+				for(int q=0;q<4;q++){
+					if(left >= 2u * q + 2) s = __dp4a(w[q], p.mk, s);
+					else if(left == 2u * q + 1) s = __dp4a(w[q], p.mk & 0x0000ffff, s);
+				}
+			}
+		}
+		for(uint32_t c0=8;c0<nch;c0+=8){ // lanes longer than 64 steps: further rounds
+			int4 v[8];
+			#pragma unroll
+			for(int k=0;k<8;k++) if(c0 + k < nch) v[k] = *(const int4*)(p.r + 128 * (c0 + k));
+			#pragma unroll
+			for(int k=0;k<8;k++){
+				if(c0 + k >= nch) break;
+				const uint32_t left = p.n - 8 * (c0 + k);
+				const int w[4] = {v[k].x, v[k].y, v[k].z, v[k].w};
+				#pragma unroll
+				for(int q=0;q<4;q++){
+					if(left >= 2u * q + 2) s = __dp4a(w[q], p.mk, s);
+					else if(left == 2u * q + 1) s = __dp4a(w[q], p.mk & 0x0000ffff, s);
+				}
+			}
+		}
+		return s;
+	}
 	// same with the row's band offset supplied by the caller (the walk keeps the offsets of rows tb, tb-1, tb-2 in registers)
 	__device__ int score_at(int row, int rbeg, int col, int &err) const {
 		if(row < -1 || row >= tlen){ err |= 1; return kScoreMin; }
@@ -97,58 +147,90 @@ __global__ void __launch_bounds__(128) epi8_backcal_kernel(const Epi8BtArgs a){
 	int qb = rs[2], tb = rs[4];
 	int mat = 0, mis = 0, ins = 0, del = 0, aln = 0;
 	int Hcur, Hprev = 0, pend = 0, prior = 0;
-	int64_t guard = 0; const int64_t guard_max = 8 * ((int64_t)qlen + tlen) + 64;
+	int64_t guard = 0; const int64_t guard_max = 16 * ((int64_t)qlen + tlen) + 64;
 	const int qe = qb + 1, te = tb + 1;
 	// band offsets of rows tb, tb-1, tb-2: the one for tb-2 is requested a full step before it is needed, which
 	// takes the anchor record out of the dependent-load chain of a step
 	int b0 = tv.beg(tb), b1 = tb >= 0 ? tv.beg(tb - 1) : 0, b2 = tb >= 1 ? tv.beg(tb - 2) : 0;
 	#define ROW_UP() { tb--; b0 = b1; b1 = b2; b2 = tb >= 1 ? tv.beg(tb - 2) : 0; }
 	Hcur = tv.score_at(tb, b0, qb, err);
+	// The walk of bsalign.h:3726-3821 as a state machine with ONE score lookup per iteration: the 32 pairs of a warp
+	// take different branches all the time, and with one shared lookup site per iteration a warp pays one memory round
+	// trip per iteration instead of one per branch taken by any of its threads.
+	enum { kStep = 0, kDrun = 1, kIsearch = 2 };
+	int state = kStep, sz = 0;
 	while(true){
 		if(++guard > guard_max){ err |= 2; break; }
-		if((pend & 0xf) == 2 || (pend & 0xf) == 4){
-			int len = pend >> 4;
-			Hprev = tv.score_at(tb, b0, qb, err);
-			int cost = ((pend & 0xf) == 2) ? go1 + len * ge1 : go2 + len * ge2;
-			if(Hprev + cost == Hcur){
+		// ---- 1. what this iteration needs -----------------------------------------------------------------
+		int lrow = 0, lbeg = 0, lcol = 0, x = 0;
+		bool need = false, cellok = false;
+		if(state == kStep){
+			if(qb < 0 || tb < 0) break;
+			x = qb - b1;
+			if(qb == b1){
+				if(qb){ Hprev = tv.ub(tb - 1, 0); prior = 0; } // left edge of the previous row: only a deletion can follow (:3761-3765)
+				else if(mode == 1 || tb == 0) Hprev = 0;
+				else if(pw < 2) Hprev = go1 + ge1 * tb;
+				else Hprev = max(go1 + ge1 * tb, go2 + ge2 * tb);
+			} else if(x <= bw){ need = true; lrow = tb - 1; lbeg = b1; lcol = qb - 1; }
+			cellok = (x >= 0 && x < bw);
+		} else if(state == kDrun){
+			need = true; lrow = tb; lbeg = b0; lcol = qb;
+		} else {
+			if(sz + b0 > qb){ err |= 2; break; } // no insertion length fits: the reference repeats this step forever (:3798-3814)
+			need = true; lrow = tb; lbeg = b0; lcol = qb - sz;
+		}
+		// ---- 2. issue every load of this step (cell above, query/target bases, lookup), then consume -------------
+		const int crow = (state == kStep) ? tb - 1 : -1;                    // row of the cell above (valid memory in any state)
+		const uint32_t cx = cellok ? (uint32_t)x : 0u;
+		const uint32_t cj = cx / tv.W, coff = epi8_cell_offset(cj, cx - cj * tv.W);
+		const uint8_t *cp = tv.tr + (size_t)tv.RS * (crow + 1) + coff;
+		const uint32_t ru = cp[0], re = pw >= 1 ? cp[tv.IB] : 0u, rq = pw == 2 ? cp[2 * (size_t)tv.IB] : 0u;
+		const uint32_t qbase = qs[qb >= 0 ? qb : 0], tbase = ts[tb >= 0 ? tb : 0];
+		TraceView::Pending pd;
+		tv.begin(pd, need, lrow, lbeg, lcol, err);
+		int val = tv.finish(pd);
+		int u = 0, e = (int)(int8_t)(go1 + ge1), q = 0;
+		if(cellok){ u = (int)(int8_t)ru; if(pw >= 1) e = (int)(int8_t)re; if(pw == 2) q = (int)(int8_t)rq; }
+		else { u = 0; e = 0; q = 0; }
+		// ---- 3. act ------------------------------------------------------------------------------------------------
+		if(state == kDrun){
+			const int len = pend >> 4;
+			const int cost = ((pend & 0xf) == 2) ? go1 + len * ge1 : go2 + len * ge2;
+			if(val + cost == Hcur){
 				cg.push(2, len);
 				del += len; aln += len;
-				Hcur = Hprev; pend = 0;
-			} else { pend += 1 << 4; ROW_UP(); continue; }
-		}
-		if(qb < 0 || tb < 0) break;
-		const int pbeg = b1;
-		if(qb == pbeg){
-			if(qb){ Hprev = tv.ub(tb - 1, 0); prior = 0; }
-			else if(mode == 1 || tb == 0) Hprev = 0;
-			else if(pw < 2) Hprev = go1 + ge1 * tb;
-			else Hprev = max(go1 + ge1 * tb, go2 + ge2 * tb);
-		} else if(qb - pbeg <= bw){
-			Hprev = tv.score_at(tb - 1, b1, qb - 1, err);
-		}
-		{
-			const int x = qb - pbeg;
-			const int s = a.mtx[qs[qb] * 4 + ts[tb]];
+				Hcur = val; pend = 0; state = kStep;
+			} else { pend += 1 << 4; ROW_UP(); }
+		} else if(state == kIsearch){
+			int tt = go1 + sz * ge1;
+			if(pw == 2) tt = max(tt, go2 + sz * ge2);
+			if(val + tt == Hcur){
+				cg.push(1, sz);
+				Hcur = val; qb -= sz; ins += sz; aln += sz;
+				state = kStep;
+			} else sz++;
+		} else {
+			if(need) Hprev = val;
+			const int s = a.mtx[qbase * 4 + tbase];
 			const int h = Hcur - Hprev;
 			int bt;
 			if(x > bw) bt = 1;
 			else if(x == bw) bt = (h == s) ? 0 : 1;
-			else if(prior && h == s) bt = 0;    // the common step: no need to look at the cell above
-			else {
-				int u = 0, e = 0, q = 0;
-				if(x >= 0 && x < bw){
-					u = tv.cell(tb - 1, 0, (uint32_t)x);
-					e = pw >= 1 ? tv.cell(tb - 1, 1, (uint32_t)x) : (int)(int8_t)(go1 + ge1);
-					q = pw == 2 ? tv.cell(tb - 1, 2, (uint32_t)x) : 0;
-				}
+			else if(prior){
+				if(h == s) bt = 0;
+				else if(h == u + e) bt = 2;
+				else if(pw == 2 && h == u + q) bt = 4;
+				else bt = 1;
+			} else {
 				if(h == u + e) bt = 2;
 				else if(pw == 2 && h == u + q) bt = 4;
-				else if(!prior && h == s) bt = 0;
+				else if(h == s) bt = 0;
 				else bt = 1;
 			}
 			prior = 1;
 			if(bt == 0){
-				if(qs[qb] == ts[tb]) mat++; else mis++;
+				if(qbase == tbase) mat++; else mis++;
 				qb--; aln++;
 				ROW_UP();
 				cg.push(0, 1);
@@ -158,23 +240,11 @@ __global__ void __launch_bounds__(128) epi8_backcal_kernel(const Epi8BtArgs a){
 					cg.push(1, 1);
 					Hcur = Hprev;
 					qb--; ins++; aln++;
-				} else {
-					const int cbeg = b0;
-					for(int sz=1;sz+cbeg<=qb;sz++){
-						int tt = go1 + sz * ge1;
-						if(pw == 2) tt = max(tt, go2 + sz * ge2);
-						int Hl = tv.score_at(tb, b0, qb - sz, err);
-						if(Hl + tt == Hcur){
-							cg.push(1, sz);
-							Hcur = Hl; qb -= sz; ins += sz; aln += sz;
-							break;
-						}
-					}
-				}
+				} else { state = kIsearch; sz = 1; }
 			} else {
 				pend = (1 << 4) | bt;
 				ROW_UP();
-				continue;
+				state = kDrun;
 			}
 		}
 	}
