@@ -427,6 +427,7 @@ __global__ void __launch_bounds__(kFwdThreads) epi8_forward_kernel(const Epi8Arg
 				if(PW == 2) cq4 = *(const uint4*)(rQ + 128 * c); \
 				P1STEP(0, LEFT) P1STEP(1, LEFT) P1STEP(2, LEFT) P1STEP(3, LEFT) P1STEP(4, LEFT) P1STEP(5, LEFT) P1STEP(6, LEFT) P1STEP(7, LEFT) }
 			uint32_t c = 0;
+			_Pragma("unroll 1")   // one chunk per iteration keeps the loop body in the instruction cache (measured: -10% time)
 			for(;c<nfull;c++) P1CHUNK(8u)
 			if(c < nchunk){ const uint32_t left = W - 8 * c; P1CHUNK(left) }
 			#undef P1CHUNK
@@ -476,6 +477,7 @@ __global__ void __launch_bounds__(kFwdThreads) epi8_forward_kernel(const Epi8Arg
 				if(PW >= 1) *(uint4*)(rE + 128 * c) = make_uint4(pack2(en[0], en[1]), pack2(en[2], en[3]), pack2(en[4], en[5]), pack2(en[6], en[7])); \
 				if(PW == 2) *(uint4*)(rQ + 128 * c) = make_uint4(pack2(qn[0], qn[1]), pack2(qn[2], qn[3]), pack2(qn[4], qn[5]), pack2(qn[6], qn[7])); }
 			uint32_t c = 0;
+			_Pragma("unroll 1")
 			for(;c<nfull;c++) P2CHUNK(8u, false)
 			if(c < nchunk){ const uint32_t left = W - 8 * c; P2CHUNK(left, true) }
 			#undef P2CHUNK
