@@ -66,6 +66,7 @@ def lib():
         L.bsb200_batch_run.argtypes = [_P, _P]
         L.bsb200_batch_sync.argtypes = [_P]
         L.bsb200_batch_fetch.argtypes = [_P, _P, _P, _P, _P, _P, _P]
+        L.bsb200_batch_fetch_dense.argtypes = [_P, _P, _P, _P, ctypes.c_uint64, _P, _P, _P]
         L.bsb200_batch_free.argtypes = [_P, _P]
         L.bsb200_epi8_pairwise_batch.argtypes = [_P, ctypes.c_uint64, _P, _P, _P, _P, _P, ctypes.c_int, ctypes.c_uint32, _P,
                                                  _I8, _I8, _I8, _I8, _P, _P, _P, _P, _P]
@@ -126,7 +127,9 @@ class Context:
         return t.as_dict()
 
     # ---- one-shot batch calls (host buffers in, host buffers out) ---------------------------------
-    def epi8_batch(self, batch, mode, bandwidth, matrix, gapo1, gape1, gapo2=0, gape2=0, want_cigar=True, out=None):
+    def epi8_batch(self, batch, mode, bandwidth, matrix, gapo1, gape1, gapo2=0, gape2=0, want_cigar=True, out=None, dense=False):
+        if dense:
+            return self._staged("epi8", batch, mode, bandwidth, matrix, (gapo1, gape1, gapo2, gape2), out)
         n = batch.n
         m = np.ascontiguousarray(matrix, dtype=np.int8)
         res, cg, off, ncg, st = out if out is not None else _alloc_out(batch, want_cigar)
@@ -136,7 +139,19 @@ class Context:
         self._check(rc, "bsb200_epi8_pairwise_batch")
         return BatchResult(res, cg, off, ncg, st)
 
-    def edit_batch(self, batch, mode, bandwidth, want_cigar=True, out=None):
+    def _staged(self, kind, batch, mode, bandwidth, matrix, gaps, out):
+        rb = self.upload(kind, batch, mode, bandwidth, matrix, gaps, want_cigar=True)
+        try:
+            rb.run()
+            r = rb.fetch_dense(out=out)
+            self.last_timing = self.timing()
+            return r
+        finally:
+            rb.free()
+
+    def edit_batch(self, batch, mode, bandwidth, want_cigar=True, out=None, dense=False):
+        if dense:
+            return self._staged("edit", batch, mode, bandwidth, None, (0, 0, 0, 0), out)
         n = batch.n
         res, cg, off, ncg, st = out if out is not None else _alloc_out(batch, want_cigar)
         rc = self._lib.bsb200_edit_pairwise_batch(self._h, n, _ptr(batch.seqs), _ptr(batch.qoff), _ptr(batch.qlen), _ptr(batch.toff), _ptr(batch.tlen),
@@ -193,6 +208,16 @@ class ResidentBatch:
         rc = self.ctx._lib.bsb200_batch_fetch(self.ctx._h, self._h, _ptr(res), _ptr(cg), _ptr(off), _ptr(ncg), _ptr(st))
         self.ctx._check(rc, "bsb200_batch_fetch")
         return BatchResult(res, cg, off, ncg, st)
+
+    def fetch_dense(self, out=None):
+        """Cigars dense and in pair order (pair i starts at sum(ncigar[:i])): the fast path, no host-side scatter."""
+        res, cg, off, ncg, st = out if out is not None else _alloc_out(self.batch, self.want_cigar)
+        total = ctypes.c_uint64(0)
+        rc = self.ctx._lib.bsb200_batch_fetch_dense(self.ctx._h, self._h, _ptr(res), _ptr(cg), 0 if cg is None else cg.size, ctypes.byref(total), _ptr(ncg), _ptr(st))
+        self.ctx._check(rc, "bsb200_batch_fetch_dense")
+        doff = np.zeros(len(ncg) + 1, dtype=np.uint64)
+        np.cumsum(ncg, out=doff[1:])
+        return BatchResult(res, cg, doff, ncg, st)
 
     def free(self):
         if self._h:

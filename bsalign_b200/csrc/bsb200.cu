@@ -10,6 +10,9 @@
 #include "epi8_backcal.cuh"
 #include "edit_kernels.cuh"
 
+#include <cub/device/device_scan.cuh>
+#include <cub/iterator/transform_input_iterator.cuh>
+
 #include <algorithm>
 #include <cstdio>
 #include <cstdlib>
@@ -67,7 +70,7 @@ struct bsb200_ctx {
 	DevBuf counter;
 	// allocations of finished batches are parked here and handed to the next batch (cudaMalloc/cudaFree and pinned
 	// allocations cost more than the kernels of a small batch)
-	DevBuf dev_cache[16];
+	DevBuf dev_cache[17];
 	HostBuf host_cache[8];
 };
 
@@ -85,7 +88,7 @@ struct bsb200_batch {
 	std::vector<Wave> waves;
 	std::vector<uint32_t> order;
 	std::vector<uint64_t> trace_off, cig_off;
-	DevBuf d_seqs, d_qoff, d_toff, d_qlen, d_tlen, d_order, d_trace_off, d_results, d_status, d_ncigar, d_cig_raw, d_cig_off, d_cig_dense, d_dense_off, d_dense_total, d_block_rows;
+	DevBuf d_seqs, d_qoff, d_toff, d_qlen, d_tlen, d_order, d_trace_off, d_results, d_status, d_ncigar, d_cig_raw, d_cig_off, d_cig_dense, d_dense_off, d_dense_total, d_block_rows, d_prefix;
 	HostBuf h_results, h_status, h_ncigar, h_dense_off, h_dense, h_total;
 	size_t seq_bytes = 0;
 	bool ran = false;
@@ -167,8 +170,8 @@ extern "C" bsb200_batch *bsb200_batch_upload(bsb200_ctx *ctx, int kind, uint64_t
 	bsb200_batch *b = new bsb200_batch();
 	{
 		DevBuf *ds[] = {&b->d_seqs, &b->d_qoff, &b->d_toff, &b->d_qlen, &b->d_tlen, &b->d_order, &b->d_trace_off, &b->d_results, &b->d_status,
-			&b->d_ncigar, &b->d_cig_raw, &b->d_cig_off, &b->d_cig_dense, &b->d_dense_off, &b->d_dense_total, &b->d_block_rows};
-		for(int k=0;k<16;k++){ *ds[k] = ctx->dev_cache[k]; ctx->dev_cache[k] = DevBuf(); }
+			&b->d_ncigar, &b->d_cig_raw, &b->d_cig_off, &b->d_cig_dense, &b->d_dense_off, &b->d_dense_total, &b->d_block_rows, &b->d_prefix};
+		for(int k=0;k<17;k++){ *ds[k] = ctx->dev_cache[k]; ctx->dev_cache[k] = DevBuf(); }
 		HostBuf *hs[] = {&b->h_results, &b->h_status, &b->h_ncigar, &b->h_dense_off, &b->h_dense, &b->h_total};
 		for(int k=0;k<6;k++){ *hs[k] = ctx->host_cache[k]; ctx->host_cache[k] = HostBuf(); }
 	}
@@ -464,8 +467,33 @@ extern "C" int bsb200_batch_sync(bsb200_ctx *ctx){
 	return 0;
 }
 
+// ---- dense cigars in PAIR ORDER: prefix sum of the per-pair counts, then one warp per pair moves its words ---------
+struct U32toU64 { __host__ __device__ uint64_t operator()(const uint32_t &x) const { return (uint64_t)x; } };
+
+__global__ void __launch_bounds__(256) cigar_order_kernel(const uint32_t *dense, const uint64_t *dense_off, const uint32_t *ncigar, const uint64_t *prefix, uint32_t *ordered, uint64_t n){
+	uint64_t pair = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+	if(pair >= n) return;
+	const uint32_t lane = threadIdx.x & 31, k = ncigar[pair];
+	const uint32_t *src = dense + dense_off[pair];
+	uint32_t *dst = ordered + prefix[pair];
+	for(uint32_t i=lane;i<k;i+=32) dst[i] = src[i];
+}
+
+static int fetch_impl(bsb200_ctx *ctx, bsb200_batch *b, bsb200_result_t *results, uint32_t *cigars, const uint64_t *cgoff,
+		uint64_t dense_cap, uint64_t *total_out, uint32_t *ncigar, int32_t *status);
+
 extern "C" int bsb200_batch_fetch(bsb200_ctx *ctx, bsb200_batch *b, bsb200_result_t *results,
 		uint32_t *cigars, const uint64_t *cgoff, uint32_t *ncigar, int32_t *status){
+	return fetch_impl(ctx, b, results, cigars, cgoff, 0, nullptr, ncigar, status);
+}
+
+extern "C" int bsb200_batch_fetch_dense(bsb200_ctx *ctx, bsb200_batch *b, bsb200_result_t *results,
+		uint32_t *cigars, uint64_t cigar_cap_words, uint64_t *total_words, uint32_t *ncigar, int32_t *status){
+	return fetch_impl(ctx, b, results, cigars, nullptr, cigar_cap_words, total_words, ncigar, status);
+}
+
+static int fetch_impl(bsb200_ctx *ctx, bsb200_batch *b, bsb200_result_t *results,
+		uint32_t *cigars, const uint64_t *cgoff, uint64_t dense_cap, uint64_t *total_out, uint32_t *ncigar, int32_t *status){
 	if(!ctx || !b || !b->ran) return fail(ctx, "bsb200_batch_fetch before run", cudaSuccess);
 	ctx->err.clear();
 	cudaSetDevice(ctx->device);
@@ -473,6 +501,8 @@ extern "C" int bsb200_batch_fetch(bsb200_ctx *ctx, bsb200_batch *b, bsb200_resul
 	uint64_t n = b->n;
 	if(n == 0) return 0;
 	const bool cg = b->want_cigar && cigars && cgoff;
+	const bool cgd = b->want_cigar && cigars && !cgoff;   // dense, pair-ordered output straight into the caller's buffer
+	if(total_out) *total_out = 0;
 	CK(b->h_results.reserve(n * 40)); CK(b->h_status.reserve(n * 4)); CK(b->h_ncigar.reserve(n * 4)); CK(b->h_total.reserve(16));
 	cudaEventRecord(ctx->ev[2], st);
 	CK(cudaMemcpyAsync(results ? (void*)results : b->h_results.p, b->d_results.p, n * 40, cudaMemcpyDeviceToHost, st));
@@ -489,6 +519,28 @@ extern "C" int bsb200_batch_fetch(bsb200_ctx *ctx, bsb200_batch *b, bsb200_resul
 		CK(b->h_dense.reserve(total * 4 + 16));
 		if(total) CK(cudaMemcpyAsync(b->h_dense.p, b->d_cig_dense.p, total * 4, cudaMemcpyDeviceToHost, st));
 		d2h += n * 8 + 8 + total * 4;
+	}
+	if(cgd){
+		// prefix[i] = words of pairs < i (device scan), one warp per pair copies into pair order, one D2H of the result
+		CK(b->d_prefix.reserve((n + 1) * 8));
+		size_t tmp_bytes = 0;
+		cub::TransformInputIterator<uint64_t, U32toU64, const uint32_t*> it(b->d_ncigar.as<uint32_t>(), U32toU64());
+		CK(cub::DeviceScan::ExclusiveSum(nullptr, tmp_bytes, it, b->d_prefix.as<uint64_t>(), (int)n, st));
+		CK(ctx->counter.reserve(tmp_bytes + 256));
+		CK(cub::DeviceScan::ExclusiveSum((uint8_t*)ctx->counter.p + 256, tmp_bytes, it, b->d_prefix.as<uint64_t>(), (int)n, st));
+		CK(cudaMemcpyAsync(b->h_total.p, b->d_dense_total.p, 8, cudaMemcpyDeviceToHost, st));
+		CK(cudaStreamSynchronize(st));
+		total = *b->h_total.as<unsigned long long>();
+		if(total_out) *total_out = total;
+		if(total > dense_cap) return fail(ctx, "cigar buffer too small for the dense cigars (see total_words)", cudaSuccess);
+		if(total){
+			uint32_t *ordered = b->d_cig_raw.as<uint32_t>(); // the per-pair scratch regions are free again once the walks are done
+			cigar_order_kernel<<<(unsigned)((n * 32 + 255) / 256), 256, 0, st>>>(b->d_cig_dense.as<uint32_t>(), b->d_dense_off.as<uint64_t>(),
+				b->d_ncigar.as<uint32_t>(), b->d_prefix.as<uint64_t>(), ordered, n);
+			CK(cudaGetLastError());
+			CK(cudaMemcpyAsync(cigars, ordered, total * 4, cudaMemcpyDeviceToHost, st));
+		}
+		d2h += 8 + total * 4;
 	}
 	cudaEventRecord(ctx->ev[3], st);
 	CK(cudaStreamSynchronize(st));
@@ -516,10 +568,10 @@ extern "C" void bsb200_batch_free(bsb200_ctx *ctx, bsb200_batch *b){
 	if(!b) return;
 	if(ctx){ cudaSetDevice(ctx->device); cudaStreamSynchronize(ctx->stream); }
 	DevBuf *ds[] = {&b->d_seqs, &b->d_qoff, &b->d_toff, &b->d_qlen, &b->d_tlen, &b->d_order, &b->d_trace_off, &b->d_results, &b->d_status,
-		&b->d_ncigar, &b->d_cig_raw, &b->d_cig_off, &b->d_cig_dense, &b->d_dense_off, &b->d_dense_total, &b->d_block_rows};
+		&b->d_ncigar, &b->d_cig_raw, &b->d_cig_off, &b->d_cig_dense, &b->d_dense_off, &b->d_dense_total, &b->d_block_rows, &b->d_prefix};
 	HostBuf *hs[] = {&b->h_results, &b->h_status, &b->h_ncigar, &b->h_dense_off, &b->h_dense, &b->h_total};
 	if(ctx){ // park the allocations for the next batch (a cache slot that is still occupied keeps the larger buffer)
-		for(int k=0;k<16;k++){ if(ctx->dev_cache[k].cap < ds[k]->cap){ ctx->dev_cache[k].release(); ctx->dev_cache[k] = *ds[k]; } else ds[k]->release(); }
+		for(int k=0;k<17;k++){ if(ctx->dev_cache[k].cap < ds[k]->cap){ ctx->dev_cache[k].release(); ctx->dev_cache[k] = *ds[k]; } else ds[k]->release(); }
 		for(int k=0;k<6;k++){ if(ctx->host_cache[k].cap < hs[k]->cap){ ctx->host_cache[k].release(); ctx->host_cache[k] = *hs[k]; } else hs[k]->release(); }
 	} else {
 		for(auto d : ds) d->release();

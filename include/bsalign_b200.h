@@ -104,10 +104,15 @@ bsb200_batch *bsb200_batch_upload(bsb200_ctx *ctx, int kind, uint64_t n, const u
 		const uint64_t *qoff, const uint32_t *qlen, const uint64_t *toff, const uint32_t *tlen,
 		int mode, uint32_t bandwidth, const int8_t matrix[16], int8_t gapo1, int8_t gape1, int8_t gapo2, int8_t gape2,
 		int want_cigar);
-int bsb200_batch_run(bsb200_ctx *ctx, bsb200_batch *b);       /* kernels only; asynchronous on the context stream */
+int bsb200_batch_run(bsb200_ctx *ctx, bsb200_batch *b);       /* kernels only; returns when they are done */
 int bsb200_batch_sync(bsb200_ctx *ctx);                       /* wait for the stream */
 int bsb200_batch_fetch(bsb200_ctx *ctx, bsb200_batch *b, bsb200_result_t *results,
 		uint32_t *cigars, const uint64_t *cgoff, uint32_t *ncigar, int32_t *status);
+/* Same, but the cigars come back DENSE and in pair order: pair i starts at word sum(ncigar[0..i-1]) of `cigars`
+ * (capacity cigar_cap_words; *total_words receives the number of words written, or needed when the call fails).
+ * This is the fast path: the ordering is done on the device and lands in the caller's buffer with one copy. */
+int bsb200_batch_fetch_dense(bsb200_ctx *ctx, bsb200_batch *b, bsb200_result_t *results,
+		uint32_t *cigars, uint64_t cigar_cap_words, uint64_t *total_words, uint32_t *ncigar, int32_t *status);
 void bsb200_batch_free(bsb200_ctx *ctx, bsb200_batch *b);
 
 /* nominal band width the kernels use for one pair (the GCUPS denominator) */

@@ -140,6 +140,17 @@ def test_waves_and_single_pair_api_agree(ctx):
     assert [rs[k] for k in api.RESULT_FIELDS] == list(one.results[5]) and np.array_equal(cg, one.cigar(5))
 
 
+def test_dense_fetch_equals_scattered_fetch(ctx):
+    b = synth.make_pairs(500, 200, seed=99)
+    a = ctx.epi8_batch(b, 1, 64, M26, -3, -2, 0, 0)
+    d = ctx.epi8_batch(b, 1, 64, M26, -3, -2, 0, 0, dense=True)
+    assert np.array_equal(a.results, d.results) and np.array_equal(a.ncigar, d.ncigar) and np.array_equal(a.status, d.status)
+    assert all(np.array_equal(x, y) for x, y in zip(a.cigars(), d.cigars()))
+    e1 = ctx.edit_batch(b, 0, 64)
+    e2 = ctx.edit_batch(b, 0, 64, dense=True)
+    assert np.array_equal(e1.results, e2.results) and all(np.array_equal(x, y) for x, y in zip(e1.cigars(), e2.cigars()))
+
+
 def cigar_score(q, t, res, cig, mtx, go, ge):
     """Affine score of the path a CIGAR describes (global): independent of the DP."""
     x, y, s = int(res[1]), int(res[3]), 0
