@@ -403,7 +403,8 @@ extern "C" int bsb200_batch_run(bsb200_ctx *ctx, bsb200_batch *b){
 			a.smax = -127; a.smin = 127;
 			for(int k=0;k<16;k++){ a.smax = std::max(a.smax, b->mtx[k]); a.smin = std::min(a.smin, b->mtx[k]); }
 			// all gap costs <= 0 (the normal case): saturation bounds that cannot bind are dropped (epi8_forward.cuh)
-			const bool fast = b->ge1 <= 0 && (int8_t)(b->go1 + b->ge1) <= 0 && (b->pw < 2 || (b->ge2 <= 0 && (int8_t)(b->go2 + b->ge2) <= 0));
+			// (linear gaps, pw = 0, stay on the literal kernel)
+			const bool fast = b->pw >= 1 && b->ge1 <= 0 && (int8_t)(b->go1 + b->ge1) <= 0 && (b->pw < 2 || (b->ge2 <= 0 && (int8_t)(b->go2 + b->ge2) <= 0));
 			int rc;
 			if(fast) rc = b->pw == 2 ? launch_epi8_forward<2, true>(ctx, a, np) : (b->pw == 1 ? launch_epi8_forward<1, true>(ctx, a, np) : launch_epi8_forward<0, true>(ctx, a, np));
 			else rc = b->pw == 2 ? launch_epi8_forward<2, false>(ctx, a, np) : (b->pw == 1 ? launch_epi8_forward<1, false>(ctx, a, np) : launch_epi8_forward<0, false>(ctx, a, np));
@@ -419,7 +420,7 @@ extern "C" int bsb200_batch_run(bsb200_ctx *ctx, bsb200_batch *b){
 			t.dense = b->want_cigar ? b->d_cig_dense.as<uint32_t>() : nullptr; t.dense_off = b->d_dense_off.as<uint64_t>();
 			t.dense_total = b->d_dense_total.as<unsigned long long>();
 			t.ncigar = b->d_ncigar.as<uint32_t>();
-			t.bandwidth = b->bandwidth; t.mode = b->mode; t.pw = b->pw; memcpy(t.mtx, b->mtx, 16);
+			t.bandwidth = b->bandwidth; t.mode = b->mode; t.pw = b->pw; t.ubias = fast ? 128 : 0; memcpy(t.mtx, b->mtx, 16);
 			t.go1 = b->go1; t.ge1 = b->ge1; t.go2 = b->go2; t.ge2 = b->ge2;
 			epi8_backcal_kernel<<<(np + 63) / 64, 64, 0, sb>>>(t);
 			CK(cudaGetLastError());
@@ -636,7 +637,7 @@ extern "C" int bsb200_edit_pairwise(bsb200_ctx *ctx, const uint8_t *qseq, uint32
 // ---- development aid: copy one pair's raw traceback block (epi8) back to the host -------------------
 // Layout: (tlen+1) rows of (pw+1) array images (8 regions of S bytes, see common.cuh), then (tlen+1) anchor
 // records of 20 ints {ub[17], rbeg, 0, 0}.  Valid after bsb200_batch_run for single-wave batches.
-extern "C" int64_t bsb200_debug_trace(bsb200_ctx *ctx, bsb200_batch *b, uint64_t pair, uint8_t *out, uint64_t cap, uint32_t *bw_out, int *pw_out){
+extern "C" int64_t bsb200_debug_trace(bsb200_ctx *ctx, bsb200_batch *b, uint64_t pair, uint8_t *out, uint64_t cap, uint32_t *bw_out, int *pw_out, int *ubias_out){
 	if(!ctx || !b || b->kind != 0 || pair >= b->n || b->waves.size() != 1 || b->empty[pair]) return -1;
 	std::vector<uint32_t> ql(1), tl(1);
 	cudaMemcpy(ql.data(), b->d_qlen.as<uint32_t>() + pair, 4, cudaMemcpyDeviceToHost);
@@ -647,5 +648,6 @@ extern "C" int64_t bsb200_debug_trace(bsb200_ctx *ctx, bsb200_batch *b, uint64_t
 	if(cudaMemcpy(out, ctx->trace.as<uint8_t>() + b->trace_off[pair], bytes, cudaMemcpyDeviceToHost) != cudaSuccess) return -1;
 	if(bw_out) *bw_out = bw;
 	if(pw_out) *pw_out = b->pw;
+	if(ubias_out) *ubias_out = (b->pw >= 1 && b->ge1 <= 0 && (int8_t)(b->go1 + b->ge1) <= 0 && (b->pw < 2 || (b->ge2 <= 0 && (int8_t)(b->go2 + b->ge2) <= 0))) ? 128 : 0;
 	return (int64_t)bytes;
 }

@@ -25,18 +25,20 @@ struct Epi8BtArgs {
 	uint32_t bandwidth;
 	int mode;
 	int pw;
+	int ubias;                   // 128 when the forward kernel stored u + 128 (FAST instantiations), else 0
 	int8_t mtx[16];
 	int8_t go1, ge1, go2, ge2;
 };
 
 struct TraceView {
-	const uint8_t *tr; const int32_t *meta; uint32_t bw, W, IB, RS; int tlen;
+	const uint8_t *tr; const int32_t *meta; uint32_t bw, W, IB, RS; int tlen, ubias;
 	__device__ __forceinline__ int beg(int row) const { return meta[(size_t)kMetaInts * (row + 1) + 17]; }
 	__device__ __forceinline__ int ub(int row, int j) const { return meta[(size_t)kMetaInts * (row + 1) + j]; }
 	// array arr (0 u, 1 e, 2 q) of the cell at band position p of a row
 	__device__ __forceinline__ int cell(int row, int arr, uint32_t p) const {
 		uint32_t j = p / W, i = p - j * W;
-		return (int)(int8_t)tr[(size_t)RS * (row + 1) + (size_t)arr * IB + epi8_cell_offset(j, i)];
+		uint8_t b = tr[(size_t)RS * (row + 1) + (size_t)arr * IB + epi8_cell_offset(j, i)];
+		return (int)(int8_t)(arr == 0 && ubias ? (uint8_t)(b ^ 0x80) : b);
 	}
 	// H(col,row) = anchor of the lane + its u cells up to col (bsalign.h:3187-3202); sets err when the lookup leaves the band
 	__device__ int score(int row, int col, int &err) const { return score_at(row, (row >= -1 && row < tlen) ? beg(row) : 0, col, err); }
@@ -64,7 +66,8 @@ struct TraceView {
 		for(int k=0;k<8;k++){
 			if((uint32_t)k < nch){
 				const uint32_t left = p.n - 8 * k;
-				const int w[4] = {p.v[k].x, p.v[k].y, p.v[k].z, p.v[k].w};
+				const int xm = ubias ? (int)0x80808080 : 0; // u + 128 as unsigned byte -> two's complement
+				const int w[4] = {p.v[k].x ^ xm, p.v[k].y ^ xm, p.v[k].z ^ xm, p.v[k].w ^ xm};
 				#pragma unroll
 				for(int q=0;q<4;q++){
 					if(left >= 2u * q + 2) s = __dp4a(w[q], p.mk, s);
@@ -80,7 +83,8 @@ struct TraceView {
 			for(int k=0;k<8;k++){
 				if(c0 + k >= nch) break;
 				const uint32_t left = p.n - 8 * (c0 + k);
-				const int w[4] = {v[k].x, v[k].y, v[k].z, v[k].w};
+				const int xm2 = ubias ? (int)0x80808080 : 0;
+				const int w[4] = {v[k].x ^ xm2, v[k].y ^ xm2, v[k].z ^ xm2, v[k].w ^ xm2};
 				#pragma unroll
 				for(int q=0;q<4;q++){
 					if(left >= 2u * q + 2) s = __dp4a(w[q], p.mk, s);
@@ -111,7 +115,8 @@ struct TraceView {
 			for(int k=0;k<8;k++){
 				if(c0 + k >= nch) break;
 				const uint32_t left = n - 8 * (c0 + k); // entries of this chunk that count (>= 1)
-				const int w[4] = {v[k].x, v[k].y, v[k].z, v[k].w};
+				const int xm2 = ubias ? (int)0x80808080 : 0;
+				const int w[4] = {v[k].x ^ xm2, v[k].y ^ xm2, v[k].z ^ xm2, v[k].w ^ xm2};
 				#pragma unroll
 				for(int q=0;q<4;q++){
 					if(left >= 2u * q + 2) s = __dp4a(w[q], mk, s);
@@ -135,7 +140,7 @@ __global__ void __launch_bounds__(128) epi8_backcal_kernel(const Epi8BtArgs a){
 	TraceView tv;
 	tv.bw = a.bandwidth ? a.bandwidth : (uint32_t)qlen;
 	tv.bw = (tv.bw + kLanes - 1) / kLanes * kLanes;
-	tv.W = tv.bw / kLanes; tv.IB = epi8_image_bytes(tv.W); tv.RS = tv.IB * (pw + 1); tv.tlen = tlen;
+	tv.W = tv.bw / kLanes; tv.IB = epi8_image_bytes(tv.W); tv.RS = tv.IB * (pw + 1); tv.tlen = tlen; tv.ubias = a.ubias;
 	tv.tr = a.trace + a.trace_off[pair];
 	tv.meta = (const int32_t*)(tv.tr + (size_t)tv.RS * (tlen + 1));
 	const int bw = (int)tv.bw;
@@ -191,7 +196,7 @@ __global__ void __launch_bounds__(128) epi8_backcal_kernel(const Epi8BtArgs a){
 		tv.begin(pd, need, lrow, lbeg, lcol, err);
 		int val = tv.finish(pd);
 		int u = 0, e = (int)(int8_t)(go1 + ge1), q = 0;
-		if(cellok){ u = (int)(int8_t)ru; if(pw >= 1) e = (int)(int8_t)re; if(pw == 2) q = (int)(int8_t)rq; }
+		if(cellok){ u = (int)(int8_t)(a.ubias ? (ru ^ 0x80u) : ru); if(pw >= 1) e = (int)(int8_t)re; if(pw == 2) q = (int)(int8_t)rq; }
 		else { u = 0; e = 0; q = 0; }
 		// ---- 3. act ------------------------------------------------------------------------------------------------
 		if(state == kDrun){

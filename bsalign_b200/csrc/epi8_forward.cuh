@@ -62,11 +62,19 @@ template<int K> __device__ __forceinline__ uint32_t ent_sel(const uint4 &c){
 	const uint32_t w = (K >> 1) == 0 ? c.x : (K >> 1) == 1 ? c.y : (K >> 1) == 2 ? c.z : c.w;
 	return (K & 1) ? (w >> 16) : w;   // PRMT reads only bits 15:0 of its selector
 }
+// entry k as ZERO-extended halves (for the +128 biased u bytes of the FAST kernels)
+template<int K> __device__ __forceinline__ uint32_t entz(const uint4 &c){
+	const uint32_t w = (K >> 1) == 0 ? c.x : (K >> 1) == 1 ? c.y : (K >> 1) == 2 ? c.z : c.w;
+	return prmt(w, 0u, (K & 1) ? 0x4342u : 0x4140u);
+}
 // low bytes of the two halves of ve (even entry) and vo (odd entry) -> one output word
 __device__ __forceinline__ uint32_t pack2(uint32_t ve, uint32_t vo){ return prmt(ve, vo, 0x6420u); }
 
 // PRMT selector that fetches (sext S[cA], sext S[cB]) from {column word, 0xC1C1C1C1}; code 4 = past the query end (-63)
 __device__ __forceinline__ uint32_t zsel(uint32_t cA, uint32_t cB){ return cA | ((8u | cA) << 4) | (cB << 8) | ((8u | cB) << 12); }
+// FAST kernels keep scores biased by +128 (unsigned): the selector fetches (S[cA]+128, 0, S[cB]+128, 0) from
+// {column word + 128, 0x00000041}: byte 4 = 65 = -63 + 128 (past the query end), byte 5 = 0
+__device__ __forceinline__ uint32_t zselb(uint32_t cA, uint32_t cB){ return cA | (5u << 4) | (cB << 8) | (5u << 12); }
 
 struct RowState { uint32_t f, g, h, u, nv; };
 
@@ -74,65 +82,102 @@ struct RowState { uint32_t f, g, h, u, nv; };
 __device__ __forceinline__ uint32_t not_fma(uint32_t x, uint32_t m1){ return x * m1 + m1; }
 
 // one DP step for the thread's two lanes.  PASS2=false: only the F/G chain (pass 1).
+// FAST=false: literal SSE arithmetic, every adds/subs with both saturation bounds, signed values.
+// FAST=true (all gap costs <= 0): u, z, h, f, g and the new u are kept BIASED by +128, so that a two-sided saturating
+// add of an unbiased term is ONE instruction (VIADDMNMX.RELU: min(a+b,255) then max(.,0)); bounds that cannot bind
+// are dropped: e,q <= 0 so e+u never exceeds 127; x-h <= 0 because h >= e+u and ge <= 0; h+goe and f+ge cannot exceed 127.
 template<int PW, bool FAST, bool PASS2>
 __device__ __forceinline__ void dp_step(RowState &s, uint32_t u, uint32_t e, uint32_t q, uint32_t z,
 		uint32_t GE, uint32_t GOE, uint32_t GP, uint32_t GQP, uint32_t NGOQ, uint32_t M1, uint32_t &un, uint32_t &en, uint32_t &qn){
+	if(FAST){
+		constexpr uint32_t C129 = 0x00810081u, C255 = 0x00ff00ffu;
+		// u, z, s.f, s.g biased; e, q, s.nv unbiased
+		const uint32_t ev = __viaddmax_s16x2(u, PW == 0 ? GE : e, 0u);         // adds(e,u) + 128   (linear gaps: e = ge)
+		uint32_t qv = 0, h;
+		if(PW == 2){
+			qv = __viaddmax_s16x2(u, q, 0u);
+			h = smax(smax3(ev, z, qv), smax(s.f, s.g));
+		} else h = smax3(ev, z, s.f);
+		const uint32_t cu = not_fma(u, M1);
+		if(PASS2){
+			const uint32_t ch = not_fma(h, M1);
+			un = __viaddmin_s16x2_relu(h, s.nv, C255);                              // subs(h, v) + 128
+			s.nv = __viaddmin_s16x2(__viaddmax_s16x2(u, ch, kLO), kONE, 0x00800080u); // -(subs(h,u)): u_b + ~h_b = u - h - 1
+			if(PW >= 1){
+				uint32_t x1 = __viaddmax_s16x2(ev, __vadd2(GE, kONE), kONE);        // adds(ev, ge) + 1 + 128
+				en = __viaddmax_s16x2(x1, ch, GOE);                                 // max(x - h, goe): x1 + ~h_b = x - h
+			}
+			if(PW == 2){
+				uint32_t x1 = __viaddmax_s16x2(qv, __vadd2(GP, kONE), kONE);
+				qn = __viaddmax_s16x2(x1, ch, GQP);
+			}
+			s.u = u;
+		}
+		if(PW == 0){
+			s.h = h;
+			uint32_t y = __viaddmax_s16x2(h, __vadd2(GE, C129), C129);            // adds(h, ge) + 128 + 129
+			s.f = __viaddmin_s16x2_relu(y, cu, C255);                               // subs(y, u) + 128: y' + ~u_b = y - u + 128
+		} else if(PW == 1){
+			uint32_t y = __viaddmax_s16x2(h, __vadd2(GOE, C129), C129);           // adds(h, goe) + 128 + 129
+			uint32_t f1 = __viaddmax_s16x2(s.f, __vadd2(GE, C129), y);            // max(adds(f, ge), y) + 128 + 129
+			s.f = __viaddmin_s16x2_relu(f1, cu, C255);
+			s.h = y;
+		} else {
+			uint32_t yb = __viaddmax_s16x2(h, GOE, 0u);                            // adds(h, goe) + 128
+			uint32_t f1 = __viaddmax_s16x2(s.f, __vadd2(GE, C129), __vadd2(yb, C129));
+			s.f = __viaddmin_s16x2_relu(f1, cu, C255);
+			yb = __viaddmin_s16x2_relu(yb, NGOQ, C255);                             // subs(., goq) + 128
+			uint32_t g1 = __viaddmax_s16x2(s.g, __vadd2(GP, C129), __vadd2(yb, C129));
+			s.g = __viaddmin_s16x2_relu(g1, cu, C255);
+			s.h = __vadd2(yb, C129);
+		}
+		return;
+	}
 	uint32_t ev, qv = 0, h;
-	if(PW == 0) ev = FAST ? sadd_lo(u, GE) : sadd(u, GE);
-	else ev = FAST ? sadd_lo(e, u) : sadd(e, u);
+	if(PW == 0) ev = sadd(u, GE);
+	else ev = sadd(e, u);
 	if(PW == 2){
-		qv = FAST ? sadd_lo(q, u) : sadd(q, u);
+		qv = sadd(q, u);
 		h = smax(smax3(ev, z, qv), smax(s.f, s.g));
 	} else h = smax3(ev, z, s.f);
-	const uint32_t cu = not_fma(u, M1);
+	const uint32_t cu = ~u;
 	if(PASS2){
-		const uint32_t ch = not_fma(h, M1);
+		const uint32_t ch = ~h;
 		un = sadd(h, s.nv);                                                    // u(x,y) = h - v(x-1,y)
 		s.nv = __viaddmin_s16x2(__viaddmax_s16x2(u, ch, kLO), kONE, 0x00800080u);  // -(subs(h,u)) = clamp(u - h, -127, 128)
-		if(PW >= 1){
-			if(FAST){
-				uint32_t x1 = __viaddmax_s16x2(ev, __vadd2(GE, kONE), 0xff81ff81u);   // adds(ev, ge) + 1
-				en = __viaddmax_s16x2(x1, ch, GOE);                                   // max(x - h, goe): (x+1) + ~h = x - h
-			} else en = smax(ssubc(sadd(ev, GE), ch), GOE);
-		}
-		if(PW == 2){
-			if(FAST){
-				uint32_t x1 = __viaddmax_s16x2(qv, __vadd2(GP, kONE), 0xff81ff81u);
-				qn = __viaddmax_s16x2(x1, ch, GQP);
-			} else qn = smax(ssubc(sadd(qv, GP), ch), GQP);
-		}
+		if(PW >= 1) en = smax(ssubc(sadd(ev, GE), ch), GOE);
+		if(PW == 2) qn = smax(ssubc(sadd(qv, GP), ch), GQP);
 		s.u = u;
 	}
 	if(PW == 0){
 		s.h = h;
-		s.f = ssubc(FAST ? sadd_lo(h, GE) : sadd(h, GE), cu);
+		s.f = ssubc(sadd(h, GE), cu);
 	} else {
-		uint32_t y = FAST ? sadd_lo(h, GOE) : sadd(h, GOE);
-		uint32_t f1 = FAST ? __viaddmax_s16x2(s.f, GE, y) : smax(sadd(s.f, GE), y);
-		s.f = ssubc(f1, cu);
+		uint32_t y = sadd(h, GOE);
+		s.f = ssubc(smax(sadd(s.f, GE), y), cu);
 		if(PW == 2){
 			y = sadd(y, NGOQ);
-			uint32_t g1 = FAST ? __viaddmax_s16x2(s.g, GP, y) : smax(sadd(s.g, GP), y);
-			s.g = ssubc(g1, cu);
+			s.g = ssubc(smax(sadd(s.g, GP), y), cu);
 		}
 		s.h = y; // the SSE code leaves h biased by the gap-open constant after the loop (:2958, :3177)
 	}
 }
 
 // sum of entries [0, count) of lane j of a row image, spread over the group's threads
-__device__ __forceinline__ int group_lane_sum(const int8_t *img, uint32_t j, uint32_t count, int t){
+// (ubias = 128 when the image holds u + 128 as unsigned bytes)
+__device__ __forceinline__ int group_lane_sum(const int8_t *img, uint32_t j, uint32_t count, int t, int ubias){
 	const unsigned gm = 0xffu << ((threadIdx.x & 31) & 24);
 	int s = 0;
-	for(uint32_t k=t;k<count;k+=kGroup) s += img[epi8_cell_offset(j, k)];
+	for(uint32_t k=t;k<count;k+=kGroup) s += (ubias ? (int)(uint8_t)img[epi8_cell_offset(j, k)] - ubias : (int)img[epi8_cell_offset(j, k)]);
 	s += __shfl_xor_sync(gm, s, 1);
 	s += __shfl_xor_sync(gm, s, 2);
 	s += __shfl_xor_sync(gm, s, 4);
 	return s;
 }
 // absolute H at band position pos (bsalign.h:3187-3197)
-__device__ __forceinline__ int group_getscore(const int8_t *sU, const int32_t *sUB, uint32_t W, uint32_t pos, int t){
+__device__ __forceinline__ int group_getscore(const int8_t *sU, const int32_t *sUB, uint32_t W, uint32_t pos, int t, int ubias){
 	uint32_t j = pos / W, i = pos - j * W;
-	return sUB[j] + group_lane_sum(sU, j, i + 1, t);
+	return sUB[j] + group_lane_sum(sU, j, i + 1, t, ubias);
 }
 
 template<int PW, bool FAST>
@@ -158,11 +203,15 @@ __global__ void __launch_bounds__(kFwdThreads) epi8_forward_kernel(const Epi8Arg
 	const int GOEi = (int8_t)(go1 + ge1), GQPi = (int8_t)(go2 + ge2);
 	const uint32_t GE = pk1(ge1), GOE = pk1(GOEi), GP = pk1(ge2), GQP = pk1(GQPi);
 	const uint32_t M1 = a.all_ones;
+	constexpr int UB = FAST ? 128 : 0;              // bias of the u bytes (and of z, h, f, g in registers)
+	#define UBYTE(raw) (FAST ? (int)(uint8_t)(raw) - 128 : (int)(int8_t)(raw))
+	#define ZSEL(ca, cb) (FAST ? zselb((ca), (cb)) : zsel((ca), (cb)))
 	const uint32_t NGOE = pk1(-GOEi), NGOQ = pk1(-clamp8(GOEi - GQPi)), NGQP = pk1(-GQPi);
 	// matrix columns: colw[tb] holds mtx[0*4+tb], mtx[1*4+tb], mtx[2*4+tb], mtx[3*4+tb] as bytes
 	uint32_t colw[4];
 	#pragma unroll
-	for(int c=0;c<4;c++) colw[c] = (uint32_t)(uint8_t)a.mtx[c] | ((uint32_t)(uint8_t)a.mtx[4 + c] << 8) | ((uint32_t)(uint8_t)a.mtx[8 + c] << 16) | ((uint32_t)(uint8_t)a.mtx[12 + c] << 24);
+	for(int c=0;c<4;c++) colw[c] = (uint32_t)(uint8_t)(a.mtx[c] + UB) | ((uint32_t)(uint8_t)(a.mtx[4 + c] + UB) << 8) | ((uint32_t)(uint8_t)(a.mtx[8 + c] + UB) << 16) | ((uint32_t)(uint8_t)(a.mtx[12 + c] + UB) << 24);
+	const uint32_t ZPAD = FAST ? 0x00000041u : 0xC1C1C1C1u;   // second PRMT source: the score past the query end (-63)
 
 	bool have = false, done = false;
 	uint32_t pair = 0, qlen = 1, tlen = 1, bw = 16, W = 1, IB = 128, row = 0, rbeg = 0, mov = 0;
@@ -215,10 +264,10 @@ __global__ void __launch_bounds__(kFwdThreads) epi8_forward_kernel(const Epi8Arg
 						vB = (two && pB < xp) ? ge1 : ext;
 					}
 					if(i >= W){ vA = 0; vB = 0; }
-					rU[TOFF(i)] = (int8_t)vA; rU[TOFF(i) + 1] = (int8_t)vB;
+					rU[TOFF(i)] = (int8_t)(vA + UB); rU[TOFF(i) + 1] = (int8_t)(vB + UB);
 					if(PW >= 1){ rE[TOFF(i)] = kEpi8Min; rE[TOFF(i) + 1] = kEpi8Min; }
 					if(PW == 2){ rQ[TOFF(i)] = kEpi8Min; rQ[TOFF(i) + 1] = kEpi8Min; }
-					*(uint16_t*)(rC + TOFF(i)) = (uint16_t)(i < W ? zsel(QCODE(pA), QCODE(pB)) : zsel(4, 4));
+					*(uint16_t*)(rC + TOFF(i)) = (uint16_t)(i < W ? ZSEL(QCODE(pA), QCODE(pB)) : ZSEL(4, 4));
 				}
 				for(int j=t;j<=kLanes;j+=kGroup){
 					int s = 0;
@@ -260,7 +309,7 @@ __global__ void __launch_bounds__(kFwdThreads) epi8_forward_kernel(const Epi8Arg
 			if((uint32_t)lim < mov) mov = (uint32_t)lim;
 		} else mov = 0;
 		if(mov){
-			rh = (mov - 1 < bw) ? group_getscore(sU, sUB, W, mov - 1, t) : kScoreMin;
+			rh = (mov - 1 < bw) ? group_getscore(sU, sUB, W, mov - 1, t, UB) : kScoreMin;
 			if(mov - 1 >= bw) stflag |= 1;
 		} else {
 			if(rbeg) rh = kScoreMin;
@@ -273,10 +322,10 @@ __global__ void __launch_bounds__(kFwdThreads) epi8_forward_kernel(const Epi8Arg
 			if(mov >= bw){
 				for(uint32_t i=0;i<IB/16;i++){
 					uint32_t xA = rbeg + mov + A * W + i, xB = xA + W;
-					*(uint16_t*)(rU + TOFF(i)) = 0;
+					*(uint16_t*)(rU + TOFF(i)) = (uint16_t)(UB | (UB << 8));
 					if(PW >= 1) *(uint16_t*)(rE + TOFF(i)) = 0;
 					if(PW == 2) *(uint16_t*)(rQ + TOFF(i)) = 0;
-					*(uint16_t*)(rC + TOFF(i)) = (uint16_t)(i < W ? zsel(QCODE(xA), QCODE(xB)) : zsel(4, 4));
+					*(uint16_t*)(rC + TOFF(i)) = (uint16_t)(i < W ? ZSEL(QCODE(xA), QCODE(xB)) : ZSEL(4, 4));
 				}
 				for(int j=t;j<=kLanes;j+=kGroup) sUB[j] = kScoreMin;
 				rbeg += mov;
@@ -285,7 +334,7 @@ __global__ void __launch_bounds__(kFwdThreads) epi8_forward_kernel(const Epi8Arg
 				// anchors of the old row advanced by the first mr cells of each block (:2310-2331)
 				for(int j=t;j<kLanes;j+=kGroup){
 					int s = sUB[j];
-					for(uint32_t k=0;k<mr;k++) s += sU[epi8_cell_offset(j, k)];
+					for(uint32_t k=0;k<mr;k++) s += UBYTE(sU[epi8_cell_offset(j, k)]);
 					sTmp[j] = s;
 				}
 				const int ub16 = sUB[kLanes];
@@ -337,7 +386,7 @@ __global__ void __launch_bounds__(kFwdThreads) epi8_forward_kernel(const Epi8Arg
 						const uint32_t i = W - mr + k;
 						uint32_t uB, eB = 0, qB = 0, cB;
 						if(t == 7){ // overhang cell k (:2370-2389)
-							uB = (uint32_t)(uint8_t)(int8_t)(k == 0 ? c : (k < d ? ge1 : ge2));
+							uB = (uint32_t)(uint8_t)((int8_t)(k == 0 ? c : (k < d ? ge1 : ge2)) + UB);
 							cB = QCODE(rbeg + bw + k);
 						} else {
 							uB = pairA(nU, k); eB = pairA(nE, k); qB = pairA(nQ, k);
@@ -349,7 +398,7 @@ __global__ void __launch_bounds__(kFwdThreads) epi8_forward_kernel(const Epi8Arg
 						rU[TOFF(i)] = (int8_t)pairB(fU, k); rU[TOFF(i) + 1] = (int8_t)uB;
 						if(PW >= 1){ rE[TOFF(i)] = (int8_t)pairB(fE, k); rE[TOFF(i) + 1] = (int8_t)eB; }
 						if(PW == 2){ rQ[TOFF(i)] = (int8_t)pairB(fQ, k); rQ[TOFF(i) + 1] = (int8_t)qB; }
-						*(uint16_t*)(rC + TOFF(i)) = (uint16_t)zsel(cA, cB);
+						*(uint16_t*)(rC + TOFF(i)) = (uint16_t)ZSEL(cA, cB);
 					}
 				} else {
 					// general path (rare: global mode hurrying to the end): gather from the previous row's image in
@@ -369,14 +418,14 @@ __global__ void __launch_bounds__(kFwdThreads) epi8_forward_kernel(const Epi8Arg
 								if(PW == 2) qv_ = (int8_t)pimg[2 * IB + off];
 							} else {
 								uint32_t k = P - bw;
-								uv = (int8_t)(k == 0 ? c : (k < d ? ge1 : ge2));
+								uv = (int8_t)(k == 0 ? c : (k < d ? ge1 : ge2)) + UB;
 							}
 							rU[TOFF(i) + ln] = (int8_t)uv;
 							if(PW >= 1) rE[TOFF(i) + ln] = (int8_t)ev_;
 							if(PW == 2) rQ[TOFF(i) + ln] = (int8_t)qv_;
 						}
 						uint32_t xA = rbeg + mov + A * W + i;
-						*(uint16_t*)(rC + TOFF(i)) = (uint16_t)zsel(QCODE(xA), QCODE(xA + W));
+						*(uint16_t*)(rC + TOFF(i)) = (uint16_t)ZSEL(QCODE(xA), QCODE(xA + W));
 					}
 				}
 				__syncwarp(gmask);
@@ -400,26 +449,26 @@ __global__ void __launch_bounds__(kFwdThreads) epi8_forward_kernel(const Epi8Arg
 		const uint32_t T32 = colw[tb & 3];
 		int h0;
 		{
-			int z0 = (int)(int8_t)prmt(T32, 0xC1C1C1C1u, (uint32_t)sC[0] & 7u);
-			int u0 = sU[0], t0;
+			int z0 = UBYTE(prmt(T32, ZPAD, (uint32_t)sC[0] & 7u) & 0xffu);
+			int u0 = UBYTE(sU[0]), t0;
 			h0 = (rh - sUB[0]) + z0;
 			if(PW == 0) t0 = u0 + ge1;
 			else if(PW == 1) t0 = u0 + sE[0];
 			else t0 = u0 + max((int)sE[0], (int)sQ[0]);
 			if(h0 >= t0){ if(h0 > kEpi8Max) h0 = kEpi8Max; } else h0 = kEpi8Min;
 		}
-		const uint32_t zmask = t == 0 ? 0xffff0000u : 0xffffffffu, zor = t == 0 ? (uint32_t)(h0 & 0xffff) : 0u;
+		const uint32_t zmask = t == 0 ? 0xffff0000u : 0xffffffffu, zor = t == 0 ? (uint32_t)((h0 + UB) & 0xffff) : 0u;
 		const uint32_t nchunk = (W + 7) / 8, nfull = W / 8;
 
 		// ---- pass 1: F (G) leaving every running block with nothing entering ------------------------
 		// (full chunks run without per-step guards; a ragged last chunk, W % 8 != 0, takes the guarded copy)
-		RowState st; st.f = pk1(kEpi8Min); st.g = pk1(kEpi8Min); st.h = 0; st.u = 0; st.nv = 0;
+		RowState st; st.f = pk1(kEpi8Min + UB); st.g = pk1(kEpi8Min + UB); st.h = 0; st.u = 0; st.nv = 0;
 		{
 			uint32_t dum0, dum1, dum2;
 			#define P1STEP(K, LEFT) { if((K) < (LEFT)){ \
-				uint32_t z = prmt(T32, 0xC1C1C1C1u, ent_sel<K>(cs4)); \
+				uint32_t z = prmt(T32, ZPAD, ent_sel<K>(cs4)); \
 				if((K) == 0 && c == 0) z = (z & zmask) | zor; \
-				dp_step<PW, FAST, false>(st, ent<K>(cu4), ent<K>(ce4), ent<K>(cq4), z, GE, GOE, GP, GQP, NGOQ, M1, dum0, dum1, dum2); } }
+				dp_step<PW, FAST, false>(st, FAST ? entz<K>(cu4) : ent<K>(cu4), ent<K>(ce4), ent<K>(cq4), z, GE, GOE, GP, GQP, NGOQ, M1, dum0, dum1, dum2); } }
 			#define P1CHUNK(LEFT) { \
 				const uint4 cu4 = *(const uint4*)(rU + 128 * c), cs4 = *(const uint4*)(rC + 128 * c); \
 				uint4 ce4 = cu4, cq4 = cu4; \
@@ -433,8 +482,8 @@ __global__ void __launch_bounds__(kFwdThreads) epi8_forward_kernel(const Epi8Arg
 			#undef P1CHUNK
 			#undef P1STEP
 		}
-		sF[A] = (int8_t)lo16(st.f); sF[B] = (int8_t)hi16(st.f);
-		if(PW == 2){ sF[16 + A] = (int8_t)lo16(st.g); sF[16 + B] = (int8_t)hi16(st.g); }
+		sF[A] = (int8_t)(lo16(st.f) - UB); sF[B] = (int8_t)(hi16(st.f) - UB);
+		if(PW == 2){ sF[16 + A] = (int8_t)(lo16(st.g) - UB); sF[16 + B] = (int8_t)(hi16(st.g) - UB); }
 		__syncwarp();
 		// ---- F penetration (bsalign.h:2639-2652): exact 16-step scalar scan, every thread redundantly ---
 		{
@@ -454,16 +503,16 @@ __global__ void __launch_bounds__(kFwdThreads) epi8_forward_kernel(const Epi8Arg
 				s = tW + fj - (ubn - ubp);
 				if(PW == 2) s2 = tW2 + gj - (ubn - ubp);
 			}
-			st.f = pk(finA, finB); st.g = pk(ginA, ginB);
+			st.f = pk(finA + UB, finB + UB); st.g = pk(ginA + UB, ginB + UB);
 		}
 		// ---- pass 2: the row, written in place (bsalign.h:2934-2957 etc.) ------------------------------
 		uint32_t unew0 = 0;
 		st.nv = 0; st.h = 0; st.u = 0;
 		{
 			#define P2STEP(K, LEFT) { if((K) < (LEFT)){ \
-				uint32_t z = prmt(T32, 0xC1C1C1C1u, ent_sel<K>(cs4)); \
+				uint32_t z = prmt(T32, ZPAD, ent_sel<K>(cs4)); \
 				if((K) == 0 && c == 0) z = (z & zmask) | zor; \
-				dp_step<PW, FAST, true>(st, ent<K>(cu4), ent<K>(ce4), ent<K>(cq4), z, GE, GOE, GP, GQP, NGOQ, M1, un[K], en[K], qn[K]); } }
+				dp_step<PW, FAST, true>(st, FAST ? entz<K>(cu4) : ent<K>(cu4), ent<K>(ce4), ent<K>(cq4), z, GE, GOE, GP, GQP, NGOQ, M1, un[K], en[K], qn[K]); } }
 			#define P2CHUNK(LEFT, RAGGED) { \
 				const uint4 cu4 = *(const uint4*)(rU + 128 * c), cs4 = *(const uint4*)(rC + 128 * c); \
 				uint4 ce4 = cu4, cq4 = cu4; \
@@ -485,21 +534,24 @@ __global__ void __launch_bounds__(kFwdThreads) epi8_forward_kernel(const Epi8Arg
 		}
 		// ---- tail (bsalign.h:2618-2636) ------------------------------------------------------------------
 		{
-			uint32_t h = st.h;
+			// back to plain signed values (FAST keeps h biased by 128, or by 128+129 behind the gap-open add)
+			constexpr int HB = FAST ? (PW == 0 ? 128 : 257) : 0;
+			uint32_t h = pk(lo16(st.h) - HB, hi16(st.h) - HB);
+			const uint32_t ul = pk(lo16(st.u) - UB, hi16(st.u) - UB);
 			if(PW == 1) h = sadd(h, NGOE);
 			else if(PW == 2) h = sadd(h, NGQP);
-			const uint32_t vt = ssubc(h, ~st.u);
+			const uint32_t vt = ssubc(h, ~ul);
 			int vtA = lo16(vt), vtB = hi16(vt);
 			int vprev = __shfl_up_sync(0xffffffffu, vtB, 1, kGroup);
 			if(t == 0) vprev = 0;
-			int uA = clamp8(lo16(unew0) - vprev);
-			int uB = clamp8(hi16(unew0) - vtA);
+			int uA = clamp8(lo16(unew0) - UB - vprev);
+			int uB = clamp8(hi16(unew0) - UB - vtA);
 			__syncwarp();
 			sUB[A + 1] += vtA;
 			sUB[B + 1] += vtB;
 			if(t == 0){ sUB[0] += uA; uA = 0; sUB[17] = (int32_t)rbeg; }
-			rU[0] = (int8_t)uA;
-			rU[1] = (int8_t)uB;
+			rU[0] = (int8_t)(uA + UB);
+			rU[1] = (int8_t)(uB + UB);
 		}
 		__syncwarp();
 		// ---- stream the finished row to the traceback store ---------------------------------------------
@@ -541,14 +593,14 @@ __global__ void __launch_bounds__(kFwdThreads) epi8_forward_kernel(const Epi8Arg
 		}
 		// ---- end-point candidates (bsalign.h:4022-4045) ---------------------------------------------------
 		if(mode != 0 && rbeg + bw >= qlen){
-			int sc = group_getscore(sU, sUB, W, qlen - 1 - rbeg, t);
+			int sc = group_getscore(sU, sUB, W, qlen - 1 - rbeg, t, UB);
 			if(sc > best){ best = sc; best_qe = (int)qlen - 1; best_te = (int)row; }
 		}
 		row++;
 		if(have && row == tlen){
 			if(mode == 0){
 				uint32_t pos = qlen - 1 - rbeg;
-				if(pos < bw) best = group_getscore(sU, sUB, W, pos, t);
+				if(pos < bw) best = group_getscore(sU, sUB, W, pos, t, UB);
 				else { best = kScoreMin; stflag |= 1; }
 				best_qe = (int)qlen - 1; best_te = (int)tlen - 1;
 			} else {
@@ -562,7 +614,7 @@ __global__ void __launch_bounds__(kFwdThreads) epi8_forward_kernel(const Epi8Arg
 					for(uint32_t c=0;c<nck;c++){
 						uint32_t lo = c * 32, hi = lo + 32 < W ? lo + 32 : W;
 						int run = 0, mx = -32767;
-						for(uint32_t i=lo;i<hi;i++){ run += p[TOFF(i)]; if(run > mx) mx = run; }
+						for(uint32_t i=lo;i<hi;i++){ run += UBYTE(p[TOFF(i)]); if(run > mx) mx = run; }
 						int hh = Scr + mx;
 						if(hh > Max){ Max = hh; Idx = (uint32_t)j | (c << 8); }
 						Scr += run;
@@ -587,7 +639,7 @@ __global__ void __launch_bounds__(kFwdThreads) epi8_forward_kernel(const Epi8Arg
 					uint32_t bl = bi & 0xff, bc = bi >> 8;
 					uint32_t x = bc * 32, y = (bc + 1) * 32 < W ? (bc + 1) * 32 : W;
 					uint32_t pos = x; int umax = kScoreMin, uscr = 0;
-					for(;x<y;x++){ uscr += sU[epi8_cell_offset(bl, x)]; if(uscr > umax){ pos = x; umax = uscr; } }
+					for(;x<y;x++){ uscr += UBYTE(sU[epi8_cell_offset(bl, x)]); if(uscr > umax){ pos = x; umax = uscr; } }
 					best = max_score; best_qe = (int)(rbeg + bl * W + pos); best_te = (int)tlen - 1;
 				}
 				__syncwarp(gmask);
@@ -603,6 +655,8 @@ __global__ void __launch_bounds__(kFwdThreads) epi8_forward_kernel(const Epi8Arg
 	}
 	#undef QCODE
 	#undef TOFF
+	#undef UBYTE
+	#undef ZSEL
 }
 
 } // namespace bsb200

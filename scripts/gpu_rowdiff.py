@@ -9,13 +9,13 @@ from bsalign_b200 import api, synth
 def rowdiff(ctx, q, t, mode, bw_req, mtx, gaps, maxshow=3):
     L = api.lib()
     L.bsb200_debug_trace.restype = ctypes.c_int64
-    L.bsb200_debug_trace.argtypes = [ctypes.c_void_p] * 2 + [ctypes.c_uint64, ctypes.c_void_p, ctypes.c_uint64, ctypes.c_void_p, ctypes.c_void_p]
+    L.bsb200_debug_trace.argtypes = [ctypes.c_void_p] * 2 + [ctypes.c_uint64, ctypes.c_void_p, ctypes.c_uint64, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]
     b = synth.PairBatch.from_lists([(q, t)])
     rb = ctx.upload("epi8", b, mode, bw_req, mtx, gaps)
     rb.run()
     buf = np.zeros(64 << 20, dtype=np.uint8)
-    bw = ctypes.c_uint32(0); pw = ctypes.c_int(0)
-    nbytes = L.bsb200_debug_trace(ctx._h, rb._h, 0, buf.ctypes.data, buf.nbytes, ctypes.byref(bw), ctypes.byref(pw))
+    bw = ctypes.c_uint32(0); pw = ctypes.c_int(0); ubias = ctypes.c_int(0)
+    nbytes = L.bsb200_debug_trace(ctx._h, rb._h, 0, buf.ctypes.data, buf.nbytes, ctypes.byref(bw), ctypes.byref(pw), ctypes.byref(ubias))
     assert nbytes > 0, nbytes
     bw, pw = bw.value, pw.value
     tlen = len(t)
@@ -34,6 +34,8 @@ def rowdiff(ctx, q, t, mode, bw_req, mtx, gaps, maxshow=3):
     for y in range(tlen):
         gb = int(meta[y + 1, 17]); gub = meta[y + 1, :17]
         gu = rows[y + 1, 0][idx]
+        if ubias.value:
+            gu = (gu.view(np.uint8).astype(np.int16) - ubias.value).astype(np.int8)
         ge = rows[y + 1, 1][idx] if pw >= 1 else None
         gq = rows[y + 1, 2][idx] if pw == 2 else None
         ok = gb == begs[y] and np.array_equal(gub, ub[y]) and np.array_equal(gu, u[y]) and (pw < 1 or np.array_equal(ge, e[y])) and (pw < 2 or np.array_equal(gq, qq[y]))
@@ -51,6 +53,8 @@ def rowdiff(ctx, q, t, mode, bw_req, mtx, gaps, maxshow=3):
 if __name__ == "__main__":
     ctx = api.Context(0)
     m = synth.score_matrix(2, -6)
+    b = synth.make_pairs(1, 300, seed=0)
+    rowdiff(ctx, b.query(0), b.target(0), 0, 128, m, (0, -2, 0, 0))
     b = synth.make_pairs(1, 100, seed=5)
     rowdiff(ctx, b.query(0), b.target(0), 0, 32, m, (-3, -2, 0, 0))
     rowdiff(ctx, b.query(0), b.target(0), 1, 0, m, (-3, -2, 0, 0))
