@@ -35,7 +35,7 @@ WORKLOADS = {
                desc="BASELINE configs[2]: 10k pairs 10kb x 10kb ONT-like, overlap, band 512"),
     "c4": dict(kind="edit", pairs=1000000, qlen=300, err=(0.02, 0.02, 0.02), mode=0, bandwidth=64,
                desc="BASELINE configs[3]: 1M pairs 300bp x 300bp, 2-bit edit, band 64"),
-    "g10k": dict(kind="epi8", pairs=690, qlen=10000, err=(0.03, 0.03, 0.04), mode=0, bandwidth=0,
+    "g10k": dict(kind="epi8", pairs=592, qlen=10000, err=(0.03, 0.03, 0.04), mode=0, bandwidth=0,
                  desc="north_star target: 10kb x 10kb global, full band"),
 }
 MATRIX = (2, -6)

@@ -192,7 +192,7 @@ extern "C" bsb200_batch *bsb200_batch_upload(bsb200_ctx *ctx, int kind, uint64_t
 		if(qlen[i] == 0 || tlen[i] == 0){ b->empty[i] = 1; work[i] = 0; tbytes[i] = 0; continue; } // bsalign.h:1051-1054
 		if(kind == 0){
 			bw = bsb200_epi8_bandwidth(qlen[i], bandwidth);
-			tbytes[i] = ((uint64_t)epi8_image_bytes(bw / 16) * (b->pw + 1) + kMetaInts * 4) * ((uint64_t)tlen[i] + 1);
+			tbytes[i] = ((uint64_t)epi8_row_bytes(bw / 16, b->pw) + kMetaInts * 4) * ((uint64_t)tlen[i] + 1); // upper bound: with sub-lane anchors
 			tbytes[i] = (tbytes[i] + 15) / 16 * 16;
 			b->cells += (uint64_t)std::min<uint32_t>(bw, (qlen[i] + 15) / 16 * 16) * tlen[i];
 			b->trace_bytes += ((uint64_t)bw * (b->pw + 1) + 84) * tlen[i];
@@ -319,22 +319,55 @@ extern "C" bsb200_batch *bsb200_batch_upload(bsb200_ctx *ctx, int kind, uint64_t
 	return b;
 }
 
-template<int PW, bool FAST>
-static int launch_epi8_forward(bsb200_ctx *ctx, const Epi8Args &a, uint32_t npairs){
-	int threads = kFwdThreads;
-	while(threads >= 32 && (size_t)(threads / kGroup) * a.group_smem > ctx->smem_optin) threads >>= 1;
-	if(threads < 32){ ctx->err = "band too wide for the shared-memory row buffers"; return -1; }
-	size_t smem = (size_t)(threads / kGroup) * a.group_smem;
-	CK(cudaFuncSetAttribute(epi8_forward_kernel<PW, FAST>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-	int per_sm = 1;
-	CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, epi8_forward_kernel<PW, FAST>, threads, smem));
-	if(per_sm < 1) per_sm = 1;
-	uint32_t groups = threads / kGroup;
-	uint32_t grid = std::min<uint32_t>((npairs + groups - 1) / groups, (uint32_t)(ctx->num_sms * per_sm));
-	if(grid == 0) grid = 1;
-	epi8_forward_kernel<PW, FAST><<<grid, threads, smem, ctx->stream>>>(a);
-	CK(cudaGetLastError());
-	return 0;
+template<int PW, bool FAST, bool ANCH>
+static int launch_epi8_forward(bsb200_ctx *ctx, Epi8Args a, uint32_t npairs){
+	// CTA shape: as many groups per SM as the shared memory allows.  Normally 128 threads = 4 warps x 4 groups; a wide band
+	// (tens of KB per group) does better with one-warp CTAs that run fewer than 4 groups each.
+	const size_t sm_bytes = ctx->smem_optin + 1024;   // per-SM shared memory ~ opt-in maximum per block + its reserved KB
+	int best_threads = 0; uint32_t best_gpw = 0, best_groups = 0;
+	double best_cost = 1e30;
+	const int shapes[6][2] = {{128, 4}, {64, 4}, {32, 4}, {32, 3}, {32, 2}, {32, 1}};
+	for(auto &sh : shapes){
+		size_t per_cta = (size_t)(sh[0] / 32) * sh[1] * a.group_smem;
+		if(per_cta > ctx->smem_optin) continue;
+		uint32_t ctas = (uint32_t)std::min<size_t>(sm_bytes / (per_cta + 1024), 2048 / sh[0]);
+		ctas = std::min<uint32_t>(ctas, 32);
+		uint32_t groups = ctas * (sh[0] / 32) * sh[1];
+		if(!groups) continue;
+		// rounds needed to seat every pair x relative cost of a round (a warp instruction serves gpw groups; measured
+		// on 10 kb bands: a round at 1 group per warp takes ~1.75x a round at 4)
+		uint64_t slots = (uint64_t)groups * ctx->num_sms;
+		double cost = (double)((npairs + slots - 1) / slots) * (1.0 + 0.25 * (4 - sh[1]));
+		if(cost < best_cost - 1e-9 || (cost < best_cost + 1e-9 && groups > best_groups)){ best_cost = cost; best_groups = groups; best_threads = sh[0]; best_gpw = sh[1]; }
+	}
+	if(!best_groups){ ctx->err = "band too wide for the shared-memory row buffers"; return -1; }
+	a.gpw = best_gpw;
+	const int threads = best_threads;
+	const size_t smem = (size_t)(threads / 32) * best_gpw * a.group_smem;
+	auto go = [&](auto kernel) -> int {
+		CK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+		int per_sm = 1;
+		CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, threads, smem));
+		if(per_sm < 1) per_sm = 1;
+		uint32_t groups = (threads / 32) * best_gpw;
+		uint32_t grid = std::min<uint32_t>((npairs + groups - 1) / groups, (uint32_t)(ctx->num_sms * per_sm));
+		if(grid == 0) grid = 1;
+		kernel<<<grid, threads, smem, ctx->stream>>>(a);
+		CK(cudaGetLastError());
+		return 0;
+	};
+	if(best_gpw < 4){
+		if constexpr (ANCH) return go(epi8_forward_kernel<PW, FAST, true, true>);
+		else { ctx->err = "internal: narrow warps without anchors"; return -1; }
+	}
+	return go(epi8_forward_kernel<PW, FAST, ANCH, false>);
+}
+
+template<bool FAST, bool ANCH>
+static int launch_epi8_forward_pw(bsb200_ctx *ctx, const Epi8Args &a, uint32_t npairs, int pw){
+	if(pw == 2) return launch_epi8_forward<2, FAST, ANCH>(ctx, a, npairs);
+	if(pw == 1) return launch_epi8_forward<1, FAST, ANCH>(ctx, a, npairs);
+	return launch_epi8_forward<0, FAST, ANCH>(ctx, a, npairs);
 }
 
 template<int WR>
@@ -405,9 +438,11 @@ extern "C" int bsb200_batch_run(bsb200_ctx *ctx, bsb200_batch *b){
 			// all gap costs <= 0 (the normal case): saturation bounds that cannot bind are dropped (epi8_forward.cuh)
 			// (linear gaps, pw = 0, stay on the literal kernel)
 			const bool fast = b->pw >= 1 && b->ge1 <= 0 && (int8_t)(b->go1 + b->ge1) <= 0 && (b->pw < 2 || (b->ge2 <= 0 && (int8_t)(b->go2 + b->ge2) <= 0));
+			const bool anch = epi8_use_anchors(b->max_bw / 16);
+			a.gpw = 4;
 			int rc;
-			if(fast) rc = b->pw == 2 ? launch_epi8_forward<2, true>(ctx, a, np) : (b->pw == 1 ? launch_epi8_forward<1, true>(ctx, a, np) : launch_epi8_forward<0, true>(ctx, a, np));
-			else rc = b->pw == 2 ? launch_epi8_forward<2, false>(ctx, a, np) : (b->pw == 1 ? launch_epi8_forward<1, false>(ctx, a, np) : launch_epi8_forward<0, false>(ctx, a, np));
+			if(fast) rc = anch ? launch_epi8_forward_pw<true, true>(ctx, a, np, b->pw) : launch_epi8_forward_pw<true, false>(ctx, a, np, b->pw);
+			else rc = anch ? launch_epi8_forward_pw<false, true>(ctx, a, np, b->pw) : launch_epi8_forward_pw<false, false>(ctx, a, np, b->pw);
 			if(rc) return rc;
 			ctx->timing.forward_launches++;
 			CK(cudaEventRecord(evs[wi * 4 + 1], st));
@@ -420,7 +455,7 @@ extern "C" int bsb200_batch_run(bsb200_ctx *ctx, bsb200_batch *b){
 			t.dense = b->want_cigar ? b->d_cig_dense.as<uint32_t>() : nullptr; t.dense_off = b->d_dense_off.as<uint64_t>();
 			t.dense_total = b->d_dense_total.as<unsigned long long>();
 			t.ncigar = b->d_ncigar.as<uint32_t>();
-			t.bandwidth = b->bandwidth; t.mode = b->mode; t.pw = b->pw; t.ubias = fast ? 128 : 0; memcpy(t.mtx, b->mtx, 16);
+			t.bandwidth = b->bandwidth; t.mode = b->mode; t.pw = b->pw; t.ubias = fast ? 128 : 0; t.anch = anch ? 1 : 0; memcpy(t.mtx, b->mtx, 16);
 			t.go1 = b->go1; t.ge1 = b->ge1; t.go2 = b->go2; t.ge2 = b->ge2;
 			epi8_backcal_kernel<<<(np + 63) / 64, 64, 0, sb>>>(t);
 			CK(cudaGetLastError());
@@ -643,7 +678,7 @@ extern "C" int64_t bsb200_debug_trace(bsb200_ctx *ctx, bsb200_batch *b, uint64_t
 	cudaMemcpy(ql.data(), b->d_qlen.as<uint32_t>() + pair, 4, cudaMemcpyDeviceToHost);
 	cudaMemcpy(tl.data(), b->d_tlen.as<uint32_t>() + pair, 4, cudaMemcpyDeviceToHost);
 	uint32_t bw = bsb200_epi8_bandwidth(ql[0], b->bandwidth);
-	uint64_t bytes = ((uint64_t)epi8_image_bytes(bw / 16) * (b->pw + 1) + kMetaInts * 4) * ((uint64_t)tl[0] + 1);
+	uint64_t bytes = ((uint64_t)(epi8_use_anchors(b->max_bw / 16) ? epi8_row_bytes(bw / 16, b->pw) : epi8_image_bytes(bw / 16) * (b->pw + 1)) + kMetaInts * 4) * ((uint64_t)tl[0] + 1);
 	if(bytes > cap) return -(int64_t)bytes;
 	if(cudaMemcpy(out, ctx->trace.as<uint8_t>() + b->trace_off[pair], bytes, cudaMemcpyDeviceToHost) != cudaSuccess) return -1;
 	if(bw_out) *bw_out = bw;

@@ -34,6 +34,16 @@ __host__ __device__ __forceinline__ uint32_t epi8_image_bytes(uint32_t W){ retur
 // byte offset of band position p (lane j = p / W, step i = p % W) inside one array image
 __host__ __device__ __forceinline__ uint32_t epi8_cell_offset(uint32_t j, uint32_t i){ return (i >> 3) * 128 + (j >> 1) * 16 + (i & 7) * 2 + (j & 1); }
 
+// Sub-lane anchors for the traceback: besides the 17 block anchors of the reference, a row carries the absolute score
+// at the end of every 32nd step of every lane (int32 [g-1][lane], g = 1 .. ngrp-1), so that a score lookup sums at
+// most 32 cells (4 chunks) instead of a whole lane.
+constexpr uint32_t kAnchorSteps = 32;
+__host__ __device__ __forceinline__ uint32_t epi8_anchor_groups(uint32_t W){ return (W + kAnchorSteps - 1) / kAnchorSteps; }
+__host__ __device__ __forceinline__ uint32_t epi8_anchor_bytes(uint32_t W){ return (epi8_anchor_groups(W) - 1) * 64; }
+// the anchors pay off (and are written) only when the widest lane of a batch exceeds 64 steps
+__host__ __device__ __forceinline__ bool epi8_use_anchors(uint32_t maxW){ return maxW > 64; }
+__host__ __device__ __forceinline__ uint32_t epi8_row_bytes(uint32_t W, int pw){ return epi8_image_bytes(W) * (pw + 1) + epi8_anchor_bytes(W); }
+
 struct CigarSink {
 	uint32_t *buf; uint32_t cap, n, run; int err;
 	__device__ __forceinline__ void put(uint32_t w){ if(buf){ if(n < cap) buf[n] = w; else err |= 4; } n++; }

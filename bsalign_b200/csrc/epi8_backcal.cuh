@@ -25,13 +25,14 @@ struct Epi8BtArgs {
 	uint32_t bandwidth;
 	int mode;
 	int pw;
+	int anch;                    // rows carry sub-lane anchors (written by the ANCH forward instantiations)
 	int ubias;                   // 128 when the forward kernel stored u + 128 (FAST instantiations), else 0
 	int8_t mtx[16];
 	int8_t go1, ge1, go2, ge2;
 };
 
 struct TraceView {
-	const uint8_t *tr; const int32_t *meta; uint32_t bw, W, IB, RS; int tlen, ubias;
+	const uint8_t *tr; const int32_t *meta; uint32_t bw, W, IB, RS, AOFF; int tlen, ubias, anch;
 	__device__ __forceinline__ int beg(int row) const { return meta[(size_t)kMetaInts * (row + 1) + 17]; }
 	__device__ __forceinline__ int ub(int row, int j) const { return meta[(size_t)kMetaInts * (row + 1) + j]; }
 	// array arr (0 u, 1 e, 2 q) of the cell at band position p of a row
@@ -51,9 +52,10 @@ struct TraceView {
 		if(need && !ok) err |= 1;
 		uint32_t up = ok ? (uint32_t)pos : 0u, j = up / W;
 		int rw = ok ? row : -1;
-		p.n = ok ? up - j * W + 1 : 0u;
-		p.ub = ok ? ub(rw, j) : kScoreMin;
-		p.r = tr + (size_t)RS * (rw + 1) + (size_t)(j >> 1) * 16;
+		const uint32_t i = up - j * W, g = anch ? i / kAnchorSteps : 0u;   // the sum starts at the sub-lane anchor before step 32g
+		p.n = ok ? i - g * kAnchorSteps + 1 : 0u;
+		p.ub = ok ? (g ? *(const int32_t*)(tr + (size_t)RS * (rw + 1) + AOFF + ((g - 1) * 16 + j) * 4) : ub(rw, j)) : kScoreMin;
+		p.r = tr + (size_t)RS * (rw + 1) + (size_t)(j >> 1) * 16 + (size_t)g * (kAnchorSteps / 8) * 128;
 		p.mk = (j & 1) ? 0x01000100 : 0x00010001;
 		const uint32_t nch = (p.n + 7) >> 3;
 		#pragma unroll
@@ -96,35 +98,9 @@ struct TraceView {
 	}
 	// same with the row's band offset supplied by the caller (the walk keeps the offsets of rows tb, tb-1, tb-2 in registers)
 	__device__ int score_at(int row, int rbeg, int col, int &err) const {
-		if(row < -1 || row >= tlen){ err |= 1; return kScoreMin; }
-		int64_t pos = (int64_t)col - rbeg;
-		if(pos < 0 || pos >= (int64_t)bw){ err |= 1; return kScoreMin; }
-		uint32_t j = (uint32_t)pos / W, n = (uint32_t)pos - j * W + 1;
-		int s = ub(row, j);
-		// the lane's cells are every other byte of its thread's 16 bytes per chunk: dp4a with a 0/1 mask adds two per word
-		const uint8_t *r = tr + (size_t)RS * (row + 1) + (size_t)(j >> 1) * 16;
-		const int mk = (j & 1) ? 0x01000100 : 0x00010001;
-		// all chunk loads of a round are issued before the first sum so that a lookup costs one memory round trip
-		// per 8 chunks (64 steps of the lane) instead of one per chunk
-		const uint32_t nch = (n + 7) >> 3;
-		for(uint32_t c0=0;c0<nch;c0+=8){
-			int4 v[8];
-			#pragma unroll
-			for(int k=0;k<8;k++) if(c0 + k < nch) v[k] = *(const int4*)(r + 128 * (c0 + k));
-			#pragma unroll
-			for(int k=0;k<8;k++){
-				if(c0 + k >= nch) break;
-				const uint32_t left = n - 8 * (c0 + k); // entries of this chunk that count (>= 1)
-				const int xm2 = ubias ? (int)0x80808080 : 0;
-				const int w[4] = {v[k].x ^ xm2, v[k].y ^ xm2, v[k].z ^ xm2, v[k].w ^ xm2};
-				#pragma unroll
-				for(int q=0;q<4;q++){
-					if(left >= 2u * q + 2) s = __dp4a(w[q], mk, s);
-					else if(left == 2u * q + 1) s = __dp4a(w[q], mk & 0x0000ffff, s);
-				}
-			}
-		}
-		return s;
+		Pending p;
+		begin(p, true, row, rbeg, col, err);
+		return finish(p);
 	}
 };
 
@@ -140,7 +116,7 @@ __global__ void __launch_bounds__(128) epi8_backcal_kernel(const Epi8BtArgs a){
 	TraceView tv;
 	tv.bw = a.bandwidth ? a.bandwidth : (uint32_t)qlen;
 	tv.bw = (tv.bw + kLanes - 1) / kLanes * kLanes;
-	tv.W = tv.bw / kLanes; tv.IB = epi8_image_bytes(tv.W); tv.RS = tv.IB * (pw + 1); tv.tlen = tlen; tv.ubias = a.ubias;
+	tv.W = tv.bw / kLanes; tv.IB = epi8_image_bytes(tv.W); tv.RS = a.anch ? epi8_row_bytes(tv.W, pw) : tv.IB * (pw + 1); tv.AOFF = tv.IB * (pw + 1); tv.anch = a.anch; tv.tlen = tlen; tv.ubias = a.ubias;
 	tv.tr = a.trace + a.trace_off[pair];
 	tv.meta = (const int32_t*)(tv.tr + (size_t)tv.RS * (tlen + 1));
 	const int bw = (int)tv.bw;

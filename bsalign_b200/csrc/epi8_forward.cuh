@@ -37,6 +37,7 @@ struct Epi8Args {
 	uint32_t bandwidth;          // requested (0 = full)
 	uint32_t max_img;            // largest array image (bytes) in the batch (smem sizing)
 	uint32_t group_smem;         // bytes of shared memory per group
+	uint32_t gpw;                // groups per warp (4; fewer when a wide band makes shared memory the limit)
 	int mode;
 	int8_t mtx[16];
 	int8_t go1, ge1, go2, ge2;
@@ -180,15 +181,20 @@ __device__ __forceinline__ int group_getscore(const int8_t *sU, const int32_t *s
 	return sUB[j] + group_lane_sum(sU, j, i + 1, t, ubias);
 }
 
-template<int PW, bool FAST>
+// ANCH: also write the sub-lane anchors (lanes longer than 64 steps; see common.cuh)
+// NARROW: fewer than 4 groups per warp (very wide bands); the normal kernels keep compile-time full-warp masks
+template<int PW, bool FAST, bool ANCH, bool NARROW>
 __global__ void __launch_bounds__(kFwdThreads) epi8_forward_kernel(const Epi8Args a){
 	extern __shared__ __align__(16) uint8_t smem_raw[];
 	const int lane = threadIdx.x & 31;
 	const int t = lane & 7;
 	const unsigned gmask = 0xffu << (lane & 24);
+	// wide bands: only the first gpw groups of a warp work (more warps then fit the shared memory); the others leave
+	if(NARROW && (uint32_t)(lane >> 3) >= a.gpw) return;
+	const unsigned amask = NARROW ? ((1u << (8 * a.gpw)) - 1u) : 0xffffffffu;
 	const int A = 2 * t, B = A + 1;
 	const uint32_t IMG = a.max_img;                 // bytes reserved per array image in shared memory
-	uint8_t *gs = smem_raw + (size_t)(threadIdx.x >> 3) * a.group_smem;
+	uint8_t *gs = smem_raw + (size_t)(NARROW ? (threadIdx.x >> 5) * a.gpw + (lane >> 3) : (threadIdx.x >> 3)) * a.group_smem;
 	int8_t *sU = (int8_t*)gs;
 	int8_t *sE = sU + IMG;
 	int8_t *sQ = sE + (PW >= 1 ? IMG : 0);
@@ -243,7 +249,7 @@ __global__ void __launch_bounds__(kFwdThreads) epi8_forward_kernel(const Epi8Arg
 				bw = (bw + kLanes - 1) / kLanes * kLanes;
 				W = bw / kLanes;
 				IB = epi8_image_bytes(W);
-				RS = IB * (PW + 1);
+				RS = ANCH ? epi8_row_bytes(W, PW) : IB * (PW + 1);
 				tr = a.trace + a.trace_off[pair];
 				meta = (int32_t*)(tr + (size_t)RS * (tlen + 1));
 				row = 0; rbeg = 0; mov = 0;
@@ -286,8 +292,8 @@ __global__ void __launch_bounds__(kFwdThreads) epi8_forward_kernel(const Epi8Arg
 				if(t == 0){ sUB[17] = 0; sUB[18] = 0; sUB[19] = 0; }
 			}
 		}
-		if(__all_sync(0xffffffffu, done)) break;
-		__syncwarp();
+		if(__all_sync(amask, done)) break;
+		__syncwarp(amask);
 		if(have && row == 0){
 			// store row -1 to the trace (backcal may walk into it, bsalign.h:3922)
 			const uint32_t nch = IB / 16;
@@ -297,8 +303,14 @@ __global__ void __launch_bounds__(kFwdThreads) epi8_forward_kernel(const Epi8Arg
 				if(PW == 2) *(uint4*)(tr + 2 * IB + 16 * c) = *(const uint4*)(sQ + 16 * c);
 			}
 			if(t < 5) *(uint4*)(meta + 4 * t) = *(const uint4*)(sUB + 4 * t);
+			// sub-lane anchors of row -1
+			for(uint32_t g=1;ANCH&&g<epi8_anchor_groups(W);g++){
+				int sA_ = sUB[A], sB_ = sUB[B];
+				for(uint32_t i=0;i<kAnchorSteps*g;i++){ sA_ += UBYTE(rU[TOFF(i)]); sB_ += UBYTE(rU[TOFF(i) + 1]); }
+				*(int2*)(tr + (size_t)IB * (PW + 1) + ((g - 1) * 16 + A) * 4) = make_int2(sA_, sB_);
+			}
 		}
-		__syncwarp();
+		__syncwarp(amask);
 
 		// =============================== one DP row ================================================
 		const uint32_t tb = tb_next;
@@ -443,7 +455,7 @@ __global__ void __launch_bounds__(kFwdThreads) epi8_forward_kernel(const Epi8Arg
 				rbeg += mov;
 			}
 		}
-		__syncwarp();
+		__syncwarp(amask);
 
 		// ---- cell 0 (bsalign.h:2899-2907) -----------------------------------------------------------
 		const uint32_t T32 = colw[tb & 3];
@@ -484,7 +496,7 @@ __global__ void __launch_bounds__(kFwdThreads) epi8_forward_kernel(const Epi8Arg
 		}
 		sF[A] = (int8_t)(lo16(st.f) - UB); sF[B] = (int8_t)(hi16(st.f) - UB);
 		if(PW == 2){ sF[16 + A] = (int8_t)(lo16(st.g) - UB); sF[16 + B] = (int8_t)(hi16(st.g) - UB); }
-		__syncwarp();
+		__syncwarp(amask);
 		// ---- F penetration (bsalign.h:2639-2652): exact 16-step scalar scan, every thread redundantly ---
 		{
 			int finA = kEpi8Min, finB = kEpi8Min, ginA = kEpi8Min, ginB = kEpi8Min;
@@ -522,7 +534,8 @@ __global__ void __launch_bounds__(kFwdThreads) epi8_forward_kernel(const Epi8Arg
 				if(RAGGED){ _Pragma("unroll") for(int k=0;k<8;k++){ un[k] = 0; en[k] = 0; qn[k] = 0; } } \
 				P2STEP(0, LEFT) P2STEP(1, LEFT) P2STEP(2, LEFT) P2STEP(3, LEFT) P2STEP(4, LEFT) P2STEP(5, LEFT) P2STEP(6, LEFT) P2STEP(7, LEFT) \
 				if(c == 0) unew0 = un[0]; \
-				*(uint4*)(rU + 128 * c) = make_uint4(pack2(un[0], un[1]), pack2(un[2], un[3]), pack2(un[4], un[5]), pack2(un[6], un[7])); \
+				const uint4 ou4 = make_uint4(pack2(un[0], un[1]), pack2(un[2], un[3]), pack2(un[4], un[5]), pack2(un[6], un[7])); \
+				*(uint4*)(rU + 128 * c) = ou4; \
 				if(PW >= 1) *(uint4*)(rE + 128 * c) = make_uint4(pack2(en[0], en[1]), pack2(en[2], en[3]), pack2(en[4], en[5]), pack2(en[6], en[7])); \
 				if(PW == 2) *(uint4*)(rQ + 128 * c) = make_uint4(pack2(qn[0], qn[1]), pack2(qn[2], qn[3]), pack2(qn[4], qn[5]), pack2(qn[6], qn[7])); }
 			uint32_t c = 0;
@@ -542,18 +555,48 @@ __global__ void __launch_bounds__(kFwdThreads) epi8_forward_kernel(const Epi8Arg
 			else if(PW == 2) h = sadd(h, NGQP);
 			const uint32_t vt = ssubc(h, ~ul);
 			int vtA = lo16(vt), vtB = hi16(vt);
-			int vprev = __shfl_up_sync(0xffffffffu, vtB, 1, kGroup);
+			int vprev = __shfl_up_sync(amask, vtB, 1, kGroup);
 			if(t == 0) vprev = 0;
 			int uA = clamp8(lo16(unew0) - UB - vprev);
 			int uB = clamp8(hi16(unew0) - UB - vtA);
-			__syncwarp();
+			__syncwarp(amask);
 			sUB[A + 1] += vtA;
 			sUB[B + 1] += vtB;
 			if(t == 0){ sUB[0] += uA; uA = 0; sUB[17] = (int32_t)rbeg; }
 			rU[0] = (int8_t)(uA + UB);
 			rU[1] = (int8_t)(uB + UB);
 		}
-		__syncwarp();
+		__syncwarp(amask);
+		if(ANCH && have){
+			// sub-lane anchors (lanes longer than 32 steps): H at the end of step 32g-1 = lane anchor + the row's u bytes so far.
+			// Done here, outside the hot loops (they are sensitive to code size), over the thread's own finished chunks;
+			// IDP.4A issues on the FMA pipe.
+			const uint32_t ng = epi8_anchor_groups(W);
+			if(ng > 1){
+				int32_t *an = (int32_t*)(tr + (size_t)RS * (row + 1) + (size_t)IB * (PW + 1));
+				const int baseA = sUB[A], baseB = sUB[B];
+				uint32_t accA = 0, accB = 0;
+				_Pragma("unroll 1")
+				for(uint32_t c=0;c<4*(ng-1);c++){
+					const uint4 w = *(const uint4*)(rU + 128 * c);
+					if(FAST){
+						accA = __dp4a(w.x, 0x00010001u, accA); accB = __dp4a(w.x, 0x01000100u, accB);
+						accA = __dp4a(w.y, 0x00010001u, accA); accB = __dp4a(w.y, 0x01000100u, accB);
+						accA = __dp4a(w.z, 0x00010001u, accA); accB = __dp4a(w.z, 0x01000100u, accB);
+						accA = __dp4a(w.w, 0x00010001u, accA); accB = __dp4a(w.w, 0x01000100u, accB);
+					} else {
+						accA = (uint32_t)__dp4a((int)w.x, 0x00010001, (int)accA); accB = (uint32_t)__dp4a((int)w.x, 0x01000100, (int)accB);
+						accA = (uint32_t)__dp4a((int)w.y, 0x00010001, (int)accA); accB = (uint32_t)__dp4a((int)w.y, 0x01000100, (int)accB);
+						accA = (uint32_t)__dp4a((int)w.z, 0x00010001, (int)accA); accB = (uint32_t)__dp4a((int)w.z, 0x01000100, (int)accB);
+						accA = (uint32_t)__dp4a((int)w.w, 0x00010001, (int)accA); accB = (uint32_t)__dp4a((int)w.w, 0x01000100, (int)accB);
+					}
+					if((c & 3) == 3){
+						const int corr = UB * (int)(8 * (c + 1));
+						*(int2*)(an + (c >> 2) * 16 + A) = make_int2(baseA + (int)accA - corr, baseB + (int)accB - corr);
+					}
+				}
+			}
+		}
 		// ---- stream the finished row to the traceback store ---------------------------------------------
 		if(have){
 			uint8_t *dst = tr + (size_t)RS * (row + 1);

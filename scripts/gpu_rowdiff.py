@@ -21,8 +21,9 @@ def rowdiff(ctx, q, t, mode, bw_req, mtx, gaps, maxshow=3):
     tlen = len(t)
     W = bw // 16
     IB = (W + 7) // 8 * 128
-    RS = IB * (pw + 1)
-    rows = buf[:RS * (tlen + 1)].reshape(tlen + 1, pw + 1, IB).view(np.int8)
+    AB = ((W + 31) // 32 - 1) * 64 if W > 64 else 0
+    RS = IB * (pw + 1) + AB
+    rows = buf[:RS * (tlen + 1)].reshape(tlen + 1, RS)[:, :IB * (pw + 1)].reshape(tlen + 1, pw + 1, IB).view(np.int8)
     pp = np.arange(bw); jj = pp // W; ii = pp % W
     idx = (ii >> 3) * 128 + (jj >> 1) * 16 + (ii & 7) * 2 + (jj & 1)
     meta = buf[RS * (tlen + 1):RS * (tlen + 1) + 80 * (tlen + 1)].view(np.int32).reshape(tlen + 1, 20)

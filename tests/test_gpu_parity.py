@@ -140,6 +140,14 @@ def test_waves_and_single_pair_api_agree(ctx):
     assert [rs[k] for k in api.RESULT_FIELDS] == list(one.results[5]) and np.array_equal(cg, one.cigar(5))
 
 
+def test_wide_bands(ctx):
+    """Lanes longer than 64 steps carry sub-lane anchors in the trace; very wide bands run fewer groups per warp."""
+    for qlen, n, mode, bw, gaps in [(2000, 6, 0, 0, (-3, -2, 0, 0)), (2500, 4, 1, 1600, (-3, -2, -8, -1)), (6000, 3, 0, 0, (-3, -2, 0, 0)), (10000, 3, 0, 0, (-3, -2, 0, 0))]:
+        b = synth.make_pairs(n, qlen, seed=qlen + mode)
+        exp, ecg, _ = ck.oracle_batch("epi8", b, mode, bw, M26, gaps, nthreads=8)
+        assert_same(ctx.epi8_batch(b, mode, bw, M26, *gaps), exp, ecg, tag=("wide", qlen, mode, bw))
+
+
 def test_dense_fetch_equals_scattered_fetch(ctx):
     b = synth.make_pairs(500, 200, seed=99)
     a = ctx.epi8_batch(b, 1, 64, M26, -3, -2, 0, 0)
