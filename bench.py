@@ -292,9 +292,18 @@ def main():
         pass
     peak = float(peaks.get("hbm_gbs", 6650.0))
     achieved = trace_bytes * args.steps / (fwd_ms * 1e-3) / 1e9 if fwd_ms > 0 else 0.0
+    kname = "epi8_forward_kernel" if w["kind"] == "epi8" else "edit_kernel"
+    traffic, traffic_src = None, None
+    try:   # DRAM bytes per launch: ncu-measured ratio (profiles/traffic_r1.json) x this launch's algorithmic bytes
+        tr = json.load(open(os.path.join(ROOT, "profiles", "traffic_r1.json")))[kname]
+        traffic = tr["ratio"] * trace_bytes / max(1, waves)
+        traffic_src = "ncu dram__bytes_read+write / algorithmic = %.3f (%s), scaled to this launch" % (tr["ratio"], tr["capture"])
+    except Exception:
+        pass
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                 "peak_source": "measured (MEASURED_PEAKS.json)" if peaks else "fallback (B200_PROFILING.md)",
-                "traffic": None, "kernel": "epi8_forward_kernel" if w["kind"] == "epi8" else "edit_kernel",
+                "traffic": traffic, "traffic_source": traffic_src, "kernel": kname, "launches_per_step": waves,
+                "algorithmic_bytes_per_launch": int(trace_bytes / max(1, waves)), "kernel_ms_per_launch": fwd_ms / args.steps / max(1, waves),
                 "algorithmic_bytes_per_step": int(trace_bytes), "kernel_ms_per_step": fwd_ms / args.steps,
                 "traceback_ms_per_step": bt_ms / args.steps, "waves_per_step": waves}
 
