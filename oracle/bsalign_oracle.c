@@ -56,6 +56,7 @@ typedef struct {
 	const int8_t *mtx;
 	int8_t go1, ge1, go2, ge2;
 	int8_t smax, smin;
+	int8_t hpc;     /* POA only: bonus added where the next query base differs (set_query_prof_hpc, :2194-2221); 0 otherwise */
 	/* trace: row y lives at index y+1 (row -1 = init row, bsalign.h:3922) */
 	int8_t *U, *E, *Q;
 	int32_t *UB;    /* (tlen+1) * 17 */
@@ -179,7 +180,11 @@ static void bso_row_shift(bso_epi8_t *a, bso_row_t src, bso_row_t dst, uint32_t 
 
 /* score of aligning query position x against target base tb: the query-profile entry (:2166-2191) */
 static inline int8_t bso_prof(bso_epi8_t *a, uint32_t x, uint8_t tb){
-	return x < a->qlen ? a->mtx[a->qseq[x] * 4 + tb] : BSO_EPI8_MIN;
+	int c;
+	if(x >= a->qlen) return BSO_EPI8_MIN;
+	c = a->mtx[a->qseq[x] * 4 + tb];
+	if(a->hpc && x + 1 < a->qlen && a->qseq[x] != a->qseq[x + 1]) c += a->hpc; /* :2204-2206 */
+	return (int8_t)c;
 }
 
 /* :2639-2652: carry the block-exit F of lane j-1 into lane j, extended across whole blocks */
@@ -871,5 +876,151 @@ int bso_edit_pairwise(const uint8_t *qseq, uint32_t qlen, const uint8_t *tseq, u
 		rs[0] = sc;
 	}
 	free(a->U); free(a->begs); free(tmp);
+	return a->err;
+}
+
+
+/* ------------------------------------------------------------------------------------------------
+ * POA read-vs-graph sweep: align_rd_bspoacore (bspoa.h:2515-2618) with dpalign_row_update_bspoa
+ * (bspoa.h:2232-2261), dpalign_row_merge_bspoa (bspoa.h:2263-2272) and
+ * banded_striped_epi8_seqalign_piecex_row_merge (bsalign.h:2474-2616).
+ *
+ * The sub-graph arrives as CSR over LOCAL node ids (0..nnode-1, the order of g->sels), out-edges in the
+ * reference's own list order and already filtered to selected nodes (bspoa.h:2538).  Rows are kept in
+ * linear band order here; par = {bandwidth, alnmode, M, X, O, E, Q, P, T, refbonus}.
+ * ------------------------------------------------------------------------------------------------ */
+static inline int16_t sat16(int v){ return (int16_t)(v > 32767 ? 32767 : (v < -32768 ? -32768 : v)); }
+
+/* bsalign.h:2474-2616: out = cell-wise max of rows a and b in absolute space, re-differenced.  out may alias b. */
+static void bso_row_merge(uint32_t W, int pw, bso_row_t a, bso_row_t b, bso_row_t out){
+	uint32_t j, i, ib, ie;
+	int k;
+	for(j=0;j<BSO_LANES;j++){
+		int32_t sa = a.ub[j], sb = b.ub[j];
+		for(ib=0;ib<W;ib=ie){
+			int d, xa, xb;
+			int16_t ta, tb, mp, mc;
+			ie = ib + 256 < W ? ib + 256 : W;
+			d = sa - sb;
+			if(d < -0x7FFF) d = -0x7FFF;
+			if(d > 0x7FFF) d = 0x7FFF;
+			xa = d >> 1; /* arithmetic shift (:2509) */
+			xb = xa - d;
+			sa -= xa; sb -= xb;
+			ta = sat16(xa); tb = sat16(xb);
+			mp = ta > tb ? ta : tb;
+			for(i=ib;i<ie;i++){
+				uint32_t p = j * W + i;
+				int16_t ya, yb, mx;
+				ta = sat16(ta + a.u[p]); tb = sat16(tb + b.u[p]);
+				mc = ta > tb ? ta : tb;
+				if(pw >= 1){ ya = sat16(ta + a.e[p]); yb = sat16(tb + b.e[p]); mx = ya > yb ? ya : yb; out.e[p] = sat8(sat16(mx - mc)); }
+				if(pw == 2){ ya = sat16(ta + a.q[p]); yb = sat16(tb + b.q[p]); mx = ya > yb ? ya : yb; out.q[p] = sat8(sat16(mx - mc)); }
+				out.u[p] = sat8(sat16(mc - mp));
+				mp = mc;
+			}
+			sa += ta; sb += tb;
+		}
+	}
+	for(k=0;k<=BSO_LANES;k++) out.ub[k] = a.ub[k] > b.ub[k] ? a.ub[k] : b.ub[k];
+}
+
+int bso_poa_sweep(const int32_t *par, const uint8_t *query, uint32_t slen, uint32_t nnode,
+		const uint8_t *base, const uint8_t *bonus, const int32_t *rpos, const int32_t *nct,
+		const int32_t *eoff, const int32_t *edst, uint32_t head, uint32_t tail,
+		int8_t *rows, int32_t *ubs, uint8_t *done, int32_t *best, uint64_t *ops){
+	bso_epi8_t A, *a = &A;
+	uint32_t bw = (uint32_t)par[0], W = bw / BSO_LANES, sp = 0, n, k;
+	int alnmode = par[1] & 3, M = par[2], X = par[3], O = par[4], E = par[5], Q = par[6], P = par[7], T = par[8], refbonus = par[9];
+	int8_t mtx[2][16], *scratch;
+	int32_t sub[2][17], *mpos;
+	uint32_t *stack, *vst;
+	bso_row_t blk0, blk1;
+	int maxscr = BSO_SCORE_MIN, maxidx = -1, maxoff = -1;
+	uint64_t nupd = 0, nmrg = 0;
+	if(bw == 0 || bw % BSO_LANES || head >= nnode || tail >= nnode) return BSO_ERR_RANGE;
+	memset(a, 0, sizeof(A));
+	a->qlen = slen; a->bw = bw; a->W = W; a->mode = alnmode; a->qseq = query;
+	a->go1 = (int8_t)O; a->ge1 = (int8_t)E; a->go2 = (int8_t)Q; a->ge2 = (int8_t)P;
+	a->pw = bso_epi8_piecewise(a->go1, a->ge1, a->go2, a->ge2, bw);
+	a->smax = (int8_t)(M + refbonus + 1); a->smin = (int8_t)X; /* bspoa.h:2226, 2240 */
+	for(k=0;k<16;k++){ /* bsalign.h:323 */
+		int same = ((k ^ (k >> 2)) & 3) == 0;
+		mtx[0][k] = (int8_t)(same ? M : X);
+		mtx[1][k] = (int8_t)(same ? M + refbonus : X);
+	}
+	scratch = malloc((size_t)bw * 6);
+	blk0.u = scratch; blk0.e = scratch + bw; blk0.q = scratch + 2 * (size_t)bw; blk0.ub = sub[0];
+	blk1.u = scratch + 3 * (size_t)bw; blk1.e = blk1.u + bw; blk1.q = blk1.u + 2 * (size_t)bw; blk1.ub = sub[1];
+	mpos = malloc(sizeof(int32_t) * nnode); stack = malloc(sizeof(uint32_t) * (nnode + 1)); vst = calloc(nnode, sizeof(uint32_t));
+	for(n=0;n<nnode;n++) mpos[n] = 0x7FFFFFFF - 1; /* MAX_B4 - 1, bspoa.h:2525 */
+	memset(done, 0, nnode);
+	#define NODE_ROW(r, n_) do { (r).u = rows + (size_t)(n_) * 3 * bw; (r).e = (r).u + bw; (r).q = (r).u + 2 * (size_t)bw; (r).ub = ubs + (size_t)(n_) * 17; } while(0)
+	{ /* bspoa.h:2224-2226: the head row */
+		bso_row_t r; NODE_ROW(r, head);
+		memset(r.u, 0, 3 * (size_t)bw);
+		bso_row_init(a, r, a->smax, a->smin);
+		if(a->pw == 0){ /* row_init leaves e untouched without a gap-open cost */ }
+		done[head] = 1;
+	}
+	mpos[head] = -1;
+	stack[sp++] = head;
+	while(sp){
+		uint32_t u = stack[--sp];
+		int32_t ei;
+		bso_row_t ur; NODE_ROW(ur, u);
+		for(ei=eoff[u];ei<eoff[u+1];ei++){
+			uint32_t v = (uint32_t)edst[ei];
+			if(mpos[u] + 1 < mpos[v]) mpos[v] = mpos[u] + 1;
+			if(v == tail){ /* bspoa.h:2548-2580 */
+				int smax, moff = (int)((int)slen < rpos[u] + (int)bw ? (int)slen : rpos[u] + (int)bw) - 1;
+				smax = bso_getscore(a, ur, (int64_t)moff - rpos[u]);
+				if((int)slen > moff + 1){
+					int rem = (int)slen - moff - 1;
+					if(a->pw < 2) smax += O + E * rem;
+					else { int c1 = O + E * rem, c2 = Q + P * rem; smax += c1 > c2 ? c1 : c2; }
+				}
+				smax += T;
+				if(smax > maxscr){ maxscr = smax; maxidx = (int)u; maxoff = moff; }
+				if(alnmode == BSO_MODE_OVERLAP){
+					uint32_t rmax = bso_row_max(a, ur, &smax);
+					if(smax > maxscr){ maxscr = smax; maxidx = (int)u; maxoff = (int)rmax + rpos[u]; }
+				}
+				vst[v]++;
+			} else {
+				bso_row_t vr, dst;
+				int rh, kprof = (base[v] == base[u]) * 2 + bonus[v];
+				uint32_t q1 = (uint32_t)rpos[u], q2 = (uint32_t)rpos[v];
+				NODE_ROW(vr, v);
+				dst = vst[v] ? blk1 : vr;
+				/* dpalign_row_update_bspoa, bspoa.h:2232-2261 */
+				bso_row_shift(a, ur, blk0, q2 - q1, a->smax, a->smin);
+				if(q1 == q2){
+					if(q1) rh = BSO_SCORE_MIN;
+					else if(alnmode == BSO_MODE_OVERLAP || mpos[v] == 0) rh = 0;
+					else if(a->pw < 2) rh = O + E * mpos[v];
+					else { int c1 = O + E * mpos[v], c2 = Q + P * mpos[v]; rh = c1 > c2 ? c1 : c2; }
+				} else if(q1 + bw >= q2) rh = blk0.ub[0];
+				else rh = BSO_SCORE_MIN;
+				a->mtx = mtx[kprof & 1]; a->hpc = (kprof < 2) ? 1 : 0; /* bspoa.h:2199-2215 */
+				bso_row_cal(a, q2, base[v], blk0, dst, rh);
+				nupd++;
+				if(vst[v]){ bso_row_merge(W, a->pw, blk1, vr, vr); nmrg++; }
+				vst[v]++;
+				done[v] = 1;
+				if((int)vst[v] == nct[v]){
+					if(alnmode != BSO_MODE_GLOBAL && q2 + bw >= slen){
+						int smax = bso_getscore(a, vr, (int64_t)slen - 1 - q2) + T;
+						if(smax > maxscr){ maxscr = smax; maxidx = (int)v; maxoff = (int)slen - 1; }
+					}
+					stack[sp++] = v;
+				}
+			}
+		}
+	}
+	#undef NODE_ROW
+	best[0] = maxscr; best[1] = maxidx; best[2] = maxoff;
+	if(ops){ ops[0] = nupd; ops[1] = nmrg; }
+	free(scratch); free(mpos); free(stack); free(vst);
 	return a->err;
 }

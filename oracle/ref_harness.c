@@ -161,3 +161,137 @@ int bsref_epi8_rows(const uint8_t *q, uint32_t qlen, const uint8_t *t, uint32_t 
 	free_u4v(cigars);
 	return piecewise;
 }
+
+/* ------------------------------------------------------------------------------------------------------------
+ * POA read-vs-graph sweep (align_rd_bspoacore, bspoa.h:2515-2618): run a whole POA job through the reference and
+ * dump, for every read alignment, what the sweep consumes (query, selected sub-graph in the reference's own edge
+ * order, per-node band offsets/base/bonus/in-degree, parameters) and what it produces (every node row, the best end).
+ * The loop below only CALLS the reference's functions in the order end_bspoa (bspoa.h:4722-4778) and align_rd_bspoa
+ * (bspoa.h:2620-2667) call them; the dump sits between prepare_rd_align_bspoa and align_rd_bspoacore.
+ * ------------------------------------------------------------------------------------------------------------ */
+#include "bspoa.h"
+
+typedef struct { uint8_t *buf; size_t n, cap; } bsref_blob_t;
+static void blob_put(bsref_blob_t *b, const void *p, size_t len){
+	size_t pad = (4 - (len & 3)) & 3;
+	if(b->n + len + pad > b->cap){ b->cap = (b->n + len + pad) * 2 + 4096; b->buf = realloc(b->buf, b->cap); }
+	memcpy(b->buf + b->n, p, len); b->n += len;
+	if(pad){ memset(b->buf + b->n, 0, pad); b->n += pad; }
+}
+
+static void bsref_poa_dump_job(BSPOA *g, BSPOAPar *par, u4i nhead, u4i ntail, bsref_blob_t *blob, int phase, size_t *hdr_at){
+	u4i i, nloc = g->sels->size, bw = g->bandwidth, W = bw / WORDSIZE, p;
+	static u4i *loc = NULL; static size_t loccap = 0;
+	if(loccap < g->nodes->size){ loccap = g->nodes->size * 2 + 16; loc = realloc(loc, loccap * sizeof(u4i)); }
+	for(i=0;i<nloc;i++) loc[g->sels->buffer[i]] = i;
+	if(phase == 0){
+		int32_t hdr[24]; u4i nedge = 0, eidx;
+		int32_t *node = malloc(sizeof(int32_t) * 5 * nloc), *eoff = malloc(sizeof(int32_t) * (nloc + 1)), *edst;
+		for(i=0;i<nloc;i++){
+			bspoanode_t *u = ref_bspoanodev(g->nodes, g->sels->buffer[i]);
+			node[i * 5 + 0] = u->base; node[i * 5 + 1] = u->bonus; node[i * 5 + 2] = u->rpos; node[i * 5 + 3] = u->nct; node[i * 5 + 4] = u->mmidx;
+			eoff[i] = nedge;
+			for(eidx=u->edge;eidx;eidx=ref_bspoaedgev(g->edges, eidx)->next) if(get_bitvec(g->states, ref_bspoaedgev(g->edges, eidx)->node)) nedge ++;
+		}
+		eoff[nloc] = nedge;
+		edst = malloc(sizeof(int32_t) * (nedge + 1)); nedge = 0;
+		for(i=0;i<nloc;i++){
+			bspoanode_t *u = ref_bspoanodev(g->nodes, g->sels->buffer[i]);
+			for(eidx=u->edge;eidx;eidx=ref_bspoaedgev(g->edges, eidx)->next){
+				bspoaedge_t *e = ref_bspoaedgev(g->edges, eidx);
+				if(get_bitvec(g->states, e->node)) edst[nedge ++] = loc[e->node];
+			}
+		}
+		memset(hdr, 0, sizeof(hdr));
+		hdr[0] = 0x504F4131; hdr[1] = bw; hdr[2] = g->piecewise; hdr[3] = g->slen; hdr[4] = par->alnmode; hdr[5] = par->M; hdr[6] = par->X;
+		hdr[7] = par->O; hdr[8] = par->E; hdr[9] = par->Q; hdr[10] = par->P; hdr[11] = par->T; hdr[12] = par->refbonus; hdr[13] = nloc;
+		hdr[14] = loc[nhead]; hdr[15] = loc[ntail]; hdr[16] = nedge; hdr[20] = (int32_t)g->mmblk;
+		*hdr_at = blob->n;
+		blob_put(blob, hdr, sizeof(hdr));
+		blob_put(blob, g->qseq->buffer + g->qb, g->slen);
+		blob_put(blob, node, sizeof(int32_t) * 5 * nloc);
+		blob_put(blob, eoff, sizeof(int32_t) * (nloc + 1));
+		blob_put(blob, edst, sizeof(int32_t) * nedge);
+		free(node); free(eoff); free(edst);
+	} else {
+		int32_t *hdr = (int32_t*)(blob->buf + *hdr_at);
+		int8_t *row = malloc(3 * (size_t)bw); int32_t ub[17]; uint8_t *done = malloc(nloc + 4);
+		hdr[17] = g->maxscr; hdr[18] = g->maxidx >= 0 ? (int32_t)loc[g->maxidx] : -1; hdr[19] = g->maxoff;
+		for(i=0;i<nloc;i++){
+			bspoanode_t *u = ref_bspoanodev(g->nodes, g->sels->buffer[i]);
+			b1i *us, *es, *qs; int *ubegs;
+			dpalign_row_prepare_data(g, u->mmidx, &us, &es, &qs, &ubegs);
+			memset(row, 0, 3 * (size_t)bw);
+			for(p=0;p<bw;p++){
+				u4i idx = (p % W) * WORDSIZE + (p / W);
+				row[p] = us[idx];
+				if(es) row[bw + p] = es[idx];
+				if(qs) row[2 * bw + p] = qs[idx];
+			}
+			memcpy(ub, ubegs, sizeof(ub));
+			blob_put(blob, row, 3 * (size_t)bw);
+			blob_put(blob, ub, sizeof(ub));
+			done[i] = (offset_bspoanodev(g->nodes, u) == nhead) ? 1 : (u->vst ? 1 : 0);
+		}
+		blob_put(blob, done, nloc);
+		free(row); free(done);
+	}
+}
+
+/* reads: one base per byte (0..3).  par_override: NULL, or 10 ints {bandwidth, M, X, O, E, Q, P, T, refbonus, alnmode}.
+ * Returns the number of sweep jobs dumped; *out receives a malloc'ed blob (free with bsref_free). */
+int64_t bsref_poa_dump(uint32_t nreads, const uint8_t *seqs, const uint64_t *off, const uint32_t *len, const int32_t *par_override,
+		uint8_t **out, uint64_t *out_len){
+	BSPOAPar par = DEFAULT_BSPOA_PAR;
+	BSPOA *g;
+	bsref_blob_t blob = {NULL, 0, 0};
+	int64_t njobs = 0;
+	u4i i; u2i rid;
+	if(par_override){
+		par.bandwidth = par_override[0]; par.M = par_override[1]; par.X = par_override[2]; par.O = par_override[3]; par.E = par_override[4];
+		par.Q = par_override[5]; par.P = par_override[6]; par.T = par_override[7]; par.refbonus = par_override[8]; par.alnmode = par_override[9];
+	}
+	par.realn = 0;
+	g = init_bspoa(par);
+	beg_bspoa(g);
+	for(i=0;i<nreads;i++) fwdbitseqpush_bspoa(g, (u1i*)seqs + off[i], len[i]);
+	/* end_bspoa, bspoa.h:4737-4760, with the dump hooks */
+	if(g->seqs->nseq > 1){
+		if(g->par->shuffle) shuffle_reads_by_kmers_bspoa(g);
+		g->nmsa = g->par->seqcore ? num_min(g->seqs->nseq, g->par->seqcore) : g->seqs->nseq;
+		for(rid=0;rid<g->seqs->nseq;rid++) _add_read_bspoa_core(g, rid);
+		g->nrds = 1;
+		for(rid=1;rid<g->nmsa;rid++){
+			u4i nhead, ntail, rlen = g->seqs->rdlens->buffer[rid];
+			u2i ridxbeg, ridxend;
+			size_t hdr_at = 0;
+			int score; seqalign_result_t rs;
+			if(!g->par->refmode && g->par->bwtrigger){ msa_bspoa(g); simple_cns_bspoa(g); }
+			/* align_rd_bspoa(g, par, 0, rid, 0, rlen), bspoa.h:2620-2650 */
+			clear_u8v(g->todels);
+			if(rlen){
+				nhead = get_rdnode_bspoa(g, rid, -1)->header;
+				ntail = get_rdnode_bspoa(g, rid, rlen)->header;
+				if(g->par->nrec){ ridxbeg = num_max(0, Int(rid) - g->par->nrec - 1); ridxend = rid; } else { ridxbeg = 0; ridxend = MAX_U2; }
+				sel_nodes_bspoa(g, nhead, ntail, ridxbeg, ridxend);
+				prepare_rd_align_bspoa(g, g->par, nhead, ntail, rid, 0, rlen);
+				bsref_poa_dump_job(g, g->par, nhead, ntail, &blob, 0, &hdr_at);
+				score = align_rd_bspoacore(g, g->par, rid, nhead, ntail);
+				bsref_poa_dump_job(g, g->par, nhead, ntail, &blob, 1, &hdr_at);
+				njobs ++;
+				rs = alignment2graph_bspoa(g, g->par, rid, 0, nhead, ntail, g->maxidx, g->maxoff, NULL);
+				UNUSED(rs); UNUSED(score);
+				for(i=0;i<g->todels->size;i++){
+					chg_edge_bspoa(g, ref_bspoanodev(g->nodes, g->todels->buffer[i] >> 32), ref_bspoanodev(g->nodes, g->todels->buffer[i] & MAX_U4), -1, NULL);
+				}
+				clear_u8v(g->todels);
+			}
+			g->nrds ++;
+		}
+	}
+	free_bspoa(g);
+	*out = blob.buf; *out_len = blob.n;
+	return njobs;
+}
+
+void bsref_free(void *p){ free(p); }

@@ -1,0 +1,131 @@
+"""POA sweep jobs for the parity tests (test infrastructure).
+
+A *sweep job* is what one call of the reference's align_rd_bspoacore (bspoa.h:2515-2618) consumes and produces:
+the read (query), the selected sub-graph in the reference's own edge order (CSR), per-node band offset / base /
+bonus / in-degree, the scoring parameters -- and every node row plus the best end (maxscr, maxidx, maxoff).
+`ref_dump` drives a whole BSPOA job through the UNMODIFIED reference (oracle/_ref/libbsref.so, bsref_poa_dump in
+oracle/ref_harness.c) and parses the dump; it only works where the reference tree was present at build time.
+"""
+import ctypes
+
+import numpy as np
+
+import checkers as ck
+
+HDR_WORDS = 24
+MAGIC = 0x504F4131
+
+
+class SweepJob:
+    __slots__ = ("bw", "pw", "slen", "alnmode", "M", "X", "O", "E", "Q", "P", "T", "refbonus", "nnode", "head", "tail", "nedge",
+                 "query", "base", "bonus", "rpos", "nct", "eoff", "edst", "maxscr", "maxidx", "maxoff", "rows", "ub", "done")
+
+    def params(self):
+        return np.array([self.bw, self.alnmode, self.M, self.X, self.O, self.E, self.Q, self.P, self.T, self.refbonus], dtype=np.int32)
+
+
+def parse_dump(blob, with_rows=True):
+    """blob: uint8 array written by bsref_poa_dump -> list of SweepJob."""
+    jobs = []
+    pos = 0
+    n = len(blob)
+    pad4 = lambda x: (x + 3) & ~3
+    while pos < n:
+        hdr = blob[pos:pos + 4 * HDR_WORDS].view(np.int32)
+        assert hdr[0] == MAGIC, "bad magic at %d" % pos
+        pos += 4 * HDR_WORDS
+        j = SweepJob()
+        (j.bw, j.pw, j.slen, j.alnmode, j.M, j.X, j.O, j.E, j.Q, j.P, j.T, j.refbonus, j.nnode, j.head, j.tail, j.nedge,
+         j.maxscr, j.maxidx, j.maxoff) = [int(x) for x in hdr[1:20]]
+        j.query = blob[pos:pos + j.slen].copy(); pos += pad4(j.slen)
+        node = blob[pos:pos + 20 * j.nnode].view(np.int32).reshape(j.nnode, 5); pos += 20 * j.nnode
+        j.base = node[:, 0].astype(np.uint8); j.bonus = node[:, 1].astype(np.uint8)
+        j.rpos = node[:, 2].astype(np.int32); j.nct = node[:, 3].astype(np.int32)
+        j.eoff = blob[pos:pos + 4 * (j.nnode + 1)].view(np.int32).copy(); pos += 4 * (j.nnode + 1)
+        j.edst = blob[pos:pos + 4 * j.nedge].view(np.int32).copy(); pos += 4 * j.nedge
+        rec = 3 * j.bw + 68
+        assert rec % 4 == 0
+        body = blob[pos:pos + rec * j.nnode].reshape(j.nnode, rec); pos += rec * j.nnode
+        if with_rows:
+            j.rows = body[:, :3 * j.bw].view(np.int8).reshape(j.nnode, 3, j.bw).copy()
+            j.ub = np.ascontiguousarray(body[:, 3 * j.bw:]).view(np.int32).reshape(j.nnode, 17).copy()
+        else:
+            j.rows = None; j.ub = None
+        j.done = blob[pos:pos + j.nnode].copy(); pos += pad4(j.nnode)
+        j.done[j.tail] = 0  # the tail is only counted (v->vst++), it has no row
+        jobs.append(j)
+    return jobs
+
+
+def ref_dump(reads, par_override=None, with_rows=True):
+    """reads: list of uint8 arrays (bases 0..3).  par_override: None or 10 ints
+    (bandwidth, M, X, O, E, Q, P, T, refbonus, alnmode).  Returns the list of sweep jobs of the whole POA job."""
+    lib = ck.ref()
+    lens = np.array([len(r) for r in reads], dtype=np.uint32)
+    off = np.zeros(len(reads), dtype=np.uint64)
+    off[1:] = np.cumsum(lens[:-1], dtype=np.uint64)
+    seqs = np.ascontiguousarray(np.concatenate(reads), dtype=np.uint8)
+    out = ctypes.c_void_p()
+    out_len = ctypes.c_uint64()
+    po = None if par_override is None else np.ascontiguousarray(par_override, dtype=np.int32)
+    lib.bsref_poa_dump.restype = ctypes.c_int64
+    nj = lib.bsref_poa_dump(ctypes.c_uint32(len(reads)), ck._ptr(seqs), ck._ptr(off), ck._ptr(lens), ck._ptr(po),
+                            ctypes.byref(out), ctypes.byref(out_len))
+    blob = np.ctypeslib.as_array(ctypes.cast(out, ctypes.POINTER(ctypes.c_uint8)), shape=(out_len.value,)).copy() if out_len.value else np.zeros(0, np.uint8)
+    lib.bsref_free.argtypes = [ctypes.c_void_p]
+    lib.bsref_free(out)
+    jobs = parse_dump(blob, with_rows)
+    assert len(jobs) == nj
+    return jobs
+
+
+def make_reads(nreads, tlen, seed, p_sub=0.03, p_ins=0.03, p_del=0.04):
+    """nreads reads mutated independently from one random template."""
+    from bsalign_b200 import synth
+    rng = np.random.default_rng(seed)
+    tmpl = rng.integers(0, 4, size=(1, tlen), dtype=np.uint8)
+    reads = []
+    for _ in range(nreads):
+        flat, _l = synth.mutate_batch(rng, tmpl, p_sub, p_ins, p_del)
+        reads.append(flat.astype(np.uint8))
+    return reads
+
+
+def oracle_sweep(j):
+    """Run oracle/bsalign_oracle.c:bso_poa_sweep on one SweepJob -> (rows[nnode,3,bw] int8 linear, ub[nnode,17], done, best[3], ops[2], rc)."""
+    lib = ck.oracle()
+    par = j.params()
+    rows = np.zeros((j.nnode, 3, j.bw), dtype=np.int8)
+    ub = np.zeros((j.nnode, 17), dtype=np.int32)
+    done = np.zeros(j.nnode, dtype=np.uint8)
+    best = np.zeros(3, dtype=np.int32)
+    ops = np.zeros(2, dtype=np.uint64)
+    q = np.ascontiguousarray(j.query, dtype=np.uint8)
+    base = np.ascontiguousarray(j.base, dtype=np.uint8)
+    bonus = np.ascontiguousarray(j.bonus, dtype=np.uint8)
+    rpos = np.ascontiguousarray(j.rpos, dtype=np.int32)
+    nct = np.ascontiguousarray(j.nct, dtype=np.int32)
+    eoff = np.ascontiguousarray(j.eoff, dtype=np.int32)
+    edst = np.ascontiguousarray(j.edst, dtype=np.int32)
+    rc = lib.bso_poa_sweep(ck._ptr(par), ck._ptr(q), ctypes.c_uint32(j.slen), ctypes.c_uint32(j.nnode), ck._ptr(base), ck._ptr(bonus),
+                           ck._ptr(rpos), ck._ptr(nct), ck._ptr(eoff), ck._ptr(edst), ctypes.c_uint32(j.head), ctypes.c_uint32(j.tail),
+                           ck._ptr(rows), ck._ptr(ub), ck._ptr(done), ck._ptr(best), ck._ptr(ops))
+    return rows, ub, done, best, ops, rc
+
+
+def compare_rows(j, rows, ub, done, best, pw=None):
+    """Mismatch description (or None) between a sweep result and the reference dump held by job j."""
+    pw = j.pw if pw is None else pw
+    if (int(best[0]), int(best[1]), int(best[2])) != (j.maxscr, j.maxidx, j.maxoff):
+        return "best %s != ref %s" % (best.tolist(), (j.maxscr, j.maxidx, j.maxoff))
+    if not np.array_equal(done.astype(bool), j.done.astype(bool)):
+        return "visited sets differ"
+    m = j.done.astype(bool)
+    if not np.array_equal(ub[m], j.ub[m]):
+        bad = np.nonzero((ub != j.ub).any(axis=1) & m)[0]
+        return "ubegs differ at nodes %s" % bad[:5].tolist()
+    for a in range(pw + 1):
+        if not np.array_equal(rows[m, a], j.rows[m, a]):
+            bad = np.nonzero((rows[:, a] != j.rows[:, a]).any(axis=1) & m)[0]
+            return "array %d differs at nodes %s" % (a, bad[:5].tolist())
+    return None
