@@ -686,3 +686,6 @@ extern "C" int64_t bsb200_debug_trace(bsb200_ctx *ctx, bsb200_batch *b, uint64_t
 	if(ubias_out) *ubias_out = (b->pw >= 1 && b->ge1 <= 0 && (int8_t)(b->go1 + b->ge1) <= 0 && (b->pw < 2 || (b->ge2 <= 0 && (int8_t)(b->go2 + b->ge2) <= 0))) ? 128 : 0;
 	return (int64_t)bytes;
 }
+
+// ---- POA read-vs-graph sweep (bspoa.h:2515-2618) ---------------------------------------------------------------
+#include "poa_host.cuh"

@@ -1,0 +1,191 @@
+// poa_host.cuh -- host side of the POA sweep entry points (included by bsb200.cu after the context definition).
+// Uploads a batch of sweep jobs (CSR sub-graphs + reads), runs poa_prep_kernel + poa_sweep_kernel on the context's
+// stream and brings back the node row blocks (reference memp layout), the best end per job and the op counts.
+#pragma once
+#include "poa_kernels.cuh"
+
+struct bsb200_poa_batch {
+	uint32_t njobs = 0;
+	uint64_t nnodes = 0, nedges = 0, qbytes = 0, row_bytes = 0;
+	uint32_t max_bw = 16;
+	std::vector<uint64_t> row_off;      // njobs + 1
+	std::vector<uint32_t> order;
+	DevBuf d_par, d_queries, d_qcode, d_qoff, d_slen, d_node_off, d_node, d_eoff, d_edge_off, d_edst, d_head, d_tail,
+		d_mpos, d_vst, d_stack, d_rows, d_row_off, d_best, d_status, d_ops, d_order, d_counter;
+	bool ran = false;
+};
+
+static uint32_t poa_mmblk(const int32_t *par){
+	const uint32_t bw = (uint32_t)par[0];
+	const int pw = epi8_piecewise((int8_t)par[4], (int8_t)par[5], (int8_t)par[6], (int8_t)par[7], (int)bw);
+	return (bw * (pw + 1) + 68 + 15) / 16 * 16;   // bspoa.h:2217
+}
+
+extern "C" uint32_t bsb200_poa_block_bytes(const int32_t par[10]){ return par ? poa_mmblk(par) : 0; }
+
+extern "C" void bsb200_poa_free(bsb200_ctx *ctx, bsb200_poa_batch *b){
+	if(!b) return;
+	if(ctx) cudaSetDevice(ctx->device);
+	DevBuf *ds[] = {&b->d_par, &b->d_queries, &b->d_qcode, &b->d_qoff, &b->d_slen, &b->d_node_off, &b->d_node, &b->d_eoff, &b->d_edge_off, &b->d_edst,
+		&b->d_head, &b->d_tail, &b->d_mpos, &b->d_vst, &b->d_stack, &b->d_rows, &b->d_row_off, &b->d_best, &b->d_status, &b->d_ops, &b->d_order, &b->d_counter};
+	for(auto d : ds) d->release();
+	delete b;
+}
+
+extern "C" bsb200_poa_batch *bsb200_poa_upload(bsb200_ctx *ctx, uint32_t njobs, const int32_t *par,
+		const uint8_t *queries, const uint64_t *qoff, const uint32_t *slen,
+		const uint64_t *node_off, const uint8_t *node_base, const uint8_t *node_bonus, const int32_t *node_rpos, const int32_t *node_nct,
+		const int32_t *eoff, const uint64_t *edge_off, const int32_t *edst, const uint32_t *head, const uint32_t *tail){
+	if(!ctx) return nullptr;
+	ctx->err.clear();
+	if(njobs && (!par || !queries || !qoff || !slen || !node_off || !node_base || !node_bonus || !node_rpos || !node_nct || !eoff || !edge_off || !edst || !head || !tail)){
+		fail(ctx, "bsb200_poa_upload", cudaSuccess); return nullptr;
+	}
+	cudaSetDevice(ctx->device);
+	bsb200_poa_batch *b = new bsb200_poa_batch();
+	b->njobs = njobs;
+	b->row_off.assign((size_t)njobs + 1, 0);
+	b->nnodes = njobs ? node_off[njobs] : 0;
+	b->nedges = njobs ? edge_off[njobs] : 0;
+	std::vector<std::pair<uint64_t, uint32_t>> kv(njobs);
+	for(uint32_t i=0;i<njobs;i++){
+		const int32_t *p = par + (size_t)i * 10;
+		const uint64_t nn = node_off[i + 1] - node_off[i];
+		if(p[0] <= 0 || p[0] % 16 || nn == 0 || head[i] >= nn || tail[i] >= nn || nn > 0x7fffffffull){
+			ctx->err = "bsb200_poa_upload: bad job (bandwidth must be a positive multiple of 16; head/tail must be local node ids)";
+			bsb200_poa_free(ctx, b); return nullptr;
+		}
+		b->max_bw = std::max<uint32_t>(b->max_bw, (uint32_t)p[0]);
+		b->row_off[i + 1] = b->row_off[i] + nn * poa_mmblk(p);
+		b->qbytes = std::max<uint64_t>(b->qbytes, qoff[i] + slen[i]);
+		kv[i] = std::make_pair(~(nn * (uint64_t)p[0]), i);
+	}
+	b->row_bytes = b->row_off[njobs];
+	std::sort(kv.begin(), kv.end());
+	b->order.resize(njobs);
+	for(uint32_t i=0;i<njobs;i++) b->order[i] = kv[i].second;
+	// node records: rpos, nct | base << 16 | bonus << 24
+	std::vector<int2> nodes(b->nnodes);
+	for(uint64_t k=0;k<b->nnodes;k++){
+		nodes[k].x = node_rpos[k];
+		nodes[k].y = (int)(((uint32_t)node_nct[k] & 0xffffu) | ((uint32_t)node_base[k] << 16) | (((uint32_t)node_bonus[k] & 1u) << 24));
+	}
+	cudaError_t e = cudaSuccess;
+	auto R = [&](cudaError_t x){ if(e == cudaSuccess) e = x; };
+	const size_t nj = njobs, nn = b->nnodes, ne = b->nedges;
+	R(b->d_par.reserve(nj * 40 + 16)); R(b->d_queries.reserve(b->qbytes + 16)); R(b->d_qcode.reserve(b->qbytes + 16));
+	R(b->d_qoff.reserve(nj * 8 + 8)); R(b->d_slen.reserve(nj * 4 + 4)); R(b->d_node_off.reserve((nj + 1) * 8)); R(b->d_node.reserve(nn * 8 + 8));
+	R(b->d_eoff.reserve((nn + nj) * 4 + 4)); R(b->d_edge_off.reserve((nj + 1) * 8)); R(b->d_edst.reserve(ne * 4 + 4));
+	R(b->d_head.reserve(nj * 4 + 4)); R(b->d_tail.reserve(nj * 4 + 4));
+	R(b->d_mpos.reserve(nn * 4 + 4)); R(b->d_vst.reserve(nn * 4 + 4)); R(b->d_stack.reserve(nn * 4 + 4));
+	R(b->d_rows.reserve(b->row_bytes + 16)); R(b->d_row_off.reserve((nj + 1) * 8));
+	R(b->d_best.reserve(nj * 12 + 12)); R(b->d_status.reserve(nj * 4 + 4)); R(b->d_ops.reserve(nj * 16 + 16));
+	R(b->d_order.reserve(nj * 4 + 4)); R(b->d_counter.reserve(256));
+	if(e != cudaSuccess){ fail(ctx, "device allocation (poa)", e); bsb200_poa_free(ctx, b); return nullptr; }
+	cudaStream_t st = ctx->stream;
+	cudaEventRecord(ctx->ev[0], st);
+	if(njobs){
+		R(cudaMemcpyAsync(b->d_par.p, par, nj * 40, cudaMemcpyHostToDevice, st));
+		R(cudaMemcpyAsync(b->d_queries.p, queries, b->qbytes, cudaMemcpyHostToDevice, st));
+		R(cudaMemcpyAsync(b->d_qoff.p, qoff, nj * 8, cudaMemcpyHostToDevice, st));
+		R(cudaMemcpyAsync(b->d_slen.p, slen, nj * 4, cudaMemcpyHostToDevice, st));
+		R(cudaMemcpyAsync(b->d_node_off.p, node_off, (nj + 1) * 8, cudaMemcpyHostToDevice, st));
+		R(cudaMemcpyAsync(b->d_node.p, nodes.data(), nn * 8, cudaMemcpyHostToDevice, st));
+		R(cudaMemcpyAsync(b->d_eoff.p, eoff, (nn + nj) * 4, cudaMemcpyHostToDevice, st));
+		R(cudaMemcpyAsync(b->d_edge_off.p, edge_off, (nj + 1) * 8, cudaMemcpyHostToDevice, st));
+		if(ne) R(cudaMemcpyAsync(b->d_edst.p, edst, ne * 4, cudaMemcpyHostToDevice, st));
+		R(cudaMemcpyAsync(b->d_head.p, head, nj * 4, cudaMemcpyHostToDevice, st));
+		R(cudaMemcpyAsync(b->d_tail.p, tail, nj * 4, cudaMemcpyHostToDevice, st));
+		R(cudaMemcpyAsync(b->d_row_off.p, b->row_off.data(), (nj + 1) * 8, cudaMemcpyHostToDevice, st));
+		R(cudaMemcpyAsync(b->d_order.p, b->order.data(), nj * 4, cudaMemcpyHostToDevice, st));
+	}
+	cudaEventRecord(ctx->ev[1], st);
+	R(cudaStreamSynchronize(st));
+	if(e != cudaSuccess){ fail(ctx, "host to device copy (poa)", e); bsb200_poa_free(ctx, b); return nullptr; }
+	float ms = 0; cudaEventElapsedTime(&ms, ctx->ev[0], ctx->ev[1]);
+	ctx->timing = bsb200_timing_t();
+	ctx->timing.h2d_ms = ms;
+	ctx->timing.h2d_bytes = nj * (40 + 8 + 4 + 8 + 8 + 4 + 4 + 8 + 4) + b->qbytes + nn * 8 + (nn + nj) * 4 + ne * 4;
+	return b;
+}
+
+extern "C" int bsb200_poa_run(bsb200_ctx *ctx, bsb200_poa_batch *b){
+	if(!ctx || !b) return -1;
+	ctx->err.clear();
+	cudaSetDevice(ctx->device);
+	cudaStream_t st = ctx->stream;
+	if(b->njobs == 0){ b->ran = true; return 0; }
+	PoaArgs a;
+	a.njobs = b->njobs; a.order = b->d_order.as<uint32_t>(); a.counter = b->d_counter.as<unsigned int>();
+	a.par = b->d_par.as<int32_t>(); a.qcode = b->d_qcode.as<uint8_t>(); a.qoff = b->d_qoff.as<uint64_t>(); a.slen = b->d_slen.as<uint32_t>();
+	a.node_off = b->d_node_off.as<uint64_t>(); a.node = b->d_node.as<int2>(); a.eoff = b->d_eoff.as<int32_t>();
+	a.edge_off = b->d_edge_off.as<uint64_t>(); a.edst = b->d_edst.as<int32_t>(); a.head = b->d_head.as<uint32_t>(); a.tail = b->d_tail.as<uint32_t>();
+	a.mpos = b->d_mpos.as<int32_t>(); a.vst = b->d_vst.as<uint32_t>(); a.stack = b->d_stack.as<uint32_t>();
+	a.rows = b->d_rows.as<uint8_t>(); a.row_off = b->d_row_off.as<uint64_t>();
+	a.best = b->d_best.as<int32_t>(); a.status = b->d_status.as<int32_t>(); a.ops = b->d_ops.as<unsigned long long>();
+	a.slot_bytes = 3 * b->max_bw + 80;
+	const size_t smem = (size_t)(kPoaThreads / kPoaGroup) * (2 * a.slot_bytes + 80 + 32 + 128);
+	if(smem > ctx->smem_optin){ ctx->err = "bsb200_poa_run: bandwidth too wide for the shared-memory row slots"; return -1; }
+	CK(cudaFuncSetAttribute(poa_sweep_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+	cudaEventRecord(ctx->ev[2], st);
+	CK(cudaMemsetAsync(b->d_counter.p, 0, 16, st));
+	const uint32_t prep_blocks = std::min<uint32_t>(b->njobs, (uint32_t)ctx->num_sms * 8);
+	poa_prep_kernel<<<prep_blocks, 256, 0, st>>>(b->njobs, b->d_queries.as<uint8_t>(), a.qoff, a.slen, b->d_qcode.as<uint8_t>(), a.node_off, a.mpos, a.vst);
+	cudaEventRecord(ctx->ev[3], st);
+	const uint32_t groups = kPoaThreads / kPoaGroup;
+	uint32_t blocks = (b->njobs + groups - 1) / groups;
+	blocks = std::min<uint32_t>(blocks, (uint32_t)ctx->num_sms * 16);
+	poa_sweep_kernel<<<blocks, kPoaThreads, smem, st>>>(a);
+	cudaEventRecord(ctx->ev[4], st);
+	CK(cudaGetLastError());
+	CK(cudaStreamSynchronize(st));
+	float prep = 0, sweep = 0;
+	cudaEventElapsedTime(&prep, ctx->ev[2], ctx->ev[3]);
+	cudaEventElapsedTime(&sweep, ctx->ev[3], ctx->ev[4]);
+	ctx->timing.forward_ms = sweep; ctx->timing.traceback_ms = 0; ctx->timing.run_ms = prep + sweep; ctx->timing.total_ms = prep + sweep;
+	ctx->timing.forward_launches = 1; ctx->timing.other_launches = 1; ctx->timing.traceback_launches = 0; ctx->timing.waves = 1;
+	b->ran = true;
+	return 0;
+}
+
+/* rows: caller buffer of bsb200_poa_rows_bytes() bytes or NULL; row_off_out (njobs+1), best (njobs x 3), status (njobs), ops (njobs x 2) may be NULL */
+extern "C" uint64_t bsb200_poa_rows_bytes(bsb200_poa_batch *b, uint64_t *row_off_out){
+	if(!b) return 0;
+	if(row_off_out) memcpy(row_off_out, b->row_off.data(), b->row_off.size() * 8);
+	return b->row_bytes;
+}
+
+extern "C" int bsb200_poa_fetch(bsb200_ctx *ctx, bsb200_poa_batch *b, uint8_t *rows, int32_t *best, int32_t *status, uint64_t *ops){
+	if(!ctx || !b) return -1;
+	ctx->err.clear();
+	if(!b->ran){ ctx->err = "bsb200_poa_fetch: batch has not been run"; return -1; }
+	cudaSetDevice(ctx->device);
+	cudaStream_t st = ctx->stream;
+	cudaEventRecord(ctx->ev[5], st);
+	const size_t nj = b->njobs;
+	uint64_t bytes = 0;
+	if(nj){
+		if(rows && b->row_bytes){ CK(cudaMemcpyAsync(rows, b->d_rows.p, b->row_bytes, cudaMemcpyDeviceToHost, st)); bytes += b->row_bytes; }
+		if(best){ CK(cudaMemcpyAsync(best, b->d_best.p, nj * 12, cudaMemcpyDeviceToHost, st)); bytes += nj * 12; }
+		if(status){ CK(cudaMemcpyAsync(status, b->d_status.p, nj * 4, cudaMemcpyDeviceToHost, st)); bytes += nj * 4; }
+		if(ops){ CK(cudaMemcpyAsync(ops, b->d_ops.p, nj * 16, cudaMemcpyDeviceToHost, st)); bytes += nj * 16; }
+	}
+	cudaEventRecord(ctx->ev[6], st);
+	CK(cudaStreamSynchronize(st));
+	float ms = 0; cudaEventElapsedTime(&ms, ctx->ev[5], ctx->ev[6]);
+	ctx->timing.d2h_ms = ms; ctx->timing.d2h_bytes = bytes;
+	return 0;
+}
+
+extern "C" int bsb200_poa_rows_batch(bsb200_ctx *ctx, uint32_t njobs, const int32_t *par,
+		const uint8_t *queries, const uint64_t *qoff, const uint32_t *slen,
+		const uint64_t *node_off, const uint8_t *node_base, const uint8_t *node_bonus, const int32_t *node_rpos, const int32_t *node_nct,
+		const int32_t *eoff, const uint64_t *edge_off, const int32_t *edst, const uint32_t *head, const uint32_t *tail,
+		uint8_t *rows, int32_t *best, int32_t *status, uint64_t *ops){
+	bsb200_poa_batch *b = bsb200_poa_upload(ctx, njobs, par, queries, qoff, slen, node_off, node_base, node_bonus, node_rpos, node_nct, eoff, edge_off, edst, head, tail);
+	if(!b) return -1;
+	int rc = bsb200_poa_run(ctx, b);
+	if(rc == 0) rc = bsb200_poa_fetch(ctx, b, rows, best, status, ops);
+	bsb200_poa_free(ctx, b);
+	return rc;
+}

@@ -115,6 +115,51 @@ int bsb200_batch_fetch_dense(bsb200_ctx *ctx, bsb200_batch *b, bsb200_result_t *
 		uint32_t *cigars, uint64_t cigar_cap_words, uint64_t *total_words, uint32_t *ncigar, int32_t *status);
 void bsb200_batch_free(bsb200_ctx *ctx, bsb200_batch *b);
 
+/* ---- POA read-vs-graph banded DP sweep: replaces align_rd_bspoacore (bspoa.h:2515-2618) -------------------- */
+/*
+ * One SWEEP JOB = one call of the reference's align_rd_bspoacore: a read (query) against the selected sub-graph
+ * of a BSPOA, i.e. everything between prepare_rd_align_bspoa (bspoa.h:2020-2230) and alignment2graph_bspoa
+ * (bspoa.h:2274).  It covers dpalign_row_update_bspoa (bspoa.h:2232-2261: row_movx + piecex_row_cal),
+ * dpalign_row_merge_bspoa (bspoa.h:2263-2272: piecex_row_merge, bsalign.h:2474-2616), the head row_init
+ * (bspoa.h:2224-2226) and the end-candidate rules (bspoa.h:2548-2602).  A batch holds many independent jobs
+ * (many BSPOA objects stepped in lock-step by the host).
+ *
+ * Job i:
+ *   par[10*i ..]   = { g->bandwidth (multiple of 16), par->alnmode, M, X, O, E, Q, P, T, refbonus }   (bspoa.h:55-76)
+ *   query          = queries[qoff[i] .. +slen[i])       g->qseq->buffer + g->qb, g->slen bases 0..3
+ *   nodes          = [node_off[i], node_off[i+1])        LOCAL id n = position in g->sels; per node:
+ *                    node_base (bspoanode_t.base), node_bonus (.bonus), node_rpos (.rpos, band offset), node_nct (.nct)
+ *   out-edges      = CSR: node n owns edst[edge_off[i] + eoff[node_off[i] + i + n] .. eoff[node_off[i] + i + n + 1])
+ *                    (eoff has nnode+1 entries per job), destinations are LOCAL ids, listed in the order of the
+ *                    node's edge list (bspoanode_t.edge / bspoaedge_t.next) and restricted to selected nodes
+ *                    (get_bitvec(g->states, e->node), bspoa.h:2538)
+ *   head[i], tail[i] LOCAL ids of nhead / ntail
+ * Outputs:
+ *   rows: for node n of job i, bsb200_poa_block_bytes(par_i) bytes at row_off[i] + n * block_bytes, laid out exactly
+ *         like the reference's g->memp block of that node (dpalign_row_prepare_data, bspoa.h:1787-1793:
+ *         [u bw][e bw][q bw][ubegs 17 x int32], striped byte order), so that the arena of job i can be copied to
+ *         g->memp->buffer + 2 * g->mmblk in one memcpy.  Blocks of nodes the sweep never reached are left untouched.
+ *   best[3*i ..]  = { g->maxscr, g->maxidx as LOCAL id (-1: none), g->maxoff }
+ *   ops[2*i ..]   = { row updates, row merges } executed (the GCUPS denominator is updates * bandwidth)
+ *   status[i]     = BSB200_ST_RANGE if an end-candidate lookup left the band (the reference reads out of bounds)
+ */
+typedef struct bsb200_poa_batch bsb200_poa_batch;
+uint32_t bsb200_poa_block_bytes(const int32_t par[10]);    /* g->mmblk, bspoa.h:2217 */
+bsb200_poa_batch *bsb200_poa_upload(bsb200_ctx *ctx, uint32_t njobs, const int32_t *par,
+		const uint8_t *queries, const uint64_t *qoff, const uint32_t *slen,
+		const uint64_t *node_off, const uint8_t *node_base, const uint8_t *node_bonus, const int32_t *node_rpos, const int32_t *node_nct,
+		const int32_t *eoff, const uint64_t *edge_off, const int32_t *edst, const uint32_t *head, const uint32_t *tail);
+int bsb200_poa_run(bsb200_ctx *ctx, bsb200_poa_batch *b);
+uint64_t bsb200_poa_rows_bytes(bsb200_poa_batch *b, uint64_t *row_off_out /* njobs + 1, may be NULL */);
+int bsb200_poa_fetch(bsb200_ctx *ctx, bsb200_poa_batch *b, uint8_t *rows, int32_t *best, int32_t *status, uint64_t *ops); /* any may be NULL */
+void bsb200_poa_free(bsb200_ctx *ctx, bsb200_poa_batch *b);
+/* one-shot: upload + run + fetch with HOST buffers */
+int bsb200_poa_rows_batch(bsb200_ctx *ctx, uint32_t njobs, const int32_t *par,
+		const uint8_t *queries, const uint64_t *qoff, const uint32_t *slen,
+		const uint64_t *node_off, const uint8_t *node_base, const uint8_t *node_bonus, const int32_t *node_rpos, const int32_t *node_nct,
+		const int32_t *eoff, const uint64_t *edge_off, const int32_t *edst, const uint32_t *head, const uint32_t *tail,
+		uint8_t *rows, int32_t *best, int32_t *status, uint64_t *ops);
+
 /* nominal band width the kernels use for one pair (the GCUPS denominator) */
 uint32_t bsb200_epi8_bandwidth(uint32_t qlen, uint32_t bandwidth);
 uint32_t bsb200_edit_bandwidth(uint32_t qlen, uint32_t tlen, int mode, uint32_t bandwidth);

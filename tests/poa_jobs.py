@@ -23,6 +23,11 @@ class SweepJob:
     def params(self):
         return np.array([self.bw, self.alnmode, self.M, self.X, self.O, self.E, self.Q, self.P, self.T, self.refbonus], dtype=np.int32)
 
+    def to_api(self):
+        """The product-side job object (bsalign_b200.poa.SweepJob) with the same content."""
+        from bsalign_b200 import poa
+        return poa.SweepJob(self.params(), self.query, self.base, self.bonus, self.rpos, self.nct, self.eoff, self.edst, self.head, self.tail)
+
 
 def parse_dump(blob, with_rows=True):
     """blob: uint8 array written by bsref_poa_dump -> list of SweepJob."""
@@ -60,6 +65,20 @@ def parse_dump(blob, with_rows=True):
 def ref_dump(reads, par_override=None, with_rows=True):
     """reads: list of uint8 arrays (bases 0..3).  par_override: None or 10 ints
     (bandwidth, M, X, O, E, Q, P, T, refbonus, alnmode).  Returns the list of sweep jobs of the whole POA job."""
+    return parse_dump(ref_dump_blob(reads, par_override), with_rows)
+
+
+def load_golden():
+    """Sweep jobs of tests/golden/poa_golden.npz (made by tests/golden/make_poa_golden.py from the reference)."""
+    import os
+    z = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "poa_golden.npz"))
+    jobs = []
+    for ci in range(int(z["ncase"])):
+        jobs += parse_dump(z["blob%d" % ci])
+    return jobs
+
+
+def ref_dump_blob(reads, par_override=None):
     lib = ck.ref()
     lens = np.array([len(r) for r in reads], dtype=np.uint32)
     off = np.zeros(len(reads), dtype=np.uint64)
@@ -74,9 +93,7 @@ def ref_dump(reads, par_override=None, with_rows=True):
     blob = np.ctypeslib.as_array(ctypes.cast(out, ctypes.POINTER(ctypes.c_uint8)), shape=(out_len.value,)).copy() if out_len.value else np.zeros(0, np.uint8)
     lib.bsref_free.argtypes = [ctypes.c_void_p]
     lib.bsref_free(out)
-    jobs = parse_dump(blob, with_rows)
-    assert len(jobs) == nj
-    return jobs
+    return blob
 
 
 def make_reads(nreads, tlen, seed, p_sub=0.03, p_ins=0.03, p_del=0.04):

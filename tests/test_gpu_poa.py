@@ -1,0 +1,107 @@
+"""GPU parity tests of the POA sweep (bsb200_poa_* in include/bsalign_b200.h) through the C ABI:
+every node row block (reference g->memp layout), the anchors and (maxscr, maxidx, maxoff) against
+  - the committed sweep dumps of the unmodified reference (tests/golden/poa_golden.npz),
+  - the oracle on larger seeded jobs (graphs from the compiled reference when oracle/_ref travelled to this box,
+    else synthetic graphs from bsalign_b200.synth_poa)."""
+import numpy as np
+import pytest
+
+import checkers as ck
+import poa_jobs as pj
+from bsalign_b200 import api, poa
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def ctx():
+    c = api.Context(0)
+    yield c
+    c.close()
+
+
+def compare_with_oracle(job, rows, ub, best):
+    orows, oub, odone, obest, _ops, rc = pj.oracle_sweep(job)
+    assert rc == 0
+    assert list(best) == list(obest), (list(best), list(obest))
+    m = odone.astype(bool)
+    assert np.array_equal(ub[m], oub[m])
+    assert np.array_equal(rows[m], orows[m])
+
+
+def test_poa_golden_dumps(ctx):
+    jobs = pj.load_golden()
+    res = poa.poa_rows_batch(ctx, poa.SweepBatch([j.to_api() for j in jobs]))
+    for k, j in enumerate(jobs):
+        rows, ub = res.linear(k)
+        assert res.status[k] == 0
+        assert pj.compare_rows(j, rows, ub, j.done, res.best[k]) is None, (k, j.bw, j.pw, pj.compare_rows(j, rows, ub, j.done, res.best[k]))
+
+
+def test_poa_blocks_are_reference_memp_bytes(ctx):
+    # the block arena must be byte-identical to g->memp from block 2 on: striped u/e/q then 17 ubegs ints
+    jobs = [j for j in pj.load_golden() if j.nnode > 2][:4]
+    res = poa.poa_rows_batch(ctx, poa.SweepBatch([j.to_api() for j in jobs]))
+    for k, j in enumerate(jobs):
+        blk = res.blocks(k)
+        W = j.bw // 16
+        p = np.arange(j.bw)
+        idx = (p % W) * 16 + p // W
+        m = j.done.astype(bool)
+        for a in range(j.pw + 1):
+            striped = np.zeros((j.nnode, j.bw), dtype=np.int8)
+            striped[:, idx] = j.rows[:, a, :]
+            assert np.array_equal(blk[m, a * j.bw:(a + 1) * j.bw].view(np.int8), striped[m])
+        off = j.bw * (j.pw + 1)
+        assert np.array_equal(np.ascontiguousarray(blk[m, off:off + 68]).view(np.int32).reshape(-1, 17), j.ub[m])
+
+
+@pytest.mark.parametrize("nreads,tlen,par,err", [
+    (24, 2500, None, (0.03, 0.03, 0.04)),
+    (12, 1500, [128, 2, -6, -3, -2, 0, 0, 20, 1, 1], (0.05, 0.05, 0.05)),
+    (12, 1500, [128, 2, -6, -3, -2, -8, -1, 20, 1, 0], (0.03, 0.03, 0.04)),
+    (12, 1500, [64, 2, -6, -3, -2, -8, -1, 20, 0, 2], (0.04, 0.04, 0.04)),
+    (12, 1200, [256, 2, -6, 0, -2, 0, 0, 0, 1, 1], (0.03, 0.03, 0.04)),
+    (12, 1500, [80, 3, -4, -5, -3, -12, -1, 5, 2, 1], (0.05, 0.05, 0.05)),
+    (20, 2000, None, (0.08, 0.08, 0.10)),
+])
+def test_poa_reference_graphs(ctx, nreads, tlen, par, err):
+    if not ck.have_ref():
+        pytest.skip("oracle/_ref/libbsref.so did not travel to this box")
+    jobs = pj.ref_dump(pj.make_reads(nreads, tlen, 77, *err), par)
+    res = poa.poa_rows_batch(ctx, poa.SweepBatch([j.to_api() for j in jobs]))
+    for k, j in enumerate(jobs):
+        rows, ub = res.linear(k)
+        assert res.status[k] == 0
+        assert pj.compare_rows(j, rows, ub, j.done, res.best[k]) is None, (k, pj.compare_rows(j, rows, ub, j.done, res.best[k]))
+        compare_with_oracle(j, rows, ub, res.best[k])
+
+
+def test_poa_staged_equals_one_shot_and_counts_ops(ctx):
+    jobs = pj.load_golden()
+    batch = poa.SweepBatch([j.to_api() for j in jobs])
+    one = poa.poa_rows_batch(ctx, batch)
+    rs = poa.ResidentSweeps(ctx, batch)
+    try:
+        rs.run(); rs.run()      # re-running resident jobs must be idempotent
+        two = rs.fetch()
+    finally:
+        rs.free()
+    assert np.array_equal(one.best, two.best) and np.array_equal(one.ops, two.ops)
+    for k, j in enumerate(jobs):
+        a, ua = one.linear(k); b, ub = two.linear(k)
+        m = j.done.astype(bool)
+        assert np.array_equal(a[m], b[m]) and np.array_equal(ua[m], ub[m])
+        _r, _u, _d, _b, ops, _rc = pj.oracle_sweep(j)
+        assert list(one.ops[k]) == list(ops)
+
+
+def test_poa_empty_batch_and_trivial_graph(ctx):
+    res = poa.poa_rows_batch(ctx, poa.SweepBatch([]))
+    assert res.best.shape == (0, 3)
+    # head -> tail only (first read of a BSPOA): the end candidate comes from the head's init row
+    jobs = [j for j in pj.load_golden() if j.nnode == 2]
+    assert jobs
+    res = poa.poa_rows_batch(ctx, poa.SweepBatch([j.to_api() for j in jobs]))
+    for k, j in enumerate(jobs):
+        assert (int(res.best[k][0]), int(res.best[k][1]), int(res.best[k][2])) == (j.maxscr, j.maxidx, j.maxoff)
