@@ -37,6 +37,11 @@ WORKLOADS = {
                desc="BASELINE configs[3]: 1M pairs 300bp x 300bp, 2-bit edit, band 64"),
     "g10k": dict(kind="epi8", pairs=592, qlen=10000, err=(0.03, 0.03, 0.04), mode=0, bandwidth=0,
                  desc="north_star target: 10kb x 10kb global, full band"),
+    # POA: `pairs` = MSA jobs per GPU stepped in lock-step; one step = one sweep round (every job aligns its next read
+    # against the graph of its previous nrec+1 = 21 reads, bspoa.h:2636-2642); seqcore = 40 makes 39 such rounds per 64-read job
+    "c5": dict(kind="poa", pairs=1000, qlen=15000, err=(0.03, 0.03, 0.04), mode=1, bandwidth=128, distinct=16,
+               desc="BASELINE configs[4]: BSPOA 64 reads x 15 kb (DEFAULT_BSPOA_PAR), 1k MSA jobs in lock-step; step = one "
+                    "read-vs-graph sweep round (graph of nrec+1 = 21 reads) over all jobs; DEFAULT_BSPOA_PAR (seqcore 40) runs 39 such rounds per 64-read job"),
 }
 MATRIX = (2, -6)
 GAPS = (-3, -2, 0, 0)
@@ -124,6 +129,206 @@ def cpu_reference_run(w, batch, nthreads, repeat=1):
     return ck.last_call_seconds, kind, res  # the C call only: results + cigars written to caller arenas
 
 
+def poa_make_batch(w, seed, njobs):
+    """njobs sweep jobs: `distinct` different synthetic graphs (bsalign_b200/synth_poa.py), tiled; every job has its own arenas."""
+    from bsalign_b200 import poa, synth_poa
+    d = min(w["distinct"], njobs)
+    protos = [synth_poa.make_sweep_job(seed * 1000 + i, tlen=w["qlen"], ngraph=21, par=dict(bandwidth=w["bandwidth"], alnmode=w["mode"]),
+                                       p_sub=w["err"][0], p_ins=w["err"][1], p_del=w["err"][2]) for i in range(d)]
+    return poa.SweepBatch([protos[i % d] for i in range(njobs)]), protos
+
+
+def poa_cpu_run(batch, nthreads):
+    """The oracle port of align_rd_bspoacore (oracle/bsalign_oracle.c:bso_poa_sweep_batch) on nthreads host threads."""
+    import poa_jobs as pj
+    r = pj.oracle_sweep_batch(batch, nthreads=nthreads, want_rows=False)
+    return r["seconds"], r
+
+
+def poa_reference_run(w, njobs, nthreads, seed=4000):
+    """The UNMODIFIED reference (oracle/_ref: bsref_poa_time): njobs whole BSPOA jobs (64 reads x qlen, DEFAULT_BSPOA_PAR, realn = 0), one per
+    host thread at a time; only the CPU time inside align_rd_bspoacore counts.  Returns (GCUPS with all threads busy, description) or None."""
+    import checkers as ck
+    import poa_jobs as pj
+    if not ck.have_ref():
+        return None
+    sets = [pj.make_reads(64, w["qlen"], seed + i, *w["err"]) for i in range(njobs)]
+    r = pj.ref_time_jobs(sets, nthreads)
+    val = r["cells"] / (r["dp_seconds"] / min(nthreads, njobs)) / 1e9
+    desc = ("%d whole BSPOA jobs (64 reads x %d bp, DEFAULT_BSPOA_PAR) through the unmodified reference on %d host threads; only the thread CPU time inside "
+            "align_rd_bspoacore counts: %.2f s for %d row updates + %d merges (%.2f us per update); GCUPS = cells / (that time / threads)"
+            % (njobs, w["qlen"], nthreads, r["dp_seconds"], r["nupd"], r["nmrg"], r["dp_seconds"] / max(1, r["nupd"]) * 1e6))
+    return val, desc, r
+
+
+def main_poa(args, w, njobs, ncores, rank, local_rank, world):
+    from bsalign_b200 import poa
+    bw = w["bandwidth"]
+    if args.impl == "reference":
+        if rank != 0:
+            return
+        # the reference's sweep lives inside BSPOA objects (graph surgery, consensus: out of scope); its CPU arm is the oracle port of
+        # align_rd_bspoacore, pinned against the reference's own sweep dumps (tests/test_poa.py)
+        sample = args.cpu_sample or ncores
+        vals, kind, dt = [], "reference", 0.0
+        for _ in range(max(1, args.steps)):
+            rr = poa_reference_run(w, sample, ncores)
+            if rr is None:
+                break
+            vals.append(rr[0]); dt += rr[2]["wall"] / max(1, args.steps)
+        if vals:
+            val = float(np.mean(vals))
+            sample_desc = rr[1]
+        else:   # the compiled reference did not travel: the oracle port of the sweep on synthetic graphs
+            kind = "port"
+            sample = args.cpu_sample or 2 * ncores
+            batch, _ = poa_make_batch(w, 1, sample)
+            for _ in range(args.steps):
+                d, r = poa_cpu_run(batch, ncores)
+                dt += d / args.steps
+            val = int(r["ops"][:, 0].sum()) * bw / dt / 1e9
+            sample_desc = "%d synthetic sweep jobs per step through the scalar oracle port, %d host threads" % (sample, ncores)
+        print(json.dumps({
+            "impl": "reference", "metric": "GCUPS", "value": val, "unit": "GCUPS (1e9 band cells/s)", "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "int8", "data": "synthetic",
+            "config": {"workload": "c5: %s" % w["desc"], "jobs_per_step": sample},
+            "cpu_baseline": {"value": val, "unit": "GCUPS", "cores": ncores, "kind": kind, "sample": sample_desc},
+            "e2e": {"value": val, "unit": "GCUPS", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        }))
+        return
+    import torch
+    import torch.distributed as dist
+    from bsalign_b200 import api
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the product path has no CPU fallback (use --impl reference for the CPU arm)")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        sys.stdout.flush()
+        saved = os.dup(1)
+        os.dup2(2, 1)
+        try:
+            dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+            dist.barrier()
+            torch.cuda.synchronize()
+        finally:
+            sys.stdout.flush()
+            os.dup2(saved, 1)
+            os.close(saved)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def reduce(x, op):
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=op)
+        return float(t.item())
+
+    batch, protos = poa_make_batch(w, 1 + rank, njobs)
+    pin = lambda a: torch.from_numpy(a).pin_memory().numpy()
+    for name in ("par", "queries", "qoff", "slen", "node_off", "base", "bonus", "rpos", "nct", "eoff", "edge_off", "edst", "head", "tail"):
+        setattr(batch, name, pin(getattr(batch, name)))
+    ctx = api.Context(local_rank)
+    # ---- kernel-only leg: jobs resident in HBM -------------------------------------------------------
+    rs = poa.ResidentSweeps(ctx, batch)
+    for _ in range(args.warmup):
+        rs.run()
+    sampler = ClockSampler(local_rank)
+    barrier()
+    sampler.start()
+    dev_ms = sweep_ms = 0.0
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        rs.run()
+        tm = ctx.timing()
+        dev_ms += tm["run_ms"]; sweep_ms += tm["forward_ms"]
+    barrier()
+    wall = time.perf_counter() - t0
+    clocks = sampler.stop()
+    res = rs.fetch(want_rows=False)
+    rs.free()
+    nupd, nmrg = int(res.ops[:, 0].sum()), int(res.ops[:, 1].sum())
+    cells = nupd * bw
+    blk = int(batch.blk[0])
+    alg_bytes = (2 * nupd + 3 * nmrg) * blk                    # SURVEY.md 8d: update reads + writes a block, merge touches three
+    step_ms = reduce(dev_ms / args.steps, dist.ReduceOp.MAX if world > 1 else None)
+    total_cells = reduce(cells, dist.ReduceOp.SUM if world > 1 else None)
+    value = total_cells / (step_ms * 1e-3) / 1e9
+    # ---- e2e leg: host buffers through the one-shot C-ABI call (graphs up, row blocks + best ends back) ----
+    rows = pin(np.zeros(int(batch.row_off[-1]), dtype=np.uint8))
+    for _ in range(min(args.warmup, 2)):
+        r = poa.poa_rows_batch(ctx, batch, rows=rows)
+    barrier()
+    t0 = time.perf_counter()
+    parts = {"h2d_ms": 0.0, "run_ms": 0.0, "d2h_ms": 0.0}
+    for _ in range(args.steps):
+        r = poa.poa_rows_batch(ctx, batch, rows=rows)
+        tm2 = ctx.timing()
+        for k in parts:
+            parts[k] += tm2[k] / args.steps
+    barrier()
+    e2e_ms = reduce((time.perf_counter() - t0) / args.steps * 1e3, dist.ReduceOp.MAX if world > 1 else None)
+    e2e_val = total_cells / (e2e_ms * 1e-3) / 1e9
+    assert np.array_equal(r.best, res.best), "e2e and resident runs disagree"
+    # ---- parity: distinct prototypes against the oracle (best ends + every row block) --------------------
+    checked = None
+    if args.check:
+        import poa_jobs as pj
+        k = min(args.check, len(protos))
+        ob = pj.oracle_sweep_batch(poa.SweepBatch(protos[:k]), nthreads=ncores)
+        ok = True
+        for i in range(k):
+            lin, ub = r.linear(i)
+            m = ob["done"][int(batch.node_off[i]):int(batch.node_off[i + 1])].astype(bool)
+            ok = ok and np.array_equal(r.best[i], ob["best"][i]) and np.array_equal(lin[m], ob["rows"][i][m]) \
+                and np.array_equal(ub[m], ob["ub"][int(batch.node_off[i]):int(batch.node_off[i + 1])][m])
+        checked = {"jobs": k, "bit_exact": bool(ok)}
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    peak = float(peaks.get("hbm_gbs", 6650.0))
+    achieved = alg_bytes * args.steps / (sweep_ms * 1e-3) / 1e9 if sweep_ms > 0 else 0.0
+    roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                "peak_source": "measured (MEASURED_PEAKS.json)" if peaks else "fallback (B200_PROFILING.md)", "traffic": None,
+                "kernel": "poa_sweep_kernel", "launches_per_step": 1, "algorithmic_bytes_per_launch": int(alg_bytes),
+                "kernel_ms_per_launch": sweep_ms / args.steps, "row_updates": nupd, "row_merges": nmrg, "block_bytes": blk}
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        rr = poa_reference_run(w, args.cpu_sample or ncores, ncores)
+        if rr is not None:
+            cpu = {"value": rr[0], "unit": "GCUPS", "cores": ncores, "kind": "reference", "sample": rr[1]}
+        else:
+            sample = min(njobs, args.cpu_sample or 2 * ncores)
+            sub = poa.SweepBatch([protos[i % len(protos)] for i in range(sample)])
+            dt, cr = poa_cpu_run(sub, ncores)
+            cpu = {"value": int(cr["ops"][:, 0].sum()) * bw / dt / 1e9, "unit": "GCUPS", "cores": ncores, "kind": "port",
+                   "sample": "first %d sweep jobs of the same batch through the scalar oracle port, %d host threads, %.1f s" % (sample, ncores, dt),
+                   "results_equal_gpu": bool(np.array_equal(cr["best"], r.best[:sample]))}
+    if rank == 0:
+        print(json.dumps({
+            "metric": "GCUPS", "value": value, "unit": "GCUPS (1e9 band cells/s)", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": step_ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "int8", "data": "synthetic",
+            "config": {"workload": "c5: %s" % w["desc"], "jobs_per_gpu": njobs, "distinct_graphs": len(protos), "nodes_per_job": int(batch.node_off[1]),
+                       "l2": "graphs (%.0f MB) and the %.1f GB of row blocks written per step exceed the 126 MB L2" % (
+                           (batch.rpos.nbytes * 3 + batch.edst.nbytes) / 1e6, float(batch.row_off[-1]) / 1e9),
+                       "timing": "CUDA events on the library stream; max over ranks", "wall_ms_per_step": wall / args.steps * 1e3,
+                       "ms_of_dp_per_64_read_job_at_this_batch": step_ms * 39},
+            "e2e": {"value": e2e_val, "unit": "GCUPS", "ms_per_step": e2e_ms, "h2d_bytes_per_step": int(tm2["h2d_bytes"]), "d2h_bytes_per_step": int(tm2["d2h_bytes"]),
+                    "device_parts_ms": parts},
+            "gpu_launches": 2 * args.steps, "roofline": roofline, "cpu_baseline": cpu, "clocks": clocks,
+            "parity": {"nonzero_status_jobs": int((r.status != 0).sum()), "score_checksum": int(r.best[:, 0].astype(np.int64).sum()), "checked": checked},
+        }))
+    ctx.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -143,6 +348,8 @@ def main():
     w = WORKLOADS[args.workload]
     pairs = args.pairs or w["pairs"]
     ncores = os.cpu_count() or 1
+    if w["kind"] == "poa":
+        return main_poa(args, w, pairs, ncores, rank, local_rank, world)
 
     # ------------------------------------------------------------------ reference arm (CPU) -----------
     if args.impl == "reference":

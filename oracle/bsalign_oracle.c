@@ -1024,3 +1024,58 @@ int bso_poa_sweep(const int32_t *par, const uint8_t *query, uint32_t slen, uint3
 	free(scratch); free(mpos); free(stack); free(vst);
 	return a->err;
 }
+
+/* Batch runner over the packed arenas of include/bsalign_b200.h (bsb200_poa_rows_batch): a pthread pool over independent
+ * sweep jobs.  rows_lin (optional): per job nnode * 3 * bw bytes at rows_off[job] (LINEAR band order); ubs (optional): per
+ * node 17 ints; done (optional): per node.  Used by the parity tests and by bench.py's cpu_baseline leg. */
+typedef struct {
+	uint32_t njobs;
+	const int32_t *par; const uint8_t *queries; const uint64_t *qoff; const uint32_t *slen;
+	const uint64_t *node_off; const uint8_t *base, *bonus; const int32_t *rpos, *nct, *eoff; const uint64_t *edge_off; const int32_t *edst;
+	const uint32_t *head, *tail;
+	int8_t *rows_lin; const uint64_t *rows_off; int32_t *ubs; uint8_t *done; int32_t *best; uint64_t *ops;
+	volatile uint32_t next; volatile int err;
+} bso_poa_batch_t;
+
+static void* bso_poa_worker(void *arg){
+	bso_poa_batch_t *b = (bso_poa_batch_t*)arg;
+	int err = 0;
+	while(1){
+		uint32_t i = __sync_fetch_and_add(&b->next, 1);
+		uint64_t n0, nn;
+		uint32_t bw;
+		int8_t *rows; int32_t *ubs; uint8_t *done;
+		if(i >= b->njobs) break;
+		n0 = b->node_off[i]; nn = b->node_off[i + 1] - n0; bw = (uint32_t)b->par[(size_t)i * 10];
+		rows = b->rows_lin ? b->rows_lin + b->rows_off[i] : malloc(nn * 3 * (size_t)bw);
+		ubs = b->ubs ? b->ubs + n0 * 17 : malloc(nn * 17 * sizeof(int32_t));
+		done = b->done ? b->done + n0 : malloc(nn);
+		err |= bso_poa_sweep(b->par + (size_t)i * 10, b->queries + b->qoff[i], b->slen[i], (uint32_t)nn, b->base + n0, b->bonus + n0, b->rpos + n0, b->nct + n0,
+			b->eoff + n0 + i, b->edst + b->edge_off[i], b->head[i], b->tail[i], rows, ubs, done, b->best + (size_t)i * 3, b->ops ? b->ops + (size_t)i * 2 : NULL);
+		if(!b->rows_lin) free(rows);
+		if(!b->ubs) free(ubs);
+		if(!b->done) free(done);
+	}
+	if(err) __sync_fetch_and_or(&b->err, err);
+	return NULL;
+}
+
+int bso_poa_sweep_batch(uint32_t njobs, const int32_t *par, const uint8_t *queries, const uint64_t *qoff, const uint32_t *slen,
+		const uint64_t *node_off, const uint8_t *base, const uint8_t *bonus, const int32_t *rpos, const int32_t *nct,
+		const int32_t *eoff, const uint64_t *edge_off, const int32_t *edst, const uint32_t *head, const uint32_t *tail,
+		int8_t *rows_lin, const uint64_t *rows_off, int32_t *ubs, uint8_t *done, int32_t *best, uint64_t *ops, int nthreads){
+	bso_poa_batch_t b;
+	pthread_t *tids;
+	int i;
+	memset(&b, 0, sizeof(b));
+	b.njobs = njobs; b.par = par; b.queries = queries; b.qoff = qoff; b.slen = slen; b.node_off = node_off; b.base = base; b.bonus = bonus;
+	b.rpos = rpos; b.nct = nct; b.eoff = eoff; b.edge_off = edge_off; b.edst = edst; b.head = head; b.tail = tail;
+	b.rows_lin = rows_lin; b.rows_off = rows_off; b.ubs = ubs; b.done = done; b.best = best; b.ops = ops;
+	if(nthreads < 1) nthreads = 1;
+	if(nthreads == 1){ bso_poa_worker(&b); return b.err; }
+	tids = malloc(sizeof(pthread_t) * nthreads);
+	for(i=0;i<nthreads;i++) pthread_create(tids + i, NULL, bso_poa_worker, &b);
+	for(i=0;i<nthreads;i++) pthread_join(tids[i], NULL);
+	free(tids);
+	return b.err;
+}

@@ -295,3 +295,65 @@ int64_t bsref_poa_dump(uint32_t nreads, const uint8_t *seqs, const uint64_t *off
 }
 
 void bsref_free(void *p){ free(p); }
+
+/* Time the reference's own sweep: run a whole POA job (same call sequence as end_bspoa, bspoa.h:4737-4760, realn = 0) and
+ * accumulate the CPU time spent inside align_rd_bspoacore only (thread CPU clock), plus the number of row updates (every update
+ * increments v->vst once, bspoa.h:2592) and merges.  One BSPOA per call: callers may run several calls on different threads. */
+#include <time.h>
+static double bsref_thread_seconds(void){ struct timespec ts; clock_gettime(CLOCK_THREAD_CPUTIME_ID, &ts); return ts.tv_sec + 1e-9 * ts.tv_nsec; }
+
+int bsref_poa_time(uint32_t nreads, const uint8_t *seqs, const uint64_t *off, const uint32_t *len, const int32_t *par_override,
+		double *dp_seconds, double *total_seconds, uint64_t *nupd_out, uint64_t *nmrg_out, uint64_t *cells_out){
+	BSPOAPar par = DEFAULT_BSPOA_PAR;
+	BSPOA *g;
+	u4i i; u2i rid;
+	double dp = 0, t0, t1, tb = bsref_thread_seconds();
+	uint64_t nupd = 0, nmrg = 0, cells = 0;
+	if(par_override){
+		par.bandwidth = par_override[0]; par.M = par_override[1]; par.X = par_override[2]; par.O = par_override[3]; par.E = par_override[4];
+		par.Q = par_override[5]; par.P = par_override[6]; par.T = par_override[7]; par.refbonus = par_override[8]; par.alnmode = par_override[9];
+	}
+	par.realn = 0;
+	g = init_bspoa(par);
+	beg_bspoa(g);
+	for(i=0;i<nreads;i++) fwdbitseqpush_bspoa(g, (u1i*)seqs + off[i], len[i]);
+	if(g->seqs->nseq > 1){
+		if(g->par->shuffle) shuffle_reads_by_kmers_bspoa(g);
+		g->nmsa = g->par->seqcore ? num_min(g->seqs->nseq, g->par->seqcore) : g->seqs->nseq;
+		for(rid=0;rid<g->seqs->nseq;rid++) _add_read_bspoa_core(g, rid);
+		g->nrds = 1;
+		for(rid=1;rid<g->nmsa;rid++){
+			u4i nhead, ntail, rlen = g->seqs->rdlens->buffer[rid], k;
+			u2i ridxbeg, ridxend;
+			if(!g->par->refmode && g->par->bwtrigger){ msa_bspoa(g); simple_cns_bspoa(g); }
+			clear_u8v(g->todels);
+			if(rlen){
+				nhead = get_rdnode_bspoa(g, rid, -1)->header;
+				ntail = get_rdnode_bspoa(g, rid, rlen)->header;
+				if(g->par->nrec){ ridxbeg = num_max(0, Int(rid) - g->par->nrec - 1); ridxend = rid; } else { ridxbeg = 0; ridxend = MAX_U2; }
+				sel_nodes_bspoa(g, nhead, ntail, ridxbeg, ridxend);
+				prepare_rd_align_bspoa(g, g->par, nhead, ntail, rid, 0, rlen);
+				t0 = bsref_thread_seconds();
+				align_rd_bspoacore(g, g->par, rid, nhead, ntail);
+				t1 = bsref_thread_seconds();
+				dp += t1 - t0;
+				for(k=0;k<g->sels->size;k++){
+					bspoanode_t *u = ref_bspoanodev(g->nodes, g->sels->buffer[k]);
+					if(g->sels->buffer[k] == ntail || g->sels->buffer[k] == nhead) continue;
+					nupd += u->vst; if(u->vst > 1) nmrg += u->vst - 1;
+					cells += (uint64_t)u->vst * g->bandwidth;
+				}
+				alignment2graph_bspoa(g, g->par, rid, 0, nhead, ntail, g->maxidx, g->maxoff, NULL);
+				for(k=0;k<g->todels->size;k++){
+					chg_edge_bspoa(g, ref_bspoanodev(g->nodes, g->todels->buffer[k] >> 32), ref_bspoanodev(g->nodes, g->todels->buffer[k] & MAX_U4), -1, NULL);
+				}
+				clear_u8v(g->todels);
+			}
+			g->nrds ++;
+		}
+	}
+	free_bspoa(g);
+	*dp_seconds = dp; *total_seconds = bsref_thread_seconds() - tb;
+	*nupd_out = nupd; *nmrg_out = nmrg; *cells_out = cells;
+	return 0;
+}

@@ -146,3 +146,58 @@ def compare_rows(j, rows, ub, done, best, pw=None):
             bad = np.nonzero((rows[:, a] != j.rows[:, a]).any(axis=1) & m)[0]
             return "array %d differs at nodes %s" % (a, bad[:5].tolist())
     return None
+
+
+def oracle_sweep_batch(batch, nthreads=1, want_rows=True):
+    """oracle/bsalign_oracle.c:bso_poa_sweep_batch on a packed bsalign_b200.poa.SweepBatch.
+    Returns dict(rows=list of [nnode,3,bw] linear arrays or None, ub, done, best, ops, seconds)."""
+    import time
+    lib = ck.oracle()
+    n = batch.n
+    nn = (batch.node_off[1:] - batch.node_off[:-1]).astype(np.uint64)
+    bw = batch.par[:, 0].astype(np.uint64) if n else np.zeros(0, np.uint64)
+    roff = np.zeros(n + 1, dtype=np.uint64)
+    np.cumsum(nn * bw * np.uint64(3), out=roff[1:])
+    rows = np.zeros(int(roff[-1]), dtype=np.int8) if want_rows else None
+    tot = int(batch.node_off[-1]) if n else 0
+    ub = np.zeros((tot, 17), dtype=np.int32) if want_rows else None
+    done = np.zeros(tot, dtype=np.uint8) if want_rows else None
+    best = np.zeros((n, 3), dtype=np.int32)
+    ops = np.zeros((n, 2), dtype=np.uint64)
+    p = ck._ptr
+    t0 = time.perf_counter()
+    rc = lib.bso_poa_sweep_batch(ctypes.c_uint32(n), p(batch.par), p(batch.queries), p(batch.qoff), p(batch.slen), p(batch.node_off), p(batch.base), p(batch.bonus),
+                                 p(batch.rpos), p(batch.nct), p(batch.eoff), p(batch.edge_off), p(batch.edst), p(batch.head), p(batch.tail),
+                                 p(rows), p(roff), p(ub), p(done), p(best), p(ops), ctypes.c_int(nthreads))
+    dt = time.perf_counter() - t0
+    out_rows = None
+    if want_rows:
+        out_rows = [rows[int(roff[i]):int(roff[i + 1])].reshape(int(nn[i]), 3, int(bw[i])) for i in range(n)]
+    return dict(rows=out_rows, ub=ub, done=done, best=best, ops=ops, seconds=dt, rc=rc)
+
+
+def ref_time_jobs(read_sets, nthreads, par_override=None):
+    """Run whole BSPOA jobs through the unmodified reference (bsref_poa_time), one job per call on `nthreads` host threads.
+    Returns dict(dp_seconds = CPU seconds inside align_rd_bspoacore summed over jobs, total_seconds, nupd, nmrg, cells, wall)."""
+    import time
+    from concurrent.futures import ThreadPoolExecutor
+    lib = ck.ref()
+    po = None if par_override is None else np.ascontiguousarray(par_override, dtype=np.int32)
+
+    def one(reads):
+        lens = np.array([len(r) for r in reads], dtype=np.uint32)
+        off = np.zeros(len(reads), dtype=np.uint64)
+        off[1:] = np.cumsum(lens[:-1], dtype=np.uint64)
+        seqs = np.ascontiguousarray(np.concatenate(reads), dtype=np.uint8)
+        dp, tot = ctypes.c_double(), ctypes.c_double()
+        nu, nm, ce = ctypes.c_uint64(), ctypes.c_uint64(), ctypes.c_uint64()
+        lib.bsref_poa_time(ctypes.c_uint32(len(reads)), ck._ptr(seqs), ck._ptr(off), ck._ptr(lens), ck._ptr(po),
+                           ctypes.byref(dp), ctypes.byref(tot), ctypes.byref(nu), ctypes.byref(nm), ctypes.byref(ce))
+        return dp.value, tot.value, nu.value, nm.value, ce.value
+    t0 = time.perf_counter()
+    with ThreadPoolExecutor(max_workers=nthreads) as ex:
+        rs = list(ex.map(one, read_sets))
+    wall = time.perf_counter() - t0
+    a = np.array(rs, dtype=np.float64)
+    return dict(dp_seconds=float(a[:, 0].sum()), total_seconds=float(a[:, 1].sum()), nupd=int(a[:, 2].sum()), nmrg=int(a[:, 3].sum()),
+                cells=int(a[:, 4].sum()), wall=wall, jobs=len(read_sets))
