@@ -3,13 +3,18 @@
 // stream and brings back the node row blocks (reference memp layout), the best end per job and the op counts.
 #pragma once
 #include "poa_kernels.cuh"
+#include "poa_fast.cuh"
 
 struct bsb200_poa_batch {
 	uint32_t njobs = 0;
 	uint64_t nnodes = 0, nedges = 0, qbytes = 0, row_bytes = 0;
 	uint32_t max_bw = 16;
 	std::vector<uint64_t> row_off;      // njobs + 1
-	std::vector<uint32_t> order;
+	std::vector<uint32_t> order;        // generic-kernel jobs, heaviest first
+	std::vector<uint32_t> order_fast[3]; // register-kernel jobs by piecewise (1, 2), heaviest first
+	std::vector<uint64_t> qsel_off;
+	uint64_t qsel_bytes = 0;
+	DevBuf d_order_fast, d_qsel, d_qsel_off, d_counter2;
 	DevBuf d_par, d_queries, d_qcode, d_qoff, d_slen, d_node_off, d_node, d_eoff, d_edge_off, d_edst, d_head, d_tail,
 		d_mpos, d_vst, d_stack, d_rows, d_row_off, d_best, d_status, d_ops, d_order, d_counter;
 	bool ran = false;
@@ -27,7 +32,8 @@ extern "C" void bsb200_poa_free(bsb200_ctx *ctx, bsb200_poa_batch *b){
 	if(!b) return;
 	if(ctx) cudaSetDevice(ctx->device);
 	DevBuf *ds[] = {&b->d_par, &b->d_queries, &b->d_qcode, &b->d_qoff, &b->d_slen, &b->d_node_off, &b->d_node, &b->d_eoff, &b->d_edge_off, &b->d_edst,
-		&b->d_head, &b->d_tail, &b->d_mpos, &b->d_vst, &b->d_stack, &b->d_rows, &b->d_row_off, &b->d_best, &b->d_status, &b->d_ops, &b->d_order, &b->d_counter};
+		&b->d_head, &b->d_tail, &b->d_mpos, &b->d_vst, &b->d_stack, &b->d_rows, &b->d_row_off, &b->d_best, &b->d_status, &b->d_ops, &b->d_order, &b->d_counter,
+		&b->d_order_fast, &b->d_qsel, &b->d_qsel_off, &b->d_counter2};
 	for(auto d : ds) d->release();
 	delete b;
 }
@@ -62,13 +68,34 @@ extern "C" bsb200_poa_batch *bsb200_poa_upload(bsb200_ctx *ctx, uint32_t njobs, 
 	}
 	b->row_bytes = b->row_off[njobs];
 	std::sort(kv.begin(), kv.end());
-	b->order.resize(njobs);
-	for(uint32_t i=0;i<njobs;i++) b->order[i] = kv[i].second;
 	// node records: rpos, nct | base << 16 | bonus << 24
 	std::vector<int2> nodes(b->nnodes);
 	for(uint64_t k=0;k<b->nnodes;k++){
 		nodes[k].x = node_rpos[k];
 		nodes[k].y = (int)(((uint32_t)node_nct[k] & 0xffffu) | ((uint32_t)node_base[k] << 16) | (((uint32_t)node_bonus[k] & 1u) << 24));
+	}
+	// jobs the register-resident kernel takes (poa_fast.cuh): band of exactly 128 cells that never runs past the read end, gap costs <= 0
+	// with a gap-open cost, small scores; everything else goes to the generic kernel
+	b->qsel_off.assign((size_t)njobs + 1, 0);
+	std::vector<uint8_t> fast_pw(njobs, 0);
+	for(uint32_t i=0;i<njobs;i++){
+		const int32_t *p = par + (size_t)i * 10;
+		const int O = p[4], E = p[5], Q = p[6], P = p[7];
+		const int pw = epi8_piecewise((int8_t)O, (int8_t)E, (int8_t)Q, (int8_t)P, p[0]);
+		bool ok = p[0] == kPoaFastBw && slen[i] >= (uint32_t)kPoaFastBw && pw >= 1 && O >= -64 && O <= 0 && E >= -64 && E <= 0 && O + E <= 0 &&
+			p[2] + p[9] + 1 <= 62 && p[2] >= -62 && p[3] >= -62 && p[3] <= 62 && p[9] >= 0;
+		if(pw == 2) ok = ok && Q >= -64 && Q <= 0 && P >= -64 && P <= 0;
+		for(uint64_t k=node_off[i];ok&&k<node_off[i+1];k++){
+			if(node_rpos[k] < 0 || (uint64_t)node_rpos[k] + kPoaFastBw > slen[i]) ok = false;
+			if(k - node_off[i] != tail[i] && k - node_off[i] != head[i] && node_base[k] > 3) ok = false;
+		}
+		if(ok){ fast_pw[i] = (uint8_t)pw; b->qsel_off[i + 1] = b->qsel_off[i] + ((uint64_t)slen[i] + 16 + 15) / 16 * 16; }
+		else b->qsel_off[i + 1] = b->qsel_off[i];
+	}
+	b->qsel_bytes = b->qsel_off[njobs];
+	for(uint32_t i=0;i<njobs;i++){
+		const uint32_t jb = kv[i].second;
+		if(fast_pw[jb]) b->order_fast[fast_pw[jb]].push_back(jb); else b->order.push_back(jb);
 	}
 	cudaError_t e = cudaSuccess;
 	auto R = [&](cudaError_t x){ if(e == cudaSuccess) e = x; };
@@ -80,7 +107,8 @@ extern "C" bsb200_poa_batch *bsb200_poa_upload(bsb200_ctx *ctx, uint32_t njobs, 
 	R(b->d_mpos.reserve(nn * 4 + 4)); R(b->d_vst.reserve(nn * 4 + 4)); R(b->d_stack.reserve(nn * 4 + 4));
 	R(b->d_rows.reserve(b->row_bytes + 16)); R(b->d_row_off.reserve((nj + 1) * 8));
 	R(b->d_best.reserve(nj * 12 + 12)); R(b->d_status.reserve(nj * 4 + 4)); R(b->d_ops.reserve(nj * 16 + 16));
-	R(b->d_order.reserve(nj * 4 + 4)); R(b->d_counter.reserve(256));
+	R(b->d_order.reserve(nj * 4 + 4)); R(b->d_counter.reserve(256)); R(b->d_counter2.reserve(256));
+	R(b->d_order_fast.reserve(nj * 4 + 4)); R(b->d_qsel.reserve(b->qsel_bytes + 64)); R(b->d_qsel_off.reserve((nj + 1) * 8));
 	if(e != cudaSuccess){ fail(ctx, "device allocation (poa)", e); bsb200_poa_free(ctx, b); return nullptr; }
 	cudaStream_t st = ctx->stream;
 	cudaEventRecord(ctx->ev[0], st);
@@ -97,7 +125,15 @@ extern "C" bsb200_poa_batch *bsb200_poa_upload(bsb200_ctx *ctx, uint32_t njobs, 
 		R(cudaMemcpyAsync(b->d_head.p, head, nj * 4, cudaMemcpyHostToDevice, st));
 		R(cudaMemcpyAsync(b->d_tail.p, tail, nj * 4, cudaMemcpyHostToDevice, st));
 		R(cudaMemcpyAsync(b->d_row_off.p, b->row_off.data(), (nj + 1) * 8, cudaMemcpyHostToDevice, st));
-		R(cudaMemcpyAsync(b->d_order.p, b->order.data(), nj * 4, cudaMemcpyHostToDevice, st));
+		if(!b->order.empty()) R(cudaMemcpyAsync(b->d_order.p, b->order.data(), b->order.size() * 4, cudaMemcpyHostToDevice, st));
+		{
+			size_t at = 0;
+			for(int pw=1;pw<=2;pw++){
+				if(!b->order_fast[pw].empty()) R(cudaMemcpyAsync(b->d_order_fast.as<uint32_t>() + at, b->order_fast[pw].data(), b->order_fast[pw].size() * 4, cudaMemcpyHostToDevice, st));
+				at += b->order_fast[pw].size();
+			}
+		}
+		R(cudaMemcpyAsync(b->d_qsel_off.p, b->qsel_off.data(), (nj + 1) * 8, cudaMemcpyHostToDevice, st));
 	}
 	cudaEventRecord(ctx->ev[1], st);
 	R(cudaStreamSynchronize(st));
@@ -125,17 +161,50 @@ extern "C" int bsb200_poa_run(bsb200_ctx *ctx, bsb200_poa_batch *b){
 	a.best = b->d_best.as<int32_t>(); a.status = b->d_status.as<int32_t>(); a.ops = b->d_ops.as<unsigned long long>();
 	a.slot_bytes = 3 * b->max_bw + 80;
 	const size_t smem = (size_t)(kPoaThreads / kPoaGroup) * (2 * a.slot_bytes + 80 + 32 + 128);
-	if(smem > ctx->smem_optin){ ctx->err = "bsb200_poa_run: bandwidth too wide for the shared-memory row slots"; return -1; }
-	CK(cudaFuncSetAttribute(poa_sweep_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+	const uint32_t ngen = (uint32_t)b->order.size();
+	if(ngen && smem > ctx->smem_optin){ ctx->err = "bsb200_poa_run: bandwidth too wide for the shared-memory row slots"; return -1; }
+	if(ngen) CK(cudaFuncSetAttribute(poa_sweep_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
 	cudaEventRecord(ctx->ev[2], st);
 	CK(cudaMemsetAsync(b->d_counter.p, 0, 16, st));
-	const uint32_t prep_blocks = std::min<uint32_t>(b->njobs, (uint32_t)ctx->num_sms * 8);
-	poa_prep_kernel<<<prep_blocks, 256, 0, st>>>(b->njobs, b->d_queries.as<uint8_t>(), a.qoff, a.slen, b->d_qcode.as<uint8_t>(), a.node_off, a.mpos, a.vst);
+	CK(cudaMemsetAsync(b->d_counter2.p, 0, 16, st));
+	uint32_t launches = 0;
+	if(ngen){
+		const uint32_t prep_blocks = std::min<uint32_t>(ngen, (uint32_t)ctx->num_sms * 8);
+		a.njobs = ngen;
+		poa_prep_kernel<<<prep_blocks, 256, 0, st>>>(ngen, a.order, b->d_queries.as<uint8_t>(), a.qoff, a.slen, b->d_qcode.as<uint8_t>(), a.node_off, a.mpos, a.vst);
+	}
+	const uint32_t nfast = (uint32_t)(b->order_fast[1].size() + b->order_fast[2].size());
+	if(nfast){
+		const uint32_t prep_blocks = std::min<uint32_t>(nfast, (uint32_t)ctx->num_sms * 8);
+		poa_fast_prep_kernel<<<prep_blocks, 256, 0, st>>>(nfast, b->d_order_fast.as<uint32_t>(), b->d_queries.as<uint8_t>(), a.qoff, a.slen,
+			b->d_qsel.as<uint8_t>(), b->d_qsel_off.as<uint64_t>(), a.node_off, a.mpos, a.vst);
+	}
 	cudaEventRecord(ctx->ev[3], st);
-	const uint32_t groups = kPoaThreads / kPoaGroup;
-	uint32_t blocks = (b->njobs + groups - 1) / groups;
-	blocks = std::min<uint32_t>(blocks, (uint32_t)ctx->num_sms * 16);
-	poa_sweep_kernel<<<blocks, kPoaThreads, smem, st>>>(a);
+	if(ngen){
+		const uint32_t groups = kPoaThreads / kPoaGroup;
+		uint32_t blocks = (ngen + groups - 1) / groups;
+		blocks = std::min<uint32_t>(blocks, (uint32_t)ctx->num_sms * 16);
+		a.njobs = ngen;
+		poa_sweep_kernel<<<blocks, kPoaThreads, smem, st>>>(a);
+		launches++;
+	}
+	{
+		size_t at = 0;
+		for(int pw=1;pw<=2;pw++){
+			const uint32_t nf = (uint32_t)b->order_fast[pw].size();
+			if(!nf) continue;
+			PoaFastArgs fa;
+			fa.base = a; fa.base.njobs = nf; fa.base.order = b->d_order_fast.as<uint32_t>() + at;
+			fa.base.counter = b->d_counter2.as<unsigned int>() + (pw - 1);
+			fa.qsel = b->d_qsel.as<uint32_t>(); fa.qsel_off = b->d_qsel_off.as<uint64_t>(); fa.all_ones = 0xffffffffu;
+			const uint32_t blocks = std::min<uint32_t>(nf, (uint32_t)ctx->num_sms * 32);   // one job per warp, up to 32 resident warps per SM
+			const size_t fsm = 384 + 80 + 32 + 128 + 64;
+			if(pw == 1) poa_sweep_fast_kernel<1><<<blocks, 32, fsm, st>>>(fa);
+			else poa_sweep_fast_kernel<2><<<blocks, 32, fsm, st>>>(fa);
+			launches++;
+			at += nf;
+		}
+	}
 	cudaEventRecord(ctx->ev[4], st);
 	CK(cudaGetLastError());
 	CK(cudaStreamSynchronize(st));
@@ -143,7 +212,7 @@ extern "C" int bsb200_poa_run(bsb200_ctx *ctx, bsb200_poa_batch *b){
 	cudaEventElapsedTime(&prep, ctx->ev[2], ctx->ev[3]);
 	cudaEventElapsedTime(&sweep, ctx->ev[3], ctx->ev[4]);
 	ctx->timing.forward_ms = sweep; ctx->timing.traceback_ms = 0; ctx->timing.run_ms = prep + sweep; ctx->timing.total_ms = prep + sweep;
-	ctx->timing.forward_launches = 1; ctx->timing.other_launches = 1; ctx->timing.traceback_launches = 0; ctx->timing.waves = 1;
+	ctx->timing.forward_launches = launches; ctx->timing.other_launches = (ngen ? 1 : 0) + (nfast ? 1 : 0); ctx->timing.traceback_launches = 0; ctx->timing.waves = 1;
 	b->ran = true;
 	return 0;
 }

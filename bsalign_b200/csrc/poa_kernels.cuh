@@ -53,9 +53,10 @@ struct PoaArgs {
 };
 
 // one block per job: query codes + traversal scratch
-__global__ void poa_prep_kernel(uint32_t njobs, const uint8_t *queries, const uint64_t *qoff, const uint32_t *slen, uint8_t *qcode,
+__global__ void poa_prep_kernel(uint32_t njobs, const uint32_t *order, const uint8_t *queries, const uint64_t *qoff, const uint32_t *slen, uint8_t *qcode,
 		const uint64_t *node_off, int32_t *mpos, uint32_t *vst){
-	for(uint32_t job=blockIdx.x;job<njobs;job+=gridDim.x){
+	for(uint32_t k=blockIdx.x;k<njobs;k+=gridDim.x){
+		const uint32_t job = order[k];
 		const uint64_t qo = qoff[job]; const uint32_t n = slen[job];
 		for(uint32_t x=threadIdx.x;x<n;x+=blockDim.x){
 			uint32_t b = queries[qo + x];
@@ -63,7 +64,7 @@ __global__ void poa_prep_kernel(uint32_t njobs, const uint8_t *queries, const ui
 			qcode[qo + x] = (uint8_t)((b & 3u) | f);
 		}
 		const uint64_t n0 = node_off[job], n1 = node_off[job + 1];
-		for(uint64_t k=n0+threadIdx.x;k<n1;k+=blockDim.x){ mpos[k] = kPoaMposInit; vst[k] = 0; }
+		for(uint64_t i=n0+threadIdx.x;i<n1;i+=blockDim.x){ mpos[i] = kPoaMposInit; vst[i] = 0; }
 	}
 }
 
@@ -104,7 +105,6 @@ __global__ void __launch_bounds__(kPoaThreads) poa_sweep_kernel(const PoaArgs a)
 		const uint32_t slen = a.slen[job];
 		const uint8_t *qc = a.qcode + a.qoff[job];
 		const uint64_t n0 = a.node_off[job];
-		const uint32_t nnode = (uint32_t)(a.node_off[job + 1] - n0);
 		const int2 *node = a.node + n0;
 		const int32_t *eoff = a.eoff + n0 + job;
 		const int32_t *edst = a.edst + a.edge_off[job];
