@@ -19,6 +19,8 @@
 #include <cstring>
 #include <numeric>
 #include <string>
+#include <thread>
+#include <atomic>
 #include <vector>
 
 using namespace bsb200;
@@ -72,6 +74,8 @@ struct bsb200_ctx {
 	// allocations cost more than the kernels of a small batch)
 	DevBuf dev_cache[17];
 	HostBuf host_cache[8];
+	DevBuf poa_cache[26];   // same, for POA sweep batches (poa_host.cuh)
+	HostBuf poa_hcache[2];
 };
 
 struct Wave { uint32_t beg, end; uint64_t trace_bytes; };
@@ -138,6 +142,8 @@ extern "C" void bsb200_destroy(bsb200_ctx *ctx){
 	ctx->trace.release(); ctx->trace2.release(); ctx->counter.release();
 	for(auto &d : ctx->dev_cache) d.release();
 	for(auto &h : ctx->host_cache) h.release();
+	for(auto &d : ctx->poa_cache) d.release();
+	for(auto &h : ctx->poa_hcache) h.release();
 	for(auto &e : ctx->ev) cudaEventDestroy(e);
 	cudaStreamDestroy(ctx->stream);
 	cudaStreamDestroy(ctx->stream_bt);

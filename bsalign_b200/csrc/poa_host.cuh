@@ -15,6 +15,7 @@ struct bsb200_poa_batch {
 	std::vector<uint64_t> qsel_off;
 	uint64_t qsel_bytes = 0;
 	DevBuf d_order_fast, d_qsel, d_qsel_off, d_counter2;
+	HostBuf h_nodes;
 	DevBuf d_par, d_queries, d_qcode, d_qoff, d_slen, d_node_off, d_node, d_eoff, d_edge_off, d_edst, d_head, d_tail,
 		d_mpos, d_vst, d_stack, d_rows, d_row_off, d_best, d_status, d_ops, d_order, d_counter;
 	bool ran = false;
@@ -34,7 +35,14 @@ extern "C" void bsb200_poa_free(bsb200_ctx *ctx, bsb200_poa_batch *b){
 	DevBuf *ds[] = {&b->d_par, &b->d_queries, &b->d_qcode, &b->d_qoff, &b->d_slen, &b->d_node_off, &b->d_node, &b->d_eoff, &b->d_edge_off, &b->d_edst,
 		&b->d_head, &b->d_tail, &b->d_mpos, &b->d_vst, &b->d_stack, &b->d_rows, &b->d_row_off, &b->d_best, &b->d_status, &b->d_ops, &b->d_order, &b->d_counter,
 		&b->d_order_fast, &b->d_qsel, &b->d_qsel_off, &b->d_counter2};
-	for(auto d : ds) d->release();
+	if(ctx){   // park the allocations for the next batch (cudaMalloc / cudaFree of a multi-GB row arena cost more than the sweep)
+		cudaStreamSynchronize(ctx->stream);
+		for(int k=0;k<26;k++){ if(ctx->poa_cache[k].cap < ds[k]->cap){ ctx->poa_cache[k].release(); ctx->poa_cache[k] = *ds[k]; } else ds[k]->release(); }
+		if(ctx->poa_hcache[0].cap < b->h_nodes.cap){ ctx->poa_hcache[0].release(); ctx->poa_hcache[0] = b->h_nodes; } else b->h_nodes.release();
+	} else {
+		for(auto d : ds) d->release();
+		b->h_nodes.release();
+	}
 	delete b;
 }
 
@@ -49,6 +57,13 @@ extern "C" bsb200_poa_batch *bsb200_poa_upload(bsb200_ctx *ctx, uint32_t njobs, 
 	}
 	cudaSetDevice(ctx->device);
 	bsb200_poa_batch *b = new bsb200_poa_batch();
+	{
+		DevBuf *ds[] = {&b->d_par, &b->d_queries, &b->d_qcode, &b->d_qoff, &b->d_slen, &b->d_node_off, &b->d_node, &b->d_eoff, &b->d_edge_off, &b->d_edst,
+			&b->d_head, &b->d_tail, &b->d_mpos, &b->d_vst, &b->d_stack, &b->d_rows, &b->d_row_off, &b->d_best, &b->d_status, &b->d_ops, &b->d_order, &b->d_counter,
+			&b->d_order_fast, &b->d_qsel, &b->d_qsel_off, &b->d_counter2};
+		for(int k=0;k<26;k++){ *ds[k] = ctx->poa_cache[k]; ctx->poa_cache[k] = DevBuf(); }
+		b->h_nodes = ctx->poa_hcache[0]; ctx->poa_hcache[0] = HostBuf();
+	}
 	b->njobs = njobs;
 	b->row_off.assign((size_t)njobs + 1, 0);
 	b->nnodes = njobs ? node_off[njobs] : 0;
@@ -68,30 +83,44 @@ extern "C" bsb200_poa_batch *bsb200_poa_upload(bsb200_ctx *ctx, uint32_t njobs, 
 	}
 	b->row_bytes = b->row_off[njobs];
 	std::sort(kv.begin(), kv.end());
-	// node records: rpos, nct | base << 16 | bonus << 24
-	std::vector<int2> nodes(b->nnodes);
-	for(uint64_t k=0;k<b->nnodes;k++){
-		nodes[k].x = node_rpos[k];
-		nodes[k].y = (int)(((uint32_t)node_nct[k] & 0xffffu) | ((uint32_t)node_base[k] << 16) | (((uint32_t)node_bonus[k] & 1u) << 24));
-	}
-	// jobs the register-resident kernel takes (poa_fast.cuh): band of exactly 128 cells that never runs past the read end, gap costs <= 0
-	// with a gap-open cost, small scores; everything else goes to the generic kernel
+	// node records (rpos, nct | base << 16 | bonus << 24) into pinned staging, and which jobs the register-resident kernel takes
+	// (poa_fast.cuh): band of exactly 128 cells that never runs past the read end, gap costs <= 0 with a gap-open cost, small scores;
+	// everything else goes to the generic kernel.  Jobs are independent: a few host threads share them.
+	if(b->h_nodes.reserve(b->nnodes * 8 + 16) != cudaSuccess){ fail(ctx, "pinned allocation (poa)", cudaErrorMemoryAllocation); bsb200_poa_free(ctx, b); return nullptr; }
+	int2 *nodes = b->h_nodes.as<int2>();
 	b->qsel_off.assign((size_t)njobs + 1, 0);
 	std::vector<uint8_t> fast_pw(njobs, 0);
-	for(uint32_t i=0;i<njobs;i++){
-		const int32_t *p = par + (size_t)i * 10;
-		const int O = p[4], E = p[5], Q = p[6], P = p[7];
-		const int pw = epi8_piecewise((int8_t)O, (int8_t)E, (int8_t)Q, (int8_t)P, p[0]);
-		bool ok = p[0] == kPoaFastBw && slen[i] >= (uint32_t)kPoaFastBw && pw >= 1 && O >= -64 && O <= 0 && E >= -64 && E <= 0 && O + E <= 0 &&
-			p[2] + p[9] + 1 <= 62 && p[2] >= -62 && p[3] >= -62 && p[3] <= 62 && p[9] >= 0;
-		if(pw == 2) ok = ok && Q >= -64 && Q <= 0 && P >= -64 && P <= 0;
-		for(uint64_t k=node_off[i];ok&&k<node_off[i+1];k++){
-			if(node_rpos[k] < 0 || (uint64_t)node_rpos[k] + kPoaFastBw > slen[i]) ok = false;
-			if(k - node_off[i] != tail[i] && k - node_off[i] != head[i] && node_base[k] > 3) ok = false;
-		}
-		if(ok){ fast_pw[i] = (uint8_t)pw; b->qsel_off[i + 1] = b->qsel_off[i] + ((uint64_t)slen[i] + 16 + 15) / 16 * 16; }
-		else b->qsel_off[i + 1] = b->qsel_off[i];
+	{
+		std::atomic<uint32_t> next(0);
+		auto work = [&](){
+			while(true){
+				const uint32_t i = next.fetch_add(1);
+				if(i >= njobs) break;
+				const int32_t *p = par + (size_t)i * 10;
+				const int O = p[4], E = p[5], Q = p[6], P = p[7];
+				const int pw = epi8_piecewise((int8_t)O, (int8_t)E, (int8_t)Q, (int8_t)P, p[0]);
+				bool ok = p[0] == kPoaFastBw && slen[i] >= (uint32_t)kPoaFastBw && pw >= 1 && O >= -64 && O <= 0 && E >= -64 && E <= 0 && O + E <= 0 &&
+					p[2] + p[9] + 1 <= 62 && p[2] >= -62 && p[3] >= -62 && p[3] <= 62 && p[9] >= 0;
+				if(pw == 2) ok = ok && Q >= -64 && Q <= 0 && P >= -64 && P <= 0;
+				const uint64_t k0 = node_off[i], k1 = node_off[i + 1];
+				const int64_t lim = (int64_t)slen[i] - kPoaFastBw;
+				bool in_band = true, bases = true;
+				for(uint64_t k=k0;k<k1;k++){
+					nodes[k].x = node_rpos[k];
+					nodes[k].y = (int)(((uint32_t)node_nct[k] & 0xffffu) | ((uint32_t)node_base[k] << 16) | (((uint32_t)node_bonus[k] & 1u) << 24));
+					in_band &= (node_rpos[k] >= 0) & ((int64_t)node_rpos[k] <= lim);
+					bases &= (node_base[k] <= 3) | (k - k0 == tail[i]) | (k - k0 == head[i]);
+				}
+				if(ok && in_band && bases) fast_pw[i] = (uint8_t)pw;
+			}
+		};
+		const uint32_t nth = std::max(1u, std::min(16u, std::min(njobs, std::thread::hardware_concurrency())));
+		std::vector<std::thread> th;
+		for(uint32_t k=1;k<nth;k++) th.emplace_back(work);
+		work();
+		for(auto &x : th) x.join();
 	}
+	for(uint32_t i=0;i<njobs;i++) b->qsel_off[i + 1] = b->qsel_off[i] + (fast_pw[i] ? ((uint64_t)slen[i] + 16 + 15) / 16 * 16 : 0);
 	b->qsel_bytes = b->qsel_off[njobs];
 	for(uint32_t i=0;i<njobs;i++){
 		const uint32_t jb = kv[i].second;
@@ -118,7 +147,7 @@ extern "C" bsb200_poa_batch *bsb200_poa_upload(bsb200_ctx *ctx, uint32_t njobs, 
 		R(cudaMemcpyAsync(b->d_qoff.p, qoff, nj * 8, cudaMemcpyHostToDevice, st));
 		R(cudaMemcpyAsync(b->d_slen.p, slen, nj * 4, cudaMemcpyHostToDevice, st));
 		R(cudaMemcpyAsync(b->d_node_off.p, node_off, (nj + 1) * 8, cudaMemcpyHostToDevice, st));
-		R(cudaMemcpyAsync(b->d_node.p, nodes.data(), nn * 8, cudaMemcpyHostToDevice, st));
+		R(cudaMemcpyAsync(b->d_node.p, nodes, nn * 8, cudaMemcpyHostToDevice, st));
 		R(cudaMemcpyAsync(b->d_eoff.p, eoff, (nn + nj) * 4, cudaMemcpyHostToDevice, st));
 		R(cudaMemcpyAsync(b->d_edge_off.p, edge_off, (nj + 1) * 8, cudaMemcpyHostToDevice, st));
 		if(ne) R(cudaMemcpyAsync(b->d_edst.p, edst, ne * 4, cudaMemcpyHostToDevice, st));

@@ -1,0 +1,228 @@
+/*
+ * bsalign_b200_poa_compat.h -- GNU-C drop-in for the read-vs-graph DP sweep of ruanjue/bsalign's BSPOA, re-bodied on top of
+ * libbsalign_b200.so (C ABI: bsalign_b200.h, bsb200_poa_*).  Include it AFTER the reference's own bspoa.h.
+ *
+ *   b200_align_rd_bspoacore(ctx, g, par, rid, nhead, ntail)
+ *       same contract as align_rd_bspoacore (bspoa.h:2515-2618) for ONE BSPOA: after it returns, every selected node's row
+ *       block sits in g->memp (dpalign_row_prepare_data, bspoa.h:1787-1793) and g->maxscr / g->maxidx / g->maxoff are set,
+ *       so alignment2graph_bspoa (bspoa.h:2274) runs unchanged.  One job per call pays a PCIe round trip.
+ *
+ *   b200_end_bspoa_batch(ctx, gs, n)
+ *       end_bspoa (bspoa.h:4722-4778) for n BSPOA objects stepped in LOCK-STEP: in round r every object prepares the alignment of
+ *       its read r on the host exactly as the reference does (msa_bspoa, simple_cns_bspoa, sel_nodes_bspoa,
+ *       prepare_rd_align_bspoa), the n sweeps run as ONE GPU batch, and every object then continues with the reference's
+ *       alignment2graph_bspoa.  Everything that is not the sweep is the reference's own code, called in the reference's order.
+ *
+ * -DBSALIGN_B200_OVERRIDE routes the reference name end_bspoa to the batch driver with n = 1.
+ * Programmer errors keep the reference's behaviour: message on stderr + abort().  There is no CPU fallback.
+ */
+#ifndef BSALIGN_B200_POA_COMPAT_H
+#define BSALIGN_B200_POA_COMPAT_H
+
+#include "bsalign_b200.h"
+
+#ifndef BANDED_STRIPED_SIMD_RECURRENT_ALIGNMENT_GRAPH_MSA_CNS_RJ_H
+#error "include the reference's bspoa.h before bsalign_b200_poa_compat.h"
+#endif
+
+/* packed arenas of a batch of sweep jobs: the argument layout of bsb200_poa_rows_batch */
+typedef struct {
+	uint32_t njobs, cap_jobs;
+	int32_t *par; uint64_t *qoff; uint32_t *slen; uint64_t *node_off, *edge_off; uint32_t *head, *tail;
+	uint8_t *queries; uint64_t nq, cap_q;
+	uint8_t *base, *bonus; int32_t *rpos, *nct; uint64_t nnode, cap_node;
+	int32_t *eoff; uint64_t neoff, cap_eoff;
+	int32_t *edst; uint64_t nedge, cap_edge;
+	uint32_t *loc; uint64_t cap_loc;          /* global node id -> local id scratch */
+	uint8_t *rows; uint64_t cap_rows; uint64_t *row_off;
+	int32_t *best, *status;
+} b200_poa_pack_t;
+
+#define B200_GROW(ptr, cap, need, type) do { if((uint64_t)(need) > (cap)){ (cap) = (uint64_t)(need) * 3 / 2 + 64; (ptr) = (type*)realloc((ptr), (cap) * sizeof(type)); \
+	if((ptr) == NULL){ fflush(stdout); fprintf(stderr, " -- Out of memory in %s -- %s:%d --\n", __FUNCTION__, __FILE__, __LINE__); fflush(stderr); abort(); } } } while(0)
+
+static inline b200_poa_pack_t* b200_poa_pack_init(void){ return (b200_poa_pack_t*)calloc(1, sizeof(b200_poa_pack_t)); }
+static inline void b200_poa_pack_clear(b200_poa_pack_t *p){ p->njobs = 0; p->nq = 0; p->nnode = 0; p->neoff = 0; p->nedge = 0; }
+static inline void b200_poa_pack_free(b200_poa_pack_t *p){
+	free(p->par); free(p->qoff); free(p->slen); free(p->node_off); free(p->edge_off); free(p->head); free(p->tail); free(p->queries);
+	free(p->base); free(p->bonus); free(p->rpos); free(p->nct); free(p->eoff); free(p->edst); free(p->loc); free(p->rows); free(p->row_off);
+	free(p->best); free(p->status); free(p);
+}
+
+/* append the sweep job of g (after prepare_rd_align_bspoa) to the pack: what align_rd_bspoacore would consume */
+static inline void b200_poa_pack_job(b200_poa_pack_t *p, BSPOA *g, BSPOAPar *par, u4i nhead, u4i ntail){
+	u4i i, nloc = g->sels->size, eidx, j = p->njobs;
+	uint64_t dummy_cap;
+	if(j + 2 > p->cap_jobs){
+		uint32_t nc = (j + 2) * 2 + 14;
+		p->par = (int32_t*)realloc(p->par, sizeof(int32_t) * 10 * nc); p->qoff = (uint64_t*)realloc(p->qoff, 8 * (size_t)nc); p->slen = (uint32_t*)realloc(p->slen, 4 * (size_t)nc);
+		p->node_off = (uint64_t*)realloc(p->node_off, 8 * (size_t)nc); p->edge_off = (uint64_t*)realloc(p->edge_off, 8 * (size_t)nc);
+		p->head = (uint32_t*)realloc(p->head, 4 * (size_t)nc); p->tail = (uint32_t*)realloc(p->tail, 4 * (size_t)nc);
+		p->row_off = (uint64_t*)realloc(p->row_off, 8 * (size_t)nc); p->best = (int32_t*)realloc(p->best, 12 * (size_t)nc); p->status = (int32_t*)realloc(p->status, 4 * (size_t)nc);
+		p->cap_jobs = nc;
+	}
+	B200_GROW(p->loc, p->cap_loc, g->nodes->size + 1, uint32_t);
+	for(i=0;i<nloc;i++) p->loc[g->sels->buffer[i]] = i;
+	{
+		int32_t *q = p->par + 10 * (size_t)j;
+		q[0] = g->bandwidth; q[1] = par->alnmode; q[2] = par->M; q[3] = par->X; q[4] = par->O; q[5] = par->E; q[6] = par->Q; q[7] = par->P; q[8] = par->T; q[9] = par->refbonus;
+	}
+	p->qoff[j] = p->nq; p->slen[j] = g->slen;
+	B200_GROW(p->queries, p->cap_q, p->nq + g->slen + 16, uint8_t);
+	memcpy(p->queries + p->nq, g->qseq->buffer + g->qb, g->slen); p->nq += g->slen;
+	p->node_off[j] = p->nnode; p->edge_off[j] = p->nedge;
+	dummy_cap = p->cap_node; B200_GROW(p->base, dummy_cap, p->nnode + nloc, uint8_t);
+	dummy_cap = p->cap_node; B200_GROW(p->bonus, dummy_cap, p->nnode + nloc, uint8_t);
+	dummy_cap = p->cap_node; B200_GROW(p->rpos, dummy_cap, p->nnode + nloc, int32_t);
+	B200_GROW(p->nct, p->cap_node, p->nnode + nloc, int32_t);
+	B200_GROW(p->eoff, p->cap_eoff, p->neoff + nloc + 1, int32_t);
+	{
+		int32_t *eo = p->eoff + p->neoff;
+		uint64_t ne = 0;
+		for(i=0;i<nloc;i++){
+			bspoanode_t *u = ref_bspoanodev(g->nodes, g->sels->buffer[i]);
+			uint64_t k = p->nnode + i;
+			p->base[k] = u->base; p->bonus[k] = u->bonus; p->rpos[k] = u->rpos; p->nct[k] = u->nct;
+			eo[i] = (int32_t)ne;
+			for(eidx=u->edge;eidx;eidx=ref_bspoaedgev(g->edges, eidx)->next){   /* the edge-list order of bspoa.h:2533-2538 */
+				bspoaedge_t *e = ref_bspoaedgev(g->edges, eidx);
+				if(get_bitvec(g->states, e->node) == 0) continue;
+				B200_GROW(p->edst, p->cap_edge, p->nedge + ne + 1, int32_t);
+				p->edst[p->nedge + ne] = (int32_t)p->loc[e->node];
+				ne ++;
+			}
+		}
+		eo[nloc] = (int32_t)ne;
+		p->nedge += ne;
+	}
+	p->neoff += nloc + 1; p->nnode += nloc;
+	p->head[j] = p->loc[nhead]; p->tail[j] = p->loc[ntail];
+	p->njobs = j + 1;
+	p->node_off[j + 1] = p->nnode; p->edge_off[j + 1] = p->nedge;
+}
+
+/* run every packed sweep on the GPU (one batch) */
+static inline void b200_poa_pack_run(bsb200_ctx *ctx, b200_poa_pack_t *p){
+	uint32_t j;
+	uint64_t tot = 0;
+	if(p->njobs == 0) return;
+	for(j=0;j<p->njobs;j++){ p->row_off[j] = tot; tot += (p->node_off[j + 1] - p->node_off[j]) * (uint64_t)bsb200_poa_block_bytes(p->par + 10 * (size_t)j); }
+	p->row_off[p->njobs] = tot;
+	B200_GROW(p->rows, p->cap_rows, tot + 16, uint8_t);
+	if(bsb200_poa_rows_batch(ctx, p->njobs, p->par, p->queries, p->qoff, p->slen, p->node_off, p->base, p->bonus, p->rpos, p->nct, p->eoff, p->edge_off, p->edst,
+			p->head, p->tail, p->rows, p->best, p->status, NULL)){
+		fflush(stdout); fprintf(stderr, " -- bsalign_b200: %s in %s -- %s:%d --\n", bsb200_last_error(ctx), __FUNCTION__, __FILE__, __LINE__); fflush(stderr);
+		abort();
+	}
+}
+
+/* hand job j's results to its BSPOA: row blocks into g->memp from block 2 on (bspoa.h:2218-2223), best end into g->max* */
+static inline int b200_poa_pack_take(b200_poa_pack_t *p, uint32_t j, BSPOA *g){
+	uint64_t bytes = p->row_off[j + 1] - p->row_off[j];
+	memcpy(g->memp->buffer + 2 * g->mmblk, p->rows + p->row_off[j], bytes);
+	g->maxscr = p->best[3 * (size_t)j];
+	g->maxidx = p->best[3 * (size_t)j + 1] >= 0 ? (int)g->sels->buffer[p->best[3 * (size_t)j + 1]] : -1;
+	g->maxoff = p->best[3 * (size_t)j + 2];
+	return g->maxscr;
+}
+
+static inline int b200_align_rd_bspoacore(bsb200_ctx *ctx, BSPOA *g, BSPOAPar *par, u2i rid, u4i nhead, u4i ntail){
+	b200_poa_pack_t *p;
+	int scr;
+	UNUSED(rid);
+	if(g->sels->size == 0) return align_rd_bspoacore(g, par, rid, nhead, ntail);   /* nothing selected: no DP rows at all */
+	p = b200_poa_pack_init();
+	b200_poa_pack_job(p, g, par, nhead, ntail);
+	b200_poa_pack_run(ctx, p);
+	scr = b200_poa_pack_take(p, 0, g);
+	b200_poa_pack_free(p);
+	return scr;
+}
+
+/* end_bspoa (bspoa.h:4722-4778) for n objects in lock-step; the read-vs-graph sweeps of one round are one GPU batch */
+static inline void b200_end_bspoa_batch(bsb200_ctx *ctx, BSPOA **gs, u4i n){
+	b200_poa_pack_t *p = b200_poa_pack_init();
+	u4i k, maxr = 0, *nheads, *ntails, *slot;
+	u2i rid;
+	int i;
+	nheads = (u4i*)malloc(sizeof(u4i) * (n + 1)); ntails = (u4i*)malloc(sizeof(u4i) * (n + 1)); slot = (u4i*)malloc(sizeof(u4i) * (n + 1));
+	for(k=0;k<n;k++){   /* bspoa.h:4726-4751 */
+		BSPOA *g = gs[k];
+		clear_u1v(g->cns); clear_u1v(g->qlt); clear_u1v(g->alt);
+		if(g->par->refmode){
+			resize_u1v(g->cns, g->seqs->rdlens->buffer[0]); resize_u1v(g->qlt, g->seqs->rdlens->buffer[0]); resize_u1v(g->alt, g->seqs->rdlens->buffer[0]);
+			bitseq_basebank(g->seqs->rdseqs, g->seqs->rdoffs->buffer[0], g->seqs->rdlens->buffer[0], g->cns->buffer);
+			memset(g->qlt->buffer, 0, g->seqs->rdlens->buffer[0]); memset(g->alt->buffer, 0, g->seqs->rdlens->buffer[0]);
+		}
+		if(g->seqs->nseq <= 1){ g->nmsa = 0; continue; }
+		if(g->par->shuffle) shuffle_reads_by_kmers_bspoa(g);
+		g->nmsa = g->par->seqcore? num_min(g->seqs->nseq, g->par->seqcore) : g->seqs->nseq;
+		for(rid=0;rid<g->seqs->nseq;rid++) _add_read_bspoa_core(g, rid);
+		g->nrds = 1;
+		if(g->nmsa > maxr) maxr = g->nmsa;
+	}
+	for(rid=1;rid<maxr;rid++){   /* bspoa.h:4752-4763 with align_rd_bspoa (bspoa.h:2620-2667) split around the sweep */
+		b200_poa_pack_clear(p);
+		for(k=0;k<n;k++){
+			BSPOA *g = gs[k];
+			u4i rlen; u2i ridxbeg, ridxend;
+			slot[k] = MAX_U4;
+			if(g->seqs->nseq <= 1 || rid >= g->nmsa) continue;
+			if(!g->par->refmode && g->par->bwtrigger){ msa_bspoa(g); simple_cns_bspoa(g); }
+			rlen = g->seqs->rdlens->buffer[rid];
+			clear_u8v(g->todels);
+			if(rlen == 0){ g->nrds ++; continue; }
+			nheads[k] = get_rdnode_bspoa(g, rid, -1)->header;
+			ntails[k] = get_rdnode_bspoa(g, rid, rlen)->header;
+			if(g->par->nrec){ ridxbeg = num_max(0, Int(rid) - g->par->nrec - 1); ridxend = rid; } else { ridxbeg = 0; ridxend = MAX_U2; }
+			sel_nodes_bspoa(g, nheads[k], ntails[k], ridxbeg, ridxend);
+			prepare_rd_align_bspoa(g, g->par, nheads[k], ntails[k], rid, 0, rlen);
+			if(g->sels->size == 0){ align_rd_bspoacore(g, g->par, rid, nheads[k], ntails[k]); slot[k] = MAX_U4 - 1; continue; }
+			slot[k] = p->njobs;
+			b200_poa_pack_job(p, g, g->par, nheads[k], ntails[k]);
+		}
+		b200_poa_pack_run(ctx, p);
+		for(k=0;k<n;k++){
+			BSPOA *g = gs[k];
+			u4i t;
+			if(slot[k] == MAX_U4) continue;
+			if(slot[k] != MAX_U4 - 1) b200_poa_pack_take(p, slot[k], g);
+			alignment2graph_bspoa(g, g->par, rid, 0, nheads[k], ntails[k], g->maxidx, g->maxoff, NULL);
+			for(t=0;t<g->todels->size;t++){
+				chg_edge_bspoa(g, ref_bspoanodev(g->nodes, g->todels->buffer[t] >> 32), ref_bspoanodev(g->nodes, g->todels->buffer[t] & MAX_U4), -1, NULL);
+			}
+			clear_u8v(g->todels);
+			g->nrds ++;
+		}
+	}
+	for(k=0;k<n;k++){   /* bspoa.h:4764-4777: the reference's own code, unchanged */
+		BSPOA *g = gs[k];
+		if(g->seqs->nseq <= 1) continue;
+		for(i=0;i<g->par->realn;i++){
+			msa_bspoa(g);
+			cns_bspoa(g);
+			if(g->par->editbw < 0) remsa_edits_bspoa(g, - g->par->editbw);
+			else remsa_pedits_bspoa(g, g->par->editbw / 2, 1, (i + 1 == g->par->realn));
+		}
+		if(g->par->shuffle) restore_rd_orders_bspoa(g);
+		msa_bspoa(g);
+		cns_bspoa(g);
+	}
+	free(nheads); free(ntails); free(slot);
+	b200_poa_pack_free(p);
+}
+
+#ifdef BSALIGN_B200_OVERRIDE
+static bsb200_ctx *bsalign_b200_poa_default_ctx(void){
+	static bsb200_ctx *ctx = NULL;
+	if(ctx == NULL){
+		ctx = bsb200_create(0, 0);
+		if(ctx == NULL){ fflush(stdout); fprintf(stderr, " -- bsalign_b200: no CUDA device, and there is no CPU fallback in %s -- %s:%d --\n", __FUNCTION__, __FILE__, __LINE__); fflush(stderr); abort(); }
+	}
+	return ctx;
+}
+static inline void b200_end_bspoa(BSPOA *g){ b200_end_bspoa_batch(bsalign_b200_poa_default_ctx(), &g, 1); }
+#define end_bspoa b200_end_bspoa
+#endif
+
+#endif

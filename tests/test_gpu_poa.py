@@ -105,3 +105,18 @@ def test_poa_empty_batch_and_trivial_graph(ctx):
     res = poa.poa_rows_batch(ctx, poa.SweepBatch([j.to_api() for j in jobs]))
     for k, j in enumerate(jobs):
         assert (int(res.best[k][0]), int(res.best[k][1]), int(res.best[k][2])) == (j.maxscr, j.maxidx, j.maxoff)
+
+
+def test_poa_dropin_end_bspoa_identical_msa():
+    """include/bsalign_b200_poa_compat.h against the reference's own end_bspoa: whole BSPOA jobs (graph surgery, consensus and re-alignment
+    rounds are the reference's code; every read-vs-graph sweep runs on the GPU, all objects in lock-step) must give byte-identical
+    consensus + MSA.  The binary is built from the reference headers where they exist (oracle/Makefile, target dropin) and travels."""
+    import os
+    import subprocess
+    exe = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "oracle", "_ref", "poa_dropin")
+    if not os.path.exists(exe):
+        pytest.skip("oracle/_ref/poa_dropin was not built (no reference tree at build time)")
+    for args in (["6", "12", "1500", "3"], ["3", "24", "4000", "5", "0"]):
+        out = subprocess.run([exe] + args, capture_output=True, text=True, timeout=600)
+        assert out.returncode == 0, out.stdout + out.stderr
+        assert "identical=%s/%s" % (args[0], args[0]) in out.stdout, out.stdout
