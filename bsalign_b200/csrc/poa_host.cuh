@@ -226,10 +226,18 @@ extern "C" int bsb200_poa_run(bsb200_ctx *ctx, bsb200_poa_batch *b){
 			fa.base = a; fa.base.njobs = nf; fa.base.order = b->d_order_fast.as<uint32_t>() + at;
 			fa.base.counter = b->d_counter2.as<unsigned int>() + (pw - 1);
 			fa.qsel = b->d_qsel.as<uint32_t>(); fa.qsel_off = b->d_qsel_off.as<uint64_t>(); fa.all_ones = 0xffffffffu;
-			const uint32_t blocks = std::min<uint32_t>(nf, (uint32_t)ctx->num_sms * 32);   // one job per warp, up to 32 resident warps per SM
-			const size_t fsm = 384 + 80 + 32 + 128 + 64;
-			if(pw == 1) poa_sweep_fast_kernel<1><<<blocks, 32, fsm, st>>>(fa);
-			else poa_sweep_fast_kernel<2><<<blocks, 32, fsm, st>>>(fa);
+			// jobs per warp: one while every job can have a resident warp of its own (the sweep is a latency-bound chain), four when
+			// the batch is large enough to be issue bound (BSB200_POA_GPW overrides, for experiments)
+			int gpw = nf > (uint32_t)ctx->num_sms * 12 ? 4 : 1;
+			if(const char *ev = getenv("BSB200_POA_GPW")){ int g = atoi(ev); if(g == 1 || g == 2 || g == 4) gpw = g; }
+			const uint32_t blocks = std::min<uint32_t>((nf + gpw - 1) / gpw, (uint32_t)ctx->num_sms * 32);
+			const size_t fsm = (size_t)kPoaFastSmem * gpw;
+			#define POA_FAST_LAUNCH(PWV) do { \
+				if(gpw == 4) poa_sweep_fast_kernel<PWV, 4><<<blocks, 32, fsm, st>>>(fa); \
+				else if(gpw == 2) poa_sweep_fast_kernel<PWV, 2><<<blocks, 32, fsm, st>>>(fa); \
+				else poa_sweep_fast_kernel<PWV, 1><<<blocks, 32, fsm, st>>>(fa); } while(0)
+			if(pw == 1) POA_FAST_LAUNCH(1); else POA_FAST_LAUNCH(2);
+			#undef POA_FAST_LAUNCH
 			launches++;
 			at += nf;
 		}
