@@ -59,6 +59,7 @@ template<int K> __device__ __forceinline__ uint32_t ent(const uint4 &c){
 	const uint32_t w = (K >> 1) == 0 ? c.x : (K >> 1) == 1 ? c.y : (K >> 1) == 2 ? c.z : c.w;
 	return prmt(w, 0u, (K & 1) ? 0xB3A2u : 0x9180u);
 }
+// (w >> 16 as IMAD.HI on the FMA pipe instead of SHF was measured slower: 93.9 vs 90.8 ms on config 2)
 template<int K> __device__ __forceinline__ uint32_t ent_sel(const uint4 &c){
 	const uint32_t w = (K >> 1) == 0 ? c.x : (K >> 1) == 1 ? c.y : (K >> 1) == 2 ? c.z : c.w;
 	return (K & 1) ? (w >> 16) : w;   // PRMT reads only bits 15:0 of its selector
@@ -89,14 +90,14 @@ __device__ __forceinline__ uint32_t not_fma(uint32_t x, uint32_t m1){ return x *
 // are dropped: e,q <= 0 so e+u never exceeds 127; x-h <= 0 because h >= e+u and ge <= 0; h+goe and f+ge cannot exceed 127.
 template<int PW, bool FAST, bool PASS2>
 __device__ __forceinline__ void dp_step(RowState &s, uint32_t u, uint32_t e, uint32_t q, uint32_t z,
-		uint32_t GE, uint32_t GOE, uint32_t GP, uint32_t GQP, uint32_t NGOQ, uint32_t M1, uint32_t &un, uint32_t &en, uint32_t &qn){
+		uint32_t GE, uint32_t GOE, uint32_t GP, uint32_t GQP, uint32_t NGOQ, uint32_t M1, uint32_t Z0, uint32_t &un, uint32_t &en, uint32_t &qn){
 	if(FAST){
 		constexpr uint32_t C129 = 0x00810081u, C255 = 0x00ff00ffu;
 		// u, z, s.f, s.g biased; e, q, s.nv unbiased
-		const uint32_t ev = __viaddmax_s16x2(u, PW == 0 ? GE : e, 0u);         // adds(e,u) + 128   (linear gaps: e = ge)
+		const uint32_t ev = __viaddmax_s16x2(u, PW == 0 ? GE : e, Z0);         // adds(e,u) + 128   (linear gaps: e = ge)
 		uint32_t qv = 0, h;
 		if(PW == 2){
-			qv = __viaddmax_s16x2(u, q, 0u);
+			qv = __viaddmax_s16x2(u, q, Z0);
 			h = smax(smax3(ev, z, qv), smax(s.f, s.g));
 		} else h = smax3(ev, z, s.f);
 		const uint32_t cu = not_fma(u, M1);
@@ -124,7 +125,7 @@ __device__ __forceinline__ void dp_step(RowState &s, uint32_t u, uint32_t e, uin
 			s.f = __viaddmin_s16x2_relu(f1, cu, C255);
 			s.h = y;
 		} else {
-			uint32_t yb = __viaddmax_s16x2(h, GOE, 0u);                            // adds(h, goe) + 128
+			uint32_t yb = __viaddmax_s16x2(h, GOE, Z0);                            // adds(h, goe) + 128
 			uint32_t f1 = __viaddmax_s16x2(s.f, __vadd2(GE, C129), __vadd2(yb, C129));
 			s.f = __viaddmin_s16x2_relu(f1, cu, C255);
 			yb = __viaddmin_s16x2_relu(yb, NGOQ, C255);                             // subs(., goq) + 128
@@ -209,6 +210,7 @@ __global__ void __launch_bounds__(kFwdThreads) epi8_forward_kernel(const Epi8Arg
 	const int GOEi = (int8_t)(go1 + ge1), GQPi = (int8_t)(go2 + ge2);
 	const uint32_t GE = pk1(ge1), GOE = pk1(GOEi), GP = pk1(ge2), GQP = pk1(GQPi);
 	const uint32_t M1 = a.all_ones;
+	const uint32_t Z0 = M1 + 1u;   // 0 as a run-time register value: ptxas otherwise re-materialises the constant with a PRMT per use
 	constexpr int UB = FAST ? 128 : 0;              // bias of the u bytes (and of z, h, f, g in registers)
 	#define UBYTE(raw) (FAST ? (int)(uint8_t)(raw) - 128 : (int)(int8_t)(raw))
 	#define ZSEL(ca, cb) (FAST ? zselb((ca), (cb)) : zsel((ca), (cb)))
@@ -480,7 +482,7 @@ __global__ void __launch_bounds__(kFwdThreads) epi8_forward_kernel(const Epi8Arg
 			#define P1STEP(K, LEFT) { if((K) < (LEFT)){ \
 				uint32_t z = prmt(T32, ZPAD, ent_sel<K>(cs4)); \
 				if((K) == 0 && c == 0) z = (z & zmask) | zor; \
-				dp_step<PW, FAST, false>(st, FAST ? entz<K>(cu4) : ent<K>(cu4), ent<K>(ce4), ent<K>(cq4), z, GE, GOE, GP, GQP, NGOQ, M1, dum0, dum1, dum2); } }
+				dp_step<PW, FAST, false>(st, FAST ? entz<K>(cu4) : ent<K>(cu4), ent<K>(ce4), ent<K>(cq4), z, GE, GOE, GP, GQP, NGOQ, M1, Z0, dum0, dum1, dum2); } }
 			#define P1CHUNK(LEFT) { \
 				const uint4 cu4 = *(const uint4*)(rU + 128 * c), cs4 = *(const uint4*)(rC + 128 * c); \
 				uint4 ce4 = cu4, cq4 = cu4; \
@@ -524,7 +526,7 @@ __global__ void __launch_bounds__(kFwdThreads) epi8_forward_kernel(const Epi8Arg
 			#define P2STEP(K, LEFT) { if((K) < (LEFT)){ \
 				uint32_t z = prmt(T32, ZPAD, ent_sel<K>(cs4)); \
 				if((K) == 0 && c == 0) z = (z & zmask) | zor; \
-				dp_step<PW, FAST, true>(st, FAST ? entz<K>(cu4) : ent<K>(cu4), ent<K>(ce4), ent<K>(cq4), z, GE, GOE, GP, GQP, NGOQ, M1, un[K], en[K], qn[K]); } }
+				dp_step<PW, FAST, true>(st, FAST ? entz<K>(cu4) : ent<K>(cu4), ent<K>(ce4), ent<K>(cq4), z, GE, GOE, GP, GQP, NGOQ, M1, Z0, un[K], en[K], qn[K]); } }
 			#define P2CHUNK(LEFT, RAGGED) { \
 				const uint4 cu4 = *(const uint4*)(rU + 128 * c), cs4 = *(const uint4*)(rC + 128 * c); \
 				uint4 ce4 = cu4, cq4 = cu4; \

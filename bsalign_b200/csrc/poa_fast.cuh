@@ -134,6 +134,7 @@ __global__ void __launch_bounds__(32) poa_sweep_fast_kernel(const PoaFastArgs fa
 	int32_t *sRM = (int32_t*)(sF + 32);
 	int32_t *sD = sRM + 32;                                 // 16 anchor deltas for the exact F scan
 	const uint32_t M1 = fa.all_ones;
+	const uint32_t Z0 = M1 + 1u;                            // 0 as a run-time register value (see dp_step)
 	constexpr uint32_t bw = kPoaFastBw, W = 8;
 	constexpr uint32_t mmblk = (bw * (PW + 1) + 68 + 15) / 16 * 16;
 
@@ -358,14 +359,14 @@ __global__ void __launch_bounds__(32) poa_sweep_fast_kernel(const PoaFastArgs fa
 				const uint32_t w0 = wp[0], w1 = wp[1], w2 = wp[2], w3 = wp[3], w4 = wp[4];
 				const uint32_t s0 = __funnelshift_r(w0, w1, sh), s1 = __funnelshift_r(w1, w2, sh), s2 = __funnelshift_r(w2, w3, sh), s3 = __funnelshift_r(w3, w4, sh);
 				constexpr uint32_t BIAS = 0x00800080u;
-				z0 = __viaddmax_s16x2(prmt(Tlo, Thi, prmt(s0, s2, 0x0040u)), BIAS, 0u);
-				z1 = __viaddmax_s16x2(prmt(Tlo, Thi, prmt(s0, s2, 0x0051u)), BIAS, 0u);
-				z2 = __viaddmax_s16x2(prmt(Tlo, Thi, prmt(s0, s2, 0x0062u)), BIAS, 0u);
-				z3 = __viaddmax_s16x2(prmt(Tlo, Thi, prmt(s0, s2, 0x0073u)), BIAS, 0u);
-				z4 = __viaddmax_s16x2(prmt(Tlo, Thi, prmt(s1, s3, 0x0040u)), BIAS, 0u);
-				z5 = __viaddmax_s16x2(prmt(Tlo, Thi, prmt(s1, s3, 0x0051u)), BIAS, 0u);
-				z6 = __viaddmax_s16x2(prmt(Tlo, Thi, prmt(s1, s3, 0x0062u)), BIAS, 0u);
-				z7 = __viaddmax_s16x2(prmt(Tlo, Thi, prmt(s1, s3, 0x0073u)), BIAS, 0u);
+				z0 = __viaddmax_s16x2(prmt(Tlo, Thi, prmt(s0, s2, 0x0040u)), BIAS, Z0);
+				z1 = __viaddmax_s16x2(prmt(Tlo, Thi, prmt(s0, s2, 0x0051u)), BIAS, Z0);
+				z2 = __viaddmax_s16x2(prmt(Tlo, Thi, prmt(s0, s2, 0x0062u)), BIAS, Z0);
+				z3 = __viaddmax_s16x2(prmt(Tlo, Thi, prmt(s0, s2, 0x0073u)), BIAS, Z0);
+				z4 = __viaddmax_s16x2(prmt(Tlo, Thi, prmt(s1, s3, 0x0040u)), BIAS, Z0);
+				z5 = __viaddmax_s16x2(prmt(Tlo, Thi, prmt(s1, s3, 0x0051u)), BIAS, Z0);
+				z6 = __viaddmax_s16x2(prmt(Tlo, Thi, prmt(s1, s3, 0x0062u)), BIAS, Z0);
+				z7 = __viaddmax_s16x2(prmt(Tlo, Thi, prmt(s1, s3, 0x0073u)), BIAS, Z0);
 			}
 			// ---- the predecessor row shifted to v's band (bsalign.h:2244-2392) ----
 			uint32_t pu0 = Pd.u0, pu1 = Pd.u1, pu2 = Pd.u2, pu3 = Pd.u3;
@@ -455,7 +456,7 @@ __global__ void __launch_bounds__(32) poa_sweep_fast_kernel(const PoaFastArgs fa
 			RowState st; st.f = pk1(kEpi8Min + 128); st.g = pk1(kEpi8Min + 128); st.h = 0; st.u = 0; st.nv = 0;
 			{
 				uint32_t d0, d1, d2;
-				#define P1(K, Z) dp_step<PW, true, false>(st, entz<K>(cu4), ent<K>(ce4), ent<K>(cq4), Z, GE, GOE, GP, GQP, NGOQ, M1, d0, d1, d2);
+				#define P1(K, Z) dp_step<PW, true, false>(st, entz<K>(cu4), ent<K>(ce4), ent<K>(cq4), Z, GE, GOE, GP, GQP, NGOQ, M1, Z0, d0, d1, d2);
 				P1(0, z0) P1(1, z1) P1(2, z2) P1(3, z3) P1(4, z4) P1(5, z5) P1(6, z6) P1(7, z7)
 				#undef P1
 			}
@@ -500,7 +501,7 @@ __global__ void __launch_bounds__(32) poa_sweep_fast_kernel(const PoaFastArgs fa
 			st.nv = 0; st.h = 0; st.u = 0;
 			uint32_t un0, un1, un2, un3, un4, un5, un6, un7, en0 = 0, en1 = 0, en2 = 0, en3 = 0, en4 = 0, en5 = 0, en6 = 0, en7 = 0,
 				qn0 = 0, qn1 = 0, qn2 = 0, qn3 = 0, qn4 = 0, qn5 = 0, qn6 = 0, qn7 = 0;
-			#define P2(K, Z) dp_step<PW, true, true>(st, entz<K>(cu4), ent<K>(ce4), ent<K>(cq4), Z, GE, GOE, GP, GQP, NGOQ, M1, un##K, en##K, qn##K);
+			#define P2(K, Z) dp_step<PW, true, true>(st, entz<K>(cu4), ent<K>(ce4), ent<K>(cq4), Z, GE, GOE, GP, GQP, NGOQ, M1, Z0, un##K, en##K, qn##K);
 			P2(0, z0) P2(1, z1) P2(2, z2) P2(3, z3) P2(4, z4) P2(5, z5) P2(6, z6) P2(7, z7)
 			#undef P2
 			// ---- tail (bsalign.h:2618-2636) ----
