@@ -74,7 +74,7 @@ struct bsb200_ctx {
 	// allocations cost more than the kernels of a small batch)
 	DevBuf dev_cache[17];
 	HostBuf host_cache[8];
-	DevBuf poa_cache[26];   // same, for POA sweep batches (poa_host.cuh)
+	DevBuf poa_cache[40];   // same, for POA sweep batches (poa_host.cuh)
 	HostBuf poa_hcache[2];
 };
 

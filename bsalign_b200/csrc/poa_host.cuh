@@ -4,6 +4,7 @@
 #pragma once
 #include "poa_kernels.cuh"
 #include "poa_fast.cuh"
+#include "poa_backtrace.cuh"
 
 struct bsb200_poa_batch {
 	uint32_t njobs = 0;
@@ -16,10 +17,19 @@ struct bsb200_poa_batch {
 	uint64_t qsel_bytes = 0;
 	DevBuf d_order_fast, d_qsel, d_qsel_off, d_counter2;
 	HostBuf h_nodes;
+	bool has_rev = false;               // reverse edges attached: the run also walks the alignment back on the device
+	uint64_t nredges = 0;
+	DevBuf d_reoff, d_redge_off, d_resrc, d_recov, d_rev, d_match, d_trace;
 	DevBuf d_par, d_queries, d_qcode, d_qoff, d_slen, d_node_off, d_node, d_eoff, d_edge_off, d_edst, d_head, d_tail,
 		d_mpos, d_vst, d_stack, d_rows, d_row_off, d_best, d_status, d_ops, d_order, d_counter;
 	bool ran = false;
 };
+
+static std::vector<DevBuf*> poa_bufs(bsb200_poa_batch *b){
+	return {&b->d_par, &b->d_queries, &b->d_qcode, &b->d_qoff, &b->d_slen, &b->d_node_off, &b->d_node, &b->d_eoff, &b->d_edge_off, &b->d_edst,
+		&b->d_head, &b->d_tail, &b->d_mpos, &b->d_vst, &b->d_stack, &b->d_rows, &b->d_row_off, &b->d_best, &b->d_status, &b->d_ops, &b->d_order, &b->d_counter,
+		&b->d_order_fast, &b->d_qsel, &b->d_qsel_off, &b->d_counter2, &b->d_reoff, &b->d_redge_off, &b->d_resrc, &b->d_recov, &b->d_rev, &b->d_match, &b->d_trace};
+}
 
 static uint32_t poa_mmblk(const int32_t *par){
 	const uint32_t bw = (uint32_t)par[0];
@@ -32,12 +42,10 @@ extern "C" uint32_t bsb200_poa_block_bytes(const int32_t par[10]){ return par ? 
 extern "C" void bsb200_poa_free(bsb200_ctx *ctx, bsb200_poa_batch *b){
 	if(!b) return;
 	if(ctx) cudaSetDevice(ctx->device);
-	DevBuf *ds[] = {&b->d_par, &b->d_queries, &b->d_qcode, &b->d_qoff, &b->d_slen, &b->d_node_off, &b->d_node, &b->d_eoff, &b->d_edge_off, &b->d_edst,
-		&b->d_head, &b->d_tail, &b->d_mpos, &b->d_vst, &b->d_stack, &b->d_rows, &b->d_row_off, &b->d_best, &b->d_status, &b->d_ops, &b->d_order, &b->d_counter,
-		&b->d_order_fast, &b->d_qsel, &b->d_qsel_off, &b->d_counter2};
+	std::vector<DevBuf*> ds = poa_bufs(b);
 	if(ctx){   // park the allocations for the next batch (cudaMalloc / cudaFree of a multi-GB row arena cost more than the sweep)
 		cudaStreamSynchronize(ctx->stream);
-		for(int k=0;k<26;k++){ if(ctx->poa_cache[k].cap < ds[k]->cap){ ctx->poa_cache[k].release(); ctx->poa_cache[k] = *ds[k]; } else ds[k]->release(); }
+		for(size_t k=0;k<ds.size();k++){ if(ctx->poa_cache[k].cap < ds[k]->cap){ ctx->poa_cache[k].release(); ctx->poa_cache[k] = *ds[k]; } else ds[k]->release(); }
 		if(ctx->poa_hcache[0].cap < b->h_nodes.cap){ ctx->poa_hcache[0].release(); ctx->poa_hcache[0] = b->h_nodes; } else b->h_nodes.release();
 	} else {
 		for(auto d : ds) d->release();
@@ -58,10 +66,8 @@ extern "C" bsb200_poa_batch *bsb200_poa_upload(bsb200_ctx *ctx, uint32_t njobs, 
 	cudaSetDevice(ctx->device);
 	bsb200_poa_batch *b = new bsb200_poa_batch();
 	{
-		DevBuf *ds[] = {&b->d_par, &b->d_queries, &b->d_qcode, &b->d_qoff, &b->d_slen, &b->d_node_off, &b->d_node, &b->d_eoff, &b->d_edge_off, &b->d_edst,
-			&b->d_head, &b->d_tail, &b->d_mpos, &b->d_vst, &b->d_stack, &b->d_rows, &b->d_row_off, &b->d_best, &b->d_status, &b->d_ops, &b->d_order, &b->d_counter,
-			&b->d_order_fast, &b->d_qsel, &b->d_qsel_off, &b->d_counter2};
-		for(int k=0;k<26;k++){ *ds[k] = ctx->poa_cache[k]; ctx->poa_cache[k] = DevBuf(); }
+		std::vector<DevBuf*> ds = poa_bufs(b);
+		for(size_t k=0;k<ds.size();k++){ *ds[k] = ctx->poa_cache[k]; ctx->poa_cache[k] = DevBuf(); }
 		b->h_nodes = ctx->poa_hcache[0]; ctx->poa_hcache[0] = HostBuf();
 	}
 	b->njobs = njobs;
@@ -243,13 +249,25 @@ extern "C" int bsb200_poa_run(bsb200_ctx *ctx, bsb200_poa_batch *b){
 		}
 	}
 	cudaEventRecord(ctx->ev[4], st);
+	if(b->has_rev){
+		PoaBtArgs t;
+		t.njobs = b->njobs; t.par = a.par; t.queries = b->d_queries.as<uint8_t>(); t.qoff = a.qoff; t.slen = a.slen;
+		t.node_off = a.node_off; t.node = a.node; t.reoff = b->d_reoff.as<int32_t>(); t.redge_off = b->d_redge_off.as<uint64_t>();
+		t.rev = b->d_rev.as<int4>(); t.head = a.head; t.tail = a.tail; t.rows = a.rows; t.row_off = a.row_off; t.best = a.best;
+		t.match = b->d_match.as<int32_t>(); t.trace = b->d_trace.as<int32_t>();
+		poa_backtrace_kernel<<<(b->njobs + 31) / 32, 32, 0, st>>>(t);
+		launches++;
+	}
+	cudaEventRecord(ctx->ev[7], st);
 	CK(cudaGetLastError());
 	CK(cudaStreamSynchronize(st));
-	float prep = 0, sweep = 0;
+	float prep = 0, sweep = 0, walk = 0;
 	cudaEventElapsedTime(&prep, ctx->ev[2], ctx->ev[3]);
 	cudaEventElapsedTime(&sweep, ctx->ev[3], ctx->ev[4]);
-	ctx->timing.forward_ms = sweep; ctx->timing.traceback_ms = 0; ctx->timing.run_ms = prep + sweep; ctx->timing.total_ms = prep + sweep;
-	ctx->timing.forward_launches = launches; ctx->timing.other_launches = (ngen ? 1 : 0) + (nfast ? 1 : 0); ctx->timing.traceback_launches = 0; ctx->timing.waves = 1;
+	cudaEventElapsedTime(&walk, ctx->ev[4], ctx->ev[7]);
+	ctx->timing.forward_ms = sweep; ctx->timing.traceback_ms = walk; ctx->timing.run_ms = prep + sweep + walk; ctx->timing.total_ms = prep + sweep + walk;
+	ctx->timing.traceback_launches = b->has_rev ? 1 : 0;
+	ctx->timing.forward_launches = launches - (b->has_rev ? 1 : 0); ctx->timing.other_launches = (ngen ? 1 : 0) + (nfast ? 1 : 0); ctx->timing.waves = 1;
 	b->ran = true;
 	return 0;
 }
@@ -292,6 +310,77 @@ extern "C" int bsb200_poa_rows_batch(bsb200_ctx *ctx, uint32_t njobs, const int3
 	if(!b) return -1;
 	int rc = bsb200_poa_run(ctx, b);
 	if(rc == 0) rc = bsb200_poa_fetch(ctx, b, rows, best, status, ops);
+	bsb200_poa_free(ctx, b);
+	return rc;
+}
+
+/* ---- device-side walk of alignment2graph_bspoa (poa_backtrace.cuh) --------------------------------------------------------- */
+extern "C" int bsb200_poa_attach_reverse(bsb200_ctx *ctx, bsb200_poa_batch *b, const int32_t *reoff, const uint64_t *redge_off,
+		const int32_t *resrc, const int32_t *recov){
+	if(!ctx || !b) return -1;
+	ctx->err.clear();
+	if(b->njobs && (!reoff || !redge_off || !resrc || !recov)) return fail(ctx, "bsb200_poa_attach_reverse", cudaSuccess);
+	cudaSetDevice(ctx->device);
+	cudaStream_t st = ctx->stream;
+	const size_t nj = b->njobs, nn = b->nnodes;
+	b->nredges = nj ? redge_off[nj] : 0;
+	const size_t ne = b->nredges;
+	CK(b->d_reoff.reserve((nn + nj) * 4 + 4)); CK(b->d_redge_off.reserve((nj + 1) * 8)); CK(b->d_resrc.reserve(ne * 4 + 4)); CK(b->d_recov.reserve(ne * 4 + 4));
+	CK(b->d_rev.reserve(ne * 16 + 16)); CK(b->d_match.reserve(b->qbytes * 4 + 16)); CK(b->d_trace.reserve(nj * 32 + 32));
+	cudaEventRecord(ctx->ev[0], st);
+	if(nj){
+		CK(cudaMemcpyAsync(b->d_reoff.p, reoff, (nn + nj) * 4, cudaMemcpyHostToDevice, st));
+		CK(cudaMemcpyAsync(b->d_redge_off.p, redge_off, (nj + 1) * 8, cudaMemcpyHostToDevice, st));
+		if(ne){
+			CK(cudaMemcpyAsync(b->d_resrc.p, resrc, ne * 4, cudaMemcpyHostToDevice, st));
+			CK(cudaMemcpyAsync(b->d_recov.p, recov, ne * 4, cudaMemcpyHostToDevice, st));
+		}
+		poa_rev_prep_kernel<<<std::min<uint32_t>(b->njobs, (uint32_t)ctx->num_sms * 8), 256, 0, st>>>(b->njobs, b->d_node_off.as<uint64_t>(), b->d_node.as<int2>(),
+			b->d_redge_off.as<uint64_t>(), b->d_resrc.as<int32_t>(), b->d_recov.as<int32_t>(), b->d_rev.as<int4>());
+	}
+	cudaEventRecord(ctx->ev[1], st);
+	CK(cudaGetLastError());
+	CK(cudaStreamSynchronize(st));
+	float ms = 0; cudaEventElapsedTime(&ms, ctx->ev[0], ctx->ev[1]);
+	ctx->timing.h2d_ms += ms;
+	ctx->timing.h2d_bytes += (nn + nj) * 4 + (nj + 1) * 8 + ne * 8;
+	b->has_rev = true;
+	return 0;
+}
+
+/* match: int32 per read position, job i at match[qoff[i] .. + slen[i]); trace: njobs x 8 */
+extern "C" int bsb200_poa_fetch_trace(bsb200_ctx *ctx, bsb200_poa_batch *b, int32_t *match, int32_t *trace){
+	if(!ctx || !b) return -1;
+	ctx->err.clear();
+	if(!b->ran || !b->has_rev){ ctx->err = "bsb200_poa_fetch_trace: batch has not been run with reverse edges attached"; return -1; }
+	cudaSetDevice(ctx->device);
+	cudaStream_t st = ctx->stream;
+	cudaEventRecord(ctx->ev[5], st);
+	uint64_t bytes = 0;
+	if(b->njobs){
+		if(match && b->qbytes){ CK(cudaMemcpyAsync(match, b->d_match.p, b->qbytes * 4, cudaMemcpyDeviceToHost, st)); bytes += b->qbytes * 4; }
+		if(trace){ CK(cudaMemcpyAsync(trace, b->d_trace.p, (size_t)b->njobs * 32, cudaMemcpyDeviceToHost, st)); bytes += (size_t)b->njobs * 32; }
+	}
+	cudaEventRecord(ctx->ev[6], st);
+	CK(cudaStreamSynchronize(st));
+	float ms = 0; cudaEventElapsedTime(&ms, ctx->ev[5], ctx->ev[6]);
+	ctx->timing.d2h_ms += ms; ctx->timing.d2h_bytes += bytes;
+	return 0;
+}
+
+/* one-shot: sweep + walk; the row blocks stay in HBM (rows may be NULL) */
+extern "C" int bsb200_poa_align_batch(bsb200_ctx *ctx, uint32_t njobs, const int32_t *par,
+		const uint8_t *queries, const uint64_t *qoff, const uint32_t *slen,
+		const uint64_t *node_off, const uint8_t *node_base, const uint8_t *node_bonus, const int32_t *node_rpos, const int32_t *node_nct,
+		const int32_t *eoff, const uint64_t *edge_off, const int32_t *edst, const uint32_t *head, const uint32_t *tail,
+		const int32_t *reoff, const uint64_t *redge_off, const int32_t *resrc, const int32_t *recov,
+		uint8_t *rows, int32_t *best, int32_t *status, uint64_t *ops, int32_t *match, int32_t *trace){
+	bsb200_poa_batch *b = bsb200_poa_upload(ctx, njobs, par, queries, qoff, slen, node_off, node_base, node_bonus, node_rpos, node_nct, eoff, edge_off, edst, head, tail);
+	if(!b) return -1;
+	int rc = bsb200_poa_attach_reverse(ctx, b, reoff, redge_off, resrc, recov);
+	if(rc == 0) rc = bsb200_poa_run(ctx, b);
+	if(rc == 0){ ctx->timing.d2h_ms = 0; ctx->timing.d2h_bytes = 0; rc = bsb200_poa_fetch(ctx, b, rows, best, status, ops); }
+	if(rc == 0) rc = bsb200_poa_fetch_trace(ctx, b, match, trace);
 	bsb200_poa_free(ctx, b);
 	return rc;
 }

@@ -32,9 +32,9 @@ def block_bytes(par):
 
 class SweepJob:
     """One sweep job; arrays are over LOCAL node ids (position in g->sels)."""
-    __slots__ = ("par", "query", "base", "bonus", "rpos", "nct", "eoff", "edst", "head", "tail")
+    __slots__ = ("par", "query", "base", "bonus", "rpos", "nct", "eoff", "edst", "head", "tail", "reoff", "resrc", "recov")
 
-    def __init__(self, par, query, base, bonus, rpos, nct, eoff, edst, head, tail):
+    def __init__(self, par, query, base, bonus, rpos, nct, eoff, edst, head, tail, reoff=None, resrc=None, recov=None):
         self.par = np.ascontiguousarray(par, dtype=np.int32)
         self.query = np.ascontiguousarray(query, dtype=np.uint8)
         self.base = np.ascontiguousarray(base, dtype=np.uint8)
@@ -44,6 +44,11 @@ class SweepJob:
         self.eoff = np.ascontiguousarray(eoff, dtype=np.int32)
         self.edst = np.ascontiguousarray(edst, dtype=np.int32)
         self.head, self.tail = int(head), int(tail)
+        # reverse edges (bspoanode_t.erev lists in list order, restricted to selected nodes) with bspoaedge_t.cov: only the
+        # device-side traceback (alignment2graph_bspoa's walk) needs them
+        self.reoff = None if reoff is None else np.ascontiguousarray(reoff, dtype=np.int32)
+        self.resrc = None if resrc is None else np.ascontiguousarray(resrc, dtype=np.int32)
+        self.recov = None if recov is None else np.ascontiguousarray(recov, dtype=np.int32)
 
     @property
     def nnode(self):
@@ -77,6 +82,14 @@ class SweepBatch:
         self.edst = cat([j.edst for j in jobs], np.int32)
         self.head = np.array([j.head for j in jobs], dtype=np.uint32)
         self.tail = np.array([j.tail for j in jobs], dtype=np.uint32)
+        self.has_rev = n > 0 and all(j.reoff is not None for j in jobs)
+        if self.has_rev:
+            self.reoff = cat([j.reoff for j in jobs], np.int32)
+            nre = np.array([len(j.resrc) for j in jobs], dtype=np.uint64)
+            self.redge_off = np.zeros(n + 1, dtype=np.uint64)
+            np.cumsum(nre, out=self.redge_off[1:])
+            self.resrc = cat([j.resrc for j in jobs], np.int32)
+            self.recov = cat([j.recov for j in jobs], np.int32)
         self.blk = np.array([block_bytes(j.par) for j in jobs], dtype=np.uint64)
         self.row_off = np.zeros(n + 1, dtype=np.uint64)
         np.cumsum(nn * self.blk, out=self.row_off[1:])
@@ -86,10 +99,22 @@ class SweepBatch:
         return (self.n, p(self.par), p(self.queries), p(self.qoff), p(self.slen), p(self.node_off), p(self.base), p(self.bonus),
                 p(self.rpos), p(self.nct), p(self.eoff), p(self.edge_off), p(self.edst), p(self.head), p(self.tail))
 
+    def rev_args(self):
+        if not self.has_rev:
+            raise ValueError("these sweep jobs carry no reverse edges (SweepJob(reoff=, resrc=, recov=))")
+        p = api._ptr
+        return (p(self.reoff), p(self.redge_off), p(self.resrc), p(self.recov))
+
 
 class SweepResult:
-    def __init__(self, batch, rows, best, status, ops):
+    def __init__(self, batch, rows, best, status, ops, match=None, trace=None):
         self.batch, self.rows, self.best, self.status, self.ops = batch, rows, best, status, ops
+        self.match_arena, self.trace = match, trace     # device-side walk of alignment2graph_bspoa (when reverse edges were given)
+
+    def match(self, i):
+        """Per read position of job i: local id of the node it is aligned to, or -1."""
+        o = int(self.batch.qoff[i])
+        return self.match_arena[o:o + int(self.batch.slen[i])]
 
     def blocks(self, i):
         """Row blocks of job i as (nnode, mmblk) uint8 -- the bytes of g->memp from block 2 on."""
@@ -129,6 +154,9 @@ def _bind(L):
     L.bsb200_poa_rows_batch.argtypes = [P] + job_args + [P, P, P, P]
     L.bsb200_poa_block_bytes.restype = ctypes.c_uint32
     L.bsb200_poa_block_bytes.argtypes = [P]
+    L.bsb200_poa_attach_reverse.argtypes = [P, P, P, P, P, P]
+    L.bsb200_poa_fetch_trace.argtypes = [P, P, P, P]
+    L.bsb200_poa_align_batch.argtypes = [P] + job_args + [P, P, P, P] + [P, P, P, P, P, P]
     L._poa_bound = True
 
 
@@ -148,6 +176,24 @@ def poa_rows_batch(ctx, batch, want_rows=True, rows=None):
     return SweepResult(batch, rows, best, status, ops)
 
 
+def _alloc_trace(batch, match=None):
+    if match is None:
+        match = np.zeros(max(1, int(batch.slen.sum())), dtype=np.int32)
+    return match, np.zeros((batch.n, 8), dtype=np.int32)
+
+
+def poa_align_batch(ctx, batch, want_rows=False, rows=None, match=None):
+    """One-shot sweep + device-side walk (bsb200_poa_align_batch): the row blocks stay in HBM unless want_rows."""
+    L = ctx._lib
+    _bind(L)
+    rows, best, status, ops = _alloc(batch, want_rows, rows)
+    match, trace = _alloc_trace(batch, match)
+    rc = L.bsb200_poa_align_batch(ctx._h, *batch.args(), *batch.rev_args(), api._ptr(rows), api._ptr(best), api._ptr(status), api._ptr(ops),
+                                  api._ptr(match), api._ptr(trace))
+    ctx._check(rc, "bsb200_poa_align_batch")
+    return SweepResult(batch, rows, best, status, ops, match, trace)
+
+
 class ResidentSweeps:
     """Staged form: jobs resident in HBM; run() = kernels only."""
 
@@ -158,6 +204,10 @@ class ResidentSweeps:
         if not self._h:
             raise RuntimeError("bsb200_poa_upload failed: %s" % ctx._lib.bsb200_last_error(ctx._h).decode())
 
+    def attach_reverse(self):
+        self.ctx._check(self.ctx._lib.bsb200_poa_attach_reverse(self.ctx._h, self._h, *self.batch.rev_args()), "bsb200_poa_attach_reverse")
+        self.has_rev = True
+
     def run(self):
         self.ctx._check(self.ctx._lib.bsb200_poa_run(self.ctx._h, self._h), "bsb200_poa_run")
 
@@ -165,7 +215,12 @@ class ResidentSweeps:
         rows, best, status, ops = _alloc(self.batch, want_rows, rows)
         rc = self.ctx._lib.bsb200_poa_fetch(self.ctx._h, self._h, api._ptr(rows), api._ptr(best), api._ptr(status), api._ptr(ops))
         self.ctx._check(rc, "bsb200_poa_fetch")
-        return SweepResult(self.batch, rows, best, status, ops)
+        match = trace = None
+        if getattr(self, "has_rev", False):
+            match, trace = _alloc_trace(self.batch)
+            rc = self.ctx._lib.bsb200_poa_fetch_trace(self.ctx._h, self._h, api._ptr(match), api._ptr(trace))
+            self.ctx._check(rc, "bsb200_poa_fetch_trace")
+        return SweepResult(self.batch, rows, best, status, ops, match, trace)
 
     def free(self):
         if self._h:

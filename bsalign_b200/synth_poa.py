@@ -67,7 +67,7 @@ def make_sweep_job(seed, tlen=15000, ngraph=21, par=None, p_sub=0.03, p_ins=0.03
         ids = nid_of_sorted[np.searchsorted(uniq, key)]
         src.append(np.concatenate([[0], ids])); dst.append(np.concatenate([ids, [1]]))
     src = np.concatenate(src); dst = np.concatenate(dst)
-    e = np.unique(src * nn + dst)
+    e, ecov = np.unique(src * nn + dst, return_counts=True)    # coverage = reads that use the edge (bspoaedge_t.cov)
     src, dst = e // nn, e % nn
     eoff = np.zeros(nn + 1, dtype=np.int64)
     np.cumsum(np.bincount(src, minlength=nn), out=eoff[1:])
@@ -87,4 +87,9 @@ def make_sweep_job(seed, tlen=15000, ngraph=21, par=None, p_sub=0.03, p_ins=0.03
         rpos = np.minimum(rpos, slen - bw)
     rpos[0] = 0
     par_arr = np.array([bw] + [int(d[k]) for k in poa.PAR_FIELDS[1:]], dtype=np.int32)
-    return poa.SweepJob(par_arr, query, base, bonus, rpos.astype(np.int32), nct.astype(np.int32), eoff.astype(np.int32), dst.astype(np.int32), 0, 1)
+    # reverse edges (the erev lists the traceback walks): grouped by destination, sources in ascending id order
+    ro = np.argsort(dst * nn + src, kind="stable")
+    reoff = np.zeros(nn + 1, dtype=np.int64)
+    np.cumsum(nct, out=reoff[1:])
+    return poa.SweepJob(par_arr, query, base, bonus, rpos.astype(np.int32), nct.astype(np.int32), eoff.astype(np.int32), dst.astype(np.int32), 0, 1,
+                        reoff=reoff.astype(np.int32), resrc=src[ro].astype(np.int32), recov=ecov[ro].astype(np.int32))

@@ -160,6 +160,30 @@ int bsb200_poa_rows_batch(bsb200_ctx *ctx, uint32_t njobs, const int32_t *par,
 		const int32_t *eoff, const uint64_t *edge_off, const int32_t *edst, const uint32_t *head, const uint32_t *tail,
 		uint8_t *rows, int32_t *best, int32_t *status, uint64_t *ops);
 
+/* ---- POA: the walk of alignment2graph_bspoa (bspoa.h:2274-2497) on the device, right behind the sweep ------------------- */
+/*
+ * The reference walks back from (maxidx, maxoff) to the head, re-deriving every step from the node rows, and interleaves graph
+ * surgery (merge_nodes_bspoa) that never changes what the walk reads.  With the reverse edges of the selected sub-graph attached,
+ * the run also performs that walk and returns its DECISIONS instead of the row blocks (15 GB per 1000-job round):
+ *   reverse edges of job i: node n owns entries [reoff[node_off[i] + i + n], reoff[.. + n + 1]) (+ redge_off[i]) of resrc / recov:
+ *         the nodes of its erev list (bspoanode_t.erev / bspoaedge_t.next order, restricted to selected nodes) as LOCAL ids, and
+ *         bspoaedge_t.cov of every entry (the tie-break of bspoa.h:2457-2464)
+ *   match: int32 per read position, job i at match[qoff[i] .. + slen[i]): LOCAL id of the node the position is aligned to
+ *         (the `u->cpos = n->cpos` / merge_nodes_bspoa step of bspoa.h:2393-2406) or -1 (insertion / outside the alignment)
+ *   trace[8*i ..] = { x at the end of the walk (rs.qb before + g->qb), node at the end, mat, mis, ins, del, start node, flags }
+ *         flags: BSB200_ST_RANGE / BSB200_ST_LOOP as for the pairwise traceback (the reference reads out of bounds / never ends)
+ * include/bsalign_b200_poa_compat.h replays merge_nodes_bspoa and the cpos bookkeeping from `match` in the reference's order.
+ */
+int bsb200_poa_attach_reverse(bsb200_ctx *ctx, bsb200_poa_batch *b, const int32_t *reoff, const uint64_t *redge_off,
+		const int32_t *resrc, const int32_t *recov);      /* after bsb200_poa_upload, before bsb200_poa_run */
+int bsb200_poa_fetch_trace(bsb200_ctx *ctx, bsb200_poa_batch *b, int32_t *match, int32_t *trace);
+int bsb200_poa_align_batch(bsb200_ctx *ctx, uint32_t njobs, const int32_t *par,
+		const uint8_t *queries, const uint64_t *qoff, const uint32_t *slen,
+		const uint64_t *node_off, const uint8_t *node_base, const uint8_t *node_bonus, const int32_t *node_rpos, const int32_t *node_nct,
+		const int32_t *eoff, const uint64_t *edge_off, const int32_t *edst, const uint32_t *head, const uint32_t *tail,
+		const int32_t *reoff, const uint64_t *redge_off, const int32_t *resrc, const int32_t *recov,
+		uint8_t *rows /* may be NULL */, int32_t *best, int32_t *status, uint64_t *ops, int32_t *match, int32_t *trace);
+
 /* nominal band width the kernels use for one pair (the GCUPS denominator) */
 uint32_t bsb200_epi8_bandwidth(uint32_t qlen, uint32_t bandwidth);
 uint32_t bsb200_edit_bandwidth(uint32_t qlen, uint32_t tlen, int mode, uint32_t bandwidth);

@@ -1079,3 +1079,123 @@ int bso_poa_sweep_batch(uint32_t njobs, const int32_t *par, const uint8_t *queri
 	free(tids);
 	return b.err;
 }
+
+/* ------------------------------------------------------------------------------------------------
+ * The walk of alignment2graph_bspoa (bspoa.h:2274-2497): from (maxidx, maxoff) back to the head, re-deriving every step from the
+ * node rows.  Only the DECISIONS are restated (which node every read position is matched to, insertions, deletions); the graph
+ * surgery the reference interleaves (merge_nodes_bspoa, cpos bookkeeping) stays host code and is replayed from them.
+ * Reverse edges: per node the erev list in list order, restricted to selected nodes, with bspoaedge_t.cov.
+ * match[x] (x < slen): local node id matched to read position x, or -1.
+ * out[8] = {final x (rs.qb before + g->qb), final node, mat, mis, ins, del, start node, flags}.
+ * ------------------------------------------------------------------------------------------------ */
+#define BSO_SCORE_MAX 536870911   /* SEQALIGN_SCORE_MAX = MAX_B4 >> 2, bsalign.h:59 */
+int bso_poa_backtrace(const int32_t *par, const uint8_t *query, uint32_t slen, uint32_t nnode,
+		const uint8_t *base, const uint8_t *bonus, const int32_t *rpos,
+		const int32_t *reoff, const int32_t *resrc, const int32_t *recov, uint32_t head, uint32_t tail,
+		const int8_t *rows, const int32_t *ubs, int32_t midx, int32_t xe, int32_t *match, int32_t *out){
+	bso_epi8_t A, *a = &A;
+	uint32_t bw = (uint32_t)par[0], W = bw / BSO_LANES, k;
+	int alnmode = par[1] & 3, M = par[2], X = par[3], O = par[4], E = par[5], Q = par[6], P = par[7], refbonus = par[9];
+	int pw, x = xe, Hs0 = 0, Hs1, Hs2 = 0, bt = -1, mat = 0, mis = 0, ins = 0, del = 0;
+	int64_t guard = 0, guard_max = 8 * ((int64_t)slen + nnode) + 64;
+	uint32_t n, nidx, urow;   /* urow: the row the reference's `us` pointer last referred to (bspoa.h:2472, 2388) */
+	(void)tail;
+	memset(a, 0, sizeof(A));
+	a->bw = bw; a->W = W; a->qlen = slen;
+	pw = bso_epi8_piecewise((int8_t)O, (int8_t)E, (int8_t)Q, (int8_t)P, bw);
+	for(k=0;k<slen;k++) match[k] = -1;
+	memset(out, 0, 8 * sizeof(int32_t));
+	out[6] = midx;
+	if(midx < 0 || (uint32_t)midx >= nnode){ out[7] = BSO_ERR_RANGE; out[0] = x; out[1] = midx; return BSO_ERR_RANGE; }
+	#define ROW_OF(r, n_) do { (r).u = (int8_t*)rows + (size_t)(n_) * 3 * bw; (r).e = (r).u + bw; (r).q = (r).u + 2 * (size_t)bw; (r).ub = (int32_t*)ubs + (size_t)(n_) * 17; } while(0)
+	n = nidx = (uint32_t)midx; urow = n;
+	{ bso_row_t r; ROW_OF(r, n); Hs1 = bso_getscore(a, r, (int64_t)x - rpos[n]); }
+	while(1){
+		if(++guard > guard_max){ a->err |= BSO_ERR_LOOP; break; }
+		if(n == head || x < 0) break;
+		if(bt == 2 || bt == 4){ /* inside a deletion: leave node n for a predecessor that explains the score (bspoa.h:2308-2356) */
+			int32_t ei, found = 0;
+			del++;
+			for(ei=reoff[n];ei<reoff[n+1];ei++){
+				uint32_t w = (uint32_t)resrc[ei];
+				bso_row_t r;
+				int8_t q;
+				if(x < rpos[w] || x >= rpos[w] + (int)bw) continue;
+				ROW_OF(r, w); urow = w;
+				Hs0 = bso_getscore(a, r, (int64_t)x - rpos[w]);
+				if(bt == 2) q = pw ? r.e[x - rpos[w]] : (int8_t)(O + E);
+				else q = r.q[x - rpos[w]];
+				if(Hs0 + q != Hs1) continue;
+				n = w;
+				if(q == ((bt == 2) ? O + E : Q + P)){ bt = -1; Hs1 = Hs0; Hs2 = 0; }
+				else { Hs1 -= (bt == 2) ? E : P; Hs2++; }
+				found = 1;
+				break;
+			}
+			if(!found){ a->err |= BSO_ERR_LOOP; break; } /* the reference would repeat this state forever */
+			continue;
+		} else if(bt == 1 || bt == 3){ /* insertion run (bspoa.h:2357-2392) */
+			int t;
+			ins++;
+			if(pw == 2){ int c1 = O + E * Hs2, c2 = Q + P * Hs2; t = c1 > c2 ? c1 : c2; } else t = O + E * Hs2;
+			x--;
+			if(Hs0 + t == Hs1){ bt = -1; Hs1 = Hs0; Hs2 = 0; }
+			else if(x >= 0){
+				int64_t p = (int64_t)x - rpos[urow];
+				if(p < 0 || p >= (int64_t)bw){ a->err |= BSO_ERR_RANGE; break; }
+				Hs0 -= rows[(size_t)urow * 3 * bw + p];
+				Hs2++;
+			}
+			continue;
+		} else if(bt == 0){ /* match / mismatch of read position x with node n (bspoa.h:2393-2410) */
+			match[x] = (int32_t)n;
+			if(n != head && n != tail && query[x] == base[n]) mat++; else mis++;
+			x--;
+			n = nidx;
+			bt = -1;
+		} else { /* decide the next step from the predecessors of n (bspoa.h:2411-2496) */
+			int32_t ei, btc = 0;
+			int have = 0, bi = 0, b_h0 = 0; uint32_t b_w = 0;
+			int bti_low = 0xFF; /* (bti & 0xFF) of the reference; bti == MAX_U4 initially */
+			for(ei=reoff[n];ei<reoff[n+1];ei++){
+				uint32_t w = (uint32_t)resrc[ei];
+				bso_row_t r;
+				int ft = 0, s, scr[3], i, kprof;
+				int64_t p;
+				ROW_OF(r, w);
+				if(x < rpos[w] || x > (int)bw + rpos[w]) continue;
+				urow = w;
+				if(x == (int)bw + rpos[w]){ Hs0 = bso_getscore(a, r, (int64_t)x - rpos[w] - 1); ft |= (1 << 2) | (1 << 4); }
+				else if(x == rpos[w]){
+					if(rpos[w] == 0 && (alnmode == BSO_MODE_OVERLAP || w == head)){ Hs0 = r.ub[0]; ft |= 1 << 15; }
+					else { Hs0 = r.ub[0]; ft |= 1 << 0; }
+				} else Hs0 = bso_getscore(a, r, (int64_t)x - rpos[w] - 1);
+				kprof = (base[w] == base[n]) * 2 + bonus[n];
+				s = (int8_t)(((query[x] & 3) == base[n]) ? ((kprof & 1) ? M + refbonus : M) : X);
+				if(kprof < 2 && (uint32_t)x + 1 < slen && query[x] != query[x + 1]) s += 1; /* the hpc profiles, bsalign.h:2204-2206 */
+				if(ft & (1 << 15)) s -= r.ub[0];
+				p = (int64_t)x - rpos[w];
+				scr[0] = (ft & (1 << 0)) ? BSO_SCORE_MIN : s;
+				scr[1] = (ft & (1 << 2)) ? BSO_SCORE_MIN : r.u[p] + (pw ? r.e[p] : E);
+				scr[2] = (ft & (1 << 4)) ? BSO_SCORE_MIN : (pw == 2 ? r.u[p] + r.q[p] : BSO_SCORE_MAX);
+				for(i=0;i<3;i++){
+					if(Hs0 + scr[i] == Hs1){
+						if(recov[ei] > btc){ have = 1; bi = i; bti_low = i; b_w = w; b_h0 = Hs0; btc = recov[ei]; }
+						else if(recov[ei] == btc && i == 0 && bti_low != 0){ have = 1; bi = 0; bti_low = 0; b_w = w; b_h0 = Hs0; btc = recov[ei]; }
+					}
+				}
+			}
+			if(!have){
+				int64_t p = (int64_t)x - rpos[n];
+				if(p < 0 || p >= (int64_t)bw){ a->err |= BSO_ERR_RANGE; break; }
+				bt = 1; Hs2 = 1; urow = n;
+				Hs0 = Hs1 - rows[(size_t)n * 3 * bw + p];
+			} else if(bi == 0){ bt = 0; nidx = b_w; Hs1 = b_h0; Hs2 = 0; }
+			else if(bi == 1){ bt = 2; Hs2 = 1; }
+			else { bt = 4; Hs2 = 1; }
+		}
+	}
+	#undef ROW_OF
+	out[0] = x; out[1] = (int32_t)n; out[2] = mat; out[3] = mis; out[4] = ins; out[5] = del; out[7] = a->err;
+	return a->err;
+}

@@ -205,7 +205,7 @@ static void bsref_poa_dump_job(BSPOA *g, BSPOAPar *par, u4i nhead, u4i ntail, bs
 		memset(hdr, 0, sizeof(hdr));
 		hdr[0] = 0x504F4131; hdr[1] = bw; hdr[2] = g->piecewise; hdr[3] = g->slen; hdr[4] = par->alnmode; hdr[5] = par->M; hdr[6] = par->X;
 		hdr[7] = par->O; hdr[8] = par->E; hdr[9] = par->Q; hdr[10] = par->P; hdr[11] = par->T; hdr[12] = par->refbonus; hdr[13] = nloc;
-		hdr[14] = loc[nhead]; hdr[15] = loc[ntail]; hdr[16] = nedge; hdr[20] = (int32_t)g->mmblk;
+		hdr[14] = loc[nhead]; hdr[15] = loc[ntail]; hdr[16] = nedge; hdr[20] = (int32_t)g->mmblk; hdr[23] = g->qb;
 		*hdr_at = blob->n;
 		blob_put(blob, hdr, sizeof(hdr));
 		blob_put(blob, g->qseq->buffer + g->qb, g->slen);
@@ -213,6 +213,29 @@ static void bsref_poa_dump_job(BSPOA *g, BSPOAPar *par, u4i nhead, u4i ntail, bs
 		blob_put(blob, eoff, sizeof(int32_t) * (nloc + 1));
 		blob_put(blob, edst, sizeof(int32_t) * nedge);
 		free(node); free(eoff); free(edst);
+		{	/* reverse edges (u->erev lists, bspoa.h:2319, 2429) restricted to selected nodes, with their coverage: what alignment2graph_bspoa walks */
+			u4i nre = 0;
+			int32_t *reoff = malloc(sizeof(int32_t) * (nloc + 1)), *resrc, *recov;
+			for(i=0;i<nloc;i++){
+				bspoanode_t *u = ref_bspoanodev(g->nodes, g->sels->buffer[i]);
+				reoff[i] = nre;
+				for(eidx=u->erev;eidx;eidx=ref_bspoaedgev(g->edges, eidx)->next) if(get_bitvec(g->states, ref_bspoaedgev(g->edges, eidx)->node)) nre ++;
+			}
+			reoff[nloc] = nre;
+			resrc = malloc(sizeof(int32_t) * (nre + 1)); recov = malloc(sizeof(int32_t) * (nre + 1)); nre = 0;
+			for(i=0;i<nloc;i++){
+				bspoanode_t *u = ref_bspoanodev(g->nodes, g->sels->buffer[i]);
+				for(eidx=u->erev;eidx;eidx=ref_bspoaedgev(g->edges, eidx)->next){
+					bspoaedge_t *e = ref_bspoaedgev(g->edges, eidx);
+					if(get_bitvec(g->states, e->node)){ resrc[nre] = loc[e->node]; recov[nre] = e->cov; nre ++; }
+				}
+			}
+			((int32_t*)(blob->buf + *hdr_at))[21] = nre;
+			blob_put(blob, reoff, sizeof(int32_t) * (nloc + 1));
+			blob_put(blob, resrc, sizeof(int32_t) * nre);
+			blob_put(blob, recov, sizeof(int32_t) * nre);
+			free(reoff); free(resrc); free(recov);
+		}
 	} else {
 		int32_t *hdr = (int32_t*)(blob->buf + *hdr_at);
 		int8_t *row = malloc(3 * (size_t)bw); int32_t ub[17]; uint8_t *done = malloc(nloc + 4);
@@ -280,7 +303,21 @@ int64_t bsref_poa_dump(uint32_t nreads, const uint8_t *seqs, const uint64_t *off
 				bsref_poa_dump_job(g, g->par, nhead, ntail, &blob, 1, &hdr_at);
 				njobs ++;
 				rs = alignment2graph_bspoa(g, g->par, rid, 0, nhead, ntail, g->maxidx, g->maxoff, NULL);
-				UNUSED(rs); UNUSED(score);
+				UNUSED(score);
+				{	/* what the traceback decided: the result counts and, per read position, the graph node it was merged into (-1: none) */
+					int32_t r10[10], *mh = malloc(sizeof(int32_t) * (g->slen + 1));
+					u4i x, k, nloc2 = g->sels->size;
+					u4i *loc2 = malloc(sizeof(u4i) * (g->nodes->size + 1));
+					for(k=0;k<nloc2;k++) loc2[g->sels->buffer[k]] = k;
+					bsref_store_result(r10, &rs);
+					for(x=0;x<g->slen;x++){
+						bspoanode_t *rn = get_rdnode_bspoa(g, rid, g->qb + x);
+						mh[x] = (rn->header < g->nodes->size && get_bitvec(g->states, rn->header)) ? (int32_t)loc2[rn->header] : -1;
+					}
+					blob_put(&blob, r10, sizeof(r10));
+					blob_put(&blob, mh, sizeof(int32_t) * g->slen);
+					free(mh); free(loc2);
+				}
 				for(i=0;i<g->todels->size;i++){
 					chg_edge_bspoa(g, ref_bspoanodev(g->nodes, g->todels->buffer[i] >> 32), ref_bspoanodev(g->nodes, g->todels->buffer[i] & MAX_U4), -1, NULL);
 				}

@@ -18,7 +18,8 @@ MAGIC = 0x504F4131
 
 class SweepJob:
     __slots__ = ("bw", "pw", "slen", "alnmode", "M", "X", "O", "E", "Q", "P", "T", "refbonus", "nnode", "head", "tail", "nedge",
-                 "query", "base", "bonus", "rpos", "nct", "eoff", "edst", "maxscr", "maxidx", "maxoff", "rows", "ub", "done")
+                 "query", "base", "bonus", "rpos", "nct", "eoff", "edst", "maxscr", "maxidx", "maxoff", "rows", "ub", "done",
+                 "reoff", "resrc", "recov", "rs", "merged", "qb")
 
     def params(self):
         return np.array([self.bw, self.alnmode, self.M, self.X, self.O, self.E, self.Q, self.P, self.T, self.refbonus], dtype=np.int32)
@@ -26,7 +27,8 @@ class SweepJob:
     def to_api(self):
         """The product-side job object (bsalign_b200.poa.SweepJob) with the same content."""
         from bsalign_b200 import poa
-        return poa.SweepJob(self.params(), self.query, self.base, self.bonus, self.rpos, self.nct, self.eoff, self.edst, self.head, self.tail)
+        return poa.SweepJob(self.params(), self.query, self.base, self.bonus, self.rpos, self.nct, self.eoff, self.edst, self.head, self.tail,
+                            reoff=self.reoff, resrc=self.resrc, recov=self.recov)
 
 
 def parse_dump(blob, with_rows=True):
@@ -48,6 +50,10 @@ def parse_dump(blob, with_rows=True):
         j.rpos = node[:, 2].astype(np.int32); j.nct = node[:, 3].astype(np.int32)
         j.eoff = blob[pos:pos + 4 * (j.nnode + 1)].view(np.int32).copy(); pos += 4 * (j.nnode + 1)
         j.edst = blob[pos:pos + 4 * j.nedge].view(np.int32).copy(); pos += 4 * j.nedge
+        nre = int(hdr[21]); j.qb = int(hdr[23])
+        j.reoff = blob[pos:pos + 4 * (j.nnode + 1)].view(np.int32).copy(); pos += 4 * (j.nnode + 1)
+        j.resrc = blob[pos:pos + 4 * nre].view(np.int32).copy(); pos += 4 * nre
+        j.recov = blob[pos:pos + 4 * nre].view(np.int32).copy(); pos += 4 * nre
         rec = 3 * j.bw + 68
         assert rec % 4 == 0
         body = blob[pos:pos + rec * j.nnode].reshape(j.nnode, rec); pos += rec * j.nnode
@@ -58,6 +64,8 @@ def parse_dump(blob, with_rows=True):
             j.rows = None; j.ub = None
         j.done = blob[pos:pos + j.nnode].copy(); pos += pad4(j.nnode)
         j.done[j.tail] = 0  # the tail is only counted (v->vst++), it has no row
+        j.rs = blob[pos:pos + 40].view(np.int32).copy(); pos += 40          # seqalign_result_t of alignment2graph_bspoa
+        j.merged = blob[pos:pos + 4 * j.slen].view(np.int32).copy(); pos += 4 * j.slen   # per read position: node it was merged into
         jobs.append(j)
     return jobs
 
@@ -201,3 +209,37 @@ def ref_time_jobs(read_sets, nthreads, par_override=None):
     a = np.array(rs, dtype=np.float64)
     return dict(dp_seconds=float(a[:, 0].sum()), total_seconds=float(a[:, 1].sum()), nupd=int(a[:, 2].sum()), nmrg=int(a[:, 3].sum()),
                 cells=int(a[:, 4].sum()), wall=wall, jobs=len(read_sets))
+
+
+def oracle_backtrace(j, rows, ub, midx, xe):
+    """oracle/bsalign_oracle.c:bso_poa_backtrace on one dumped job with the given (linear) rows -> (match[slen], out[8])."""
+    lib = ck.oracle()
+    par = j.params()
+    match = np.zeros(max(1, j.slen), dtype=np.int32)
+    out = np.zeros(8, dtype=np.int32)
+    rows = np.ascontiguousarray(rows, dtype=np.int8); ub = np.ascontiguousarray(ub, dtype=np.int32)
+    q = np.ascontiguousarray(j.query, dtype=np.uint8); base = np.ascontiguousarray(j.base, dtype=np.uint8); bonus = np.ascontiguousarray(j.bonus, dtype=np.uint8)
+    rpos = np.ascontiguousarray(j.rpos, dtype=np.int32)
+    lib.bso_poa_backtrace(ck._ptr(par), ck._ptr(q), ctypes.c_uint32(j.slen), ctypes.c_uint32(j.nnode), ck._ptr(base), ck._ptr(bonus), ck._ptr(rpos),
+                          ck._ptr(j.reoff), ck._ptr(j.resrc), ck._ptr(j.recov), ctypes.c_uint32(j.head), ctypes.c_uint32(j.tail),
+                          ck._ptr(rows), ck._ptr(ub), ctypes.c_int32(midx), ctypes.c_int32(xe), ck._ptr(match), ck._ptr(out))
+    return match[:j.slen], out
+
+
+def compare_backtrace(j, match, out):
+    """Mismatch description (or None) between a walk result and what the reference's alignment2graph_bspoa did (dump of job j)."""
+    rs = j.rs   # score, qb, qe, tb, te, mat, mis, ins, del, aln
+    if int(out[7]) != 0:
+        return "flags %d" % int(out[7])
+    if (int(out[2]), int(out[3]), int(out[4]), int(out[5])) != (int(rs[5]), int(rs[6]), int(rs[7]), int(rs[8])):
+        return "counts %s != ref %s" % (out[2:6].tolist(), rs[5:9].tolist())
+    if int(out[0]) + j.qb != int(rs[1]):
+        return "qb %d != ref %d" % (int(out[0]) + j.qb, int(rs[1]))
+    # every position the reference merged into a graph node must be matched to that node; matched-but-not-merged = mismatches
+    m = j.merged >= 0
+    if not np.array_equal(match[m], j.merged[m]):
+        bad = np.nonzero(m & (match != j.merged))[0]
+        return "merged nodes differ at read positions %s" % bad[:5].tolist()
+    if int((match >= 0).sum()) != int(rs[5]) + int(rs[6]):
+        return "matched positions %d != mat + mis" % int((match >= 0).sum())
+    return None

@@ -120,3 +120,51 @@ def test_poa_dropin_end_bspoa_identical_msa():
         out = subprocess.run([exe] + args, capture_output=True, text=True, timeout=600)
         assert out.returncode == 0, out.stdout + out.stderr
         assert "identical=%s/%s" % (args[0], args[0]) in out.stdout, out.stdout
+
+
+def _as_dump_like(job):
+    """A bsalign_b200.poa.SweepJob viewed through the attribute names the checker helpers use."""
+    w = pj.SweepJob()
+    w.bw = int(job.par[0]); w.alnmode, w.M, w.X, w.O, w.E, w.Q, w.P, w.T, w.refbonus = [int(x) for x in job.par[1:]]
+    w.slen = len(job.query); w.nnode = job.nnode; w.head = job.head; w.tail = job.tail; w.nedge = len(job.edst)
+    w.query = job.query; w.base = job.base; w.bonus = job.bonus; w.rpos = job.rpos; w.nct = job.nct; w.eoff = job.eoff; w.edst = job.edst
+    w.reoff = job.reoff; w.resrc = job.resrc; w.recov = job.recov
+    return w
+
+
+def test_poa_device_walk_matches_reference_and_oracle(ctx):
+    """alignment2graph_bspoa's walk on the device: counts, end state and the node every read position was merged into equal what the
+    unmodified reference did (golden dumps), and the per-position matches equal the oracle's restatement of the walk."""
+    jobs = pj.load_golden()
+    res = poa.poa_align_batch(ctx, poa.SweepBatch([j.to_api() for j in jobs]), want_rows=True)
+    for k, j in enumerate(jobs):
+        assert pj.compare_backtrace(j, res.match(k), res.trace[k]) is None, (k, pj.compare_backtrace(j, res.match(k), res.trace[k]))
+        rows, ub = res.linear(k)
+        om, oo = pj.oracle_backtrace(j, rows, ub, int(res.best[k][1]), int(res.best[k][2]))
+        assert np.array_equal(om, res.match(k)) and np.array_equal(oo, res.trace[k]), (k, oo.tolist(), res.trace[k].tolist())
+
+
+def test_poa_device_walk_on_larger_graphs(ctx):
+    from bsalign_b200 import synth_poa
+    if ck.have_ref():
+        jobs = pj.ref_dump(pj.make_reads(20, 2500, 91, 0.05, 0.05, 0.06), None)
+        api_jobs = [j.to_api() for j in jobs]
+    else:
+        jobs = None
+        api_jobs = [synth_poa.make_sweep_job(300 + i, tlen=2500) for i in range(8)]
+    res = poa.poa_align_batch(ctx, poa.SweepBatch(api_jobs), want_rows=True)
+    for k, aj in enumerate(api_jobs):
+        w = jobs[k] if jobs is not None else _as_dump_like(aj)
+        if jobs is not None:
+            assert pj.compare_backtrace(w, res.match(k), res.trace[k]) is None, (k, pj.compare_backtrace(w, res.match(k), res.trace[k]))
+        rows, ub = res.linear(k)
+        om, oo = pj.oracle_backtrace(w, rows, ub, int(res.best[k][1]), int(res.best[k][2]))
+        assert np.array_equal(om, res.match(k)) and np.array_equal(oo, res.trace[k]), (k, oo.tolist(), res.trace[k].tolist())
+    # synthetic graphs (what bench.py --workload c5 runs) through the same check
+    sj = [synth_poa.make_sweep_job(500 + i, tlen=3000) for i in range(4)]
+    res = poa.poa_align_batch(ctx, poa.SweepBatch(sj), want_rows=True)
+    for k, aj in enumerate(sj):
+        rows, ub = res.linear(k)
+        om, oo = pj.oracle_backtrace(_as_dump_like(aj), rows, ub, int(res.best[k][1]), int(res.best[k][2]))
+        assert int(oo[7]) == 0 and np.array_equal(om, res.match(k)) and np.array_equal(oo, res.trace[k])
+        assert int((om >= 0).sum()) > 0.8 * len(aj.query)

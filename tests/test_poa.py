@@ -80,3 +80,23 @@ def test_poa_entry_points_fail_without_gpu():
         pytest.skip("a GPU is present")
     with pytest.raises(RuntimeError):
         poa.poa_rows_batch(api.Context(0), poa.SweepBatch([j.to_api() for j in pj.load_golden()[:1]]))
+
+
+def test_oracle_walk_matches_golden_dumps():
+    """bso_poa_backtrace (the walk of alignment2graph_bspoa) on the reference's own rows: mat/mis/ins/del, the end of the walk and
+    the node every read position was merged into equal what the unmodified reference did."""
+    n = 0
+    for j in pj.load_golden():
+        match, out = pj.oracle_backtrace(j, j.rows, j.ub, j.maxidx, j.maxoff)
+        assert pj.compare_backtrace(j, match, out) is None, (j.bw, j.pw, j.nnode, pj.compare_backtrace(j, match, out))
+        n += int((match >= 0).sum())
+    assert n > 3000
+
+
+@pytest.mark.ref
+@pytest.mark.skipif(not ck.have_ref(), reason="oracle/_ref/libbsref.so not built")
+def test_oracle_walk_matches_live_reference():
+    for par, err in ((None, (0.05, 0.05, 0.06)), ([128, 2, -6, -3, -2, 0, 0, 20, 1, 0], (0.03, 0.03, 0.04)), ([64, 2, -6, -3, -2, -8, -1, 20, 0, 2], (0.04, 0.04, 0.04))):
+        for j in pj.ref_dump(pj.make_reads(12, 1200, 17, *err), par):
+            match, out = pj.oracle_backtrace(j, j.rows, j.ub, j.maxidx, j.maxoff)
+            assert pj.compare_backtrace(j, match, out) is None
