@@ -230,22 +230,24 @@ def main_poa(args, w, njobs, ncores, rank, local_rank, world):
 
     batch, protos = poa_make_batch(w, 1 + rank, njobs)
     pin = lambda a: torch.from_numpy(a).pin_memory().numpy()
-    for name in ("par", "queries", "qoff", "slen", "node_off", "base", "bonus", "rpos", "nct", "eoff", "edge_off", "edst", "head", "tail"):
+    for name in ("par", "queries", "qoff", "slen", "node_off", "base", "bonus", "rpos", "nct", "eoff", "edge_off", "edst", "head", "tail",
+                 "reoff", "redge_off", "resrc", "recov"):
         setattr(batch, name, pin(getattr(batch, name)))
     ctx = api.Context(local_rank)
     # ---- kernel-only leg: jobs resident in HBM -------------------------------------------------------
     rs = poa.ResidentSweeps(ctx, batch)
+    rs.attach_reverse()          # the run = sweep + the walk of alignment2graph_bspoa on the device
     for _ in range(args.warmup):
         rs.run()
     sampler = ClockSampler(local_rank)
     barrier()
     sampler.start()
-    dev_ms = sweep_ms = 0.0
+    dev_ms = sweep_ms = walk_ms = 0.0
     t0 = time.perf_counter()
     for _ in range(args.steps):
         rs.run()
         tm = ctx.timing()
-        dev_ms += tm["run_ms"]; sweep_ms += tm["forward_ms"]
+        dev_ms += tm["run_ms"]; sweep_ms += tm["forward_ms"]; walk_ms += tm["traceback_ms"]
     barrier()
     wall = time.perf_counter() - t0
     clocks = sampler.stop()
@@ -258,15 +260,17 @@ def main_poa(args, w, njobs, ncores, rank, local_rank, world):
     step_ms = reduce(dev_ms / args.steps, dist.ReduceOp.MAX if world > 1 else None)
     total_cells = reduce(cells, dist.ReduceOp.SUM if world > 1 else None)
     value = total_cells / (step_ms * 1e-3) / 1e9
-    # ---- e2e leg: host buffers through the one-shot C-ABI call (graphs up, row blocks + best ends back) ----
-    rows = pin(np.zeros(int(batch.row_off[-1]), dtype=np.uint8))
+    # ---- e2e leg: host buffers through the one-shot C-ABI call: graphs up, sweep + walk, per-read-position matches + best ends back
+    # (what include/bsalign_b200_poa_compat.h calls per round).  e2e_rows = the older boundary that returns every row block for the host
+    # traceback of the reference (15 MB per job).
+    match = pin(np.zeros(int(batch.slen.sum()), dtype=np.int32))
     for _ in range(min(args.warmup, 2)):
-        r = poa.poa_rows_batch(ctx, batch, rows=rows)
+        r = poa.poa_align_batch(ctx, batch, match=match)
     barrier()
     t0 = time.perf_counter()
     parts = {"h2d_ms": 0.0, "run_ms": 0.0, "d2h_ms": 0.0}
     for _ in range(args.steps):
-        r = poa.poa_rows_batch(ctx, batch, rows=rows)
+        r = poa.poa_align_batch(ctx, batch, match=match)
         tm2 = ctx.timing()
         for k in parts:
             parts[k] += tm2[k] / args.steps
@@ -274,6 +278,16 @@ def main_poa(args, w, njobs, ncores, rank, local_rank, world):
     e2e_ms = reduce((time.perf_counter() - t0) / args.steps * 1e3, dist.ReduceOp.MAX if world > 1 else None)
     e2e_val = total_cells / (e2e_ms * 1e-3) / 1e9
     assert np.array_equal(r.best, res.best), "e2e and resident runs disagree"
+    assert np.array_equal(r.trace, res.trace) and int((r.trace[:, 7] != 0).sum()) == 0, "device walk: e2e and resident runs disagree"
+    rows = pin(np.zeros(int(batch.row_off[-1]), dtype=np.uint8))
+    rr = poa.poa_rows_batch(ctx, batch, rows=rows)
+    barrier()
+    t0 = time.perf_counter()
+    rr = poa.poa_rows_batch(ctx, batch, rows=rows)
+    barrier()
+    e2e_rows_ms = (time.perf_counter() - t0) * 1e3
+    tm3 = ctx.timing()
+    r.rows = rr.rows
     # ---- parity: distinct prototypes against the oracle (best ends + every row block) --------------------
     checked = None
     if args.check:
@@ -286,6 +300,10 @@ def main_poa(args, w, njobs, ncores, rank, local_rank, world):
             m = ob["done"][int(batch.node_off[i]):int(batch.node_off[i + 1])].astype(bool)
             ok = ok and np.array_equal(r.best[i], ob["best"][i]) and np.array_equal(lin[m], ob["rows"][i][m]) \
                 and np.array_equal(ub[m], ob["ub"][int(batch.node_off[i]):int(batch.node_off[i + 1])][m])
+            import test_gpu_poa as tg          # the walk against the oracle's restatement of alignment2graph_bspoa's decisions
+            om, oo = pj.oracle_backtrace(tg._as_dump_like(protos[i]), ob["rows"][i], ob["ub"][int(batch.node_off[i]):int(batch.node_off[i + 1])],
+                                         int(r.best[i][1]), int(r.best[i][2]))
+            ok = ok and np.array_equal(om, r.match(i)) and np.array_equal(oo, r.trace[i])
         checked = {"jobs": k, "bit_exact": bool(ok)}
     peaks = {}
     try:
@@ -297,7 +315,8 @@ def main_poa(args, w, njobs, ncores, rank, local_rank, world):
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                 "peak_source": "measured (MEASURED_PEAKS.json)" if peaks else "fallback (B200_PROFILING.md)", "traffic": None,
                 "kernel": "poa_sweep_kernel", "launches_per_step": 1, "algorithmic_bytes_per_launch": int(alg_bytes),
-                "kernel_ms_per_launch": sweep_ms / args.steps, "row_updates": nupd, "row_merges": nmrg, "block_bytes": blk}
+                "kernel_ms_per_launch": sweep_ms / args.steps, "row_updates": nupd, "row_merges": nmrg, "block_bytes": blk,
+                "walk_kernel_ms_per_step": walk_ms / args.steps}
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         rr = poa_reference_run(w, args.cpu_sample or ncores, ncores)
@@ -320,8 +339,10 @@ def main_poa(args, w, njobs, ncores, rank, local_rank, world):
                        "timing": "CUDA events on the library stream; max over ranks", "wall_ms_per_step": wall / args.steps * 1e3,
                        "ms_of_dp_per_64_read_job_at_this_batch": step_ms * 39},
             "e2e": {"value": e2e_val, "unit": "GCUPS", "ms_per_step": e2e_ms, "h2d_bytes_per_step": int(tm2["h2d_bytes"]), "d2h_bytes_per_step": int(tm2["d2h_bytes"]),
-                    "device_parts_ms": parts},
-            "gpu_launches": 2 * args.steps, "roofline": roofline, "cpu_baseline": cpu, "clocks": clocks,
+                    "device_parts_ms": parts, "returns": "per-read-position matched node + counts (device-side walk of alignment2graph_bspoa)",
+                    "e2e_rows": {"value": total_cells / world / (e2e_rows_ms * 1e-3) / 1e9 * world, "ms_per_step": e2e_rows_ms, "d2h_bytes_per_step": int(tm3["d2h_bytes"]),
+                                 "returns": "every node row block (host traceback of the reference)"}},
+            "gpu_launches": 4 * args.steps, "roofline": roofline, "cpu_baseline": cpu, "clocks": clocks,
             "parity": {"nonzero_status_jobs": int((r.status != 0).sum()), "score_checksum": int(r.best[:, 0].astype(np.int64).sum()), "checked": checked},
         }))
     ctx.close()

@@ -255,7 +255,8 @@ extern "C" int bsb200_poa_run(bsb200_ctx *ctx, bsb200_poa_batch *b){
 		t.node_off = a.node_off; t.node = a.node; t.reoff = b->d_reoff.as<int32_t>(); t.redge_off = b->d_redge_off.as<uint64_t>();
 		t.rev = b->d_rev.as<int4>(); t.head = a.head; t.tail = a.tail; t.rows = a.rows; t.row_off = a.row_off; t.best = a.best;
 		t.match = b->d_match.as<int32_t>(); t.trace = b->d_trace.as<int32_t>();
-		poa_backtrace_kernel<<<(b->njobs + 31) / 32, 32, 0, st>>>(t);
+		if(b->max_bw == 128 && b->order.empty()) poa_backtrace_kernel<true><<<b->njobs, 32, 0, st>>>(t);   // every job has the default band
+		else poa_backtrace_kernel<false><<<b->njobs, 32, 0, st>>>(t);
 		launches++;
 	}
 	cudaEventRecord(ctx->ev[7], st);
@@ -326,7 +327,7 @@ extern "C" int bsb200_poa_attach_reverse(bsb200_ctx *ctx, bsb200_poa_batch *b, c
 	b->nredges = nj ? redge_off[nj] : 0;
 	const size_t ne = b->nredges;
 	CK(b->d_reoff.reserve((nn + nj) * 4 + 4)); CK(b->d_redge_off.reserve((nj + 1) * 8)); CK(b->d_resrc.reserve(ne * 4 + 4)); CK(b->d_recov.reserve(ne * 4 + 4));
-	CK(b->d_rev.reserve(ne * 16 + 16)); CK(b->d_match.reserve(b->qbytes * 4 + 16)); CK(b->d_trace.reserve(nj * 32 + 32));
+	CK(b->d_rev.reserve(ne * 32 + 32)); CK(b->d_match.reserve(b->qbytes * 4 + 16)); CK(b->d_trace.reserve(nj * 32 + 32));
 	cudaEventRecord(ctx->ev[0], st);
 	if(nj){
 		CK(cudaMemcpyAsync(b->d_reoff.p, reoff, (nn + nj) * 4, cudaMemcpyHostToDevice, st));
@@ -336,7 +337,7 @@ extern "C" int bsb200_poa_attach_reverse(bsb200_ctx *ctx, bsb200_poa_batch *b, c
 			CK(cudaMemcpyAsync(b->d_recov.p, recov, ne * 4, cudaMemcpyHostToDevice, st));
 		}
 		poa_rev_prep_kernel<<<std::min<uint32_t>(b->njobs, (uint32_t)ctx->num_sms * 8), 256, 0, st>>>(b->njobs, b->d_node_off.as<uint64_t>(), b->d_node.as<int2>(),
-			b->d_redge_off.as<uint64_t>(), b->d_resrc.as<int32_t>(), b->d_recov.as<int32_t>(), b->d_rev.as<int4>());
+			b->d_reoff.as<int32_t>(), b->d_redge_off.as<uint64_t>(), b->d_resrc.as<int32_t>(), b->d_recov.as<int32_t>(), b->d_rev.as<int4>());
 	}
 	cudaEventRecord(ctx->ev[1], st);
 	CK(cudaGetLastError());

@@ -10,8 +10,11 @@
  *   b200_end_bspoa_batch(ctx, gs, n)
  *       end_bspoa (bspoa.h:4722-4778) for n BSPOA objects stepped in LOCK-STEP: in round r every object prepares the alignment of
  *       its read r on the host exactly as the reference does (msa_bspoa, simple_cns_bspoa, sel_nodes_bspoa,
- *       prepare_rd_align_bspoa), the n sweeps run as ONE GPU batch, and every object then continues with the reference's
- *       alignment2graph_bspoa.  Everything that is not the sweep is the reference's own code, called in the reference's order.
+ *       prepare_rd_align_bspoa), the n sweeps AND the walk of alignment2graph_bspoa (bspoa.h:2274-2497) run as ONE GPU batch, and
+ *       every object then replays the graph surgery of alignment2graph_bspoa (merge_nodes_bspoa, cpos, connect_rdnode_bspoa) from
+ *       the walk's decisions, in the reference's order.  Only 4 bytes per read position come back from the GPU.
+ *       With -DBSALIGN_B200_POA_HOST_TRACEBACK the row blocks are copied into g->memp instead and the reference's own
+ *       alignment2graph_bspoa runs on them (15 MB per sweep of a 15 kb read).
  *
  * -DBSALIGN_B200_OVERRIDE routes the reference name end_bspoa to the batch driver with n = 1.
  * Programmer errors keep the reference's behaviour: message on stderr + abort().  There is no CPU fallback.
@@ -36,17 +39,21 @@ typedef struct {
 	uint32_t *loc; uint64_t cap_loc;          /* global node id -> local id scratch */
 	uint8_t *rows; uint64_t cap_rows; uint64_t *row_off;
 	int32_t *best, *status;
+	/* reverse edges + what the device-side walk returns */
+	int32_t *reoff; uint64_t nreoff, cap_reoff;
+	int32_t *resrc, *recov; uint64_t nredge, cap_redge; uint64_t *redge_off;
+	int32_t *match; uint64_t cap_match; int32_t *trace;
 } b200_poa_pack_t;
 
 #define B200_GROW(ptr, cap, need, type) do { if((uint64_t)(need) > (cap)){ (cap) = (uint64_t)(need) * 3 / 2 + 64; (ptr) = (type*)realloc((ptr), (cap) * sizeof(type)); \
 	if((ptr) == NULL){ fflush(stdout); fprintf(stderr, " -- Out of memory in %s -- %s:%d --\n", __FUNCTION__, __FILE__, __LINE__); fflush(stderr); abort(); } } } while(0)
 
 static inline b200_poa_pack_t* b200_poa_pack_init(void){ return (b200_poa_pack_t*)calloc(1, sizeof(b200_poa_pack_t)); }
-static inline void b200_poa_pack_clear(b200_poa_pack_t *p){ p->njobs = 0; p->nq = 0; p->nnode = 0; p->neoff = 0; p->nedge = 0; }
+static inline void b200_poa_pack_clear(b200_poa_pack_t *p){ p->njobs = 0; p->nq = 0; p->nnode = 0; p->neoff = 0; p->nedge = 0; p->nreoff = 0; p->nredge = 0; }
 static inline void b200_poa_pack_free(b200_poa_pack_t *p){
 	free(p->par); free(p->qoff); free(p->slen); free(p->node_off); free(p->edge_off); free(p->head); free(p->tail); free(p->queries);
 	free(p->base); free(p->bonus); free(p->rpos); free(p->nct); free(p->eoff); free(p->edst); free(p->loc); free(p->rows); free(p->row_off);
-	free(p->best); free(p->status); free(p);
+	free(p->best); free(p->status); free(p->reoff); free(p->resrc); free(p->recov); free(p->redge_off); free(p->match); free(p->trace); free(p);
 }
 
 /* append the sweep job of g (after prepare_rd_align_bspoa) to the pack: what align_rd_bspoacore would consume */
@@ -59,6 +66,7 @@ static inline void b200_poa_pack_job(b200_poa_pack_t *p, BSPOA *g, BSPOAPar *par
 		p->node_off = (uint64_t*)realloc(p->node_off, 8 * (size_t)nc); p->edge_off = (uint64_t*)realloc(p->edge_off, 8 * (size_t)nc);
 		p->head = (uint32_t*)realloc(p->head, 4 * (size_t)nc); p->tail = (uint32_t*)realloc(p->tail, 4 * (size_t)nc);
 		p->row_off = (uint64_t*)realloc(p->row_off, 8 * (size_t)nc); p->best = (int32_t*)realloc(p->best, 12 * (size_t)nc); p->status = (int32_t*)realloc(p->status, 4 * (size_t)nc);
+		p->redge_off = (uint64_t*)realloc(p->redge_off, 8 * (size_t)nc); p->trace = (int32_t*)realloc(p->trace, 32 * (size_t)nc);
 		p->cap_jobs = nc;
 	}
 	B200_GROW(p->loc, p->cap_loc, g->nodes->size + 1, uint32_t);
@@ -95,6 +103,30 @@ static inline void b200_poa_pack_job(b200_poa_pack_t *p, BSPOA *g, BSPOAPar *par
 		eo[nloc] = (int32_t)ne;
 		p->nedge += ne;
 	}
+	/* reverse edges: the erev lists alignment2graph_bspoa walks (bspoa.h:2319, 2429), with their coverage (bspoa.h:2457-2464) */
+	p->redge_off[j] = p->nredge;
+	B200_GROW(p->reoff, p->cap_reoff, p->nreoff + nloc + 1, int32_t);
+	{
+		int32_t *ro = p->reoff + p->nreoff;
+		uint64_t ne = 0;
+		for(i=0;i<nloc;i++){
+			bspoanode_t *u = ref_bspoanodev(g->nodes, g->sels->buffer[i]);
+			ro[i] = (int32_t)ne;
+			for(eidx=u->erev;eidx;eidx=ref_bspoaedgev(g->edges, eidx)->next){
+				bspoaedge_t *e = ref_bspoaedgev(g->edges, eidx);
+				if(get_bitvec(g->states, e->node) == 0) continue;
+				dummy_cap = p->cap_redge; B200_GROW(p->resrc, dummy_cap, p->nredge + ne + 1, int32_t);
+				B200_GROW(p->recov, p->cap_redge, p->nredge + ne + 1, int32_t);
+				p->resrc[p->nredge + ne] = (int32_t)p->loc[e->node];
+				p->recov[p->nredge + ne] = (int32_t)e->cov;
+				ne ++;
+			}
+		}
+		ro[nloc] = (int32_t)ne;
+		p->nredge += ne;
+	}
+	p->nreoff += nloc + 1;
+	p->redge_off[j + 1] = p->nredge;
 	p->neoff += nloc + 1; p->nnode += nloc;
 	p->head[j] = p->loc[nhead]; p->tail[j] = p->loc[ntail];
 	p->njobs = j + 1;
@@ -113,6 +145,58 @@ static inline void b200_poa_pack_run(bsb200_ctx *ctx, b200_poa_pack_t *p){
 			p->head, p->tail, p->rows, p->best, p->status, NULL)){
 		fflush(stdout); fprintf(stderr, " -- bsalign_b200: %s in %s -- %s:%d --\n", bsb200_last_error(ctx), __FUNCTION__, __FILE__, __LINE__); fflush(stderr);
 		abort();
+	}
+}
+
+/* run every packed sweep AND the walk of alignment2graph_bspoa on the GPU; the row blocks stay in HBM */
+static inline void b200_poa_pack_run_walk(bsb200_ctx *ctx, b200_poa_pack_t *p){
+	if(p->njobs == 0) return;
+	B200_GROW(p->match, p->cap_match, p->nq + 16, int32_t);
+	if(bsb200_poa_align_batch(ctx, p->njobs, p->par, p->queries, p->qoff, p->slen, p->node_off, p->base, p->bonus, p->rpos, p->nct, p->eoff, p->edge_off, p->edst,
+			p->head, p->tail, p->reoff, p->redge_off, p->resrc, p->recov, NULL, p->best, p->status, NULL, p->match, p->trace)){
+		fflush(stdout); fprintf(stderr, " -- bsalign_b200: %s in %s -- %s:%d --\n", bsb200_last_error(ctx), __FUNCTION__, __FILE__, __LINE__); fflush(stderr);
+		abort();
+	}
+}
+
+/* The side effects of alignment2graph_bspoa (bspoa.h:2274-2512) replayed from the device walk of job j: per read position the node it
+ * was aligned to.  merge_nodes_bspoa / cpos in decreasing read position like the reference's walk, then its closing loop. */
+static inline void b200_poa_pack_replay(b200_poa_pack_t *p, uint32_t j, BSPOA *g, u4i rid, u4i rbeg, u4i nhead, u4i ntail){
+	const int32_t *match = p->match + p->qoff[j], *tr = p->trace + 8 * (size_t)j;
+	bspoanode_t *u, *v, *n;
+	int x, cpos;
+	g->maxscr = p->best[3 * (size_t)j];
+	g->maxidx = p->best[3 * (size_t)j + 1] >= 0 ? (int)g->sels->buffer[p->best[3 * (size_t)j + 1]] : -1;
+	g->maxoff = p->best[3 * (size_t)j + 2];
+	if(tr[7] || g->maxidx < 0){   /* the reference itself reads outside a row or never leaves its walk on this input */
+		fflush(stdout); fprintf(stderr, " -- bsalign_b200: inconsistent traceback (flags %d) in %s -- %s:%d --\n", tr[7], __FUNCTION__, __FILE__, __LINE__); fflush(stderr);
+		abort();
+	}
+	nhead = ref_bspoanodev(g->nodes, nhead)->header;
+	ntail = ref_bspoanodev(g->nodes, ntail)->header;
+	u = get_rdnode_bspoa(g, rid, 0);
+	v = get_rdnode_bspoa(g, rid, g->qlen);
+	while(u < v){ u->cpos = 0; u ++; }
+	cpos = ref_bspoanodev(g->nodes, g->maxidx)->cpos;
+	for(x=g->maxoff;x>tr[0]&&x>=0;x--){
+		if(match[x] < 0) continue;                                   /* insertion */
+		n = ref_bspoanodev(g->nodes, g->sels->buffer[match[x]]);
+		u = get_rdnode_bspoa(g, rid, rbeg + g->qb + x);
+		u->cpos = n->cpos;                                             /* bspoa.h:2394-2395 */
+		if(offset_bspoanodev(g->nodes, n) != nhead && offset_bspoanodev(g->nodes, n) != ntail && u->base == n->base){
+			merge_nodes_bspoa(g, n, u);                                /* bspoa.h:2402-2404 */
+		}
+	}
+	v = get_rdnode_bspoa(g, rid, rbeg + g->qlen);                      /* bspoa.h:2500-2511 */
+	connect_rdnode_bspoa(g, rid, rbeg + g->qlen);
+	for(x=g->qlen-1;x>=0;x--){
+		connect_rdnode_bspoa(g, rid, rbeg + x);
+		v --;
+		if(v->cpos){
+			cpos = v->cpos;
+		} else if(x < Int(g->qlen)){
+			v->cpos = cpos;
+		}
 	}
 }
 
@@ -181,13 +265,22 @@ static inline void b200_end_bspoa_batch(bsb200_ctx *ctx, BSPOA **gs, u4i n){
 			slot[k] = p->njobs;
 			b200_poa_pack_job(p, g, g->par, nheads[k], ntails[k]);
 		}
+#ifdef BSALIGN_B200_POA_HOST_TRACEBACK
 		b200_poa_pack_run(ctx, p);
+#else
+		b200_poa_pack_run_walk(ctx, p);
+#endif
 		for(k=0;k<n;k++){
 			BSPOA *g = gs[k];
 			u4i t;
 			if(slot[k] == MAX_U4) continue;
+#ifdef BSALIGN_B200_POA_HOST_TRACEBACK
 			if(slot[k] != MAX_U4 - 1) b200_poa_pack_take(p, slot[k], g);
 			alignment2graph_bspoa(g, g->par, rid, 0, nheads[k], ntails[k], g->maxidx, g->maxoff, NULL);
+#else
+			if(slot[k] != MAX_U4 - 1) b200_poa_pack_replay(p, slot[k], g, rid, 0, nheads[k], ntails[k]);
+			else alignment2graph_bspoa(g, g->par, rid, 0, nheads[k], ntails[k], g->maxidx, g->maxoff, NULL);
+#endif
 			for(t=0;t<g->todels->size;t++){
 				chg_edge_bspoa(g, ref_bspoanodev(g->nodes, g->todels->buffer[t] >> 32), ref_bspoanodev(g->nodes, g->todels->buffer[t] & MAX_U4), -1, NULL);
 			}

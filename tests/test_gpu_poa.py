@@ -113,13 +113,15 @@ def test_poa_dropin_end_bspoa_identical_msa():
     consensus + MSA.  The binary is built from the reference headers where they exist (oracle/Makefile, target dropin) and travels."""
     import os
     import subprocess
-    exe = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "oracle", "_ref", "poa_dropin")
-    if not os.path.exists(exe):
+    ref_dir = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "oracle", "_ref")
+    if not os.path.exists(os.path.join(ref_dir, "poa_dropin")):
         pytest.skip("oracle/_ref/poa_dropin was not built (no reference tree at build time)")
-    for args in (["6", "12", "1500", "3"], ["3", "24", "4000", "5", "0"]):
-        out = subprocess.run([exe] + args, capture_output=True, text=True, timeout=600)
-        assert out.returncode == 0, out.stdout + out.stderr
-        assert "identical=%s/%s" % (args[0], args[0]) in out.stdout, out.stdout
+    # poa_dropin: sweep + walk on the device, graph surgery replayed on the host; poa_dropin_hosttb: row blocks back, the reference's own traceback
+    for name in ("poa_dropin", "poa_dropin_hosttb"):
+        for args in (["6", "12", "1500", "3"], ["3", "24", "4000", "5", "0"]):
+            out = subprocess.run([os.path.join(ref_dir, name)] + args, capture_output=True, text=True, timeout=600)
+            assert out.returncode == 0, out.stdout + out.stderr
+            assert "identical=%s/%s" % (args[0], args[0]) in out.stdout, out.stdout
 
 
 def _as_dump_like(job):
