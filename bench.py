@@ -312,9 +312,17 @@ def main_poa(args, w, njobs, ncores, rank, local_rank, world):
         pass
     peak = float(peaks.get("hbm_gbs", 6650.0))
     achieved = alg_bytes * args.steps / (sweep_ms * 1e-3) / 1e9 if sweep_ms > 0 else 0.0
+    traffic, traffic_src = None, None
+    try:   # DRAM bytes per launch: ncu-measured ratio (profiles/traffic_r1.json) x this launch's algorithmic bytes
+        tr = json.load(open(os.path.join(ROOT, "profiles", "traffic_r1.json")))["poa_sweep_fast_kernel"]
+        traffic = tr["ratio"] * alg_bytes
+        traffic_src = "ncu dram__bytes_read+write / algorithmic = %.3f (%s), scaled to this launch" % (tr["ratio"], tr["capture"])
+    except Exception:
+        pass
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "peak_source": "measured (MEASURED_PEAKS.json)" if peaks else "fallback (B200_PROFILING.md)", "traffic": None,
-                "kernel": "poa_sweep_kernel", "launches_per_step": 1, "algorithmic_bytes_per_launch": int(alg_bytes),
+                "peak_source": "measured (MEASURED_PEAKS.json)" if peaks else "fallback (B200_PROFILING.md)", "traffic": traffic, "traffic_source": traffic_src,
+                "kernel": "poa_sweep_fast_kernel<2,1> (register-resident sweep; jobs with other bands would run poa_sweep_kernel)", "launches_per_step": 1,
+                "algorithmic_bytes_per_launch": int(alg_bytes),
                 "kernel_ms_per_launch": sweep_ms / args.steps, "row_updates": nupd, "row_merges": nmrg, "block_bytes": blk,
                 "walk_kernel_ms_per_step": walk_ms / args.steps}
     cpu = None

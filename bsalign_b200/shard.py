@@ -82,3 +82,40 @@ def run_sharded(batch, kind, bandwidth, align_fn, dist, device="cpu"):
     sub, idx = shard(batch, kind, bandwidth, dist.get_rank(), dist.get_world_size())
     res, st, cg = align_fn(sub)
     return gather_to_rank0(res, st, cg, idx, batch.n, dist, device)
+
+
+# ---- POA sweep jobs (MSA jobs never interact either) -------------------------------------------------
+def job_work(jobs):
+    """Nominal work of a sweep job: out-edges (row updates) x band width."""
+    return np.array([len(j.edst) * int(j.par[0]) for j in jobs], dtype=np.int64)
+
+
+def shard_jobs(jobs, rank, world):
+    """This rank's balanced share of a list of bsalign_b200.poa.SweepJob (and their global indices)."""
+    idx = balanced_partition(job_work(jobs), world)[rank]
+    return [jobs[i] for i in idx], idx
+
+
+def gather_jobs_to_rank0(best, trace, idx, n_total, dist, device="cpu"):
+    """best (n_local,3) int32, trace (n_local,8) int32 or None, idx: global job ids.  Rank 0 returns (best[n_total,3], trace[n_total,8])."""
+    import torch
+    world, rank = dist.get_world_size(), dist.get_rank()
+    tr = trace if trace is not None else np.zeros((len(idx), 8), dtype=np.int32)
+    rec = np.concatenate([idx.astype(np.int64)[:, None], best.astype(np.int64), tr.astype(np.int64)], axis=1)
+    size = torch.tensor([rec.shape[0]], dtype=torch.int64, device=device)
+    sizes = [torch.zeros(1, dtype=torch.int64, device=device) for _ in range(world)]
+    dist.all_gather(sizes, size)
+    mx = int(max(s.item() for s in sizes))
+    rec_t = torch.zeros((max(mx, 1), 12), dtype=torch.int64, device=device)
+    rec_t[:rec.shape[0]] = torch.from_numpy(rec).to(device)
+    rec_all = [torch.zeros_like(rec_t) for _ in range(world)] if rank == 0 else None
+    dist.gather(rec_t, rec_all, dst=0)
+    if rank != 0:
+        return None
+    ob = np.zeros((n_total, 3), dtype=np.int32)
+    ot = np.zeros((n_total, 8), dtype=np.int32)
+    for r in range(world):
+        a = rec_all[r][:int(sizes[r].item())].cpu().numpy()
+        ob[a[:, 0]] = a[:, 1:4]
+        ot[a[:, 0]] = a[:, 4:12]
+    return ob, ot

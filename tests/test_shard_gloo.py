@@ -53,3 +53,35 @@ def test_sharded_run_equals_single_process():
         p.join(120)
         assert p.exitcode == 0
     assert q.get(timeout=5) is True
+
+
+def _poa_worker(rank, world, port, q):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    import poa_jobs as pj
+    from bsalign_b200 import poa, synth_poa
+    jobs = [synth_poa.make_sweep_job(40 + i, tlen=300 + 40 * (i % 5)) for i in range(11)]
+    mine, idx = shard.shard_jobs(jobs, rank, world)
+    r = pj.oracle_sweep_batch(poa.SweepBatch(mine), nthreads=1, want_rows=False)   # the oracle stands in for the GPU sweep (a test)
+    out = shard.gather_jobs_to_rank0(r["best"], None, idx, len(jobs), dist)
+    if rank == 0:
+        exp = pj.oracle_sweep_batch(poa.SweepBatch(jobs), nthreads=1, want_rows=False)
+        q.put(bool(np.array_equal(out[0], exp["best"])))
+    dist.destroy_process_group()
+
+
+def test_sharded_poa_jobs_equal_single_process():
+    work = shard.job_work
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        port = s.getsockname()[1]
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_poa_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    for p in procs:
+        p.join(120)
+        assert p.exitcode == 0
+    assert q.get(timeout=5) is True
