@@ -356,16 +356,32 @@ static int launch_epi8_forward(bsb200_ctx *ctx, Epi8Args a, uint32_t npairs){
 		CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, threads, smem));
 		if(per_sm < 1) per_sm = 1;
 		uint32_t groups = (threads / 32) * best_gpw;
-		uint32_t grid = std::min<uint32_t>((npairs + groups - 1) / groups, (uint32_t)(ctx->num_sms * per_sm));
+		uint32_t grid = (npairs + groups - 1) / groups;
+		// a grid that seats every pair at once is rounded up to whole CTAs-per-SM: groups race for pairs (atomic counter), so each SM ends
+		// up with about the same number of pairs instead of some SMs carrying one CTA more than the others (config 3: 625 CTAs on 148 SMs)
+		if(grid > (uint32_t)ctx->num_sms) grid = (grid + ctx->num_sms - 1) / ctx->num_sms * ctx->num_sms;
+		grid = std::min<uint32_t>(grid, (uint32_t)(ctx->num_sms * per_sm));
 		if(grid == 0) grid = 1;
 		kernel<<<grid, threads, smem, ctx->stream>>>(a);
 		CK(cudaGetLastError());
 		return 0;
 	};
-	if(best_gpw < 4){
-		if constexpr (ANCH) return go(epi8_forward_kernel<PW, FAST, true, true>);
-		else { ctx->err = "internal: narrow warps without anchors"; return -1; }
+	// batches that leave an SM with at most two warps per scheduler are bound by the latency of the row loop's dependency chain, not
+	// by ALU throughput: they take the LAT instantiation (short F chain, loads of the next chunk in flight; affine gaps only)
+	bool lat = false;
+	if constexpr (FAST && PW == 1){
+		const uint64_t seated = std::min<uint64_t>(npairs, (uint64_t)best_groups * ctx->num_sms);
+		const uint64_t warps_per_sm = (seated + (uint64_t)best_gpw * ctx->num_sms - 1) / ((uint64_t)best_gpw * ctx->num_sms);
+		lat = warps_per_sm <= 8;
+		if(const char *ev = getenv("BSB200_LAT")) lat = atoi(ev) != 0;   // experiments
 	}
+	if(best_gpw < 4){
+		if constexpr (ANCH){
+			if constexpr (FAST && PW == 1){ if(lat) return go(epi8_forward_kernel<PW, FAST, true, true, true>); }
+			return go(epi8_forward_kernel<PW, FAST, true, true>);
+		} else { ctx->err = "internal: narrow warps without anchors"; return -1; }
+	}
+	if constexpr (FAST && PW == 1){ if(lat) return go(epi8_forward_kernel<PW, FAST, ANCH, false, true>); }
 	return go(epi8_forward_kernel<PW, FAST, ANCH, false>);
 }
 

@@ -88,7 +88,11 @@ __device__ __forceinline__ uint32_t not_fma(uint32_t x, uint32_t m1){ return x *
 // FAST=true (all gap costs <= 0): u, z, h, f, g and the new u are kept BIASED by +128, so that a two-sided saturating
 // add of an unbiased term is ONE instruction (VIADDMNMX.RELU: min(a+b,255) then max(.,0)); bounds that cannot bind
 // are dropped: e,q <= 0 so e+u never exceeds 127; x-h <= 0 because h >= e+u and ge <= 0; h+goe and f+ge cannot exceed 127.
-template<int PW, bool FAST, bool PASS2>
+// LAT=true (FAST, PW == 1; chosen for batches that leave an SM with a handful of warps, where the row loop is bound by
+// the latency of the F chain and not by ALU throughput): the gap-open candidate is taken from max(ev, z) instead of
+// max(ev, z, f).  Identical values (f + goe <= f + ge because go <= 0, and the lower clamp sits under both), but the
+// loop-carried chain f -> h -> y -> f1 -> f (4 DPX ops) becomes f -> f1 -> f (2); pass 2 pays one more instruction.
+template<int PW, bool FAST, bool PASS2, bool LAT = false>
 __device__ __forceinline__ void dp_step(RowState &s, uint32_t u, uint32_t e, uint32_t q, uint32_t z,
 		uint32_t GE, uint32_t GOE, uint32_t GP, uint32_t GQP, uint32_t NGOQ, uint32_t M1, uint32_t Z0, uint32_t &un, uint32_t &en, uint32_t &qn){
 	if(FAST){
@@ -101,6 +105,23 @@ __device__ __forceinline__ void dp_step(RowState &s, uint32_t u, uint32_t e, uin
 			h = smax(smax3(ev, z, qv), smax(s.f, s.g));
 		} else h = smax3(ev, z, s.f);
 		const uint32_t cu = not_fma(u, M1);
+		if(LAT && PW == 1){
+			const uint32_t hz = smax(ev, z);                                        // the part of h that does not hang on the F chain
+			const uint32_t yz = __viaddmax_s16x2(hz, __vadd2(GOE, C129), C129);
+			const uint32_t f1 = __viaddmax_s16x2(s.f, __vadd2(GE, C129), yz);
+			if(PASS2){
+				h = smax(hz, s.f);
+				const uint32_t ch = not_fma(h, M1);
+				un = __viaddmin_s16x2_relu(h, s.nv, C255);
+				s.nv = __viaddmin_s16x2(__viaddmax_s16x2(u, ch, kLO), kONE, 0x00800080u);
+				uint32_t x1 = __viaddmax_s16x2(ev, __vadd2(GE, kONE), kONE);
+				en = __viaddmax_s16x2(x1, ch, GOE);
+				s.u = u;
+				s.h = __viaddmax_s16x2(h, __vadd2(GOE, C129), C129);               // only the last step's value is read (row tail)
+			}
+			s.f = __viaddmin_s16x2_relu(f1, cu, C255);
+			return;
+		}
 		if(PASS2){
 			const uint32_t ch = not_fma(h, M1);
 			un = __viaddmin_s16x2_relu(h, s.nv, C255);                              // subs(h, v) + 128
@@ -184,7 +205,9 @@ __device__ __forceinline__ int group_getscore(const int8_t *sU, const int32_t *s
 
 // ANCH: also write the sub-lane anchors (lanes longer than 64 steps; see common.cuh)
 // NARROW: fewer than 4 groups per warp (very wide bands); the normal kernels keep compile-time full-warp masks
-template<int PW, bool FAST, bool ANCH, bool NARROW>
+// LAT: latency-bound batches (a few warps per SM): short F chain (dp_step) and the next chunk's loads issued before the
+// current chunk's arithmetic
+template<int PW, bool FAST, bool ANCH, bool NARROW, bool LAT = false>
 __global__ void __launch_bounds__(kFwdThreads) epi8_forward_kernel(const Epi8Args a){
 	extern __shared__ __align__(16) uint8_t smem_raw[];
 	const int lane = threadIdx.x & 31;
@@ -482,40 +505,91 @@ __global__ void __launch_bounds__(kFwdThreads) epi8_forward_kernel(const Epi8Arg
 			#define P1STEP(K, LEFT) { if((K) < (LEFT)){ \
 				uint32_t z = prmt(T32, ZPAD, ent_sel<K>(cs4)); \
 				if((K) == 0 && c == 0) z = (z & zmask) | zor; \
-				dp_step<PW, FAST, false>(st, FAST ? entz<K>(cu4) : ent<K>(cu4), ent<K>(ce4), ent<K>(cq4), z, GE, GOE, GP, GQP, NGOQ, M1, Z0, dum0, dum1, dum2); } }
+				dp_step<PW, FAST, false, LAT>(st, FAST ? entz<K>(cu4) : ent<K>(cu4), ent<K>(ce4), ent<K>(cq4), z, GE, GOE, GP, GQP, NGOQ, M1, Z0, dum0, dum1, dum2); } }
+			#define P1BODY(LEFT) { P1STEP(0, LEFT) P1STEP(1, LEFT) P1STEP(2, LEFT) P1STEP(3, LEFT) P1STEP(4, LEFT) P1STEP(5, LEFT) P1STEP(6, LEFT) P1STEP(7, LEFT) }
 			#define P1CHUNK(LEFT) { \
 				const uint4 cu4 = *(const uint4*)(rU + 128 * c), cs4 = *(const uint4*)(rC + 128 * c); \
 				uint4 ce4 = cu4, cq4 = cu4; \
 				if(PW >= 1) ce4 = *(const uint4*)(rE + 128 * c); \
 				if(PW == 2) cq4 = *(const uint4*)(rQ + 128 * c); \
-				P1STEP(0, LEFT) P1STEP(1, LEFT) P1STEP(2, LEFT) P1STEP(3, LEFT) P1STEP(4, LEFT) P1STEP(5, LEFT) P1STEP(6, LEFT) P1STEP(7, LEFT) }
+				P1BODY(LEFT) }
 			uint32_t c = 0;
-			_Pragma("unroll 1")   // one chunk per iteration keeps the loop body in the instruction cache (measured: -10% time)
-			for(;c<nfull;c++) P1CHUNK(8u)
-			if(c < nchunk){ const uint32_t left = W - 8 * c; P1CHUNK(left) }
+			if(LAT){
+				// chunk c + 1 is in flight while chunk c is computed
+				uint4 nu4 = *(const uint4*)rU, ns4 = *(const uint4*)rC, ne4 = nu4, nq4 = nu4;
+				if(PW >= 1) ne4 = *(const uint4*)rE;
+				if(PW == 2) nq4 = *(const uint4*)rQ;
+				_Pragma("unroll 1")
+				for(;c<nfull;c++){
+					const uint4 cu4 = nu4, cs4 = ns4, ce4 = ne4, cq4 = nq4;
+					const uint32_t cn = c + 1 < nchunk ? c + 1 : c;
+					nu4 = *(const uint4*)(rU + 128 * cn); ns4 = *(const uint4*)(rC + 128 * cn);
+					if(PW >= 1) ne4 = *(const uint4*)(rE + 128 * cn);
+					if(PW == 2) nq4 = *(const uint4*)(rQ + 128 * cn);
+					P1BODY(8u)
+				}
+				if(c < nchunk){ const uint4 cu4 = nu4, cs4 = ns4, ce4 = ne4, cq4 = nq4; const uint32_t left = W - 8 * c; P1BODY(left) }
+			} else {
+				_Pragma("unroll 1")   // one chunk per iteration keeps the loop body in the instruction cache (measured: -10% time)
+				for(;c<nfull;c++) P1CHUNK(8u)
+				if(c < nchunk){ const uint32_t left = W - 8 * c; P1CHUNK(left) }
+			}
 			#undef P1CHUNK
+			#undef P1BODY
 			#undef P1STEP
 		}
-		sF[A] = (int8_t)(lo16(st.f) - UB); sF[B] = (int8_t)(hi16(st.f) - UB);
-		if(PW == 2){ sF[16 + A] = (int8_t)(lo16(st.g) - UB); sF[16 + B] = (int8_t)(hi16(st.g) - UB); }
-		__syncwarp(amask);
-		// ---- F penetration (bsalign.h:2639-2652): exact 16-step scalar scan, every thread redundantly ---
+		// ---- F penetration (bsalign.h:2639-2652) ---------------------------------------------------------
+		// The reference hands F across the 16 blocks with a scalar scan: fin[0] = -63, fin[j+1] = max(fend[j], fin[j] + a[j]) with
+		// a[j] = W*ge - (ub[j+1] - ub[j]), the sum truncated to int8 when it is taken.  Without the truncation this is a max-plus
+		// recurrence, i.e. a prefix "product" of the maps x -> max(x + a, m): composed per thread (two lanes), scanned over the
+		// group's 8 threads with shuffles (3 steps) instead of 15 dependent steps with shared-memory loads.  A taken sum always
+		// exceeds a stored int8, so truncation can only bite when a sum exceeds 127: the group votes on that and only then runs
+		// the literal scan.
 		{
-			int finA = kEpi8Min, finB = kEpi8Min, ginA = kEpi8Min, ginB = kEpi8Min;
-			int tW = (int)W * ge1, tW2 = (int)W * ge2;
-			int ubp = sUB[0], ubn = sUB[1];
-			int s = tW + kEpi8Min - (ubn - ubp), s2 = tW2 + kEpi8Min - (ubn - ubp);
-			#pragma unroll
-			for(int j=1;j<kLanes;j++){
-				int fj = sF[j - 1];
-				if(fj < s) fj = (int)(int8_t)s;
-				int gj = 0;
-				if(PW == 2){ gj = sF[16 + j - 1]; if(gj < s2) gj = (int)(int8_t)s2; }
-				if(j == A){ finA = fj; ginA = gj; }
-				if(j == B){ finB = fj; ginB = gj; }
-				ubp = ubn; ubn = sUB[j + 1];
-				s = tW + fj - (ubn - ubp);
-				if(PW == 2) s2 = tW2 + gj - (ubn - ubp);
+			const int ub0 = sUB[A], ub1 = sUB[B], ub2 = sUB[B + 1];
+			constexpr int NEG = -(1 << 28);
+			auto scan = [&](uint32_t fpk, int tW, int &finA, int &finB) -> bool {
+				const int feA = lo16(fpk) - UB, feB = hi16(fpk) - UB;
+				const int aA = tW - (ub1 - ub0), aB = tW - (ub2 - ub1);
+				int GA = aA + aB, GM = max(feA + aB, feB);
+				#pragma unroll
+				for(int d=1;d<kGroup;d<<=1){
+					const int pA = __shfl_up_sync(gmask, GA, d, kGroup), pM = __shfl_up_sync(gmask, GM, d, kGroup);
+					if(t >= d){ GM = max(pM + GA, GM); GA += pA; }
+				}
+				int PA = __shfl_up_sync(gmask, GA, 1, kGroup), PM = __shfl_up_sync(gmask, GM, 1, kGroup);
+				if(t == 0){ PA = 0; PM = NEG; }
+				finA = max(kEpi8Min + PA, PM);
+				const int sA = finA + aA;
+				finB = max(sA, feA);
+				const int sB = finB + aB;
+				return max(sA, sB) > 127;
+			};
+			int finA, finB, ginA = kEpi8Min, ginB = kEpi8Min;
+			bool ovf = scan(st.f, (int)W * ge1, finA, finB);
+			if(PW == 2) ovf |= scan(st.g, (int)W * ge2, ginA, ginB);
+			if(__any_sync(gmask, ovf)){
+				// literal 16-step scan with the int8 truncation, every thread redundantly
+				sF[A] = (int8_t)(lo16(st.f) - UB); sF[B] = (int8_t)(hi16(st.f) - UB);
+				if(PW == 2){ sF[16 + A] = (int8_t)(lo16(st.g) - UB); sF[16 + B] = (int8_t)(hi16(st.g) - UB); }
+				__syncwarp(gmask);
+				finA = finB = ginA = ginB = kEpi8Min;
+				int tW = (int)W * ge1, tW2 = (int)W * ge2;
+				int ubp = sUB[0], ubn = sUB[1];
+				int s = tW + kEpi8Min - (ubn - ubp), s2 = tW2 + kEpi8Min - (ubn - ubp);
+				#pragma unroll 1
+				for(int j=1;j<kLanes;j++){
+					int fj = sF[j - 1];
+					if(fj < s) fj = (int)(int8_t)s;
+					int gj = 0;
+					if(PW == 2){ gj = sF[16 + j - 1]; if(gj < s2) gj = (int)(int8_t)s2; }
+					if(j == A){ finA = fj; ginA = gj; }
+					if(j == B){ finB = fj; ginB = gj; }
+					ubp = ubn; ubn = sUB[j + 1];
+					s = tW + fj - (ubn - ubp);
+					if(PW == 2) s2 = tW2 + gj - (ubn - ubp);
+				}
+				__syncwarp(gmask);
 			}
 			st.f = pk(finA + UB, finB + UB); st.g = pk(ginA + UB, ginB + UB);
 		}
@@ -526,12 +600,14 @@ __global__ void __launch_bounds__(kFwdThreads) epi8_forward_kernel(const Epi8Arg
 			#define P2STEP(K, LEFT) { if((K) < (LEFT)){ \
 				uint32_t z = prmt(T32, ZPAD, ent_sel<K>(cs4)); \
 				if((K) == 0 && c == 0) z = (z & zmask) | zor; \
-				dp_step<PW, FAST, true>(st, FAST ? entz<K>(cu4) : ent<K>(cu4), ent<K>(ce4), ent<K>(cq4), z, GE, GOE, GP, GQP, NGOQ, M1, Z0, un[K], en[K], qn[K]); } }
+				dp_step<PW, FAST, true, LAT>(st, FAST ? entz<K>(cu4) : ent<K>(cu4), ent<K>(ce4), ent<K>(cq4), z, GE, GOE, GP, GQP, NGOQ, M1, Z0, un[K], en[K], qn[K]); } }
 			#define P2CHUNK(LEFT, RAGGED) { \
 				const uint4 cu4 = *(const uint4*)(rU + 128 * c), cs4 = *(const uint4*)(rC + 128 * c); \
 				uint4 ce4 = cu4, cq4 = cu4; \
 				if(PW >= 1) ce4 = *(const uint4*)(rE + 128 * c); \
 				if(PW == 2) cq4 = *(const uint4*)(rQ + 128 * c); \
+				P2BODY(LEFT, RAGGED) }
+			#define P2BODY(LEFT, RAGGED) { \
 				uint32_t un[8], en[8], qn[8]; \
 				if(RAGGED){ _Pragma("unroll") for(int k=0;k<8;k++){ un[k] = 0; en[k] = 0; qn[k] = 0; } } \
 				P2STEP(0, LEFT) P2STEP(1, LEFT) P2STEP(2, LEFT) P2STEP(3, LEFT) P2STEP(4, LEFT) P2STEP(5, LEFT) P2STEP(6, LEFT) P2STEP(7, LEFT) \
@@ -541,10 +617,27 @@ __global__ void __launch_bounds__(kFwdThreads) epi8_forward_kernel(const Epi8Arg
 				if(PW >= 1) *(uint4*)(rE + 128 * c) = make_uint4(pack2(en[0], en[1]), pack2(en[2], en[3]), pack2(en[4], en[5]), pack2(en[6], en[7])); \
 				if(PW == 2) *(uint4*)(rQ + 128 * c) = make_uint4(pack2(qn[0], qn[1]), pack2(qn[2], qn[3]), pack2(qn[4], qn[5]), pack2(qn[6], qn[7])); }
 			uint32_t c = 0;
-			_Pragma("unroll 1")
-			for(;c<nfull;c++) P2CHUNK(8u, false)
-			if(c < nchunk){ const uint32_t left = W - 8 * c; P2CHUNK(left, true) }
+			if(LAT){
+				uint4 nu4 = *(const uint4*)rU, ns4 = *(const uint4*)rC, ne4 = nu4, nq4 = nu4;
+				if(PW >= 1) ne4 = *(const uint4*)rE;
+				if(PW == 2) nq4 = *(const uint4*)rQ;
+				_Pragma("unroll 1")
+				for(;c<nfull;c++){
+					const uint4 cu4 = nu4, cs4 = ns4, ce4 = ne4, cq4 = nq4;
+					const uint32_t cn = c + 1 < nchunk ? c + 1 : c;   // (without a ragged chunk the last iteration re-reads its own chunk before writing it)
+					nu4 = *(const uint4*)(rU + 128 * cn); ns4 = *(const uint4*)(rC + 128 * cn);
+					if(PW >= 1) ne4 = *(const uint4*)(rE + 128 * cn);
+					if(PW == 2) nq4 = *(const uint4*)(rQ + 128 * cn);
+					P2BODY(8u, false)
+				}
+				if(c < nchunk){ const uint4 cu4 = nu4, cs4 = ns4, ce4 = ne4, cq4 = nq4; const uint32_t left = W - 8 * c; P2BODY(left, true) }
+			} else {
+				_Pragma("unroll 1")
+				for(;c<nfull;c++) P2CHUNK(8u, false)
+				if(c < nchunk){ const uint32_t left = W - 8 * c; P2CHUNK(left, true) }
+			}
 			#undef P2CHUNK
+			#undef P2BODY
 			#undef P2STEP
 		}
 		// ---- tail (bsalign.h:2618-2636) ------------------------------------------------------------------

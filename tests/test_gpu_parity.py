@@ -148,6 +148,20 @@ def test_wide_bands(ctx):
         assert_same(ctx.epi8_batch(b, mode, bw, M26, *gaps), exp, ecg, tag=("wide", qlen, mode, bw))
 
 
+def test_latency_and_throughput_variants(ctx):
+    """Affine-gap batches that leave an SM with a few warps take the LAT instantiation of the forward kernel (short F
+    chain, prefetched chunks); BSB200_LAT forces one or the other: both must give the oracle's answer."""
+    try:
+        for mode, bw, qlen, n in [(0, 0, 300, 40), (1, 64, 500, 40), (2, 128, 700, 24), (0, 0, 1000, 16), (1, 512, 3000, 6), (0, 0, 2100, 4)]:
+            b = synth.make_pairs(n, qlen, seed=31 * qlen + mode)
+            exp, ecg, _ = ck.oracle_batch("epi8", b, mode, bw, M26, (-3, -2, 0, 0), nthreads=8)
+            for lat in ("0", "1"):
+                os.environ["BSB200_LAT"] = lat
+                assert_same(ctx.epi8_batch(b, mode, bw, M26, -3, -2, 0, 0), exp, ecg, tag=("lat", lat, mode, bw, qlen))
+    finally:
+        os.environ.pop("BSB200_LAT", None)
+
+
 def test_dense_fetch_equals_scattered_fetch(ctx):
     b = synth.make_pairs(500, 200, seed=99)
     a = ctx.epi8_batch(b, 1, 64, M26, -3, -2, 0, 0)
