@@ -15,7 +15,7 @@ import numpy as np
 from .synth import PairBatch
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libbsalign_b200.so")
+LIB_PATH = os.environ.get("BSB200_LIB") or os.path.join(_HERE, "libbsalign_b200.so")   # BSB200_LIB: development builds
 
 SEQALIGN_MODE_GLOBAL = 0   # bsalign.h:30
 SEQALIGN_MODE_OVERLAP = 1  # bsalign.h:31

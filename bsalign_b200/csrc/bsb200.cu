@@ -326,7 +326,7 @@ extern "C" bsb200_batch *bsb200_batch_upload(bsb200_ctx *ctx, int kind, uint64_t
 }
 
 template<int PW, bool FAST, bool ANCH>
-static int launch_epi8_forward(bsb200_ctx *ctx, Epi8Args a, uint32_t npairs){
+static int launch_epi8_forward(bsb200_ctx *ctx, Epi8Args a, uint32_t npairs, bool full){
 	// CTA shape: as many groups per SM as the shared memory allows.  Normally 128 threads = 4 warps x 4 groups; a wide band
 	// (tens of KB per group) does better with one-warp CTAs that run fewer than 4 groups each.
 	const size_t sm_bytes = ctx->smem_optin + 1024;   // per-SM shared memory ~ opt-in maximum per block + its reserved KB
@@ -381,15 +381,19 @@ static int launch_epi8_forward(bsb200_ctx *ctx, Epi8Args a, uint32_t npairs){
 			return go(epi8_forward_kernel<PW, FAST, true, true>);
 		} else { ctx->err = "internal: narrow warps without anchors"; return -1; }
 	}
-	if constexpr (FAST && PW == 1){ if(lat) return go(epi8_forward_kernel<PW, FAST, ANCH, false, true>); }
+	if constexpr (FAST && PW == 1){
+		// full-band batches (bandwidth 0) never move their band: instantiation without the shift / steering code
+		if(full) return lat ? go(epi8_forward_kernel<PW, FAST, ANCH, false, true, true>) : go(epi8_forward_kernel<PW, FAST, ANCH, false, false, true>);
+		if(lat) return go(epi8_forward_kernel<PW, FAST, ANCH, false, true>);
+	}
 	return go(epi8_forward_kernel<PW, FAST, ANCH, false>);
 }
 
 template<bool FAST, bool ANCH>
-static int launch_epi8_forward_pw(bsb200_ctx *ctx, const Epi8Args &a, uint32_t npairs, int pw){
-	if(pw == 2) return launch_epi8_forward<2, FAST, ANCH>(ctx, a, npairs);
-	if(pw == 1) return launch_epi8_forward<1, FAST, ANCH>(ctx, a, npairs);
-	return launch_epi8_forward<0, FAST, ANCH>(ctx, a, npairs);
+static int launch_epi8_forward_pw(bsb200_ctx *ctx, const Epi8Args &a, uint32_t npairs, int pw, bool full){
+	if(pw == 2) return launch_epi8_forward<2, FAST, ANCH>(ctx, a, npairs, full);
+	if(pw == 1) return launch_epi8_forward<1, FAST, ANCH>(ctx, a, npairs, full);
+	return launch_epi8_forward<0, FAST, ANCH>(ctx, a, npairs, full);
 }
 
 template<int WR>
@@ -463,8 +467,9 @@ extern "C" int bsb200_batch_run(bsb200_ctx *ctx, bsb200_batch *b){
 			const bool anch = epi8_use_anchors(b->max_bw / 16);
 			a.gpw = 4;
 			int rc;
-			if(fast) rc = anch ? launch_epi8_forward_pw<true, true>(ctx, a, np, b->pw) : launch_epi8_forward_pw<true, false>(ctx, a, np, b->pw);
-			else rc = anch ? launch_epi8_forward_pw<false, true>(ctx, a, np, b->pw) : launch_epi8_forward_pw<false, false>(ctx, a, np, b->pw);
+			const bool full = b->bandwidth == 0 && !getenv("BSB200_NOFULL");   // (BSB200_NOFULL: tests run the general instantiation on full bands too)
+			if(fast) rc = anch ? launch_epi8_forward_pw<true, true>(ctx, a, np, b->pw, full) : launch_epi8_forward_pw<true, false>(ctx, a, np, b->pw, full);
+			else rc = anch ? launch_epi8_forward_pw<false, true>(ctx, a, np, b->pw, full) : launch_epi8_forward_pw<false, false>(ctx, a, np, b->pw, full);
 			if(rc) return rc;
 			ctx->timing.forward_launches++;
 			CK(cudaEventRecord(evs[wi * 4 + 1], st));

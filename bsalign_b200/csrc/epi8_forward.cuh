@@ -207,7 +207,9 @@ __device__ __forceinline__ int group_getscore(const int8_t *sU, const int32_t *s
 // NARROW: fewer than 4 groups per warp (very wide bands); the normal kernels keep compile-time full-warp masks
 // LAT: latency-bound batches (a few warps per SM): short F chain (dp_step) and the next chunk's loads issued before the
 // current chunk's arithmetic
-template<int PW, bool FAST, bool ANCH, bool NARROW, bool LAT = false>
+// FULL: bandwidth 0, every pair's band covers its whole query: the band never moves (bsalign.h:3932 needs rbeg + bw < qlen),
+// so the shift and steering code is left out of the instantiation
+template<int PW, bool FAST, bool ANCH, bool NARROW, bool LAT = false, bool FULL = false>
 __global__ void __launch_bounds__(kFwdThreads) epi8_forward_kernel(const Epi8Args a){
 	extern __shared__ __align__(16) uint8_t smem_raw[];
 	const int lane = threadIdx.x & 31;
@@ -341,11 +343,11 @@ __global__ void __launch_bounds__(kFwdThreads) epi8_forward_kernel(const Epi8Arg
 		const uint32_t tb = tb_next;
 		if(have && row + 1 < tlen) tb_next = ts[row + 1];
 		int rh;
-		if(mov && rbeg + bw < qlen){ // bsalign.h:3932-3946
+		if(!FULL && mov && rbeg + bw < qlen){ // bsalign.h:3932-3946
 			int lim = (int)qlen - (int)(rbeg + bw); if(lim < 0) lim = 0;
 			if((uint32_t)lim < mov) mov = (uint32_t)lim;
 		} else mov = 0;
-		if(mov){
+		if(!FULL && mov){
 			rh = (mov - 1 < bw) ? group_getscore(sU, sUB, W, mov - 1, t, UB) : kScoreMin;
 			if(mov - 1 >= bw) stflag |= 1;
 		} else {
@@ -355,7 +357,7 @@ __global__ void __launch_bounds__(kFwdThreads) epi8_forward_kernel(const Epi8Arg
 			else { uint32_t c1 = (uint32_t)go1 + (uint32_t)ge1 * row, c2 = (uint32_t)go2 + (uint32_t)ge2 * row; rh = (int)(c1 > c2 ? c1 : c2); }
 		}
 		// ---- band shift (bsalign.h:2244-2392) ----------------------------------------------------------
-		if(mov){
+		if(!FULL && mov){
 			if(mov >= bw){
 				for(uint32_t i=0;i<IB/16;i++){
 					uint32_t xA = rbeg + mov + A * W + i, xB = xA + W;
@@ -413,9 +415,32 @@ __global__ void __launch_bounds__(kFwdThreads) epi8_forward_kernel(const Epi8Arg
 						}
 					};
 					#undef WOFF
-					slide((uint8_t*)rU); slide((uint8_t*)rC);
-					if(PW >= 1) slide((uint8_t*)rE);
-					if(PW == 2) slide((uint8_t*)rQ);
+					// shifts by one or two cells (what band_mov asks for; larger ones only come from the global-mode steering):
+					// whole chunks, 128 bits per access, the shift as a clamped funnel over neighbouring words (16 or 32 bits)
+					auto slide12 = [&](uint8_t *r){
+						const uint32_t nC = IB / 128, sh = 16 * mr;
+						uint4 cur = *(const uint4*)r;
+						_Pragma("unroll 1")
+						for(uint32_t c=0;c<nC;c++){
+							uint4 nxt = cur;
+							if(c + 1 < nC) nxt = *(const uint4*)(r + 128 * (c + 1));
+							else nxt.x = cur.w;
+							uint4 o;
+							o.x = __funnelshift_rc(cur.x, cur.y, sh); o.y = __funnelshift_rc(cur.y, cur.z, sh);
+							o.z = __funnelshift_rc(cur.z, cur.w, sh); o.w = __funnelshift_rc(cur.w, nxt.x, sh);
+							*(uint4*)(r + 128 * c) = o;
+							cur = nxt;
+						}
+					};
+					if(mr <= 2){
+						slide12((uint8_t*)rU); slide12((uint8_t*)rC);
+						if(PW >= 1) slide12((uint8_t*)rE);
+						if(PW == 2) slide12((uint8_t*)rQ);
+					} else {
+						slide((uint8_t*)rU); slide((uint8_t*)rC);
+						if(PW >= 1) slide((uint8_t*)rE);
+						if(PW == 2) slide((uint8_t*)rQ);
+					}
 					// entry k of a saved first chunk: byte pair (A, B)
 					auto pairA = [](const uint4 &c4, uint32_t k){ uint32_t w = (k >> 1) == 0 ? c4.x : (k >> 1) == 1 ? c4.y : (k >> 1) == 2 ? c4.z : c4.w; return (w >> ((k & 1) * 16)) & 0xffu; };
 					auto pairB = [](const uint4 &c4, uint32_t k){ uint32_t w = (k >> 1) == 0 ? c4.x : (k >> 1) == 1 ? c4.y : (k >> 1) == 2 ? c4.z : c4.w; return (w >> ((k & 1) * 16 + 8)) & 0xffu; };
@@ -618,6 +643,9 @@ __global__ void __launch_bounds__(kFwdThreads) epi8_forward_kernel(const Epi8Arg
 				if(PW == 2) *(uint4*)(rQ + 128 * c) = make_uint4(pack2(qn[0], qn[1]), pack2(qn[2], qn[3]), pack2(qn[4], qn[5]), pack2(qn[6], qn[7])); }
 			uint32_t c = 0;
 			if(LAT){
+				// compiler barrier: chunk 0 is loaded afresh.  Without it nvcc 12.9 re-uses pass 1's first loads across the pass-1 loop
+				// and the <1, FAST, ANCH, ., LAT> instantiation came out wrong (every score; caught by test_wide_bands)
+				asm volatile("" ::: "memory");
 				uint4 nu4 = *(const uint4*)rU, ns4 = *(const uint4*)rC, ne4 = nu4, nq4 = nu4;
 				if(PW >= 1) ne4 = *(const uint4*)rE;
 				if(PW == 2) nq4 = *(const uint4*)rQ;
@@ -704,7 +732,7 @@ __global__ void __launch_bounds__(kFwdThreads) epi8_forward_kernel(const Epi8Arg
 			if(t < 5) *(uint4*)(meta + (size_t)kMetaInts * (row + 1) + 4 * t) = *(const uint4*)(sUB + 4 * t);
 		}
 		// ---- adaptive band steering (bsalign.h:3331-3349, 4005-4021) -------------------------------------
-		{
+		if(!FULL){
 			int rbx = 0;
 			if(!(row <= W * kLanes / 4) && !(rbeg + W * kLanes >= qlen)){
 				int noisy = 0, p0 = sUB[0];

@@ -158,8 +158,13 @@ def test_latency_and_throughput_variants(ctx):
             for lat in ("0", "1"):
                 os.environ["BSB200_LAT"] = lat
                 assert_same(ctx.epi8_batch(b, mode, bw, M26, -3, -2, 0, 0), exp, ecg, tag=("lat", lat, mode, bw, qlen))
+                if bw == 0:   # full bands normally take the instantiation without the band-shift code: also run the general one
+                    os.environ["BSB200_NOFULL"] = "1"
+                    assert_same(ctx.epi8_batch(b, mode, bw, M26, -3, -2, 0, 0), exp, ecg, tag=("lat-nofull", lat, mode, bw, qlen))
+                    os.environ.pop("BSB200_NOFULL")
     finally:
         os.environ.pop("BSB200_LAT", None)
+        os.environ.pop("BSB200_NOFULL", None)
 
 
 def test_dense_fetch_equals_scattered_fetch(ctx):
