@@ -92,9 +92,21 @@ __device__ __forceinline__ uint32_t not_fma(uint32_t x, uint32_t m1){ return x *
 // the latency of the F chain and not by ALU throughput): the gap-open candidate is taken from max(ev, z) instead of
 // max(ev, z, f).  Identical values (f + goe <= f + ge because go <= 0, and the lower clamp sits under both), but the
 // loop-carried chain f -> h -> y -> f1 -> f (4 DPX ops) becomes f -> f1 -> f (2); pass 2 pays one more instruction.
+// gap constants of dp_step as s16x2 (both halves equal).  The sums with 1 / 129 are built from the scalars here, once per kernel (or
+// job): written as __vadd2(GOE, C129) inside dp_step, nvcc 12.9 split the constant into halves in one instantiation's ragged-chunk
+// code and lost the +129 of the low half (caught by test_wide_bands / test_latency_and_throughput_variants).
+struct DpK {
+	uint32_t GE, GOE, GP, GQP, NGOQ, M1, Z0, GE1, GP1, GE129, GOE129, GP129;
+	__device__ __forceinline__ void set(int ge1, int goe, int ge2, int gqp, int ngoq, uint32_t m1){
+		GE = pk1(ge1); GOE = pk1(goe); GP = pk1(ge2); GQP = pk1(gqp); NGOQ = pk1(ngoq); M1 = m1;
+		Z0 = m1 + 1u;   // 0 as a run-time register value: ptxas otherwise re-materialises the constant with a PRMT per use
+		GE1 = pk1(ge1 + 1); GP1 = pk1(ge2 + 1); GE129 = pk1(ge1 + 129); GOE129 = pk1(goe + 129); GP129 = pk1(ge2 + 129);
+	}
+};
+
 template<int PW, bool FAST, bool PASS2, bool LAT = false>
-__device__ __forceinline__ void dp_step(RowState &s, uint32_t u, uint32_t e, uint32_t q, uint32_t z,
-		uint32_t GE, uint32_t GOE, uint32_t GP, uint32_t GQP, uint32_t NGOQ, uint32_t M1, uint32_t Z0, uint32_t &un, uint32_t &en, uint32_t &qn){
+__device__ __forceinline__ void dp_step(RowState &s, uint32_t u, uint32_t e, uint32_t q, uint32_t z, const DpK &k, uint32_t &un, uint32_t &en, uint32_t &qn){
+	const uint32_t GE = k.GE, GOE = k.GOE, GP = k.GP, GQP = k.GQP, NGOQ = k.NGOQ, M1 = k.M1, Z0 = k.Z0;
 	if(FAST){
 		constexpr uint32_t C129 = 0x00810081u, C255 = 0x00ff00ffu;
 		// u, z, s.f, s.g biased; e, q, s.nv unbiased
@@ -107,17 +119,17 @@ __device__ __forceinline__ void dp_step(RowState &s, uint32_t u, uint32_t e, uin
 		const uint32_t cu = not_fma(u, M1);
 		if(LAT && PW == 1){
 			const uint32_t hz = smax(ev, z);                                        // the part of h that does not hang on the F chain
-			const uint32_t yz = __viaddmax_s16x2(hz, __vadd2(GOE, C129), C129);
-			const uint32_t f1 = __viaddmax_s16x2(s.f, __vadd2(GE, C129), yz);
+			const uint32_t yz = __viaddmax_s16x2(hz, k.GOE129, C129);
+			const uint32_t f1 = __viaddmax_s16x2(s.f, k.GE129, yz);
 			if(PASS2){
 				h = smax(hz, s.f);
 				const uint32_t ch = not_fma(h, M1);
 				un = __viaddmin_s16x2_relu(h, s.nv, C255);
 				s.nv = __viaddmin_s16x2(__viaddmax_s16x2(u, ch, kLO), kONE, 0x00800080u);
-				uint32_t x1 = __viaddmax_s16x2(ev, __vadd2(GE, kONE), kONE);
+				uint32_t x1 = __viaddmax_s16x2(ev, k.GE1, kONE);
 				en = __viaddmax_s16x2(x1, ch, GOE);
 				s.u = u;
-				s.h = __viaddmax_s16x2(h, __vadd2(GOE, C129), C129);               // only the last step's value is read (row tail)
+				s.h = __viaddmax_s16x2(h, k.GOE129, C129);               // only the last step's value is read (row tail)
 			}
 			s.f = __viaddmin_s16x2_relu(f1, cu, C255);
 			return;
@@ -127,30 +139,30 @@ __device__ __forceinline__ void dp_step(RowState &s, uint32_t u, uint32_t e, uin
 			un = __viaddmin_s16x2_relu(h, s.nv, C255);                              // subs(h, v) + 128
 			s.nv = __viaddmin_s16x2(__viaddmax_s16x2(u, ch, kLO), kONE, 0x00800080u); // -(subs(h,u)): u_b + ~h_b = u - h - 1
 			if(PW >= 1){
-				uint32_t x1 = __viaddmax_s16x2(ev, __vadd2(GE, kONE), kONE);        // adds(ev, ge) + 1 + 128
+				uint32_t x1 = __viaddmax_s16x2(ev, k.GE1, kONE);        // adds(ev, ge) + 1 + 128
 				en = __viaddmax_s16x2(x1, ch, GOE);                                 // max(x - h, goe): x1 + ~h_b = x - h
 			}
 			if(PW == 2){
-				uint32_t x1 = __viaddmax_s16x2(qv, __vadd2(GP, kONE), kONE);
+				uint32_t x1 = __viaddmax_s16x2(qv, k.GP1, kONE);
 				qn = __viaddmax_s16x2(x1, ch, GQP);
 			}
 			s.u = u;
 		}
 		if(PW == 0){
 			s.h = h;
-			uint32_t y = __viaddmax_s16x2(h, __vadd2(GE, C129), C129);            // adds(h, ge) + 128 + 129
+			uint32_t y = __viaddmax_s16x2(h, k.GE129, C129);            // adds(h, ge) + 128 + 129
 			s.f = __viaddmin_s16x2_relu(y, cu, C255);                               // subs(y, u) + 128: y' + ~u_b = y - u + 128
 		} else if(PW == 1){
-			uint32_t y = __viaddmax_s16x2(h, __vadd2(GOE, C129), C129);           // adds(h, goe) + 128 + 129
-			uint32_t f1 = __viaddmax_s16x2(s.f, __vadd2(GE, C129), y);            // max(adds(f, ge), y) + 128 + 129
+			uint32_t y = __viaddmax_s16x2(h, k.GOE129, C129);           // adds(h, goe) + 128 + 129
+			uint32_t f1 = __viaddmax_s16x2(s.f, k.GE129, y);            // max(adds(f, ge), y) + 128 + 129
 			s.f = __viaddmin_s16x2_relu(f1, cu, C255);
 			s.h = y;
 		} else {
 			uint32_t yb = __viaddmax_s16x2(h, GOE, Z0);                            // adds(h, goe) + 128
-			uint32_t f1 = __viaddmax_s16x2(s.f, __vadd2(GE, C129), __vadd2(yb, C129));
+			uint32_t f1 = __viaddmax_s16x2(s.f, k.GE129, __vadd2(yb, C129));
 			s.f = __viaddmin_s16x2_relu(f1, cu, C255);
 			yb = __viaddmin_s16x2_relu(yb, NGOQ, C255);                             // subs(., goq) + 128
-			uint32_t g1 = __viaddmax_s16x2(s.g, __vadd2(GP, C129), __vadd2(yb, C129));
+			uint32_t g1 = __viaddmax_s16x2(s.g, k.GP129, __vadd2(yb, C129));
 			s.g = __viaddmin_s16x2_relu(g1, cu, C255);
 			s.h = __vadd2(yb, C129);
 		}
@@ -208,9 +220,11 @@ __device__ __forceinline__ int group_getscore(const int8_t *sU, const int32_t *s
 // LAT: latency-bound batches (a few warps per SM): short F chain (dp_step) and the next chunk's loads issued before the
 // current chunk's arithmetic
 // FULL: bandwidth 0, every pair's band covers its whole query: the band never moves (bsalign.h:3932 needs rbeg + bw < qlen),
-// so the shift and steering code is left out of the instantiation
+// so the shift and steering code is left out of the instantiation.  These kernels are compiled for 4 CTAs per SM (<= 128 registers;
+// ptxas then takes ~115 instead of ~80 and schedules the hot loops better: c2 forward 82.5 -> 81.1 ms, 10 kb global 264 -> 248 ms);
+// the same bound made the general kernels slower (c3 83.8 -> 90.6 ms), so they keep the default.
 template<int PW, bool FAST, bool ANCH, bool NARROW, bool LAT = false, bool FULL = false>
-__global__ void __launch_bounds__(kFwdThreads) epi8_forward_kernel(const Epi8Args a){
+__global__ void __launch_bounds__(kFwdThreads, FULL ? 4 : 0) epi8_forward_kernel(const Epi8Args a){
 	extern __shared__ __align__(16) uint8_t smem_raw[];
 	const int lane = threadIdx.x & 31;
 	const int t = lane & 7;
@@ -235,11 +249,11 @@ __global__ void __launch_bounds__(kFwdThreads) epi8_forward_kernel(const Epi8Arg
 	const int GOEi = (int8_t)(go1 + ge1), GQPi = (int8_t)(go2 + ge2);
 	const uint32_t GE = pk1(ge1), GOE = pk1(GOEi), GP = pk1(ge2), GQP = pk1(GQPi);
 	const uint32_t M1 = a.all_ones;
-	const uint32_t Z0 = M1 + 1u;   // 0 as a run-time register value: ptxas otherwise re-materialises the constant with a PRMT per use
 	constexpr int UB = FAST ? 128 : 0;              // bias of the u bytes (and of z, h, f, g in registers)
 	#define UBYTE(raw) (FAST ? (int)(uint8_t)(raw) - 128 : (int)(int8_t)(raw))
 	#define ZSEL(ca, cb) (FAST ? zselb((ca), (cb)) : zsel((ca), (cb)))
 	const uint32_t NGOE = pk1(-GOEi), NGOQ = pk1(-clamp8(GOEi - GQPi)), NGQP = pk1(-GQPi);
+	DpK dpk; dpk.set(ge1, GOEi, ge2, GQPi, -clamp8(GOEi - GQPi), M1);
 	// matrix columns: colw[tb] holds mtx[0*4+tb], mtx[1*4+tb], mtx[2*4+tb], mtx[3*4+tb] as bytes
 	uint32_t colw[4];
 	#pragma unroll
@@ -508,7 +522,10 @@ __global__ void __launch_bounds__(kFwdThreads) epi8_forward_kernel(const Epi8Arg
 		__syncwarp(amask);
 
 		// ---- cell 0 (bsalign.h:2899-2907) -----------------------------------------------------------
-		const uint32_t T32 = colw[tb & 3];
+		// (FULL: selects over registers instead of the dynamic index, which puts colw in local memory and costs an LDL stall per row:
+		// c2 forward 84.0 -> 82.5 ms.  The general instantiation keeps the indexed form: with the selects ptxas settles on 80 instead
+		// of 94 registers and c3 runs 9 % slower, 83.7 -> 91.3 ms)
+		const uint32_t T32 = FULL ? ((tb & 2) ? ((tb & 1) ? colw[3] : colw[2]) : ((tb & 1) ? colw[1] : colw[0])) : colw[tb & 3];
 		int h0;
 		{
 			int z0 = UBYTE(prmt(T32, ZPAD, (uint32_t)sC[0] & 7u) & 0xffu);
@@ -530,7 +547,7 @@ __global__ void __launch_bounds__(kFwdThreads) epi8_forward_kernel(const Epi8Arg
 			#define P1STEP(K, LEFT) { if((K) < (LEFT)){ \
 				uint32_t z = prmt(T32, ZPAD, ent_sel<K>(cs4)); \
 				if((K) == 0 && c == 0) z = (z & zmask) | zor; \
-				dp_step<PW, FAST, false, LAT>(st, FAST ? entz<K>(cu4) : ent<K>(cu4), ent<K>(ce4), ent<K>(cq4), z, GE, GOE, GP, GQP, NGOQ, M1, Z0, dum0, dum1, dum2); } }
+				dp_step<PW, FAST, false, LAT>(st, FAST ? entz<K>(cu4) : ent<K>(cu4), ent<K>(ce4), ent<K>(cq4), z, dpk, dum0, dum1, dum2); } }
 			#define P1BODY(LEFT) { P1STEP(0, LEFT) P1STEP(1, LEFT) P1STEP(2, LEFT) P1STEP(3, LEFT) P1STEP(4, LEFT) P1STEP(5, LEFT) P1STEP(6, LEFT) P1STEP(7, LEFT) }
 			#define P1CHUNK(LEFT) { \
 				const uint4 cu4 = *(const uint4*)(rU + 128 * c), cs4 = *(const uint4*)(rC + 128 * c); \
@@ -579,10 +596,10 @@ __global__ void __launch_bounds__(kFwdThreads) epi8_forward_kernel(const Epi8Arg
 				int GA = aA + aB, GM = max(feA + aB, feB);
 				#pragma unroll
 				for(int d=1;d<kGroup;d<<=1){
-					const int pA = __shfl_up_sync(gmask, GA, d, kGroup), pM = __shfl_up_sync(gmask, GM, d, kGroup);
+					const int pA = __shfl_up_sync(amask, GA, d, kGroup), pM = __shfl_up_sync(amask, GM, d, kGroup);
 					if(t >= d){ GM = max(pM + GA, GM); GA += pA; }
 				}
-				int PA = __shfl_up_sync(gmask, GA, 1, kGroup), PM = __shfl_up_sync(gmask, GM, 1, kGroup);
+				int PA = __shfl_up_sync(amask, GA, 1, kGroup), PM = __shfl_up_sync(amask, GM, 1, kGroup);
 				if(t == 0){ PA = 0; PM = NEG; }
 				finA = max(kEpi8Min + PA, PM);
 				const int sA = finA + aA;
@@ -593,7 +610,8 @@ __global__ void __launch_bounds__(kFwdThreads) epi8_forward_kernel(const Epi8Arg
 			int finA, finB, ginA = kEpi8Min, ginB = kEpi8Min;
 			bool ovf = scan(st.f, (int)W * ge1, finA, finB);
 			if(PW == 2) ovf |= scan(st.g, (int)W * ge2, ginA, ginB);
-			if(__any_sync(gmask, ovf)){
+			// (whole-warp shuffles and ballot: a partial mask costs a convergence check per call and runs the four groups one after the other)
+			if((__ballot_sync(amask, ovf) >> (lane & 24)) & 0xffu){
 				// literal 16-step scan with the int8 truncation, every thread redundantly
 				sF[A] = (int8_t)(lo16(st.f) - UB); sF[B] = (int8_t)(hi16(st.f) - UB);
 				if(PW == 2){ sF[16 + A] = (int8_t)(lo16(st.g) - UB); sF[16 + B] = (int8_t)(hi16(st.g) - UB); }
@@ -625,7 +643,7 @@ __global__ void __launch_bounds__(kFwdThreads) epi8_forward_kernel(const Epi8Arg
 			#define P2STEP(K, LEFT) { if((K) < (LEFT)){ \
 				uint32_t z = prmt(T32, ZPAD, ent_sel<K>(cs4)); \
 				if((K) == 0 && c == 0) z = (z & zmask) | zor; \
-				dp_step<PW, FAST, true, LAT>(st, FAST ? entz<K>(cu4) : ent<K>(cu4), ent<K>(ce4), ent<K>(cq4), z, GE, GOE, GP, GQP, NGOQ, M1, Z0, un[K], en[K], qn[K]); } }
+				dp_step<PW, FAST, true, LAT>(st, FAST ? entz<K>(cu4) : ent<K>(cu4), ent<K>(ce4), ent<K>(cq4), z, dpk, un[K], en[K], qn[K]); } }
 			#define P2CHUNK(LEFT, RAGGED) { \
 				const uint4 cu4 = *(const uint4*)(rU + 128 * c), cs4 = *(const uint4*)(rC + 128 * c); \
 				uint4 ce4 = cu4, cq4 = cu4; \
@@ -643,9 +661,6 @@ __global__ void __launch_bounds__(kFwdThreads) epi8_forward_kernel(const Epi8Arg
 				if(PW == 2) *(uint4*)(rQ + 128 * c) = make_uint4(pack2(qn[0], qn[1]), pack2(qn[2], qn[3]), pack2(qn[4], qn[5]), pack2(qn[6], qn[7])); }
 			uint32_t c = 0;
 			if(LAT){
-				// compiler barrier: chunk 0 is loaded afresh.  Without it nvcc 12.9 re-uses pass 1's first loads across the pass-1 loop
-				// and the <1, FAST, ANCH, ., LAT> instantiation came out wrong (every score; caught by test_wide_bands)
-				asm volatile("" ::: "memory");
 				uint4 nu4 = *(const uint4*)rU, ns4 = *(const uint4*)rC, ne4 = nu4, nq4 = nu4;
 				if(PW >= 1) ne4 = *(const uint4*)rE;
 				if(PW == 2) nq4 = *(const uint4*)rQ;

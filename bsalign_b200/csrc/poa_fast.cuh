@@ -143,6 +143,7 @@ __global__ void __launch_bounds__(32) poa_sweep_fast_kernel(const PoaFastArgs fa
 	uint32_t job = 0;
 	int mode = 1, Mm = 0, Xx = 0, O = 0, E = 0, Q = 0, P = 0, T = 0, refbonus = 0, go1 = 0, ge1 = 0, go2 = 0, ge2 = 0;
 	uint32_t GE = 0, GOE = 0, GP = 0, GQP = 0, NGOE = 0, NGOQ = 0, NGQP = 0;
+	DpK dpk; dpk.set(0, 0, 0, 0, 0, M1);
 	int smax_nt = 0, smin_nt = 0;
 	uint32_t slen = 0;
 	const uint32_t *qsel = fa.qsel;
@@ -195,6 +196,7 @@ __global__ void __launch_bounds__(32) poa_sweep_fast_kernel(const PoaFastArgs fa
 				const int GOEi = (int8_t)(go1 + ge1), GQPi = (int8_t)(go2 + ge2);
 				GE = pk1(ge1); GOE = pk1(GOEi); GP = pk1(ge2); GQP = pk1(GQPi);
 				NGOE = pk1(-GOEi); NGOQ = pk1(-clamp8(GOEi - GQPi)); NGQP = pk1(-GQPi);
+				dpk.set(ge1, GOEi, ge2, GQPi, -clamp8(GOEi - GQPi), M1);
 				smax_nt = (int8_t)(Mm + refbonus + 1); smin_nt = (int8_t)Xx;
 				slen = a.slen[job];
 				qsel = (const uint32_t*)((const uint8_t*)fa.qsel + fa.qsel_off[job]);
@@ -456,7 +458,7 @@ __global__ void __launch_bounds__(32) poa_sweep_fast_kernel(const PoaFastArgs fa
 			RowState st; st.f = pk1(kEpi8Min + 128); st.g = pk1(kEpi8Min + 128); st.h = 0; st.u = 0; st.nv = 0;
 			{
 				uint32_t d0, d1, d2;
-				#define P1(K, Z) dp_step<PW, true, false>(st, entz<K>(cu4), ent<K>(ce4), ent<K>(cq4), Z, GE, GOE, GP, GQP, NGOQ, M1, Z0, d0, d1, d2);
+				#define P1(K, Z) dp_step<PW, true, false>(st, entz<K>(cu4), ent<K>(ce4), ent<K>(cq4), Z, dpk, d0, d1, d2);
 				P1(0, z0) P1(1, z1) P1(2, z2) P1(3, z3) P1(4, z4) P1(5, z5) P1(6, z6) P1(7, z7)
 				#undef P1
 			}
@@ -501,7 +503,7 @@ __global__ void __launch_bounds__(32) poa_sweep_fast_kernel(const PoaFastArgs fa
 			st.nv = 0; st.h = 0; st.u = 0;
 			uint32_t un0, un1, un2, un3, un4, un5, un6, un7, en0 = 0, en1 = 0, en2 = 0, en3 = 0, en4 = 0, en5 = 0, en6 = 0, en7 = 0,
 				qn0 = 0, qn1 = 0, qn2 = 0, qn3 = 0, qn4 = 0, qn5 = 0, qn6 = 0, qn7 = 0;
-			#define P2(K, Z) dp_step<PW, true, true>(st, entz<K>(cu4), ent<K>(ce4), ent<K>(cq4), Z, GE, GOE, GP, GQP, NGOQ, M1, Z0, un##K, en##K, qn##K);
+			#define P2(K, Z) dp_step<PW, true, true>(st, entz<K>(cu4), ent<K>(ce4), ent<K>(cq4), Z, dpk, un##K, en##K, qn##K);
 			P2(0, z0) P2(1, z1) P2(2, z2) P2(3, z3) P2(4, z4) P2(5, z5) P2(6, z6) P2(7, z7)
 			#undef P2
 			// ---- tail (bsalign.h:2618-2636) ----
