@@ -37,10 +37,12 @@ __host__ __device__ __forceinline__ uint32_t epi8_cell_offset(uint32_t j, uint32
 // Sub-lane anchors for the traceback: besides the 17 block anchors of the reference, a row carries the absolute score
 // at the end of every 32nd step of every lane (int32 [g-1][lane], g = 1 .. ngrp-1), so that a score lookup sums at
 // most 32 cells (4 chunks) instead of a whole lane.
-constexpr uint32_t kAnchorSteps = 32;
+constexpr uint32_t kAnchorSteps = 32, kAnchorChunks = kAnchorSteps / 8;
 __host__ __device__ __forceinline__ uint32_t epi8_anchor_groups(uint32_t W){ return (W + kAnchorSteps - 1) / kAnchorSteps; }
 __host__ __device__ __forceinline__ uint32_t epi8_anchor_bytes(uint32_t W){ return (epi8_anchor_groups(W) - 1) * 64; }
-// the anchors pay off (and are written) only when the widest lane of a batch exceeds 64 steps
+// the anchors pay off (and are written) only when the widest lane of a batch exceeds 64 steps.  (Measured on config 2, W = 63:
+// anchors every 16 steps for W > 32 cut the traceback from 16.8 to 12.1 ms - it is bound by the sectors a lookup touches - but
+// the forward kernel's anchor loop cost 5 ms, a wash; fusing the anchor sums into pass 2 is the open follow-up.)
 __host__ __device__ __forceinline__ bool epi8_use_anchors(uint32_t maxW){ return maxW > 64; }
 __host__ __device__ __forceinline__ uint32_t epi8_row_bytes(uint32_t W, int pw){ return epi8_image_bytes(W) * (pw + 1) + epi8_anchor_bytes(W); }
 

@@ -715,7 +715,7 @@ __global__ void __launch_bounds__(kFwdThreads, FULL ? 4 : 0) epi8_forward_kernel
 				const int baseA = sUB[A], baseB = sUB[B];
 				uint32_t accA = 0, accB = 0;
 				_Pragma("unroll 1")
-				for(uint32_t c=0;c<4*(ng-1);c++){
+				for(uint32_t c=0;c<kAnchorChunks*(ng-1);c++){
 					const uint4 w = *(const uint4*)(rU + 128 * c);
 					if(FAST){
 						accA = __dp4a(w.x, 0x00010001u, accA); accB = __dp4a(w.x, 0x01000100u, accB);
@@ -728,9 +728,9 @@ __global__ void __launch_bounds__(kFwdThreads, FULL ? 4 : 0) epi8_forward_kernel
 						accA = (uint32_t)__dp4a((int)w.z, 0x00010001, (int)accA); accB = (uint32_t)__dp4a((int)w.z, 0x01000100, (int)accB);
 						accA = (uint32_t)__dp4a((int)w.w, 0x00010001, (int)accA); accB = (uint32_t)__dp4a((int)w.w, 0x01000100, (int)accB);
 					}
-					if((c & 3) == 3){
+					if((c % kAnchorChunks) == kAnchorChunks - 1){
 						const int corr = UB * (int)(8 * (c + 1));
-						*(int2*)(an + (c >> 2) * 16 + A) = make_int2(baseA + (int)accA - corr, baseB + (int)accB - corr);
+						*(int2*)(an + (c / kAnchorChunks) * 16 + A) = make_int2(baseA + (int)accA - corr, baseB + (int)accB - corr);
 					}
 				}
 			}
