@@ -347,6 +347,13 @@ static int launch_epi8_forward(bsb200_ctx *ctx, Epi8Args a, uint32_t npairs, boo
 		if(cost < best_cost - 1e-9 || (cost < best_cost + 1e-9 && groups > best_groups)){ best_cost = cost; best_groups = groups; best_threads = sh[0]; best_gpw = sh[1]; }
 	}
 	if(!best_groups){ ctx->err = "band too wide for the shared-memory row buffers"; return -1; }
+	if constexpr (ANCH){
+		// test hook: one-warp CTAs with 1..3 groups per warp (the NARROW instantiations) on any batch that carries anchors
+		if(const char *ev = getenv("BSB200_GPW")){
+			int g = atoi(ev);
+			if(g >= 1 && g <= 3 && (size_t)g * a.group_smem <= ctx->smem_optin){ best_threads = 32; best_gpw = (uint32_t)g; best_groups = (uint32_t)g; }
+		}
+	}
 	a.gpw = best_gpw;
 	const int threads = best_threads;
 	const size_t smem = (size_t)(threads / 32) * best_gpw * a.group_smem;
@@ -463,7 +470,8 @@ extern "C" int bsb200_batch_run(bsb200_ctx *ctx, bsb200_batch *b){
 			for(int k=0;k<16;k++){ a.smax = std::max(a.smax, b->mtx[k]); a.smin = std::min(a.smin, b->mtx[k]); }
 			// all gap costs <= 0 (the normal case): saturation bounds that cannot bind are dropped (epi8_forward.cuh)
 			// (linear gaps, pw = 0, stay on the literal kernel)
-			const bool fast = b->pw >= 1 && b->ge1 <= 0 && (int8_t)(b->go1 + b->ge1) <= 0 && (b->pw < 2 || (b->ge2 <= 0 && (int8_t)(b->go2 + b->ge2) <= 0));
+			// (BSB200_NOFAST: tests run the literal kernels on ordinary gap costs too)
+			const bool fast = b->pw >= 1 && b->ge1 <= 0 && (int8_t)(b->go1 + b->ge1) <= 0 && (b->pw < 2 || (b->ge2 <= 0 && (int8_t)(b->go2 + b->ge2) <= 0)) && !getenv("BSB200_NOFAST");
 			const bool anch = epi8_use_anchors(b->max_bw / 16);
 			a.gpw = 4;
 			int rc;

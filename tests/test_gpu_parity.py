@@ -167,6 +167,28 @@ def test_latency_and_throughput_variants(ctx):
         os.environ.pop("BSB200_NOFULL", None)
 
 
+def test_every_forward_instantiation(ctx):
+    """The forward kernel is a family of template instantiations chosen by gap model, band width and batch shape; the env hooks of
+    the host side force each of them on inputs the oracle finishes quickly: literal arithmetic (BSB200_NOFAST) for affine and
+    two-piece gaps, sub-lane anchors with every gap model, one-warp CTAs with 1-3 groups per warp (BSB200_GPW), with and without LAT."""
+    keys = ("BSB200_NOFAST", "BSB200_GPW", "BSB200_LAT", "BSB200_NOFULL")
+    try:
+        cases = [(0, 0, 1200, 5), (1, 1100, 1500, 5), (2, 0, 1300, 4), (1, 96, 600, 12)]
+        for mode, bw, qlen, n in cases:
+            b = synth.make_pairs(n, qlen, seed=17 * qlen + mode)
+            for gaps in [(-3, -2, 0, 0), (0, -2, 0, 0), (-3, -2, -8, -1)]:
+                exp, ecg, _ = ck.oracle_batch("epi8", b, mode, bw, M26, gaps, nthreads=8)
+                for env in [{}, {"BSB200_NOFAST": "1"}, {"BSB200_GPW": "1"}, {"BSB200_GPW": "3", "BSB200_LAT": "0"}, {"BSB200_GPW": "2", "BSB200_LAT": "1", "BSB200_NOFULL": "1"},
+                            {"BSB200_NOFAST": "1", "BSB200_GPW": "2"}]:
+                    for k in keys:
+                        os.environ.pop(k, None)
+                    os.environ.update(env)
+                    assert_same(ctx.epi8_batch(b, mode, bw, M26, *gaps), exp, ecg, tag=("inst", mode, bw, qlen, gaps, sorted(env.items())))
+    finally:
+        for k in keys:
+            os.environ.pop(k, None)
+
+
 def test_dense_fetch_equals_scattered_fetch(ctx):
     b = synth.make_pairs(500, 200, seed=99)
     a = ctx.epi8_batch(b, 1, 64, M26, -3, -2, 0, 0)
