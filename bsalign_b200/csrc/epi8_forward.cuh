@@ -557,20 +557,28 @@ __global__ void __launch_bounds__(kFwdThreads, FULL ? 4 : 0) epi8_forward_kernel
 				P1BODY(LEFT) }
 			uint32_t c = 0;
 			if(LAT){
-				// chunk c + 1 is in flight while chunk c is computed
-				uint4 nu4 = *(const uint4*)rU, ns4 = *(const uint4*)rC, ne4 = nu4, nq4 = nu4;
-				if(PW >= 1) ne4 = *(const uint4*)rE;
-				if(PW == 2) nq4 = *(const uint4*)rQ;
+				// chunk c + 1 is in flight while chunk c is computed; two register sets take turns (no copies)
+				uint4 au, as_, ae, aq, bu, bs, be, bq;
+				#define LDSET(U, S, E, Q, CI) { const uint32_t ci_ = (CI); U = *(const uint4*)(rU + 128 * ci_); S = *(const uint4*)(rC + 128 * ci_); \
+					E = U; Q = U; if(PW >= 1) E = *(const uint4*)(rE + 128 * ci_); if(PW == 2) Q = *(const uint4*)(rQ + 128 * ci_); }
+				#define P1ON(U, S, E, Q, LEFT) { const uint4 &cu4 = U, &cs4 = S, &ce4 = E, &cq4 = Q; P1BODY(LEFT) }
+				LDSET(au, as_, ae, aq, 0u)
 				_Pragma("unroll 1")
-				for(;c<nfull;c++){
-					const uint4 cu4 = nu4, cs4 = ns4, ce4 = ne4, cq4 = nq4;
-					const uint32_t cn = c + 1 < nchunk ? c + 1 : c;
-					nu4 = *(const uint4*)(rU + 128 * cn); ns4 = *(const uint4*)(rC + 128 * cn);
-					if(PW >= 1) ne4 = *(const uint4*)(rE + 128 * cn);
-					if(PW == 2) nq4 = *(const uint4*)(rQ + 128 * cn);
-					P1BODY(8u)
+				while(c + 2 <= nfull){
+					LDSET(bu, bs, be, bq, c + 1)
+					P1ON(au, as_, ae, aq, 8u)
+					c++;
+					LDSET(au, as_, ae, aq, c + 1 < nchunk ? c + 1 : c)
+					P1ON(bu, bs, be, bq, 8u)
+					c++;
 				}
-				if(c < nchunk){ const uint4 cu4 = nu4, cs4 = ns4, ce4 = ne4, cq4 = nq4; const uint32_t left = W - 8 * c; P1BODY(left) }
+				if(c < nfull){
+					LDSET(bu, bs, be, bq, c + 1 < nchunk ? c + 1 : c)
+					P1ON(au, as_, ae, aq, 8u)
+					c++;
+					if(c < nchunk){ const uint32_t left = W - 8 * c; P1ON(bu, bs, be, bq, left) }
+				} else if(c < nchunk){ const uint32_t left = W - 8 * c; P1ON(au, as_, ae, aq, left) }
+				#undef P1ON
 			} else {
 				_Pragma("unroll 1")   // one chunk per iteration keeps the loop body in the instruction cache (measured: -10% time)
 				for(;c<nfull;c++) P1CHUNK(8u)
@@ -661,19 +669,26 @@ __global__ void __launch_bounds__(kFwdThreads, FULL ? 4 : 0) epi8_forward_kernel
 				if(PW == 2) *(uint4*)(rQ + 128 * c) = make_uint4(pack2(qn[0], qn[1]), pack2(qn[2], qn[3]), pack2(qn[4], qn[5]), pack2(qn[6], qn[7])); }
 			uint32_t c = 0;
 			if(LAT){
-				uint4 nu4 = *(const uint4*)rU, ns4 = *(const uint4*)rC, ne4 = nu4, nq4 = nu4;
-				if(PW >= 1) ne4 = *(const uint4*)rE;
-				if(PW == 2) nq4 = *(const uint4*)rQ;
+				uint4 au, as_, ae, aq, bu, bs, be, bq;
+				#define P2ON(U, S, E, Q, LEFT, RAGGED) { const uint4 &cu4 = U, &cs4 = S, &ce4 = E, &cq4 = Q; P2BODY(LEFT, RAGGED) }
+				LDSET(au, as_, ae, aq, 0u)
 				_Pragma("unroll 1")
-				for(;c<nfull;c++){
-					const uint4 cu4 = nu4, cs4 = ns4, ce4 = ne4, cq4 = nq4;
-					const uint32_t cn = c + 1 < nchunk ? c + 1 : c;   // (without a ragged chunk the last iteration re-reads its own chunk before writing it)
-					nu4 = *(const uint4*)(rU + 128 * cn); ns4 = *(const uint4*)(rC + 128 * cn);
-					if(PW >= 1) ne4 = *(const uint4*)(rE + 128 * cn);
-					if(PW == 2) nq4 = *(const uint4*)(rQ + 128 * cn);
-					P2BODY(8u, false)
+				while(c + 2 <= nfull){
+					LDSET(bu, bs, be, bq, c + 1)
+					P2ON(au, as_, ae, aq, 8u, false)
+					c++;
+					LDSET(au, as_, ae, aq, c + 1 < nchunk ? c + 1 : c)   // (the row's last chunk re-reads itself before it is written)
+					P2ON(bu, bs, be, bq, 8u, false)
+					c++;
 				}
-				if(c < nchunk){ const uint4 cu4 = nu4, cs4 = ns4, ce4 = ne4, cq4 = nq4; const uint32_t left = W - 8 * c; P2BODY(left, true) }
+				if(c < nfull){
+					LDSET(bu, bs, be, bq, c + 1 < nchunk ? c + 1 : c)
+					P2ON(au, as_, ae, aq, 8u, false)
+					c++;
+					if(c < nchunk){ const uint32_t left = W - 8 * c; P2ON(bu, bs, be, bq, left, true) }
+				} else if(c < nchunk){ const uint32_t left = W - 8 * c; P2ON(au, as_, ae, aq, left, true) }
+				#undef P2ON
+				#undef LDSET
 			} else {
 				_Pragma("unroll 1")
 				for(;c<nfull;c++) P2CHUNK(8u, false)
