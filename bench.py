@@ -93,18 +93,30 @@ class ClockSampler:
 
     def _read(self):
         for line in self.proc.stdout:
-            self.lines.append(line.strip())
+            self.lines.append((time.perf_counter(), line.strip()))
+
+    def mark(self):
+        """Start of the timed region: nvidia-smi is started earlier (before the warm-up steps) because it needs a few hundred
+        ms to come up, longer with eight ranks starting one each; only samples from here on are used."""
+        self.t_begin = time.perf_counter()
 
     def stop(self):
         if not self.proc:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        t_end = time.perf_counter()
+        if not any(t >= getattr(self, "t_begin", 0.0) for t, _ in self.lines):
+            time.sleep(0.45)   # region shorter than the sampling period: take the samples right behind it (clocks ramp down after seconds)
         self.proc.terminate()
         try:
             self.proc.wait(timeout=2)
         except Exception:
             self.proc.kill()
         sm, mx, reasons = [], None, set()
-        for ln in self.lines:
+        t0 = getattr(self, "t_begin", 0.0)
+        inside = [ln for t, ln in self.lines if t0 <= t <= t_end + 0.25]
+        if not inside:
+            inside = [ln for t, ln in self.lines if t >= t0][:2] or [ln for _, ln in self.lines[-1:]]
+        for ln in inside:
             f = [x.strip() for x in ln.split(",")]
             if len(f) < 9:
                 continue
@@ -237,11 +249,12 @@ def main_poa(args, w, njobs, ncores, rank, local_rank, world):
     # ---- kernel-only leg: jobs resident in HBM -------------------------------------------------------
     rs = poa.ResidentSweeps(ctx, batch)
     rs.attach_reverse()          # the run = sweep + the walk of alignment2graph_bspoa on the device
+    sampler = ClockSampler(local_rank)
+    sampler.start()
     for _ in range(args.warmup):
         rs.run()
-    sampler = ClockSampler(local_rank)
     barrier()
-    sampler.start()
+    sampler.mark()
     dev_ms = sweep_ms = walk_ms = 0.0
     t0 = time.perf_counter()
     for _ in range(args.steps):
@@ -467,11 +480,12 @@ def main():
 
     # ---- kernel-only leg: inputs resident in HBM --------------------------------------------------
     rb = ctx.upload(w["kind"], hb, w["mode"], w["bandwidth"], mtx, GAPS, want_cigar=True)
+    sampler = ClockSampler(local_rank)
+    sampler.start()
     for _ in range(args.warmup):
         rb.run()
-    sampler = ClockSampler(local_rank)
     barrier()
-    sampler.start()
+    sampler.mark()
     dev_ms = fwd_ms = bt_ms = 0.0
     fwd_launches = bt_launches = 0
     t0 = time.perf_counter()

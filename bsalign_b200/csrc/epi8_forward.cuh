@@ -362,7 +362,11 @@ __global__ void __launch_bounds__(kFwdThreads, FULL ? 4 : 0) epi8_forward_kernel
 			if((uint32_t)lim < mov) mov = (uint32_t)lim;
 		} else mov = 0;
 		if(!FULL && mov){
-			rh = (mov - 1 < bw) ? group_getscore(sU, sUB, W, mov - 1, t, UB) : kScoreMin;
+			if(mov <= 8 && mov <= W){
+				// H at band position mov - 1, which lies in lane 0: every thread adds the same few cells (broadcast loads, no shuffles)
+				rh = sUB[0];
+				for(uint32_t k=0;k<mov;k++) rh += UBYTE(sU[2 * k]);
+			} else rh = (mov - 1 < bw) ? group_getscore(sU, sUB, W, mov - 1, t, UB) : kScoreMin;
 			if(mov - 1 >= bw) stflag |= 1;
 		} else {
 			if(rbeg) rh = kScoreMin;
@@ -764,11 +768,18 @@ __global__ void __launch_bounds__(kFwdThreads, FULL ? 4 : 0) epi8_forward_kernel
 		// ---- adaptive band steering (bsalign.h:3331-3349, 4005-4021) -------------------------------------
 		if(!FULL){
 			int rbx = 0;
+			// sum of |ub[j] - ub[j-1]| (band_mov's noise term): each thread its two lanes, added up over the group with whole-warp
+			// shuffles (hence outside the condition below) instead of 16 dependent shared-memory steps in every thread
+			int noisy;
+			{
+				const int a_ = sUB[A], b_ = sUB[B], c_ = sUB[B + 1];
+				noisy = abs(b_ - a_) + abs(c_ - b_);
+				noisy += __shfl_xor_sync(amask, noisy, 1);
+				noisy += __shfl_xor_sync(amask, noisy, 2);
+				noisy += __shfl_xor_sync(amask, noisy, 4);
+			}
 			if(!(row <= W * kLanes / 4) && !(rbeg + W * kLanes >= qlen)){
-				int noisy = 0, p0 = sUB[0];
-				const int ub0 = p0;
-				#pragma unroll
-				for(int j=1;j<=kLanes;j++){ int p1 = sUB[j]; noisy += p1 < p0 ? p0 - p1 : p1 - p0; p0 = p1; }
+				const int ub0 = sUB[0], p0 = sUB[kLanes];
 				uint32_t nz = ((uint32_t)(noisy / kLanes)) / W * kLanes / 2;
 				noisy = (int)(16u > nz ? 16u : nz);
 				if(ub0 + noisy < p0) rbx = 2;
