@@ -389,11 +389,6 @@ __global__ void __launch_bounds__(kFwdThreads, FULL ? 4 : 0) epi8_forward_kernel
 			} else {
 				const uint32_t cyc = mov / W, mr = mov - cyc * W;
 				// anchors of the old row advanced by the first mr cells of each block (:2310-2331)
-				for(int j=t;j<kLanes;j+=kGroup){
-					int s = sUB[j];
-					for(uint32_t k=0;k<mr;k++) s += UBYTE(sU[epi8_cell_offset(j, k)]);
-					sTmp[j] = s;
-				}
 				const int ub16 = sUB[kLanes];
 				// overhang parameters (:2357-2369)
 				uint32_t d; int c;
@@ -420,6 +415,20 @@ __global__ void __launch_bounds__(kFwdThreads, FULL ? 4 : 0) epi8_forward_kernel
 						nQ.z = __shfl_down_sync(gmask, fQ.z, 1, kGroup); nQ.w = __shfl_down_sync(gmask, fQ.w, 1, kGroup);
 					}
 					__syncwarp(gmask);
+					// anchors (:2310-2331, :2372-2389): a lane's anchor advances by its first mr cells, which this thread holds in fU;
+					// with a shift inside one lane only the end anchor ub[16] is reached by the overhang
+					{
+						int sumA = 0, sumB = 0;
+						for(uint32_t k=0;k<mr;k++){
+							const uint32_t w_ = (k >> 1) == 0 ? fU.x : (k >> 1) == 1 ? fU.y : (k >> 1) == 2 ? fU.z : fU.w, sh_ = (k & 1) * 16;
+							sumA += UBYTE((w_ >> sh_) & 0xffu); sumB += UBYTE((w_ >> (sh_ + 8)) & 0xffu);
+						}
+						sUB[A] += sumA; sUB[B] += sumB;
+						if(t == kGroup - 1){
+							const uint32_t n1 = (mov - 1 < d - 1) ? mov - 1 : d - 1;
+							sUB[kLanes] = ub16 + c + (int)n1 * ge1 + (int)(mov - 1 - n1) * ge2;
+						}
+					}
 					// the thread's stream is 4 words per chunk; word w lives at chunk w/4, offset 4*(w%4)
 					const uint32_t nW = IB / 32, ws = (2 * mr) / 4, bb = ((2 * mr) & 3) * 8;
 					#define WOFF(w) ((((w) >> 2) << 7) + (((w) & 3) << 2))
@@ -483,6 +492,12 @@ __global__ void __launch_bounds__(kFwdThreads, FULL ? 4 : 0) epi8_forward_kernel
 				} else {
 					// general path (rare: global mode hurrying to the end): gather from the previous row's image in
 					// the HBM trace, which this group finished writing in the previous iteration
+					// anchors of the old row advanced by the first mr cells of each block (:2310-2331)
+					for(int j=t;j<kLanes;j+=kGroup){
+						int s = sUB[j];
+						for(uint32_t k=0;k<mr;k++) s += UBYTE(sU[epi8_cell_offset(j, k)]);
+						sTmp[j] = s;
+					}
 					__syncwarp(gmask);
 					const uint8_t *pimg = tr + (size_t)RS * row; // image of row-1
 					for(uint32_t i=0;i<W;i++){
@@ -507,18 +522,18 @@ __global__ void __launch_bounds__(kFwdThreads, FULL ? 4 : 0) epi8_forward_kernel
 						uint32_t xA = rbeg + mov + A * W + i;
 						*(uint16_t*)(rC + TOFF(i)) = (uint16_t)ZSEL(QCODE(xA), QCODE(xA + W));
 					}
-				}
-				__syncwarp(gmask);
-				for(int j=t;j<=kLanes;j+=kGroup){
-					int v = (j + cyc < (uint32_t)kLanes) ? sTmp[j + cyc] : ub16;
-					// block ends crossed by the overhang add the running overhang total (:2372-2389)
-					uint32_t P = (uint32_t)j * W;
-					if(j >= 1 && P > i0){
-						uint32_t k = P - i0; // overhang cells in [i0, P)
-						uint32_t n1 = (k - 1 < d - 1) ? k - 1 : d - 1;
-						v += c + (int)n1 * ge1 + (int)(k - 1 - n1) * ge2;
+					__syncwarp(gmask);
+					for(int j=t;j<=kLanes;j+=kGroup){
+						int v = (j + cyc < (uint32_t)kLanes) ? sTmp[j + cyc] : ub16;
+						// block ends crossed by the overhang add the running overhang total (:2372-2389)
+						uint32_t P = (uint32_t)j * W;
+						if(j >= 1 && P > i0){
+							uint32_t k = P - i0; // overhang cells in [i0, P)
+							uint32_t n1 = (k - 1 < d - 1) ? k - 1 : d - 1;
+							v += c + (int)n1 * ge1 + (int)(k - 1 - n1) * ge2;
+						}
+						sUB[j] = v;
 					}
-					sUB[j] = v;
 				}
 				rbeg += mov;
 			}
