@@ -401,18 +401,16 @@ __global__ void __launch_bounds__(kFwdThreads, FULL ? 4 : 0) epi8_forward_kernel
 					uint4 fU = *(const uint4*)rU, fE = make_uint4(0, 0, 0, 0), fQ = fE, fC = *(const uint4*)rC;
 					if(PW >= 1) fE = *(const uint4*)rE;
 					if(PW == 2) fQ = *(const uint4*)rQ;
-					uint4 nU, nE = fE, nQ = fQ, nC;
-					nU.x = __shfl_down_sync(gmask, fU.x, 1, kGroup); nU.y = __shfl_down_sync(gmask, fU.y, 1, kGroup);
-					nU.z = __shfl_down_sync(gmask, fU.z, 1, kGroup); nU.w = __shfl_down_sync(gmask, fU.w, 1, kGroup);
-					nC.x = __shfl_down_sync(gmask, fC.x, 1, kGroup); nC.y = __shfl_down_sync(gmask, fC.y, 1, kGroup);
-					nC.z = __shfl_down_sync(gmask, fC.z, 1, kGroup); nC.w = __shfl_down_sync(gmask, fC.w, 1, kGroup);
-					if(PW >= 1){
-						nE.x = __shfl_down_sync(gmask, fE.x, 1, kGroup); nE.y = __shfl_down_sync(gmask, fE.y, 1, kGroup);
-						nE.z = __shfl_down_sync(gmask, fE.z, 1, kGroup); nE.w = __shfl_down_sync(gmask, fE.w, 1, kGroup);
-					}
-					if(PW == 2){
-						nQ.x = __shfl_down_sync(gmask, fQ.x, 1, kGroup); nQ.y = __shfl_down_sync(gmask, fQ.y, 1, kGroup);
-						nQ.z = __shfl_down_sync(gmask, fQ.z, 1, kGroup); nQ.w = __shfl_down_sync(gmask, fQ.w, 1, kGroup);
+					// the neighbour's first mr entries: one word per array covers shifts of one or two cells
+					uint4 nU = fU, nE = fE, nQ = fQ, nC = fC;
+					nU.x = __shfl_down_sync(gmask, fU.x, 1, kGroup); nC.x = __shfl_down_sync(gmask, fC.x, 1, kGroup);
+					if(PW >= 1) nE.x = __shfl_down_sync(gmask, fE.x, 1, kGroup);
+					if(PW == 2) nQ.x = __shfl_down_sync(gmask, fQ.x, 1, kGroup);
+					if(mr > 2){
+						nU.y = __shfl_down_sync(gmask, fU.y, 1, kGroup); nU.z = __shfl_down_sync(gmask, fU.z, 1, kGroup); nU.w = __shfl_down_sync(gmask, fU.w, 1, kGroup);
+						nC.y = __shfl_down_sync(gmask, fC.y, 1, kGroup); nC.z = __shfl_down_sync(gmask, fC.z, 1, kGroup); nC.w = __shfl_down_sync(gmask, fC.w, 1, kGroup);
+						if(PW >= 1){ nE.y = __shfl_down_sync(gmask, fE.y, 1, kGroup); nE.z = __shfl_down_sync(gmask, fE.z, 1, kGroup); nE.w = __shfl_down_sync(gmask, fE.w, 1, kGroup); }
+						if(PW == 2){ nQ.y = __shfl_down_sync(gmask, fQ.y, 1, kGroup); nQ.z = __shfl_down_sync(gmask, fQ.z, 1, kGroup); nQ.w = __shfl_down_sync(gmask, fQ.w, 1, kGroup); }
 					}
 					__syncwarp(gmask);
 					// anchors (:2310-2331, :2372-2389): a lane's anchor advances by its first mr cells, which this thread holds in fU;
