@@ -186,16 +186,39 @@ extern "C" bsb200_batch *bsb200_batch_upload(bsb200_ctx *ctx, int kind, uint64_t
 		memcpy(b->mtx, matrix, 16); b->go1 = go1; b->ge1 = ge1; b->go2 = go2; b->ge2 = ge2;
 		b->pw = epi8_piecewise(go1, ge1, go2, ge2, 16);
 	}
-	// ---- plan: per-pair band, trace footprint, heaviest-first order, waves ---------------------------
-	std::vector<uint64_t> work(n), tbytes(n);
+	// ---- the caller's arrays start crossing PCIe before the host plans: the copies do not depend on the plan ----------------
 	size_t seq_end = 0;
+	for(uint64_t i=0;i<n;i++) seq_end = std::max<size_t>(seq_end, std::max<size_t>(qoff[i] + qlen[i], toff[i] + tlen[i]));
+	cudaStream_t st = ctx->stream;
+	cudaError_t e = cudaSuccess;
+	auto R = [&](cudaError_t x){ if(e == cudaSuccess) e = x; };
+	// every early return below first waits for the copies in flight (they read the caller's memory)
+	auto bail = [&]() -> bsb200_batch* { cudaStreamSynchronize(st); bsb200_batch_free(ctx, b); return nullptr; };
+	R(b->d_seqs.reserve(seq_end + 16)); R(b->d_qoff.reserve(n * 8 + 8)); R(b->d_toff.reserve(n * 8 + 8));
+	R(b->d_qlen.reserve(n * 4 + 4)); R(b->d_tlen.reserve(n * 4 + 4));
+	if(e != cudaSuccess){ fail(ctx, "device allocation", e); return bail(); }
+	// (epi8 batches only: with a million short edit pairs the plan is the longer part and ran three times slower next to the DMA
+	// stream - config 4 end to end 53 -> 93 ms - so edit batches copy after planning)
+	const bool early = kind == 0;
+	auto copy_inputs = [&](){
+		cudaEventRecord(ctx->ev[0], st);
+		if(n){
+			R(cudaMemcpyAsync(b->d_seqs.p, seqs, seq_end, cudaMemcpyHostToDevice, st));
+			R(cudaMemcpyAsync(b->d_qoff.p, qoff, n * 8, cudaMemcpyHostToDevice, st));
+			R(cudaMemcpyAsync(b->d_toff.p, toff, n * 8, cudaMemcpyHostToDevice, st));
+			R(cudaMemcpyAsync(b->d_qlen.p, qlen, n * 4, cudaMemcpyHostToDevice, st));
+			R(cudaMemcpyAsync(b->d_tlen.p, tlen, n * 4, cudaMemcpyHostToDevice, st));
+		}
+	};
+	if(early) copy_inputs();
+	// ---- plan: per-pair band, trace footprint, heaviest-first order, waves ---------------------------
+	std::vector<uint64_t> work(kind == 0 ? n : 0), tbytes(kind == 0 ? n : 0);   // epi8 only (a million short edit pairs: every O(n) array counts)
 	b->max_bw = kind == 0 ? 16 : 64;
 	b->empty.assign(n, 0);
 	b->order.clear(); b->order.reserve(n);
 	for(uint64_t i=0;i<n;i++){
 		uint32_t bw;
-		seq_end = std::max<size_t>(seq_end, std::max<size_t>(qoff[i] + qlen[i], toff[i] + tlen[i]));
-		if(qlen[i] == 0 || tlen[i] == 0){ b->empty[i] = 1; work[i] = 0; tbytes[i] = 0; continue; } // bsalign.h:1051-1054
+		if(qlen[i] == 0 || tlen[i] == 0){ b->empty[i] = 1; continue; } // bsalign.h:1051-1054 (work/tbytes stay 0)
 		if(kind == 0){
 			bw = bsb200_epi8_bandwidth(qlen[i], bandwidth);
 			tbytes[i] = ((uint64_t)epi8_row_bytes(bw / 16, b->pw) + kMetaInts * 4) * ((uint64_t)tlen[i] + 1); // upper bound: with sub-lane anchors
@@ -208,7 +231,7 @@ extern "C" bsb200_batch *bsb200_batch_upload(bsb200_ctx *ctx, int kind, uint64_t
 			b->trace_bytes += ((uint64_t)bw / 4 + 4) * tlen[i];
 			b->max_q64 = std::max<uint32_t>(b->max_q64, (qlen[i] + 63) / 64 * 64);
 		}
-		work[i] = (uint64_t)bw * tlen[i];
+		if(kind == 0) work[i] = (uint64_t)bw * tlen[i];
 		b->max_bw = std::max(b->max_bw, bw);
 		b->order.push_back((uint32_t)i);
 	}
@@ -220,6 +243,8 @@ extern "C" bsb200_batch *bsb200_batch_upload(bsb200_ctx *ctx, int kind, uint64_t
 		uint64_t kmax = 0;
 		std::vector<uint64_t> key(nact);
 		for(uint32_t k=0;k<nact;k++){ uint32_t i = b->order[k]; key[k] = kind == 0 ? work[i] : (uint64_t)tlen[i]; kmax = std::max(kmax, key[k]); }
+		// the order only balances the schedule: epi8 keys are quantised to 16 bits so that the counting sort's table stays small
+		if(kind == 0){ int sh = 0; while((kmax >> sh) >= (1u << 16)) sh++; if(sh){ for(auto &kk : key) kk >>= sh; kmax >>= sh; } }
 		if(kmax < (1u << 22)){
 			std::vector<uint32_t> cnt(kmax + 2, 0);
 			for(uint32_t k=0;k<nact;k++) cnt[kmax - key[k] + 1]++;
@@ -240,7 +265,8 @@ extern "C" bsb200_batch *bsb200_batch_upload(bsb200_ctx *ctx, int kind, uint64_t
 		cudaMemGetInfo(&fr, &tot);
 		budget = (uint64_t)((fr + ctx->trace.cap + ctx->trace2.cap) * 0.80);
 	}
-	b->trace_off.assign(n + 1, 0);
+	const uint64_t ntoff = kind == 0 ? n : ((uint64_t)nact + 31) / 32;   // epi8: per pair; edit: per block of 32 pairs
+	b->trace_off.assign(ntoff + 1, 0);
 	b->cig_off.assign(n + 1, 0);
 	std::vector<uint32_t> block_rows;
 	if(kind == 0){
@@ -249,7 +275,7 @@ extern "C" bsb200_batch *bsb200_batch_upload(bsb200_ctx *ctx, int kind, uint64_t
 		Wave w = {0, 0, 0};
 		for(uint32_t k=0;k<nact;k++){
 			uint32_t i = b->order[k];
-			if(tbytes[i] > budget){ ctx->err = "a single pair needs more traceback memory than the budget"; bsb200_batch_free(ctx, b); return nullptr; }
+			if(tbytes[i] > budget){ ctx->err = "a single pair needs more traceback memory than the budget"; return bail(); }
 			if(w.trace_bytes + tbytes[i] > budget && w.end > w.beg){
 				b->waves.push_back(w);
 				w.beg = w.end; w.trace_bytes = 0;
@@ -270,7 +296,7 @@ extern "C" bsb200_batch *bsb200_batch_upload(bsb200_ctx *ctx, int kind, uint64_t
 			for(uint32_t k=lo;k<hi;k++) mt = std::max(mt, tlen[b->order[k]]);
 			uint64_t R = (uint64_t)mt + 1;
 			uint64_t bytes = R * WB * 2 * 32 * 8 + R * 32 * 4;
-			if(bytes > budget){ ctx->err = "a single block of pairs needs more traceback memory than the budget"; bsb200_batch_free(ctx, b); return nullptr; }
+			if(bytes > budget){ ctx->err = "a single block of pairs needs more traceback memory than the budget"; return bail(); }
 			if(w.trace_bytes + bytes > budget && w.end > w.beg){
 				b->waves.push_back(w);
 				w.beg = w.end; w.trace_bytes = 0;
@@ -289,32 +315,23 @@ extern "C" bsb200_batch *bsb200_batch_upload(bsb200_ctx *ctx, int kind, uint64_t
 	// ---- device buffers + H2D ---------------------------------------------------------------------------
 	uint64_t max_wave = 0;
 	for(auto &w : b->waves) max_wave = std::max(max_wave, w.trace_bytes);
-	cudaError_t e = cudaSuccess;
-	auto R = [&](cudaError_t x){ if(e == cudaSuccess) e = x; };
-	R(b->d_seqs.reserve(seq_end + 16)); R(b->d_qoff.reserve(n * 8 + 8)); R(b->d_toff.reserve(n * 8 + 8));
-	R(b->d_qlen.reserve(n * 4 + 4)); R(b->d_tlen.reserve(n * 4 + 4)); R(b->d_order.reserve(n * 4 + 4));
+	R(b->d_order.reserve(n * 4 + 4));
 	R(b->d_trace_off.reserve(n * 8 + 8)); R(b->d_results.reserve(n * 40 + 40)); R(b->d_status.reserve(n * 4 + 4));
 	R(b->d_ncigar.reserve(n * 4 + 4)); R(b->d_dense_off.reserve(n * 8 + 8)); R(b->d_dense_total.reserve(16));
 	if(want_cigar){ R(b->d_cig_raw.reserve(b->cig_words * 4 + 16)); R(b->d_cig_off.reserve((n + 1) * 8)); R(b->d_cig_dense.reserve(b->cig_words * 4 + 16)); }
 	R(ctx->trace.reserve(max_wave + 256)); R(ctx->counter.reserve(256));
 	if(kind == 1) R(b->d_block_rows.reserve(block_rows.size() * 4 + 16));
-	if(e != cudaSuccess){ fail(ctx, "device allocation", e); bsb200_batch_free(ctx, b); return nullptr; }
-	cudaStream_t st = ctx->stream;
-	cudaEventRecord(ctx->ev[0], st);
+	if(e != cudaSuccess){ fail(ctx, "device allocation", e); return bail(); }
+	if(!early) copy_inputs();
 	if(n){
-		R(cudaMemcpyAsync(b->d_seqs.p, seqs, seq_end, cudaMemcpyHostToDevice, st));
-		R(cudaMemcpyAsync(b->d_qoff.p, qoff, n * 8, cudaMemcpyHostToDevice, st));
-		R(cudaMemcpyAsync(b->d_toff.p, toff, n * 8, cudaMemcpyHostToDevice, st));
-		R(cudaMemcpyAsync(b->d_qlen.p, qlen, n * 4, cudaMemcpyHostToDevice, st));
-		R(cudaMemcpyAsync(b->d_tlen.p, tlen, n * 4, cudaMemcpyHostToDevice, st));
 		if(nact) R(cudaMemcpyAsync(b->d_order.p, b->order.data(), (size_t)nact * 4, cudaMemcpyHostToDevice, st));
 		if(kind == 1 && !block_rows.empty()) R(cudaMemcpyAsync(b->d_block_rows.p, block_rows.data(), block_rows.size() * 4, cudaMemcpyHostToDevice, st));
-		R(cudaMemcpyAsync(b->d_trace_off.p, b->trace_off.data(), n * 8, cudaMemcpyHostToDevice, st));
+		if(ntoff) R(cudaMemcpyAsync(b->d_trace_off.p, b->trace_off.data(), ntoff * 8, cudaMemcpyHostToDevice, st));
 		if(want_cigar) R(cudaMemcpyAsync(b->d_cig_off.p, b->cig_off.data(), (n + 1) * 8, cudaMemcpyHostToDevice, st));
 	}
 	cudaEventRecord(ctx->ev[1], st);
 	R(cudaStreamSynchronize(st)); // order/trace_off are host vectors owned by b, but seqs belong to the caller
-	if(e != cudaSuccess){ fail(ctx, "host to device copy", e); bsb200_batch_free(ctx, b); return nullptr; }
+	if(e != cudaSuccess){ fail(ctx, "host to device copy", e); return bail(); }
 	float ms = 0; cudaEventElapsedTime(&ms, ctx->ev[0], ctx->ev[1]);
 	ctx->timing = bsb200_timing_t();
 	ctx->timing.h2d_ms = ms;
