@@ -240,21 +240,24 @@ extern "C" bsb200_batch *bsb200_batch_upload(bsb200_ctx *ctx, int kind, uint64_t
 	{
 		// heaviest first (epi8: band cells; edit: target length, so the 32 pairs of a warp finish together); counting
 		// sort when the key range is small, else one sort of packed (key, index) words
+		// the order only balances the schedule: epi8 keys are quantised to 16 bits so that the counting sort's table stays small;
+		// the key is recomputed where it is used instead of being stored (one O(n) array less)
 		uint64_t kmax = 0;
-		std::vector<uint64_t> key(nact);
-		for(uint32_t k=0;k<nact;k++){ uint32_t i = b->order[k]; key[k] = kind == 0 ? work[i] : (uint64_t)tlen[i]; kmax = std::max(kmax, key[k]); }
-		// the order only balances the schedule: epi8 keys are quantised to 16 bits so that the counting sort's table stays small
-		if(kind == 0){ int sh = 0; while((kmax >> sh) >= (1u << 16)) sh++; if(sh){ for(auto &kk : key) kk >>= sh; kmax >>= sh; } }
+		for(uint32_t k=0;k<nact;k++){ uint32_t i = b->order[k]; kmax = std::max<uint64_t>(kmax, kind == 0 ? work[i] : (uint64_t)tlen[i]); }
+		int sh = 0;
+		if(kind == 0) while((kmax >> sh) >= (1u << 16)) sh++;
+		kmax >>= sh;
+		auto key_of = [&](uint32_t i) -> uint64_t { return kind == 0 ? (work[i] >> sh) : (uint64_t)tlen[i]; };
 		if(kmax < (1u << 22)){
 			std::vector<uint32_t> cnt(kmax + 2, 0);
-			for(uint32_t k=0;k<nact;k++) cnt[kmax - key[k] + 1]++;
+			for(uint32_t k=0;k<nact;k++) cnt[kmax - key_of(b->order[k]) + 1]++;
 			for(uint64_t v=1;v<cnt.size();v++) cnt[v] += cnt[v - 1];
 			std::vector<uint32_t> sorted(nact);
-			for(uint32_t k=0;k<nact;k++) sorted[cnt[kmax - key[k]]++] = b->order[k];
+			for(uint32_t k=0;k<nact;k++){ const uint32_t i = b->order[k]; sorted[cnt[kmax - key_of(i)]++] = i; }
 			b->order.swap(sorted);
 		} else {
 			std::vector<std::pair<uint64_t, uint32_t>> kv(nact);
-			for(uint32_t k=0;k<nact;k++) kv[k] = std::make_pair(~key[k], b->order[k]);
+			for(uint32_t k=0;k<nact;k++) kv[k] = std::make_pair(~key_of(b->order[k]), b->order[k]);
 			std::sort(kv.begin(), kv.end());
 			for(uint32_t k=0;k<nact;k++) b->order[k] = kv[k].second;
 		}
