@@ -189,6 +189,41 @@ def test_every_forward_instantiation(ctx):
             os.environ.pop(k, None)
 
 
+def test_asymmetric_and_long_narrow_pairs(ctx):
+    """Shapes that drive the band steering hard: a query against a window of it and against a target with long flanks (global mode
+    hurries the band to the end with shifts of many cells, overlap / extend end inside the target), bands wider than the query,
+    and long pairs under the narrowest bands.  Pairs on which the reference reads out of bounds must come back flagged."""
+    rng = np.random.default_rng(11)
+    pairs = []
+    for k in range(24):
+        ql = int(rng.integers(150, 1200))
+        q = rng.integers(0, 4, ql).astype(np.uint8)
+        if k % 3 == 0:      # target = a mutated window of the query
+            a_ = int(rng.integers(0, ql // 2)); w = q[a_:a_ + max(20, ql // 3)]
+            t, _ = synth.mutate_batch(rng, w[None, :], 0.02, 0.02, 0.02)
+        elif k % 3 == 1:    # target = mutated query with random flanks
+            m, _ = synth.mutate_batch(rng, q[None, :], 0.03, 0.03, 0.03)
+            t = np.concatenate([rng.integers(0, 4, int(rng.integers(0, 900))).astype(np.uint8), m, rng.integers(0, 4, int(rng.integers(0, 900))).astype(np.uint8)])
+        else:               # unrelated
+            t = rng.integers(0, 4, int(rng.integers(50, 2000))).astype(np.uint8)
+        pairs.append((q, np.ascontiguousarray(t, dtype=np.uint8)))
+    b = synth.PairBatch.from_lists(pairs)
+    for mode in (0, 1, 2):
+        for bw, gaps in [(16, (-3, -2, 0, 0)), (64, (-3, -2, -8, -1)), (256, (-3, -2, 0, 0)), (2048, (0, -2, 0, 0)), (0, (-3, -2, 0, 0))]:
+            errs = np.zeros(b.n, np.int32)
+            exp, ecg, _ = ck.oracle_batch("epi8", b, mode, bw, M26, gaps, errs=errs, nthreads=8)
+            assert_same(ctx.epi8_batch(b, mode, bw, M26, *gaps), exp, ecg, errs=errs, tag=("asym", mode, bw, gaps))
+        for bwe in (0, 64, 320):
+            errs = np.zeros(b.n, np.int32)
+            exp, ecg, _ = ck.oracle_batch("edit", b, mode, bwe, errs=errs, nthreads=8)
+            assert_same(ctx.edit_batch(b, mode, bwe), exp, ecg, errs=errs, tag=("asym-edit", mode, bwe))
+    long_b = synth.make_pairs(3, 30000, seed=77, p_sub=0.01, p_ins=0.01, p_del=0.01)
+    for mode, bw in [(0, 16), (1, 32), (0, 128)]:
+        errs = np.zeros(long_b.n, np.int32)
+        exp, ecg, _ = ck.oracle_batch("epi8", long_b, mode, bw, M26, (-3, -2, 0, 0), errs=errs, nthreads=3)
+        assert_same(ctx.epi8_batch(long_b, mode, bw, M26, -3, -2, 0, 0), exp, ecg, errs=errs, tag=("long", mode, bw))
+
+
 def test_dense_fetch_equals_scattered_fetch(ctx):
     b = synth.make_pairs(500, 200, seed=99)
     a = ctx.epi8_batch(b, 1, 64, M26, -3, -2, 0, 0)
