@@ -86,7 +86,7 @@ struct bsb200_batch {
 	int mode = 0; uint32_t bandwidth = 0;
 	int8_t mtx[16] = {}; int8_t go1 = 0, ge1 = 0, go2 = 0, ge2 = 0;
 	int pw = 0; int want_cigar = 1;
-	uint32_t max_bw = 16, max_q64 = 64;
+	uint32_t max_bw = 16, max_q64 = 64, max_qlen = 0;
 	std::vector<uint8_t> empty;
 	uint64_t cells = 0, trace_bytes = 0, cig_words = 0;
 	std::vector<Wave> waves;
@@ -233,6 +233,7 @@ extern "C" bsb200_batch *bsb200_batch_upload(bsb200_ctx *ctx, int kind, uint64_t
 		}
 		if(kind == 0) work[i] = (uint64_t)bw * tlen[i];
 		b->max_bw = std::max(b->max_bw, bw);
+		b->max_qlen = std::max(b->max_qlen, qlen[i]);
 		b->order.push_back((uint32_t)i);
 	}
 	b->seq_bytes = seq_end;
@@ -495,7 +496,8 @@ extern "C" int bsb200_batch_run(bsb200_ctx *ctx, bsb200_batch *b){
 			const bool anch = epi8_use_anchors(b->max_bw / 16);
 			a.gpw = 4;
 			int rc;
-			const bool full = b->bandwidth == 0 && !getenv("BSB200_NOFULL");   // (BSB200_NOFULL: tests run the general instantiation on full bands too)
+			// every band covers its whole query: bandwidth 0, or a bandwidth (rounded up to 16 by the kernel) no shorter than the longest query
+			const bool full = (b->bandwidth == 0 || (b->bandwidth + 15) / 16 * 16 >= b->max_qlen) && !getenv("BSB200_NOFULL");   // (BSB200_NOFULL: tests run the general instantiation on full bands too)
 			if(fast) rc = anch ? launch_epi8_forward_pw<true, true>(ctx, a, np, b->pw, full) : launch_epi8_forward_pw<true, false>(ctx, a, np, b->pw, full);
 			else rc = anch ? launch_epi8_forward_pw<false, true>(ctx, a, np, b->pw, full) : launch_epi8_forward_pw<false, false>(ctx, a, np, b->pw, full);
 			if(rc) return rc;

@@ -219,7 +219,7 @@ __device__ __forceinline__ int group_getscore(const int8_t *sU, const int32_t *s
 // NARROW: fewer than 4 groups per warp (very wide bands); the normal kernels keep compile-time full-warp masks
 // LAT: latency-bound batches (a few warps per SM): short F chain (dp_step) and the next chunk's loads issued before the
 // current chunk's arithmetic
-// FULL: bandwidth 0, every pair's band covers its whole query: the band never moves (bsalign.h:3932 needs rbeg + bw < qlen),
+// FULL: every pair's band covers its whole query (bandwidth 0, or a bandwidth no shorter than the longest query): the band never moves (bsalign.h:3932 needs rbeg + bw < qlen),
 // so the shift and steering code is left out of the instantiation.  These kernels are compiled for 4 CTAs per SM (<= 128 registers;
 // ptxas then takes ~115 instead of ~80 and schedules the hot loops better: c2 forward 82.5 -> 81.1 ms, 10 kb global 264 -> 248 ms);
 // the same bound made the general kernels slower (c3 83.8 -> 90.6 ms), so they keep the default.
