@@ -35,6 +35,7 @@ WORKLOADS = {
                desc="BASELINE configs[2]: 10k pairs 10kb x 10kb ONT-like, overlap, band 512"),
     "c4": dict(kind="edit", pairs=1000000, qlen=300, err=(0.02, 0.02, 0.02), mode=0, bandwidth=64,
                desc="BASELINE configs[3]: 1M pairs 300bp x 300bp, 2-bit edit, band 64"),
+    # g10k: `pairs` is the fallback; on a GPU main() takes as many pairs as one wave of the traceback store seats
     "g10k": dict(kind="epi8", pairs=592, qlen=10000, err=(0.03, 0.03, 0.04), mode=0, bandwidth=0,
                  desc="north_star target: 10kb x 10kb global, full band"),
     # POA: `pairs` = MSA jobs per GPU stepped in lock-step; one step = one sweep round (every job aligns its next read
@@ -389,6 +390,16 @@ def main():
     world = int(os.environ.get("WORLD_SIZE", "1"))
     w = WORKLOADS[args.workload]
     pairs = args.pairs or w["pairs"]
+    if args.workload == "g10k" and not args.pairs and args.impl == "ours":
+        # a 10 kb x 10 kb pair is one dependency chain (one warp's issue rate): throughput comes from the number of pairs in flight,
+        # which the traceback store bounds (215 MB per pair incl. anchors and row padding).  Take what ONE wave of the library's
+        # default budget (90 % of free HBM) seats, with 3 % to spare.
+        try:
+            import torch
+            free, _total = torch.cuda.mem_get_info(local_rank)
+            pairs = max(148, int(0.90 * free * 0.97 / 217.5e6))
+        except Exception:
+            pass
     ncores = os.cpu_count() or 1
     if w["kind"] == "poa":
         return main_poa(args, w, pairs, ncores, rank, local_rank, world)

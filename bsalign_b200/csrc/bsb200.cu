@@ -29,11 +29,12 @@ using namespace bsb200;
 
 struct DevBuf {
 	void *p = nullptr; size_t cap = 0;
-	cudaError_t reserve(size_t n){
+	// exact: no growth slack (the traceback arena is sized against the free memory)
+	cudaError_t reserve(size_t n, bool exact = false){
 		if(n <= cap) return cudaSuccess;
 		if(p) cudaFree(p);
 		p = nullptr; cap = 0;
-		size_t want = n + n / 8 + 256;
+		size_t want = exact ? n + 256 : n + n / 8 + 256;
 		cudaError_t e = cudaMalloc(&p, want);
 		if(e == cudaSuccess) cap = want;
 		return e;
@@ -188,7 +189,11 @@ extern "C" bsb200_batch *bsb200_batch_upload(bsb200_ctx *ctx, int kind, uint64_t
 	}
 	// ---- the caller's arrays start crossing PCIe before the host plans: the copies do not depend on the plan ----------------
 	size_t seq_end = 0;
-	for(uint64_t i=0;i<n;i++) seq_end = std::max<size_t>(seq_end, std::max<size_t>(qoff[i] + qlen[i], toff[i] + tlen[i]));
+	uint64_t cig_cap_words = 0;   // per-pair cigar capacity (qlen + tlen + 2 words), summed: sizes the side buffers
+	for(uint64_t i=0;i<n;i++){
+		seq_end = std::max<size_t>(seq_end, std::max<size_t>(qoff[i] + qlen[i], toff[i] + tlen[i]));
+		if(qlen[i] && tlen[i]) cig_cap_words += (uint64_t)qlen[i] + tlen[i] + 2;
+	}
 	cudaStream_t st = ctx->stream;
 	cudaError_t e = cudaSuccess;
 	auto R = [&](cudaError_t x){ if(e == cudaSuccess) e = x; };
@@ -267,7 +272,12 @@ extern "C" bsb200_batch *bsb200_batch_upload(bsb200_ctx *ctx, int kind, uint64_t
 	if(budget == 0){
 		size_t fr = 0, tot = 0;
 		cudaMemGetInfo(&fr, &tot);
-		budget = (uint64_t)((fr + ctx->trace.cap + ctx->trace2.cap) * 0.80);
+		// 90 % of what is free after this batch's other device buffers (sequences, tables, results, two cigar arenas; counted in
+		// full although cached ones are re-used) and the same again for a second batch on this context: batches whose pairs are bound
+		// by a dependency chain (10 kb bands: one warp's issue rate per pair) gain throughput only through the pairs a wave seats
+		const uint64_t side = seq_end + n * 100 + (want_cigar ? cig_cap_words * 8 + n * 8 : 0) + (64ull << 20);
+		const uint64_t avail = (uint64_t)fr + ctx->trace.cap + ctx->trace2.cap;
+		budget = avail > 2 * side ? (uint64_t)((avail - 2 * side) * 0.90) : avail / 2;
 	}
 	const uint64_t ntoff = kind == 0 ? n : ((uint64_t)nact + 31) / 32;   // epi8: per pair; edit: per block of 32 pairs
 	b->trace_off.assign(ntoff + 1, 0);
@@ -323,7 +333,7 @@ extern "C" bsb200_batch *bsb200_batch_upload(bsb200_ctx *ctx, int kind, uint64_t
 	R(b->d_trace_off.reserve(n * 8 + 8)); R(b->d_results.reserve(n * 40 + 40)); R(b->d_status.reserve(n * 4 + 4));
 	R(b->d_ncigar.reserve(n * 4 + 4)); R(b->d_dense_off.reserve(n * 8 + 8)); R(b->d_dense_total.reserve(16));
 	if(want_cigar){ R(b->d_cig_raw.reserve(b->cig_words * 4 + 16)); R(b->d_cig_off.reserve((n + 1) * 8)); R(b->d_cig_dense.reserve(b->cig_words * 4 + 16)); }
-	R(ctx->trace.reserve(max_wave + 256)); R(ctx->counter.reserve(256));
+	R(ctx->trace.reserve(max_wave + 256, true)); R(ctx->counter.reserve(256));
 	if(kind == 1) R(b->d_block_rows.reserve(block_rows.size() * 4 + 16));
 	if(e != cudaSuccess){ fail(ctx, "device allocation", e); return bail(); }
 	if(!early) copy_inputs();
@@ -405,7 +415,10 @@ static int launch_epi8_forward(bsb200_ctx *ctx, Epi8Args a, uint32_t npairs, boo
 	}
 	if(best_gpw < 4){
 		if constexpr (ANCH){
-			if constexpr (FAST && PW == 1){ if(lat) return go(epi8_forward_kernel<PW, FAST, true, true, true>); }
+			if constexpr (FAST && PW == 1){
+				if(full) return lat ? go(epi8_forward_kernel<PW, FAST, true, true, true, true>) : go(epi8_forward_kernel<PW, FAST, true, true, false, true>);
+				if(lat) return go(epi8_forward_kernel<PW, FAST, true, true, true>);
+			}
 			return go(epi8_forward_kernel<PW, FAST, true, true>);
 		} else { ctx->err = "internal: narrow warps without anchors"; return -1; }
 	}

@@ -61,7 +61,7 @@ typedef struct {
 } bsb200_timing_t;
 
 /* ---- context ------------------------------------------------------------------------------------ */
-/* device: CUDA ordinal.  trace_budget_bytes: cap for the traceback store per wave (0 = 80% of free HBM). */
+/* device: CUDA ordinal.  trace_budget_bytes: cap for the traceback store per wave (0 = 90% of free HBM). */
 bsb200_ctx *bsb200_create(int device, uint64_t trace_budget_bytes);
 void bsb200_destroy(bsb200_ctx *ctx);
 const char *bsb200_last_error(bsb200_ctx *ctx);   /* "" when the last call succeeded */
