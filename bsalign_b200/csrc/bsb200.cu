@@ -66,6 +66,7 @@ struct bsb200_ctx {
 	cudaStream_t stream_bt = nullptr;   // traceback kernels run here, concurrently with the next wave's forward kernel
 	cudaEvent_t ev[8] = {};
 	uint64_t trace_budget = 0;
+	uint64_t auto_budget = 0;   // last automatic budget computed from cudaMemGetInfo
 	std::string err;
 	bsb200_timing_t timing = {};
 	DevBuf trace;       // traceback arena, even waves (shared by all batches of this context; one batch runs at a time)
@@ -268,72 +269,103 @@ extern "C" bsb200_batch *bsb200_batch_upload(bsb200_ctx *ctx, int kind, uint64_t
 			for(uint32_t k=0;k<nact;k++) b->order[k] = kv[k].second;
 		}
 	}
-	uint64_t budget = ctx->trace_budget;
-	if(budget == 0){
+	// Budget of the traceback arena per wave.  Automatic (trace_budget 0): 90 % of what is free after this batch's other device
+	// buffers (sequences, tables, results, two cigar arenas; counted in full although cached ones are re-used) and the same again
+	// for a second batch on this context: batches whose pairs are bound by a dependency chain (10 kb bands: one warp's issue rate
+	// per pair) gain throughput only through the pairs a wave seats.  cudaMemGetInfo takes milliseconds once a 100+ GB arena
+	// exists, so an existing arena is planned against first and the device is only asked when that splits the batch and the last
+	// answer promised noticeably more.
+	auto query_budget = [&]() -> uint64_t {
 		size_t fr = 0, tot = 0;
 		cudaMemGetInfo(&fr, &tot);
-		// 90 % of what is free after this batch's other device buffers (sequences, tables, results, two cigar arenas; counted in
-		// full although cached ones are re-used) and the same again for a second batch on this context: batches whose pairs are bound
-		// by a dependency chain (10 kb bands: one warp's issue rate per pair) gain throughput only through the pairs a wave seats
 		const uint64_t side = seq_end + n * 100 + (want_cigar ? cig_cap_words * 8 + n * 8 : 0) + (64ull << 20);
 		const uint64_t avail = (uint64_t)fr + ctx->trace.cap + ctx->trace2.cap;
-		budget = avail > 2 * side ? (uint64_t)((avail - 2 * side) * 0.90) : avail / 2;
+		ctx->auto_budget = avail > 2 * side ? (uint64_t)((avail - 2 * side) * 0.90) : avail / 2;
+		return ctx->auto_budget;
+	};
+	uint64_t budget = ctx->trace_budget;
+	bool queried = budget != 0;
+	if(budget == 0){
+		if(ctx->trace.cap > 512) budget = ctx->trace.cap - 512;
+		else { budget = query_budget(); queried = true; }
 	}
 	const uint64_t ntoff = kind == 0 ? n : ((uint64_t)nact + 31) / 32;   // epi8: per pair; edit: per block of 32 pairs
-	b->trace_off.assign(ntoff + 1, 0);
 	b->cig_off.assign(n + 1, 0);
-	std::vector<uint32_t> block_rows;
-	if(kind == 0){
-		// as few waves as the trace budget allows: a wave must keep every SM's groups busy, and splitting further to
-		// overlap the traceback with the next forward sweep cost more (idle groups, co-scheduling) than it hid
-		Wave w = {0, 0, 0};
-		for(uint32_t k=0;k<nact;k++){
-			uint32_t i = b->order[k];
-			if(tbytes[i] > budget){ ctx->err = "a single pair needs more traceback memory than the budget"; return bail(); }
-			if(w.trace_bytes + tbytes[i] > budget && w.end > w.beg){
-				b->waves.push_back(w);
-				w.beg = w.end; w.trace_bytes = 0;
-			}
-			b->trace_off[i] = w.trace_bytes;
-			w.trace_bytes += tbytes[i];
-			w.end = k + 1;
-		}
-		if(w.end > w.beg) b->waves.push_back(w);
-	} else {
-		// 32 consecutive pairs (one warp) share an interleaved trace block sized by the longest target in it
-		const uint32_t WB = b->max_bw / 64;
-		const uint32_t nblk = (nact + 31) / 32;
-		block_rows.assign(nblk + 1, 0);
-		Wave w = {0, 0, 0};
-		for(uint32_t bk=0;bk<nblk;bk++){
-			uint32_t lo = bk * 32, hi = std::min<uint32_t>(lo + 32, nact), mt = 0;
-			for(uint32_t k=lo;k<hi;k++) mt = std::max(mt, tlen[b->order[k]]);
-			uint64_t R = (uint64_t)mt + 1;
-			uint64_t bytes = R * WB * 2 * 32 * 8 + R * 32 * 4;
-			if(bytes > budget){ ctx->err = "a single block of pairs needs more traceback memory than the budget"; return bail(); }
-			if(w.trace_bytes + bytes > budget && w.end > w.beg){
-				b->waves.push_back(w);
-				w.beg = w.end; w.trace_bytes = 0;
-			}
-			block_rows[bk] = (uint32_t)R;
-			b->trace_off[bk] = w.trace_bytes;
-			w.trace_bytes += bytes;
-			w.end = hi;
-		}
-		if(w.end > w.beg) b->waves.push_back(w);
-	}
 	if(want_cigar){
 		for(uint64_t i=0;i<n;i++) b->cig_off[i + 1] = b->cig_off[i] + ((qlen[i] && tlen[i]) ? (uint64_t)qlen[i] + tlen[i] + 2 : 0);
 		b->cig_words = b->cig_off[n];
 	}
-	// ---- device buffers + H2D ---------------------------------------------------------------------------
-	uint64_t max_wave = 0;
-	for(auto &w : b->waves) max_wave = std::max(max_wave, w.trace_bytes);
+	// ---- device buffers: everything but the traceback arena first, the arena takes what is left ---------------------
 	R(b->d_order.reserve(n * 4 + 4));
 	R(b->d_trace_off.reserve(n * 8 + 8)); R(b->d_results.reserve(n * 40 + 40)); R(b->d_status.reserve(n * 4 + 4));
 	R(b->d_ncigar.reserve(n * 4 + 4)); R(b->d_dense_off.reserve(n * 8 + 8)); R(b->d_dense_total.reserve(16));
 	if(want_cigar){ R(b->d_cig_raw.reserve(b->cig_words * 4 + 16)); R(b->d_cig_off.reserve((n + 1) * 8)); R(b->d_cig_dense.reserve(b->cig_words * 4 + 16)); }
-	R(ctx->trace.reserve(max_wave + 256, true)); R(ctx->counter.reserve(256));
+	R(ctx->counter.reserve(256));
+	if(e != cudaSuccess){ fail(ctx, "device allocation", e); return bail(); }
+	std::vector<uint32_t> block_rows;
+	// ---- waves against the budget; when the arena of an automatic budget cannot be had after all (memory taken by someone else
+	// since the query), plan again with three quarters of it ---------------------------------------------------------------
+	for(int attempt=0;;attempt++){
+		b->waves.clear();
+		b->trace_off.assign(ntoff + 1, 0);
+		if(kind == 0){
+			// as few waves as the trace budget allows: a wave must keep every SM's groups busy, and splitting further to
+			// overlap the traceback with the next forward sweep cost more (idle groups, co-scheduling) than it hid
+			Wave w = {0, 0, 0};
+			for(uint32_t k=0;k<nact;k++){
+				uint32_t i = b->order[k];
+				if(tbytes[i] > budget){
+					if(!queried){ queried = true; const uint64_t bq = query_budget(); if(bq > budget){ budget = bq; w.end = w.beg = 0; k = (uint32_t)-1; b->waves.clear(); w.trace_bytes = 0; continue; } }
+					ctx->err = "a single pair needs more traceback memory than the budget"; return bail();
+				}
+				if(w.trace_bytes + tbytes[i] > budget && w.end > w.beg){
+					b->waves.push_back(w);
+					w.beg = w.end; w.trace_bytes = 0;
+				}
+				b->trace_off[i] = w.trace_bytes;
+				w.trace_bytes += tbytes[i];
+				w.end = k + 1;
+			}
+			if(w.end > w.beg) b->waves.push_back(w);
+		} else {
+			// 32 consecutive pairs (one warp) share an interleaved trace block sized by the longest target in it
+			const uint32_t WB = b->max_bw / 64;
+			const uint32_t nblk = (nact + 31) / 32;
+			block_rows.assign(nblk + 1, 0);
+			Wave w = {0, 0, 0};
+			for(uint32_t bk=0;bk<nblk;bk++){
+				uint32_t lo = bk * 32, hi = std::min<uint32_t>(lo + 32, nact), mt = 0;
+				for(uint32_t k=lo;k<hi;k++) mt = std::max(mt, tlen[b->order[k]]);
+				uint64_t R_ = (uint64_t)mt + 1;
+				uint64_t bytes = R_ * WB * 2 * 32 * 8 + R_ * 32 * 4;
+				if(bytes > budget){
+					if(!queried){ queried = true; const uint64_t bq = query_budget(); if(bq > budget){ budget = bq; w.end = w.beg = 0; bk = (uint32_t)-1; b->waves.clear(); w.trace_bytes = 0; continue; } }
+					ctx->err = "a single block of pairs needs more traceback memory than the budget"; return bail();
+				}
+				if(w.trace_bytes + bytes > budget && w.end > w.beg){
+					b->waves.push_back(w);
+					w.beg = w.end; w.trace_bytes = 0;
+				}
+				block_rows[bk] = (uint32_t)R_;
+				b->trace_off[bk] = w.trace_bytes;
+				w.trace_bytes += bytes;
+				w.end = hi;
+			}
+			if(w.end > w.beg) b->waves.push_back(w);
+		}
+		if(!queried && b->waves.size() > 1 && (ctx->auto_budget == 0 || ctx->auto_budget > budget + budget / 4)){
+			queried = true;
+			const uint64_t bq = query_budget();
+			if(bq > budget + budget / 4){ budget = bq; continue; }   // a noticeably larger arena can be had: plan again
+		}
+		uint64_t max_wave = 0;
+		for(auto &w : b->waves) max_wave = std::max(max_wave, w.trace_bytes);
+		const cudaError_t ea = ctx->trace.reserve(max_wave + 256, true);
+		if(ea == cudaSuccess) break;
+		cudaGetLastError();   // clear the sticky allocation error
+		if(ctx->trace_budget != 0 || attempt >= 3){ fail(ctx, "device allocation (traceback arena)", ea); return bail(); }
+		budget = budget / 4 * 3;
+	}
 	if(kind == 1) R(b->d_block_rows.reserve(block_rows.size() * 4 + 16));
 	if(e != cudaSuccess){ fail(ctx, "device allocation", e); return bail(); }
 	if(!early) copy_inputs();
