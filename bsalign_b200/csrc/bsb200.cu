@@ -14,6 +14,7 @@
 #include <cub/iterator/transform_input_iterator.cuh>
 
 #include <algorithm>
+#include <chrono>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -175,6 +176,10 @@ extern "C" bsb200_batch *bsb200_batch_upload(bsb200_ctx *ctx, int kind, uint64_t
 		fail(ctx, "bsb200_batch_upload", cudaSuccess); return nullptr;
 	}
 	cudaSetDevice(ctx->device);
+	// BSB200_HOSTPROF=1: wall-clock split of this call on stderr (development aid)
+	const bool hostprof = getenv("BSB200_HOSTPROF") != nullptr;
+	auto tp0 = std::chrono::steady_clock::now();
+	auto lap = [&](const char *what){ if(hostprof){ auto t1 = std::chrono::steady_clock::now(); fprintf(stderr, "[upload] %-28s %8.3f ms\n", what, std::chrono::duration<double, std::milli>(t1 - tp0).count()); tp0 = t1; } };
 	bsb200_batch *b = new bsb200_batch();
 	{
 		DevBuf *ds[] = {&b->d_seqs, &b->d_qoff, &b->d_toff, &b->d_qlen, &b->d_tlen, &b->d_order, &b->d_trace_off, &b->d_results, &b->d_status,
@@ -203,9 +208,9 @@ extern "C" bsb200_batch *bsb200_batch_upload(bsb200_ctx *ctx, int kind, uint64_t
 	R(b->d_seqs.reserve(seq_end + 16)); R(b->d_qoff.reserve(n * 8 + 8)); R(b->d_toff.reserve(n * 8 + 8));
 	R(b->d_qlen.reserve(n * 4 + 4)); R(b->d_tlen.reserve(n * 4 + 4));
 	if(e != cudaSuccess){ fail(ctx, "device allocation", e); return bail(); }
-	// (epi8 batches only: with a million short edit pairs the plan is the longer part and ran three times slower next to the DMA
-	// stream - config 4 end to end 53 -> 93 ms - so edit batches copy after planning)
-	const bool early = kind == 0;
+	// (a first attempt ran the plan of a million edit pairs three times slower next to the DMA stream - config 4 end to end
+	// 53 -> 93 ms; once the plan no longer touched 50 MB of fresh per-pair arrays the overlap paid off: 35.6 -> 28.1 ms)
+	const bool early = true;
 	auto copy_inputs = [&](){
 		cudaEventRecord(ctx->ev[0], st);
 		if(n){
@@ -217,6 +222,7 @@ extern "C" bsb200_batch *bsb200_batch_upload(bsb200_ctx *ctx, int kind, uint64_t
 		}
 	};
 	if(early) copy_inputs();
+	lap("buffers + seq_end + early H2D");
 	// ---- plan: per-pair band, trace footprint, heaviest-first order, waves ---------------------------
 	std::vector<uint64_t> work(kind == 0 ? n : 0), tbytes(kind == 0 ? n : 0);   // epi8 only (a million short edit pairs: every O(n) array counts)
 	b->max_bw = kind == 0 ? 16 : 64;
@@ -244,6 +250,7 @@ extern "C" bsb200_batch *bsb200_batch_upload(bsb200_ctx *ctx, int kind, uint64_t
 	}
 	b->seq_bytes = seq_end;
 	const uint32_t nact = (uint32_t)b->order.size();
+	lap("per-pair loop");
 	{
 		// heaviest first (epi8: band cells; edit: target length, so the 32 pairs of a warp finish together); counting
 		// sort when the key range is small, else one sort of packed (key, index) words
@@ -269,6 +276,7 @@ extern "C" bsb200_batch *bsb200_batch_upload(bsb200_ctx *ctx, int kind, uint64_t
 			for(uint32_t k=0;k<nact;k++) b->order[k] = kv[k].second;
 		}
 	}
+	lap("sort");
 	// Budget of the traceback arena per wave.  Automatic (trace_budget 0): 90 % of what is free after this batch's other device
 	// buffers (sequences, tables, results, two cigar arenas; counted in full although cached ones are re-used) and the same again
 	// for a second batch on this context: batches whose pairs are bound by a dependency chain (10 kb bands: one warp's issue rate
@@ -295,6 +303,7 @@ extern "C" bsb200_batch *bsb200_batch_upload(bsb200_ctx *ctx, int kind, uint64_t
 		for(uint64_t i=0;i<n;i++) b->cig_off[i + 1] = b->cig_off[i] + ((qlen[i] && tlen[i]) ? (uint64_t)qlen[i] + tlen[i] + 2 : 0);
 		b->cig_words = b->cig_off[n];
 	}
+	lap("cig_off");
 	// ---- device buffers: everything but the traceback arena first, the arena takes what is left ---------------------
 	R(b->d_order.reserve(n * 4 + 4));
 	R(b->d_trace_off.reserve(n * 8 + 8)); R(b->d_results.reserve(n * 40 + 40)); R(b->d_status.reserve(n * 4 + 4));
@@ -302,6 +311,7 @@ extern "C" bsb200_batch *bsb200_batch_upload(bsb200_ctx *ctx, int kind, uint64_t
 	if(want_cigar){ R(b->d_cig_raw.reserve(b->cig_words * 4 + 16)); R(b->d_cig_off.reserve((n + 1) * 8)); R(b->d_cig_dense.reserve(b->cig_words * 4 + 16)); }
 	R(ctx->counter.reserve(256));
 	if(e != cudaSuccess){ fail(ctx, "device allocation", e); return bail(); }
+	lap("side buffers");
 	std::vector<uint32_t> block_rows;
 	// ---- waves against the budget; when the arena of an automatic budget cannot be had after all (memory taken by someone else
 	// since the query), plan again with three quarters of it ---------------------------------------------------------------
@@ -366,6 +376,7 @@ extern "C" bsb200_batch *bsb200_batch_upload(bsb200_ctx *ctx, int kind, uint64_t
 		if(ctx->trace_budget != 0 || attempt >= 3){ fail(ctx, "device allocation (traceback arena)", ea); return bail(); }
 		budget = budget / 4 * 3;
 	}
+	lap("waves + arena");
 	if(kind == 1) R(b->d_block_rows.reserve(block_rows.size() * 4 + 16));
 	if(e != cudaSuccess){ fail(ctx, "device allocation", e); return bail(); }
 	if(!early) copy_inputs();
@@ -378,6 +389,7 @@ extern "C" bsb200_batch *bsb200_batch_upload(bsb200_ctx *ctx, int kind, uint64_t
 	cudaEventRecord(ctx->ev[1], st);
 	R(cudaStreamSynchronize(st)); // order/trace_off are host vectors owned by b, but seqs belong to the caller
 	if(e != cudaSuccess){ fail(ctx, "host to device copy", e); return bail(); }
+	lap("H2D + sync");
 	float ms = 0; cudaEventElapsedTime(&ms, ctx->ev[0], ctx->ev[1]);
 	ctx->timing = bsb200_timing_t();
 	ctx->timing.h2d_ms = ms;
