@@ -7,6 +7,7 @@
 #include "../../include/bsalign_b200.h"
 #include "common.cuh"
 #include "epi8_forward.cuh"
+#include "epi8_wave.cuh"
 #include "epi8_backcal.cuh"
 #include "edit_kernels.cuh"
 
@@ -233,7 +234,8 @@ extern "C" bsb200_batch *bsb200_batch_upload(bsb200_ctx *ctx, int kind, uint64_t
 		if(qlen[i] == 0 || tlen[i] == 0){ b->empty[i] = 1; continue; } // bsalign.h:1051-1054 (work/tbytes stay 0)
 		if(kind == 0){
 			bw = bsb200_epi8_bandwidth(qlen[i], bandwidth);
-			tbytes[i] = ((uint64_t)epi8_row_bytes(bw / 16, b->pw) + kMetaInts * 4) * ((uint64_t)tlen[i] + 1); // upper bound: with sub-lane anchors
+			// upper bound: with sub-lane anchors, and with the extra slots of the wavefront kernel's skewed layout
+			tbytes[i] = ((uint64_t)epi8_row_bytes(bw / 16, b->pw) + kMetaInts * 4) * ((uint64_t)tlen[i] + 1 + kWaveSlack);
 			tbytes[i] = (tbytes[i] + 15) / 16 * 16;
 			b->cells += (uint64_t)std::min<uint32_t>(bw, (qlen[i] + 15) / 16 * 16) * tlen[i];
 			b->trace_bytes += ((uint64_t)bw * (b->pw + 1) + 84) * tlen[i];
@@ -452,6 +454,24 @@ static int launch_epi8_forward(bsb200_ctx *ctx, Epi8Args a, uint32_t npairs, boo
 	// by ALU throughput: they take the LAT instantiation (short F chain, loads of the next chunk in flight; affine gaps only)
 	bool lat = false;
 	if constexpr (FAST && PW == 1){
+		// full-band affine batches with scores inside +-63: the single-pass wavefront kernel (epi8_wave.cuh), then the two-pass
+		// kernel below over the pairs it flagged (normally none: that launch only reads the status words)
+		bool wave = full && !getenv("BSB200_NOWAVE");
+		for(int k=0;k<16;k++) if(a.mtx[k] > 63 || a.mtx[k] < -63) wave = false;
+		if(wave && (best_gpw == 4 || ANCH)){
+			a.redo = 0;
+			a.force_redo = getenv("BSB200_WAVE_REDO") ? 1 : 0;
+			int rc;
+			if(best_gpw < 4){
+				if constexpr (ANCH) rc = go(epi8_wave_kernel<true, true>); else rc = -1;
+			} else rc = go(epi8_wave_kernel<ANCH, false>);
+			if(rc) return rc;
+			ctx->timing.forward_launches++;
+			CK(cudaMemsetAsync(a.counter, 0, 16, ctx->stream));
+			a.redo = 1;
+		}
+	}
+	if constexpr (FAST && PW == 1){
 		const uint64_t seated = std::min<uint64_t>(npairs, (uint64_t)best_groups * ctx->num_sms);
 		const uint64_t warps_per_sm = (seated + (uint64_t)best_gpw * ctx->num_sms - 1) / ((uint64_t)best_gpw * ctx->num_sms);
 		lat = warps_per_sm <= 8;
@@ -543,7 +563,7 @@ extern "C" int bsb200_batch_run(bsb200_ctx *ctx, bsb200_batch *b){
 			// groups of a warp keep their small per-group words (anchors, F hand-over) on different banks
 			a.group_smem = (uint32_t)(((size_t)a.max_img * (b->pw + 2) + (kMetaInts * 2) * 4 + 32 + 32 * 4 + 127) / 128 * 128 + 32);
 			a.mode = b->mode; memcpy(a.mtx, b->mtx, 16); a.go1 = b->go1; a.ge1 = b->ge1; a.go2 = b->go2; a.ge2 = b->ge2;
-			a.all_ones = 0xffffffffu;
+			a.all_ones = 0xffffffffu; a.redo = 0; a.force_redo = 0;
 			a.smax = -127; a.smin = 127;
 			for(int k=0;k<16;k++){ a.smax = std::max(a.smax, b->mtx[k]); a.smin = std::min(a.smin, b->mtx[k]); }
 			// all gap costs <= 0 (the normal case): saturation bounds that cannot bind are dropped (epi8_forward.cuh)

@@ -33,12 +33,20 @@ struct Epi8BtArgs {
 
 struct TraceView {
 	const uint8_t *tr; const int32_t *meta; uint32_t bw, W, IB, RS, AOFF; int tlen, ubias, anch;
-	__device__ __forceinline__ int beg(int row) const { return meta[(size_t)kMetaInts * (row + 1) + 17]; }
-	__device__ __forceinline__ int ub(int row, int j) const { return meta[(size_t)kMetaInts * (row + 1) + j]; }
+	// skew = 1: the pair was written by the wavefront kernel (epi8_wave.cuh): lane j's row y sits in image slot y + 1 + j, the end
+	// anchor ub[k] (k >= 1) of row y in record y + k of `meta` (16 ints per record), ub[0] in `ub0`, and the band never moved
+	int skew; const int32_t *ub0;
+	__device__ __forceinline__ int beg(int row) const { return skew ? 0 : meta[(size_t)kMetaInts * (row + 1) + 17]; }
+	__device__ __forceinline__ int ub(int row, int j) const {
+		if(skew) return j ? meta[(size_t)16 * (row + j) + j - 1] : ub0[row + 1];
+		return meta[(size_t)kMetaInts * (row + 1) + j];
+	}
+	// first byte of the image slot that holds lane j of a row
+	__device__ __forceinline__ const uint8_t *slot(int row, uint32_t j) const { return tr + (size_t)RS * (row + 1 + (skew ? (int)j : 0)); }
 	// array arr (0 u, 1 e, 2 q) of the cell at band position p of a row
 	__device__ __forceinline__ int cell(int row, int arr, uint32_t p) const {
 		uint32_t j = p / W, i = p - j * W;
-		uint8_t b = tr[(size_t)RS * (row + 1) + (size_t)arr * IB + epi8_cell_offset(j, i)];
+		uint8_t b = slot(row, j)[(size_t)arr * IB + epi8_cell_offset(j, i)];
 		return (int)(int8_t)(arr == 0 && ubias ? (uint8_t)(b ^ 0x80) : b);
 	}
 	// H(col,row) = anchor of the lane + its u cells up to col (bsalign.h:3187-3202); sets err when the lookup leaves the band
@@ -54,8 +62,9 @@ struct TraceView {
 		int rw = ok ? row : -1;
 		const uint32_t i = up - j * W, g = anch ? i / kAnchorSteps : 0u;   // the sum starts at the sub-lane anchor before step 32g
 		p.n = ok ? i - g * kAnchorSteps + 1 : 0u;
-		p.ub = ok ? (g ? *(const int32_t*)(tr + (size_t)RS * (rw + 1) + AOFF + ((g - 1) * 16 + j) * 4) : ub(rw, j)) : kScoreMin;
-		p.r = tr + (size_t)RS * (rw + 1) + (size_t)(j >> 1) * 16 + (size_t)g * (kAnchorSteps / 8) * 128;
+		const uint8_t *sl = slot(rw, j);
+		p.ub = ok ? (g ? *(const int32_t*)(sl + AOFF + ((g - 1) * 16 + j) * 4) : ub(rw, j)) : kScoreMin;
+		p.r = sl + (size_t)(j >> 1) * 16 + (size_t)g * (kAnchorSteps / 8) * 128;
 		p.mk = (j & 1) ? 0x01000100 : 0x00010001;
 		const uint32_t nch = (p.n + 7) >> 3;
 		#pragma unroll
@@ -118,13 +127,16 @@ __global__ void __launch_bounds__(128) epi8_backcal_kernel(const Epi8BtArgs a){
 	tv.bw = (tv.bw + kLanes - 1) / kLanes * kLanes;
 	tv.W = tv.bw / kLanes; tv.IB = epi8_image_bytes(tv.W); tv.RS = a.anch ? epi8_row_bytes(tv.W, pw) : tv.IB * (pw + 1); tv.AOFF = tv.IB * (pw + 1); tv.anch = a.anch; tv.tlen = tlen; tv.ubias = a.ubias;
 	tv.tr = a.trace + a.trace_off[pair];
-	tv.meta = (const int32_t*)(tv.tr + (size_t)tv.RS * (tlen + 1));
+	int err = a.status[pair];
+	tv.skew = (err & kStSkew) ? 1 : 0;
+	err &= ~(kStSkew | kStRedo);
+	tv.meta = (const int32_t*)(tv.tr + (size_t)tv.RS * (tlen + 1 + (tv.skew ? kWaveSlack : 0u)));
+	tv.ub0 = tv.meta + (size_t)16 * (tlen + 1 + kWaveSlack);
 	const int bw = (int)tv.bw;
 	CigarSink cg;
 	cg.buf = a.cigars ? a.cigars + a.cig_off[pair] : nullptr;
 	cg.cap = a.cigars ? (uint32_t)(a.cig_off[pair + 1] - a.cig_off[pair]) : 0;
 	cg.n = 0; cg.run = 0; cg.err = 0;
-	int err = a.status[pair];
 	int qb = rs[2], tb = rs[4];
 	int mat = 0, mis = 0, ins = 0, del = 0, aln = 0;
 	int Hcur, Hprev = 0, pend = 0, prior = 0;
@@ -165,7 +177,7 @@ __global__ void __launch_bounds__(128) epi8_backcal_kernel(const Epi8BtArgs a){
 		const int crow = (state == kStep) ? tb - 1 : -1;                    // row of the cell above (valid memory in any state)
 		const uint32_t cx = cellok ? (uint32_t)x : 0u;
 		const uint32_t cj = cx / tv.W, coff = epi8_cell_offset(cj, cx - cj * tv.W);
-		const uint8_t *cp = tv.tr + (size_t)tv.RS * (crow + 1) + coff;
+		const uint8_t *cp = tv.slot(crow, cj) + coff;
 		const uint32_t ru = cp[0], re = pw >= 1 ? cp[tv.IB] : 0u, rq = pw == 2 ? cp[2 * (size_t)tv.IB] : 0u;
 		const uint32_t qbase = qs[qb >= 0 ? qb : 0], tbase = ts[tb >= 0 ? tb : 0];
 		TraceView::Pending pd;

@@ -43,6 +43,8 @@ struct Epi8Args {
 	int8_t go1, ge1, go2, ge2;
 	int8_t smax, smin;
 	uint32_t all_ones;           // 0xffffffff, passed at run time so that ~x can be issued as IMAD on the otherwise idle FMA pipe
+	int redo;                    // two-pass kernel: only take the pairs the wavefront kernel flagged (kStRedo)
+	int force_redo;              // wavefront kernel: flag every pair (test hook: exercises the redo path)
 };
 
 // ---- saturating s16x2 arithmetic ------------------------------------------------------------------------
@@ -282,6 +284,7 @@ __global__ void __launch_bounds__(kFwdThreads, FULL ? 4 : 0) epi8_forward_kernel
 			if(t == 0) idx = atomicAdd(a.counter, 1u);
 			idx = __shfl_sync(gmask, idx, lane & 24);
 			if(idx >= a.npairs) done = true;
+			else if(a.redo && !(a.status[a.order[idx]] & kStRedo)){ /* redo launch behind the wavefront kernel: this pair was not flagged */ }
 			else {
 				pair = a.order[idx];
 				qlen = a.qlen[pair]; tlen = a.tlen[pair];

@@ -1,0 +1,374 @@
+// epi8_wave.cuh -- single-pass "wavefront" forward kernel for full-band affine batches (replaces the two-pass row of
+// bsalign.h:2885-2960 + the F hand-over of bsalign.h:2639-2652 where that is provably the same computation).
+//
+// The reference evaluates a row twice because its 16 SSE lanes run side by side: pass 1 finds the F leaving every lane's
+// running block with nothing entering, a scalar scan hands F from block to block, pass 2 computes the row.  One step of the F
+// chain is the map f -> min(127, max(f + (ge - u), beta)) (beta: the gap-open candidate of the cell, lower clamp included).
+// Maps of that form are closed under composition, so a block is  F(f) = min(C, max(f + A, B))  with A = W*ge - sum(u) and, as
+// long as the upper clamp never binds, the reference's hand-over  fin[j+1] = max(F(-63), fin[j] + A)  is just F(fin[j]) for
+// fin[j] >= -63: the F that pass 2 itself leaves the block with.  So the lanes of a pair can run ONE pass each if lane j+1
+// works one row behind lane j:
+//   * thread t of the pair's group of 8 owns lanes 2t (low s16x2 half, row y - 2t) and 2t+1 (high half, row y - 2t - 1);
+//     the block-exit F and the last cell's v travel to the next lane in a register (same thread) or one shuffle (next thread);
+//   * the two halves of a register sit on different target rows, so the substitution scores come from PRMT(column of row A,
+//     column of row B, selector): scores are kept +63 (0..126), whose sign-replicating nibble yields the zero high byte and,
+//     for positions past the query end, the -63 of the reference (0);
+//   * the trace is written straight from the registers of the pass, in a SKEWED layout: slot s of a pair holds lane j's row
+//     s - 1 - j, which is what the group produces together in one time step (one coalesced 128-byte line per chunk and
+//     array); the traceback kernel adds the lane to the row index (TraceView::skew).
+// Exactness is guarded, not assumed: a pair is flagged for the two-pass kernel (kStRedo) when (G1) an F of the pass reaches the
+// upper clamp, (G2) a block-exit F drops under -63, or (G3) the u bytes of a finished lane do not add up to the difference of
+// its anchors (the reference's scan uses the anchors, the pass the bytes: a saturated u or v makes them differ).  With G1-G3
+// clean every value of the pass equals the reference's pass 2.  Full bands only (the band never moves: bsalign.h:3932 needs
+// rbeg + bw < qlen), affine gaps with all costs <= 0, scores within +-63.
+#pragma once
+#include "epi8_forward.cuh"
+
+namespace bsb200 {
+
+struct WaveK { uint32_t Z0, C65, GOE129, GE129, GE1, GOE, M1; };
+struct WaveState { uint32_t f, h, u, nv; };
+
+// one DP step of the thread's two lanes: dp_step<1, true, true, true> with the score operand biased by +63 instead of +128
+__device__ __forceinline__ void wave_step(WaveState &s, uint32_t u, uint32_t e, uint32_t z63, const WaveK &k, uint32_t &un, uint32_t &en){
+	constexpr uint32_t C129 = 0x00810081u, C255 = 0x00ff00ffu;
+	const uint32_t ev = __viaddmax_s16x2(u, e, k.Z0);                       // adds(e, u) + 128
+	const uint32_t hz = __viaddmax_s16x2(z63, k.C65, ev);                   // max(z, ev) + 128
+	const uint32_t yz = __viaddmax_s16x2(hz, k.GOE129, C129);               // adds(max(z, ev), goe) + 128 + 129
+	const uint32_t f1 = __viaddmax_s16x2(s.f, k.GE129, yz);                 // max(adds(f, ge), y) + 128 + 129
+	const uint32_t cu = not_fma(u, k.M1);
+	const uint32_t h = __vmaxs2(hz, s.f);
+	const uint32_t ch = not_fma(h, k.M1);
+	un = __viaddmin_s16x2_relu(h, s.nv, C255);                              // subs(h, v) + 128
+	s.nv = __viaddmin_s16x2(__viaddmax_s16x2(u, ch, kLO), kONE, 0x00800080u);
+	const uint32_t x1 = __viaddmax_s16x2(ev, k.GE1, kONE);
+	en = __viaddmax_s16x2(x1, ch, k.GOE);
+	s.u = u; s.h = h;
+	s.f = __viaddmin_s16x2_relu(f1, cu, C255);
+}
+
+// PRMT selector of one step: low byte fetches lane A's score from source a (the column of row A), high byte lane B's from
+// source b; nibble 8|x replicates the sign of a byte < 128, i.e. yields 0: the high byte of each half, and the whole half for
+// code 4 (past the query end: -63 + 63)
+__device__ __forceinline__ uint32_t wsel(uint32_t cA, uint32_t cB){
+	const uint32_t lo = cA < 4u ? (cA | ((8u | cA) << 4)) : 0x88u;
+	const uint32_t hi = cB < 4u ? ((4u | cB) | ((12u | cB) << 4)) : 0xCCu;
+	return lo | (hi << 8);
+}
+
+template<bool ANCH, bool NARROW>
+__global__ void __launch_bounds__(kFwdThreads, 4) epi8_wave_kernel(const Epi8Args a){
+	extern __shared__ __align__(16) uint8_t smem_raw[];
+	const int lane = threadIdx.x & 31;
+	const int t = lane & 7;
+	const unsigned gmask = 0xffu << (lane & 24);
+	if(NARROW && (uint32_t)(lane >> 3) >= a.gpw) return;
+	const unsigned amask = NARROW ? ((1u << (8 * a.gpw)) - 1u) : 0xffffffffu;
+	const int A = 2 * t, B = A + 1;
+	const uint32_t IMG = a.max_img;
+	uint8_t *gs = smem_raw + (size_t)(NARROW ? (threadIdx.x >> 5) * a.gpw + (lane >> 3) : (threadIdx.x >> 3)) * a.group_smem;
+	int8_t *sU = (int8_t*)gs;
+	int8_t *sE = sU + IMG;
+	uint8_t *sC = (uint8_t*)(sE + IMG);
+	int32_t *sUB = (int32_t*)(sC + IMG);
+	int32_t *sRM = sUB + 2 * kMetaInts + 8;
+
+	const int mode = a.mode & 3;
+	const int go1 = a.go1, ge1 = a.ge1;
+	const int GOEi = (int8_t)(go1 + ge1);
+	constexpr uint32_t C255 = 0x00ff00ffu, C129 = 0x00810081u;
+	WaveK wk;
+	wk.M1 = a.all_ones; wk.Z0 = wk.M1 + 1u; wk.C65 = pk1(65); wk.GOE129 = pk1(GOEi + 129); wk.GE129 = pk1(ge1 + 129); wk.GE1 = pk1(ge1 + 1); wk.GOE = pk1(GOEi);
+	const uint32_t NGOE = pk1(-GOEi);
+	uint32_t colw[4];
+	#pragma unroll
+	for(int c=0;c<4;c++) colw[c] = (uint32_t)(uint8_t)(a.mtx[c] + 63) | ((uint32_t)(uint8_t)(a.mtx[4 + c] + 63) << 8) | ((uint32_t)(uint8_t)(a.mtx[8 + c] + 63) << 16) | ((uint32_t)(uint8_t)(a.mtx[12 + c] + 63) << 24);
+	#define COLW(tb) (((tb) & 2) ? (((tb) & 1) ? colw[3] : colw[2]) : (((tb) & 1) ? colw[1] : colw[0]))
+
+	bool have = false, done = false;
+	uint32_t pair = 0, qlen = 1, tlen = 1, W = 1, IB = 128, RS = 256;
+	const uint8_t *qs = a.seqs, *ts = a.seqs;
+	uint8_t *tr = a.trace;
+	int32_t *metaS = nullptr, *ub0p = nullptr;
+	int T = 0;                               // time step of the pair: lane j works on row T - j
+	int SA = 0, EA = 0, EB = 0;              // anchors ub[A], ub[A+1] of lane A's last row, ub[B+1] of lane B's last row
+	int fexA = kEpi8Min + 128, vtA_prev = 0; // lane A's block-exit F (biased) and last v of the previous time step: lane B's inputs
+	uint32_t pktB = 0;                       // lane B's (F, v) of the previous time step, for thread t+1
+	uint32_t T32A = 0, T32B = 0;
+	int best = kScoreMin, best_te = 0, flagged = 0;
+	uint32_t jq = 0, iq = 0;
+	int8_t *const rU = sU + 16 * t, *const rE = sE + 16 * t; uint8_t *const rC = sC + 16 * t;
+	#define TOFF(i) ((((i) >> 3) << 7) + (((i) & 7) << 1))
+	#define QCODE(x) ((x) < qlen ? (uint32_t)qs[(x)] : 4u)
+
+	// A lane that has finished the pair's last row leaves what the end of the pair needs in the group's scratch words (its bytes in
+	// shared memory are overwritten by the next, idle, time step): GLOBAL: H(qlen-1, tlen-1) if the lane holds that cell
+	// (bsalign.h:4023); else the lane's part of row_max (bsalign.h:3213-3263): its maximum - the earliest 32-step chunk whose prefix
+	// maximum is strictly largest - and the first position inside that chunk that reaches it.
+	auto lane_final = [&](int j, int anchor, int which){
+		const int8_t *p = rU + which;
+		if(mode == 0){
+			if((uint32_t)j == jq){
+				int s = anchor;
+				for(uint32_t i=0;i<=iq;i++) s += (int)(uint8_t)p[TOFF(i)] - 128;
+				sRM[0] = s;
+			}
+			return;
+		}
+		const uint32_t nck = (W + 31) / 32;
+		int Max = kScoreMin, Scr = anchor; uint32_t bc = 0;
+		for(uint32_t c=0;c<nck;c++){
+			uint32_t lo = c * 32, hi = lo + 32 < W ? lo + 32 : W;
+			int run = 0, mx = -32767;
+			for(uint32_t i=lo;i<hi;i++){ run += (int)(uint8_t)p[TOFF(i)] - 128; if(run > mx) mx = run; }
+			int hh = Scr + mx;
+			if(hh > Max){ Max = hh; bc = c; }
+			Scr += run;
+		}
+		uint32_t x = bc * 32, y = (bc + 1) * 32 < W ? (bc + 1) * 32 : W;
+		uint32_t pos = x; int umax = kScoreMin, uscr = 0;
+		for(;x<y;x++){ uscr += (int)(uint8_t)p[TOFF(x)] - 128; if(uscr > umax){ pos = x; umax = uscr; } }
+		sRM[j] = Max; sRM[16 + j] = (int)pos;
+	};
+
+	while(true){
+		if(!have && !done){
+			uint32_t idx = 0;
+			if(t == 0) idx = atomicAdd(a.counter, 1u);
+			idx = __shfl_sync(gmask, idx, lane & 24);
+			if(idx >= a.npairs) done = true;
+			else {
+				pair = a.order[idx];
+				qlen = a.qlen[pair]; tlen = a.tlen[pair];
+				qs = a.seqs + a.qoff[pair]; ts = a.seqs + a.toff[pair];
+				const uint32_t bw = ((a.bandwidth ? a.bandwidth : qlen) + kLanes - 1) / kLanes * kLanes;   // full band: no shorter than the query
+				W = bw / kLanes;
+				IB = epi8_image_bytes(W);
+				RS = ANCH ? epi8_row_bytes(W, 1) : IB * 2;
+				tr = a.trace + a.trace_off[pair];
+				metaS = (int32_t*)(tr + (size_t)RS * (tlen + 1 + kWaveSlack));
+				ub0p = metaS + (size_t)16 * (tlen + 1 + kWaveSlack);
+				T = 0; have = true; flagged = a.force_redo ? 1 : 0;
+				best = kScoreMin; best_te = 0;
+				jq = (qlen - 1) / W; iq = (qlen - 1) - jq * W;
+				fexA = kEpi8Min + 128; vtA_prev = 0; pktB = 0;
+				T32A = COLW((uint32_t)ts[0]); T32B = T32A;   // thread 0's first row; the others re-load before they start
+				// ---- row -1 of the thread's two lanes (bsalign.h:2094-2140) -----------------------------------
+				const bool glob = (mode == 0 || mode == 2);
+				const int u0 = (int8_t)(go1 + ge1 + a.smin - a.smax);
+				for(uint32_t i=0;i<IB/16;i++){
+					uint32_t pA = A * W + i, pB = B * W + i;
+					int vA = 0, vB = 0;
+					if(glob){ vA = (pA == 0) ? u0 : ge1; vB = ge1; }
+					if(i >= W){ vA = 0; vB = 0; }
+					rU[TOFF(i)] = (int8_t)(vA + 128); rU[TOFF(i) + 1] = (int8_t)(vB + 128);
+					rE[TOFF(i)] = kEpi8Min; rE[TOFF(i) + 1] = kEpi8Min;
+					*(uint16_t*)(rC + TOFF(i)) = (uint16_t)(i < W ? wsel(QCODE(pA), QCODE(pB)) : wsel(4, 4));
+				}
+				auto ubinit = [&](int j) -> int {
+					int s = 0;
+					if(glob){
+						int64_t n = (int64_t)j * W;
+						s = a.smax - a.smin;
+						if(n > 0) s += u0 + (int)((n - 1) * ge1);
+					}
+					return s;
+				};
+				SA = ubinit(A); EA = ubinit(A + 1); EB = ubinit(B + 1);
+				// row -1 in the trace: lane j's row -1 is slot j.  Lane A's piece goes out here (the B bytes of that slot are
+				// never read); slot 2t+1 is written by the thread's first time step, which leaves lane B as it is.
+				{
+					uint8_t *d0 = tr + (size_t)RS * A + 16 * t;
+					for(uint32_t c=0;c<IB/128;c++){
+						*(uint4*)(d0 + 128 * c) = *(const uint4*)(rU + 128 * c);
+						*(uint4*)(d0 + IB + 128 * c) = *(const uint4*)(rE + 128 * c);
+					}
+					metaS[(size_t)16 * A + A] = EA;
+					metaS[(size_t)16 * B + B] = EB;
+					if(t == 0) ub0p[0] = SA;
+					if(ANCH){
+						int sA_ = SA, sB_ = EA; uint32_t i = 0;
+						for(uint32_t g=1;g<epi8_anchor_groups(W);g++){
+							for(;i<kAnchorSteps*g;i++){ sA_ += (int)(uint8_t)rU[TOFF(i)] - 128; sB_ += (int)(uint8_t)rU[TOFF(i) + 1] - 128; }
+							*(int32_t*)(tr + (size_t)RS * A + (size_t)IB * 2 + ((g - 1) * 16 + A) * 4) = sA_;
+							*(int32_t*)(tr + (size_t)RS * B + (size_t)IB * 2 + ((g - 1) * 16 + B) * 4) = sB_;
+						}
+					}
+				}
+			}
+		}
+		if(__all_sync(amask, done)) break;
+
+		// =============================== one time step ================================================
+		const int rA = T - 2 * t, rB = rA - 1;
+		const bool actA = have && rA >= 0 && rA < (int)tlen, actB = have && rB >= 0 && rB < (int)tlen;
+		// target base of lane A's next row, in flight during this step
+		uint32_t tbn = 0;
+		if(have && rA + 1 >= 0 && rA + 1 < (int)tlen) tbn = ts[rA + 1];
+		// hand-over: lane A takes F and v from lane B of the previous thread (same row, one time step ago), lane B from lane A
+		const uint32_t pin = __shfl_up_sync(amask, pktB, 1, kGroup);
+		int finA = kEpi8Min + 128, vpA = 0;
+		if(t){ finA = (int)(pin & 0xffffu); vpA = (int)(short)(pin >> 16); }
+		const int finB = fexA, vpB = vtA_prev;
+		if(actA || actB){
+			// ---- cell 0 (bsalign.h:2899-2907): lane 0 only; the override of its score rides on the first chunk's first step ----
+			uint32_t zm = 0xffffffffu, zo = 0u;
+			if(t == 0){
+				int rh;
+				if(mode == 1 || rA == 0) rh = 0;
+				else rh = (int)((uint32_t)go1 + (uint32_t)ge1 * (uint32_t)rA);
+				const uint32_t n0 = (uint32_t)sC[0] & 0xfu;
+				const int z0 = (n0 & 8u) ? kEpi8Min : (int)((T32A >> (8 * n0)) & 0xffu) - 63;
+				const int u0 = (int)(uint8_t)sU[0] - 128, t0 = u0 + sE[0];
+				int h0 = (rh - SA) + z0;
+				if(h0 >= t0){ if(h0 > kEpi8Max) h0 = kEpi8Max; } else h0 = kEpi8Min;
+				zm = 0xffff0000u; zo = (uint32_t)(h0 + 63);
+			}
+			// first cell of a lane: u = subs(u, v of the previous lane's last cell) (bsalign.h:2618-2636); 0 after the first chunk
+			uint32_t NV0 = pk(-vpA, -vpB);
+			const uint32_t nchunk = (W + 7) / 8, nfull = W / 8;
+			WaveState st; st.f = pk(finA, finB); st.h = 0; st.u = 0; st.nv = 0;
+			uint32_t gacc = st.f, fk = st.f, accA = 0, accB = 0;
+			uint8_t *const gU = tr + (size_t)RS * (T + 1) + 16 * t, *const gE = gU + IB;
+			// anchors of the rows in work: ub[A] (lane 0: the old ub[0], its u[0] is re-based after the loop), ub[B]
+			const int ancA = t ? SA + vpA : SA, ancB = EA;
+			#define WSTEP(K, LEFT) { if((K) < (LEFT)){ \
+				uint32_t z = prmt(T32A, T32B, ent_sel<K>(cs4)); \
+				if((K) == 0) z = (z & zm) | zo; \
+				wave_step(st, entz<K>(cu4), ent<K>(ce4), z, wk, un[K], en[K]); \
+				if((K) & 1) gacc = __vimax3_s16x2(gacc, fk, st.f); else fk = st.f; } }
+			#define WCHUNK(LEFT, RAGGED) { \
+				const uint4 cu4 = *(const uint4*)(rU + 128 * c), cs4 = *(const uint4*)(rC + 128 * c), ce4 = *(const uint4*)(rE + 128 * c); \
+				uint32_t un[8], en[8]; \
+				if(RAGGED){ _Pragma("unroll") for(int k=0;k<8;k++){ un[k] = 0; en[k] = 0; } } \
+				WSTEP(0, LEFT) WSTEP(1, LEFT) WSTEP(2, LEFT) WSTEP(3, LEFT) WSTEP(4, LEFT) WSTEP(5, LEFT) WSTEP(6, LEFT) WSTEP(7, LEFT) \
+				un[0] = __viaddmin_s16x2_relu(un[0], NV0, C255); \
+				zm = 0xffffffffu; zo = 0u; NV0 = 0u; \
+				const uint4 ou4 = make_uint4(pack2(un[0], un[1]), pack2(un[2], un[3]), pack2(un[4], un[5]), pack2(un[6], un[7])); \
+				const uint4 oe4 = make_uint4(pack2(en[0], en[1]), pack2(en[2], en[3]), pack2(en[4], en[5]), pack2(en[6], en[7])); \
+				accA = __dp4a(ou4.x, 0x00010001u, accA); accB = __dp4a(ou4.x, 0x01000100u, accB); \
+				accA = __dp4a(ou4.y, 0x00010001u, accA); accB = __dp4a(ou4.y, 0x01000100u, accB); \
+				accA = __dp4a(ou4.z, 0x00010001u, accA); accB = __dp4a(ou4.z, 0x01000100u, accB); \
+				accA = __dp4a(ou4.w, 0x00010001u, accA); accB = __dp4a(ou4.w, 0x01000100u, accB); \
+				*(uint4*)(rU + 128 * c) = ou4; *(uint4*)(rE + 128 * c) = oe4; \
+				*(uint4*)(gU + (size_t)c * 128) = ou4; *(uint4*)(gE + (size_t)c * 128) = oe4; \
+				if(ANCH && (c & (kAnchorChunks - 1)) == kAnchorChunks - 1 && c + 1 < nchunk){ \
+					/* sub-lane anchors: H at the end of step 8(c+1)-1 = lane anchor + the row's u bytes so far */ \
+					int32_t *an = (int32_t*)(tr + (size_t)RS * (T + 1) + (size_t)IB * 2) + (c / kAnchorChunks) * 16; \
+					const int corr = 128 * (int)(8 * (c + 1)); \
+					if(actA) an[A] = ancA + (int)accA - corr; \
+					if(actB) an[B] = ancB + (int)accB - corr; \
+				} }
+			uint32_t c = 0;
+			_Pragma("unroll 1")
+			for(;c<nfull;c++) WCHUNK(8u, false)
+			if(c < nchunk){ const uint32_t left = W - 8 * c; WCHUNK(left, true) }
+			#undef WCHUNK
+			#undef WSTEP
+			gacc = __vmaxs2(gacc, st.f);
+			// ---- tail (bsalign.h:2618-2636): v of each lane's last cell, new anchors ----------------------------
+			int vtA, vtB;
+			{
+				const uint32_t yb = __viaddmax_s16x2(st.h, wk.GOE129, C129);
+				uint32_t h = pk(lo16(yb) - 257, hi16(yb) - 257);
+				const uint32_t ul = pk(lo16(st.u) - 128, hi16(st.u) - 128);
+				h = sadd(h, NGOE);
+				const uint32_t vt = ssubc(h, ~ul);
+				vtA = lo16(vt); vtB = hi16(vt);
+			}
+			const int fxA = lo16(st.f), fxB = hi16(st.f);
+			if(actB){
+				// lane B's row: its start anchor is lane A's end anchor of the same row, i.e. EA before this step's update
+				const int nEB = EB + vtB;
+				const int sum = (int)accB - 128 * (int)W;
+				if(fxB >= 255 || hi16(gacc) >= 255 || (t < 7 && fxB < kEpi8Min + 128) || sum != nEB - EA) flagged = 1;
+				EB = nEB;
+				metaS[(size_t)16 * (T + 1) + B] = EB;
+				if(mode != 0 && jq == (uint32_t)B){
+					int sc = EB;
+					for(uint32_t i=iq+1;i<W;i++) sc -= (int)(uint8_t)rU[TOFF(i) + 1] - 128;
+					if(sc > best){ best = sc; best_te = rB; }
+				}
+				if(rB == (int)tlen - 1) lane_final(B, EA, 1);
+			}
+			if(actA){
+				int dub0 = 0;
+				if(t == 0){
+					// lane 0 re-bases: ub[0] takes the first cell's u, which is stored as 0 (bsalign.h:2630-2634)
+					dub0 = (int)(uint8_t)rU[0] - 128;
+					rU[0] = (int8_t)128; gU[0] = 128;
+					accA -= (uint32_t)dub0;
+				}
+				const int nSA = t ? SA + vpA : SA + dub0;
+				const int nEA = EA + vtA;
+				const int sum = (int)accA - 128 * (int)W;
+				if(fxA >= 255 || lo16(gacc) >= 255 || fxA < kEpi8Min + 128 || sum != nEA - nSA) flagged = 1;
+				SA = nSA; EA = nEA;
+				metaS[(size_t)16 * (T + 1) + A] = EA;
+				if(t == 0) ub0p[rA + 1] = SA;
+				if(mode != 0 && jq == (uint32_t)A){
+					int sc = EA;
+					for(uint32_t i=iq+1;i<W;i++) sc -= (int)(uint8_t)rU[TOFF(i)] - 128;
+					if(sc > best){ best = sc; best_te = rA; }
+				}
+				if(rA == (int)tlen - 1) lane_final(A, SA, 0);
+				if(rA == 0){
+					// the thread's first step ran lane B on its row -1 image: put that image back (shared memory and slot 2t+1)
+					const bool glob = (mode == 0 || mode == 2);
+					for(uint32_t i=0;i<IB/16;i++){
+						const int8_t ub_ = (int8_t)(((glob && i < W) ? ge1 : 0) + 128);
+						rU[TOFF(i) + 1] = ub_; rE[TOFF(i) + 1] = kEpi8Min;
+						gU[TOFF(i) + 1] = (uint8_t)ub_; gE[TOFF(i) + 1] = (uint8_t)kEpi8Min;
+					}
+				}
+			}
+			fexA = fxA; vtA_prev = vtA;
+			pktB = (uint32_t)(fxB & 0xffff) | ((uint32_t)vtB << 16);
+		}
+		T32B = T32A; T32A = COLW(tbn);
+		T++;
+		if(have && T == (int)tlen + 15){
+			// ---- the pair is through: every lane left its share of the last row in the group's scratch words ----
+			flagged |= __shfl_xor_sync(gmask, flagged, 1);
+			flagged |= __shfl_xor_sync(gmask, flagged, 2);
+			flagged |= __shfl_xor_sync(gmask, flagged, 4);
+			__syncwarp(gmask);
+			int best_qe = (int)qlen - 1;
+			if(mode == 0){
+				best = sRM[0];
+				best_te = (int)tlen - 1;
+			} else {
+				// the per-row candidates H(qlen-1, y) were collected by the thread that owns that lane
+				best = __shfl_sync(gmask, best, (lane & 24) + (int)(jq >> 1));
+				best_te = __shfl_sync(gmask, best_te, (lane & 24) + (int)(jq >> 1));
+				// row_max: lane-wise maxima reduced in the SSE code's tie-break order (bsalign.h:3264-3291)
+				int M4[4]; uint32_t I4[4];
+				#pragma unroll
+				for(int j=0;j<4;j++){
+					int m0 = sRM[j], m1 = sRM[j + 8];
+					uint32_t i0 = (uint32_t)j, i1 = (uint32_t)j + 8;
+					if(sRM[j + 4] > m0){ m0 = sRM[j + 4]; i0 = (uint32_t)j + 4; }
+					if(sRM[j + 12] > m1){ m1 = sRM[j + 12]; i1 = (uint32_t)j + 12; }
+					if(m1 > m0){ m0 = m1; i0 = i1; }
+					M4[j] = m0; I4[j] = i0;
+				}
+				int max_score = M4[0]; uint32_t bl = I4[0];
+				#pragma unroll
+				for(int j=1;j<4;j++) if(M4[j] > max_score){ max_score = M4[j]; bl = I4[j]; }
+				if(max_score > best){ best = max_score; best_qe = (int)(bl * W) + sRM[16 + bl]; best_te = (int)tlen - 1; }
+			}
+			if(t == 0){
+				int32_t *rs = a.results + (size_t)pair * 10;
+				rs[0] = best; rs[2] = best_qe; rs[4] = best_te;
+				a.status[pair] = flagged ? kStRedo : kStSkew;
+			}
+			__syncwarp(gmask);
+			have = false;
+		}
+	}
+	#undef QCODE
+	#undef TOFF
+	#undef COLW
+}
+
+} // namespace bsb200
