@@ -464,7 +464,8 @@ static int launch_epi8_forward(bsb200_ctx *ctx, Epi8Args a, uint32_t npairs, boo
 			int rc;
 			if(best_gpw < 4){
 				if constexpr (ANCH) rc = go(epi8_wave_kernel<true, true>); else rc = -1;
-			} else rc = go(epi8_wave_kernel<ANCH, false>);
+			} else if(getenv("BSB200_WAVE_VAR") && atoi(getenv("BSB200_WAVE_VAR")) == 1) rc = go(epi8_wave_kernel<ANCH, false, 1>);   // experiments
+			else rc = go(epi8_wave_kernel<ANCH, false>);
 			if(rc) return rc;
 			ctx->timing.forward_launches++;
 			CK(cudaMemsetAsync(a.counter, 0, 16, ctx->stream));
@@ -563,7 +564,7 @@ extern "C" int bsb200_batch_run(bsb200_ctx *ctx, bsb200_batch *b){
 			// groups of a warp keep their small per-group words (anchors, F hand-over) on different banks
 			a.group_smem = (uint32_t)(((size_t)a.max_img * (b->pw + 2) + (kMetaInts * 2) * 4 + 32 + 32 * 4 + 127) / 128 * 128 + 32);
 			a.mode = b->mode; memcpy(a.mtx, b->mtx, 16); a.go1 = b->go1; a.ge1 = b->ge1; a.go2 = b->go2; a.ge2 = b->ge2;
-			a.all_ones = 0xffffffffu; a.redo = 0; a.force_redo = 0;
+			a.all_ones = 0xffffffffu; a.c256 = 256u; a.c65536 = 65536u; a.redo = 0; a.force_redo = 0;
 			a.smax = -127; a.smin = 127;
 			for(int k=0;k<16;k++){ a.smax = std::max(a.smax, b->mtx[k]); a.smin = std::min(a.smin, b->mtx[k]); }
 			// all gap costs <= 0 (the normal case): saturation bounds that cannot bind are dropped (epi8_forward.cuh)

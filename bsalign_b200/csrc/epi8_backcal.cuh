@@ -34,7 +34,8 @@ struct Epi8BtArgs {
 struct TraceView {
 	const uint8_t *tr; const int32_t *meta; uint32_t bw, W, IB, RS, AOFF; int tlen, ubias, anch;
 	// skew = 1: the pair was written by the wavefront kernel (epi8_wave.cuh): lane j's row y sits in image slot y + 1 + j, the end
-	// anchor ub[k] (k >= 1) of row y in record y + k of `meta` (16 ints per record), ub[0] in `ub0`, and the band never moved
+	// anchor ub[k] (k >= 1) of row y in record y + k of `meta` (16 ints per record), ub[0] in `ub0`, the band never moved, the two
+	// steps of a word are step-major (epi8_cell_offset_w) and e is stored + 128
 	int skew; const int32_t *ub0;
 	__device__ __forceinline__ int beg(int row) const { return skew ? 0 : meta[(size_t)kMetaInts * (row + 1) + 17]; }
 	__device__ __forceinline__ int ub(int row, int j) const {
@@ -46,14 +47,16 @@ struct TraceView {
 	// array arr (0 u, 1 e, 2 q) of the cell at band position p of a row
 	__device__ __forceinline__ int cell(int row, int arr, uint32_t p) const {
 		uint32_t j = p / W, i = p - j * W;
-		uint8_t b = slot(row, j)[(size_t)arr * IB + epi8_cell_offset(j, i)];
-		return (int)(int8_t)(arr == 0 && ubias ? (uint8_t)(b ^ 0x80) : b);
+		uint8_t b = slot(row, j)[(size_t)arr * IB + (skew ? epi8_cell_offset_w(j, i) : epi8_cell_offset(j, i))];
+		return (int)(int8_t)(((arr == 0 && ubias) || (arr == 1 && skew)) ? (uint8_t)(b ^ 0x80) : b);
 	}
 	// H(col,row) = anchor of the lane + its u cells up to col (bsalign.h:3187-3202); sets err when the lookup leaves the band
 	__device__ int score(int row, int col, int &err) const { return score_at(row, (row >= -1 && row < tlen) ? beg(row) : 0, col, err); }
 	// ---- split lookup: `begin` only computes addresses and issues the loads (anchor + up to 8 chunks), `finish` sums.
 	// Between the two the caller issues its other loads, so that one walk step costs a single memory round trip.
 	struct Pending { const uint8_t *r; int4 v[8]; int ub; uint32_t n; int mk; };
+	// a word holds two steps of the lane: mask of the first one
+	__device__ __forceinline__ int first_step(int mk) const { return skew ? (mk & 0x00ff00ff) : (mk & 0x0000ffff); }
 	__device__ __forceinline__ void begin(Pending &p, bool need, int row, int rbeg, int col, int &err) const {
 		int64_t pos = (int64_t)col - rbeg;
 		bool ok = need && row >= -1 && row < tlen && pos >= 0 && pos < (int64_t)bw;
@@ -65,7 +68,7 @@ struct TraceView {
 		const uint8_t *sl = slot(rw, j);
 		p.ub = ok ? (g ? *(const int32_t*)(sl + AOFF + ((g - 1) * 16 + j) * 4) : ub(rw, j)) : kScoreMin;
 		p.r = sl + (size_t)(j >> 1) * 16 + (size_t)g * (kAnchorSteps / 8) * 128;
-		p.mk = (j & 1) ? 0x01000100 : 0x00010001;
+		p.mk = skew ? ((j & 1) ? 0x01010000 : 0x00000101) : ((j & 1) ? 0x01000100 : 0x00010001);
 		const uint32_t nch = (p.n + 7) >> 3;
 		#pragma unroll
 		for(int k=0;k<8;k++) p.v[k] = (uint32_t)k < nch ? *(const int4*)(p.r + 128 * k) : make_int4(0, 0, 0, 0);
@@ -82,7 +85,7 @@ struct TraceView {
 				#pragma unroll
 				for(int q=0;q<4;q++){
 					if(left >= 2u * q + 2) s = __dp4a(w[q], p.mk, s);
-					else if(left == 2u * q + 1) s = __dp4a(w[q], p.mk & 0x0000ffff, s);
+					else if(left == 2u * q + 1) s = __dp4a(w[q], first_step(p.mk), s);
 				}
 			}
 		}
@@ -99,7 +102,7 @@ struct TraceView {
 				#pragma unroll
 				for(int q=0;q<4;q++){
 					if(left >= 2u * q + 2) s = __dp4a(w[q], p.mk, s);
-					else if(left == 2u * q + 1) s = __dp4a(w[q], p.mk & 0x0000ffff, s);
+					else if(left == 2u * q + 1) s = __dp4a(w[q], first_step(p.mk), s);
 				}
 			}
 		}
@@ -176,7 +179,7 @@ __global__ void __launch_bounds__(128) epi8_backcal_kernel(const Epi8BtArgs a){
 		// ---- 2. issue every load of this step (cell above, query/target bases, lookup), then consume -------------
 		const int crow = (state == kStep) ? tb - 1 : -1;                    // row of the cell above (valid memory in any state)
 		const uint32_t cx = cellok ? (uint32_t)x : 0u;
-		const uint32_t cj = cx / tv.W, coff = epi8_cell_offset(cj, cx - cj * tv.W);
+		const uint32_t cj = cx / tv.W, coff = tv.skew ? epi8_cell_offset_w(cj, cx - cj * tv.W) : epi8_cell_offset(cj, cx - cj * tv.W);
 		const uint8_t *cp = tv.slot(crow, cj) + coff;
 		const uint32_t ru = cp[0], re = pw >= 1 ? cp[tv.IB] : 0u, rq = pw == 2 ? cp[2 * (size_t)tv.IB] : 0u;
 		const uint32_t qbase = qs[qb >= 0 ? qb : 0], tbase = ts[tb >= 0 ? tb : 0];
@@ -184,7 +187,7 @@ __global__ void __launch_bounds__(128) epi8_backcal_kernel(const Epi8BtArgs a){
 		tv.begin(pd, need, lrow, lbeg, lcol, err);
 		int val = tv.finish(pd);
 		int u = 0, e = (int)(int8_t)(go1 + ge1), q = 0;
-		if(cellok){ u = (int)(int8_t)(a.ubias ? (ru ^ 0x80u) : ru); if(pw >= 1) e = (int)(int8_t)re; if(pw == 2) q = (int)(int8_t)rq; }
+		if(cellok){ u = (int)(int8_t)(a.ubias ? (ru ^ 0x80u) : ru); if(pw >= 1) e = (int)(int8_t)(tv.skew ? (re ^ 0x80u) : re); if(pw == 2) q = (int)(int8_t)rq; }
 		else { u = 0; e = 0; q = 0; }
 		// ---- 3. act ------------------------------------------------------------------------------------------------
 		if(state == kDrun){

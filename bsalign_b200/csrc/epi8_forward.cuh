@@ -43,6 +43,7 @@ struct Epi8Args {
 	int8_t go1, ge1, go2, ge2;
 	int8_t smax, smin;
 	uint32_t all_ones;           // 0xffffffff, passed at run time so that ~x can be issued as IMAD on the otherwise idle FMA pipe
+	uint32_t c256, c65536;       // 256 and 65536 at run time: byte packing / half-word shifts as IMAD on the FMA pipe (wavefront kernel)
 	int redo;                    // two-pass kernel: only take the pairs the wavefront kernel flagged (kStRedo)
 	int force_redo;              // wavefront kernel: flag every pair (test hook: exercises the redo path)
 };

@@ -26,25 +26,32 @@
 
 namespace bsb200 {
 
-struct WaveK { uint32_t Z0, C65, GOE129, GE129, GE1, GOE, M1; };
+struct WaveK { uint32_t C193, CM128, GOE1, GOE129, GE129, GE1, GOE128, M1; };
 struct WaveState { uint32_t f, h, u, nv; };
 
-// one DP step of the thread's two lanes: dp_step<1, true, true, true> with the score operand biased by +63 instead of +128
+// one DP step of the thread's two lanes: dp_step<1, true, true, true> with the score operand biased by +63 instead of +128 and
+// e biased by +128 (unsigned byte like u); ev and hz carry that extra 128, which the constants of their consumers take back
 __device__ __forceinline__ void wave_step(WaveState &s, uint32_t u, uint32_t e, uint32_t z63, const WaveK &k, uint32_t &un, uint32_t &en){
-	constexpr uint32_t C129 = 0x00810081u, C255 = 0x00ff00ffu;
-	const uint32_t ev = __viaddmax_s16x2(u, e, k.Z0);                       // adds(e, u) + 128
-	const uint32_t hz = __viaddmax_s16x2(z63, k.C65, ev);                   // max(z, ev) + 128
-	const uint32_t yz = __viaddmax_s16x2(hz, k.GOE129, C129);               // adds(max(z, ev), goe) + 128 + 129
+	constexpr uint32_t C129 = 0x00810081u, C255 = 0x00ff00ffu, C128 = 0x00800080u;
+	const uint32_t ev = __viaddmax_s16x2(u, e, C128);                       // adds(e, u) + 128 + 128
+	const uint32_t hz = __viaddmax_s16x2(z63, k.C193, ev);                  // max(z, ev) + 128 + 128
+	const uint32_t yz = __viaddmax_s16x2(hz, k.GOE1, C129);                 // adds(max(z, ev), goe) + 128 + 129
 	const uint32_t f1 = __viaddmax_s16x2(s.f, k.GE129, yz);                 // max(adds(f, ge), y) + 128 + 129
 	const uint32_t cu = not_fma(u, k.M1);
-	const uint32_t h = __vmaxs2(hz, s.f);
+	const uint32_t h = __viaddmax_s16x2(hz, k.CM128, s.f);                  // max(z, ev, f) + 128
 	const uint32_t ch = not_fma(h, k.M1);
 	un = __viaddmin_s16x2_relu(h, s.nv, C255);                              // subs(h, v) + 128
-	s.nv = __viaddmin_s16x2(__viaddmax_s16x2(u, ch, kLO), kONE, 0x00800080u);
-	const uint32_t x1 = __viaddmax_s16x2(ev, k.GE1, kONE);
-	en = __viaddmax_s16x2(x1, ch, k.GOE);
+	s.nv = __viaddmin_s16x2(__viaddmax_s16x2(u, ch, kLO), kONE, C128);
+	const uint32_t x1 = __viaddmax_s16x2(ev, k.GE1, C129);                  // adds(ev, ge) + 1 + 128 + 128
+	en = __viaddmax_s16x2(x1, ch, k.GOE128);                                // max(x - h, goe) + 128
 	s.u = u; s.h = h;
 	s.f = __viaddmin_s16x2_relu(f1, cu, C255);
+}
+
+// step K (0..7) of a 16-byte chunk in the step-major byte order, zero-extended: (lane A byte, lane B byte) -> s16x2
+template<int K> __device__ __forceinline__ uint32_t entw(const uint4 &c){
+	const uint32_t w = (K >> 1) == 0 ? c.x : (K >> 1) == 1 ? c.y : (K >> 1) == 2 ? c.z : c.w;
+	return prmt(w, 0u, (K & 1) ? 0x4341u : 0x4240u);
 }
 
 // PRMT selector of one step: low byte fetches lane A's score from source a (the column of row A), high byte lane B's from
@@ -56,7 +63,13 @@ __device__ __forceinline__ uint32_t wsel(uint32_t cA, uint32_t cB){
 	return lo | (hi << 8);
 }
 
-template<bool ANCH, bool NARROW>
+// VAR (experiments): bit 0: the selectors of odd steps are shifted down with IMAD.HI (FMA pipe) instead of SHF (ALU pipe)
+template<int K> __device__ __forceinline__ uint32_t wsel_of(const uint4 &c, uint32_t k64k){
+	const uint32_t w = (K >> 1) == 0 ? c.x : (K >> 1) == 1 ? c.y : (K >> 1) == 2 ? c.z : c.w;
+	return (K & 1) ? __umulhi(w, k64k) : w;
+}
+
+template<bool ANCH, bool NARROW, int VAR = 0>
 __global__ void __launch_bounds__(kFwdThreads, 4) epi8_wave_kernel(const Epi8Args a){
 	extern __shared__ __align__(16) uint8_t smem_raw[];
 	const int lane = threadIdx.x & 31;
@@ -78,8 +91,9 @@ __global__ void __launch_bounds__(kFwdThreads, 4) epi8_wave_kernel(const Epi8Arg
 	const int GOEi = (int8_t)(go1 + ge1);
 	constexpr uint32_t C255 = 0x00ff00ffu, C129 = 0x00810081u;
 	WaveK wk;
-	wk.M1 = a.all_ones; wk.Z0 = wk.M1 + 1u; wk.C65 = pk1(65); wk.GOE129 = pk1(GOEi + 129); wk.GE129 = pk1(ge1 + 129); wk.GE1 = pk1(ge1 + 1); wk.GOE = pk1(GOEi);
+	wk.M1 = a.all_ones; wk.C193 = pk1(193); wk.CM128 = pk1(-128); wk.GOE1 = pk1(GOEi + 1); wk.GOE129 = pk1(GOEi + 129); wk.GE129 = pk1(ge1 + 129); wk.GE1 = pk1(ge1 + 1); wk.GOE128 = pk1(GOEi + 128);
 	const uint32_t NGOE = pk1(-GOEi);
+	const uint32_t K256 = a.c256, K64K = a.c65536;
 	uint32_t colw[4];
 	#pragma unroll
 	for(int c=0;c<4;c++) colw[c] = (uint32_t)(uint8_t)(a.mtx[c] + 63) | ((uint32_t)(uint8_t)(a.mtx[4 + c] + 63) << 8) | ((uint32_t)(uint8_t)(a.mtx[8 + c] + 63) << 16) | ((uint32_t)(uint8_t)(a.mtx[12 + c] + 63) << 24);
@@ -97,8 +111,10 @@ __global__ void __launch_bounds__(kFwdThreads, 4) epi8_wave_kernel(const Epi8Arg
 	uint32_t T32A = 0, T32B = 0;
 	int best = kScoreMin, best_te = 0, flagged = 0;
 	uint32_t jq = 0, iq = 0;
+	uint32_t n0 = 0; int c0u = 0, c0e = kEpi8Min;   // lane 0's first cell: selector nibble, u and e of the previous row (thread 0)
 	int8_t *const rU = sU + 16 * t, *const rE = sE + 16 * t; uint8_t *const rC = sC + 16 * t;
-	#define TOFF(i) ((((i) >> 3) << 7) + (((i) & 7) << 1))
+	#define TOFF(i) ((((i) >> 3) << 7) + (((i) & 7) << 1))                       /* selectors: 2 bytes per step */
+	#define WOFF(i) ((((i) >> 3) << 7) + ((((i) & 7) >> 1) << 2) + ((i) & 1))       /* u, e: lane A's byte of step i (lane B: + 2) */
 	#define QCODE(x) ((x) < qlen ? (uint32_t)qs[(x)] : 4u)
 
 	// A lane that has finished the pair's last row leaves what the end of the pair needs in the group's scratch words (its bytes in
@@ -106,11 +122,11 @@ __global__ void __launch_bounds__(kFwdThreads, 4) epi8_wave_kernel(const Epi8Arg
 	// (bsalign.h:4023); else the lane's part of row_max (bsalign.h:3213-3263): its maximum - the earliest 32-step chunk whose prefix
 	// maximum is strictly largest - and the first position inside that chunk that reaches it.
 	auto lane_final = [&](int j, int anchor, int which){
-		const int8_t *p = rU + which;
+		const int8_t *p = rU + 2 * which;
 		if(mode == 0){
 			if((uint32_t)j == jq){
 				int s = anchor;
-				for(uint32_t i=0;i<=iq;i++) s += (int)(uint8_t)p[TOFF(i)] - 128;
+				for(uint32_t i=0;i<=iq;i++) s += (int)(uint8_t)p[WOFF(i)] - 128;
 				sRM[0] = s;
 			}
 			return;
@@ -120,14 +136,14 @@ __global__ void __launch_bounds__(kFwdThreads, 4) epi8_wave_kernel(const Epi8Arg
 		for(uint32_t c=0;c<nck;c++){
 			uint32_t lo = c * 32, hi = lo + 32 < W ? lo + 32 : W;
 			int run = 0, mx = -32767;
-			for(uint32_t i=lo;i<hi;i++){ run += (int)(uint8_t)p[TOFF(i)] - 128; if(run > mx) mx = run; }
+			for(uint32_t i=lo;i<hi;i++){ run += (int)(uint8_t)p[WOFF(i)] - 128; if(run > mx) mx = run; }
 			int hh = Scr + mx;
 			if(hh > Max){ Max = hh; bc = c; }
 			Scr += run;
 		}
 		uint32_t x = bc * 32, y = (bc + 1) * 32 < W ? (bc + 1) * 32 : W;
 		uint32_t pos = x; int umax = kScoreMin, uscr = 0;
-		for(;x<y;x++){ uscr += (int)(uint8_t)p[TOFF(x)] - 128; if(uscr > umax){ pos = x; umax = uscr; } }
+		for(;x<y;x++){ uscr += (int)(uint8_t)p[WOFF(x)] - 128; if(uscr > umax){ pos = x; umax = uscr; } }
 		sRM[j] = Max; sRM[16 + j] = (int)pos;
 	};
 
@@ -161,8 +177,8 @@ __global__ void __launch_bounds__(kFwdThreads, 4) epi8_wave_kernel(const Epi8Arg
 					int vA = 0, vB = 0;
 					if(glob){ vA = (pA == 0) ? u0 : ge1; vB = ge1; }
 					if(i >= W){ vA = 0; vB = 0; }
-					rU[TOFF(i)] = (int8_t)(vA + 128); rU[TOFF(i) + 1] = (int8_t)(vB + 128);
-					rE[TOFF(i)] = kEpi8Min; rE[TOFF(i) + 1] = kEpi8Min;
+					rU[WOFF(i)] = (int8_t)(vA + 128); rU[WOFF(i) + 2] = (int8_t)(vB + 128);
+					rE[WOFF(i)] = (int8_t)(kEpi8Min + 128); rE[WOFF(i) + 2] = (int8_t)(kEpi8Min + 128);
 					*(uint16_t*)(rC + TOFF(i)) = (uint16_t)(i < W ? wsel(QCODE(pA), QCODE(pB)) : wsel(4, 4));
 				}
 				auto ubinit = [&](int j) -> int {
@@ -175,6 +191,7 @@ __global__ void __launch_bounds__(kFwdThreads, 4) epi8_wave_kernel(const Epi8Arg
 					return s;
 				};
 				SA = ubinit(A); EA = ubinit(A + 1); EB = ubinit(B + 1);
+				n0 = qlen ? (uint32_t)qs[0] : 8u; c0u = glob ? u0 : 0; c0e = kEpi8Min;
 				// row -1 in the trace: lane j's row -1 is slot j.  Lane A's piece goes out here (the B bytes of that slot are
 				// never read); slot 2t+1 is written by the thread's first time step, which leaves lane B as it is.
 				{
@@ -189,7 +206,7 @@ __global__ void __launch_bounds__(kFwdThreads, 4) epi8_wave_kernel(const Epi8Arg
 					if(ANCH){
 						int sA_ = SA, sB_ = EA; uint32_t i = 0;
 						for(uint32_t g=1;g<epi8_anchor_groups(W);g++){
-							for(;i<kAnchorSteps*g;i++){ sA_ += (int)(uint8_t)rU[TOFF(i)] - 128; sB_ += (int)(uint8_t)rU[TOFF(i) + 1] - 128; }
+							for(;i<kAnchorSteps*g;i++){ sA_ += (int)(uint8_t)rU[WOFF(i)] - 128; sB_ += (int)(uint8_t)rU[WOFF(i) + 2] - 128; }
 							*(int32_t*)(tr + (size_t)RS * A + (size_t)IB * 2 + ((g - 1) * 16 + A) * 4) = sA_;
 							*(int32_t*)(tr + (size_t)RS * B + (size_t)IB * 2 + ((g - 1) * 16 + B) * 4) = sB_;
 						}
@@ -217,9 +234,8 @@ __global__ void __launch_bounds__(kFwdThreads, 4) epi8_wave_kernel(const Epi8Arg
 				int rh;
 				if(mode == 1 || rA == 0) rh = 0;
 				else rh = (int)((uint32_t)go1 + (uint32_t)ge1 * (uint32_t)rA);
-				const uint32_t n0 = (uint32_t)sC[0] & 0xfu;
 				const int z0 = (n0 & 8u) ? kEpi8Min : (int)((T32A >> (8 * n0)) & 0xffu) - 63;
-				const int u0 = (int)(uint8_t)sU[0] - 128, t0 = u0 + sE[0];
+				const int t0 = c0u + c0e;
 				int h0 = (rh - SA) + z0;
 				if(h0 >= t0){ if(h0 > kEpi8Max) h0 = kEpi8Max; } else h0 = kEpi8Min;
 				zm = 0xffff0000u; zo = (uint32_t)(h0 + 63);
@@ -233,9 +249,9 @@ __global__ void __launch_bounds__(kFwdThreads, 4) epi8_wave_kernel(const Epi8Arg
 			// anchors of the rows in work: ub[A] (lane 0: the old ub[0], its u[0] is re-based after the loop), ub[B]
 			const int ancA = t ? SA + vpA : SA, ancB = EA;
 			#define WSTEP(K, LEFT) { if((K) < (LEFT)){ \
-				uint32_t z = prmt(T32A, T32B, ent_sel<K>(cs4)); \
+				uint32_t z = prmt(T32A, T32B, (VAR & 1) ? wsel_of<K>(cs4, K64K) : ent_sel<K>(cs4)); \
 				if((K) == 0) z = (z & zm) | zo; \
-				wave_step(st, entz<K>(cu4), ent<K>(ce4), z, wk, un[K], en[K]); \
+				wave_step(st, entw<K>(cu4), entw<K>(ce4), z, wk, un[K], en[K]); \
 				if((K) & 1) gacc = __vimax3_s16x2(gacc, fk, st.f); else fk = st.f; } }
 			#define WCHUNK(LEFT, RAGGED) { \
 				const uint4 cu4 = *(const uint4*)(rU + 128 * c), cs4 = *(const uint4*)(rC + 128 * c), ce4 = *(const uint4*)(rE + 128 * c); \
@@ -244,12 +260,13 @@ __global__ void __launch_bounds__(kFwdThreads, 4) epi8_wave_kernel(const Epi8Arg
 				WSTEP(0, LEFT) WSTEP(1, LEFT) WSTEP(2, LEFT) WSTEP(3, LEFT) WSTEP(4, LEFT) WSTEP(5, LEFT) WSTEP(6, LEFT) WSTEP(7, LEFT) \
 				un[0] = __viaddmin_s16x2_relu(un[0], NV0, C255); \
 				zm = 0xffffffffu; zo = 0u; NV0 = 0u; \
-				const uint4 ou4 = make_uint4(pack2(un[0], un[1]), pack2(un[2], un[3]), pack2(un[4], un[5]), pack2(un[6], un[7])); \
-				const uint4 oe4 = make_uint4(pack2(en[0], en[1]), pack2(en[2], en[3]), pack2(en[4], en[5]), pack2(en[6], en[7])); \
-				accA = __dp4a(ou4.x, 0x00010001u, accA); accB = __dp4a(ou4.x, 0x01000100u, accB); \
-				accA = __dp4a(ou4.y, 0x00010001u, accA); accB = __dp4a(ou4.y, 0x01000100u, accB); \
-				accA = __dp4a(ou4.z, 0x00010001u, accA); accB = __dp4a(ou4.z, 0x01000100u, accB); \
-				accA = __dp4a(ou4.w, 0x00010001u, accA); accB = __dp4a(ou4.w, 0x01000100u, accB); \
+				/* u + 128 and e + 128 lie in 0..255 in both halves: two steps interleave into a word with one IMAD (FMA pipe) */ \
+				const uint4 ou4 = make_uint4(un[1] * K256 + un[0], un[3] * K256 + un[2], un[5] * K256 + un[4], un[7] * K256 + un[6]); \
+				const uint4 oe4 = make_uint4(en[1] * K256 + en[0], en[3] * K256 + en[2], en[5] * K256 + en[4], en[7] * K256 + en[6]); \
+				accA = __dp4a(ou4.x, 0x00000101u, accA); accB = __dp4a(ou4.x, 0x01010000u, accB); \
+				accA = __dp4a(ou4.y, 0x00000101u, accA); accB = __dp4a(ou4.y, 0x01010000u, accB); \
+				accA = __dp4a(ou4.z, 0x00000101u, accA); accB = __dp4a(ou4.z, 0x01010000u, accB); \
+				accA = __dp4a(ou4.w, 0x00000101u, accA); accB = __dp4a(ou4.w, 0x01010000u, accB); \
 				*(uint4*)(rU + 128 * c) = ou4; *(uint4*)(rE + 128 * c) = oe4; \
 				*(uint4*)(gU + (size_t)c * 128) = ou4; *(uint4*)(gE + (size_t)c * 128) = oe4; \
 				if(ANCH && (c & (kAnchorChunks - 1)) == kAnchorChunks - 1 && c + 1 < nchunk){ \
@@ -286,7 +303,7 @@ __global__ void __launch_bounds__(kFwdThreads, 4) epi8_wave_kernel(const Epi8Arg
 				metaS[(size_t)16 * (T + 1) + B] = EB;
 				if(mode != 0 && jq == (uint32_t)B){
 					int sc = EB;
-					for(uint32_t i=iq+1;i<W;i++) sc -= (int)(uint8_t)rU[TOFF(i) + 1] - 128;
+					for(uint32_t i=iq+1;i<W;i++) sc -= (int)(uint8_t)rU[WOFF(i) + 2] - 128;
 					if(sc > best){ best = sc; best_te = rB; }
 				}
 				if(rB == (int)tlen - 1) lane_final(B, EA, 1);
@@ -298,6 +315,7 @@ __global__ void __launch_bounds__(kFwdThreads, 4) epi8_wave_kernel(const Epi8Arg
 					dub0 = (int)(uint8_t)rU[0] - 128;
 					rU[0] = (int8_t)128; gU[0] = 128;
 					accA -= (uint32_t)dub0;
+					c0u = 0; c0e = (int)(uint8_t)rE[0] - 128;
 				}
 				const int nSA = t ? SA + vpA : SA + dub0;
 				const int nEA = EA + vtA;
@@ -308,7 +326,7 @@ __global__ void __launch_bounds__(kFwdThreads, 4) epi8_wave_kernel(const Epi8Arg
 				if(t == 0) ub0p[rA + 1] = SA;
 				if(mode != 0 && jq == (uint32_t)A){
 					int sc = EA;
-					for(uint32_t i=iq+1;i<W;i++) sc -= (int)(uint8_t)rU[TOFF(i)] - 128;
+					for(uint32_t i=iq+1;i<W;i++) sc -= (int)(uint8_t)rU[WOFF(i)] - 128;
 					if(sc > best){ best = sc; best_te = rA; }
 				}
 				if(rA == (int)tlen - 1) lane_final(A, SA, 0);
@@ -317,8 +335,8 @@ __global__ void __launch_bounds__(kFwdThreads, 4) epi8_wave_kernel(const Epi8Arg
 					const bool glob = (mode == 0 || mode == 2);
 					for(uint32_t i=0;i<IB/16;i++){
 						const int8_t ub_ = (int8_t)(((glob && i < W) ? ge1 : 0) + 128);
-						rU[TOFF(i) + 1] = ub_; rE[TOFF(i) + 1] = kEpi8Min;
-						gU[TOFF(i) + 1] = (uint8_t)ub_; gE[TOFF(i) + 1] = (uint8_t)kEpi8Min;
+						rU[WOFF(i) + 2] = ub_; rE[WOFF(i) + 2] = (int8_t)(kEpi8Min + 128);
+						gU[WOFF(i) + 2] = (uint8_t)ub_; gE[WOFF(i) + 2] = (uint8_t)(kEpi8Min + 128);
 					}
 				}
 			}
@@ -368,6 +386,7 @@ __global__ void __launch_bounds__(kFwdThreads, 4) epi8_wave_kernel(const Epi8Arg
 	}
 	#undef QCODE
 	#undef TOFF
+	#undef WOFF
 	#undef COLW
 }
 
