@@ -458,6 +458,7 @@ static int launch_epi8_forward(bsb200_ctx *ctx, Epi8Args a, uint32_t npairs, boo
 		// kernel below over the pairs it flagged (normally none: that launch only reads the status words)
 		bool wave = full && !getenv("BSB200_NOWAVE");
 		for(int k=0;k<16;k++) if(a.mtx[k] > 63 || a.mtx[k] < -63) wave = false;
+		if(a.ge1 > -1 || (int)a.go1 + a.ge1 < -64 || (int)a.go1 + a.ge1 > -1) wave = false;   // the kernel's unclamped adds need these
 		if(wave && (best_gpw == 4 || ANCH)){
 			a.redo = 0;
 			a.force_redo = getenv("BSB200_WAVE_REDO") ? 1 : 0;

@@ -20,32 +20,44 @@
 // upper clamp, (G2) a block-exit F drops under -63, or (G3) the u bytes of a finished lane do not add up to the difference of
 // its anchors (the reference's scan uses the anchors, the pass the bytes: a saturated u or v makes them differ).  With G1-G3
 // clean every value of the pass equals the reference's pass 2.  Full bands only (the band never moves: bsalign.h:3932 needs
-// rbeg + bw < qlen), affine gaps with all costs <= 0, scores within +-63.
+// rbeg + bw < qlen), affine gaps with gape <= -1 and -64 <= gapo + gape <= -1, scores within +-63.
 #pragma once
 #include "epi8_forward.cuh"
 
 namespace bsb200 {
 
-struct WaveK { uint32_t C193, CM128, GOE1, GOE129, GE129, GE1, GOE128, M1; };
+struct WaveK { uint32_t C193, CM128, KGO, KUG, KHG, GOE129, GOE128, M1, ONE; };
 struct WaveState { uint32_t f, h, u, nv; };
 
-// one DP step of the thread's two lanes: dp_step<1, true, true, true> with the score operand biased by +63 instead of +128 and
-// e biased by +128 (unsigned byte like u); ev and hz carry that extra 128, which the constants of their consumers take back
+// ~x + g in both 16-bit halves as ONE IMAD (FMA pipe): x * 0xffffffff + K.  x * 0xffffffff + 0xffffffff is the bitwise complement;
+// adding a negative g to its low half (0xffff - x, x small) always carries into the high half, g = 0 never does, so the high half's
+// addend is pre-compensated.  g must be <= 0.
+__host__ __device__ __forceinline__ uint32_t nadd_const(int g){
+	const uint32_t lo = (uint32_t)g & 0xffffu, hi = (uint32_t)(g - (g < 0 ? 1 : 0)) & 0xffffu;
+	return 0xffffffffu + ((hi << 16) | lo);
+}
+
+// One DP step of the thread's two lanes (bsalign.h:2934-2957 in difference form).  Values: u, e, f, h and the new u, e are kept + 128
+// (unsigned bytes in the row images), the score + 63.  Against dp_step<1, true, true, true>:
+//   * ev = e + u is a plain add (IMAD): its lower clamp at -128 cannot change anything because h >= z >= -63 and go >= -64;
+//   * the gap-open candidate is not clamped (max(z, ev) >= -63, goe >= -64), which turns max(f + ge, max(z, ev) + goe) into
+//     goe + max(f - go, max(z, ev)): one VIADDMNMX, the goe joins the subtraction of u in the IMAD that complements u;
+//   * e' = max(ev + ge - h, goe): ge joins the complement of h in an IMAD, one VIADDMNMX.
+// 8 ALU-pipe instructions (+ 4 IMAD) for two cells; the upper clamp of f and both clamps of u', v are the int8 saturation of the SSE code.
 __device__ __forceinline__ void wave_step(WaveState &s, uint32_t u, uint32_t e, uint32_t z63, const WaveK &k, uint32_t &un, uint32_t &en){
-	constexpr uint32_t C129 = 0x00810081u, C255 = 0x00ff00ffu, C128 = 0x00800080u;
-	const uint32_t ev = __viaddmax_s16x2(u, e, C128);                       // adds(e, u) + 128 + 128
-	const uint32_t hz = __viaddmax_s16x2(z63, k.C193, ev);                  // max(z, ev) + 128 + 128
-	const uint32_t yz = __viaddmax_s16x2(hz, k.GOE1, C129);                 // adds(max(z, ev), goe) + 128 + 129
-	const uint32_t f1 = __viaddmax_s16x2(s.f, k.GE129, yz);                 // max(adds(f, ge), y) + 128 + 129
-	const uint32_t cu = not_fma(u, k.M1);
+	constexpr uint32_t C255 = 0x00ff00ffu, C128 = 0x00800080u;
+	const uint32_t ev = u * k.ONE + e;                                      // e + u + 256
+	const uint32_t hz = __viaddmax_s16x2(z63, k.C193, ev);                  // max(z, ev) + 256
+	const uint32_t m = __viaddmax_s16x2(s.f, k.KGO, hz);                    // max(f - go, z, ev) + 256
+	const uint32_t cug = u * k.M1 + k.KUG;                                  // ~u + goe + 1
 	const uint32_t h = __viaddmax_s16x2(hz, k.CM128, s.f);                  // max(z, ev, f) + 128
 	const uint32_t ch = not_fma(h, k.M1);
+	const uint32_t chg = h * k.M1 + k.KHG;                                  // ~h + ge + 1
 	un = __viaddmin_s16x2_relu(h, s.nv, C255);                              // subs(h, v) + 128
-	s.nv = __viaddmin_s16x2(__viaddmax_s16x2(u, ch, kLO), kONE, C128);
-	const uint32_t x1 = __viaddmax_s16x2(ev, k.GE1, C129);                  // adds(ev, ge) + 1 + 128 + 128
-	en = __viaddmax_s16x2(x1, ch, k.GOE128);                                // max(x - h, goe) + 128
+	s.nv = __viaddmin_s16x2(__viaddmax_s16x2(u, ch, kLO), kONE, C128);      // -subs(h, u)
+	en = __viaddmax_s16x2(ev, chg, k.GOE128);                               // max(ev + ge - h, goe) + 128
 	s.u = u; s.h = h;
-	s.f = __viaddmin_s16x2_relu(f1, cu, C255);
+	s.f = __viaddmin_s16x2_relu(m, cug, C255);                              // subs(max(f + ge, max(z, ev) + goe), u) + 128
 }
 
 // step K (0..7) of a 16-byte chunk in the step-major byte order, zero-extended: (lane A byte, lane B byte) -> s16x2
@@ -91,7 +103,8 @@ __global__ void __launch_bounds__(kFwdThreads, 4) epi8_wave_kernel(const Epi8Arg
 	const int GOEi = (int8_t)(go1 + ge1);
 	constexpr uint32_t C255 = 0x00ff00ffu, C129 = 0x00810081u;
 	WaveK wk;
-	wk.M1 = a.all_ones; wk.C193 = pk1(193); wk.CM128 = pk1(-128); wk.GOE1 = pk1(GOEi + 1); wk.GOE129 = pk1(GOEi + 129); wk.GE129 = pk1(ge1 + 129); wk.GE1 = pk1(ge1 + 1); wk.GOE128 = pk1(GOEi + 128);
+	wk.M1 = a.all_ones; wk.ONE = wk.M1 + 2u; wk.C193 = pk1(193); wk.CM128 = pk1(-128); wk.KGO = pk1(128 - go1); wk.KUG = nadd_const(GOEi + 1); wk.KHG = nadd_const(ge1 + 1);
+	wk.GOE129 = pk1(GOEi + 129); wk.GOE128 = pk1(GOEi + 128);
 	const uint32_t NGOE = pk1(-GOEi);
 	const uint32_t K256 = a.c256, K64K = a.c65536;
 	uint32_t colw[4];
