@@ -3,8 +3,9 @@
 
 One "step" = one pass of the hot path over one batch of synthetic pairs.  Default workload is
 BASELINE.json configs[1] ("c2": 100k pairs, 1 kb x 1 kb, global, 8-bit affine, full band) per GPU;
-with N > 1 every rank aligns its own shard of the same shape (independent pairs, no data-path
-collective; "scaling": "weak").
+with N > 1 the ONE batch lives on rank 0 and is sharded: lengths broadcast, compact shard arenas scattered over
+NVLink (NCCL), every rank aligns its shard, records + dense cigars gathered to rank 0 ("scaling": "strong";
+bsalign_b200/shard.py).
 
   value : whole-job GCUPS with inputs resident in HBM (kernels only, CUDA events on the library stream)
   e2e   : same metric through the host-buffer C-ABI call (pinned host inputs -> H2D -> kernels -> D2H)
@@ -131,14 +132,16 @@ class ClockSampler:
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons), "samples": len(sm)}
 
 
-def cpu_reference_run(w, batch, nthreads, repeat=1):
+def cpu_reference_run(w, batch, nthreads, repeat=1, want_cigars=False):
     """Reference CPU implementation (or the oracle port) over `batch` on `nthreads` host threads; seconds."""
     import checkers as ck
     from bsalign_b200 import synth
     kind = "reference" if ck.have_ref() else "port"
     fn = ck.ref_batch if kind == "reference" else ck.oracle_batch
     mtx = synth.score_matrix(*MATRIX)
-    res, _, _ = fn(w["kind"], batch, w["mode"], w["bandwidth"], mtx, GAPS, nthreads=nthreads, repeat=repeat, want_cigar=True)
+    res, cigs, _ = fn(w["kind"], batch, w["mode"], w["bandwidth"], mtx, GAPS, nthreads=nthreads, repeat=repeat, want_cigar=True)
+    if want_cigars:
+        return ck.last_call_seconds, kind, res, cigs
     return ck.last_call_seconds, kind, res  # the C call only: results + cigars written to caller arenas
 
 
@@ -372,6 +375,261 @@ def main_poa(args, w, njobs, ncores, rank, local_rank, world):
         dist.destroy_process_group()
 
 
+def load_peaks():
+    try:
+        return json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        return {}
+
+
+def profile_facts(kind, waved):
+    """Per-kernel facts measured once under ncu and committed under profiles/ (traffic ratio, ALU-pipe share): profiles/kernel_facts_r2.json."""
+    try:
+        facts = json.load(open(os.path.join(ROOT, "profiles", "kernel_facts_r2.json")))
+        return facts["epi8_wave_kernel" if (kind == "epi8" and waved) else ("epi8_forward_kernel" if kind == "epi8" else "edit_kernel")]
+    except Exception:
+        return None
+
+
+def config_of(name, w, pairs):
+    """The same keys in both arms (the driver compares them)."""
+    return {"workload": "%s: %s" % (name, w["desc"]), "pairs": int(pairs), "qlen": w["qlen"], "mode": w["mode"], "bandwidth": w["bandwidth"],
+            "matrix": list(MATRIX), "gaps": list(GAPS), "seed": 1000}
+
+
+def compare_with_cpu(r, idx, exp, ecg):
+    """Bit-exact check of result records AND cigar words of the pairs idx; returns the number of pairs that differ."""
+    idx = np.asarray(idx, dtype=np.int64)
+    bad = (r.results[idx] != np.asarray(exp)).any(axis=1)
+    bad |= np.asarray(r.ncigar)[idx].astype(np.int64) != np.array([len(c) for c in ecg], dtype=np.int64)
+    for k in np.nonzero(~bad)[0]:
+        if not np.array_equal(r.cigar(int(idx[k])), ecg[k]):
+            bad[k] = True
+    return int(bad.sum())
+
+
+def run_workload(ctx, name, w, pairs, args, ncores, rank, world, local_rank, dist, torch, cpu_seconds, check):
+    """One workload on this rank's GPU (N = 1) or sharded over all ranks (N > 1: the batch lives on rank 0).  Returns the JSON fields."""
+    from bsalign_b200 import api, synth, shard
+    import checkers as ck
+    mtx = synth.score_matrix(*MATRIX)
+    kind = w["kind"]
+    dev = torch.device("cuda", local_rank)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def allred(x, op):
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=op)
+        return float(t.item())
+    pin = lambda a: torch.from_numpy(a).pin_memory().numpy()
+    batch = make_batch(w, 1000, pairs) if rank == 0 else None       # ONE batch; with N > 1 it lives on rank 0 only
+    cells = nominal_cells(w, batch) if rank == 0 else 0
+    sampler = ClockSampler(local_rank)
+    out = {}
+    if world == 1:
+        hb = synth.PairBatch.__new__(synth.PairBatch)
+        hb.seqs, hb.qoff, hb.qlen, hb.toff, hb.tlen = pin(batch.seqs), pin(batch.qoff), pin(batch.qlen), pin(batch.toff), pin(batch.tlen)
+        outbuf = tuple(pin(a) if a is not None else None for a in api._alloc_out(hb, True))
+        rb = ctx.upload(kind, hb, w["mode"], w["bandwidth"], mtx, GAPS, want_cigar=True)
+    else:
+        # ---- scatter once, shards stay resident for the kernel-only leg ------------------------------------------------
+        hdr = torch.zeros(1, dtype=torch.int64, device=dev)
+        if rank == 0:
+            hdr[0] = batch.n
+        dist.broadcast(hdr, 0)
+        n = int(hdr.item())
+        lens = torch.zeros((2, n), dtype=torch.int32, device=dev)
+        if rank == 0:
+            lens[0] = torch.from_numpy(batch.qlen.astype(np.int32)).to(dev); lens[1] = torch.from_numpy(batch.tlen.astype(np.int32)).to(dev)
+        dist.broadcast(lens, 0)
+        lh = lens.cpu().numpy()
+        plans = shard.plan_shards(lh[0].astype(np.uint32), lh[1].astype(np.uint32), kind, w["bandwidth"], world)
+        mine = plans[rank]
+        if rank == 0:
+            reqs, keep = [], []
+            for r in list(range(1, world)) + [0]:
+                pb, nb = api.pack_pairs(batch, plans[r]["idx"], nthreads=ncores)
+                t = torch.from_numpy(pb.seqs[:max(nb, 1)]).to(dev)
+                keep.append(t)
+                if r:
+                    reqs.append(dist.isend(t, r))
+                else:
+                    arena = t
+            for q in reqs:
+                q.wait()
+        else:
+            arena = torch.empty(max(mine["nbytes"], 1), dtype=torch.uint8, device=dev)
+            dist.recv(arena, 0)
+        torch.cuda.synchronize()
+        rb = ctx.upload_dev(kind, arena.data_ptr(), shard.ShardView(mine), w["mode"], w["bandwidth"], mtx, GAPS, want_cigar=True)
+    # ---- kernel-only leg: inputs resident in HBM ------------------------------------------------------------------------
+    sampler.start()
+    for _ in range(args.warmup):
+        rb.run()
+    barrier()
+    sampler.mark()
+    dev_ms = fwd_ms = bt_ms = 0.0
+    fwd_launches = bt_launches = 0
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        rb.run()
+        tm = ctx.timing()
+        dev_ms += tm["run_ms"]; fwd_ms += tm["forward_ms"]; bt_ms += tm["traceback_ms"]
+        fwd_launches += tm["forward_launches"]; bt_launches += tm["traceback_launches"]
+    barrier()
+    wall = time.perf_counter() - t0
+    clocks = sampler.stop()
+    trace_bytes, waves = tm["trace_bytes"], tm["waves"]
+    if world == 1:
+        last = rb.fetch(out=outbuf)
+    rb.free()
+    step_ms = allred(dev_ms / args.steps, dist.ReduceOp.MAX if world > 1 else None)
+    fwd_step_ms = allred(fwd_ms / args.steps, dist.ReduceOp.MAX if world > 1 else None)
+    bt_step_ms = allred(bt_ms / args.steps, dist.ReduceOp.MAX if world > 1 else None)
+    total_cells = allred(cells, dist.ReduceOp.SUM if world > 1 else None)
+    total_trace = allred(trace_bytes, dist.ReduceOp.SUM if world > 1 else None)
+    launches = allred(fwd_launches + bt_launches, dist.ReduceOp.SUM if world > 1 else None)
+    value = total_cells / (step_ms * 1e-3) / 1e9
+
+    # ---- e2e leg: host buffers on rank 0 through the public call ---------------------------------------------------------
+    e2e_extra = {}
+    if world == 1:
+        def one_e2e():
+            if kind == "epi8":
+                return ctx.epi8_batch(hb, w["mode"], w["bandwidth"], mtx, *GAPS, out=outbuf, dense=True)
+            return ctx.edit_batch(hb, w["mode"], w["bandwidth"], out=outbuf, dense=True)
+        for _ in range(min(args.warmup, 3)):
+            one_e2e()
+        barrier()
+        t0 = time.perf_counter()
+        parts = {"h2d_ms": 0.0, "run_ms": 0.0, "d2h_ms": 0.0}
+        for _ in range(args.steps):
+            r = one_e2e()
+            tm2 = ctx.last_timing
+            h2d, d2h = tm2["h2d_bytes"], tm2["d2h_bytes"]
+            for k in parts:
+                parts[k] += tm2[k] / args.steps
+        barrier()
+        e2e_ms = (time.perf_counter() - t0) / args.steps * 1e3
+        e2e_extra = {"device_parts_ms": parts, "host_planning_and_scatter_ms": e2e_ms - sum(parts.values()), "host_buffers": "pinned"}
+        # the same call with PAGEABLE caller buffers (what a reference caller holds: plain u1i* arrays)
+        pout = api._alloc_out(batch, True)
+        t0 = time.perf_counter()
+        if kind == "epi8":
+            ctx.epi8_batch(batch, w["mode"], w["bandwidth"], mtx, *GAPS, out=pout, dense=True)
+        else:
+            ctx.edit_batch(batch, w["mode"], w["bandwidth"], out=pout, dense=True)
+        torch.cuda.synchronize()
+        pg_ms = (time.perf_counter() - t0) * 1e3
+        e2e_extra["pageable"] = {"value": total_cells / (pg_ms * 1e-3) / 1e9, "ms_per_step": pg_ms}
+        assert int(r.results[:, 0].astype(np.int64).sum()) == int(last.results[:, 0].astype(np.int64).sum()), "e2e and resident runs disagree"
+    else:
+        # rank 0 owns the batch in (pinned) host memory: lengths broadcast, compact arenas scattered over NVLink, every rank aligns its
+        # shard in place, records + dense cigars gathered to rank 0 and merged into pair order (bsalign_b200/shard.py)
+        if rank == 0:
+            hb = synth.PairBatch.__new__(synth.PairBatch)
+            hb.seqs, hb.qoff, hb.qlen, hb.toff, hb.tlen = pin(batch.seqs), batch.qoff, batch.qlen, batch.toff, batch.tlen
+        else:
+            hb = None
+        pool = {}
+
+        def pinned(nbytes):   # pinned staging arenas, kept between steps
+            k = len(pool_used)
+            if k not in pool or pool[k].size < nbytes:
+                pool[k] = torch.empty(int(nbytes * 1.05) + 64, dtype=torch.uint8).pin_memory().numpy()
+            pool_used.append(k)
+            return pool[k]
+        al = shard.cuda_aligner(ctx, kind, w["mode"], w["bandwidth"], mtx, GAPS)
+        stage = {}
+        for it in range(min(args.warmup, 2) + args.steps):
+            if it == min(args.warmup, 2):
+                barrier()
+                t0 = time.perf_counter()
+                stage = {}
+            pool_used = []
+            timers = {}
+            res = shard.run_sharded_device(hb, kind, w["bandwidth"], al, dist, device=dev, pinned=pinned, nthreads=ncores, timers=timers)
+            for k in ("plan", "scatter_issued", "aligned", "gathered", "assembled"):
+                if k in timers:
+                    stage[k] = stage.get(k, 0.0) + timers[k] / args.steps
+        barrier()
+        e2e_ms = (time.perf_counter() - t0) / args.steps * 1e3
+        h2d = int(batch.seqs.nbytes + 8 * batch.n) if rank == 0 else 0
+        d2h = 0
+        if rank == 0:
+            results, status, ncigar, dense, goff = res
+            d2h = int(results.nbytes + status.nbytes + ncigar.nbytes + dense.nbytes)
+            r = api.BatchResult(results, dense, goff, ncigar, status)
+            e2e_extra = {"scatter_bytes_over_nvlink": int(timers.get("scatter_bytes", 0)), "gather_bytes_over_nvlink": int(timers.get("gather_bytes", 0)),
+                         "rank0_stage_ms_cumulative": stage,
+                         "path": "rank 0 host batch -> broadcast lengths -> pack + H2D + NCCL send of compact shard arenas -> bsb200_batch_upload_dev / run / fetch_dense_dev on every rank -> NCCL send of records + dense cigars -> pair-ordered merge on rank 0"}
+    e2e_ms = allred(e2e_ms, dist.ReduceOp.MAX if world > 1 else None)
+    e2e_val = total_cells / (e2e_ms * 1e-3) / 1e9
+
+    if rank == 0:
+        checksum = int(r.results[:, 0].astype(np.int64).sum())
+        bad_status = int((r.status != 0).sum())
+        # ---- parity: `check` pairs of the last e2e step against the CPU restatement, result records AND cigar words ----
+        checked = None
+        if check:
+            idx = np.unique(np.linspace(0, batch.n - 1, min(check, batch.n)).astype(np.int64))
+            exp, ecg, _ = ck.oracle_batch(kind, batch.subset(idx), w["mode"], w["bandwidth"], mtx, GAPS, nthreads=ncores)
+            nbad = compare_with_cpu(r, idx, exp, ecg)
+            checked = {"pairs": int(len(idx)), "fields": "10 result ints + every cigar word", "against": "oracle port (pinned to the reference)", "mismatches": int(nbad), "bit_exact": nbad == 0}
+        # ---- roofline of the dominant kernel (forward): algorithmic trace bytes / its event time, max over ranks ----------
+        peaks = load_peaks()
+        peak = float(peaks.get("hbm_gbs", 6650.0))
+        achieved = total_trace / world / (fwd_step_ms * 1e-3) / 1e9 if fwd_step_ms > 0 else 0.0    # per GPU
+        waved = kind == "epi8" and fwd_launches >= 2 * args.steps * max(1, waves) and w["bandwidth"] == 0
+        kname = ("epi8_wave_kernel" if waved else "epi8_forward_kernel") if kind == "epi8" else "edit_kernel"
+        facts = profile_facts(kind, waved)
+        traffic = traffic_src = int_issue = None
+        if facts:
+            traffic = facts["dram_over_algorithmic"] * total_trace / world / max(1, waves)
+            traffic_src = "ncu dram__bytes_read+write / algorithmic = %.3f (%s), scaled to this launch" % (facts["dram_over_algorithmic"], facts["capture"])
+            # ALU-pipe share measured under ncu, scaled by the ratio of the live kernel time per cell to the profiled one
+            live = fwd_step_ms * 1e-3 / (total_cells / world)
+            if facts.get("alu_pipe_pct") and facts.get("seconds_per_cell"):
+                int_issue = facts["alu_pipe_pct"] / 100.0 * facts["seconds_per_cell"] / live
+        out["roofline"] = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                           "peak_source": "measured (MEASURED_PEAKS.json)" if peaks else "fallback (B200_PROFILING.md)",
+                           "traffic": traffic, "traffic_source": traffic_src, "kernel": kname, "launches_per_step": int(waves),
+                           "int_issue_frac": int_issue,
+                           "int_issue_note": "the kernel's binding bound is integer issue, not HBM: ALU-pipe utilisation (sm__inst_executed_pipe_alu, ncu) of the committed capture scaled to this run's time per cell",
+                           "algorithmic_bytes_per_launch": int(total_trace / world / max(1, waves)), "kernel_ms_per_launch": fwd_step_ms / max(1, waves),
+                           "algorithmic_bytes_per_step": int(total_trace / world), "kernel_ms_per_step": fwd_step_ms,
+                           "traceback_ms_per_step": bt_step_ms, "waves_per_step": int(waves), "per": "GPU (max over ranks)"}
+        # ---- CPU baseline on this box's host cores (rank 0, N = 1 only) ----------------------------------------------------
+        cpu = None
+        if world == 1 and cpu_seconds > 0:
+            per_core = {"c2": 2.3, "c3": 1.5, "c4": 1.1, "g10k": 2.1}[name]
+            sample = args.cpu_sample or int(max(ncores, min(pairs, cpu_seconds * per_core * 1e9 * ncores / (cells / batch.n))))
+            sub = batch.subset(np.arange(sample))
+            cpu_reference_run(w, sub.subset(np.arange(min(sample, 2 * ncores))), ncores)
+            dt, ckind, cres, ccg = cpu_reference_run(w, sub, ncores, want_cigars=True)
+            nbad = compare_with_cpu(r, np.arange(sample), cres, ccg)
+            cpu = {"value": nominal_cells(w, sub) / dt / 1e9, "unit": "GCUPS", "cores": ncores, "kind": ckind,
+                   "sample": "first %d pairs of the same batch, %d host threads, %.1f s" % (sample, ncores, dt),
+                   "results_equal_gpu": nbad == 0, "compared": "10 result ints + every cigar word of %d pairs" % sample}
+        out.update({
+            "value": value, "ms_per_step": step_ms,
+            "config": config_of(name, w, pairs),
+            "e2e": dict({"value": e2e_val, "unit": "GCUPS", "ms_per_step": e2e_ms, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h)}, **e2e_extra),
+            "gpu_launches": int(launches), "cpu_baseline": cpu, "clocks": clocks,
+            "parity": {"nonzero_status_pairs": bad_status, "score_checksum": checksum, "checked": checked},
+            "notes": {"l2": "inputs (%.0f MB) and the %.1f GB traceback store written per step both exceed the 126 MB L2" % (batch.seqs.nbytes / 1e6, total_trace / 1e9),
+                      "timing": "CUDA events on the library stream; max over ranks", "wall_ms_per_step": wall / args.steps * 1e3,
+                      "sharding": None if world == 1 else "one batch on rank 0, %d shards of equal DP cells (bsalign_b200/shard.py); value = kernels on resident shards, e2e = the whole scatter/align/gather call" % world},
+        })
+    return out
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -379,10 +637,11 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS))
-    ap.add_argument("--pairs", type=int, default=0, help="pairs per GPU (default: the workload's)")
+    ap.add_argument("--pairs", type=int, default=0, help="pairs in the batch (default: the workload's)")
     ap.add_argument("--cpu-sample", type=int, default=0, help="pairs in the CPU baseline sample (default: sized for ~10-20 s)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--check", type=int, default=0, help="verify this many pairs of the last step against the oracle")
+    ap.add_argument("--no-secondary", action="store_true", help="skip the short g10k / c3 / c4 runs reported under `secondary`")
+    ap.add_argument("--check", type=int, default=1024, help="verify this many pairs of the last step (results + cigars) against the oracle")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
@@ -390,16 +649,17 @@ def main():
     world = int(os.environ.get("WORLD_SIZE", "1"))
     w = WORKLOADS[args.workload]
     pairs = args.pairs or w["pairs"]
-    if args.workload == "g10k" and not args.pairs and args.impl == "ours":
-        # a 10 kb x 10 kb pair is one dependency chain (one warp's issue rate): throughput comes from the number of pairs in flight,
-        # which the traceback store bounds (215 MB per pair incl. anchors and row padding).  Take what ONE wave of the library's
-        # default budget (90 % of free HBM) seats, with 3 % to spare.
+
+    def g10k_pairs():
+        # a 10 kb x 10 kb pair needs 215 MB of traceback store: take what ONE wave of the library's default budget (90 % of free HBM) seats
         try:
             import torch
             free, _total = torch.cuda.mem_get_info(local_rank)
-            pairs = max(148, int(0.90 * free * 0.97 / 217.5e6))
+            return max(148, int(0.90 * free * 0.97 / 218.0e6)) * world
         except Exception:
-            pass
+            return WORKLOADS["g10k"]["pairs"]
+    if args.workload == "g10k" and not args.pairs and args.impl == "ours":
+        pairs = g10k_pairs()
     ncores = os.cpu_count() or 1
     if w["kind"] == "poa":
         return main_poa(args, w, pairs, ncores, rank, local_rank, world)
@@ -425,9 +685,9 @@ def main():
         sample_desc = "%d pairs of the %s shape per step, %d host threads" % (sample, args.workload, ncores)
         print(json.dumps({
             "impl": "reference", "metric": "GCUPS", "value": val, "unit": "GCUPS (1e9 band cells/s)", "n_gpus": args.gpus, "steps": args.steps,
-            "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "strong" if args.gpus > 1 else "weak", "vs_baseline": None,
             "dtype": "int8" if w["kind"] == "epi8" else "u64 bit-planes", "data": "synthetic",
-            "config": {"workload": "%s: %s" % (args.workload, w["desc"]), "pairs_per_step": sample, "matrix": MATRIX, "gaps": GAPS},
+            "config": config_of(args.workload, w, pairs),
             "cpu_baseline": {"value": val, "unit": "GCUPS", "cores": ncores, "kind": kind, "sample": sample_desc},
             "e2e": {"value": val, "unit": "GCUPS", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         }))
@@ -436,7 +696,7 @@ def main():
     # ------------------------------------------------------------------ our arm (GPU) -----------------
     import torch
     import torch.distributed as dist
-    from bsalign_b200 import api, synth
+    from bsalign_b200 import api
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device; the product path has no CPU fallback (use --impl reference for the CPU arm)")
     torch.cuda.set_device(local_rank)
@@ -453,149 +713,40 @@ def main():
             sys.stdout.flush()
             os.dup2(saved, 1)
             os.close(saved)
-
-    def barrier():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-
-    def max_over_ranks(x):
-        if world == 1:
-            return x
-        t = torch.tensor([x], dtype=torch.float64, device="cuda")
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        return float(t.item())
-
-    def sum_over_ranks(x):
-        if world == 1:
-            return x
-        t = torch.tensor([x], dtype=torch.float64, device="cuda")
-        dist.all_reduce(t, op=dist.ReduceOp.SUM)
-        return float(t.item())
-
-    mtx = synth.score_matrix(*MATRIX)
-    batch = make_batch(w, 1000 + rank, pairs)          # this rank's shard
-    cells = nominal_cells(w, batch)
-    # pinned host copies of the inputs for the e2e leg
-    pin = lambda a: torch.from_numpy(a).pin_memory().numpy()
-    hb = synth.PairBatch.__new__(synth.PairBatch)
-    hb.seqs, hb.qoff, hb.qlen, hb.toff, hb.tlen = pin(batch.seqs), pin(batch.qoff), pin(batch.qlen), pin(batch.toff), pin(batch.tlen)
     ctx = api.Context(local_rank)
-    out = tuple(pin(a) if a is not None else None for a in api._alloc_out(hb, True))   # pinned result / cigar arenas
-
-    def one_e2e():
-        # the public host-buffer call: upload -> kernels -> dense, pair-ordered results into the pinned arenas
-        if w["kind"] == "epi8":
-            return ctx.epi8_batch(hb, w["mode"], w["bandwidth"], mtx, *GAPS, out=out, dense=True)
-        return ctx.edit_batch(hb, w["mode"], w["bandwidth"], out=out, dense=True)
-
-    # ---- kernel-only leg: inputs resident in HBM --------------------------------------------------
-    rb = ctx.upload(w["kind"], hb, w["mode"], w["bandwidth"], mtx, GAPS, want_cigar=True)
-    sampler = ClockSampler(local_rank)
-    sampler.start()
-    for _ in range(args.warmup):
-        rb.run()
-    barrier()
-    sampler.mark()
-    dev_ms = fwd_ms = bt_ms = 0.0
-    fwd_launches = bt_launches = 0
-    t0 = time.perf_counter()
-    for _ in range(args.steps):
-        rb.run()
-        tm = ctx.timing()
-        dev_ms += tm["run_ms"]; fwd_ms += tm["forward_ms"]; bt_ms += tm["traceback_ms"]
-        fwd_launches += tm["forward_launches"]; bt_launches += tm["traceback_launches"]
-    barrier()
-    wall = time.perf_counter() - t0
-    clocks = sampler.stop()
-    trace_bytes, waves = tm["trace_bytes"], tm["waves"]
-    last = rb.fetch(out=out)
-    rb.free()
-    step_ms = max_over_ranks(dev_ms / args.steps)
-    total_cells = sum_over_ranks(cells)
-    value = total_cells / (step_ms * 1e-3) / 1e9
-
-    # ---- e2e leg: host buffers through the C-ABI call ---------------------------------------------
-    for _ in range(min(args.warmup, 3)):
-        one_e2e()
-    barrier()
-    t0 = time.perf_counter()
-    h2d = d2h = 0
-    e2e_parts = {"h2d_ms": 0.0, "run_ms": 0.0, "d2h_ms": 0.0}
-    for _ in range(args.steps):
-        r = one_e2e()
-        tm2 = ctx.last_timing
-        h2d, d2h = tm2["h2d_bytes"], tm2["d2h_bytes"]
-        for k in e2e_parts:
-            e2e_parts[k] += tm2[k] / args.steps
-    barrier()
-    e2e_ms = max_over_ranks((time.perf_counter() - t0) / args.steps * 1e3)
-    e2e_val = total_cells / (e2e_ms * 1e-3) / 1e9
-    checksum = int(r.results[:, 0].astype(np.int64).sum())
-    assert checksum == int(last.results[:, 0].astype(np.int64).sum()), "e2e and resident runs disagree"
-    bad_status = int((r.status != 0).sum())
-
-    # ---- optional parity spot check ------------------------------------------------------------------
-    checked = None
-    if args.check:
-        import checkers as ck
-        idx = np.linspace(0, batch.n - 1, args.check).astype(np.int64)
-        sub = batch.subset(idx)
-        exp, ecg, _ = ck.oracle_batch(w["kind"], sub, w["mode"], w["bandwidth"], mtx, GAPS, nthreads=ncores)
-        ok = all(np.array_equal(r.results[i], exp[k]) and np.array_equal(r.cigar(i), ecg[k]) for k, i in enumerate(idx))
-        checked = {"pairs": int(args.check), "bit_exact": bool(ok)}
-
-    # ---- roofline of the dominant kernel (forward): algorithmic trace bytes / its event time ---------
-    peaks = {}
-    try:
-        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
-    except Exception:
-        pass
-    peak = float(peaks.get("hbm_gbs", 6650.0))
-    achieved = trace_bytes * args.steps / (fwd_ms * 1e-3) / 1e9 if fwd_ms > 0 else 0.0
-    kname = "epi8_forward_kernel" if w["kind"] == "epi8" else "edit_kernel"
-    traffic, traffic_src = None, None
-    try:   # DRAM bytes per launch: ncu-measured ratio (profiles/traffic_r1.json) x this launch's algorithmic bytes
-        tr = json.load(open(os.path.join(ROOT, "profiles", "traffic_r1.json")))[kname]
-        traffic = tr["ratio"] * trace_bytes / max(1, waves)
-        traffic_src = "ncu dram__bytes_read+write / algorithmic = %.3f (%s), scaled to this launch" % (tr["ratio"], tr["capture"])
-    except Exception:
-        pass
-    roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "peak_source": "measured (MEASURED_PEAKS.json)" if peaks else "fallback (B200_PROFILING.md)",
-                "traffic": traffic, "traffic_source": traffic_src, "kernel": kname, "launches_per_step": waves,
-                "algorithmic_bytes_per_launch": int(trace_bytes / max(1, waves)), "kernel_ms_per_launch": fwd_ms / args.steps / max(1, waves),
-                "algorithmic_bytes_per_step": int(trace_bytes), "kernel_ms_per_step": fwd_ms / args.steps,
-                "traceback_ms_per_step": bt_ms / args.steps, "waves_per_step": waves}
-
-    # ---- CPU baseline on this box's host cores (rank 0, N=1 only) ------------------------------------
-    cpu = None
-    if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        per_core = {"c2": 2.3, "c3": 1.5, "c4": 1.1, "g10k": 2.1}[args.workload]
-        sample = args.cpu_sample or int(max(ncores, min(pairs, 12.0 * per_core * 1e9 * ncores / (cells / batch.n))))
-        sub = batch.subset(np.arange(sample))
-        scells = nominal_cells(w, sub)
-        cpu_reference_run(w, sub.subset(np.arange(min(sample, 2 * ncores))), ncores)
-        dt, kind, cres = cpu_reference_run(w, sub, ncores)
-        same = bool(np.array_equal(cres, r.results[:sample]))
-        cpu = {"value": scells / dt / 1e9, "unit": "GCUPS", "cores": ncores, "kind": kind,
-               "sample": "first %d pairs of the same batch, %d host threads, %.1f s" % (sample, ncores, dt),
-               "results_equal_gpu": same}
-
+    main_out = run_workload(ctx, args.workload, w, pairs, args, ncores, rank, world, local_rank, dist, torch,
+                            0 if args.no_cpu_baseline else 12.0, args.check)
+    # ---- secondary: short runs of the other pairwise workloads in the same process (N = 1 only), so that their numbers are
+    # driver-visible next to the headline: g10k (north_star target: >= 10x the reference's CPU GCUPS), c3, c4 ---------------------
+    secondary = None
+    if world == 1 and not args.no_secondary and args.workload == "c2" and not args.pairs:
+        secondary = {}
+        sargs = argparse.Namespace(**vars(args))
+        sargs.steps, sargs.warmup, sargs.cpu_sample = 2, 2, 0
+        for name in ("g10k", "c3", "c4"):
+            sw = WORKLOADS[name]
+            try:
+                ctx.trim()   # hand the previous workload's traceback arena back, so that the next one plans against the whole device
+                sp = g10k_pairs() if name == "g10k" else sw["pairs"]
+                so = run_workload(ctx, name, sw, sp, sargs, ncores, rank, world, local_rank, dist, torch, 0 if args.no_cpu_baseline else 5.0, min(args.check, 256))
+                cpu = so.get("cpu_baseline")
+                secondary[name] = {"workload": so["config"]["workload"], "pairs": so["config"]["pairs"], "value": so["value"], "ms_per_step": so["ms_per_step"],
+                                   "e2e": so["e2e"]["value"], "e2e_ms_per_step": so["e2e"]["ms_per_step"], "e2e_pageable": so["e2e"].get("pageable", {}).get("value"),
+                                   "roofline_frac": so["roofline"]["frac"], "kernel": so["roofline"]["kernel"], "kernel_ms_per_step": so["roofline"]["kernel_ms_per_step"],
+                                   "traceback_ms_per_step": so["roofline"]["traceback_ms_per_step"],
+                                   "cpu": None if not cpu else {"value": cpu["value"], "cores": cpu["cores"], "kind": cpu["kind"], "sample": cpu["sample"], "results_equal_gpu": cpu["results_equal_gpu"]},
+                                   "speedup_vs_cpu": None if not cpu else so["value"] / cpu["value"], "e2e_speedup_vs_cpu": None if not cpu else so["e2e"]["value"] / cpu["value"],
+                                   "parity": so["parity"], "steps": sargs.steps, "warmup": sargs.warmup}
+            except Exception as e:   # a secondary run must never take the headline line with it
+                secondary[name] = {"error": repr(e)}
     if rank == 0:
-        print(json.dumps({
-            "metric": "GCUPS", "value": value, "unit": "GCUPS (1e9 band cells/s)", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": step_ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "int8" if w["kind"] == "epi8" else "u64 bit-planes", "data": "synthetic",
-            "config": {"workload": "%s: %s" % (args.workload, w["desc"]), "pairs_per_gpu": pairs, "matrix": MATRIX, "gaps": GAPS,
-                       "l2": "inputs (%.0f MB) and the %.1f GB traceback store written per step both exceed the 126 MB L2" % (batch.seqs.nbytes / 1e6, trace_bytes / 1e9),
-                       "timing": "CUDA events on the library stream; max over ranks", "wall_ms_per_step": wall / args.steps * 1e3},
-            "e2e": {"value": e2e_val, "unit": "GCUPS", "ms_per_step": e2e_ms, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
-                    "device_parts_ms": e2e_parts, "host_planning_and_scatter_ms": e2e_ms - sum(e2e_parts.values())},
-            "gpu_launches": int(fwd_launches + bt_launches),
-            "roofline": roofline, "cpu_baseline": cpu, "clocks": clocks,
-            "parity": {"nonzero_status_pairs": bad_status, "score_checksum": checksum, "checked": checked},
-        }))
+        line = {"metric": "GCUPS", "value": main_out["value"], "unit": "GCUPS (1e9 band cells/s)", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+                "ms_per_step": main_out["ms_per_step"], "higher_is_better": True, "scaling": "strong" if world > 1 else "weak", "vs_baseline": None,
+                "dtype": "int8" if w["kind"] == "epi8" else "u64 bit-planes", "data": "synthetic"}
+        for k in ("config", "e2e", "gpu_launches", "roofline", "cpu_baseline", "clocks", "parity", "notes"):
+            line[k] = main_out[k]
+        line["secondary"] = secondary
+        print(json.dumps(line))
     ctx.close()
     if world > 1:
         dist.destroy_process_group()

@@ -72,6 +72,14 @@ def lib():
                                                  _I8, _I8, _I8, _I8, _P, _P, _P, _P, _P]
         L.bsb200_edit_pairwise_batch.argtypes = [_P, ctypes.c_uint64, _P, _P, _P, _P, _P, ctypes.c_int, ctypes.c_uint32,
                                                  _P, _P, _P, _P, _P]
+        L.bsb200_batch_upload_dev.restype = _P
+        L.bsb200_batch_upload_dev.argtypes = L.bsb200_batch_upload.argtypes
+        L.bsb200_batch_fetch_dense_dev.argtypes = [_P, _P, _P, _P, ctypes.c_uint64, _P, _P, _P]
+        L.bsb200_pack_pairs.restype = ctypes.c_uint64
+        L.bsb200_pack_pairs.argtypes = [_P, _P, _P, _P, _P, _P, ctypes.c_uint64, _P, _P, _P, ctypes.c_int]
+        L.bsb200_scatter_words.argtypes = [_P, _P, _P, _P, _P, ctypes.c_uint64, ctypes.c_int]
+        L.bsb200_trim.argtypes = [_P]
+        L.bsb200_default_context.restype = _P
         L.bsb200_epi8_bandwidth.restype = ctypes.c_uint32
         L.bsb200_epi8_bandwidth.argtypes = [ctypes.c_uint32, ctypes.c_uint32]
         L.bsb200_edit_bandwidth.restype = ctypes.c_uint32
@@ -170,6 +178,46 @@ class Context:
         return ResidentBatch(self, h, batch, want_cigar)
 
 
+    def upload_dev(self, kind, d_seqs_ptr, batch, mode, bandwidth, matrix=None, gaps=(0, 0, 0, 0), want_cigar=True):
+        """Like upload(), but the sequence arena is already in this device's memory (int device pointer; the caller keeps it alive
+        until the batch is freed); batch.qoff/qlen/toff/tlen are host arrays that index it (batch.seqs is not read)."""
+        m = np.ascontiguousarray(matrix if matrix is not None else np.zeros(16), dtype=np.int8)
+        h = self._lib.bsb200_batch_upload_dev(self._h, 0 if kind == "epi8" else 1, batch.n, ctypes.c_void_p(int(d_seqs_ptr)), _ptr(batch.qoff), _ptr(batch.qlen),
+                                              _ptr(batch.toff), _ptr(batch.tlen), int(mode), int(bandwidth), _ptr(m),
+                                              gaps[0], gaps[1], gaps[2], gaps[3], 1 if want_cigar else 0)
+        if not h:
+            raise RuntimeError("bsb200_batch_upload_dev failed: %s" % self._lib.bsb200_last_error(self._h).decode())
+        return ResidentBatch(self, h, batch, want_cigar)
+
+    def trim(self):
+        self._lib.bsb200_trim(self._h)
+
+
+def pack_pairs(batch, idx, out_seqs=None, nthreads=8):
+    """Compact arena of the pairs idx of a batch (query then target of each pair, in idx order).  Returns (PairBatch over the compact
+    arena, bytes).  out_seqs: optional uint8 array (e.g. pinned) of sufficient size to pack into."""
+    L = lib()
+    idx = np.ascontiguousarray(idx, dtype=np.uint64)
+    m = len(idx)
+    qoff = np.zeros(m, dtype=np.uint64)
+    toff = np.zeros(m, dtype=np.uint64)
+    nbytes = int(batch.qlen[idx.astype(np.int64)].astype(np.int64).sum() + batch.tlen[idx.astype(np.int64)].astype(np.int64).sum()) if m else 0
+    if out_seqs is None:
+        out_seqs = np.empty(max(nbytes, 1), dtype=np.uint8)
+    assert out_seqs.size >= nbytes
+    L.bsb200_pack_pairs(_ptr(batch.seqs), _ptr(batch.qoff), _ptr(batch.qlen), _ptr(batch.toff), _ptr(batch.tlen), _ptr(idx), m,
+                        _ptr(out_seqs), _ptr(qoff), _ptr(toff), int(nthreads))
+    i64 = idx.astype(np.int64)
+    pb = PairBatch.__new__(PairBatch)
+    pb.seqs, pb.qoff, pb.qlen, pb.toff, pb.tlen = out_seqs[:max(nbytes, 1)], qoff, np.ascontiguousarray(batch.qlen[i64]), toff, np.ascontiguousarray(batch.tlen[i64])
+    return pb, nbytes
+
+
+def scatter_words(dst, dst_off, src, src_off, length, nthreads=8):
+    lib().bsb200_scatter_words(_ptr(dst), _ptr(np.ascontiguousarray(dst_off, dtype=np.uint64)), _ptr(src), _ptr(np.ascontiguousarray(src_off, dtype=np.uint64)),
+                               _ptr(np.ascontiguousarray(length, dtype=np.uint32)), len(length), int(nthreads))
+
+
 def _alloc_out(batch, want_cigar):
     n = batch.n
     res = np.zeros((n, 10), dtype=np.int32)
@@ -218,6 +266,15 @@ class ResidentBatch:
         doff = np.zeros(len(ncg) + 1, dtype=np.uint64)
         np.cumsum(ncg, out=doff[1:])
         return BatchResult(res, cg, doff, ncg, st)
+
+    def fetch_dense_dev(self, d_results, d_cigars, cigar_cap_words, d_ncigar, d_status):
+        """Results into DEVICE buffers (int device pointers, any may be 0/None).  Returns the number of dense cigar words."""
+        total = ctypes.c_uint64(0)
+        vp = lambda x: ctypes.c_void_p(int(x)) if x else None
+        rc = self.ctx._lib.bsb200_batch_fetch_dense_dev(self.ctx._h, self._h, vp(d_results), vp(d_cigars), int(cigar_cap_words), ctypes.byref(total), vp(d_ncigar), vp(d_status))
+        if rc != 0 and not (d_cigars and total.value > cigar_cap_words):
+            self.ctx._check(rc, "bsb200_batch_fetch_dense_dev")
+        return int(total.value), rc
 
     def free(self):
         if self._h:

@@ -92,13 +92,15 @@ struct bsb200_batch {
 	int pw = 0; int want_cigar = 1;
 	uint32_t max_bw = 16, max_q64 = 64, max_qlen = 0;
 	std::vector<uint8_t> empty;
-	uint64_t cells = 0, trace_bytes = 0, cig_words = 0;
+	uint64_t cells = 0, trace_bytes = 0, cig_words = 0, max_wave_bytes = 0;
 	std::vector<Wave> waves;
 	std::vector<uint32_t> order;
 	std::vector<uint64_t> trace_off, cig_off;
 	DevBuf d_seqs, d_qoff, d_toff, d_qlen, d_tlen, d_order, d_trace_off, d_results, d_status, d_ncigar, d_cig_raw, d_cig_off, d_cig_dense, d_dense_off, d_dense_total, d_block_rows, d_prefix;
 	HostBuf h_results, h_status, h_ncigar, h_dense_off, h_dense, h_total;
 	size_t seq_bytes = 0;
+	const uint8_t *d_seqs_ext = nullptr;   // device-resident arena owned by the caller (bsb200_batch_upload_dev)
+	const uint8_t *seqs_dev() const { return d_seqs_ext ? d_seqs_ext : d_seqs.as<uint8_t>(); }
 	bool ran = false;
 };
 
@@ -154,6 +156,29 @@ extern "C" void bsb200_destroy(bsb200_ctx *ctx){
 	delete ctx;
 }
 
+// give the traceback arena and every cached buffer back to the device (the next batch allocates again)
+extern "C" void bsb200_trim(bsb200_ctx *ctx){
+	if(!ctx) return;
+	cudaSetDevice(ctx->device);
+	cudaStreamSynchronize(ctx->stream);
+	ctx->trace.release(); ctx->trace2.release();
+	for(auto &d : ctx->dev_cache) d.release();
+	for(auto &h : ctx->host_cache) h.release();
+	for(auto &d : ctx->poa_cache) d.release();
+	for(auto &h : ctx->poa_hcache) h.release();
+	ctx->auto_budget = 0;
+}
+
+// one shared context on device 0 for callers that have none (the compat headers; every translation unit gets the same one)
+extern "C" bsb200_ctx *bsb200_default_context(void){
+	static bsb200_ctx *ctx = nullptr;
+	static std::atomic<int> lock{0};
+	while(lock.exchange(1)) std::this_thread::yield();
+	if(!ctx) ctx = bsb200_create(0, 0);
+	lock.store(0);
+	return ctx;
+}
+
 extern "C" const char *bsb200_last_error(bsb200_ctx *ctx){ return ctx ? ctx->err.c_str() : "null context"; }
 extern "C" void bsb200_get_timing(bsb200_ctx *ctx, bsb200_timing_t *out){ if(ctx && out) *out = ctx->timing; }
 
@@ -168,12 +193,14 @@ extern "C" uint32_t bsb200_edit_bandwidth(uint32_t qlen, uint32_t tlen, int mode
 
 void bsb200_batch_free(bsb200_ctx *ctx, bsb200_batch *b);
 
-extern "C" bsb200_batch *bsb200_batch_upload(bsb200_ctx *ctx, int kind, uint64_t n, const uint8_t *seqs,
+// d_seqs_ext: the sequence arena is already in this device's memory (it arrived over NVLink: bsalign_b200/shard.py); the batch
+// uses it in place and the caller keeps it alive until bsb200_batch_free.  Offsets and lengths are host arrays in both cases.
+static bsb200_batch *upload_impl(bsb200_ctx *ctx, int kind, uint64_t n, const uint8_t *seqs, const uint8_t *d_seqs_ext,
 		const uint64_t *qoff, const uint32_t *qlen, const uint64_t *toff, const uint32_t *tlen,
 		int mode, uint32_t bandwidth, const int8_t matrix[16], int8_t go1, int8_t ge1, int8_t go2, int8_t ge2, int want_cigar){
 	if(!ctx) return nullptr;
 	ctx->err.clear();
-	if(n >= 0xFFFFFFF0ull || (n && (!seqs || !qoff || !qlen || !toff || !tlen)) || (kind == 0 && !matrix) || kind < 0 || kind > 1){
+	if(n >= 0xFFFFFFF0ull || (n && ((!seqs && !d_seqs_ext) || !qoff || !qlen || !toff || !tlen)) || (kind == 0 && !matrix) || kind < 0 || kind > 1){
 		fail(ctx, "bsb200_batch_upload", cudaSuccess); return nullptr;
 	}
 	cudaSetDevice(ctx->device);
@@ -206,7 +233,9 @@ extern "C" bsb200_batch *bsb200_batch_upload(bsb200_ctx *ctx, int kind, uint64_t
 	auto R = [&](cudaError_t x){ if(e == cudaSuccess) e = x; };
 	// every early return below first waits for the copies in flight (they read the caller's memory)
 	auto bail = [&]() -> bsb200_batch* { cudaStreamSynchronize(st); bsb200_batch_free(ctx, b); return nullptr; };
-	R(b->d_seqs.reserve(seq_end + 16)); R(b->d_qoff.reserve(n * 8 + 8)); R(b->d_toff.reserve(n * 8 + 8));
+	if(!d_seqs_ext) R(b->d_seqs.reserve(seq_end + 16));
+	b->d_seqs_ext = d_seqs_ext;
+	R(b->d_qoff.reserve(n * 8 + 8)); R(b->d_toff.reserve(n * 8 + 8));
 	R(b->d_qlen.reserve(n * 4 + 4)); R(b->d_tlen.reserve(n * 4 + 4));
 	if(e != cudaSuccess){ fail(ctx, "device allocation", e); return bail(); }
 	// (a first attempt ran the plan of a million edit pairs three times slower next to the DMA stream - config 4 end to end
@@ -215,7 +244,7 @@ extern "C" bsb200_batch *bsb200_batch_upload(bsb200_ctx *ctx, int kind, uint64_t
 	auto copy_inputs = [&](){
 		cudaEventRecord(ctx->ev[0], st);
 		if(n){
-			R(cudaMemcpyAsync(b->d_seqs.p, seqs, seq_end, cudaMemcpyHostToDevice, st));
+			if(!d_seqs_ext) R(cudaMemcpyAsync(b->d_seqs.p, seqs, seq_end, cudaMemcpyHostToDevice, st));
 			R(cudaMemcpyAsync(b->d_qoff.p, qoff, n * 8, cudaMemcpyHostToDevice, st));
 			R(cudaMemcpyAsync(b->d_toff.p, toff, n * 8, cudaMemcpyHostToDevice, st));
 			R(cudaMemcpyAsync(b->d_qlen.p, qlen, n * 4, cudaMemcpyHostToDevice, st));
@@ -372,6 +401,7 @@ extern "C" bsb200_batch *bsb200_batch_upload(bsb200_ctx *ctx, int kind, uint64_t
 		}
 		uint64_t max_wave = 0;
 		for(auto &w : b->waves) max_wave = std::max(max_wave, w.trace_bytes);
+		b->max_wave_bytes = max_wave;
 		const cudaError_t ea = ctx->trace.reserve(max_wave + 256, true);
 		if(ea == cudaSuccess) break;
 		cudaGetLastError();   // clear the sticky allocation error
@@ -395,11 +425,23 @@ extern "C" bsb200_batch *bsb200_batch_upload(bsb200_ctx *ctx, int kind, uint64_t
 	float ms = 0; cudaEventElapsedTime(&ms, ctx->ev[0], ctx->ev[1]);
 	ctx->timing = bsb200_timing_t();
 	ctx->timing.h2d_ms = ms;
-	ctx->timing.h2d_bytes = seq_end + n * (8 + 8 + 4 + 4 + 4 + 8) + (want_cigar ? (n + 1) * 8 : 0);
+	ctx->timing.h2d_bytes = (d_seqs_ext ? 0 : seq_end) + n * (8 + 8 + 4 + 4 + 4 + 8) + (want_cigar ? (n + 1) * 8 : 0);
 	ctx->timing.cells = b->cells;
 	ctx->timing.trace_bytes = b->trace_bytes;
 	ctx->timing.waves = (uint32_t)b->waves.size();
 	return b;
+}
+
+extern "C" bsb200_batch *bsb200_batch_upload(bsb200_ctx *ctx, int kind, uint64_t n, const uint8_t *seqs,
+		const uint64_t *qoff, const uint32_t *qlen, const uint64_t *toff, const uint32_t *tlen,
+		int mode, uint32_t bandwidth, const int8_t matrix[16], int8_t go1, int8_t ge1, int8_t go2, int8_t ge2, int want_cigar){
+	return upload_impl(ctx, kind, n, seqs, nullptr, qoff, qlen, toff, tlen, mode, bandwidth, matrix, go1, ge1, go2, ge2, want_cigar);
+}
+
+extern "C" bsb200_batch *bsb200_batch_upload_dev(bsb200_ctx *ctx, int kind, uint64_t n, const uint8_t *d_seqs,
+		const uint64_t *qoff, const uint32_t *qlen, const uint64_t *toff, const uint32_t *tlen,
+		int mode, uint32_t bandwidth, const int8_t matrix[16], int8_t go1, int8_t ge1, int8_t go2, int8_t ge2, int want_cigar){
+	return upload_impl(ctx, kind, n, nullptr, d_seqs, qoff, qlen, toff, tlen, mode, bandwidth, matrix, go1, ge1, go2, ge2, want_cigar);
 }
 
 template<int PW, bool FAST, bool ANCH>
@@ -535,7 +577,13 @@ extern "C" int bsb200_batch_run(bsb200_ctx *ctx, bsb200_batch *b){
 	cudaStream_t st = ctx->stream;
 	ctx->timing.forward_launches = ctx->timing.traceback_launches = ctx->timing.other_launches = 0;
 	float fwd_ms = 0, bt_ms = 0;
-	std::vector<cudaEvent_t> evs;
+	// four events per wave, destroyed on every way out (an error return first waits for the kernels already in flight)
+	struct EventSet {
+		std::vector<cudaEvent_t> v; cudaStream_t st;
+		~EventSet(){ if(!v.empty()) cudaStreamSynchronize(st); for(auto &e : v) if(e) cudaEventDestroy(e); }
+		cudaEvent_t &operator[](size_t i){ return v[i]; }
+	} evs;
+	evs.st = st;
 	if(b->n == 0 || b->waves.empty()){ if(b->n){ cudaMemsetAsync(b->d_results.p, 0, b->n * 40, st); cudaMemsetAsync(b->d_status.p, 0, b->n * 4, st); cudaMemsetAsync(b->d_ncigar.p, 0, b->n * 4, st); cudaMemsetAsync(b->d_dense_off.p, 0, b->n * 8, st); cudaMemsetAsync(b->d_dense_total.p, 0, 16, st); cudaStreamSynchronize(st);} b->ran = true; return 0; }
 	CK(cudaEventRecord(ctx->ev[4], st));
 	CK(cudaMemsetAsync(b->d_results.p, 0, b->n * 40, st));
@@ -544,8 +592,12 @@ extern "C" int bsb200_batch_run(bsb200_ctx *ctx, bsb200_batch *b){
 	CK(cudaMemsetAsync(b->d_dense_total.p, 0, 16, st));
 	CK(cudaMemsetAsync(b->d_dense_off.p, 0, b->n * 8, st));
 	// four events per wave: [forward start, forward done, traceback start, traceback done]
-	evs.resize(b->waves.size() * 4);
-	for(auto &e : evs) CK(cudaEventCreate(&e));
+	evs.v.assign(b->waves.size() * 4, nullptr);
+	for(auto &e : evs.v) CK(cudaEventCreate(&e));
+	// the arena may have been trimmed or re-planned smaller since this batch was uploaded (bsb200_trim, another batch's allocation failure)
+	if(ctx->trace.cap < b->max_wave_bytes + 256){
+		if(ctx->trace.reserve(b->max_wave_bytes + 256, true) != cudaSuccess){ cudaGetLastError(); return fail(ctx, "traceback arena smaller than this batch's largest wave and it cannot be re-allocated", cudaErrorMemoryAllocation); }
+	}
 	cudaStream_t sb = st; // (ctx->stream_bt is kept for experiments with concurrent traceback)
 	for(size_t wi=0;wi<b->waves.size();wi++){
 		const Wave &w = b->waves[wi];
@@ -555,7 +607,7 @@ extern "C" int bsb200_batch_run(bsb200_ctx *ctx, bsb200_batch *b){
 		CK(cudaEventRecord(evs[wi * 4 + 0], st));
 		if(b->kind == 0){
 			Epi8Args a;
-			a.seqs = b->d_seqs.as<uint8_t>(); a.qoff = b->d_qoff.as<uint64_t>(); a.toff = b->d_toff.as<uint64_t>();
+			a.seqs = b->seqs_dev(); a.qoff = b->d_qoff.as<uint64_t>(); a.toff = b->d_toff.as<uint64_t>();
 			a.qlen = b->d_qlen.as<uint32_t>(); a.tlen = b->d_tlen.as<uint32_t>();
 			a.order = b->d_order.as<uint32_t>() + w.beg; a.npairs = np; a.counter = ctx->counter.as<unsigned int>();
 			a.trace = arena; a.trace_off = b->d_trace_off.as<uint64_t>();
@@ -599,7 +651,7 @@ extern "C" int bsb200_batch_run(bsb200_ctx *ctx, bsb200_batch *b){
 			CK(cudaEventRecord(evs[wi * 4 + 3], sb));
 		} else {
 			EditArgs a;
-			a.seqs = b->d_seqs.as<uint8_t>(); a.qoff = b->d_qoff.as<uint64_t>(); a.toff = b->d_toff.as<uint64_t>();
+			a.seqs = b->seqs_dev(); a.qoff = b->d_qoff.as<uint64_t>(); a.toff = b->d_toff.as<uint64_t>();
 			a.qlen = b->d_qlen.as<uint32_t>(); a.tlen = b->d_tlen.as<uint32_t>();
 			a.order = b->d_order.as<uint32_t>() + w.beg; a.npairs = np;
 			a.trace = ctx->trace.as<uint8_t>();
@@ -626,7 +678,6 @@ extern "C" int bsb200_batch_run(bsb200_ctx *ctx, bsb200_batch *b){
 		cudaEventElapsedTime(&m2, evs[wi * 4 + 2], evs[wi * 4 + 3]);
 		fwd_ms += m1; bt_ms += m2;
 	}
-	for(auto &e : evs) cudaEventDestroy(e);
 	ctx->timing.forward_ms = fwd_ms; ctx->timing.traceback_ms = bt_ms;
 	ctx->timing.other_launches = 5 + (uint32_t)b->waves.size();
 	b->ran = true;
@@ -734,6 +785,91 @@ static int fetch_impl(bsb200_ctx *ctx, bsb200_batch *b, bsb200_result_t *results
 		}
 	}
 	return 0;
+}
+
+// Results of a finished run into DEVICE buffers of the caller (they travel on to another GPU over NVLink: bsalign_b200/shard.py):
+// d_results n x 10 int32, d_ncigar n, d_status n (kernel flags; BSB200_ST_EMPTY is a host-side flag - pairs with qlen or tlen 0
+// come back all zero), d_cigars dense and pair-ordered like bsb200_batch_fetch_dense.  *total_words always receives the word count.
+extern "C" int bsb200_batch_fetch_dense_dev(bsb200_ctx *ctx, bsb200_batch *b, int32_t *d_results, uint32_t *d_cigars, uint64_t cigar_cap_words,
+		uint64_t *total_words, uint32_t *d_ncigar, int32_t *d_status){
+	if(!ctx || !b || !b->ran) return fail(ctx, "bsb200_batch_fetch_dense_dev before run", cudaSuccess);
+	ctx->err.clear();
+	cudaSetDevice(ctx->device);
+	cudaStream_t st = ctx->stream;
+	const uint64_t n = b->n;
+	if(total_words) *total_words = 0;
+	if(n == 0) return 0;
+	cudaEventRecord(ctx->ev[2], st);
+	if(d_results) CK(cudaMemcpyAsync(d_results, b->d_results.p, n * 40, cudaMemcpyDeviceToDevice, st));
+	if(d_status) CK(cudaMemcpyAsync(d_status, b->d_status.p, n * 4, cudaMemcpyDeviceToDevice, st));
+	if(d_ncigar) CK(cudaMemcpyAsync(d_ncigar, b->d_ncigar.p, n * 4, cudaMemcpyDeviceToDevice, st));
+	uint64_t total = 0;
+	if(b->want_cigar){
+		CK(b->h_total.reserve(16));
+		CK(b->d_prefix.reserve((n + 1) * 8));
+		size_t tmp_bytes = 0;
+		cub::TransformInputIterator<uint64_t, U32toU64, const uint32_t*> it(b->d_ncigar.as<uint32_t>(), U32toU64());
+		CK(cub::DeviceScan::ExclusiveSum(nullptr, tmp_bytes, it, b->d_prefix.as<uint64_t>(), (int)n, st));
+		CK(ctx->counter.reserve(tmp_bytes + 256));
+		CK(cub::DeviceScan::ExclusiveSum((uint8_t*)ctx->counter.p + 256, tmp_bytes, it, b->d_prefix.as<uint64_t>(), (int)n, st));
+		CK(cudaMemcpyAsync(b->h_total.p, b->d_dense_total.p, 8, cudaMemcpyDeviceToHost, st));
+		CK(cudaStreamSynchronize(st));
+		total = *b->h_total.as<unsigned long long>();
+		if(total_words) *total_words = total;
+		if(d_cigars){
+			if(total > cigar_cap_words) return fail(ctx, "cigar buffer too small for the dense cigars (see total_words)", cudaSuccess);
+			if(total){
+				cigar_order_kernel<<<(unsigned)((n * 32 + 255) / 256), 256, 0, st>>>(b->d_cig_dense.as<uint32_t>(), b->d_dense_off.as<uint64_t>(),
+					b->d_ncigar.as<uint32_t>(), b->d_prefix.as<uint64_t>(), d_cigars, n);
+				CK(cudaGetLastError());
+			}
+		}
+	}
+	cudaEventRecord(ctx->ev[3], st);
+	CK(cudaStreamSynchronize(st));
+	float ms = 0; cudaEventElapsedTime(&ms, ctx->ev[2], ctx->ev[3]);
+	ctx->timing.d2h_ms = ms; ctx->timing.d2h_bytes = 8;
+	return 0;
+}
+
+// ---- host helpers of the multi-GPU split (bsalign_b200/shard.py): compact arenas per shard, pair-ordered merge of the shards' cigars ----
+// The pairs idx[0..m) of a batch are copied into one compact arena (query then target of each pair, in idx order); out_qoff / out_toff
+// receive their offsets in it.  Returns the bytes written (out_seqs may be NULL to size the arena).
+extern "C" uint64_t bsb200_pack_pairs(const uint8_t *seqs, const uint64_t *qoff, const uint32_t *qlen, const uint64_t *toff, const uint32_t *tlen,
+		const uint64_t *idx, uint64_t m, uint8_t *out_seqs, uint64_t *out_qoff, uint64_t *out_toff, int nthreads){
+	std::vector<uint64_t> pos(m + 1, 0);
+	for(uint64_t k=0;k<m;k++) pos[k + 1] = pos[k] + qlen[idx[k]] + tlen[idx[k]];
+	if(out_qoff) for(uint64_t k=0;k<m;k++) out_qoff[k] = pos[k];
+	if(out_toff) for(uint64_t k=0;k<m;k++) out_toff[k] = pos[k] + qlen[idx[k]];
+	if(!out_seqs) return pos[m];
+	if(nthreads < 1) nthreads = 1;
+	auto work = [&](int w){
+		// equal byte shares
+		const uint64_t lo_b = pos[m] / nthreads * w, hi_b = w + 1 == nthreads ? pos[m] : pos[m] / nthreads * (w + 1);
+		uint64_t k = std::lower_bound(pos.begin(), pos.end() - 1, lo_b) - pos.begin();
+		for(;k<m && pos[k]<hi_b;k++){
+			const uint64_t i = idx[k];
+			if(qlen[i]) memcpy(out_seqs + pos[k], seqs + qoff[i], qlen[i]);
+			if(tlen[i]) memcpy(out_seqs + pos[k] + qlen[i], seqs + toff[i], tlen[i]);
+		}
+	};
+	std::vector<std::thread> th;
+	for(int w=1;w<nthreads;w++) th.emplace_back(work, w);
+	work(0);
+	for(auto &t : th) t.join();
+	return pos[m];
+}
+
+// dst[dst_off[k] .. + len[k]) = src[src_off[k] .. + len[k]) for k in [0, m): 32-bit words
+extern "C" void bsb200_scatter_words(uint32_t *dst, const uint64_t *dst_off, const uint32_t *src, const uint64_t *src_off, const uint32_t *len, uint64_t m, int nthreads){
+	if(nthreads < 1) nthreads = 1;
+	auto work = [&](int w){
+		for(uint64_t k=m*w/nthreads;k<m*(w+1)/nthreads;k++) if(len[k]) memcpy(dst + dst_off[k], src + src_off[k], (size_t)len[k] * 4);
+	};
+	std::vector<std::thread> th;
+	for(int w=1;w<nthreads;w++) th.emplace_back(work, w);
+	work(0);
+	for(auto &t : th) t.join();
 }
 
 extern "C" void bsb200_batch_free(bsb200_ctx *ctx, bsb200_batch *b){

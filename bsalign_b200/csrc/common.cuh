@@ -69,9 +69,11 @@ struct CigarSink {
 // The walk emits operations end-to-start; the final cigar is their reverse (bsalign.h:3850, :1042).  Each pair
 // reserves its exact length in one dense arena so that only real cigar words travel back over PCIe.
 __device__ __forceinline__ void emit_dense(const CigarSink &cg, uint32_t *dense, uint64_t *dense_off, unsigned long long *dense_total, uint32_t *ncigar, uint32_t pair){
-	if(ncigar) ncigar[pair] = cg.n;
+	// the count that lays out the dense arena is the clamped one (a walk only outgrows its qlen + tlen + 2 scratch on pairs that
+	// are flagged anyway; cg.err then carries BSB200_ST_CIGCAP)
+	uint32_t n = (cg.buf && cg.n > cg.cap) ? cg.cap : cg.n;
+	if(ncigar) ncigar[pair] = n;
 	if(!cg.buf || !dense) return;
-	uint32_t n = cg.n < cg.cap ? cg.n : cg.cap;
 	unsigned long long off = atomicAdd(dense_total, (unsigned long long)n);
 	dense_off[pair] = off;
 	for(uint32_t i=0;i<n;i++) dense[off + i] = cg.buf[n - 1 - i];

@@ -1,9 +1,11 @@
-"""Multi-GPU sharding of a batch of independent pairs.
+"""Multi-GPU sharding of a batch of independent pairs (BASELINE.json north_star: "sharded across the
+8 GPUs of one box with NCCL over NVLink only to scatter the input batch and gather results").
 
-Pairs never interact, so there is no collective on the DP path: every rank aligns its own shard on its own
-GPU.  torch.distributed is used only as plumbing around it: the balanced partition is computed identically on
-every rank from the pair lengths, and results travel back to rank 0 with one gather of fixed-size records
-plus one gather of the dense cigar words (NCCL over NVLink when the tensors live on GPUs, gloo in the CPU tests).
+Pairs never interact, so there is no collective on the DP path.  The batch lives on rank 0: the pair lengths are broadcast,
+every rank derives the same balanced partition from them, rank 0 packs each shard's sequences into a compact arena and sends it
+to its rank's GPU, every rank aligns its shard in place (bsb200_batch_upload_dev) and sends fixed-size records plus its dense,
+pair-ordered cigar words back (bsb200_batch_fetch_dense_dev); rank 0 merges them into pair order.  NCCL when the tensors live
+on GPUs, gloo in the CPU tests (which inject the oracle as the aligner).
 """
 import numpy as np
 
@@ -30,58 +32,185 @@ def balanced_partition(work, nparts):
     return [np.sort(order[part == p]) for p in range(nparts)]
 
 
-def shard(batch, kind, bandwidth, rank, world):
-    idx = balanced_partition(pair_work(batch, kind, bandwidth), world)[rank]
-    return batch.subset(idx), idx
+# ---- the product path: one batch on rank 0, shards over NVLink, results back to rank 0 ----------------------------------------
+def plan_shards(qlen, tlen, kind, bandwidth, world):
+    """Every rank computes the same plan from the broadcast pair lengths: per rank the global pair ids of its shard (ascending) and
+    the offsets of its pairs inside the shard's compact arena (query then target of each pair, in shard order)."""
+    class _L:  # pair_work only reads lengths
+        pass
+    b = _L(); b.qlen, b.tlen = qlen, tlen
+    parts = balanced_partition(pair_work(b, kind, bandwidth), world)
+    plans = []
+    for idx in parts:
+        ql, tl = qlen[idx].astype(np.uint64), tlen[idx].astype(np.uint64)
+        pos = np.zeros(len(idx) + 1, dtype=np.uint64)
+        np.cumsum(ql + tl, out=pos[1:])
+        plans.append(dict(idx=idx, qoff=pos[:-1].copy(), toff=pos[:-1] + ql, qlen=np.ascontiguousarray(qlen[idx], dtype=np.uint32),
+                          tlen=np.ascontiguousarray(tlen[idx], dtype=np.uint32), nbytes=int(pos[-1])))
+    return plans
 
 
-def gather_to_rank0(results, status, cigars, idx, n_total, dist, device="cpu"):
-    """results (n_local,10) int32, status (n_local,) int32, cigars: list of uint32 arrays, idx: global pair ids.
-    Rank 0 returns (results[n_total,10], status[n_total], list of n_total cigar arrays); other ranks return None."""
+class ShardView:
+    """The offset / length tables of one shard (host arrays) over its compact arena; quacks like synth.PairBatch for the C ABI."""
+
+    def __init__(self, plan, seqs=None):
+        self.qoff, self.qlen, self.toff, self.tlen, self.seqs = plan["qoff"], plan["qlen"], plan["toff"], plan["tlen"], seqs
+
+    @property
+    def n(self):
+        return len(self.qlen)
+
+
+def cuda_aligner(ctx, kind, mode, bandwidth, mtx=None, gaps=(0, 0, 0, 0)):
+    """align_fn for run_sharded_device on a GPU rank: the arena that arrived over NVLink is aligned in place (bsb200_batch_upload_dev),
+    results and the dense pair-ordered cigars stay in device tensors for the way back (bsb200_batch_fetch_dense_dev)."""
     import torch
+
+    def align(arena, view):
+        n = view.n
+        dev = arena.device
+        rec = torch.zeros((n, 12), dtype=torch.int32, device=dev)
+        if n == 0:
+            return rec, torch.zeros(0, dtype=torch.int32, device=dev), {}
+        rb = ctx.upload_dev(kind, arena.data_ptr(), view, mode, bandwidth, mtx, gaps, want_cigar=True)
+        try:
+            rb.run()
+            tm = ctx.timing()
+            res = torch.empty((n, 10), dtype=torch.int32, device=dev)
+            st = torch.empty(n, dtype=torch.int32, device=dev)
+            ncg = torch.empty(n, dtype=torch.int32, device=dev)
+            total, _ = rb.fetch_dense_dev(res.data_ptr(), 0, 0, ncg.data_ptr(), st.data_ptr())
+            cig = torch.empty(max(total, 1), dtype=torch.int32, device=dev)
+            rb.fetch_dense_dev(0, cig.data_ptr(), cig.numel(), 0, 0)
+        finally:
+            rb.free()
+        rec[:, :10] = res
+        rec[:, 10] = st
+        rec[:, 11] = ncg
+        return rec, cig[:total], tm
+    return align
+
+
+def run_sharded_device(batch, kind, bandwidth, align_fn, dist, device="cpu", pinned=None, nthreads=8, timers=None):
+    """One batch on rank 0 (`batch` is None elsewhere) -> shards of equal DP cells -> every rank aligns its shard on its own device ->
+    rank 0 gets (results[n,10] int32, status[n] int32, ncigar[n] uint32, dense pair-ordered cigar words uint32).  Other ranks return None.
+
+    Collectives (NCCL over NVLink when device is a cuda device, gloo in the CPU tests): one broadcast of the pair lengths, one send per
+    rank of its compact sequence arena (rank 0 packs it in host memory and moves it to its own GPU first), one all_gather of the cigar
+    word counts, and per rank one send of its fixed-size records and one of its cigar words.  Nothing is exchanged during the DP.
+    align_fn(arena tensor on `device`, ShardView) -> (records int32 [n_r, 12] = 10 result ints, status, ncigar; cigar words as int32; timing dict)
+    timers: optional dict that receives wall-clock milliseconds of the stages on this rank."""
+    import time
+    import torch
+    from . import api
     world, rank = dist.get_world_size(), dist.get_rank()
-    ncig = np.array([len(c) for c in cigars], dtype=np.int64)
-    rec = np.concatenate([idx.astype(np.int64)[:, None], results.astype(np.int64), status.astype(np.int64)[:, None], ncig[:, None]], axis=1)
-    dense = np.concatenate(cigars).astype(np.int64) if len(cigars) and ncig.sum() else np.zeros(0, np.int64)
-    sizes = torch.tensor([rec.shape[0], dense.shape[0]], dtype=torch.int64, device=device)
-    all_sizes = [torch.zeros(2, dtype=torch.int64, device=device) for _ in range(world)]
-    dist.all_gather(all_sizes, sizes)
-    max_rec = int(max(s[0].item() for s in all_sizes))
-    max_den = int(max(s[1].item() for s in all_sizes))
-    rec_t = torch.zeros((max_rec, 13), dtype=torch.int64, device=device)
-    rec_t[:rec.shape[0]] = torch.from_numpy(rec).to(device)
-    den_t = torch.zeros(max(max_den, 1), dtype=torch.int64, device=device)
-    den_t[:dense.shape[0]] = torch.from_numpy(dense).to(device)
-    rec_all = [torch.zeros_like(rec_t) for _ in range(world)] if rank == 0 else None
-    den_all = [torch.zeros_like(den_t) for _ in range(world)] if rank == 0 else None
-    dist.gather(rec_t, rec_all, dst=0)
-    dist.gather(den_t, den_all, dst=0)
+    t0 = time.perf_counter()
+    lap = {}
+
+    def mark(name):
+        if str(device).startswith("cuda"):
+            torch.cuda.synchronize()
+        lap[name] = (time.perf_counter() - t0) * 1e3
+    # ---- pair lengths to every rank -----------------------------------------------------------------------------------------
+    hdr = torch.zeros(1, dtype=torch.int64, device=device)
+    if rank == 0:
+        hdr[0] = batch.n
+    if world > 1:
+        dist.broadcast(hdr, 0)
+    n = int(hdr.item())
+    lens = torch.zeros((2, n), dtype=torch.int32, device=device)
+    if rank == 0:
+        lens[0] = torch.from_numpy(batch.qlen.astype(np.int32)).to(device)
+        lens[1] = torch.from_numpy(batch.tlen.astype(np.int32)).to(device)
+    if world > 1:
+        dist.broadcast(lens, 0)
+    lens_h = lens.cpu().numpy()
+    qlen, tlen = lens_h[0].astype(np.uint32), lens_h[1].astype(np.uint32)
+    plans = plan_shards(qlen, tlen, kind, bandwidth, world)
+    mine = plans[rank]
+    mark("plan")
+    # ---- scatter: rank 0 packs every shard's compact arena, moves it to its GPU and sends it on --------------------------------
+    sends, keep = [], []
+    arena = None
+    scatter_bytes = 0
+    if rank == 0:
+        for r in list(range(1, world)) + [0]:
+            p = plans[r]
+            host = None
+            if pinned is not None:
+                host = pinned(max(p["nbytes"], 1))
+            pb, nb = api.pack_pairs(batch, p["idx"], out_seqs=host, nthreads=nthreads)
+            t = torch.from_numpy(pb.seqs[:max(nb, 1)]).to(device, non_blocking=True)
+            keep.append((pb, t))
+            if r == 0:
+                arena = t
+            else:
+                sends.append(dist.isend(t, r))
+                scatter_bytes += nb
+    else:
+        arena = torch.empty(max(mine["nbytes"], 1), dtype=torch.uint8, device=device)
+        dist.recv(arena, 0)
+    mark("scatter_issued")
+    # ---- this rank's shard ------------------------------------------------------------------------------------------------------
+    if str(device).startswith("cuda"):
+        torch.cuda.current_stream().synchronize()
+    rec, cig, tm = align_fn(arena, ShardView(mine, None))
+    for w in sends:
+        w.wait()
+    mark("aligned")
+    # ---- gather ---------------------------------------------------------------------------------------------------------------------
+    cnt = torch.tensor([cig.numel()], dtype=torch.int64, device=device)
+    counts = [torch.zeros(1, dtype=torch.int64, device=device) for _ in range(world)]
+    if world > 1:
+        dist.all_gather(counts, cnt)
+    else:
+        counts = [cnt]
+    counts = [int(c.item()) for c in counts]
     if rank != 0:
+        dist.send(rec.contiguous(), 0)
+        if counts[rank]:
+            dist.send(cig.contiguous(), 0)
+        mark("gathered")
+        if timers is not None:
+            timers.update(lap); timers["kernel"] = tm
         return None
-    out_res = np.zeros((n_total, 10), dtype=np.int32)
-    out_st = np.zeros(n_total, dtype=np.int32)
-    out_cg = [None] * n_total
+    recs, cigs = [rec], [cig]
+    gather_bytes = 0
+    for r in range(1, world):
+        rr = torch.empty((len(plans[r]["idx"]), 12), dtype=torch.int32, device=device)
+        dist.recv(rr, r)
+        cc = torch.empty(counts[r], dtype=torch.int32, device=device)
+        if counts[r]:
+            dist.recv(cc, r)
+        recs.append(rr); cigs.append(cc)
+        gather_bytes += rr.numel() * 4 + cc.numel() * 4
+    mark("gathered")
+    results = np.zeros((n, 10), dtype=np.int32)
+    status = np.zeros(n, dtype=np.int32)
+    ncigar = np.zeros(n, dtype=np.uint32)
+    recs_h = [r_.cpu().numpy() for r_ in recs]
     for r in range(world):
-        nr = int(all_sizes[r][0].item())
-        rr = rec_all[r][:nr].cpu().numpy()
-        dd = den_all[r].cpu().numpy()
-        off = 0
-        for row in rr:
-            g = int(row[0])
-            out_res[g] = row[1:11]
-            out_st[g] = row[11]
-            k = int(row[12])
-            out_cg[g] = dd[off:off + k].astype(np.uint32)
-            off += k
-    return out_res, out_st, out_cg
-
-
-def run_sharded(batch, kind, bandwidth, align_fn, dist, device="cpu"):
-    """align_fn(sub_batch) -> (results, status, cigars).  In production align_fn is Context.epi8_batch / edit_batch
-    on this rank's GPU; the CPU tests inject the oracle."""
-    sub, idx = shard(batch, kind, bandwidth, dist.get_rank(), dist.get_world_size())
-    res, st, cg = align_fn(sub)
-    return gather_to_rank0(res, st, cg, idx, batch.n, dist, device)
+        idx = plans[r]["idx"]
+        results[idx] = recs_h[r][:, :10]
+        status[idx] = recs_h[r][:, 10]
+        ncigar[idx] = recs_h[r][:, 11].astype(np.uint32)
+    status[(qlen == 0) | (tlen == 0)] |= 16   # BSB200_ST_EMPTY (a host-side flag of the C ABI)
+    goff = np.zeros(n + 1, dtype=np.uint64)
+    np.cumsum(ncigar, out=goff[1:])
+    dense = np.zeros(max(int(goff[-1]), 1), dtype=np.uint32)
+    for r in range(world):
+        idx = plans[r]["idx"]
+        ln = ncigar[idx]
+        soff = np.zeros(len(idx) + 1, dtype=np.uint64)
+        np.cumsum(ln, out=soff[1:])
+        src = cigs[r].cpu().numpy().view(np.uint32)
+        if len(idx) and int(soff[-1]):
+            api.scatter_words(dense, goff[idx], src, soff[:-1], ln, nthreads=nthreads)
+    mark("assembled")
+    if timers is not None:
+        timers.update(lap); timers["kernel"] = tm
+        timers["scatter_bytes"] = scatter_bytes; timers["gather_bytes"] = gather_bytes
+    return results, status, ncigar, dense[:int(goff[-1])], goff
 
 
 # ---- POA sweep jobs (SURVEY.md section 8e: MSA jobs never interact either) -------------------------------------------------

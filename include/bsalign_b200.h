@@ -65,6 +65,8 @@ typedef struct {
 bsb200_ctx *bsb200_create(int device, uint64_t trace_budget_bytes);
 void bsb200_destroy(bsb200_ctx *ctx);
 const char *bsb200_last_error(bsb200_ctx *ctx);   /* "" when the last call succeeded */
+void bsb200_trim(bsb200_ctx *ctx);                /* release the traceback arena and all cached buffers (they are re-allocated on demand) */
+bsb200_ctx *bsb200_default_context(void);         /* one shared context on device 0, created on first use (used by the compat headers) */
 int bsb200_device_count(void);
 const char *bsb200_version(void);
 void bsb200_get_timing(bsb200_ctx *ctx, bsb200_timing_t *out);
@@ -114,6 +116,26 @@ int bsb200_batch_fetch(bsb200_ctx *ctx, bsb200_batch *b, bsb200_result_t *result
 int bsb200_batch_fetch_dense(bsb200_ctx *ctx, bsb200_batch *b, bsb200_result_t *results,
 		uint32_t *cigars, uint64_t cigar_cap_words, uint64_t *total_words, uint32_t *ncigar, int32_t *status);
 void bsb200_batch_free(bsb200_ctx *ctx, bsb200_batch *b);
+
+/* ---- multi-GPU split (one process per GPU; the batch lives on rank 0) ------------------------------------------
+ * The reference has no notion of devices: banded_striped_epi8_seqalign_pairwise (bsalign.h:3854) is called pair by pair, and pairs
+ * never interact.  A batch is therefore cut into shards of equal DP cells, each shard's compact arena travels from rank 0's GPU to
+ * its rank's GPU (NCCL over NVLink, bsalign_b200/shard.py), is aligned there in place and the results travel back the same way.
+ * These entry points are that path's ends on a rank: the sequence arena / the results are DEVICE memory of the caller, the small
+ * offset and length tables stay host arrays (every rank derives them from the broadcast pair lengths). */
+bsb200_batch *bsb200_batch_upload_dev(bsb200_ctx *ctx, int kind, uint64_t n, const uint8_t *d_seqs /* device; kept alive by the caller until batch_free */,
+		const uint64_t *qoff, const uint32_t *qlen, const uint64_t *toff, const uint32_t *tlen,
+		int mode, uint32_t bandwidth, const int8_t matrix[16], int8_t gapo1, int8_t gape1, int8_t gapo2, int8_t gape2,
+		int want_cigar);
+/* d_results n x 10 int32, d_ncigar n, d_status n (kernel flags only; BSB200_ST_EMPTY is added by the host-side fetches), d_cigars dense
+ * and pair-ordered like bsb200_batch_fetch_dense; all DEVICE pointers, any may be NULL.  *total_words always receives the word count. */
+int bsb200_batch_fetch_dense_dev(bsb200_ctx *ctx, bsb200_batch *b, int32_t *d_results, uint32_t *d_cigars, uint64_t cigar_cap_words,
+		uint64_t *total_words, uint32_t *d_ncigar, int32_t *d_status);
+/* host helpers of the split: pairs idx[0..m) copied into one compact arena (query, then target, in idx order; offsets to out_qoff /
+ * out_toff; out_seqs NULL: only size it), and the pair-ordered merge of the shards' dense cigars */
+uint64_t bsb200_pack_pairs(const uint8_t *seqs, const uint64_t *qoff, const uint32_t *qlen, const uint64_t *toff, const uint32_t *tlen,
+		const uint64_t *idx, uint64_t m, uint8_t *out_seqs, uint64_t *out_qoff, uint64_t *out_toff, int nthreads);
+void bsb200_scatter_words(uint32_t *dst, const uint64_t *dst_off, const uint32_t *src, const uint64_t *src_off, const uint32_t *len, uint64_t m, int nthreads);
 
 /* ---- POA read-vs-graph banded DP sweep: replaces align_rd_bspoacore (bspoa.h:2515-2618) -------------------- */
 /*

@@ -29,17 +29,34 @@
 #error "include the reference's bsalign.h before bsalign_b200_compat.h"
 #endif
 
-static bsb200_ctx *bsalign_b200_default_ctx(void){
-	static bsb200_ctx *ctx = NULL;
+/* one context for the whole program (the library owns it, so every translation unit sees the same one) */
+static inline bsb200_ctx *bsalign_b200_default_ctx(void){
+	bsb200_ctx *ctx = bsb200_default_context();
 	if(ctx == NULL){
-		ctx = bsb200_create(0, 0);
-		if(ctx == NULL){
-			fflush(stdout); fprintf(stderr, " -- bsalign_b200: no CUDA device, and there is no CPU fallback in %s -- %s:%d --\n", __FUNCTION__, __FILE__, __LINE__); fflush(stderr);
-			abort();
-		}
+		fflush(stdout); fprintf(stderr, " -- bsalign_b200: no CUDA device, and there is no CPU fallback in %s -- %s:%d --\n", __FUNCTION__, __FILE__, __LINE__); fflush(stderr);
+		abort();
 	}
 	return ctx;
 }
+
+/*
+ * Per-pair status of the last call (bsalign_b200.h: BSB200_ST_*).  The reference has no error codes; on the inputs the library
+ * flags it either reads outside its traceback band / never leaves its traceback loop (RANGE, LOOP: a global alignment forced
+ * through a band that cannot hold it, bsalign.h:3199-3202, :3798-3814) or computes on stale scratch words (REFBUG, bsalign.h:704-713).
+ * A flagged result must not look valid to the caller: RANGE and LOOP end the program like the reference's own programmer errors
+ * (message + abort()), REFBUG is reported on stderr and the result (which follows the intended algorithm) is returned.
+ * Define BSALIGN_B200_ON_STATUS(st, func) before including this header to handle the flags yourself.
+ */
+static int bsalign_b200_last_status = 0;
+#ifndef BSALIGN_B200_ON_STATUS
+#define BSALIGN_B200_ON_STATUS(st, func) do { \
+	if((st) & (BSB200_ST_RANGE | BSB200_ST_LOOP)){ \
+		fflush(stdout); fprintf(stderr, " -- bsalign_b200: status %d in %s: the reference's traceback leaves its band / never terminates on this pair (bsalign.h:3199, :3798) -- %s:%d --\n", (int)(st), func, __FILE__, __LINE__); fflush(stderr); \
+		abort(); \
+	} else if((st) & BSB200_ST_REFBUG){ \
+		fprintf(stderr, " -- bsalign_b200: status %d in %s: the reference shifts this edit band through stale scratch words (bsalign.h:704-713); result follows the intended algorithm --\n", (int)(st), func); \
+	} } while(0)
+#endif
 
 static inline void bsalign_b200_take_cigars(u4v *cigars, int mode, const uint32_t *buf, uint32_t n){
 	uint32_t i;
@@ -61,6 +78,8 @@ static inline seqalign_result_t b200_banded_striped_epi8_seqalign_pairwise(u1i *
 		fflush(stdout); fprintf(stderr, " -- bsalign_b200: %s in %s -- %s:%d --\n", bsb200_last_error(bsalign_b200_default_ctx()), __FUNCTION__, __FILE__, __LINE__); fflush(stderr);
 		abort();
 	}
+	bsalign_b200_last_status = st;
+	if(st & ~BSB200_ST_EMPTY) BSALIGN_B200_ON_STATUS(st, __FUNCTION__);
 	rs.score = r.score; rs.qb = r.qb; rs.qe = r.qe; rs.tb = r.tb; rs.te = r.te;
 	rs.mat = r.mat; rs.mis = r.mis; rs.ins = r.ins; rs.del = r.del; rs.aln = r.aln;
 	bsalign_b200_take_cigars(cigars, mode, buf, n);
@@ -80,6 +99,8 @@ static inline seqalign_result_t b200_striped_seqedit_pairwise(u1i *qseq, u4i qle
 		fflush(stdout); fprintf(stderr, " -- bsalign_b200: %s in %s -- %s:%d --\n", bsb200_last_error(bsalign_b200_default_ctx()), __FUNCTION__, __FILE__, __LINE__); fflush(stderr);
 		abort();
 	}
+	bsalign_b200_last_status = st;
+	if(st & ~BSB200_ST_EMPTY) BSALIGN_B200_ON_STATUS(st, __FUNCTION__);
 	rs.score = r.score; rs.qb = r.qb; rs.qe = r.qe; rs.tb = r.tb; rs.te = r.te;
 	rs.mat = r.mat; rs.mis = r.mis; rs.ins = r.ins; rs.del = r.del; rs.aln = r.aln;
 	bsalign_b200_take_cigars(cigars, mode, buf, n);

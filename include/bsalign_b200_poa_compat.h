@@ -306,12 +306,9 @@ static inline void b200_end_bspoa_batch(bsb200_ctx *ctx, BSPOA **gs, u4i n){
 }
 
 #ifdef BSALIGN_B200_OVERRIDE
-static bsb200_ctx *bsalign_b200_poa_default_ctx(void){
-	static bsb200_ctx *ctx = NULL;
-	if(ctx == NULL){
-		ctx = bsb200_create(0, 0);
-		if(ctx == NULL){ fflush(stdout); fprintf(stderr, " -- bsalign_b200: no CUDA device, and there is no CPU fallback in %s -- %s:%d --\n", __FUNCTION__, __FILE__, __LINE__); fflush(stderr); abort(); }
-	}
+static inline bsb200_ctx *bsalign_b200_poa_default_ctx(void){
+	bsb200_ctx *ctx = bsb200_default_context();
+	if(ctx == NULL){ fflush(stdout); fprintf(stderr, " -- bsalign_b200: no CUDA device, and there is no CPU fallback in %s -- %s:%d --\n", __FUNCTION__, __FILE__, __LINE__); fflush(stderr); abort(); }
 	return ctx;
 }
 static inline void b200_end_bspoa(BSPOA *g){ b200_end_bspoa_batch(bsalign_b200_poa_default_ctx(), &g, 1); }

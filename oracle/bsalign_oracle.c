@@ -8,7 +8,7 @@
  * p in [j*W, (j+1)*W), W = bw/16).  Every int8 operation saturates exactly where the SSE code
  * saturates (adds/subs_epi8), so the output is bit-identical to the reference's SSE4.2 build.
  *
- * Parity status: PINNED.  tests/test_oracle_vs_ref.py compares every function here against the
+ * Parity status: PINNED.  tests/test_oracle.py (epi8, edit) and tests/test_poa.py (POA sweep, walk) compare every function here against the
  * unmodified reference compiled into oracle/_ref/libbsref.so (see oracle/ref_harness.c), and
  * tests/golden/ holds vectors generated from that build (tests/golden/make_golden.py) plus the README
  * example (README.md:36-42).

@@ -1,5 +1,6 @@
-"""world_size-2 gloo test of the multi-GPU host logic (partition + gather) on CPU.  The aligner injected into
-run_sharded is the oracle (allowed: this is a test); on a GPU box bench.py injects the CUDA path instead."""
+"""world_size-2 gloo test of the multi-GPU path (plan, compact arenas, scatter, gather, pair-ordered merge) on CPU.  The aligner
+injected into run_sharded_device is the oracle (allowed: this is a test); on GPUs bench.py and tests/test_gpu_parity.py inject
+shard.cuda_aligner, the CUDA path."""
 import os
 import socket
 
@@ -22,21 +23,49 @@ def test_balanced_partition_is_balanced_and_complete():
         assert tot.max() / tot.mean() < 1.01
 
 
+def _oracle_aligner(kind, mode, bw, mtx, gaps):
+    """Stands in for shard.cuda_aligner on a box without GPUs: same contract (arena tensor + ShardView in, records + dense cigars out)."""
+    import torch
+
+    def align(arena, view):
+        sub = synth.PairBatch(arena.numpy(), view.qoff, view.qlen, view.toff, view.tlen)
+        r, c, _ = ck.oracle_batch(kind, sub, mode, bw, mtx, gaps)
+        rec = np.zeros((sub.n, 12), dtype=np.int32)
+        rec[:, :10] = r
+        rec[:, 11] = [len(x) for x in c]
+        dense = np.concatenate(c).astype(np.uint32) if sub.n and rec[:, 11].sum() else np.zeros(0, np.uint32)
+        return torch.from_numpy(rec), torch.from_numpy(dense.view(np.int32).copy()), {}
+    return align
+
+
 def _worker(rank, world, port, q):
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
     dist.init_process_group("gloo", rank=rank, world_size=world)
-    batch = synth.make_pairs(60, 150, seed=11)
     mtx = synth.score_matrix(2, -6)
-
-    def align(sub):
-        r, c, _ = ck.oracle_batch("epi8", sub, 1, 64, mtx, (-3, -2, 0, 0))
-        return r, np.zeros(sub.n, np.int32), c
-    out = shard.run_sharded(batch, "epi8", 64, align, dist)
+    # ragged lengths, one empty pair: rank 0 owns the batch, the others only learn the lengths
+    rng = np.random.default_rng(3)
+    pairs = [(rng.integers(0, 4, int(rng.integers(1, 300))).astype(np.uint8), rng.integers(0, 4, int(rng.integers(1, 300))).astype(np.uint8)) for _ in range(59)]
+    pairs.insert(7, (np.zeros(0, np.uint8), np.array([1, 2], np.uint8)))
+    batch = synth.PairBatch.from_lists(pairs) if rank == 0 else None
+    timers = {}
+    out = shard.run_sharded_device(batch, "epi8", 64, _oracle_aligner("epi8", 1, 64, mtx, (-3, -2, 0, 0)), dist, device="cpu", nthreads=2, timers=timers)
     if rank == 0:
-        exp_r, exp_c, _ = ck.oracle_batch("epi8", batch, 1, 64, mtx, (-3, -2, 0, 0))
-        ok = np.array_equal(out[0], exp_r) and all(np.array_equal(a, b) for a, b in zip(out[2], exp_c))
+        res, st, ncg, dense, goff = out
+        valid = np.array([len(a) > 0 and len(b) > 0 for a, b in pairs])
+        vb = synth.PairBatch.from_lists([p for p, v in zip(pairs, valid) if v])
+        exp_r, exp_c, _ = ck.oracle_batch("epi8", vb, 1, 64, mtx, (-3, -2, 0, 0))
+        ok = st[7] == 16 and not res[7].any() and int(ncg[7]) == 0
+        k = 0
+        for i in range(len(pairs)):
+            if not valid[i]:
+                continue
+            ok = ok and np.array_equal(res[i], exp_r[k]) and np.array_equal(dense[int(goff[i]):int(goff[i + 1])], exp_c[k]) and st[i] == 0
+            k += 1
+        ok = ok and timers["scatter_bytes"] > 0 and timers["gather_bytes"] > 0
         q.put(bool(ok))
+    else:
+        assert out is None
     dist.destroy_process_group()
 
 
