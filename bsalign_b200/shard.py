@@ -185,27 +185,36 @@ def run_sharded_device(batch, kind, bandwidth, align_fn, dist, device="cpu", pin
         recs.append(rr); cigs.append(cc)
         gather_bytes += rr.numel() * 4 + cc.numel() * 4
     mark("gathered")
-    results = np.zeros((n, 10), dtype=np.int32)
-    status = np.zeros(n, dtype=np.int32)
-    ncigar = np.zeros(n, dtype=np.uint32)
-    recs_h = [r_.cpu().numpy() for r_ in recs]
-    for r in range(world):
-        idx = plans[r]["idx"]
-        results[idx] = recs_h[r][:, :10]
-        status[idx] = recs_h[r][:, 10]
-        ncigar[idx] = recs_h[r][:, 11].astype(np.uint32)
+    # ---- merge into pair order on rank 0's device (index arithmetic on tensors), then one copy per array to the host -------------
+    idx_all = torch.from_numpy(np.concatenate([p["idx"] for p in plans]).astype(np.int64)).to(device)
+    rec_all = torch.cat(recs, 0)
+    rec_g = torch.empty_like(rec_all)
+    rec_g[idx_all] = rec_all                                  # record of pair i at row i
+    ncg_g = rec_g[:, 11].to(torch.int64)
+    goff_d = torch.zeros(n + 1, dtype=torch.int64, device=device)
+    torch.cumsum(ncg_g, 0, out=goff_d[1:])
+    total = int(goff_d[-1].item())
+    dense_d = torch.empty(max(total, 1), dtype=torch.int32, device=device)
+    if total:
+        cig_all = torch.cat(cigs, 0)
+        ln = rec_all[:, 11].to(torch.int64)                   # words per pair, in shard order (= order of cig_all)
+        soff = torch.cumsum(ln, 0) - ln
+        shift = goff_d[:-1][idx_all] - soff                   # where a pair's words move: destination - source offset
+        dst = torch.repeat_interleave(shift, ln) + torch.arange(total, dtype=torch.int64, device=device)
+        dense_d[dst] = cig_all
+    if pinned is not None and str(device).startswith("cuda"):
+        rec_h = torch.from_numpy(pinned(rec_g.numel() * 4)[:rec_g.numel() * 4].view(np.int32)).view(n, 12)
+        den_h = torch.from_numpy(pinned(max(total, 1) * 4)[:max(total, 1) * 4].view(np.int32))
+        rec_h.copy_(rec_g, non_blocking=True); den_h.copy_(dense_d, non_blocking=True)
+        torch.cuda.synchronize()
+        rec_np, dense = rec_h.numpy(), den_h.numpy().view(np.uint32)
+    else:
+        rec_np, dense = rec_g.cpu().numpy(), dense_d.cpu().numpy().view(np.uint32)
+    results = np.ascontiguousarray(rec_np[:, :10])
+    status = np.ascontiguousarray(rec_np[:, 10])
+    ncigar = np.ascontiguousarray(rec_np[:, 11]).astype(np.uint32)
     status[(qlen == 0) | (tlen == 0)] |= 16   # BSB200_ST_EMPTY (a host-side flag of the C ABI)
-    goff = np.zeros(n + 1, dtype=np.uint64)
-    np.cumsum(ncigar, out=goff[1:])
-    dense = np.zeros(max(int(goff[-1]), 1), dtype=np.uint32)
-    for r in range(world):
-        idx = plans[r]["idx"]
-        ln = ncigar[idx]
-        soff = np.zeros(len(idx) + 1, dtype=np.uint64)
-        np.cumsum(ln, out=soff[1:])
-        src = cigs[r].cpu().numpy().view(np.uint32)
-        if len(idx) and int(soff[-1]):
-            api.scatter_words(dense, goff[idx], src, soff[:-1], ln, nthreads=nthreads)
+    goff = goff_d.cpu().numpy().astype(np.uint64)
     mark("assembled")
     if timers is not None:
         timers.update(lap); timers["kernel"] = tm
