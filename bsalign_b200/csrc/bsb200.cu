@@ -64,6 +64,7 @@ struct bsb200_ctx {
 	int device = 0;
 	int num_sms = 0;
 	size_t smem_optin = 0;
+	size_t total_mem = 0;
 	cudaStream_t stream = nullptr;
 	cudaStream_t stream_bt = nullptr;   // traceback kernels run here, concurrently with the next wave's forward kernel
 	cudaEvent_t ev[8] = {};
@@ -91,6 +92,7 @@ struct bsb200_batch {
 	int8_t mtx[16] = {}; int8_t go1 = 0, ge1 = 0, go2 = 0, ge2 = 0;
 	int pw = 0; int want_cigar = 1;
 	uint32_t max_bw = 16, max_q64 = 64, max_qlen = 0;
+	int wave_split = 0;   // > 0: the batch takes the wavefront forward kernel with that many sub-blocks per lane (epi8_wave.cuh)
 	std::vector<uint8_t> empty;
 	uint64_t cells = 0, trace_bytes = 0, cig_words = 0, max_wave_bytes = 0;
 	std::vector<Wave> waves;
@@ -134,6 +136,7 @@ extern "C" bsb200_ctx *bsb200_create(int device, uint64_t trace_budget_bytes){
 	cudaGetDeviceProperties(&prop, device);
 	ctx->num_sms = prop.multiProcessorCount;
 	ctx->smem_optin = prop.sharedMemPerBlockOptin;
+	ctx->total_mem = prop.totalGlobalMem;
 	cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking);
 	{ int lo = 0, hi = 0; cudaDeviceGetStreamPriorityRange(&lo, &hi); cudaStreamCreateWithPriority(&ctx->stream_bt, cudaStreamNonBlocking, hi); }
 	for(auto &e : ctx->ev) cudaEventCreate(&e);
@@ -192,6 +195,44 @@ extern "C" uint32_t bsb200_edit_bandwidth(uint32_t qlen, uint32_t tlen, int mode
 }
 
 void bsb200_batch_free(bsb200_ctx *ctx, bsb200_batch *b);
+
+// shared memory of one pair's group in the wavefront kernel: u, e and selector images + the scratch words of its stages
+static size_t wave_group_smem(uint32_t max_bw, int split){
+	const size_t img = epi8_image_bytes(max_bw / 16);
+	const size_t scratch = std::max<size_t>(320, (size_t)(2 + 2 * kLanes * split) * 4);
+	return (img * 3 + scratch + 127) / 128 * 128 + 32;
+}
+
+// Does the batch take the wavefront kernel, and with how many sub-blocks per lane?  Full bands (the band never moves), affine gaps
+// in the ranges the kernel's unclamped adds need, scores inside +-63.  The split: the smallest one that gives an SM three warps per
+// scheduler with the pairs that are in flight at once (bounded by the pairs, by shared memory and by the traceback store), among those
+// that leave no sub-block of the narrowest band empty.
+static int plan_wave(const bsb200_ctx *ctx, const bsb200_batch *b, uint32_t min_bw, uint64_t nact){
+	if(b->kind != 0 || b->pw != 1 || getenv("BSB200_NOWAVE") || getenv("BSB200_NOFAST") || getenv("BSB200_NOFULL") || nact == 0) return 0;
+	if(!(b->bandwidth == 0 || (b->bandwidth + 15) / 16 * 16 >= b->max_qlen)) return 0;
+	for(int k=0;k<16;k++) if(b->mtx[k] > 63 || b->mtx[k] < -63) return 0;
+	if(b->ge1 > -1 || (int)b->go1 + b->ge1 < -64 || (int)b->go1 + b->ge1 > -1) return 0;
+	const uint64_t per_pair = ((uint64_t)epi8_row_bytes(b->max_bw / 16, 1) + kMetaInts * 4) * ((uint64_t)b->max_qlen + 64);
+	const uint64_t by_mem = std::max<uint64_t>(1, (uint64_t)(ctx->total_mem * 0.85) / std::max<uint64_t>(per_pair, 1));
+	int best = 0;
+	for(int split : {1, 2, 4}){
+		if(!epi8_wave_split_ok(min_bw / 16, (uint32_t)split)) break;
+		if(split > 1 && !epi8_use_anchors(b->max_bw / 16)) break;   // a traceback lookup must not cross sub-blocks: needs the sub-lane anchors
+		const size_t gsm = wave_group_smem(b->max_bw, split);
+		const size_t per_warp = gsm * (size_t)(4 / split);
+		if(per_warp > ctx->smem_optin) continue;
+		const uint64_t warps_by_smem = std::min<uint64_t>(64, (ctx->smem_optin + 1024) / (per_warp + 256)) * ctx->num_sms;
+		const uint64_t in_flight = std::min<uint64_t>(std::min<uint64_t>(nact, by_mem), warps_by_smem * (4 / split));
+		const double warps_per_sm = (double)in_flight * split / 4.0 / ctx->num_sms;
+		best = split;
+		if(warps_per_sm >= 12.0) break;
+	}
+	if(const char *ev = getenv("BSB200_WAVE_SPLIT")){   // tests / experiments: force a split (when the batch allows it)
+		const int f = atoi(ev);
+		if((f == 1 || f == 2 || f == 4) && best && (f == 1 || epi8_use_anchors(b->max_bw / 16)) && epi8_wave_split_ok(min_bw / 16, (uint32_t)f) && wave_group_smem(b->max_bw, f) * (size_t)(4 / f) <= ctx->smem_optin) best = f;
+	}
+	return best;
+}
 
 // d_seqs_ext: the sequence arena is already in this device's memory (it arrived over NVLink: bsalign_b200/shard.py); the batch
 // uses it in place and the caller keeps it alive until bsb200_batch_free.  Offsets and lengths are host arrays in both cases.
@@ -256,6 +297,19 @@ static bsb200_batch *upload_impl(bsb200_ctx *ctx, int kind, uint64_t n, const ui
 	// ---- plan: per-pair band, trace footprint, heaviest-first order, waves ---------------------------
 	std::vector<uint64_t> work(kind == 0 ? n : 0), tbytes(kind == 0 ? n : 0);   // epi8 only (a million short edit pairs: every O(n) array counts)
 	b->max_bw = kind == 0 ? 16 : 64;
+	uint32_t wave_slack = 0;
+	if(kind == 0){
+		// the wavefront kernel's skewed trace needs extra slots per pair, how many depends on the split: decide it before sizing
+		uint32_t min_bw = 0xffffffffu; uint64_t nact0 = 0;
+		for(uint64_t i=0;i<n;i++){
+			if(qlen[i] == 0 || tlen[i] == 0) continue;
+			const uint32_t bw = bsb200_epi8_bandwidth(qlen[i], bandwidth);
+			min_bw = std::min(min_bw, bw); b->max_bw = std::max(b->max_bw, bw); b->max_qlen = std::max(b->max_qlen, qlen[i]);
+			nact0++;
+		}
+		b->wave_split = plan_wave(ctx, b, min_bw, nact0);
+		wave_slack = b->wave_split ? epi8_wave_slack((uint32_t)b->wave_split) : 0;
+	}
 	b->empty.assign(n, 0);
 	b->order.clear(); b->order.reserve(n);
 	for(uint64_t i=0;i<n;i++){
@@ -264,7 +318,7 @@ static bsb200_batch *upload_impl(bsb200_ctx *ctx, int kind, uint64_t n, const ui
 		if(kind == 0){
 			bw = bsb200_epi8_bandwidth(qlen[i], bandwidth);
 			// upper bound: with sub-lane anchors, and with the extra slots of the wavefront kernel's skewed layout
-			tbytes[i] = ((uint64_t)epi8_row_bytes(bw / 16, b->pw) + kMetaInts * 4) * ((uint64_t)tlen[i] + 1 + kWaveSlack);
+			tbytes[i] = ((uint64_t)epi8_row_bytes(bw / 16, b->pw) + kMetaInts * 4) * ((uint64_t)tlen[i] + 1 + wave_slack);
 			tbytes[i] = (tbytes[i] + 15) / 16 * 16;
 			b->cells += (uint64_t)std::min<uint32_t>(bw, (qlen[i] + 15) / 16 * 16) * tlen[i];
 			b->trace_bytes += ((uint64_t)bw * (b->pw + 1) + 84) * tlen[i];
@@ -496,26 +550,6 @@ static int launch_epi8_forward(bsb200_ctx *ctx, Epi8Args a, uint32_t npairs, boo
 	// by ALU throughput: they take the LAT instantiation (short F chain, loads of the next chunk in flight; affine gaps only)
 	bool lat = false;
 	if constexpr (FAST && PW == 1){
-		// full-band affine batches with scores inside +-63: the single-pass wavefront kernel (epi8_wave.cuh), then the two-pass
-		// kernel below over the pairs it flagged (normally none: that launch only reads the status words)
-		bool wave = full && !getenv("BSB200_NOWAVE");
-		for(int k=0;k<16;k++) if(a.mtx[k] > 63 || a.mtx[k] < -63) wave = false;
-		if(a.ge1 > -1 || (int)a.go1 + a.ge1 < -64 || (int)a.go1 + a.ge1 > -1) wave = false;   // the kernel's unclamped adds need these
-		if(wave && (best_gpw == 4 || ANCH)){
-			a.redo = 0;
-			a.force_redo = getenv("BSB200_WAVE_REDO") ? 1 : 0;
-			int rc;
-			if(best_gpw < 4){
-				if constexpr (ANCH) rc = go(epi8_wave_kernel<true, true>); else rc = -1;
-			} else if(getenv("BSB200_WAVE_VAR") && atoi(getenv("BSB200_WAVE_VAR")) == 1) rc = go(epi8_wave_kernel<ANCH, false, 1>);   // experiments
-			else rc = go(epi8_wave_kernel<ANCH, false>);
-			if(rc) return rc;
-			ctx->timing.forward_launches++;
-			CK(cudaMemsetAsync(a.counter, 0, 16, ctx->stream));
-			a.redo = 1;
-		}
-	}
-	if constexpr (FAST && PW == 1){
 		const uint64_t seated = std::min<uint64_t>(npairs, (uint64_t)best_groups * ctx->num_sms);
 		const uint64_t warps_per_sm = (seated + (uint64_t)best_gpw * ctx->num_sms - 1) / ((uint64_t)best_gpw * ctx->num_sms);
 		lat = warps_per_sm <= 8;
@@ -536,6 +570,45 @@ static int launch_epi8_forward(bsb200_ctx *ctx, Epi8Args a, uint32_t npairs, boo
 		if(lat) return go(epi8_forward_kernel<PW, FAST, ANCH, false, true>);
 	}
 	return go(epi8_forward_kernel<PW, FAST, ANCH, false>);
+}
+
+// the wavefront kernel: CTAs of whole warps (4 / split pairs each), as many pairs per SM as the shared memory seats
+template<bool ANCH, int SPLIT>
+static int launch_epi8_wave_t(bsb200_ctx *ctx, Epi8Args a, uint32_t npairs){
+	const size_t per_warp = (size_t)a.group_smem * (4 / SPLIT);
+	int threads = 0; uint32_t best_pairs = 0;
+	for(int th : {128, 64, 32}){
+		const size_t per_cta = per_warp * (th / 32);
+		if(per_cta > ctx->smem_optin) continue;
+		const uint32_t ctas = (uint32_t)std::min<size_t>((ctx->smem_optin + 1024) / (per_cta + 1024), 2048 / th);
+		const uint32_t pairs_sm = std::min<uint32_t>(ctas, 32) * (th / 32) * (4 / SPLIT);
+		if(pairs_sm > best_pairs){ best_pairs = pairs_sm; threads = th; }
+	}
+	if(!threads){ ctx->err = "band too wide for the shared-memory row buffers"; return -1; }
+	const size_t smem = per_warp * (threads / 32);
+	auto kernel = epi8_wave_kernel<ANCH, SPLIT>;
+	CK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+	int per_sm = 1;
+	CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, threads, smem));
+	if(per_sm < 1) per_sm = 1;
+	const uint32_t groups = (threads / 32) * (4 / SPLIT);
+	uint32_t grid = (npairs + groups - 1) / groups;
+	if(grid > (uint32_t)ctx->num_sms) grid = (grid + ctx->num_sms - 1) / ctx->num_sms * ctx->num_sms;
+	grid = std::min<uint32_t>(grid, (uint32_t)(ctx->num_sms * per_sm));
+	if(grid == 0) grid = 1;
+	kernel<<<grid, threads, smem, ctx->stream>>>(a);
+	CK(cudaGetLastError());
+	return 0;
+}
+
+static int launch_epi8_wave(bsb200_ctx *ctx, const Epi8Args &a, uint32_t npairs, bool anch, int split){
+	if(anch){
+		if(split == 4) return launch_epi8_wave_t<true, 4>(ctx, a, npairs);
+		if(split == 2) return launch_epi8_wave_t<true, 2>(ctx, a, npairs);
+		return launch_epi8_wave_t<true, 1>(ctx, a, npairs);
+	}
+	if(split != 1){ ctx->err = "internal: split wavefront kernel without anchors"; return -1; }
+	return launch_epi8_wave_t<false, 1>(ctx, a, npairs);
 }
 
 template<bool FAST, bool ANCH>
@@ -627,6 +700,18 @@ extern "C" int bsb200_batch_run(bsb200_ctx *ctx, bsb200_batch *b){
 			const bool anch = epi8_use_anchors(b->max_bw / 16);
 			a.gpw = 4;
 			int rc;
+			if(b->wave_split){
+				// the single-pass wavefront kernel (epi8_wave.cuh), then the two-pass kernel below over the pairs it flagged
+				// (normally none: that launch only reads the status words)
+				Epi8Args wa = a;
+				wa.group_smem = (uint32_t)wave_group_smem(b->max_bw, b->wave_split);
+				wa.force_redo = getenv("BSB200_WAVE_REDO") ? 1 : 0;
+				rc = launch_epi8_wave(ctx, wa, np, anch, b->wave_split);
+				if(rc) return rc;
+				ctx->timing.forward_launches++;
+				CK(cudaMemsetAsync(ctx->counter.p, 0, 16, st));
+				a.redo = 1;
+			}
 			// every band covers its whole query: bandwidth 0, or a bandwidth (rounded up to 16 by the kernel) no shorter than the longest query
 			const bool full = (b->bandwidth == 0 || (b->bandwidth + 15) / 16 * 16 >= b->max_qlen) && !getenv("BSB200_NOFULL");   // (BSB200_NOFULL: tests run the general instantiation on full bands too)
 			if(fast) rc = anch ? launch_epi8_forward_pw<true, true>(ctx, a, np, b->pw, full) : launch_epi8_forward_pw<true, false>(ctx, a, np, b->pw, full);
@@ -643,7 +728,7 @@ extern "C" int bsb200_batch_run(bsb200_ctx *ctx, bsb200_batch *b){
 			t.dense = b->want_cigar ? b->d_cig_dense.as<uint32_t>() : nullptr; t.dense_off = b->d_dense_off.as<uint64_t>();
 			t.dense_total = b->d_dense_total.as<unsigned long long>();
 			t.ncigar = b->d_ncigar.as<uint32_t>();
-			t.bandwidth = b->bandwidth; t.mode = b->mode; t.pw = b->pw; t.ubias = fast ? 128 : 0; t.anch = anch ? 1 : 0; memcpy(t.mtx, b->mtx, 16);
+			t.bandwidth = b->bandwidth; t.mode = b->mode; t.pw = b->pw; t.split = b->wave_split; t.ubias = fast ? 128 : 0; t.anch = anch ? 1 : 0; memcpy(t.mtx, b->mtx, 16);
 			t.go1 = b->go1; t.ge1 = b->ge1; t.go2 = b->go2; t.ge2 = b->ge2;
 			epi8_backcal_kernel<<<(np + 63) / 64, 64, 0, sb>>>(t);
 			CK(cudaGetLastError());
@@ -950,7 +1035,7 @@ extern "C" int64_t bsb200_debug_trace(bsb200_ctx *ctx, bsb200_batch *b, uint64_t
 	cudaMemcpy(ql.data(), b->d_qlen.as<uint32_t>() + pair, 4, cudaMemcpyDeviceToHost);
 	cudaMemcpy(tl.data(), b->d_tlen.as<uint32_t>() + pair, 4, cudaMemcpyDeviceToHost);
 	uint32_t bw = bsb200_epi8_bandwidth(ql[0], b->bandwidth);
-	uint64_t bytes = ((uint64_t)(epi8_use_anchors(b->max_bw / 16) ? epi8_row_bytes(bw / 16, b->pw) : epi8_image_bytes(bw / 16) * (b->pw + 1)) + kMetaInts * 4) * ((uint64_t)tl[0] + 1);
+	uint64_t bytes = ((uint64_t)(epi8_use_anchors(b->max_bw / 16) ? epi8_row_bytes(bw / 16, b->pw) : epi8_image_bytes(bw / 16) * (b->pw + 1)) + kMetaInts * 4) * ((uint64_t)tl[0] + 1 + (b->wave_split ? epi8_wave_slack((uint32_t)b->wave_split) : 0u));   // (skewed layout when the wavefront kernel wrote it: epi8_wave.cuh)
 	if(bytes > cap) return -(int64_t)bytes;
 	if(cudaMemcpy(out, ctx->trace.as<uint8_t>() + b->trace_off[pair], bytes, cudaMemcpyDeviceToHost) != cudaSuccess) return -1;
 	if(bw_out) *bw_out = bw;

@@ -14,7 +14,6 @@ constexpr int kEpi8Max = 63;
 // internal per-pair status bits between the forward and the traceback kernel (never returned to the caller)
 constexpr int kStSkew = 0x10000000;   // the pair's trace is in the skewed layout of the wavefront kernel (epi8_wave.cuh)
 constexpr int kStRedo = 0x20000000;   // a guard of the wavefront kernel tripped: the two-pass kernel redoes the pair
-constexpr uint32_t kWaveSlack = 15;   // extra trace slots of a pair in the skewed layout (lane j works j rows behind lane 0)
 
 // ---- s16x2 helpers: two int8 lanes per register ------------------------------------------------------
 __device__ __forceinline__ uint32_t pk(int lo, int hi){ return (uint32_t)(lo & 0xffff) | ((uint32_t)hi << 16); }

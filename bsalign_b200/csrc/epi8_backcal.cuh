@@ -27,6 +27,7 @@ struct Epi8BtArgs {
 	int pw;
 	int anch;                    // rows carry sub-lane anchors (written by the ANCH forward instantiations)
 	int ubias;                   // 128 when the forward kernel stored u + 128 (FAST instantiations), else 0
+	int split;                   // sub-blocks per lane of the wavefront kernel that wrote the skewed pairs (epi8_wave.cuh)
 	int8_t mtx[16];
 	int8_t go1, ge1, go2, ge2;
 };
@@ -36,18 +37,19 @@ struct TraceView {
 	// skew = 1: the pair was written by the wavefront kernel (epi8_wave.cuh): lane j's row y sits in image slot y + 1 + j, the end
 	// anchor ub[k] (k >= 1) of row y in record y + k of `meta` (16 ints per record), ub[0] in `ub0`, the band never moved, the two
 	// steps of a word are step-major (epi8_cell_offset_w) and e is stored + 128
-	int skew; const int32_t *ub0;
+	// With `split` sub-blocks per lane the stage of (lane j, step i) is split * j + i / Wb, and that many slots further down.
+	int skew, split; uint32_t Wb; const int32_t *ub0;
 	__device__ __forceinline__ int beg(int row) const { return skew ? 0 : meta[(size_t)kMetaInts * (row + 1) + 17]; }
 	__device__ __forceinline__ int ub(int row, int j) const {
-		if(skew) return j ? meta[(size_t)16 * (row + j) + j - 1] : ub0[row + 1];
+		if(skew) return j ? meta[(size_t)16 * (row + split * j) + j - 1] : ub0[row + 1];
 		return meta[(size_t)kMetaInts * (row + 1) + j];
 	}
-	// first byte of the image slot that holds lane j of a row
-	__device__ __forceinline__ const uint8_t *slot(int row, uint32_t j) const { return tr + (size_t)RS * (row + 1 + (skew ? (int)j : 0)); }
+	// first byte of the image slot that holds step i of lane j of a row
+	__device__ __forceinline__ const uint8_t *slot(int row, uint32_t j, uint32_t i) const { return tr + (size_t)RS * (row + 1 + (skew ? (int)(split * j + i / Wb) : 0)); }
 	// array arr (0 u, 1 e, 2 q) of the cell at band position p of a row
 	__device__ __forceinline__ int cell(int row, int arr, uint32_t p) const {
 		uint32_t j = p / W, i = p - j * W;
-		uint8_t b = slot(row, j)[(size_t)arr * IB + (skew ? epi8_cell_offset_w(j, i) : epi8_cell_offset(j, i))];
+		uint8_t b = slot(row, j, i)[(size_t)arr * IB + (skew ? epi8_cell_offset_w(j, i) : epi8_cell_offset(j, i))];
 		return (int)(int8_t)(((arr == 0 && ubias) || (arr == 1 && skew)) ? (uint8_t)(b ^ 0x80) : b);
 	}
 	// H(col,row) = anchor of the lane + its u cells up to col (bsalign.h:3187-3202); sets err when the lookup leaves the band
@@ -65,8 +67,9 @@ struct TraceView {
 		int rw = ok ? row : -1;
 		const uint32_t i = up - j * W, g = anch ? i / kAnchorSteps : 0u;   // the sum starts at the sub-lane anchor before step 32g
 		p.n = ok ? i - g * kAnchorSteps + 1 : 0u;
-		const uint8_t *sl = slot(rw, j);
-		p.ub = ok ? (g ? *(const int32_t*)(sl + AOFF + ((g - 1) * 16 + j) * 4) : ub(rw, j)) : kScoreMin;
+		const uint8_t *sl = slot(rw, j, i);
+		// (the sub-lane anchor before step 32g was written by the stage of step 32g - 1)
+		p.ub = ok ? (g ? *(const int32_t*)(slot(rw, j, g * kAnchorSteps - 1) + AOFF + ((g - 1) * 16 + j) * 4) : ub(rw, j)) : kScoreMin;
 		p.r = sl + (size_t)(j >> 1) * 16 + (size_t)g * (kAnchorSteps / 8) * 128;
 		p.mk = skew ? ((j & 1) ? 0x01010000 : 0x00000101) : ((j & 1) ? 0x01000100 : 0x00010001);
 		const uint32_t nch = (p.n + 7) >> 3;
@@ -133,8 +136,11 @@ __global__ void __launch_bounds__(128) epi8_backcal_kernel(const Epi8BtArgs a){
 	int err = a.status[pair];
 	tv.skew = (err & kStSkew) ? 1 : 0;
 	err &= ~(kStSkew | kStRedo);
-	tv.meta = (const int32_t*)(tv.tr + (size_t)tv.RS * (tlen + 1 + (tv.skew ? kWaveSlack : 0u)));
-	tv.ub0 = tv.meta + (size_t)16 * (tlen + 1 + kWaveSlack);
+	tv.split = a.split > 0 ? a.split : 1;
+	tv.Wb = tv.split > 1 ? ((tv.W + tv.split - 1) / tv.split + kAnchorSteps - 1) / kAnchorSteps * kAnchorSteps : (tv.W + 7) / 8 * 8;
+	const uint32_t nslot = (uint32_t)tlen + 1 + (tv.skew ? (uint32_t)(kLanes * tv.split - 1) : 0u);
+	tv.meta = (const int32_t*)(tv.tr + (size_t)tv.RS * nslot);
+	tv.ub0 = tv.meta + (size_t)16 * nslot;
 	const int bw = (int)tv.bw;
 	CigarSink cg;
 	cg.buf = a.cigars ? a.cigars + a.cig_off[pair] : nullptr;
@@ -180,7 +186,7 @@ __global__ void __launch_bounds__(128) epi8_backcal_kernel(const Epi8BtArgs a){
 		const int crow = (state == kStep) ? tb - 1 : -1;                    // row of the cell above (valid memory in any state)
 		const uint32_t cx = cellok ? (uint32_t)x : 0u;
 		const uint32_t cj = cx / tv.W, coff = tv.skew ? epi8_cell_offset_w(cj, cx - cj * tv.W) : epi8_cell_offset(cj, cx - cj * tv.W);
-		const uint8_t *cp = tv.slot(crow, cj) + coff;
+		const uint8_t *cp = tv.slot(crow, cj, cx - cj * tv.W) + coff;
 		const uint32_t ru = cp[0], re = pw >= 1 ? cp[tv.IB] : 0u, rq = pw == 2 ? cp[2 * (size_t)tv.IB] : 0u;
 		const uint32_t qbase = qs[qb >= 0 ? qb : 0], tbase = ts[tb >= 0 ? tb : 0];
 		TraceView::Pending pd;

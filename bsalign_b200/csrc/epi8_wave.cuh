@@ -9,7 +9,11 @@
 // fin[j] >= -63: the F that pass 2 itself leaves the block with.  So the lanes of a pair can run ONE pass each if lane j+1
 // works one row behind lane j:
 //   * thread t of the pair's group of 8 owns lanes 2t (low s16x2 half, row y - 2t) and 2t+1 (high half, row y - 2t - 1);
-//     the block-exit F and the last cell's v travel to the next lane in a register (same thread) or one shuffle (next thread);
+//     the block-exit F and the last cell's v travel to the next lane with a shuffle;
+//   * SPLIT > 1 cuts every lane into SPLIT sub-blocks of whole 32-step groups, one more pipeline stage each (stage = SPLIT * lane +
+//     sub-block, one row behind the stage before it): inside a lane that is nothing but the sequential chain of the SSE code cut
+//     in pieces (F, the running -v and the running absolute score are handed on), and a pair is spread over 8 * SPLIT threads:
+//     batches of a few long pairs (10 kb x 10 kb: HBM capacity seats ~5 pairs per SM) fill the SMs with 4x the warps;
 //   * the two halves of a register sit on different target rows, so the substitution scores come from PRMT(column of row A,
 //     column of row B, selector): scores are kept +63 (0..126), whose sign-replicating nibble yields the zero high byte and,
 //     for positions past the query end, the -63 of the reference (0);
@@ -76,27 +80,31 @@ __device__ __forceinline__ uint32_t wsel(uint32_t cA, uint32_t cB){
 }
 
 // VAR (experiments): bit 0: the selectors of odd steps are shifted down with IMAD.HI (FMA pipe) instead of SHF (ALU pipe)
-template<int K> __device__ __forceinline__ uint32_t wsel_of(const uint4 &c, uint32_t k64k){
-	const uint32_t w = (K >> 1) == 0 ? c.x : (K >> 1) == 1 ? c.y : (K >> 1) == 2 ? c.z : c.w;
-	return (K & 1) ? __umulhi(w, k64k) : w;
+// number of steps of a sub-block: the whole lane (in whole chunks) without a split, else whole 32-step anchor groups
+__host__ __device__ __forceinline__ uint32_t epi8_wave_block_steps(uint32_t W, uint32_t split){
+	if(split <= 1) return (W + 7) / 8 * 8;
+	return ((W + split - 1) / split + kAnchorSteps - 1) / kAnchorSteps * kAnchorSteps;
 }
+// a batch can be split when every sub-block of its narrowest band holds at least one step
+__host__ __device__ __forceinline__ bool epi8_wave_split_ok(uint32_t minW, uint32_t split){ return split <= 1 || (split - 1) * epi8_wave_block_steps(minW, split) < minW; }
+__host__ __device__ __forceinline__ uint32_t epi8_wave_slack(uint32_t split){ return kLanes * split - 1; }   // extra trace slots of a pair
 
-template<bool ANCH, bool NARROW, int VAR = 0>
+template<bool ANCH, int SPLIT>
 __global__ void __launch_bounds__(kFwdThreads, 4) epi8_wave_kernel(const Epi8Args a){
 	extern __shared__ __align__(16) uint8_t smem_raw[];
+	constexpr int kGT = 8 * SPLIT;                 // threads per pair
 	const int lane = threadIdx.x & 31;
-	const int t = lane & 7;
-	const unsigned gmask = 0xffu << (lane & 24);
-	if(NARROW && (uint32_t)(lane >> 3) >= a.gpw) return;
-	const unsigned amask = NARROW ? ((1u << (8 * a.gpw)) - 1u) : 0xffffffffu;
+	const int g = lane & (kGT - 1), t = g & 7, b = g >> 3, gbase = lane - g;
+	const unsigned gmask = (SPLIT == 4 ? 0xffffffffu : ((1u << kGT) - 1u)) << gbase;
+	constexpr unsigned amask = 0xffffffffu;
 	const int A = 2 * t, B = A + 1;
+	const bool lane_end = (b == SPLIT - 1);
 	const uint32_t IMG = a.max_img;
-	uint8_t *gs = smem_raw + (size_t)(NARROW ? (threadIdx.x >> 5) * a.gpw + (lane >> 3) : (threadIdx.x >> 3)) * a.group_smem;
+	uint8_t *gs = smem_raw + (size_t)(threadIdx.x / kGT) * a.group_smem;
 	int8_t *sU = (int8_t*)gs;
 	int8_t *sE = sU + IMG;
 	uint8_t *sC = (uint8_t*)(sE + IMG);
-	int32_t *sUB = (int32_t*)(sC + IMG);
-	int32_t *sRM = sUB + 2 * kMetaInts + 8;
+	int32_t *sRM = (int32_t*)(sC + IMG);         // scratch words of the group: [0] global score, [1 + stage] maximum, [1 + 16 * SPLIT + stage] position
 
 	const int mode = a.mode & 3;
 	const int go1 = a.go1, ge1 = a.ge1;
@@ -106,22 +114,26 @@ __global__ void __launch_bounds__(kFwdThreads, 4) epi8_wave_kernel(const Epi8Arg
 	wk.M1 = a.all_ones; wk.ONE = wk.M1 + 2u; wk.C193 = pk1(193); wk.CM128 = pk1(-128); wk.KGO = pk1(128 - go1); wk.KUG = nadd_const(GOEi + 1); wk.KHG = nadd_const(ge1 + 1);
 	wk.GOE129 = pk1(GOEi + 129); wk.GOE128 = pk1(GOEi + 128);
 	const uint32_t NGOE = pk1(-GOEi);
-	const uint32_t K256 = a.c256, K64K = a.c65536;
+	const uint32_t K256 = a.c256;
 	uint32_t colw[4];
 	#pragma unroll
 	for(int c=0;c<4;c++) colw[c] = (uint32_t)(uint8_t)(a.mtx[c] + 63) | ((uint32_t)(uint8_t)(a.mtx[4 + c] + 63) << 8) | ((uint32_t)(uint8_t)(a.mtx[8 + c] + 63) << 16) | ((uint32_t)(uint8_t)(a.mtx[12 + c] + 63) << 24);
 	#define COLW(tb) (((tb) & 2) ? (((tb) & 1) ? colw[3] : colw[2]) : (((tb) & 1) ? colw[1] : colw[0]))
+	// who hands over to this thread: inside a lane the thread of the previous sub-block (both halves), at a lane's start the last
+	// sub-block of the previous lane - the other half of thread t's own lane pair for lane B, thread t-1's lane B for lane A
+	const int srcA = b ? lane - 8 : (t ? gbase + 8 * (SPLIT - 1) + t - 1 : lane);
+	const int srcB = b ? lane - 8 : gbase + 8 * (SPLIT - 1) + t;
 
 	bool have = false, done = false;
 	uint32_t pair = 0, qlen = 1, tlen = 1, W = 1, IB = 128, RS = 256;
+	uint32_t s0 = 0, nst = 0, cb0 = 0, cb1 = 0;   // this thread's sub-block: first step, steps, chunk range
 	const uint8_t *qs = a.seqs, *ts = a.seqs;
 	uint8_t *tr = a.trace;
 	int32_t *metaS = nullptr, *ub0p = nullptr;
-	int T = 0;                               // time step of the pair: lane j works on row T - j
-	int SA = 0, EA = 0, EB = 0;              // anchors ub[A], ub[A+1] of lane A's last row, ub[B+1] of lane B's last row
-	int fexA = kEpi8Min + 128, vtA_prev = 0; // lane A's block-exit F (biased) and last v of the previous time step: lane B's inputs
-	uint32_t pktB = 0;                       // lane B's (F, v) of the previous time step, for thread t+1
-	uint32_t T32A = 0, T32B = 0;
+	int T = 0;                               // time step of the pair: stage s works on row T - s
+	int SA = 0, EA = 0, EB = 0;              // vertically accumulated anchors (bsalign.h:2618-2636): ub[0] (thread 0 of sub-block 0), ub[A+1], ub[B+1] (lane-end threads)
+	uint32_t pubX1 = 0, pubY1 = 0; int pubX2 = 0, pubY2 = 0;   // what the stages after this thread's two take over: (F | v << 16, absolute score)
+	uint32_t T32A = 0, T32B = 0, hist[SPLIT];
 	int best = kScoreMin, best_te = 0, flagged = 0;
 	uint32_t jq = 0, iq = 0;
 	uint32_t n0 = 0; int c0u = 0, c0e = kEpi8Min;   // lane 0's first cell: selector nibble, u and e of the previous row (thread 0)
@@ -129,42 +141,34 @@ __global__ void __launch_bounds__(kFwdThreads, 4) epi8_wave_kernel(const Epi8Arg
 	#define TOFF(i) ((((i) >> 3) << 7) + (((i) & 7) << 1))                       /* selectors: 2 bytes per step */
 	#define WOFF(i) ((((i) >> 3) << 7) + ((((i) & 7) >> 1) << 2) + ((i) & 1))       /* u, e: lane A's byte of step i (lane B: + 2) */
 	#define QCODE(x) ((x) < qlen ? (uint32_t)qs[(x)] : 4u)
+	#pragma unroll
+	for(int k=0;k<SPLIT;k++) hist[k] = 0;
 
-	// A lane that has finished the pair's last row leaves what the end of the pair needs in the group's scratch words (its bytes in
-	// shared memory are overwritten by the next, idle, time step): GLOBAL: H(qlen-1, tlen-1) if the lane holds that cell
-	// (bsalign.h:4023); else the lane's part of row_max (bsalign.h:3213-3263): its maximum - the earliest 32-step chunk whose prefix
-	// maximum is strictly largest - and the first position inside that chunk that reaches it.
-	auto lane_final = [&](int j, int anchor, int which){
+	// A stage that has finished the pair's last row leaves its share of row_max (bsalign.h:3213-3263) in the group's scratch words
+	// (its bytes in shared memory are overwritten by the idle time steps that follow): the maximum over its 32-step chunks - the
+	// earliest chunk whose prefix maximum is strictly largest - and the first position inside that chunk that reaches it.
+	auto stage_final = [&](int j, int anchor, int which){
 		const int8_t *p = rU + 2 * which;
-		if(mode == 0){
-			if((uint32_t)j == jq){
-				int s = anchor;
-				for(uint32_t i=0;i<=iq;i++) s += (int)(uint8_t)p[WOFF(i)] - 128;
-				sRM[0] = s;
-			}
-			return;
-		}
-		const uint32_t nck = (W + 31) / 32;
-		int Max = kScoreMin, Scr = anchor; uint32_t bc = 0;
-		for(uint32_t c=0;c<nck;c++){
-			uint32_t lo = c * 32, hi = lo + 32 < W ? lo + 32 : W;
+		int Max = kScoreMin, Scr = anchor; uint32_t bc = s0;
+		for(uint32_t lo=s0;lo<s0+nst;lo+=32){
+			const uint32_t hi = lo + 32 < s0 + nst ? lo + 32 : s0 + nst;
 			int run = 0, mx = -32767;
 			for(uint32_t i=lo;i<hi;i++){ run += (int)(uint8_t)p[WOFF(i)] - 128; if(run > mx) mx = run; }
-			int hh = Scr + mx;
-			if(hh > Max){ Max = hh; bc = c; }
+			const int hh = Scr + mx;
+			if(hh > Max){ Max = hh; bc = lo; }
 			Scr += run;
 		}
-		uint32_t x = bc * 32, y = (bc + 1) * 32 < W ? (bc + 1) * 32 : W;
+		uint32_t x = bc; const uint32_t y = bc + 32 < s0 + nst ? bc + 32 : s0 + nst;
 		uint32_t pos = x; int umax = kScoreMin, uscr = 0;
 		for(;x<y;x++){ uscr += (int)(uint8_t)p[WOFF(x)] - 128; if(uscr > umax){ pos = x; umax = uscr; } }
-		sRM[j] = Max; sRM[16 + j] = (int)pos;
+		sRM[1 + j * SPLIT + b] = Max; sRM[1 + kLanes * SPLIT + j * SPLIT + b] = (int)pos;
 	};
 
 	while(true){
 		if(!have && !done){
 			uint32_t idx = 0;
-			if(t == 0) idx = atomicAdd(a.counter, 1u);
-			idx = __shfl_sync(gmask, idx, lane & 24);
+			if(g == 0) idx = atomicAdd(a.counter, 1u);
+			idx = __shfl_sync(gmask, idx, gbase);
 			if(idx >= a.npairs) done = true;
 			else {
 				pair = a.order[idx];
@@ -174,18 +178,24 @@ __global__ void __launch_bounds__(kFwdThreads, 4) epi8_wave_kernel(const Epi8Arg
 				W = bw / kLanes;
 				IB = epi8_image_bytes(W);
 				RS = ANCH ? epi8_row_bytes(W, 1) : IB * 2;
+				const uint32_t Wb = epi8_wave_block_steps(W, SPLIT);
+				s0 = b * Wb; nst = s0 < W ? (W - s0 < Wb ? W - s0 : Wb) : 0;
+				cb0 = s0 / 8; cb1 = (s0 + nst + 7) / 8;
 				tr = a.trace + a.trace_off[pair];
-				metaS = (int32_t*)(tr + (size_t)RS * (tlen + 1 + kWaveSlack));
-				ub0p = metaS + (size_t)16 * (tlen + 1 + kWaveSlack);
+				const uint32_t nslot = tlen + 1 + epi8_wave_slack(SPLIT);
+				metaS = (int32_t*)(tr + (size_t)RS * nslot);
+				ub0p = metaS + (size_t)16 * nslot;
 				T = 0; have = true; flagged = a.force_redo ? 1 : 0;
 				best = kScoreMin; best_te = 0;
 				jq = (qlen - 1) / W; iq = (qlen - 1) - jq * W;
-				fexA = kEpi8Min + 128; vtA_prev = 0; pktB = 0;
-				T32A = COLW((uint32_t)ts[0]); T32B = T32A;   // thread 0's first row; the others re-load before they start
-				// ---- row -1 of the thread's two lanes (bsalign.h:2094-2140) -----------------------------------
+				pubX1 = pubY1 = (uint32_t)(kEpi8Min + 128); pubX2 = pubY2 = 0;
+				T32A = COLW((uint32_t)ts[0]); T32B = T32A;   // stage 0's first row; the others re-load before they start
+				// ---- row -1 of the thread's sub-blocks (bsalign.h:2094-2140) -----------------------------------
 				const bool glob = (mode == 0 || mode == 2);
 				const int u0 = (int8_t)(go1 + ge1 + a.smin - a.smax);
-				for(uint32_t i=0;i<IB/16;i++){
+				// absolute score of row -1 at the end of band position p
+				auto hinit = [&](int64_t p) -> int { return glob ? (int)(a.smax - a.smin + u0 + p * ge1) : 0; };
+				for(uint32_t i=8*cb0;i<8*cb1;i++){
 					uint32_t pA = A * W + i, pB = B * W + i;
 					int vA = 0, vB = 0;
 					if(glob){ vA = (pA == 0) ? u0 : ge1; vB = ge1; }
@@ -194,34 +204,23 @@ __global__ void __launch_bounds__(kFwdThreads, 4) epi8_wave_kernel(const Epi8Arg
 					rE[WOFF(i)] = (int8_t)(kEpi8Min + 128); rE[WOFF(i) + 2] = (int8_t)(kEpi8Min + 128);
 					*(uint16_t*)(rC + TOFF(i)) = (uint16_t)(i < W ? wsel(QCODE(pA), QCODE(pB)) : wsel(4, 4));
 				}
-				auto ubinit = [&](int j) -> int {
-					int s = 0;
-					if(glob){
-						int64_t n = (int64_t)j * W;
-						s = a.smax - a.smin;
-						if(n > 0) s += u0 + (int)((n - 1) * ge1);
-					}
-					return s;
-				};
-				SA = ubinit(A); EA = ubinit(A + 1); EB = ubinit(B + 1);
-				n0 = qlen ? (uint32_t)qs[0] : 8u; c0u = glob ? u0 : 0; c0e = kEpi8Min;
-				// row -1 in the trace: lane j's row -1 is slot j.  Lane A's piece goes out here (the B bytes of that slot are
-				// never read); slot 2t+1 is written by the thread's first time step, which leaves lane B as it is.
+				SA = glob ? a.smax - a.smin : 0; EA = hinit((int64_t)(A + 1) * W - 1); EB = hinit((int64_t)(B + 1) * W - 1);
+				n0 = (uint32_t)qs[0]; c0u = glob ? u0 : 0; c0e = kEpi8Min;
+				// row -1 in the trace: a stage's row -1 is the slot of its number.  Lane A's pieces go out here (the B bytes of that slot
+				// are never read); lane B's slot is written by the time step before lane B starts, which then puts its image back.
 				{
-					uint8_t *d0 = tr + (size_t)RS * A + 16 * t;
-					for(uint32_t c=0;c<IB/128;c++){
+					const uint32_t sA = SPLIT * A + b, sB = sA + SPLIT;
+					uint8_t *d0 = tr + (size_t)RS * sA + 16 * t;
+					for(uint32_t c=cb0;c<cb1;c++){
 						*(uint4*)(d0 + 128 * c) = *(const uint4*)(rU + 128 * c);
 						*(uint4*)(d0 + IB + 128 * c) = *(const uint4*)(rE + 128 * c);
 					}
-					metaS[(size_t)16 * A + A] = EA;
-					metaS[(size_t)16 * B + B] = EB;
-					if(t == 0) ub0p[0] = SA;
+					if(lane_end){ metaS[(size_t)16 * sA + A] = EA; metaS[(size_t)16 * sB + B] = EB; }
+					if(g == 0) ub0p[0] = SA;
 					if(ANCH){
-						int sA_ = SA, sB_ = EA; uint32_t i = 0;
-						for(uint32_t g=1;g<epi8_anchor_groups(W);g++){
-							for(;i<kAnchorSteps*g;i++){ sA_ += (int)(uint8_t)rU[WOFF(i)] - 128; sB_ += (int)(uint8_t)rU[WOFF(i) + 2] - 128; }
-							*(int32_t*)(tr + (size_t)RS * A + (size_t)IB * 2 + ((g - 1) * 16 + A) * 4) = sA_;
-							*(int32_t*)(tr + (size_t)RS * B + (size_t)IB * 2 + ((g - 1) * 16 + B) * 4) = sB_;
+						for(uint32_t gi=s0/kAnchorSteps+1;gi*kAnchorSteps<=s0+nst&&gi<epi8_anchor_groups(W);gi++){
+							*(int32_t*)(tr + (size_t)RS * sA + (size_t)IB * 2 + ((gi - 1) * 16 + A) * 4) = hinit((int64_t)A * W + gi * kAnchorSteps - 1);
+							*(int32_t*)(tr + (size_t)RS * sB + (size_t)IB * 2 + ((gi - 1) * 16 + B) * 4) = hinit((int64_t)B * W + gi * kAnchorSteps - 1);
 						}
 					}
 				}
@@ -230,39 +229,45 @@ __global__ void __launch_bounds__(kFwdThreads, 4) epi8_wave_kernel(const Epi8Arg
 		if(__all_sync(amask, done)) break;
 
 		// =============================== one time step ================================================
-		const int rA = T - 2 * t, rB = rA - 1;
+		const int rA = T - (SPLIT * A + b), rB = rA - SPLIT;
 		const bool actA = have && rA >= 0 && rA < (int)tlen, actB = have && rB >= 0 && rB < (int)tlen;
 		// target base of lane A's next row, in flight during this step
 		uint32_t tbn = 0;
 		if(have && rA + 1 >= 0 && rA + 1 < (int)tlen) tbn = ts[rA + 1];
-		// hand-over: lane A takes F and v from lane B of the previous thread (same row, one time step ago), lane B from lane A
-		const uint32_t pin = __shfl_up_sync(amask, pktB, 1, kGroup);
-		int finA = kEpi8Min + 128, vpA = 0;
-		if(t){ finA = (int)(pin & 0xffffu); vpA = (int)(short)(pin >> 16); }
-		const int finB = fexA, vpB = vtA_prev;
+		// hand-over from the stages before this thread's two (they worked on the same rows one time step ago)
+		const uint32_t inA1 = __shfl_sync(amask, pubX1, srcA), inB1 = __shfl_sync(amask, pubY1, srcB);
+		const int inA2 = __shfl_sync(amask, pubX2, srcA), inB2 = __shfl_sync(amask, pubY2, srcB);
 		if(actA || actB){
 			// ---- cell 0 (bsalign.h:2899-2907): lane 0 only; the override of its score rides on the first chunk's first step ----
 			uint32_t zm = 0xffffffffu, zo = 0u;
-			if(t == 0){
+			if(g == 0){
 				int rh;
 				if(mode == 1 || rA == 0) rh = 0;
 				else rh = (int)((uint32_t)go1 + (uint32_t)ge1 * (uint32_t)rA);
-				const int z0 = (n0 & 8u) ? kEpi8Min : (int)((T32A >> (8 * n0)) & 0xffu) - 63;
+				const int z0 = (int)((T32A >> (8 * n0)) & 0xffu) - 63;
 				const int t0 = c0u + c0e;
 				int h0 = (rh - SA) + z0;
 				if(h0 >= t0){ if(h0 > kEpi8Max) h0 = kEpi8Max; } else h0 = kEpi8Min;
 				zm = 0xffff0000u; zo = (uint32_t)(h0 + 63);
 			}
-			// first cell of a lane: u = subs(u, v of the previous lane's last cell) (bsalign.h:2618-2636); 0 after the first chunk
-			uint32_t NV0 = pk(-vpA, -vpB);
-			const uint32_t nchunk = (W + 7) / 8, nfull = W / 8;
-			WaveState st; st.f = pk(finA, finB); st.h = 0; st.u = 0; st.nv = 0;
+			WaveState st; st.h = 0; st.u = 0;
+			uint32_t NV0 = 0u;
+			if(b == 0){
+				// start of a lane: F from the previous lane's exit (lane 0: -63), v starts at 0 and the first cell's u takes the previous
+				// lane's last v afterwards: u = subs(u, v) (bsalign.h:2618-2636)
+				const int finA = g ? (int)(inA1 & 0xffffu) : kEpi8Min + 128, vpA = g ? (int)(short)(inA1 >> 16) : 0;
+				st.f = pk(finA, (int)(inB1 & 0xffffu)); st.nv = 0;
+				NV0 = pk(-vpA, -(int)(short)(inB1 >> 16));
+			} else {
+				st.f = pk((int)(inA1 & 0xffffu), (int)(inB1 & 0xffffu));
+				st.nv = pk((int)(short)(inA1 >> 16), (int)(short)(inB1 >> 16));
+			}
+			// absolute score at the start of the two sub-blocks (lane 0: the old ub[0]; its first u is re-based after the loop)
+			const int ancA = g ? inA2 : SA, ancB = inB2;
 			uint32_t gacc = st.f, fk = st.f, accA = 0, accB = 0;
 			uint8_t *const gU = tr + (size_t)RS * (T + 1) + 16 * t, *const gE = gU + IB;
-			// anchors of the rows in work: ub[A] (lane 0: the old ub[0], its u[0] is re-based after the loop), ub[B]
-			const int ancA = t ? SA + vpA : SA, ancB = EA;
 			#define WSTEP(K, LEFT) { if((K) < (LEFT)){ \
-				uint32_t z = prmt(T32A, T32B, (VAR & 1) ? wsel_of<K>(cs4, K64K) : ent_sel<K>(cs4)); \
+				uint32_t z = prmt(T32A, T32B, ent_sel<K>(cs4)); \
 				if((K) == 0) z = (z & zm) | zo; \
 				wave_step(st, entw<K>(cu4), entw<K>(ce4), z, wk, un[K], en[K]); \
 				if((K) & 1) gacc = __vimax3_s16x2(gacc, fk, st.f); else fk = st.f; } }
@@ -283,112 +288,137 @@ __global__ void __launch_bounds__(kFwdThreads, 4) epi8_wave_kernel(const Epi8Arg
 				*(uint4*)(rU + 128 * c) = ou4; *(uint4*)(rE + 128 * c) = oe4; \
 				*(uint4*)(gU + (size_t)c * 128) = ou4; *(uint4*)(gE + (size_t)c * 128) = oe4; \
 				if(ANCH && (c & (kAnchorChunks - 1)) == kAnchorChunks - 1 && c + 1 < nchunk){ \
-					/* sub-lane anchors: H at the end of step 8(c+1)-1 = lane anchor + the row's u bytes so far */ \
+					/* sub-lane anchors: H at the end of step 8(c+1)-1 = score at the sub-block's start + its u bytes so far */ \
 					int32_t *an = (int32_t*)(tr + (size_t)RS * (T + 1) + (size_t)IB * 2) + (c / kAnchorChunks) * 16; \
-					const int corr = 128 * (int)(8 * (c + 1)); \
+					const int corr = 128 * (int)(8 * (c + 1 - cb0)); \
 					if(actA) an[A] = ancA + (int)accA - corr; \
 					if(actB) an[B] = ancB + (int)accB - corr; \
 				} }
-			uint32_t c = 0;
+			const uint32_t nchunk = (W + 7) / 8, nfull = (s0 + nst) / 8;
+			uint32_t c = cb0;
 			_Pragma("unroll 1")
 			for(;c<nfull;c++) WCHUNK(8u, false)
-			if(c < nchunk){ const uint32_t left = W - 8 * c; WCHUNK(left, true) }
+			if(c < cb1){ const uint32_t left = s0 + nst - 8 * c; WCHUNK(left, true) }
 			#undef WCHUNK
 			#undef WSTEP
 			gacc = __vmaxs2(gacc, st.f);
-			// ---- tail (bsalign.h:2618-2636): v of each lane's last cell, new anchors ----------------------------
-			int vtA, vtB;
-			{
+			const int fxA = lo16(st.f), fxB = hi16(st.f);
+			// absolute score at the end of the two sub-blocks
+			int HA = ancA + (int)accA - 128 * (int)nst;
+			const int HB = ancB + (int)accB - 128 * (int)nst;
+			int xA = lo16(st.nv), xB = hi16(st.nv);      // what the next stage continues with: the running -v ...
+			if(lane_end){
+				// ... or, at the end of a lane, v of its last cell as the tail of the SSE code computes it (bsalign.h:2618-2636)
 				const uint32_t yb = __viaddmax_s16x2(st.h, wk.GOE129, C129);
 				uint32_t h = pk(lo16(yb) - 257, hi16(yb) - 257);
 				const uint32_t ul = pk(lo16(st.u) - 128, hi16(st.u) - 128);
 				h = sadd(h, NGOE);
 				const uint32_t vt = ssubc(h, ~ul);
-				vtA = lo16(vt); vtB = hi16(vt);
+				xA = lo16(vt); xB = hi16(vt);
 			}
-			const int fxA = lo16(st.f), fxB = hi16(st.f);
 			if(actB){
-				// lane B's row: its start anchor is lane A's end anchor of the same row, i.e. EA before this step's update
-				const int nEB = EB + vtB;
-				const int sum = (int)accB - 128 * (int)W;
-				if(fxB >= 255 || hi16(gacc) >= 255 || (t < 7 && fxB < kEpi8Min + 128) || sum != nEB - EA) flagged = 1;
-				EB = nEB;
-				metaS[(size_t)16 * (T + 1) + B] = EB;
-				if(mode != 0 && jq == (uint32_t)B){
-					int sc = EB;
-					for(uint32_t i=iq+1;i<W;i++) sc -= (int)(uint8_t)rU[WOFF(i) + 2] - 128;
-					if(sc > best){ best = sc; best_te = rB; }
+				if(fxB >= 255 || hi16(gacc) >= 255) flagged = 1;                                        // G1
+				if(lane_end){
+					EB += xB;
+					if((t < 7 && fxB < kEpi8Min + 128) || HB != EB) flagged = 1;                         // G2, G3
+					metaS[(size_t)16 * (T + 1) + B] = EB;
 				}
-				if(rB == (int)tlen - 1) lane_final(B, EA, 1);
+				if(jq == (uint32_t)B && iq >= s0 && iq < s0 + nst && (mode != 0 || rB == (int)tlen - 1)){
+					int sc = HB;
+					for(uint32_t i=iq+1;i<s0+nst;i++) sc -= (int)(uint8_t)rU[WOFF(i) + 2] - 128;
+					if(mode == 0) sRM[0] = sc;
+					else if(sc > best){ best = sc; best_te = rB; }
+				}
+				if(mode != 0 && rB == (int)tlen - 1) stage_final(B, ancB, 1);
 			}
 			if(actA){
-				int dub0 = 0;
-				if(t == 0){
+				if(g == 0){
 					// lane 0 re-bases: ub[0] takes the first cell's u, which is stored as 0 (bsalign.h:2630-2634)
-					dub0 = (int)(uint8_t)rU[0] - 128;
+					const int dub0 = (int)(uint8_t)rU[0] - 128;
 					rU[0] = (int8_t)128; gU[0] = 128;
-					accA -= (uint32_t)dub0;
+					SA += dub0;
+					ub0p[rA + 1] = SA;
 					c0u = 0; c0e = (int)(uint8_t)rE[0] - 128;
 				}
-				const int nSA = t ? SA + vpA : SA + dub0;
-				const int nEA = EA + vtA;
-				const int sum = (int)accA - 128 * (int)W;
-				if(fxA >= 255 || lo16(gacc) >= 255 || fxA < kEpi8Min + 128 || sum != nEA - nSA) flagged = 1;
-				SA = nSA; EA = nEA;
-				metaS[(size_t)16 * (T + 1) + A] = EA;
-				if(t == 0) ub0p[rA + 1] = SA;
-				if(mode != 0 && jq == (uint32_t)A){
-					int sc = EA;
-					for(uint32_t i=iq+1;i<W;i++) sc -= (int)(uint8_t)rU[WOFF(i)] - 128;
-					if(sc > best){ best = sc; best_te = rA; }
+				if(fxA >= 255 || lo16(gacc) >= 255) flagged = 1;
+				if(lane_end){
+					EA += xA;
+					if(fxA < kEpi8Min + 128 || HA != EA) flagged = 1;
+					metaS[(size_t)16 * (T + 1) + A] = EA;
 				}
-				if(rA == (int)tlen - 1) lane_final(A, SA, 0);
-				if(rA == 0){
-					// the thread's first step ran lane B on its row -1 image: put that image back (shared memory and slot 2t+1)
-					const bool glob = (mode == 0 || mode == 2);
-					for(uint32_t i=0;i<IB/16;i++){
-						const int8_t ub_ = (int8_t)(((glob && i < W) ? ge1 : 0) + 128);
-						rU[WOFF(i) + 2] = ub_; rE[WOFF(i) + 2] = (int8_t)(kEpi8Min + 128);
-						gU[WOFF(i) + 2] = (uint8_t)ub_; gE[WOFF(i) + 2] = (uint8_t)(kEpi8Min + 128);
-					}
+				if(jq == (uint32_t)A && iq >= s0 && iq < s0 + nst && (mode != 0 || rA == (int)tlen - 1)){
+					int sc = HA;
+					for(uint32_t i=iq+1;i<s0+nst;i++) sc -= (int)(uint8_t)rU[WOFF(i)] - 128;
+					if(mode == 0) sRM[0] = sc;
+					else if(sc > best){ best = sc; best_te = rA; }
 				}
+				if(mode != 0 && rA == (int)tlen - 1) stage_final(A, g ? ancA : SA, 0);
 			}
-			fexA = fxA; vtA_prev = vtA;
-			pktB = (uint32_t)(fxB & 0xffff) | ((uint32_t)vtB << 16);
+			// what the next stages take over: inside a lane the next sub-block of the same thread column, at a lane's end lane B goes to
+			// thread t+1's lane A and lane A to this column's lane B
+			const uint32_t pA1 = (uint32_t)(fxA & 0xffff) | ((uint32_t)xA << 16), pB1 = (uint32_t)(fxB & 0xffff) | ((uint32_t)xB << 16);
+			const int pA2 = lane_end ? EA : HA, pB2 = lane_end ? EB : HB;
+			if(lane_end){ pubX1 = pB1; pubX2 = pB2; pubY1 = pA1; pubY2 = pA2; }
+			else { pubX1 = pA1; pubX2 = pA2; pubY1 = pB1; pubY2 = pB2; }
 		}
-		T32B = T32A; T32A = COLW(tbn);
+		if(have && rB == -1){
+			// lane B starts with the next time step: the steps before ran it on its row -1 image; put that image back (shared memory
+			// and lane B's bytes of its row -1 slot, which is the slot of this time step)
+			const bool glob = (mode == 0 || mode == 2);
+			uint8_t *const gU = tr + (size_t)RS * (T + 1) + 16 * t, *const gE = gU + IB;
+			for(uint32_t i=8*cb0;i<8*cb1;i++){
+				const int8_t ub_ = (int8_t)(((glob && i < W) ? ge1 : 0) + 128);
+				rU[WOFF(i) + 2] = ub_; rE[WOFF(i) + 2] = (int8_t)(kEpi8Min + 128);
+				gU[WOFF(i) + 2] = (uint8_t)ub_; gE[WOFF(i) + 2] = (uint8_t)(kEpi8Min + 128);
+			}
+		}
+		#pragma unroll
+		for(int k=SPLIT-1;k>0;k--) hist[k] = hist[k - 1];
+		hist[0] = T32A;
+		T32B = hist[SPLIT - 1]; T32A = COLW(tbn);
 		T++;
-		if(have && T == (int)tlen + 15){
-			// ---- the pair is through: every lane left its share of the last row in the group's scratch words ----
+		if(have && T == (int)tlen + kLanes * SPLIT - 1){
+			// ---- the pair is through: every stage left its share of the last row in the group's scratch words ----
 			flagged |= __shfl_xor_sync(gmask, flagged, 1);
 			flagged |= __shfl_xor_sync(gmask, flagged, 2);
 			flagged |= __shfl_xor_sync(gmask, flagged, 4);
+			if(SPLIT >= 2) flagged |= __shfl_xor_sync(gmask, flagged, 8);
+			if(SPLIT >= 4) flagged |= __shfl_xor_sync(gmask, flagged, 16);
 			__syncwarp(gmask);
 			int best_qe = (int)qlen - 1;
 			if(mode == 0){
 				best = sRM[0];
 				best_te = (int)tlen - 1;
 			} else {
-				// the per-row candidates H(qlen-1, y) were collected by the thread that owns that lane
-				best = __shfl_sync(gmask, best, (lane & 24) + (int)(jq >> 1));
-				best_te = __shfl_sync(gmask, best_te, (lane & 24) + (int)(jq >> 1));
-				// row_max: lane-wise maxima reduced in the SSE code's tie-break order (bsalign.h:3264-3291)
-				int M4[4]; uint32_t I4[4];
+				// the per-row candidates H(qlen-1, y) were collected by the thread that owns that stage
+				const uint32_t Wb = epi8_wave_block_steps(W, SPLIT);
+				const int own = gbase + 8 * (int)(iq / Wb) + (int)(jq >> 1);
+				best = __shfl_sync(gmask, best, own);
+				best_te = __shfl_sync(gmask, best_te, own);
+				// row_max: per lane the earliest strictly largest chunk over its sub-blocks, then the lanes in the SSE code's tie-break
+				// order (bsalign.h:3264-3291)
+				auto lane_max = [&](int j, int &m, int &pos){
+					m = sRM[1 + j * SPLIT]; pos = sRM[1 + kLanes * SPLIT + j * SPLIT];
+					#pragma unroll
+					for(int k=1;k<SPLIT;k++) if(sRM[1 + j * SPLIT + k] > m){ m = sRM[1 + j * SPLIT + k]; pos = sRM[1 + kLanes * SPLIT + j * SPLIT + k]; }
+				};
+				int M4[4], P4[4]; uint32_t I4[4];
 				#pragma unroll
 				for(int j=0;j<4;j++){
-					int m0 = sRM[j], m1 = sRM[j + 8];
-					uint32_t i0 = (uint32_t)j, i1 = (uint32_t)j + 8;
-					if(sRM[j + 4] > m0){ m0 = sRM[j + 4]; i0 = (uint32_t)j + 4; }
-					if(sRM[j + 12] > m1){ m1 = sRM[j + 12]; i1 = (uint32_t)j + 12; }
-					if(m1 > m0){ m0 = m1; i0 = i1; }
-					M4[j] = m0; I4[j] = i0;
+					int m0, p0, m1, p1, m2, p2, m3, p3;
+					lane_max(j, m0, p0); lane_max(j + 4, m1, p1); lane_max(j + 8, m2, p2); lane_max(j + 12, m3, p3);
+					uint32_t i0 = (uint32_t)j, i2 = (uint32_t)j + 8;
+					if(m1 > m0){ m0 = m1; p0 = p1; i0 = (uint32_t)j + 4; }
+					if(m3 > m2){ m2 = m3; p2 = p3; i2 = (uint32_t)j + 12; }
+					if(m2 > m0){ m0 = m2; p0 = p2; i0 = i2; }
+					M4[j] = m0; P4[j] = p0; I4[j] = i0;
 				}
-				int max_score = M4[0]; uint32_t bl = I4[0];
+				int max_score = M4[0], bp = P4[0]; uint32_t bl = I4[0];
 				#pragma unroll
-				for(int j=1;j<4;j++) if(M4[j] > max_score){ max_score = M4[j]; bl = I4[j]; }
-				if(max_score > best){ best = max_score; best_qe = (int)(bl * W) + sRM[16 + bl]; best_te = (int)tlen - 1; }
+				for(int j=1;j<4;j++) if(M4[j] > max_score){ max_score = M4[j]; bp = P4[j]; bl = I4[j]; }
+				if(max_score > best){ best = max_score; best_qe = (int)(bl * W) + bp; best_te = (int)tlen - 1; }
 			}
-			if(t == 0){
+			if(g == 0){
 				int32_t *rs = a.results + (size_t)pair * 10;
 				rs[0] = best; rs[2] = best_qe; rs[4] = best_te;
 				a.status[pair] = flagged ? kStRedo : kStSkew;

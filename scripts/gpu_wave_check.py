@@ -60,3 +60,18 @@ cmp(synth.PairBatch.from_lists(pairs), 1, 0, m, G, "homopolymer + long indel ove
 cmp(synth.make_pairs(4, 10000, seed=5), 0, 0, m, G, "10kb global full (anchors)")
 cmp(synth.make_pairs(4, 6000, seed=6), 1, 0, m, G, "6kb overlap full (anchors)")
 print("TOTAL", tot, "BAD", bad)
+# forced splits (sub-blocks per lane): long pairs, every mode
+for split in (2, 4):
+    os.environ["BSB200_WAVE_SPLIT"] = str(split)
+    for mode in (0, 1, 2):
+        for qlen, n in ((1200 if split == 2 else 6500, 6), (10000, 3)):
+            cmp(synth.make_pairs(n, qlen, seed=split * 100 + mode * 10 + qlen % 7), mode, 0, m, G, "split%d mode%d full qlen%d" % (split, mode, qlen))
+    pairs = []
+    for k in range(4):
+        ql = int(rng.integers(6500, 9000)); tl = int(rng.integers(3, 9000))
+        pairs.append((rng.integers(0, 4, ql).astype(np.uint8), rng.integers(0, 4, tl).astype(np.uint8)))
+    pairs.append((rng.integers(0, 4, 7000).astype(np.uint8), rng.integers(0, 4, 2).astype(np.uint8)))
+    cmp(synth.PairBatch.from_lists(pairs), 0, 0, m, G, "split%d unrelated long, short targets" % split)
+    cmp(synth.PairBatch.from_lists(pairs), 1, 0, m, G, "split%d unrelated long overlap" % split)
+os.environ.pop("BSB200_WAVE_SPLIT")
+print("TOTAL", tot, "BAD", bad)

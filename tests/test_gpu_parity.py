@@ -291,3 +291,35 @@ def test_full_size_properties(ctx):
     exp, ecg, _ = ck.oracle_batch("edit", b.subset(sub), 0, 64, nthreads=8)
     for k, i in enumerate(sub):
         assert np.array_equal(res[i], exp[k]) and np.array_equal(e1.cigar(i), ecg[k])
+
+
+def test_real_ont_example_all_pairs(ctx):
+    """All 12,477 ONT read pairs of the reference's own example (example/real.ont.b10M.txt) under the three configurations of
+    example/run.sh:5-9, against the answers of the unmodified reference (tests/golden/real_ont.npz): ten result ints, cigar word
+    counts and checksums of every pair."""
+    import real_ont
+    batch, cfgs, mtx, gaps = real_ont.load()
+    for cfg in cfgs:
+        if cfg["kind"] == "epi8":
+            got = ctx.epi8_batch(batch, cfg["mode"], cfg["bandwidth"], mtx, *gaps, dense=True)
+        else:
+            got = ctx.edit_batch(batch, cfg["mode"], cfg["bandwidth"], dense=True)
+        assert not got.status.any(), (cfg["kind"], cfg["bandwidth"], np.nonzero(got.status)[0][:5])
+        total = int(got.ncigar.astype(np.int64).sum())
+        assert real_ont.compare(cfg, np.arange(batch.n), got.results, got.ncigar, got.cigar_arena[:total]) == [], (cfg["kind"], cfg["bandwidth"])
+
+
+def test_pairwise_compat_header_runs_against_reference():
+    """include/bsalign_b200_compat.h EXECUTED: a C program built from the reference's own headers calls the reference functions and the
+    re-bodied ones on the same pairs (oracle/pairwise_dropin_test.c; built by oracle/Makefile where the reference tree exists, travels
+    as a binary) - identical seqalign_result_t + cigar vectors, CIGRESV appends, empty edit input, and a flagged pair reaches the
+    status hook instead of looking valid."""
+    import subprocess
+    exe = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "oracle", "_ref", "pairwise_dropin")
+    if not os.path.exists(exe):
+        pytest.skip("oracle/_ref/pairwise_dropin was not built (no reference tree at build time)")
+    for args in (["40", "500", "3"], ["12", "2300", "9"]):
+        out = subprocess.run([exe] + args, capture_output=True, text=True, timeout=600)
+        assert out.returncode == 0, out.stdout + out.stderr
+        n = 2 * int(args[0])
+        assert "identical=%d/%d" % (n, n) in out.stdout and "flagged_calls=0" not in out.stdout, out.stdout

@@ -118,7 +118,8 @@ def test_poa_dropin_end_bspoa_identical_msa():
         pytest.skip("oracle/_ref/poa_dropin was not built (no reference tree at build time)")
     # poa_dropin: sweep + walk on the device, graph surgery replayed on the host; poa_dropin_hosttb: row blocks back, the reference's own traceback
     for name in ("poa_dropin", "poa_dropin_hosttb"):
-        for args in (["6", "12", "1500", "3"], ["3", "24", "4000", "5", "0"]):
+        # (the last one is ONE job at BASELINE config 5's full shape: 64 reads x 15 kb, DEFAULT_BSPOA_PAR)
+        for args in (["6", "12", "1500", "3"], ["3", "24", "4000", "5", "0"]) + ((["1", "64", "15000", "7"],) if name == "poa_dropin" else ()):
             out = subprocess.run([os.path.join(ref_dir, name)] + args, capture_output=True, text=True, timeout=600)
             assert out.returncode == 0, out.stdout + out.stderr
             assert "identical=%s/%s" % (args[0], args[0]) in out.stdout, out.stdout

@@ -147,3 +147,18 @@ def test_oracle_rows_equal_reference_rows():
             assert np.array_equal(o[4], r[4])
         if pw == 2:
             assert np.array_equal(o[5], r[5])
+
+
+def test_oracle_matches_reference_on_real_ont_example():
+    """Every 6th of the 12,477 ONT pairs of the reference's example/real.ont.b10M.txt under the three configurations of example/run.sh
+    (answers of the unmodified reference: tests/golden/make_real_golden.py).  The GPU suite runs all of them."""
+    import real_ont
+    batch, cfgs, mtx, gaps = real_ont.load()
+    assert batch.n == 12477
+    idx = np.arange(0, batch.n, 6)
+    sub = batch.subset(idx)
+    for cfg in cfgs:
+        r, c, _ = ck.oracle_batch(cfg["kind"], sub, cfg["mode"], cfg["bandwidth"], mtx, gaps, nthreads=8)
+        ncg = np.array([len(x) for x in c], np.uint32)
+        words = np.concatenate(c) if ncg.sum() else np.zeros(0, np.uint32)
+        assert real_ont.compare(cfg, idx, r, ncg, words) == [], cfg["kind"]
