@@ -74,6 +74,8 @@ def lib():
                                                  _P, _P, _P, _P, _P]
         L.bsb200_batch_upload_dev.restype = _P
         L.bsb200_batch_upload_dev.argtypes = L.bsb200_batch_upload.argtypes
+        L.bsb200_batch_upload_bits.restype = _P
+        L.bsb200_batch_upload_bits.argtypes = L.bsb200_batch_upload.argtypes
         L.bsb200_batch_fetch_dense_dev.argtypes = [_P, _P, _P, _P, ctypes.c_uint64, _P, _P, _P]
         L.bsb200_pack_pairs.restype = ctypes.c_uint64
         L.bsb200_pack_pairs.argtypes = [_P, _P, _P, _P, _P, _P, ctypes.c_uint64, _P, _P, _P, ctypes.c_int]
@@ -189,6 +191,16 @@ class Context:
             raise RuntimeError("bsb200_batch_upload_dev failed: %s" % self._lib.bsb200_last_error(self._h).decode())
         return ResidentBatch(self, h, batch, want_cigar)
 
+    def upload_bits(self, kind, bits, batch, mode, bandwidth, matrix=None, gaps=(0, 0, 0, 0), want_cigar=True):
+        """Like upload(), with the sequences 2-bit packed in the reference's BaseBank word layout (pack_bits); batch.qoff / toff are base offsets."""
+        m = np.ascontiguousarray(matrix if matrix is not None else np.zeros(16), dtype=np.int8)
+        h = self._lib.bsb200_batch_upload_bits(self._h, 0 if kind == "epi8" else 1, batch.n, _ptr(bits), _ptr(batch.qoff), _ptr(batch.qlen),
+                                               _ptr(batch.toff), _ptr(batch.tlen), int(mode), int(bandwidth), _ptr(m),
+                                               gaps[0], gaps[1], gaps[2], gaps[3], 1 if want_cigar else 0)
+        if not h:
+            raise RuntimeError("bsb200_batch_upload_bits failed: %s" % self._lib.bsb200_last_error(self._h).decode())
+        return ResidentBatch(self, h, batch, want_cigar)
+
     def trim(self):
         self._lib.bsb200_trim(self._h)
 
@@ -211,6 +223,15 @@ def pack_pairs(batch, idx, out_seqs=None, nthreads=8):
     pb = PairBatch.__new__(PairBatch)
     pb.seqs, pb.qoff, pb.qlen, pb.toff, pb.tlen = out_seqs[:max(nbytes, 1)], qoff, np.ascontiguousarray(batch.qlen[i64]), toff, np.ascontiguousarray(batch.tlen[i64])
     return pb, nbytes
+
+
+def pack_bits(seqs):
+    """uint8 bases 0..3 -> the reference's BaseBank words (dna.h:63): base i sits in word i >> 5 at bit ((~i) & 31) << 1."""
+    n = len(seqs)
+    pad = (-n) % 32
+    s = np.concatenate([np.asarray(seqs, np.uint8), np.zeros(pad, np.uint8)]).reshape(-1, 32).astype(np.uint64)
+    sh = ((31 - np.arange(32)) * 2).astype(np.uint64)
+    return np.bitwise_or.reduce(s << sh, axis=1).astype(np.uint64)
 
 
 def scatter_words(dst, dst_off, src, src_off, length, nthreads=8):

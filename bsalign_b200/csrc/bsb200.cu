@@ -77,7 +77,7 @@ struct bsb200_ctx {
 	DevBuf counter;
 	// allocations of finished batches are parked here and handed to the next batch (cudaMalloc/cudaFree and pinned
 	// allocations cost more than the kernels of a small batch)
-	DevBuf dev_cache[17];
+	DevBuf dev_cache[18];
 	HostBuf host_cache[8];
 	DevBuf poa_cache[40];   // same, for POA sweep batches (poa_host.cuh)
 	HostBuf poa_hcache[2];
@@ -98,7 +98,7 @@ struct bsb200_batch {
 	std::vector<Wave> waves;
 	std::vector<uint32_t> order;
 	std::vector<uint64_t> trace_off, cig_off;
-	DevBuf d_seqs, d_qoff, d_toff, d_qlen, d_tlen, d_order, d_trace_off, d_results, d_status, d_ncigar, d_cig_raw, d_cig_off, d_cig_dense, d_dense_off, d_dense_total, d_block_rows, d_prefix;
+	DevBuf d_seqs, d_qoff, d_toff, d_qlen, d_tlen, d_order, d_trace_off, d_results, d_status, d_ncigar, d_cig_raw, d_cig_off, d_cig_dense, d_dense_off, d_dense_total, d_block_rows, d_prefix, d_bits;
 	HostBuf h_results, h_status, h_ncigar, h_dense_off, h_dense, h_total;
 	size_t seq_bytes = 0;
 	const uint8_t *d_seqs_ext = nullptr;   // device-resident arena owned by the caller (bsb200_batch_upload_dev)
@@ -196,6 +196,26 @@ extern "C" uint32_t bsb200_edit_bandwidth(uint32_t qlen, uint32_t tlen, int mode
 
 void bsb200_batch_free(bsb200_ctx *ctx, bsb200_batch *b);
 
+// 2-bit packed sequences (the reference's BaseBank words, dna.h:63: base i = bits[i >> 5] >> (((~i) & 31) << 1) & 3) -> one base per byte
+__global__ void __launch_bounds__(256) unpack_bits_kernel(const uint64_t *bits, uint8_t *out, uint64_t nwords, uint64_t nbases){
+	const uint64_t w = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+	if(w >= nwords) return;
+	const uint64_t v = bits[w];
+	uint32_t o[8];
+	#pragma unroll
+	for(int k=0;k<8;k++){
+		const uint32_t b4 = (uint32_t)(v >> (56 - 8 * k)) & 0xffu;   // bases 4k .. 4k+3, first base in the top two bits
+		o[k] = ((b4 >> 6) & 3u) | (((b4 >> 4) & 3u) << 8) | (((b4 >> 2) & 3u) << 16) | ((b4 & 3u) << 24);
+	}
+	uint8_t *dst = out + w * 32;
+	if(w * 32 + 32 <= nbases + 16){   // (the arena is allocated with 16 spare bytes and is 16-byte aligned)
+		*(uint4*)dst = make_uint4(o[0], o[1], o[2], o[3]);
+		if(w * 32 + 16 < nbases + 16) *(uint4*)(dst + 16) = make_uint4(o[4], o[5], o[6], o[7]);
+	} else {
+		for(uint64_t k=0;w*32+k<nbases;k++) dst[k] = (uint8_t)((o[k >> 2] >> (8 * (k & 3))) & 3u);
+	}
+}
+
 // shared memory of one pair's group in the wavefront kernel: u, e and selector images + the scratch words of its stages
 static size_t wave_group_smem(uint32_t max_bw, int split){
 	const size_t img = epi8_image_bytes(max_bw / 16);
@@ -217,7 +237,7 @@ static int plan_wave(const bsb200_ctx *ctx, const bsb200_batch *b, uint32_t min_
 	int best = 0;
 	for(int split : {1, 2, 4}){
 		if(!epi8_wave_split_ok(min_bw / 16, (uint32_t)split)) break;
-		if(split > 1 && !epi8_use_anchors(b->max_bw / 16)) break;   // a traceback lookup must not cross sub-blocks: needs the sub-lane anchors
+		if(split > 1 && !epi8_wave_use_anchors(b->max_bw / 16)) break;   // a traceback lookup must not cross sub-blocks: needs the sub-lane anchors
 		const size_t gsm = wave_group_smem(b->max_bw, split);
 		const size_t per_warp = gsm * (size_t)(4 / split);
 		if(per_warp > ctx->smem_optin) continue;
@@ -229,19 +249,20 @@ static int plan_wave(const bsb200_ctx *ctx, const bsb200_batch *b, uint32_t min_
 	}
 	if(const char *ev = getenv("BSB200_WAVE_SPLIT")){   // tests / experiments: force a split (when the batch allows it)
 		const int f = atoi(ev);
-		if((f == 1 || f == 2 || f == 4) && best && (f == 1 || epi8_use_anchors(b->max_bw / 16)) && epi8_wave_split_ok(min_bw / 16, (uint32_t)f) && wave_group_smem(b->max_bw, f) * (size_t)(4 / f) <= ctx->smem_optin) best = f;
+		if((f == 1 || f == 2 || f == 4) && best && (f == 1 || epi8_wave_use_anchors(b->max_bw / 16)) && epi8_wave_split_ok(min_bw / 16, (uint32_t)f) && wave_group_smem(b->max_bw, f) * (size_t)(4 / f) <= ctx->smem_optin) best = f;
 	}
 	return best;
 }
 
 // d_seqs_ext: the sequence arena is already in this device's memory (it arrived over NVLink: bsalign_b200/shard.py); the batch
 // uses it in place and the caller keeps it alive until bsb200_batch_free.  Offsets and lengths are host arrays in both cases.
-static bsb200_batch *upload_impl(bsb200_ctx *ctx, int kind, uint64_t n, const uint8_t *seqs, const uint8_t *d_seqs_ext,
+// bits64: the sequences come 2-bit packed (bsb200_batch_upload_bits): a quarter of the bytes cross PCIe, a kernel unpacks them.
+static bsb200_batch *upload_impl(bsb200_ctx *ctx, int kind, uint64_t n, const uint8_t *seqs, const uint8_t *d_seqs_ext, const uint64_t *bits64,
 		const uint64_t *qoff, const uint32_t *qlen, const uint64_t *toff, const uint32_t *tlen,
 		int mode, uint32_t bandwidth, const int8_t matrix[16], int8_t go1, int8_t ge1, int8_t go2, int8_t ge2, int want_cigar){
 	if(!ctx) return nullptr;
 	ctx->err.clear();
-	if(n >= 0xFFFFFFF0ull || (n && ((!seqs && !d_seqs_ext) || !qoff || !qlen || !toff || !tlen)) || (kind == 0 && !matrix) || kind < 0 || kind > 1){
+	if(n >= 0xFFFFFFF0ull || (n && ((!seqs && !d_seqs_ext && !bits64) || !qoff || !qlen || !toff || !tlen)) || (kind == 0 && !matrix) || kind < 0 || kind > 1){
 		fail(ctx, "bsb200_batch_upload", cudaSuccess); return nullptr;
 	}
 	cudaSetDevice(ctx->device);
@@ -252,8 +273,8 @@ static bsb200_batch *upload_impl(bsb200_ctx *ctx, int kind, uint64_t n, const ui
 	bsb200_batch *b = new bsb200_batch();
 	{
 		DevBuf *ds[] = {&b->d_seqs, &b->d_qoff, &b->d_toff, &b->d_qlen, &b->d_tlen, &b->d_order, &b->d_trace_off, &b->d_results, &b->d_status,
-			&b->d_ncigar, &b->d_cig_raw, &b->d_cig_off, &b->d_cig_dense, &b->d_dense_off, &b->d_dense_total, &b->d_block_rows, &b->d_prefix};
-		for(int k=0;k<17;k++){ *ds[k] = ctx->dev_cache[k]; ctx->dev_cache[k] = DevBuf(); }
+			&b->d_ncigar, &b->d_cig_raw, &b->d_cig_off, &b->d_cig_dense, &b->d_dense_off, &b->d_dense_total, &b->d_block_rows, &b->d_prefix, &b->d_bits};
+		for(int k=0;k<18;k++){ *ds[k] = ctx->dev_cache[k]; ctx->dev_cache[k] = DevBuf(); }
 		HostBuf *hs[] = {&b->h_results, &b->h_status, &b->h_ncigar, &b->h_dense_off, &b->h_dense, &b->h_total};
 		for(int k=0;k<6;k++){ *hs[k] = ctx->host_cache[k]; ctx->host_cache[k] = HostBuf(); }
 	}
@@ -285,7 +306,14 @@ static bsb200_batch *upload_impl(bsb200_ctx *ctx, int kind, uint64_t n, const ui
 	auto copy_inputs = [&](){
 		cudaEventRecord(ctx->ev[0], st);
 		if(n){
-			if(!d_seqs_ext) R(cudaMemcpyAsync(b->d_seqs.p, seqs, seq_end, cudaMemcpyHostToDevice, st));
+			if(bits64){
+				const uint64_t nw = (seq_end + 31) / 32;
+				R(b->d_bits.reserve(nw * 8 + 8));
+				if(e == cudaSuccess){
+					R(cudaMemcpyAsync(b->d_bits.p, bits64, nw * 8, cudaMemcpyHostToDevice, st));
+					unpack_bits_kernel<<<(unsigned)((nw + 255) / 256), 256, 0, st>>>(b->d_bits.as<uint64_t>(), b->d_seqs.as<uint8_t>(), nw, seq_end);
+				}
+			} else if(!d_seqs_ext) R(cudaMemcpyAsync(b->d_seqs.p, seqs, seq_end, cudaMemcpyHostToDevice, st));
 			R(cudaMemcpyAsync(b->d_qoff.p, qoff, n * 8, cudaMemcpyHostToDevice, st));
 			R(cudaMemcpyAsync(b->d_toff.p, toff, n * 8, cudaMemcpyHostToDevice, st));
 			R(cudaMemcpyAsync(b->d_qlen.p, qlen, n * 4, cudaMemcpyHostToDevice, st));
@@ -479,7 +507,7 @@ static bsb200_batch *upload_impl(bsb200_ctx *ctx, int kind, uint64_t n, const ui
 	float ms = 0; cudaEventElapsedTime(&ms, ctx->ev[0], ctx->ev[1]);
 	ctx->timing = bsb200_timing_t();
 	ctx->timing.h2d_ms = ms;
-	ctx->timing.h2d_bytes = (d_seqs_ext ? 0 : seq_end) + n * (8 + 8 + 4 + 4 + 4 + 8) + (want_cigar ? (n + 1) * 8 : 0);
+	ctx->timing.h2d_bytes = (d_seqs_ext ? 0 : (bits64 ? (seq_end + 31) / 32 * 8 : seq_end)) + n * (8 + 8 + 4 + 4 + 4 + 8) + (want_cigar ? (n + 1) * 8 : 0);
 	ctx->timing.cells = b->cells;
 	ctx->timing.trace_bytes = b->trace_bytes;
 	ctx->timing.waves = (uint32_t)b->waves.size();
@@ -489,13 +517,19 @@ static bsb200_batch *upload_impl(bsb200_ctx *ctx, int kind, uint64_t n, const ui
 extern "C" bsb200_batch *bsb200_batch_upload(bsb200_ctx *ctx, int kind, uint64_t n, const uint8_t *seqs,
 		const uint64_t *qoff, const uint32_t *qlen, const uint64_t *toff, const uint32_t *tlen,
 		int mode, uint32_t bandwidth, const int8_t matrix[16], int8_t go1, int8_t ge1, int8_t go2, int8_t ge2, int want_cigar){
-	return upload_impl(ctx, kind, n, seqs, nullptr, qoff, qlen, toff, tlen, mode, bandwidth, matrix, go1, ge1, go2, ge2, want_cigar);
+	return upload_impl(ctx, kind, n, seqs, nullptr, nullptr, qoff, qlen, toff, tlen, mode, bandwidth, matrix, go1, ge1, go2, ge2, want_cigar);
 }
 
 extern "C" bsb200_batch *bsb200_batch_upload_dev(bsb200_ctx *ctx, int kind, uint64_t n, const uint8_t *d_seqs,
 		const uint64_t *qoff, const uint32_t *qlen, const uint64_t *toff, const uint32_t *tlen,
 		int mode, uint32_t bandwidth, const int8_t matrix[16], int8_t go1, int8_t ge1, int8_t go2, int8_t ge2, int want_cigar){
-	return upload_impl(ctx, kind, n, nullptr, d_seqs, qoff, qlen, toff, tlen, mode, bandwidth, matrix, go1, ge1, go2, ge2, want_cigar);
+	return upload_impl(ctx, kind, n, nullptr, d_seqs, nullptr, qoff, qlen, toff, tlen, mode, bandwidth, matrix, go1, ge1, go2, ge2, want_cigar);
+}
+
+extern "C" bsb200_batch *bsb200_batch_upload_bits(bsb200_ctx *ctx, int kind, uint64_t n, const uint64_t *bits,
+		const uint64_t *qoff, const uint32_t *qlen, const uint64_t *toff, const uint32_t *tlen,
+		int mode, uint32_t bandwidth, const int8_t matrix[16], int8_t go1, int8_t ge1, int8_t go2, int8_t ge2, int want_cigar){
+	return upload_impl(ctx, kind, n, nullptr, nullptr, bits, qoff, qlen, toff, tlen, mode, bandwidth, matrix, go1, ge1, go2, ge2, want_cigar);
 }
 
 template<int PW, bool FAST, bool ANCH>
@@ -697,7 +731,7 @@ extern "C" int bsb200_batch_run(bsb200_ctx *ctx, bsb200_batch *b){
 			// (linear gaps, pw = 0, stay on the literal kernel)
 			// (BSB200_NOFAST: tests run the literal kernels on ordinary gap costs too)
 			const bool fast = b->pw >= 1 && b->ge1 <= 0 && (int8_t)(b->go1 + b->ge1) <= 0 && (b->pw < 2 || (b->ge2 <= 0 && (int8_t)(b->go2 + b->ge2) <= 0)) && !getenv("BSB200_NOFAST");
-			const bool anch = epi8_use_anchors(b->max_bw / 16);
+			const bool anch = b->wave_split ? epi8_wave_use_anchors(b->max_bw / 16) : epi8_use_anchors(b->max_bw / 16);
 			a.gpw = 4;
 			int rc;
 			if(b->wave_split){
@@ -730,7 +764,19 @@ extern "C" int bsb200_batch_run(bsb200_ctx *ctx, bsb200_batch *b){
 			t.ncigar = b->d_ncigar.as<uint32_t>();
 			t.bandwidth = b->bandwidth; t.mode = b->mode; t.pw = b->pw; t.split = b->wave_split; t.ubias = fast ? 128 : 0; t.anch = anch ? 1 : 0; memcpy(t.mtx, b->mtx, 16);
 			t.go1 = b->go1; t.ge1 = b->ge1; t.go2 = b->go2; t.ge2 = b->ge2;
-			epi8_backcal_kernel<<<(np + 63) / 64, 64, 0, sb>>>(t);
+			// one walk per thread; a batch too small to fill the GPU with warps spreads its walks (one every `stride` threads)
+			{
+				// (as long as every block is resident at once: a second round of blocks would double the time)
+				int per_sm = 1;
+				cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, epi8_backcal_kernel, 64, 0);
+				const uint64_t resident = (uint64_t)std::max(per_sm, 1) * ctx->num_sms * 64;
+				uint32_t stride = 1;
+				while(stride < 32 && (uint64_t)np * stride * 2 <= resident) stride *= 2;
+				if(const char *ev = getenv("BSB200_BT_S")){ const int v = atoi(ev); if(v == 1 || v == 2 || v == 4 || v == 8 || v == 16 || v == 32) stride = (uint32_t)v; }
+				t.stride = stride;
+				const uint64_t threads = (uint64_t)np * stride;
+				epi8_backcal_kernel<<<(unsigned)((threads + 63) / 64), 64, 0, sb>>>(t);
+			}
 			CK(cudaGetLastError());
 			ctx->timing.traceback_launches++;
 			CK(cudaEventRecord(evs[wi * 4 + 3], sb));
@@ -961,10 +1007,10 @@ extern "C" void bsb200_batch_free(bsb200_ctx *ctx, bsb200_batch *b){
 	if(!b) return;
 	if(ctx){ cudaSetDevice(ctx->device); cudaStreamSynchronize(ctx->stream); }
 	DevBuf *ds[] = {&b->d_seqs, &b->d_qoff, &b->d_toff, &b->d_qlen, &b->d_tlen, &b->d_order, &b->d_trace_off, &b->d_results, &b->d_status,
-		&b->d_ncigar, &b->d_cig_raw, &b->d_cig_off, &b->d_cig_dense, &b->d_dense_off, &b->d_dense_total, &b->d_block_rows, &b->d_prefix};
+		&b->d_ncigar, &b->d_cig_raw, &b->d_cig_off, &b->d_cig_dense, &b->d_dense_off, &b->d_dense_total, &b->d_block_rows, &b->d_prefix, &b->d_bits};
 	HostBuf *hs[] = {&b->h_results, &b->h_status, &b->h_ncigar, &b->h_dense_off, &b->h_dense, &b->h_total};
 	if(ctx){ // park the allocations for the next batch (a cache slot that is still occupied keeps the larger buffer)
-		for(int k=0;k<17;k++){ if(ctx->dev_cache[k].cap < ds[k]->cap){ ctx->dev_cache[k].release(); ctx->dev_cache[k] = *ds[k]; } else ds[k]->release(); }
+		for(int k=0;k<18;k++){ if(ctx->dev_cache[k].cap < ds[k]->cap){ ctx->dev_cache[k].release(); ctx->dev_cache[k] = *ds[k]; } else ds[k]->release(); }
 		for(int k=0;k<6;k++){ if(ctx->host_cache[k].cap < hs[k]->cap){ ctx->host_cache[k].release(); ctx->host_cache[k] = *hs[k]; } else hs[k]->release(); }
 	} else {
 		for(auto d : ds) d->release();
@@ -1035,7 +1081,7 @@ extern "C" int64_t bsb200_debug_trace(bsb200_ctx *ctx, bsb200_batch *b, uint64_t
 	cudaMemcpy(ql.data(), b->d_qlen.as<uint32_t>() + pair, 4, cudaMemcpyDeviceToHost);
 	cudaMemcpy(tl.data(), b->d_tlen.as<uint32_t>() + pair, 4, cudaMemcpyDeviceToHost);
 	uint32_t bw = bsb200_epi8_bandwidth(ql[0], b->bandwidth);
-	uint64_t bytes = ((uint64_t)(epi8_use_anchors(b->max_bw / 16) ? epi8_row_bytes(bw / 16, b->pw) : epi8_image_bytes(bw / 16) * (b->pw + 1)) + kMetaInts * 4) * ((uint64_t)tl[0] + 1 + (b->wave_split ? epi8_wave_slack((uint32_t)b->wave_split) : 0u));   // (skewed layout when the wavefront kernel wrote it: epi8_wave.cuh)
+	uint64_t bytes = ((uint64_t)((b->wave_split ? epi8_wave_use_anchors(b->max_bw / 16) : epi8_use_anchors(b->max_bw / 16)) ? epi8_row_bytes(bw / 16, b->pw) : epi8_image_bytes(bw / 16) * (b->pw + 1)) + kMetaInts * 4) * ((uint64_t)tl[0] + 1 + (b->wave_split ? epi8_wave_slack((uint32_t)b->wave_split) : 0u));   // (skewed layout when the wavefront kernel wrote it: epi8_wave.cuh)
 	if(bytes > cap) return -(int64_t)bytes;
 	if(cudaMemcpy(out, ctx->trace.as<uint8_t>() + b->trace_off[pair], bytes, cudaMemcpyDeviceToHost) != cudaSuccess) return -1;
 	if(bw_out) *bw_out = bw;

@@ -44,14 +44,18 @@ __host__ __device__ __forceinline__ uint32_t epi8_cell_offset_w(uint32_t j, uint
 
 // Sub-lane anchors for the traceback: besides the 17 block anchors of the reference, a row carries the absolute score
 // at the end of every 32nd step of every lane (int32 [g-1][lane], g = 1 .. ngrp-1), so that a score lookup sums at
-// most 32 cells (4 chunks) instead of a whole lane.
+// most 32 cells (4 chunks = 4 sectors) instead of a whole lane.  (16-step anchors were measured in round 2: the walk of config 2
+// drops from 15.9 to 10.9 ms - it is bound by the sectors it touches - but the anchor code in the wavefront kernel's chunk loop
+// cost 15 ms of forward time and the store grows by 9 %; not kept.)
 constexpr uint32_t kAnchorSteps = 32, kAnchorChunks = kAnchorSteps / 8;
+constexpr uint32_t kStageAlign = 32;   // sub-blocks of the wavefront kernel are whole 32-step groups (the chunks of row_max, bsalign.h:3227)
 __host__ __device__ __forceinline__ uint32_t epi8_anchor_groups(uint32_t W){ return (W + kAnchorSteps - 1) / kAnchorSteps; }
 __host__ __device__ __forceinline__ uint32_t epi8_anchor_bytes(uint32_t W){ return (epi8_anchor_groups(W) - 1) * 64; }
-// the anchors pay off (and are written) only when the widest lane of a batch exceeds 64 steps.  (Measured on config 2, W = 63:
-// anchors every 16 steps for W > 32 cut the traceback from 16.8 to 12.1 ms - it is bound by the sectors a lookup touches - but
-// the forward kernel's anchor loop cost 5 ms, a wash; fusing the anchor sums into pass 2 is the open follow-up.)
+// The two-pass kernel computes the anchors in a loop of its own behind pass 2: they pay off only when the widest lane of a batch
+// exceeds 64 steps.  The wavefront kernel has the running sums in registers anyway and writes them whenever a lane has more than
+// one anchor group ... in principle; the branch in its chunk loop is not free either, so the same rule applies for now.
 __host__ __device__ __forceinline__ bool epi8_use_anchors(uint32_t maxW){ return maxW > 64; }
+__host__ __device__ __forceinline__ bool epi8_wave_use_anchors(uint32_t maxW){ return maxW > 64; }
 __host__ __device__ __forceinline__ uint32_t epi8_row_bytes(uint32_t W, int pw){ return epi8_image_bytes(W) * (pw + 1) + epi8_anchor_bytes(W); }
 
 struct CigarSink {

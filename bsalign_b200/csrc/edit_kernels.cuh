@@ -78,9 +78,16 @@ __global__ void __launch_bounds__(kEditThreads) edit_kernel(const EditArgs a){
 	const uint32_t blk = gid >> 5;
 	const uint32_t R = a.block_rows[blk];
 	uint64_t *tp = (uint64_t*)(a.trace + a.block_off[blk]);                 // planes: ((row*WB + w)*2 + plane)*32 + lane
-	uint32_t *tbeg = (uint32_t*)(tp + (size_t)R * a.WB * 2 * 32);           // begs:   row*32 + lane
+	(void)R;
 	#define TP(row, w, plane) tp[(((size_t)(row) * a.WB + (w)) * 2 + (plane)) * 32 + lane]
-	#define TBEG(row) tbeg[(size_t)(row) * 32 + lane]
+	// band offset of target row y (bsalign.h:1112-1114): a function of y alone, so the backtrace computes it instead of reading it back
+	auto rbeg_of = [&](int y) -> uint32_t {
+		if(type != 0) return 0u;
+		uint32_t r_ = (uint32_t)(((uint64_t)(uint32_t)y * qlen) / tlen);
+		r_ = (r_ < bw / 2) ? 0u : r_ - bw / 2;
+		return (r_ + bw > q64) ? q64 - bw : r_;
+	};
+	#define RBEG(y) rbeg_of(y)
 	// ---- query bit-planes in shared memory (bit x of plane 0/1 = low/high bit of q[x]) --------------
 	#define QB(word, plane) qbits[((size_t)(word) * 2 + (plane)) * nthr + threadIdx.x]
 	const uint32_t nqw = a.nQW;
@@ -98,7 +105,6 @@ __global__ void __launch_bounds__(kEditThreads) edit_kernel(const EditArgs a){
 	#pragma unroll (REG ? WR : 1)
 	for(int w=0;w<WR;w++){ if(!REG && w >= (int)W) break; Pv[w] = ~0ull; Mv[w] = 0ull; }
 	for(uint32_t w=0;w<W;w++){ TP(0, w, 0) = 0ull; TP(0, w, 1) = ~0ull; }
-	TBEG(0) = 0;
 	int sbeg = 0, smin = 0x7FFFFFFF, rx = (int)qlen - 1, ry = (int)tlen - 1;
 	uint32_t rbeg = 0, prev_beg = 0;
 	const uint32_t qd = qlen / tlen, qr = qlen % tlen;   // floor(i*qlen/tlen) kept incrementally (bsalign.h:1112)
@@ -201,7 +207,6 @@ __global__ void __launch_bounds__(kEditThreads) edit_kernel(const EditArgs a){
 			TP(i + 1, w, 0) = mv; TP(i + 1, w, 1) = pv;
 			rowsum += __popcll(pv & valid) - __popcll(mv & valid);
 		}
-		TBEG(i + 1) = rbeg;
 		if(type != 0){ // bsalign.h:1124-1139: H(qlen-1, i)
 			int srow = sbeg + rowsum;
 			if(srow < smin){ smin = srow; rx = (int)qlen - 1; ry = (int)i; }
@@ -255,16 +260,19 @@ __global__ void __launch_bounds__(kEditThreads) edit_kernel(const EditArgs a){
 		uint32_t op;
 		if(qc == ts[y]){ mat++; op = 0; x--; y--; }
 		else {
-			int64_t p1 = (int64_t)x - (int64_t)TBEG(y + 1);
+			// both rows the decision may need are requested together (slot y + 1 = row y, slot y = row y - 1; slot 0 is the init row)
+			const int64_t p1 = (int64_t)x - (int64_t)RBEG(y), p0 = (int64_t)x - (int64_t)(y > 0 ? RBEG(y - 1) : 0u);
+			const bool ok1 = p1 >= 0 && p1 < (int64_t)bw, ok0 = p0 >= 0 && p0 < (int64_t)bw;
+			const uint64_t w1p = ok1 ? TP(y + 1, p1 >> 6, 1) : 0ull, w1m = ok1 ? TP(y + 1, p1 >> 6, 0) : 0ull;
+			const uint64_t w0p = ok0 ? TP(y, p0 >> 6, 1) : 0ull, w0m = ok0 ? TP(y, p0 >> 6, 0) : 0ull;
 			int u_here = 0;
-			if(p1 < 0 || p1 >= (int64_t)bw) err |= 1;
-			else u_here = (int)((TP(y + 1, p1 >> 6, 1) >> (p1 & 63)) & 1) - (int)((TP(y + 1, p1 >> 6, 0) >> (p1 & 63)) & 1);
+			if(!ok1) err |= 1;
+			else u_here = (int)((w1p >> (p1 & 63)) & 1) - (int)((w1m >> (p1 & 63)) & 1);
 			if(u_here == 1){ ins++; op = 1; x--; }
 			else {
-				int64_t p0 = (int64_t)x - (int64_t)TBEG(y);
 				int u_up = 0;
-				if(p0 < 0 || p0 >= (int64_t)bw) err |= 1;
-				else u_up = (int)((TP(y, p0 >> 6, 1) >> (p0 & 63)) & 1) - (int)((TP(y, p0 >> 6, 0) >> (p0 & 63)) & 1);
+				if(!ok0) err |= 1;
+				else u_up = (int)((w0p >> (p0 & 63)) & 1) - (int)((w0m >> (p0 & 63)) & 1);
 				if(u_up == -1){ del++; op = 2; y--; }
 				else { mis++; op = 0; x--; y--; }
 			}
@@ -290,7 +298,7 @@ __global__ void __launch_bounds__(kEditThreads) edit_kernel(const EditArgs a){
 	emit_dense(cg, a.dense, a.dense_off, a.dense_total, a.ncigar, pair);
 	a.status[pair] = err | cg.err;
 	#undef TP
-	#undef TBEG
+	#undef RBEG
 	#undef QB
 }
 

@@ -28,6 +28,7 @@ struct Epi8BtArgs {
 	int anch;                    // rows carry sub-lane anchors (written by the ANCH forward instantiations)
 	int ubias;                   // 128 when the forward kernel stored u + 128 (FAST instantiations), else 0
 	int split;                   // sub-blocks per lane of the wavefront kernel that wrote the skewed pairs (epi8_wave.cuh)
+	uint32_t stride;             // one walk every `stride` threads (power of two <= 32): small batches spread their walks over more warps
 	int8_t mtx[16];
 	int8_t go1, ge1, go2, ge2;
 };
@@ -39,6 +40,9 @@ struct TraceView {
 	// steps of a word are step-major (epi8_cell_offset_w) and e is stored + 128
 	// With `split` sub-blocks per lane the stage of (lane j, step i) is split * j + i / Wb, and that many slots further down.
 	int skew, split; uint32_t Wb; const int32_t *ub0;
+	// p / W without a division (the walk does it twice per step): one multiply with ceil(2^32 / W) and a correction; exact for p < 16 W, W < 16384
+	uint32_t Wmagic;
+	__device__ __forceinline__ uint32_t div_w(uint32_t p) const { if(W == 1) return p; uint32_t j = __umulhi(p, Wmagic); return j * W > p ? j - 1 : j; }
 	__device__ __forceinline__ int beg(int row) const { return skew ? 0 : meta[(size_t)kMetaInts * (row + 1) + 17]; }
 	__device__ __forceinline__ int ub(int row, int j) const {
 		if(skew) return j ? meta[(size_t)16 * (row + split * j) + j - 1] : ub0[row + 1];
@@ -48,7 +52,7 @@ struct TraceView {
 	__device__ __forceinline__ const uint8_t *slot(int row, uint32_t j, uint32_t i) const { return tr + (size_t)RS * (row + 1 + (skew ? (int)(split * j + i / Wb) : 0)); }
 	// array arr (0 u, 1 e, 2 q) of the cell at band position p of a row
 	__device__ __forceinline__ int cell(int row, int arr, uint32_t p) const {
-		uint32_t j = p / W, i = p - j * W;
+		uint32_t j = div_w(p), i = p - j * W;
 		uint8_t b = slot(row, j, i)[(size_t)arr * IB + (skew ? epi8_cell_offset_w(j, i) : epi8_cell_offset(j, i))];
 		return (int)(int8_t)(((arr == 0 && ubias) || (arr == 1 && skew)) ? (uint8_t)(b ^ 0x80) : b);
 	}
@@ -63,7 +67,7 @@ struct TraceView {
 		int64_t pos = (int64_t)col - rbeg;
 		bool ok = need && row >= -1 && row < tlen && pos >= 0 && pos < (int64_t)bw;
 		if(need && !ok) err |= 1;
-		uint32_t up = ok ? (uint32_t)pos : 0u, j = up / W;
+		uint32_t up = ok ? (uint32_t)pos : 0u, j = div_w(up);
 		int rw = ok ? row : -1;
 		const uint32_t i = up - j * W, g = anch ? i / kAnchorSteps : 0u;   // the sum starts at the sub-lane anchor before step 32g
 		p.n = ok ? i - g * kAnchorSteps + 1 : 0u;
@@ -76,37 +80,32 @@ struct TraceView {
 		#pragma unroll
 		for(int k=0;k<8;k++) p.v[k] = (uint32_t)k < nch ? *(const int4*)(p.r + 128 * k) : make_int4(0, 0, 0, 0);
 	}
+	// (branch-free: a word holds two steps of the lane; the mask of a word is the lane's, the first step's, or 0)
+	__device__ __forceinline__ int word_mask(int left, int mk) const { return left >= 2 ? mk : (left == 1 ? first_step(mk) : 0); }
 	__device__ __forceinline__ int finish(const Pending &p) const {
 		int s = p.ub;
-		const uint32_t nch = (p.n + 7) >> 3;
+		const int xm = ubias ? (int)0x80808080 : 0; // u + 128 as unsigned byte -> two's complement
 		#pragma unroll
 		for(int k=0;k<8;k++){
-			if((uint32_t)k < nch){
-				const uint32_t left = p.n - 8 * k;
-				const int xm = ubias ? (int)0x80808080 : 0; // u + 128 as unsigned byte -> two's complement
-				const int w[4] = {p.v[k].x ^ xm, p.v[k].y ^ xm, p.v[k].z ^ xm, p.v[k].w ^ xm};
-				#pragma unroll
-				for(int q=0;q<4;q++){
-					if(left >= 2u * q + 2) s = __dp4a(w[q], p.mk, s);
-					else if(left == 2u * q + 1) s = __dp4a(w[q], first_step(p.mk), s);
-				}
-			}
+			const int left = (int)p.n - 8 * k;
+			if(left <= 0) break;   // (one test per chunk; the words of a chunk are branch-free)
+			s = __dp4a(p.v[k].x ^ xm, word_mask(left, p.mk), s);
+			s = __dp4a(p.v[k].y ^ xm, word_mask(left - 2, p.mk), s);
+			s = __dp4a(p.v[k].z ^ xm, word_mask(left - 4, p.mk), s);
+			s = __dp4a(p.v[k].w ^ xm, word_mask(left - 6, p.mk), s);
 		}
-		for(uint32_t c0=8;c0<nch;c0+=8){ // lanes longer than 64 steps: further rounds
+		const uint32_t nch = (p.n + 7) >> 3;
+		for(uint32_t c0=8;c0<nch;c0+=8){ // lanes longer than 64 steps without anchors: further rounds
 			int4 v[8];
 			#pragma unroll
-			for(int k=0;k<8;k++) if(c0 + k < nch) v[k] = *(const int4*)(p.r + 128 * (c0 + k));
+			for(int k=0;k<8;k++) v[k] = c0 + k < nch ? *(const int4*)(p.r + 128 * (c0 + k)) : make_int4(0, 0, 0, 0);
 			#pragma unroll
 			for(int k=0;k<8;k++){
-				if(c0 + k >= nch) break;
-				const uint32_t left = p.n - 8 * (c0 + k);
-				const int xm2 = ubias ? (int)0x80808080 : 0;
-				const int w[4] = {v[k].x ^ xm2, v[k].y ^ xm2, v[k].z ^ xm2, v[k].w ^ xm2};
-				#pragma unroll
-				for(int q=0;q<4;q++){
-					if(left >= 2u * q + 2) s = __dp4a(w[q], p.mk, s);
-					else if(left == 2u * q + 1) s = __dp4a(w[q], first_step(p.mk), s);
-				}
+				const int left = (int)p.n - 8 * (int)(c0 + k);
+				s = __dp4a(v[k].x ^ xm, word_mask(left, p.mk), s);
+				s = __dp4a(v[k].y ^ xm, word_mask(left - 2, p.mk), s);
+				s = __dp4a(v[k].z ^ xm, word_mask(left - 4, p.mk), s);
+				s = __dp4a(v[k].w ^ xm, word_mask(left - 6, p.mk), s);
 			}
 		}
 		return s;
@@ -121,6 +120,10 @@ struct TraceView {
 
 __global__ void __launch_bounds__(128) epi8_backcal_kernel(const Epi8BtArgs a){
 	uint32_t idx = blockIdx.x * blockDim.x + threadIdx.x;
+	// The 32 walks of a warp run in lock step: every iteration waits for the slowest of 32 scattered loads and executes the union of
+	// the branches taken.  A batch that cannot fill the GPU with warps anyway puts one walk every `stride` threads.
+	if(idx & (a.stride - 1)) return;
+	idx /= a.stride;
 	if(idx >= a.npairs) return;
 	const uint32_t pair = a.order[idx];
 	const int qlen = (int)a.qlen[pair], tlen = (int)a.tlen[pair];
@@ -131,13 +134,13 @@ __global__ void __launch_bounds__(128) epi8_backcal_kernel(const Epi8BtArgs a){
 	TraceView tv;
 	tv.bw = a.bandwidth ? a.bandwidth : (uint32_t)qlen;
 	tv.bw = (tv.bw + kLanes - 1) / kLanes * kLanes;
-	tv.W = tv.bw / kLanes; tv.IB = epi8_image_bytes(tv.W); tv.RS = a.anch ? epi8_row_bytes(tv.W, pw) : tv.IB * (pw + 1); tv.AOFF = tv.IB * (pw + 1); tv.anch = a.anch; tv.tlen = tlen; tv.ubias = a.ubias;
+	tv.W = tv.bw / kLanes; tv.Wmagic = tv.W > 1 ? (uint32_t)((0x100000000ull + tv.W - 1) / tv.W) : 0xffffffffu; tv.IB = epi8_image_bytes(tv.W); tv.RS = a.anch ? epi8_row_bytes(tv.W, pw) : tv.IB * (pw + 1); tv.AOFF = tv.IB * (pw + 1); tv.anch = a.anch; tv.tlen = tlen; tv.ubias = a.ubias;
 	tv.tr = a.trace + a.trace_off[pair];
 	int err = a.status[pair];
 	tv.skew = (err & kStSkew) ? 1 : 0;
 	err &= ~(kStSkew | kStRedo);
 	tv.split = a.split > 0 ? a.split : 1;
-	tv.Wb = tv.split > 1 ? ((tv.W + tv.split - 1) / tv.split + kAnchorSteps - 1) / kAnchorSteps * kAnchorSteps : (tv.W + 7) / 8 * 8;
+	tv.Wb = tv.split > 1 ? ((tv.W + tv.split - 1) / tv.split + kStageAlign - 1) / kStageAlign * kStageAlign : (tv.W + 7) / 8 * 8;
 	const uint32_t nslot = (uint32_t)tlen + 1 + (tv.skew ? (uint32_t)(kLanes * tv.split - 1) : 0u);
 	tv.meta = (const int32_t*)(tv.tr + (size_t)tv.RS * nslot);
 	tv.ub0 = tv.meta + (size_t)16 * nslot;
@@ -185,7 +188,7 @@ __global__ void __launch_bounds__(128) epi8_backcal_kernel(const Epi8BtArgs a){
 		// ---- 2. issue every load of this step (cell above, query/target bases, lookup), then consume -------------
 		const int crow = (state == kStep) ? tb - 1 : -1;                    // row of the cell above (valid memory in any state)
 		const uint32_t cx = cellok ? (uint32_t)x : 0u;
-		const uint32_t cj = cx / tv.W, coff = tv.skew ? epi8_cell_offset_w(cj, cx - cj * tv.W) : epi8_cell_offset(cj, cx - cj * tv.W);
+		const uint32_t cj = tv.div_w(cx), coff = tv.skew ? epi8_cell_offset_w(cj, cx - cj * tv.W) : epi8_cell_offset(cj, cx - cj * tv.W);
 		const uint8_t *cp = tv.slot(crow, cj, cx - cj * tv.W) + coff;
 		const uint32_t ru = cp[0], re = pw >= 1 ? cp[tv.IB] : 0u, rq = pw == 2 ? cp[2 * (size_t)tv.IB] : 0u;
 		const uint32_t qbase = qs[qb >= 0 ? qb : 0], tbase = ts[tb >= 0 ? tb : 0];

@@ -80,10 +80,10 @@ __device__ __forceinline__ uint32_t wsel(uint32_t cA, uint32_t cB){
 }
 
 // VAR (experiments): bit 0: the selectors of odd steps are shifted down with IMAD.HI (FMA pipe) instead of SHF (ALU pipe)
-// number of steps of a sub-block: the whole lane (in whole chunks) without a split, else whole 32-step anchor groups
+// number of steps of a sub-block: the whole lane (in whole chunks) without a split, else whole 32-step groups
 __host__ __device__ __forceinline__ uint32_t epi8_wave_block_steps(uint32_t W, uint32_t split){
 	if(split <= 1) return (W + 7) / 8 * 8;
-	return ((W + split - 1) / split + kAnchorSteps - 1) / kAnchorSteps * kAnchorSteps;
+	return ((W + split - 1) / split + kStageAlign - 1) / kStageAlign * kStageAlign;
 }
 // a batch can be split when every sub-block of its narrowest band holds at least one step
 __host__ __device__ __forceinline__ bool epi8_wave_split_ok(uint32_t minW, uint32_t split){ return split <= 1 || (split - 1) * epi8_wave_block_steps(minW, split) < minW; }

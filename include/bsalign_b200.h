@@ -106,6 +106,14 @@ bsb200_batch *bsb200_batch_upload(bsb200_ctx *ctx, int kind, uint64_t n, const u
 		const uint64_t *qoff, const uint32_t *qlen, const uint64_t *toff, const uint32_t *tlen,
 		int mode, uint32_t bandwidth, const int8_t matrix[16], int8_t gapo1, int8_t gape1, int8_t gapo2, int8_t gape2,
 		int want_cigar);
+/* Same, with the sequences 2-BIT PACKED as the reference stores them: `bits` is a BaseBank's word array (dna.h:63 bits2bit: base i =
+ * bits[i >> 5] >> (((~i) & 31) << 1) & 3; main.c keeps every read that way, seqs->rdseqs, and unpacks a pair with bitseq_basebank,
+ * dna.h:769, before each call); qoff / toff are BASE offsets into it (seqs->rdoffs).  A quarter of the bytes cross PCIe; the bases
+ * are unpacked on the device. */
+bsb200_batch *bsb200_batch_upload_bits(bsb200_ctx *ctx, int kind, uint64_t n, const uint64_t *bits,
+		const uint64_t *qoff, const uint32_t *qlen, const uint64_t *toff, const uint32_t *tlen,
+		int mode, uint32_t bandwidth, const int8_t matrix[16], int8_t gapo1, int8_t gape1, int8_t gapo2, int8_t gape2,
+		int want_cigar);
 int bsb200_batch_run(bsb200_ctx *ctx, bsb200_batch *b);       /* kernels only; returns when they are done */
 int bsb200_batch_sync(bsb200_ctx *ctx);                       /* wait for the stream */
 int bsb200_batch_fetch(bsb200_ctx *ctx, bsb200_batch *b, bsb200_result_t *results,
