@@ -528,6 +528,22 @@ def run_workload(ctx, name, w, pairs, args, ncores, rank, world, local_rank, dis
         torch.cuda.synchronize()
         pg_ms = (time.perf_counter() - t0) * 1e3
         e2e_extra["pageable"] = {"value": total_cells / (pg_ms * 1e-3) / 1e9, "ms_per_step": pg_ms}
+        # ... and with the sequences 2-bit packed the way the reference keeps them (BaseBank words, dna.h:63; main.c unpacks a pair per call):
+        # bsb200_batch_upload_bits + run + fetch_dense, packed words in pinned memory
+        bits = pin(api.pack_bits(batch.seqs))
+        pk_ms = 0.0
+        for it in range(1 + args.steps):
+            t0 = time.perf_counter()
+            rbb = ctx.upload_bits(kind, bits, hb, w["mode"], w["bandwidth"], mtx, GAPS, want_cigar=True)
+            tmb = ctx.timing()
+            rbb.run()
+            rpk = rbb.fetch_dense(out=outbuf)
+            rbb.free()
+            if it:
+                pk_ms += (time.perf_counter() - t0) * 1e3 / args.steps
+        assert np.array_equal(rpk.results, last.results), "2-bit packed upload and byte upload disagree"
+        e2e_extra["packed_2bit"] = {"value": total_cells / (pk_ms * 1e-3) / 1e9, "ms_per_step": pk_ms, "h2d_bytes_per_step": int(tmb["h2d_bytes"])}
+        r = rpk
         assert int(r.results[:, 0].astype(np.int64).sum()) == int(last.results[:, 0].astype(np.int64).sum()), "e2e and resident runs disagree"
     else:
         # rank 0 owns the batch in (pinned) host memory: lengths broadcast, compact arenas scattered over NVLink, every rank aligns its
@@ -731,7 +747,7 @@ def main():
                 so = run_workload(ctx, name, sw, sp, sargs, ncores, rank, world, local_rank, dist, torch, 0 if args.no_cpu_baseline else 5.0, min(args.check, 256))
                 cpu = so.get("cpu_baseline")
                 secondary[name] = {"workload": so["config"]["workload"], "pairs": so["config"]["pairs"], "value": so["value"], "ms_per_step": so["ms_per_step"],
-                                   "e2e": so["e2e"]["value"], "e2e_ms_per_step": so["e2e"]["ms_per_step"], "e2e_pageable": so["e2e"].get("pageable", {}).get("value"),
+                                   "e2e": so["e2e"]["value"], "e2e_ms_per_step": so["e2e"]["ms_per_step"], "e2e_pageable": so["e2e"].get("pageable", {}).get("value"), "e2e_packed_2bit": so["e2e"].get("packed_2bit", {}).get("value"),
                                    "roofline_frac": so["roofline"]["frac"], "kernel": so["roofline"]["kernel"], "kernel_ms_per_step": so["roofline"]["kernel_ms_per_step"],
                                    "traceback_ms_per_step": so["roofline"]["traceback_ms_per_step"],
                                    "cpu": None if not cpu else {"value": cpu["value"], "cores": cpu["cores"], "kind": cpu["kind"], "sample": cpu["sample"], "results_equal_gpu": cpu["results_equal_gpu"]},

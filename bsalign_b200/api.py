@@ -74,6 +74,27 @@ def lib():
                                                  _P, _P, _P, _P, _P]
         L.bsb200_batch_upload_dev.restype = _P
         L.bsb200_batch_upload_dev.argtypes = L.bsb200_batch_upload.argtypes
+        L.bsb200_pairwise_batch_dense.argtypes = [_P, ctypes.c_int, ctypes.c_uint64, _P, _P, _P, _P, _P, ctypes.c_int, ctypes.c_uint32, _P,
+                                                  _I8, _I8, _I8, _I8, _P, _P, ctypes.c_uint64, _P, _P, _P]
+        L.bsb200_pairwise_batch_ptrs.argtypes = [_P, ctypes.c_int, ctypes.c_uint64, _P, _P, _P, _P, ctypes.c_int, ctypes.c_uint32, _P,
+                                                 _I8, _I8, _I8, _I8, _P, _P, _P, _P, ctypes.c_int]
+        L.bsb200_pairwise_batch_multi.argtypes = [_P, ctypes.c_int, ctypes.c_int, ctypes.c_uint64, _P, _P, _P, _P, _P, ctypes.c_int, ctypes.c_uint32, _P,
+                                                  _I8, _I8, _I8, _I8, _P, _P, _P, _P, _P]
+        L.bsb200_seqfile_read.restype = _P
+        L.bsb200_seqfile_read.argtypes = [ctypes.c_char_p]
+        L.bsb200_seqfile_error.restype = ctypes.c_char_p
+        L.bsb200_seqfile_error.argtypes = [_P]
+        for fn in ("bsb200_seqfile_nseq", "bsb200_seqfile_nbases"):
+            getattr(L, fn).restype = ctypes.c_uint64
+            getattr(L, fn).argtypes = [_P]
+        for fn in ("bsb200_seqfile_bits", "bsb200_seqfile_offsets", "bsb200_seqfile_lengths"):
+            getattr(L, fn).restype = _P
+            getattr(L, fn).argtypes = [_P]
+        L.bsb200_seqfile_name.restype = ctypes.c_char_p
+        L.bsb200_seqfile_name.argtypes = [_P, ctypes.c_uint64]
+        L.bsb200_seqfile_free.argtypes = [_P]
+        L.bsb200_format_pair_text.restype = ctypes.c_uint64
+        L.bsb200_format_pair_text.argtypes = [_P, ctypes.c_uint64, ctypes.c_char_p, ctypes.c_uint32, ctypes.c_char_p, ctypes.c_uint32, _P, _P, ctypes.c_uint64, ctypes.c_uint64, _P, ctypes.c_uint32]
         L.bsb200_batch_upload_bits.restype = _P
         L.bsb200_batch_upload_bits.argtypes = L.bsb200_batch_upload.argtypes
         L.bsb200_batch_fetch_dense_dev.argtypes = [_P, _P, _P, _P, ctypes.c_uint64, _P, _P, _P]
@@ -150,14 +171,18 @@ class Context:
         return BatchResult(res, cg, off, ncg, st)
 
     def _staged(self, kind, batch, mode, bandwidth, matrix, gaps, out):
-        rb = self.upload(kind, batch, mode, bandwidth, matrix, gaps, want_cigar=True)
-        try:
-            rb.run()
-            r = rb.fetch_dense(out=out)
-            self.last_timing = self.timing()
-            return r
-        finally:
-            rb.free()
+        """ONE C-ABI call (bsb200_pairwise_batch_dense): host buffers in, results + dense pair-ordered cigars out."""
+        m = np.ascontiguousarray(matrix if matrix is not None else np.zeros(16), dtype=np.int8)
+        res, cg, off, ncg, st = out if out is not None else _alloc_out(batch, True)
+        total = ctypes.c_uint64(0)
+        rc = self._lib.bsb200_pairwise_batch_dense(self._h, 0 if kind == "epi8" else 1, batch.n, _ptr(batch.seqs), _ptr(batch.qoff), _ptr(batch.qlen),
+                                                   _ptr(batch.toff), _ptr(batch.tlen), int(mode), int(bandwidth), _ptr(m), gaps[0], gaps[1], gaps[2], gaps[3],
+                                                   _ptr(res), _ptr(cg), 0 if cg is None else cg.size, ctypes.byref(total), _ptr(ncg), _ptr(st))
+        self._check(rc, "bsb200_pairwise_batch_dense")
+        self.last_timing = self.timing()
+        doff = np.zeros(len(ncg) + 1, dtype=np.uint64)
+        np.cumsum(ncg, out=doff[1:])
+        return BatchResult(res, cg, doff, ncg, st)
 
     def edit_batch(self, batch, mode, bandwidth, want_cigar=True, out=None, dense=False):
         if dense:
@@ -223,6 +248,84 @@ def pack_pairs(batch, idx, out_seqs=None, nthreads=8):
     pb = PairBatch.__new__(PairBatch)
     pb.seqs, pb.qoff, pb.qlen, pb.toff, pb.tlen = out_seqs[:max(nbytes, 1)], qoff, np.ascontiguousarray(batch.qlen[i64]), toff, np.ascontiguousarray(batch.tlen[i64])
     return pb, nbytes
+
+
+def pairwise_batch_ptrs(ctx, kind, queries, targets, mode, bandwidth, matrix=None, gaps=(0, 0, 0, 0), nthreads=4):
+    """bsb200_pairwise_batch_ptrs: one numpy array per sequence (one pointer each, like the reference's callers).  Returns (results, list of cigars, status)."""
+    L = lib()
+    n = len(queries)
+    qs = [np.ascontiguousarray(x, dtype=np.uint8) for x in queries]
+    ts = [np.ascontiguousarray(x, dtype=np.uint8) for x in targets]
+    qp = (ctypes.c_void_p * n)(*[x.ctypes.data for x in qs])
+    tp = (ctypes.c_void_p * n)(*[x.ctypes.data for x in ts])
+    ql = np.array([len(x) for x in qs], np.uint32); tl = np.array([len(x) for x in ts], np.uint32)
+    cgs = [np.zeros(int(a) + int(b) + 2, np.uint32) for a, b in zip(ql, tl)]
+    cp = (ctypes.c_void_p * n)(*[x.ctypes.data for x in cgs])
+    res = np.zeros((n, 10), np.int32); ncg = np.zeros(n, np.uint32); st = np.zeros(n, np.int32)
+    m = np.ascontiguousarray(matrix if matrix is not None else np.zeros(16), dtype=np.int8)
+    rc = L.bsb200_pairwise_batch_ptrs(ctx._h, 0 if kind == "epi8" else 1, n, qp, _ptr(ql), tp, _ptr(tl), int(mode), int(bandwidth), _ptr(m),
+                                      gaps[0], gaps[1], gaps[2], gaps[3], _ptr(res), cp, _ptr(ncg), _ptr(st), int(nthreads))
+    ctx._check(rc, "bsb200_pairwise_batch_ptrs")
+    return res, [c[:int(k)] for c, k in zip(cgs, ncg)], st
+
+
+def pairwise_batch_multi(ctxs, kind, batch, mode, bandwidth, matrix=None, gaps=(0, 0, 0, 0)):
+    """bsb200_pairwise_batch_multi: every context's GPU from this one process."""
+    L = lib()
+    hs = (ctypes.c_void_p * len(ctxs))(*[c._h for c in ctxs])
+    m = np.ascontiguousarray(matrix if matrix is not None else np.zeros(16), dtype=np.int8)
+    res, cg, off, ncg, st = _alloc_out(batch, True)
+    rc = L.bsb200_pairwise_batch_multi(hs, len(ctxs), 0 if kind == "epi8" else 1, batch.n, _ptr(batch.seqs), _ptr(batch.qoff), _ptr(batch.qlen), _ptr(batch.toff), _ptr(batch.tlen),
+                                       int(mode), int(bandwidth), _ptr(m), gaps[0], gaps[1], gaps[2], gaps[3], _ptr(res), _ptr(cg), _ptr(off), _ptr(ncg), _ptr(st))
+    if rc != 0:
+        raise RuntimeError("bsb200_pairwise_batch_multi failed: " + "; ".join(L.bsb200_last_error(c._h).decode() for c in ctxs))
+    return BatchResult(res, cg, off, ncg, st)
+
+
+class SeqFile:
+    """bsb200_seqfile_read: FASTA / FASTQ (plain or .gz) into the reference's BaseBank words (readseq_filereader + seq2basebank)."""
+
+    def __init__(self, path):
+        L = lib()
+        h = L.bsb200_seqfile_read(os.fsencode(path))
+        err = L.bsb200_seqfile_error(h).decode()
+        if err:
+            L.bsb200_seqfile_free(h)
+            raise IOError(err)
+        n = int(L.bsb200_seqfile_nseq(h))
+        self.nbases = int(L.bsb200_seqfile_nbases(h))
+        nw = (self.nbases + 31) // 32 + 1
+        self.bits = np.ctypeslib.as_array(ctypes.cast(L.bsb200_seqfile_bits(h), ctypes.POINTER(ctypes.c_uint64)), shape=(nw,)).copy()
+        self.off = np.ctypeslib.as_array(ctypes.cast(L.bsb200_seqfile_offsets(h), ctypes.POINTER(ctypes.c_uint64)), shape=(max(n, 1),))[:n].copy()
+        self.len = np.ctypeslib.as_array(ctypes.cast(L.bsb200_seqfile_lengths(h), ctypes.POINTER(ctypes.c_uint32)), shape=(max(n, 1),))[:n].copy()
+        self.names = [L.bsb200_seqfile_name(h, i).decode() for i in range(n)]
+        L.bsb200_seqfile_free(h)
+
+    def bases(self, i):
+        idx = np.arange(int(self.off[i]), int(self.off[i]) + int(self.len[i]), dtype=np.uint64)
+        return ((self.bits[(idx >> np.uint64(5)).astype(np.int64)] >> (((~idx) & np.uint64(31)) << np.uint64(1))) & np.uint64(3)).astype(np.uint8)
+
+    def pairs(self):
+        """Consecutive records as a PairBatch whose offsets are BASE offsets into self.bits (for Context.upload_bits)."""
+        n = len(self.len) // 2
+        pb = PairBatch.__new__(PairBatch)
+        pb.seqs = None
+        pb.qoff, pb.toff = np.ascontiguousarray(self.off[0:2 * n:2]), np.ascontiguousarray(self.off[1:2 * n:2])
+        pb.qlen, pb.tlen = np.ascontiguousarray(self.len[0:2 * n:2]), np.ascontiguousarray(self.len[1:2 * n:2])
+        return pb
+
+
+def format_pair_text(sf, k, result, cigar):
+    """The text `bsalign align` / `bsalign edit` print for pair k of a SeqFile (records 2k, 2k+1)."""
+    L = lib()
+    rs = np.ascontiguousarray(result, dtype=np.int32)
+    cg = np.ascontiguousarray(cigar, dtype=np.uint32)
+    args = (sf.names[2 * k].encode(), int(sf.len[2 * k]), sf.names[2 * k + 1].encode(), int(sf.len[2 * k + 1]), _ptr(rs), _ptr(sf.bits),
+            int(sf.off[2 * k]), int(sf.off[2 * k + 1]), _ptr(cg), len(cg))
+    need = int(L.bsb200_format_pair_text(None, 0, *args))
+    buf = ctypes.create_string_buffer(need + 1)
+    L.bsb200_format_pair_text(buf, need, *args)
+    return buf.raw[:need]
 
 
 def pack_bits(seqs):

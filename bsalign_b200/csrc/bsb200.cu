@@ -1049,6 +1049,105 @@ extern "C" int bsb200_edit_pairwise_batch(bsb200_ctx *ctx, uint64_t n, const uin
 	return run_whole(ctx, 1, n, seqs, qoff, qlen, toff, tlen, mode, bandwidth, nullptr, 0, 0, 0, 0, results, cigars, cgoff, ncigar, status);
 }
 
+// ---- one call, dense pair-ordered cigars (the fast path of the staged form as ONE ABI function) ---------------------------------
+extern "C" int bsb200_pairwise_batch_dense(bsb200_ctx *ctx, int kind, uint64_t n, const uint8_t *seqs,
+		const uint64_t *qoff, const uint32_t *qlen, const uint64_t *toff, const uint32_t *tlen,
+		int mode, uint32_t bandwidth, const int8_t matrix[16], int8_t go1, int8_t ge1, int8_t go2, int8_t ge2,
+		bsb200_result_t *results, uint32_t *cigars, uint64_t cigar_cap_words, uint64_t *total_words, uint32_t *ncigar, int32_t *status){
+	if(!ctx) return -1;
+	bsb200_batch *b = bsb200_batch_upload(ctx, kind, n, seqs, qoff, qlen, toff, tlen, mode, bandwidth, matrix, go1, ge1, go2, ge2, cigars != nullptr);
+	if(!b) return -1;
+	int rc = bsb200_batch_run(ctx, b);
+	if(rc == 0) rc = bsb200_batch_fetch_dense(ctx, b, results, cigars, cigar_cap_words, total_words, ncigar, status);
+	bsb200_timing_t tm = ctx->timing;
+	bsb200_batch_free(ctx, b);
+	tm.total_ms = tm.h2d_ms + tm.run_ms + tm.d2h_ms;
+	ctx->timing = tm;
+	return rc;
+}
+
+// ---- one pointer per sequence, as the reference hands them out (bsalign.h:399: u1i *qseq, u1i *tseq per call) -----------------------
+// The pairs are gathered into one pinned arena by `nthreads` host threads and go through the arena entry point.  cigar_out[i] (may be
+// NULL) must have room for qlen[i] + tlen[i] + 2 words.
+extern "C" int bsb200_pairwise_batch_ptrs(bsb200_ctx *ctx, int kind, uint64_t n, const uint8_t *const *q, const uint32_t *qlen,
+		const uint8_t *const *t, const uint32_t *tlen, int mode, uint32_t bandwidth, const int8_t matrix[16],
+		int8_t go1, int8_t ge1, int8_t go2, int8_t ge2, bsb200_result_t *results, uint32_t *const *cigar_out, uint32_t *ncigar, int32_t *status, int nthreads){
+	if(!ctx) return -1;
+	if(n && (!q || !t || !qlen || !tlen)) return fail(ctx, "bsb200_pairwise_batch_ptrs", cudaSuccess);
+	cudaSetDevice(ctx->device);
+	std::vector<uint64_t> qoff(n), toff(n), cgoff(n + 1, 0);
+	uint64_t pos = 0;
+	for(uint64_t i=0;i<n;i++){ qoff[i] = pos; pos += qlen[i]; toff[i] = pos; pos += tlen[i]; cgoff[i + 1] = cgoff[i] + ((qlen[i] && tlen[i]) ? (uint64_t)qlen[i] + tlen[i] + 2 : 0); }
+	HostBuf &arena = ctx->host_cache[6];
+	CK(arena.reserve(pos + 16));
+	uint8_t *dst = arena.as<uint8_t>();
+	if(nthreads < 1) nthreads = 1;
+	auto work = [&](int w){
+		for(uint64_t i=n*w/nthreads;i<n*(w+1)/nthreads;i++){
+			if(qlen[i]) memcpy(dst + qoff[i], q[i], qlen[i]);
+			if(tlen[i]) memcpy(dst + toff[i], t[i], tlen[i]);
+		}
+	};
+	{ std::vector<std::thread> th; for(int w=1;w<nthreads;w++) th.emplace_back(work, w); work(0); for(auto &x : th) x.join(); }
+	const bool want = cigar_out != nullptr;
+	std::vector<uint32_t> cg(want ? cgoff[n] : 0), ncg(n);
+	int rc = run_whole(ctx, kind, n, dst, qoff.data(), qlen, toff.data(), tlen, mode, bandwidth, matrix, go1, ge1, go2, ge2,
+		results, want ? cg.data() : nullptr, want ? cgoff.data() : nullptr, ncg.data(), status);
+	if(rc) return rc;
+	if(ncigar) memcpy(ncigar, ncg.data(), n * 4);
+	if(want) for(uint64_t i=0;i<n;i++) if(cigar_out[i] && ncg[i]) memcpy(cigar_out[i], cg.data() + cgoff[i], (size_t)ncg[i] * 4);
+	return 0;
+}
+
+// ---- every GPU of the box from ONE process (the reference is a single-process C library): one context per device, the batch cut
+// into shards of equal DP cells (heaviest first, dealt in snake order), one host thread per device packs its shard's compact arena
+// and runs it through the arena entry point; results land in the caller's arrays at the pairs' own indices ------------------------
+extern "C" int bsb200_pairwise_batch_multi(bsb200_ctx *const *ctxs, int nctx, int kind, uint64_t n, const uint8_t *seqs,
+		const uint64_t *qoff, const uint32_t *qlen, const uint64_t *toff, const uint32_t *tlen,
+		int mode, uint32_t bandwidth, const int8_t matrix[16], int8_t go1, int8_t ge1, int8_t go2, int8_t ge2,
+		bsb200_result_t *results, uint32_t *cigars, const uint64_t *cgoff, uint32_t *ncigar, int32_t *status){
+	if(!ctxs || nctx < 1) return -1;
+	for(int d=0;d<nctx;d++) if(!ctxs[d]) return -1;
+	if(nctx == 1) return run_whole(ctxs[0], kind, n, seqs, qoff, qlen, toff, tlen, mode, bandwidth, matrix, go1, ge1, go2, ge2, results, cigars, cgoff, ncigar, status);
+	// balanced partition (the same rule as bsalign_b200/shard.py: nominal band cells, heaviest first, snake order)
+	std::vector<std::pair<uint64_t, uint64_t>> wk(n);
+	for(uint64_t i=0;i<n;i++){
+		const uint64_t bw = kind == 0 ? bsb200_epi8_bandwidth(qlen[i], bandwidth) : edit_bandwidth(qlen[i], tlen[i], mode, bandwidth);
+		wk[i] = std::make_pair(~(bw * (uint64_t)tlen[i]), i);
+	}
+	std::sort(wk.begin(), wk.end());
+	std::vector<std::vector<uint64_t>> part(nctx);
+	for(uint64_t k=0;k<n;k++){ const uint64_t rnd = k / nctx, c = k % nctx; part[(rnd & 1) ? nctx - 1 - c : c].push_back(wk[k].second); }
+	std::vector<int> rcs(nctx, 0);
+	auto work = [&](int d){
+		std::vector<uint64_t> &idx = part[d];
+		std::sort(idx.begin(), idx.end());
+		const uint64_t m = idx.size();
+		std::vector<uint64_t> sq(m), st_(m), scg(m + 1, 0);
+		std::vector<uint32_t> sql(m), stl(m), sncg(m);
+		std::vector<int32_t> sst(m);
+		std::vector<bsb200_result_t> sres(m);
+		const uint64_t bytes = bsb200_pack_pairs(seqs, qoff, qlen, toff, tlen, idx.data(), m, nullptr, nullptr, nullptr, 1);
+		std::vector<uint8_t> arena(bytes + 16);
+		bsb200_pack_pairs(seqs, qoff, qlen, toff, tlen, idx.data(), m, arena.data(), sq.data(), st_.data(), 2);
+		for(uint64_t k=0;k<m;k++){ sql[k] = qlen[idx[k]]; stl[k] = tlen[idx[k]]; scg[k + 1] = scg[k] + ((cigars && cgoff) ? cgoff[idx[k] + 1] - cgoff[idx[k]] : 0); }
+		std::vector<uint32_t> scig((cigars && cgoff) ? scg[m] : 0);
+		rcs[d] = run_whole(ctxs[d], kind, m, arena.data(), sq.data(), sql.data(), st_.data(), stl.data(), mode, bandwidth, matrix, go1, ge1, go2, ge2,
+			sres.data(), (cigars && cgoff) ? scig.data() : nullptr, (cigars && cgoff) ? scg.data() : nullptr, sncg.data(), sst.data());
+		if(rcs[d]) return;
+		for(uint64_t k=0;k<m;k++){
+			const uint64_t i = idx[k];
+			if(results) results[i] = sres[k];
+			if(ncigar) ncigar[i] = sncg[k];
+			if(status) status[i] = sst[k];
+			if(cigars && cgoff){ const uint64_t c = std::min<uint64_t>(sncg[k], scg[k + 1] - scg[k]); if(c) memcpy(cigars + cgoff[i], scig.data() + scg[k], c * 4); }
+		}
+	};
+	{ std::vector<std::thread> th; for(int d=1;d<nctx;d++) th.emplace_back(work, d); work(0); for(auto &x : th) x.join(); }
+	for(int d=0;d<nctx;d++) if(rcs[d]) return rcs[d];
+	return 0;
+}
+
 static int run_single(bsb200_ctx *ctx, int kind, const uint8_t *qseq, uint32_t qlen, const uint8_t *tseq, uint32_t tlen,
 		int mode, uint32_t bandwidth, const int8_t *matrix, int8_t go1, int8_t ge1, int8_t go2, int8_t ge2,
 		bsb200_result_t *result, uint32_t *cigar, uint32_t cigar_cap, uint32_t *ncigar, int32_t *status){
@@ -1089,6 +1188,9 @@ extern "C" int64_t bsb200_debug_trace(bsb200_ctx *ctx, bsb200_batch *b, uint64_t
 	if(ubias_out) *ubias_out = (b->pw >= 1 && b->ge1 <= 0 && (int8_t)(b->go1 + b->ge1) <= 0 && (b->pw < 2 || (b->ge2 <= 0 && (int8_t)(b->go2 + b->ge2) <= 0))) ? 128 : 0;
 	return (int64_t)bytes;
 }
+
+// ---- ingest / egress ---------------------------------------------------------------------------------------------
+#include "io_host.cuh"
 
 // ---- POA read-vs-graph sweep (bspoa.h:2515-2618) ---------------------------------------------------------------
 #include "poa_host.cuh"

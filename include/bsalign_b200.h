@@ -99,6 +99,25 @@ int bsb200_edit_pairwise(bsb200_ctx *ctx, const uint8_t *qseq, uint32_t qlen, co
 		int mode, uint32_t bandwidth,
 		bsb200_result_t *result, uint32_t *cigar, uint32_t cigar_cap, uint32_t *ncigar, int32_t *status);
 
+/* ---- more shapes of the same call (kind: 0 = epi8, 1 = edit; matrix / gaps ignored for kind 1) ------------------------------------ */
+/* one call, cigars DENSE and in pair order (pair i starts at word sum(ncigar[0..i-1]); see bsb200_batch_fetch_dense): the fast path */
+int bsb200_pairwise_batch_dense(bsb200_ctx *ctx, int kind, uint64_t n, const uint8_t *seqs,
+		const uint64_t *qoff, const uint32_t *qlen, const uint64_t *toff, const uint32_t *tlen,
+		int mode, uint32_t bandwidth, const int8_t matrix[16], int8_t gapo1, int8_t gape1, int8_t gapo2, int8_t gape2,
+		bsb200_result_t *results, uint32_t *cigars, uint64_t cigar_cap_words, uint64_t *total_words, uint32_t *ncigar, int32_t *status);
+/* one POINTER per sequence, the way the reference's callers hold them (bsalign.h:399 takes u1i *qseq, u1i *tseq per call); gathered into
+ * one pinned arena by `nthreads` host threads.  cigar_out (may be NULL) holds one pointer per pair (entries may be NULL) with room for
+ * qlen[i] + tlen[i] + 2 words. */
+int bsb200_pairwise_batch_ptrs(bsb200_ctx *ctx, int kind, uint64_t n, const uint8_t *const *q, const uint32_t *qlen,
+		const uint8_t *const *t, const uint32_t *tlen, int mode, uint32_t bandwidth, const int8_t matrix[16],
+		int8_t gapo1, int8_t gape1, int8_t gapo2, int8_t gape2, bsb200_result_t *results, uint32_t *const *cigar_out, uint32_t *ncigar, int32_t *status, int nthreads);
+/* every GPU of the box from ONE process: ctxs[d] = bsb200_create(d, 0).  The batch is cut into shards of equal DP cells, one host thread
+ * per device packs and runs its shard; same arguments and results as bsb200_epi8_pairwise_batch / bsb200_edit_pairwise_batch. */
+int bsb200_pairwise_batch_multi(bsb200_ctx *const *ctxs, int nctx, int kind, uint64_t n, const uint8_t *seqs,
+		const uint64_t *qoff, const uint32_t *qlen, const uint64_t *toff, const uint32_t *tlen,
+		int mode, uint32_t bandwidth, const int8_t matrix[16], int8_t gapo1, int8_t gape1, int8_t gapo2, int8_t gape2,
+		bsb200_result_t *results, uint32_t *cigars, const uint64_t *cgoff, uint32_t *ncigar, int32_t *status);
+
 /* ---- staged form (inputs resident in HBM): upload once, run the kernels many times, fetch ---------- */
 typedef struct bsb200_batch bsb200_batch;
 /* kind: 0 = epi8, 1 = edit.  matrix/gaps are ignored for kind 1. */
@@ -144,6 +163,32 @@ int bsb200_batch_fetch_dense_dev(bsb200_ctx *ctx, bsb200_batch *b, int32_t *d_re
 uint64_t bsb200_pack_pairs(const uint8_t *seqs, const uint64_t *qoff, const uint32_t *qlen, const uint64_t *toff, const uint32_t *tlen,
 		const uint64_t *idx, uint64_t m, uint8_t *out_seqs, uint64_t *out_qoff, uint64_t *out_toff, int nthreads);
 void bsb200_scatter_words(uint32_t *dst, const uint64_t *dst_off, const uint32_t *src, const uint64_t *src_off, const uint32_t *len, uint64_t m, int nthreads);
+
+/* ---- ingest / egress next to the path (host code): sequence files into BaseBank words, and the command line's text ------------------ */
+/* readseq_filereader (filereader.h:609) + seq2basebank (dna.h:653-671): FASTA / FASTQ, plain or .gz; tag = header up to the first blank;
+ * every base becomes base_bit_table[c] & 3 (non-ACGT -> A), first base of a word in its top two bits; empty records are dropped like
+ * main.c:312 does.  Check bsb200_seqfile_error ("" = fine). */
+typedef struct bsb200_seqfile bsb200_seqfile;
+bsb200_seqfile *bsb200_seqfile_read(const char *path);
+const char *bsb200_seqfile_error(const bsb200_seqfile *sf);
+uint64_t bsb200_seqfile_nseq(const bsb200_seqfile *sf);
+uint64_t bsb200_seqfile_nbases(const bsb200_seqfile *sf);
+const uint64_t *bsb200_seqfile_bits(const bsb200_seqfile *sf);       /* BaseBank words (+ one spare word) */
+const uint64_t *bsb200_seqfile_offsets(const bsb200_seqfile *sf);    /* base offset of every record */
+const uint32_t *bsb200_seqfile_lengths(const bsb200_seqfile *sf);
+const char *bsb200_seqfile_name(const bsb200_seqfile *sf, uint64_t i);
+void bsb200_seqfile_free(bsb200_seqfile *sf);
+/* seqalign_cigar2alnstr (bsalign.h:531-582) on BaseBank words: query row, target row, match row ('|' '*' '-'); each needs length + 1 bytes */
+uint32_t bsb200_cigar2alnstr(const uint64_t *bits, uint64_t qoff, uint64_t toff, const bsb200_result_t *rs, const uint32_t *cigar, uint32_t ncigar,
+		char *qrow, char *trow, char *mrow, uint32_t length);
+/* the text `bsalign align` / `bsalign edit` print for one pair (main.c:346-347 / 226-228 + the three rows; nothing when rs->mat == 0);
+ * returns the bytes needed, writes them when they fit cap */
+uint64_t bsb200_format_pair_text(char *out, uint64_t cap, const char *qname, uint32_t qlen, const char *tname, uint32_t tlen, const bsb200_result_t *rs,
+		const uint64_t *bits, uint64_t qoff, uint64_t toff, const uint32_t *cigar, uint32_t ncigar);
+/* the whole command: consecutive records of `path` are pairs (main.c:314), aligned in batches through bsb200_batch_upload_bits; the
+ * reference's text goes to `out` (a FILE*) in input order.  Returns the number of pairs, or -1. */
+int64_t bsb200_align_file(bsb200_ctx *ctx, int kind, const char *path, int mode, uint32_t bandwidth, const int8_t matrix[16],
+		int8_t gapo1, int8_t gape1, int8_t gapo2, int8_t gape2, void *out /* FILE* */, uint64_t batch_pairs /* 0 = 1M */);
 
 /* ---- POA read-vs-graph banded DP sweep: replaces align_rd_bspoacore (bspoa.h:2515-2618) -------------------- */
 /*

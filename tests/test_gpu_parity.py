@@ -323,3 +323,62 @@ def test_pairwise_compat_header_runs_against_reference():
         assert out.returncode == 0, out.stdout + out.stderr
         n = 2 * int(args[0])
         assert "identical=%d/%d" % (n, n) in out.stdout and "flagged_calls=0" not in out.stdout, out.stdout
+
+
+def test_packed_2bit_upload_equals_byte_upload(ctx):
+    """bsb200_batch_upload_bits: sequences in the reference's BaseBank word layout (dna.h:63), unpacked on the device."""
+    for kind, n, qlen, mode, bw in (("epi8", 97, 333, 0, 0), ("epi8", 50, 1001, 1, 64), ("edit", 300, 300, 0, 64)):
+        b = synth.make_pairs(n, qlen, seed=qlen + n)
+        bits = api.pack_bits(b.seqs)
+        # spot-check the layout against the reference's accessor: base i = bits[i >> 5] >> (((~i) & 31) << 1) & 3
+        for i in (0, 1, 31, 32, 33, len(b.seqs) - 1):
+            assert (int(bits[i >> 5]) >> (((~i) & 31) << 1)) & 3 == int(b.seqs[i])
+        rb = ctx.upload_bits(kind, bits, b, mode, bw, M26, (-3, -2, 0, 0))
+        rb.run()
+        got = rb.fetch()
+        rb.free()
+        exp, ecg, _ = ck.oracle_batch(kind, b, mode, bw, M26, (-3, -2, 0, 0), nthreads=8)
+        assert_same(got, exp, ecg, tag=("bits", kind, mode, bw))
+
+
+def test_pointer_array_and_multi_device_entries(ctx):
+    """bsb200_pairwise_batch_ptrs (one pointer per sequence, the reference's calling convention) and bsb200_pairwise_batch_multi (every
+    GPU of the box from one process; one context twice when the box has a single GPU) give the arena entry point's answers."""
+    import torch
+    b = synth.make_pairs(120, 350, seed=21)
+    exp, ecg, _ = ck.oracle_batch("epi8", b, 1, 64, M26, (-3, -2, 0, 0), nthreads=8)
+    res, cgs, st = api.pairwise_batch_ptrs(ctx, "epi8", [b.query(i) for i in range(b.n)], [b.target(i) for i in range(b.n)], 1, 64, M26, (-3, -2, 0, 0))
+    assert np.array_equal(res, exp) and not st.any() and all(np.array_equal(x, y) for x, y in zip(cgs, ecg))
+    ndev = min(2, torch.cuda.device_count())
+    ctxs = [ctx] + [api.Context(d) for d in range(1, ndev)]
+    if len(ctxs) == 1:
+        ctxs.append(api.Context(0))   # two contexts on the one device: still the multi-context code path
+    for kind, mode, bw in (("epi8", 0, 0), ("edit", 0, 64)):
+        exp, ecg, _ = ck.oracle_batch(kind, b, mode, bw, M26, (-3, -2, 0, 0), nthreads=8)
+        assert_same(api.pairwise_batch_multi(ctxs, kind, b, mode, bw, M26, (-3, -2, 0, 0)), exp, ecg, tag=("multi", kind))
+    for c in ctxs[1:]:
+        c.close()
+
+
+def test_command_line_text_equals_reference_on_real_example(tmp_path):
+    """The whole command, files in, text out: bsalign_b200_cli (tools/bsalign_b200_cli.c -> bsb200_align_file: reader, BaseBank words, GPU
+    batches, formatter) on the reference's own example under the three configurations of example/run.sh prints byte for byte what the
+    reference prints (md5 + size of 31 MB of text each: tests/golden/real_ont_cli.json, equal to BASELINE.md's fingerprints)."""
+    import hashlib
+    import json
+    import subprocess
+    import real_ont
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    exe = os.path.join(root, "bsalign_b200", "bsalign_b200_cli")
+    if not os.path.exists(exe):
+        pytest.skip("bsalign_b200/bsalign_b200_cli not built (python __graft_entry__.py build)")
+    gold = json.load(open(os.path.join(root, "tests", "golden", "real_ont_cli.json")))
+    batch, _, _, _ = real_ont.load()
+    fa = tmp_path / "real_ont.fa"
+    with open(fa, "w") as f:
+        for i in range(batch.n):
+            f.write(">%d.1\n%s\n>%d.2\n%s\n" % (i, "".join("ACGT"[c] for c in batch.query(i)), i, "".join("ACGT"[c] for c in batch.target(i))))
+    for name, g in gold.items():
+        out = subprocess.run([exe] + g["args"] + [str(fa)], capture_output=True, timeout=600)
+        assert out.returncode == 0, out.stderr.decode()
+        assert len(out.stdout) == g["bytes"] and hashlib.md5(out.stdout).hexdigest() == g["md5"], name
