@@ -223,7 +223,89 @@ static inline int b200_align_rd_bspoacore(bsb200_ctx *ctx, BSPOA *g, BSPOAPar *p
 	return scr;
 }
 
-/* end_bspoa (bspoa.h:4722-4778) for n objects in lock-step; the read-vs-graph sweeps of one round are one GPU batch */
+/* end_bspoa (bspoa.h:4722-4778) for n objects in lock-step; the read-vs-graph sweeps of one round are one GPU batch.  The host work
+ * around the sweeps (graph surgery, msa, consensus, re-alignment: the reference's own code) is per object and independent: compiled
+ * b200_poa_host_threads sets how many host threads share it (one per in-flight object). */
+#include <pthread.h>
+#include <unistd.h>
+typedef struct {
+	bsb200_ctx *ctx; BSPOA **gs; u4i n, *nheads, *ntails, *slot; u2i rid; b200_poa_pack_t *p;
+	int phase; volatile u4i next;
+} b200_poa_round_t;
+
+static inline void b200_poa_round_object(b200_poa_round_t *r, u4i k){
+	BSPOA *g = r->gs[k];
+	u2i rid = r->rid;
+	if(r->phase == 0){   /* before the sweep: bspoa.h:4753-4755 and the head of align_rd_bspoa (bspoa.h:2620-2642) */
+		u4i rlen; u2i ridxbeg, ridxend;
+		r->slot[k] = MAX_U4;
+		if(g->seqs->nseq <= 1 || rid >= g->nmsa) return;
+		if(!g->par->refmode && g->par->bwtrigger){ msa_bspoa(g); simple_cns_bspoa(g); }
+		rlen = g->seqs->rdlens->buffer[rid];
+		clear_u8v(g->todels);
+		if(rlen == 0){ g->nrds ++; return; }
+		r->nheads[k] = get_rdnode_bspoa(g, rid, -1)->header;
+		r->ntails[k] = get_rdnode_bspoa(g, rid, rlen)->header;
+		if(g->par->nrec){ ridxbeg = num_max(0, Int(rid) - g->par->nrec - 1); ridxend = rid; } else { ridxbeg = 0; ridxend = MAX_U2; }
+		sel_nodes_bspoa(g, r->nheads[k], r->ntails[k], ridxbeg, ridxend);
+		prepare_rd_align_bspoa(g, g->par, r->nheads[k], r->ntails[k], rid, 0, rlen);
+		if(g->sels->size == 0){ align_rd_bspoacore(g, g->par, rid, r->nheads[k], r->ntails[k]); r->slot[k] = MAX_U4 - 1; return; }
+		r->slot[k] = MAX_U4 - 2;   /* takes part in this round's batch */
+	} else if(r->phase == 1){   /* behind the sweep: the tail of align_rd_bspoa (bspoa.h:2652-2666) */
+		u4i t;
+		if(r->slot[k] == MAX_U4) return;
+#ifdef BSALIGN_B200_POA_HOST_TRACEBACK
+		if(r->slot[k] != MAX_U4 - 1) b200_poa_pack_take(r->p, r->slot[k], g);
+		alignment2graph_bspoa(g, g->par, rid, 0, r->nheads[k], r->ntails[k], g->maxidx, g->maxoff, NULL);
+#else
+		if(r->slot[k] != MAX_U4 - 1) b200_poa_pack_replay(r->p, r->slot[k], g, rid, 0, r->nheads[k], r->ntails[k]);
+		else alignment2graph_bspoa(g, g->par, rid, 0, r->nheads[k], r->ntails[k], g->maxidx, g->maxoff, NULL);
+#endif
+		for(t=0;t<g->todels->size;t++){
+			chg_edge_bspoa(g, ref_bspoanodev(g->nodes, g->todels->buffer[t] >> 32), ref_bspoanodev(g->nodes, g->todels->buffer[t] & MAX_U4), -1, NULL);
+		}
+		clear_u8v(g->todels);
+		g->nrds ++;
+	} else {   /* bspoa.h:4764-4777: the reference's own code, unchanged */
+		int i;
+		if(g->seqs->nseq <= 1) return;
+		for(i=0;i<g->par->realn;i++){
+			msa_bspoa(g);
+			cns_bspoa(g);
+			if(g->par->editbw < 0) remsa_edits_bspoa(g, - g->par->editbw);
+			else remsa_pedits_bspoa(g, g->par->editbw / 2, 1, (i + 1 == g->par->realn));
+		}
+		if(g->par->shuffle) restore_rd_orders_bspoa(g);
+		msa_bspoa(g);
+		cns_bspoa(g);
+	}
+}
+
+static void *b200_poa_round_worker(void *arg){
+	b200_poa_round_t *r = (b200_poa_round_t*)arg;
+	while(1){
+		u4i k = __sync_fetch_and_add(&r->next, 1);
+		if(k >= r->n) break;
+		b200_poa_round_object(r, k);
+	}
+	return NULL;
+}
+
+/* objects are independent between the sweeps: one host thread per in-flight object, up to b200_poa_host_threads (0: all cores; 1: serial) */
+static int b200_poa_host_threads = 1;
+static inline void b200_poa_round_run(b200_poa_round_t *r, int phase){
+	long nt = b200_poa_host_threads > 0 ? b200_poa_host_threads : sysconf(_SC_NPROCESSORS_ONLN);
+	pthread_t th[256];
+	long t;
+	r->phase = phase; r->next = 0;
+	if(nt > (long)r->n) nt = r->n;
+	if(nt > 256) nt = 256;
+	if(nt <= 1){ b200_poa_round_worker(r); return; }
+	for(t=1;t<nt;t++) pthread_create(&th[t], NULL, b200_poa_round_worker, r);
+	b200_poa_round_worker(r);
+	for(t=1;t<nt;t++) pthread_join(th[t], NULL);
+}
+
 static inline void b200_end_bspoa_batch(bsb200_ctx *ctx, BSPOA **gs, u4i n){
 	b200_poa_pack_t *p = b200_poa_pack_init();
 	u4i k, maxr = 0, *nheads, *ntails, *slot;
@@ -245,61 +327,27 @@ static inline void b200_end_bspoa_batch(bsb200_ctx *ctx, BSPOA **gs, u4i n){
 		g->nrds = 1;
 		if(g->nmsa > maxr) maxr = g->nmsa;
 	}
-	for(rid=1;rid<maxr;rid++){   /* bspoa.h:4752-4763 with align_rd_bspoa (bspoa.h:2620-2667) split around the sweep */
-		b200_poa_pack_clear(p);
-		for(k=0;k<n;k++){
-			BSPOA *g = gs[k];
-			u4i rlen; u2i ridxbeg, ridxend;
-			slot[k] = MAX_U4;
-			if(g->seqs->nseq <= 1 || rid >= g->nmsa) continue;
-			if(!g->par->refmode && g->par->bwtrigger){ msa_bspoa(g); simple_cns_bspoa(g); }
-			rlen = g->seqs->rdlens->buffer[rid];
-			clear_u8v(g->todels);
-			if(rlen == 0){ g->nrds ++; continue; }
-			nheads[k] = get_rdnode_bspoa(g, rid, -1)->header;
-			ntails[k] = get_rdnode_bspoa(g, rid, rlen)->header;
-			if(g->par->nrec){ ridxbeg = num_max(0, Int(rid) - g->par->nrec - 1); ridxend = rid; } else { ridxbeg = 0; ridxend = MAX_U2; }
-			sel_nodes_bspoa(g, nheads[k], ntails[k], ridxbeg, ridxend);
-			prepare_rd_align_bspoa(g, g->par, nheads[k], ntails[k], rid, 0, rlen);
-			if(g->sels->size == 0){ align_rd_bspoacore(g, g->par, rid, nheads[k], ntails[k]); slot[k] = MAX_U4 - 1; continue; }
-			slot[k] = p->njobs;
-			b200_poa_pack_job(p, g, g->par, nheads[k], ntails[k]);
-		}
-#ifdef BSALIGN_B200_POA_HOST_TRACEBACK
-		b200_poa_pack_run(ctx, p);
-#else
-		b200_poa_pack_run_walk(ctx, p);
-#endif
-		for(k=0;k<n;k++){
-			BSPOA *g = gs[k];
-			u4i t;
-			if(slot[k] == MAX_U4) continue;
-#ifdef BSALIGN_B200_POA_HOST_TRACEBACK
-			if(slot[k] != MAX_U4 - 1) b200_poa_pack_take(p, slot[k], g);
-			alignment2graph_bspoa(g, g->par, rid, 0, nheads[k], ntails[k], g->maxidx, g->maxoff, NULL);
-#else
-			if(slot[k] != MAX_U4 - 1) b200_poa_pack_replay(p, slot[k], g, rid, 0, nheads[k], ntails[k]);
-			else alignment2graph_bspoa(g, g->par, rid, 0, nheads[k], ntails[k], g->maxidx, g->maxoff, NULL);
-#endif
-			for(t=0;t<g->todels->size;t++){
-				chg_edge_bspoa(g, ref_bspoanodev(g->nodes, g->todels->buffer[t] >> 32), ref_bspoanodev(g->nodes, g->todels->buffer[t] & MAX_U4), -1, NULL);
+	{
+		b200_poa_round_t rd;
+		rd.ctx = ctx; rd.gs = gs; rd.n = n; rd.nheads = nheads; rd.ntails = ntails; rd.slot = slot; rd.p = p;
+		for(rid=1;rid<maxr;rid++){   /* bspoa.h:4752-4763 with align_rd_bspoa (bspoa.h:2620-2667) split around the sweep */
+			b200_poa_pack_clear(p);
+			rd.rid = rid;
+			b200_poa_round_run(&rd, 0);
+			for(k=0;k<n;k++){   /* the batch is packed in object order */
+				if(slot[k] != MAX_U4 - 2) continue;
+				slot[k] = p->njobs;
+				b200_poa_pack_job(p, gs[k], gs[k]->par, nheads[k], ntails[k]);
 			}
-			clear_u8v(g->todels);
-			g->nrds ++;
+#ifdef BSALIGN_B200_POA_HOST_TRACEBACK
+			b200_poa_pack_run(ctx, p);
+#else
+			b200_poa_pack_run_walk(ctx, p);
+#endif
+			b200_poa_round_run(&rd, 1);
 		}
-	}
-	for(k=0;k<n;k++){   /* bspoa.h:4764-4777: the reference's own code, unchanged */
-		BSPOA *g = gs[k];
-		if(g->seqs->nseq <= 1) continue;
-		for(i=0;i<g->par->realn;i++){
-			msa_bspoa(g);
-			cns_bspoa(g);
-			if(g->par->editbw < 0) remsa_edits_bspoa(g, - g->par->editbw);
-			else remsa_pedits_bspoa(g, g->par->editbw / 2, 1, (i + 1 == g->par->realn));
-		}
-		if(g->par->shuffle) restore_rd_orders_bspoa(g);
-		msa_bspoa(g);
-		cns_bspoa(g);
+		rd.rid = 0;
+		b200_poa_round_run(&rd, 2);
 	}
 	free(nheads); free(ntails); free(slot);
 	b200_poa_pack_free(p);

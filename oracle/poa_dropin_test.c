@@ -6,7 +6,7 @@
  *   (a) the reference's own end_bspoa (bspoa.h:4722), and
  *   (b) b200_end_bspoa_batch: all BSPOA objects in lock-step, every read-vs-graph sweep on the GPU (libbsalign_b200.so),
  * and the consensus, its qualities, the alternative bases and the whole MSA matrix must be byte-identical.
- * Usage: poa_dropin <jobs> <reads per job> <template length> <seed> [realn]
+ * Usage: poa_dropin <jobs> <reads per job> <template length> <seed> [realn] [host threads, 0 = all cores]
  */
 #include "bspoa.h"
 #include "bsalign_b200_poa_compat.h"
@@ -29,7 +29,11 @@ static u4i mutate(const u1i *tmpl, u4i tlen, u1i *out, double ps, double pi, dou
 	return n;
 }
 
+static volatile u4i ref_next; static u4i ref_n; static BSPOA **ref_jobs;
+static void *ref_worker(void *arg){ while(1){ u4i j = __sync_fetch_and_add(&ref_next, 1); if(j >= ref_n) break; end_bspoa(ref_jobs[j]); } return NULL; }
+
 int main(int argc, char **argv){
+	int nthr;
 	u4i njobs = argc > 1 ? atoi(argv[1]) : 4, nreads = argc > 2 ? atoi(argv[2]) : 16, tlen = argc > 3 ? atoi(argv[3]) : 2000, j, r, bad = 0;
 	BSPOAPar par = DEFAULT_BSPOA_PAR;
 	BSPOA **ga, **gb;
@@ -52,8 +56,19 @@ int main(int argc, char **argv){
 			fwdbitseqpush_bspoa(gb[j], buf, len);
 		}
 	}
+	/* whole-job arm (6th argument = host threads, 0 = all cores): the reference on that many cores (objects are independent), against the
+	   lock-step GPU path with as many host threads sharing the work between the sweeps */
+	nthr = argc > 6 ? atoi(argv[6]) : 1;
+	if(nthr <= 0) nthr = (int)sysconf(_SC_NPROCESSORS_ONLN);
+	b200_poa_host_threads = nthr;
 	t0 = now_s();
-	for(j=0;j<njobs;j++) end_bspoa(ga[j]);
+	if(nthr > 1){
+		pthread_t th[256]; int t; ref_next = 0; ref_n = njobs; ref_jobs = ga;
+		if(nthr > 256) nthr = 256;
+		for(t=1;t<nthr;t++) pthread_create(&th[t], NULL, ref_worker, NULL);
+		ref_worker(NULL);
+		for(t=1;t<nthr;t++) pthread_join(th[t], NULL);
+	} else for(j=0;j<njobs;j++) end_bspoa(ga[j]);
 	t_ref = now_s() - t0;
 	t0 = now_s();
 	b200_end_bspoa_batch(ctx, gb, njobs);
@@ -67,8 +82,10 @@ int main(int argc, char **argv){
 			&& a->msacols->size == b->msacols->size && memcmp(a->msacols->buffer, b->msacols->buffer, a->msacols->size) == 0;
 		if(!same){ bad ++; fprintf(stderr, "job %u: consensus / MSA differ (cns %u vs %u, msa %u vs %u)\n", j, (u4i)a->cns->size, (u4i)b->cns->size, (u4i)a->msacols->size, (u4i)b->msacols->size); }
 	}
-	printf("poa_dropin: jobs=%u reads=%u tlen=%u realn=%d  identical=%u/%u  cns_len[0]=%u msa_bytes[0]=%u  reference_s=%.3f  gpu_lockstep_s=%.3f\n",
-		njobs, nreads, tlen, par.realn, njobs - bad, njobs, (u4i)ga[0]->cns->size, (u4i)ga[0]->msacols->size, t_ref, t_gpu);
+	{
+		printf("poa_dropin: jobs=%u reads=%u tlen=%u realn=%d  identical=%u/%u  cns_len[0]=%u msa_bytes[0]=%u  host_threads=%d  reference_s=%.3f  gpu_lockstep_s=%.3f  whole_job_speedup=%.2f\n",
+			njobs, nreads, tlen, par.realn, njobs - bad, njobs, (u4i)ga[0]->cns->size, (u4i)ga[0]->msacols->size, nthr, t_ref, t_gpu, t_ref / t_gpu);
+	}
 	for(j=0;j<njobs;j++){ free_bspoa(ga[j]); free_bspoa(gb[j]); }
 	bsb200_destroy(ctx);
 	return bad ? 1 : 0;
