@@ -775,7 +775,9 @@ extern "C" int bsb200_batch_run(bsb200_ctx *ctx, bsb200_batch *b){
 				if(const char *ev = getenv("BSB200_BT_S")){ const int v = atoi(ev); if(v == 1 || v == 2 || v == 4 || v == 8 || v == 16 || v == 32) stride = (uint32_t)v; }
 				t.stride = stride;
 				const uint64_t threads = (uint64_t)np * stride;
-				epi8_backcal_kernel<<<(unsigned)((threads + 63) / 64), 64, 0, sb>>>(t);
+				size_t bt_smem = 0;   // experiments: dynamic shared memory as an occupancy limiter of the walk kernel
+				if(const char *ev = getenv("BSB200_BT_SMEM")){ bt_smem = (size_t)atoi(ev); cudaFuncSetAttribute(epi8_backcal_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bt_smem); }
+				epi8_backcal_kernel<<<(unsigned)((threads + 63) / 64), 64, bt_smem, sb>>>(t);
 			}
 			CK(cudaGetLastError());
 			ctx->timing.traceback_launches++;
