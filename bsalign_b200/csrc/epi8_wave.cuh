@@ -287,17 +287,29 @@ __global__ void __launch_bounds__(kFwdThreads, 4) epi8_wave_kernel(const Epi8Arg
 				accA = __dp4a(ou4.w, 0x00000101u, accA); accB = __dp4a(ou4.w, 0x01010000u, accB); \
 				*(uint4*)(rU + 128 * c) = ou4; *(uint4*)(rE + 128 * c) = oe4; \
 				*(uint4*)(gU + (size_t)c * 128) = ou4; *(uint4*)(gE + (size_t)c * 128) = oe4; \
-				if(ANCH && (c & (kAnchorChunks - 1)) == kAnchorChunks - 1 && c + 1 < nchunk){ \
-					/* sub-lane anchors: H at the end of step 8(c+1)-1 = score at the sub-block's start + its u bytes so far */ \
-					int32_t *an = (int32_t*)(tr + (size_t)RS * (T + 1) + (size_t)IB * 2) + (c / kAnchorChunks) * 16; \
-					const int corr = 128 * (int)(8 * (c + 1 - cb0)); \
-					if(actA) an[A] = ancA + (int)accA - corr; \
-					if(actB) an[B] = ancB + (int)accB - corr; \
-				} }
+				}
 			const uint32_t nchunk = (W + 7) / 8, nfull = (s0 + nst) / 8;
 			uint32_t c = cb0;
-			_Pragma("unroll 1")
-			for(;c<nfull;c++) WCHUNK(8u, false)
+			if(ANCH){
+				// the chunks of one anchor group at a time; the sub-lane anchor behind a group (H at the end of its last step = score at
+				// the sub-block's start + its u bytes so far) is written between the groups, outside the chunk loop
+				int32_t *an = (int32_t*)(tr + (size_t)RS * (T + 1) + (size_t)IB * 2) + (cb0 / kAnchorChunks) * 16;
+				_Pragma("unroll 1")
+				while(c < nfull){
+					const uint32_t cend = c + kAnchorChunks < nfull ? c + kAnchorChunks : nfull;
+					_Pragma("unroll 1")
+					for(;c<cend;c++) WCHUNK(8u, false)
+					if((c & (kAnchorChunks - 1)) == 0 && c < nchunk){
+						const int corr = 128 * (int)(8 * (c - cb0));
+						if(actA) an[A] = ancA + (int)accA - corr;
+						if(actB) an[B] = ancB + (int)accB - corr;
+						an += 16;
+					}
+				}
+			} else {
+				_Pragma("unroll 1")
+				for(;c<nfull;c++) WCHUNK(8u, false)
+			}
 			if(c < cb1){ const uint32_t left = s0 + nst - 8 * c; WCHUNK(left, true) }
 			#undef WCHUNK
 			#undef WSTEP
