@@ -795,7 +795,7 @@ extern "C" int bsb200_batch_run(bsb200_ctx *ctx, bsb200_batch *b){
 			// (linear gaps, pw = 0, stay on the literal kernel)
 			// (BSB200_NOFAST: tests run the literal kernels on ordinary gap costs too)
 			const bool fast = b->pw >= 1 && b->ge1 <= 0 && (int8_t)(b->go1 + b->ge1) <= 0 && (b->pw < 2 || (b->ge2 <= 0 && (int8_t)(b->go2 + b->ge2) <= 0)) && !getenv("BSB200_NOFAST");
-			const bool anch = b->wave_split ? (getenv("BSB200_WAVE_ANCH32") ? b->max_bw / 16 > kAnchorSteps : epi8_wave_use_anchors(b->max_bw / 16)) : epi8_use_anchors(b->max_bw / 16);   // (BSB200_WAVE_ANCH32: experiments)
+			const bool anch = b->wave_split ? epi8_wave_use_anchors(b->max_bw / 16) : epi8_use_anchors(b->max_bw / 16);
 			a.gpw = 4;
 			int rc;
 			if(b->wave_split){

@@ -44,19 +44,17 @@ __host__ __device__ __forceinline__ uint32_t epi8_cell_offset_w(uint32_t j, uint
 
 // Sub-lane anchors for the traceback: besides the 17 block anchors of the reference, a row carries the absolute score
 // at the end of every 32nd step of every lane (int32 [g-1][lane], g = 1 .. ngrp-1), so that a score lookup sums at
-// most 32 cells (4 chunks = 4 sectors) instead of a whole lane.  (16-step anchors were measured in round 2: the walk of config 2
-// drops from 15.9 to 10.9 ms - it is bound by the sectors it touches - but the anchor code in the wavefront kernel's chunk loop
-// cost 15 ms of forward time and the store grows by 9 %; not kept.)
+// most 32 cells (4 chunks = 4 sectors) instead of a whole lane.
 constexpr uint32_t kAnchorSteps = 32, kAnchorChunks = kAnchorSteps / 8;
 constexpr uint32_t kStageAlign = 32;   // sub-blocks of the wavefront kernel are whole 32-step groups (the chunks of row_max, bsalign.h:3227)
 __host__ __device__ __forceinline__ uint32_t epi8_anchor_groups(uint32_t W){ return (W + kAnchorSteps - 1) / kAnchorSteps; }
 __host__ __device__ __forceinline__ uint32_t epi8_anchor_bytes(uint32_t W){ return ((epi8_anchor_groups(W) - 1) * 64 + 127) / 128 * 128; }   // rows stay 128-byte aligned
 // The two-pass kernel computes the anchors in a loop of its own behind pass 2: they pay off only when the widest lane of a batch
 // exceeds 64 steps.  The wavefront kernel has the running sums in registers anyway and writes them whenever a lane has more than
-// one anchor group ... in principle.  Measured on config 2 (W = 63, one anchor per lane and row, written between the chunk groups):
-// walk 15.7 -> 12.3 ms but forward 60.9 -> 65.2 ms (rows no longer 128-byte aligned, 3 % more store): the same rule applies.
+// one anchor group (written between the chunk groups, rows padded to whole 128-byte lines).  Config 2 (W = 63, one anchor per lane
+// and row): forward 52.4 -> 53.9 ms, walk 16.9 -> 12.1 ms.
 __host__ __device__ __forceinline__ bool epi8_use_anchors(uint32_t maxW){ return maxW > 64; }
-__host__ __device__ __forceinline__ bool epi8_wave_use_anchors(uint32_t maxW){ return maxW > 64; }
+__host__ __device__ __forceinline__ bool epi8_wave_use_anchors(uint32_t maxW){ return maxW > kAnchorSteps; }
 __host__ __device__ __forceinline__ uint32_t epi8_row_bytes(uint32_t W, int pw){ return epi8_image_bytes(W) * (pw + 1) + epi8_anchor_bytes(W); }
 
 struct CigarSink {
