@@ -267,6 +267,7 @@ __global__ void __launch_bounds__(kFwdThreads, 4) epi8_wave_kernel(const Epi8Arg
 			uint32_t gacc = st.f, fk = st.f, accA = 0, accB = 0;
 			uint8_t *const gU = tr + (size_t)RS * (T + 1) + 16 * t, *const gE = gU + IB;
 			#define WSTEP(K, LEFT) { if((K) < (LEFT)){ \
+				/* (odd steps' selectors: SHF on the ALU pipe; IMAD.HI on the FMA pipe measured slower, c2 forward 53.9 -> 55.2 ms) */ \
 				uint32_t z = prmt(T32A, T32B, ent_sel<K>(cs4)); \
 				if((K) == 0) z = (z & zm) | zo; \
 				wave_step(st, entw<K>(cu4), entw<K>(ce4), z, wk, un[K], en[K]); \
