@@ -41,6 +41,9 @@ __host__ __device__ __forceinline__ uint32_t epi8_cell_offset(uint32_t j, uint32
 // of (A_k, B_k, A_k+1, B_k+1) - so that two s16x2 results with values in 0..255 interleave into a word with one IMAD (lo + 256 * hi),
 // and stores e biased by +128 like u.  Traces in the skewed layout use this byte order.
 __host__ __device__ __forceinline__ uint32_t epi8_cell_offset_w(uint32_t j, uint32_t i){ return (i >> 3) * 128 + (j >> 1) * 16 + ((i & 7) >> 1) * 4 + (j & 1) * 2 + (i & 1); }
+// ... and in the HBM trace of those pairs a thread's 16 bytes of u and its 16 bytes of e of a chunk sit side by side (256 bytes per chunk):
+// byte offset of u of (lane j, step i) inside a slot; e is 16 bytes further
+__host__ __device__ __forceinline__ uint32_t epi8_trace_offset_w(uint32_t j, uint32_t i){ return (i >> 3) * 256 + (j >> 1) * 32 + ((i & 7) >> 1) * 4 + (j & 1) * 2 + (i & 1); }
 
 // Sub-lane anchors for the traceback: besides the 17 block anchors of the reference, a row carries the absolute score
 // at the end of every 32nd step of every lane (int32 [g-1][lane], g = 1 .. ngrp-1), so that a score lookup sums at

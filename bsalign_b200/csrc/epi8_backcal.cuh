@@ -53,14 +53,14 @@ struct TraceView {
 	// array arr (0 u, 1 e, 2 q) of the cell at band position p of a row
 	__device__ __forceinline__ int cell(int row, int arr, uint32_t p) const {
 		uint32_t j = div_w(p), i = p - j * W;
-		uint8_t b = slot(row, j, i)[(size_t)arr * IB + (skew ? epi8_cell_offset_w(j, i) : epi8_cell_offset(j, i))];
+		uint8_t b = skew ? slot(row, j, i)[epi8_trace_offset_w(j, i) + 16 * arr] : slot(row, j, i)[(size_t)arr * IB + epi8_cell_offset(j, i)];
 		return (int)(int8_t)(((arr == 0 && ubias) || (arr == 1 && skew)) ? (uint8_t)(b ^ 0x80) : b);
 	}
 	// H(col,row) = anchor of the lane + its u cells up to col (bsalign.h:3187-3202); sets err when the lookup leaves the band
 	__device__ int score(int row, int col, int &err) const { return score_at(row, (row >= -1 && row < tlen) ? beg(row) : 0, col, err); }
 	// ---- split lookup: `begin` only computes addresses and issues the loads (anchor + up to 8 chunks), `finish` sums.
 	// Between the two the caller issues its other loads, so that one walk step costs a single memory round trip.
-	struct Pending { const uint8_t *r; int4 v[8]; int ub; uint32_t n; int mk; };
+	struct Pending { const uint8_t *r; int4 v[8]; int ub; uint32_t n, cs; int mk; };
 	// a word holds two steps of the lane: mask of the first one
 	__device__ __forceinline__ int first_step(int mk) const { return skew ? (mk & 0x00ff00ff) : (mk & 0x0000ffff); }
 	__device__ __forceinline__ void begin(Pending &p, bool need, int row, int rbeg, int col, int &err) const {
@@ -74,11 +74,12 @@ struct TraceView {
 		const uint8_t *sl = slot(rw, j, i);
 		// (the sub-lane anchor before step 32g was written by the stage of step 32g - 1)
 		p.ub = ok ? (g ? *(const int32_t*)(slot(rw, j, g * kAnchorSteps - 1) + AOFF + ((g - 1) * 16 + j) * 4) : ub(rw, j)) : kScoreMin;
-		p.r = sl + (size_t)(j >> 1) * 16 + (size_t)g * (kAnchorSteps / 8) * 128;
+		p.r = skew ? sl + (size_t)(j >> 1) * 32 + (size_t)g * (kAnchorSteps / 8) * 256 : sl + (size_t)(j >> 1) * 16 + (size_t)g * (kAnchorSteps / 8) * 128;
+		p.cs = skew ? 256u : 128u;   // bytes from one chunk of the lane pair to the next
 		p.mk = skew ? ((j & 1) ? 0x01010000 : 0x00000101) : ((j & 1) ? 0x01000100 : 0x00010001);
 		const uint32_t nch = (p.n + 7) >> 3;
 		#pragma unroll
-		for(int k=0;k<8;k++) p.v[k] = (uint32_t)k < nch ? *(const int4*)(p.r + 128 * k) : make_int4(0, 0, 0, 0);
+		for(int k=0;k<8;k++) p.v[k] = (uint32_t)k < nch ? *(const int4*)(p.r + (size_t)p.cs * k) : make_int4(0, 0, 0, 0);
 	}
 	// (branch-free: a word holds two steps of the lane; the mask of a word is the lane's, the first step's, or 0)
 	__device__ __forceinline__ int word_mask(int left, int mk) const { return left >= 2 ? mk : (left == 1 ? first_step(mk) : 0); }
@@ -98,7 +99,7 @@ struct TraceView {
 		for(uint32_t c0=8;c0<nch;c0+=8){ // lanes longer than 64 steps without anchors: further rounds
 			int4 v[8];
 			#pragma unroll
-			for(int k=0;k<8;k++) v[k] = c0 + k < nch ? *(const int4*)(p.r + 128 * (c0 + k)) : make_int4(0, 0, 0, 0);
+			for(int k=0;k<8;k++) v[k] = c0 + k < nch ? *(const int4*)(p.r + (size_t)p.cs * (c0 + k)) : make_int4(0, 0, 0, 0);
 			#pragma unroll
 			for(int k=0;k<8;k++){
 				const int left = (int)p.n - 8 * (int)(c0 + k);
@@ -188,9 +189,9 @@ __global__ void __launch_bounds__(128) epi8_backcal_kernel(const Epi8BtArgs a){
 		// ---- 2. issue every load of this step (cell above, query/target bases, lookup), then consume -------------
 		const int crow = (state == kStep) ? tb - 1 : -1;                    // row of the cell above (valid memory in any state)
 		const uint32_t cx = cellok ? (uint32_t)x : 0u;
-		const uint32_t cj = tv.div_w(cx), coff = tv.skew ? epi8_cell_offset_w(cj, cx - cj * tv.W) : epi8_cell_offset(cj, cx - cj * tv.W);
+		const uint32_t cj = tv.div_w(cx), coff = tv.skew ? epi8_trace_offset_w(cj, cx - cj * tv.W) : epi8_cell_offset(cj, cx - cj * tv.W);
 		const uint8_t *cp = tv.slot(crow, cj, cx - cj * tv.W) + coff;
-		const uint32_t ru = cp[0], re = pw >= 1 ? cp[tv.IB] : 0u, rq = pw == 2 ? cp[2 * (size_t)tv.IB] : 0u;
+		const uint32_t ru = cp[0], re = pw >= 1 ? cp[tv.skew ? 16 : tv.IB] : 0u, rq = pw == 2 ? cp[2 * (size_t)tv.IB] : 0u;
 		const uint32_t qbase = qs[qb >= 0 ? qb : 0], tbase = ts[tb >= 0 ? tb : 0];
 		TraceView::Pending pd;
 		tv.begin(pd, need, lrow, lbeg, lcol, err);

@@ -17,6 +17,8 @@
 //   * the two halves of a register sit on different target rows, so the substitution scores come from PRMT(column of row A,
 //     column of row B, selector): scores are kept +63 (0..126), whose sign-replicating nibble yields the zero high byte and,
 //     for positions past the query end, the -63 of the reference (0);
+//   * in the trace the u and e pieces of a thread sit side by side (chunk c of a slot = 256 bytes: per thread 16 bytes of u, then its 16
+//     bytes of e): the cell above a traceback step and the last chunk of its score lookup are then one 32-byte sector;
 //   * the trace is written straight from the registers of the pass, in a SKEWED layout: slot s of a pair holds lane j's row
 //     s - 1 - j, which is what the group produces together in one time step (one coalesced 128-byte line per chunk and
 //     array); the traceback kernel adds the lane to the row index (TraceView::skew).
@@ -140,6 +142,7 @@ __global__ void __launch_bounds__(kFwdThreads, 4) epi8_wave_kernel(const Epi8Arg
 	int8_t *const rU = sU + 16 * t, *const rE = sE + 16 * t; uint8_t *const rC = sC + 16 * t;
 	#define TOFF(i) ((((i) >> 3) << 7) + (((i) & 7) << 1))                       /* selectors: 2 bytes per step */
 	#define WOFF(i) ((((i) >> 3) << 7) + ((((i) & 7) >> 1) << 2) + ((i) & 1))       /* u, e: lane A's byte of step i (lane B: + 2) */
+	#define GOFF(i) ((((i) >> 3) << 8) + ((((i) & 7) >> 1) << 2) + ((i) & 1))       /* the same byte of u in the trace (e: + 16) */
 	#define QCODE(x) ((x) < qlen ? (uint32_t)qs[(x)] : 4u)
 	#pragma unroll
 	for(int k=0;k<SPLIT;k++) hist[k] = 0;
@@ -210,10 +213,10 @@ __global__ void __launch_bounds__(kFwdThreads, 4) epi8_wave_kernel(const Epi8Arg
 				// are never read); lane B's slot is written by the time step before lane B starts, which then puts its image back.
 				{
 					const uint32_t sA = SPLIT * A + b, sB = sA + SPLIT;
-					uint8_t *d0 = tr + (size_t)RS * sA + 16 * t;
+					uint8_t *d0 = tr + (size_t)RS * sA + 32 * t;
 					for(uint32_t c=cb0;c<cb1;c++){
-						*(uint4*)(d0 + 128 * c) = *(const uint4*)(rU + 128 * c);
-						*(uint4*)(d0 + IB + 128 * c) = *(const uint4*)(rE + 128 * c);
+						*(uint4*)(d0 + 256 * c) = *(const uint4*)(rU + 128 * c);
+						*(uint4*)(d0 + 256 * c + 16) = *(const uint4*)(rE + 128 * c);
 					}
 					if(lane_end){ metaS[(size_t)16 * sA + A] = EA; metaS[(size_t)16 * sB + B] = EB; }
 					if(g == 0) ub0p[0] = SA;
@@ -265,7 +268,7 @@ __global__ void __launch_bounds__(kFwdThreads, 4) epi8_wave_kernel(const Epi8Arg
 			// absolute score at the start of the two sub-blocks (lane 0: the old ub[0]; its first u is re-based after the loop)
 			const int ancA = g ? inA2 : SA, ancB = inB2;
 			uint32_t gacc = st.f, fk = st.f, accA = 0, accB = 0;
-			uint8_t *const gU = tr + (size_t)RS * (T + 1) + 16 * t, *const gE = gU + IB;
+			uint8_t *const gU = tr + (size_t)RS * (T + 1) + 32 * t;   // this thread's 32 bytes (u, e) of chunk 0 of the time step's slot
 			#define WSTEP(K, LEFT) { if((K) < (LEFT)){ \
 				/* (odd steps' selectors: SHF on the ALU pipe; IMAD.HI on the FMA pipe measured slower, c2 forward 53.9 -> 55.2 ms) */ \
 				uint32_t z = prmt(T32A, T32B, ent_sel<K>(cs4)); \
@@ -287,7 +290,7 @@ __global__ void __launch_bounds__(kFwdThreads, 4) epi8_wave_kernel(const Epi8Arg
 				accA = __dp4a(ou4.z, 0x00000101u, accA); accB = __dp4a(ou4.z, 0x01010000u, accB); \
 				accA = __dp4a(ou4.w, 0x00000101u, accA); accB = __dp4a(ou4.w, 0x01010000u, accB); \
 				*(uint4*)(rU + 128 * c) = ou4; *(uint4*)(rE + 128 * c) = oe4; \
-				*(uint4*)(gU + (size_t)c * 128) = ou4; *(uint4*)(gE + (size_t)c * 128) = oe4; \
+				*(uint4*)(gU + (size_t)c * 256) = ou4; *(uint4*)(gU + (size_t)c * 256 + 16) = oe4; \
 				}
 			const uint32_t nchunk = (W + 7) / 8, nfull = (s0 + nst) / 8;
 			uint32_t c = cb0;
@@ -378,11 +381,11 @@ __global__ void __launch_bounds__(kFwdThreads, 4) epi8_wave_kernel(const Epi8Arg
 			// lane B starts with the next time step: the steps before ran it on its row -1 image; put that image back (shared memory
 			// and lane B's bytes of its row -1 slot, which is the slot of this time step)
 			const bool glob = (mode == 0 || mode == 2);
-			uint8_t *const gU = tr + (size_t)RS * (T + 1) + 16 * t, *const gE = gU + IB;
+			uint8_t *const gU = tr + (size_t)RS * (T + 1) + 32 * t;
 			for(uint32_t i=8*cb0;i<8*cb1;i++){
 				const int8_t ub_ = (int8_t)(((glob && i < W) ? ge1 : 0) + 128);
 				rU[WOFF(i) + 2] = ub_; rE[WOFF(i) + 2] = (int8_t)(kEpi8Min + 128);
-				gU[WOFF(i) + 2] = (uint8_t)ub_; gE[WOFF(i) + 2] = (uint8_t)(kEpi8Min + 128);
+				gU[GOFF(i) + 2] = (uint8_t)ub_; gU[GOFF(i) + 18] = (uint8_t)(kEpi8Min + 128);
 			}
 		}
 		#pragma unroll
@@ -443,6 +446,7 @@ __global__ void __launch_bounds__(kFwdThreads, 4) epi8_wave_kernel(const Epi8Arg
 	#undef QCODE
 	#undef TOFF
 	#undef WOFF
+	#undef GOFF
 	#undef COLW
 }
 
