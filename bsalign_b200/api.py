@@ -95,6 +95,18 @@ def lib():
         L.bsb200_seqfile_free.argtypes = [_P]
         L.bsb200_format_pair_text.restype = ctypes.c_uint64
         L.bsb200_format_pair_text.argtypes = [_P, ctypes.c_uint64, ctypes.c_char_p, ctypes.c_uint32, ctypes.c_char_p, ctypes.c_uint32, _P, _P, ctypes.c_uint64, ctypes.c_uint64, _P, ctypes.c_uint32]
+        L.bsb200_msa_read.restype = _P
+        L.bsb200_msa_read.argtypes = [_P]
+        L.bsb200_msa_write.argtypes = [_P, ctypes.c_uint32, ctypes.c_uint32, _P, _P, _P, ctypes.c_char_p, ctypes.c_uint32]
+        for fn in ("bsb200_msa_nseq", "bsb200_msa_mlen"):
+            getattr(L, fn).restype = ctypes.c_uint32
+            getattr(L, fn).argtypes = [_P]
+        for fn in ("bsb200_msa_cols", "bsb200_msa_qlt", "bsb200_msa_alt"):
+            getattr(L, fn).restype = _P
+            getattr(L, fn).argtypes = [_P]
+        L.bsb200_msa_meta.restype = _P
+        L.bsb200_msa_meta.argtypes = [_P, ctypes.POINTER(ctypes.c_uint32)]
+        L.bsb200_msa_free.argtypes = [_P]
         L.bsb200_batch_upload_bits.restype = _P
         L.bsb200_batch_upload_bits.argtypes = L.bsb200_batch_upload.argtypes
         L.bsb200_batch_fetch_dense_dev.argtypes = [_P, _P, _P, _P, ctypes.c_uint64, _P, _P, _P]
@@ -326,6 +338,52 @@ def format_pair_text(sf, k, result, cigar):
     buf = ctypes.create_string_buffer(need + 1)
     L.bsb200_format_pair_text(buf, need, *args)
     return buf.raw[:need]
+
+
+_libc = ctypes.CDLL(None)
+_libc.fopen.restype = ctypes.c_void_p
+_libc.fopen.argtypes = [ctypes.c_char_p, ctypes.c_char_p]
+_libc.fclose.argtypes = [ctypes.c_void_p]
+
+
+def read_binary_msa(path):
+    """All MSAs of a file in the reference's binary MSA format (bspoa.h:1555-1643) as dicts: nseq, mlen, cols (mlen, nseq + 1), qlt, alt, meta."""
+    L = lib()
+    fp = _libc.fopen(os.fsencode(path), b"rb")
+    if not fp:
+        raise IOError("cannot open %s" % path)
+    out = []
+    try:
+        while True:
+            m = L.bsb200_msa_read(fp)
+            if not m:
+                break
+            nseq, mlen = int(L.bsb200_msa_nseq(m)), int(L.bsb200_msa_mlen(m))
+            grab = lambda p, n: np.ctypeslib.as_array(ctypes.cast(p, ctypes.POINTER(ctypes.c_uint8)), shape=(max(n, 1),))[:n].copy()
+            ln = ctypes.c_uint32(0)
+            mp = L.bsb200_msa_meta(m, ctypes.byref(ln))
+            out.append(dict(nseq=nseq, mlen=mlen, cols=grab(L.bsb200_msa_cols(m), mlen * (nseq + 1)).reshape(mlen, nseq + 1), qlt=grab(L.bsb200_msa_qlt(m), mlen),
+                            alt=grab(L.bsb200_msa_alt(m), mlen), meta=ctypes.string_at(mp, ln.value) if ln.value else b""))
+            L.bsb200_msa_free(m)
+    finally:
+        _libc.fclose(fp)
+    return out
+
+
+def write_binary_msa(path, msas, mode="wb"):
+    L = lib()
+    fp = _libc.fopen(os.fsencode(path), mode.encode())
+    if not fp:
+        raise IOError("cannot open %s" % path)
+    try:
+        for m in msas:
+            cols = np.ascontiguousarray(m["cols"], dtype=np.uint8)
+            rc = L.bsb200_msa_write(fp, int(m["nseq"]), int(m["mlen"]), _ptr(cols), _ptr(np.ascontiguousarray(m["qlt"], np.uint8)),
+                                    _ptr(np.ascontiguousarray(m["alt"], np.uint8)), m.get("meta") or None, len(m.get("meta") or b""))
+            if rc:
+                raise IOError("bsb200_msa_write failed")
+    finally:
+        _libc.fclose(fp)
 
 
 def pack_bits(seqs):

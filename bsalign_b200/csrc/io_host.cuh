@@ -211,3 +211,52 @@ extern "C" uint64_t bsb200_format_pair_text(char *out, uint64_t cap, const char 
 	if(out && s.size() <= cap) memcpy(out, s.data(), s.size());
 	return s.size();
 }
+
+// ---- binary MSA (bspoa.h:1555-1685: dump_binary_msa_bspoa / load_binary_msa_bspoa_core) -------------------------------------------
+// Records: 0x81 u32 len, bytes            metadata (optional)
+//          0x22 u32 mlen, u32 nseq        then mlen columns of nseq + 1 bytes (the reads' bases 0..3 / 4 = gap, then the consensus base),
+//                                          then mlen quality bytes and mlen alternative-base bytes
+//          0xFF                           end of one MSA
+struct bsb200_msa { uint32_t nseq = 0, mlen = 0; std::vector<uint8_t> cols, qlt, alt; std::string meta; };
+
+extern "C" int bsb200_msa_write(void *out_, uint32_t nseq, uint32_t mlen, const uint8_t *cols, const uint8_t *qlt, const uint8_t *alt, const char *meta, uint32_t metalen){
+	FILE *out = (FILE*)out_;
+	uint8_t tag;
+	if(!out || (mlen && (!cols || !qlt || !alt))) return -1;
+	if(meta && metalen){ tag = 0x81; fwrite(&tag, 1, 1, out); fwrite(&metalen, 4, 1, out); fwrite(meta, 1, metalen, out); }
+	tag = 0x22; fwrite(&tag, 1, 1, out); fwrite(&mlen, 4, 1, out); fwrite(&nseq, 4, 1, out);
+	if(mlen){ fwrite(cols, 1, (size_t)mlen * (nseq + 1), out); fwrite(qlt, 1, mlen, out); fwrite(alt, 1, mlen, out); }
+	tag = 0xFF; fwrite(&tag, 1, 1, out);
+	return ferror(out) ? -1 : 0;
+}
+
+// reads the next MSA of the stream; returns NULL at the end of the file or on a malformed record
+extern "C" bsb200_msa *bsb200_msa_read(void *inp_){
+	FILE *inp = (FILE*)inp_;
+	bsb200_msa *m = new bsb200_msa();
+	uint8_t tag; uint32_t a, b; bool any = false;
+	while(inp && fread(&tag, 1, 1, inp) == 1){
+		if(tag == 0xFF){ if(any) return m; continue; }
+		if(tag == 0x81){
+			if(fread(&a, 4, 1, inp) != 1) break;
+			m->meta.resize(a);
+			if(a && fread(&m->meta[0], 1, a, inp) != a) break;
+			any = true;
+		} else if(tag == 0x22){
+			if(fread(&a, 4, 1, inp) != 1 || fread(&b, 4, 1, inp) != 1) break;
+			m->mlen = a; m->nseq = b;
+			m->cols.resize((size_t)a * (b + 1)); m->qlt.resize(a); m->alt.resize(a);
+			if(a && (fread(m->cols.data(), 1, m->cols.size(), inp) != m->cols.size() || fread(m->qlt.data(), 1, a, inp) != a || fread(m->alt.data(), 1, a, inp) != a)) break;
+			any = true;
+		} else break;
+	}
+	delete m;
+	return nullptr;
+}
+extern "C" uint32_t bsb200_msa_nseq(const bsb200_msa *m){ return m->nseq; }
+extern "C" uint32_t bsb200_msa_mlen(const bsb200_msa *m){ return m->mlen; }
+extern "C" const uint8_t *bsb200_msa_cols(const bsb200_msa *m){ return m->cols.data(); }
+extern "C" const uint8_t *bsb200_msa_qlt(const bsb200_msa *m){ return m->qlt.data(); }
+extern "C" const uint8_t *bsb200_msa_alt(const bsb200_msa *m){ return m->alt.data(); }
+extern "C" const char *bsb200_msa_meta(const bsb200_msa *m, uint32_t *len){ if(len) *len = (uint32_t)m->meta.size(); return m->meta.data(); }
+extern "C" void bsb200_msa_free(bsb200_msa *m){ delete m; }

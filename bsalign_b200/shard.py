@@ -25,11 +25,21 @@ def pair_work(batch, kind, bandwidth):
 def balanced_partition(work, nparts):
     """Deal pairs, heaviest first, in snake order (0..g-1, g-1..0, ...): per-part totals agree within a fraction
     of one heavy pair.  Returns a list of index arrays (each sorted ascending, so shards keep input order)."""
-    order = np.argsort(-np.asarray(work, dtype=np.int64), kind="stable")
-    pos = np.arange(len(order))
+    work = np.asarray(work, dtype=np.int64)
+    n = len(work)
+    if n == 0:
+        return [np.zeros(0, np.int64) for _ in range(nparts)]
+    # the order only has to be roughly heaviest-first: keys quantised to 16 bits sort with numpy's radix sort (O(n)); ties keep input order
+    wmax = int(work.max())
+    sh = max(0, wmax.bit_length() - 16)
+    key = (np.uint16(0xFFFF) - (work >> sh).astype(np.uint16)) if wmax else np.zeros(n, np.uint16)
+    order = np.argsort(key, kind="stable")
+    pos = np.arange(n)
     rnd, k = pos // nparts, pos % nparts
-    part = np.where(rnd % 2 == 0, k, nparts - 1 - k)
-    return [np.sort(order[part == p]) for p in range(nparts)]
+    part_of_pos = np.where(rnd % 2 == 0, k, nparts - 1 - k)
+    part = np.empty(n, dtype=np.int64)
+    part[order] = part_of_pos                      # part of every pair, in pair order
+    return [np.flatnonzero(part == p) for p in range(nparts)]
 
 
 # ---- the product path: one batch on rank 0, shards over NVLink, results back to rank 0 ----------------------------------------
@@ -134,19 +144,24 @@ def run_sharded_device(batch, kind, bandwidth, align_fn, dist, device="cpu", pin
     arena = None
     scatter_bytes = 0
     if rank == 0:
-        for r in list(range(1, world)) + [0]:
-            p = plans[r]
-            host = None
-            if pinned is not None:
-                host = pinned(max(p["nbytes"], 1))
-            pb, nb = api.pack_pairs(batch, p["idx"], out_seqs=host, nthreads=nthreads)
-            t = torch.from_numpy(pb.seqs[:max(nb, 1)]).to(device, non_blocking=True)
-            keep.append((pb, t))
+        # one pass over the batch packs every shard's compact arena, shard after shard in one (pinned) host arena; one copy moves it to
+        # rank 0's GPU, and the shards of the other ranks are sent on from there
+        idx_all = np.concatenate([p["idx"] for p in plans]).astype(np.uint64)
+        total = int(sum(p["nbytes"] for p in plans))
+        host = pinned(max(total, 1)) if pinned is not None else None
+        pb, nb = api.pack_pairs(batch, idx_all, out_seqs=host, nthreads=nthreads)
+        whole = torch.from_numpy(pb.seqs[:max(nb, 1)]).to(device, non_blocking=True)
+        keep.append((pb, whole))
+        off = 0
+        for r in range(world):
+            nbr = plans[r]["nbytes"]
+            t = whole[off:off + max(nbr, 1)] if nbr else torch.zeros(1, dtype=torch.uint8, device=device)
+            off += nbr
             if r == 0:
                 arena = t
             else:
                 sends.append(dist.isend(t, r))
-                scatter_bytes += nb
+                scatter_bytes += nbr
     else:
         arena = torch.empty(max(mine["nbytes"], 1), dtype=torch.uint8, device=device)
         dist.recv(arena, 0)

@@ -190,6 +190,21 @@ uint64_t bsb200_format_pair_text(char *out, uint64_t cap, const char *qname, uin
 int64_t bsb200_align_file(bsb200_ctx *ctx, int kind, const char *path, int mode, uint32_t bandwidth, const int8_t matrix[16],
 		int8_t gapo1, int8_t gape1, int8_t gapo2, int8_t gape2, void *out /* FILE* */, uint64_t batch_pairs /* 0 = 1M */);
 
+/* binary MSA of the reference (dump_binary_msa_bspoa / load_binary_msa_bspoa_core, bspoa.h:1555-1643): [0x81 u32 len, metadata] 0x22 u32 mlen
+ * u32 nseq, mlen columns of nseq + 1 bytes (read bases 0..3, 4 = gap; then the consensus base), mlen quality bytes, mlen alternative-base bytes,
+ * 0xFF.  `out` / `inp` are FILE*; bsb200_msa_read returns the next MSA of the stream or NULL.  include/bsalign_b200_poa_compat.h wraps them
+ * for a BSPOA (b200_dump_binary_msa_bspoa). */
+typedef struct bsb200_msa bsb200_msa;
+int bsb200_msa_write(void *out, uint32_t nseq, uint32_t mlen, const uint8_t *cols, const uint8_t *qlt, const uint8_t *alt, const char *meta, uint32_t metalen);
+bsb200_msa *bsb200_msa_read(void *inp);
+uint32_t bsb200_msa_nseq(const bsb200_msa *m);
+uint32_t bsb200_msa_mlen(const bsb200_msa *m);
+const uint8_t *bsb200_msa_cols(const bsb200_msa *m);
+const uint8_t *bsb200_msa_qlt(const bsb200_msa *m);
+const uint8_t *bsb200_msa_alt(const bsb200_msa *m);
+const char *bsb200_msa_meta(const bsb200_msa *m, uint32_t *len);
+void bsb200_msa_free(bsb200_msa *m);
+
 /* ---- POA read-vs-graph banded DP sweep: replaces align_rd_bspoacore (bspoa.h:2515-2618) -------------------- */
 /*
  * One SWEEP JOB = one call of the reference's align_rd_bspoacore: a read (query) against the selected sub-graph

@@ -353,6 +353,19 @@ static inline void b200_end_bspoa_batch(bsb200_ctx *ctx, BSPOA **gs, u4i n){
 	b200_poa_pack_free(p);
 }
 
+/* dump_binary_msa_bspoa (bspoa.h:1555-1584) through the library's writer: the columns are gathered in MSA order */
+static inline void b200_dump_binary_msa_bspoa(BSPOA *g, char *metadat, u4i metalen, FILE *out){
+	u4i nseq = g->nrds, mlen = g->msaidxs->size, mrow = g->seqs->nseq + 3, i;
+	u1i *cols = (u1i*)malloc((size_t)mlen * (nseq + 1) + 1), *qa = (u1i*)malloc(2 * (size_t)mlen + 1);
+	for(i=0;i<mlen;i++){
+		u1i *col = g->msacols->buffer + g->msaidxs->buffer[i] * mrow;
+		memcpy(cols + (size_t)i * (nseq + 1), col, nseq + 1);
+		qa[i] = col[nseq + 1]; qa[mlen + i] = col[nseq + 2];
+	}
+	bsb200_msa_write(out, nseq, mlen, cols, qa, qa + mlen, metadat, metalen);
+	free(cols); free(qa);
+}
+
 #ifdef BSALIGN_B200_OVERRIDE
 static inline bsb200_ctx *bsalign_b200_poa_default_ctx(void){
 	bsb200_ctx *ctx = bsb200_default_context();

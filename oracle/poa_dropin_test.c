@@ -80,6 +80,21 @@ int main(int argc, char **argv){
 			&& a->alt->size == b->alt->size && memcmp(a->alt->buffer, b->alt->buffer, a->alt->size) == 0
 			&& a->msaidxs->size == b->msaidxs->size && memcmp(a->msaidxs->buffer, b->msaidxs->buffer, a->msaidxs->size * sizeof(u4i)) == 0
 			&& a->msacols->size == b->msacols->size && memcmp(a->msacols->buffer, b->msacols->buffer, a->msacols->size) == 0;
+		if(same){   /* the binary MSA: the reference's own writer on its object, the library's writer on ours, byte for byte; and read back */
+			char *b1 = NULL, *b2 = NULL; size_t n1 = 0, n2 = 0;
+			FILE *f1 = open_memstream(&b1, &n1), *f2 = open_memstream(&b2, &n2);
+			dump_binary_msa_bspoa(a, "job", 3, f1); fclose(f1);
+			b200_dump_binary_msa_bspoa(b, "job", 3, f2); fclose(f2);
+			if(n1 != n2 || memcmp(b1, b2, n1)){ same = 0; fprintf(stderr, "job %u: binary MSA differs (%zu vs %zu bytes)\n", j, n1, n2); }
+			else {
+				FILE *f3 = fmemopen(b2, n2, "rb");
+				bsb200_msa *m = bsb200_msa_read(f3);
+				if(!m || bsb200_msa_nseq(m) != a->nrds || bsb200_msa_mlen(m) != a->msaidxs->size){ same = 0; fprintf(stderr, "job %u: binary MSA does not read back\n", j); }
+				if(m) bsb200_msa_free(m);
+				fclose(f3);
+			}
+			free(b1); free(b2);
+		}
 		if(!same){ bad ++; fprintf(stderr, "job %u: consensus / MSA differ (cns %u vs %u, msa %u vs %u)\n", j, (u4i)a->cns->size, (u4i)b->cns->size, (u4i)a->msacols->size, (u4i)b->msacols->size); }
 	}
 	{

@@ -333,6 +333,25 @@ int64_t bsref_poa_dump(uint32_t nreads, const uint8_t *seqs, const uint64_t *off
 
 void bsref_free(void *p){ free(p); }
 
+/* a whole BSPOA job (DEFAULT_BSPOA_PAR) through the unmodified end_bspoa, then the reference's own dump_binary_msa_bspoa (bspoa.h:1555) into
+   a malloc'ed buffer: the golden bytes of the binary MSA format */
+int64_t bsref_poa_msa_bytes(uint32_t nreads, const uint8_t *seqs, const uint64_t *off, const uint32_t *len, const char *meta, uint32_t metalen, uint8_t **out){
+	BSPOAPar par = DEFAULT_BSPOA_PAR;
+	BSPOA *g = init_bspoa(par);
+	char *buf = NULL; size_t sz = 0;
+	FILE *f;
+	u4i i;
+	beg_bspoa(g);
+	for(i=0;i<nreads;i++) fwdbitseqpush_bspoa(g, (u1i*)seqs + off[i], len[i]);
+	end_bspoa(g);
+	f = open_memstream(&buf, &sz);
+	dump_binary_msa_bspoa(g, (char*)meta, metalen, f);
+	fclose(f);
+	free_bspoa(g);
+	*out = (uint8_t*)buf;
+	return (int64_t)sz;
+}
+
 /* Time the reference's own sweep: run a whole POA job (same call sequence as end_bspoa, bspoa.h:4737-4760, realn = 0) and
  * accumulate the CPU time spent inside align_rd_bspoacore only (thread CPU clock), plus the number of row updates (every update
  * increments v->vst once, bspoa.h:2592) and merges.  One BSPOA per call: callers may run several calls on different threads. */

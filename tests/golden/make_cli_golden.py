@@ -63,5 +63,32 @@ def main():
             print(src, name, len(txt))
 
 
+def msa_golden():
+    """msa_small.bin: two small BSPOA jobs through the unmodified end_bspoa + dump_binary_msa_bspoa (oracle/_ref/libbsref.so: bsref_poa_msa_bytes)."""
+    import ctypes
+    import checkers as ck
+    from bsalign_b200 import synth
+    L = ck.ref()
+    blob = b""
+    for seed, nreads, tlen, meta in ((3, 6, 300, b"job-a"), (4, 9, 450, b"")):
+        rng = np.random.default_rng(seed)
+        tmpl = rng.integers(0, 4, (1, tlen)).astype(np.uint8)
+        reads = []
+        for _ in range(nreads):
+            t, _l = synth.mutate_batch(rng, tmpl, 0.03, 0.03, 0.04)
+            reads.append(t)
+        seqs = np.concatenate(reads); ln = np.array([len(r) for r in reads], np.uint32)
+        off = np.concatenate([[0], np.cumsum(ln[:-1])]).astype(np.uint64)
+        out = ctypes.c_void_p()
+        L.bsref_poa_msa_bytes.restype = ctypes.c_int64
+        n = L.bsref_poa_msa_bytes(ctypes.c_uint32(nreads), seqs.ctypes.data_as(ctypes.c_void_p), off.ctypes.data_as(ctypes.c_void_p), ln.ctypes.data_as(ctypes.c_void_p),
+                                  meta or None, ctypes.c_uint32(len(meta)), ctypes.byref(out))
+        blob += ctypes.string_at(out, n)
+        L.bsref_free(out)
+    open(os.path.join(HERE, "msa_small.bin"), "wb").write(blob)
+    print("msa_small.bin", len(blob))
+
+
 if __name__ == "__main__":
     main()
+    msa_golden()

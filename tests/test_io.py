@@ -35,3 +35,16 @@ def test_formatter_reproduces_reference_text():
             res, cigs, _ = ck.oracle_batch(kind, batch, mode, 0, mtx, (-3, -2, 0, 0))
             text = b"".join(api.format_pair_text(sf, k, res[k], cigs[k]) for k in range(npair))
             assert text == open(os.path.join(GOLD, "%s.%s.txt" % (tag, name)), "rb").read(), (src, name)
+
+
+def test_binary_msa_round_trips_the_reference_bytes(tmp_path):
+    """tests/golden/msa_small.bin was written by the reference's own dump_binary_msa_bspoa (two jobs, one with metadata): the library reads
+    it and writes the same bytes back."""
+    src = os.path.join(GOLD, "msa_small.bin")
+    msas = api.read_binary_msa(src)
+    assert len(msas) == 2 and msas[0]["meta"] == b"job-a" and msas[1]["meta"] == b""
+    assert msas[0]["nseq"] == 7 and msas[1]["nseq"] == 10 and msas[0]["cols"].shape == (msas[0]["mlen"], 8)   # 6 / 9 reads; the reference's realignment round leaves one all-5 row in front
+    assert msas[0]["cols"].max() <= 5 and 250 < msas[0]["mlen"] < 400
+    dst = tmp_path / "copy.bin"
+    api.write_binary_msa(str(dst), msas)
+    assert open(dst, "rb").read() == open(src, "rb").read()
