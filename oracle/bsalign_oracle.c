@@ -591,6 +591,8 @@ int bso_epi8_pairwise(const uint8_t *qseq, uint32_t qlen, const uint8_t *tseq, u
  * ------------------------------------------------------------------------------------------------ */
 int bso_edit_pairwise(const uint8_t *qseq, uint32_t qlen, const uint8_t *tseq, uint32_t tlen, int mode, uint32_t bandwidth,
 		int32_t *rs, uint32_t *cigar, uint32_t cigar_cap, uint32_t *ncigar);
+int bso_kmer_edit_pairwise(uint32_t ksz, const uint8_t *qseq, uint32_t qlen, const uint8_t *tseq, uint32_t tlen,
+		int32_t *rs, uint32_t *cigar, uint32_t cigar_cap, uint32_t *ncigar);
 
 typedef struct {
 	int kind;
@@ -628,8 +630,11 @@ static void* bso_worker(void *arg){
 				if(job->kind == 0){
 					perr |= bso_epi8_pairwise(job->seqs + job->qoff[j], job->qlen[j], job->seqs + job->toff[j], job->tlen[j], job->mode, job->bandwidth,
 						job->matrix, job->go1, job->ge1, job->go2, job->ge2, job->results + j * 10, cg, cap, &ncg);
-				} else {
+				} else if(job->kind == 1){
 					perr |= bso_edit_pairwise(job->seqs + job->qoff[j], job->qlen[j], job->seqs + job->toff[j], job->tlen[j], job->mode, job->bandwidth,
+						job->results + j * 10, cg, cap, &ncg);
+				} else {
+					perr |= bso_kmer_edit_pairwise(job->bandwidth, job->seqs + job->qoff[j], job->qlen[j], job->seqs + job->toff[j], job->tlen[j],
 						job->results + j * 10, cg, cap, &ncg);
 				}
 			}
@@ -691,6 +696,16 @@ int bso_edit_batch_ex(uint64_t n, const uint8_t *seqs, const uint64_t *qoff, con
 	return bso_run(&job, nthreads);
 }
 
+/* k-mer guided edit (kind 2; the k-mer size travels in the bandwidth field); cigar capacity per pair: 2 * (qlen + tlen) + 4 words */
+int bso_kmer_edit_batch(uint64_t n, const uint8_t *seqs, const uint64_t *qoff, const uint32_t *qlen, const uint64_t *toff, const uint32_t *tlen,
+		uint32_t ksz, int32_t *results, uint32_t *cigars, const uint64_t *cgoff, uint32_t *ncigar, int nthreads, int repeat, int32_t *errs){
+	bso_job_t job;
+	memset(&job, 0, sizeof(job));
+	job.kind = 2; job.errs = errs; job.n = n; job.seqs = seqs; job.qoff = qoff; job.qlen = qlen; job.toff = toff; job.tlen = tlen;
+	job.mode = 0; job.bandwidth = ksz;
+	job.results = results; job.cigars = cigars; job.cgoff = cgoff; job.ncigar = ncigar; job.repeat = repeat;
+	return bso_run(&job, nthreads);
+}
 
 /* ------------------------------------------------------------------------------------------------
  * Edit-distance kernel (bsalign.h:612-1206), restated per cell.
@@ -1198,4 +1213,177 @@ int bso_poa_backtrace(const int32_t *par, const uint8_t *query, uint32_t slen, u
 	#undef ROW_OF
 	out[0] = x; out[1] = (int32_t)n; out[2] = mat; out[3] = mis; out[4] = ins; out[5] = del; out[7] = a->err;
 	return a->err;
+}
+
+/* ------------------------------------------------------------------------------------------------
+ * k-mer guided edit alignment: kmer_striped_seqedit_pairwise, bsalign.h:1209-1536 (main.c:196 `edit -m kmer -k ksz`,
+ * bspoa.h:2089 band placement of long reads).  Restated as: unique shared canonical k-mers (:1230-1276), the reference's chain over
+ * them (:1277-1334; note its predecessor rule for a replaced tail), the offset filter (:1347-1394), the coverage tests, and the
+ * stitching of per-gap edit alignments around the anchors (:1446-1533) with its cigar-push order kept as it is.
+ * ------------------------------------------------------------------------------------------------ */
+typedef struct { uint32_t kmer, src, dir, off; } bso_km_t;
+typedef struct { uint32_t q, t, on; } bso_hit_t;
+
+static int bso_km_cmp(const void *a, const void *b){
+	const bso_km_t *x = (const bso_km_t*)a, *y = (const bso_km_t*)b;
+	if(x->kmer != y->kmer) return x->kmer < y->kmer ? -1 : 1;
+	return (int)x->src - (int)y->src;
+}
+static int bso_hit_cmp(const void *a, const void *b){
+	const bso_hit_t *x = (const bso_hit_t*)a, *y = (const bso_hit_t*)b;
+	return x->q < y->q ? -1 : (x->q > y->q);
+}
+static int bso_int_cmp(const void *a, const void *b){ int x = *(const int*)a, y = *(const int*)b; return x < y ? -1 : (x > y); }
+
+/* anchors of a pair in query order; returns their number (0 = the caller falls back to the plain global edit) */
+uint32_t bso_kmer_anchors(uint32_t ksz, const uint8_t *qseq, uint32_t qlen, const uint8_t *tseq, uint32_t tlen, uint32_t *aq, uint32_t *at){
+	uint32_t cmin, kmk, sft, nk = 0, nh = 0, i, b, e, m, len, kept = 0, fw, rv;
+	bso_km_t *km;
+	bso_hit_t *hit;
+	uint32_t *tails, *pred;
+	int *dl;
+	if(ksz > 15) ksz = 15;
+	if(ksz == 0) return 0;
+	cmin = (uint32_t)((qlen < tlen ? qlen : tlen) * 0.05 + 1); /* :1221-1222 */
+	if(cmin > 2 * ksz) cmin = 2 * ksz;
+	kmk = 0xFFFFFFFFu >> ((16 - ksz) << 1);
+	sft = (ksz - 1) << 1;
+	km = malloc(sizeof(bso_km_t) * ((size_t)qlen + tlen + 1));
+	for(int src=0;src<2;src++){ /* canonical k-mers of both sequences (:1236-1255) */
+		const uint8_t *s = src ? tseq : qseq;
+		uint32_t n = src ? tlen : qlen;
+		if(n < ksz) continue;
+		fw = rv = 0;
+		for(i=0;i<n;i++){
+			uint32_t c = s[i];
+			fw = ((fw << 2) | c) & kmk;
+			rv = (rv >> 2) | (((~c) & 3u) << sft);
+			if(i + 1 >= ksz){
+				uint32_t d = rv < fw;
+				km[nk].kmer = (d ? rv : fw) & 0x3FFFFFFFu; km[nk].src = src; km[nk].dir = d; km[nk].off = i + 1 - ksz; nk++;
+			}
+		}
+	}
+	qsort(km, nk, sizeof(bso_km_t), bso_km_cmp);
+	hit = malloc(sizeof(bso_hit_t) * ((size_t)(qlen < tlen ? qlen : tlen) + 1));
+	/* k-mers seen exactly twice, once per sequence, same strand (:1259-1273).  The reference ends its scan on a zeroed sentinel, so a
+	 * final group of k-mer value 0 is never looked at. */
+	for(b=0;b<nk;b=e){
+		for(e=b+1;e<nk&&km[e].kmer==km[b].kmer;e++);
+		if(e == nk && km[b].kmer == 0) break;
+		if(e - b == 2 && km[b].src != km[b + 1].src && km[b].dir == km[b + 1].dir){ hit[nh].q = km[b].off; hit[nh].t = km[b + 1].off; hit[nh].on = 0; nh++; }
+	}
+	free(km);
+	if(nh * ksz < cmin){ free(hit); return 0; }
+	qsort(hit, nh, sizeof(bso_hit_t), bso_hit_cmp);
+	/* chain (:1281-1330): patience tails; an element that replaces an inner tail inherits the predecessor OF THE TAIL BEFORE IT */
+	tails = malloc(sizeof(uint32_t) * nh); pred = malloc(sizeof(uint32_t) * nh);
+	tails[0] = 0; pred[0] = 0xFFFFFFFFu; len = 1;
+	for(i=1;i<nh;i++){
+		if(hit[i].t > hit[tails[len - 1]].t){ pred[i] = tails[len - 1]; tails[len++] = i; }
+		else if(hit[i].t <= hit[tails[0]].t){ pred[i] = 0xFFFFFFFFu; tails[0] = i; }
+		else {
+			b = 0; e = len;
+			while(b < e){
+				m = b + ((e - b) >> 1);
+				if(hit[i].t > hit[tails[m]].t) b = m + 1;
+				else if(hit[i].t < hit[tails[m]].t) e = m;
+				else { b = m; break; }
+			}
+			pred[i] = pred[tails[b - 1]];
+			tails[b] = i;
+		}
+	}
+	b = 0; e = 0xFFFFFFFFu;
+	for(m=tails[len-1];m!=0xFFFFFFFFu;m=pred[m]){
+		hit[m].on = 1;
+		if(hit[m].t + ksz <= e) b += ksz; else b += e - hit[m].t;
+		e = hit[m].t;
+	}
+	free(tails); free(pred);
+	if(b < cmin){ free(hit); return 0; }
+	/* drop anchors whose diagonal is far from the mean (:1347-1394) */
+	dl = malloc(sizeof(int) * nh);
+	while(1){
+		int tot = 0, mean, median, var, d;
+		uint32_t cnt = 0, drop = 0;
+		for(i=0;i<nh;i++) if(hit[i].on){ d = (int)hit[i].q - (int)hit[i].t; tot += d; dl[cnt++] = d; }
+		if(cnt * ksz < cmin) break;
+		mean = tot / (int)cnt;
+		qsort(dl, cnt, sizeof(int), bso_int_cmp);
+		median = dl[cnt / 2]; /* quick_median_array, sort.h:268-310: the element of rank size/2 */
+		var = (median > mean ? median - mean : mean - median) * 3;
+		if(var < 50) var = 50;
+		for(i=0;i<nh;i++) if(hit[i].on){
+			d = (int)hit[i].q - (int)hit[i].t - mean;
+			if((d < 0 ? -d : d) > var){ hit[i].on = 0; drop++; }
+		}
+		if(drop == 0) break;
+	}
+	free(dl);
+	m = 0; e = 0;
+	for(i=0;i<nh;i++) if(hit[i].on){ /* target bases covered by the kept anchors (:1403-1413) */
+		if(hit[i].t >= e + ksz) m += ksz; else m += hit[i].t + ksz - e;
+		e = hit[i].t + ksz;
+		aq[kept] = hit[i].q; at[kept] = hit[i].t; kept++;
+	}
+	free(hit);
+	if(m < cmin) return 0;
+	return kept;
+}
+
+typedef struct { uint32_t *buf; uint32_t cap, n; int over; } bso_cv_t;
+static void bso_cv_raw(bso_cv_t *v, uint32_t w){ if(v->buf && v->n < v->cap) v->buf[v->n] = w; else if(v->buf) v->over = 1; v->n++; }
+static void bso_cv_push(bso_cv_t *v, uint32_t op, uint32_t sz){ /* _push_cigar_u4v, :401-407 */
+	if(v->n && v->buf && v->n <= v->cap && (v->buf[v->n - 1] & 0xf) == op) v->buf[v->n - 1] += sz << 4;
+	else bso_cv_raw(v, sz << 4 | op);
+}
+
+/* cigar must have room for 2 * (qlen + tlen) + 4 words */
+int bso_kmer_edit_pairwise(uint32_t ksz, const uint8_t *qseq, uint32_t qlen, const uint8_t *tseq, uint32_t tlen,
+		int32_t *rs, uint32_t *cigar, uint32_t cigar_cap, uint32_t *ncigar){
+	uint32_t *aq = malloc(sizeof(uint32_t) * ((size_t)qlen + 1)), *at = malloc(sizeof(uint32_t) * ((size_t)qlen + 1));
+	uint32_t kmap, i, k, qb = 0, tb = 0, qe, te, ml = 0, mode, nseg;
+	int32_t r2[10];
+	int err = 0;
+	bso_cv_t cv;
+	if(ksz > 15) ksz = 15;
+	kmap = bso_kmer_anchors(ksz, qseq, qlen, tseq, tlen, aq, at);
+	if(kmap == 0){
+		free(aq); free(at);
+		return bso_edit_pairwise(qseq, qlen, tseq, tlen, BSO_MODE_GLOBAL, 0, rs, cigar, cigar_cap, ncigar);
+	}
+	memset(rs, 0, 10 * sizeof(int32_t));
+	cv.buf = cigar; cv.cap = cigar_cap; cv.n = 0; cv.over = 0;
+	mode = 3;
+	for(i=0;i<=kmap;i++){
+		if(i == kmap){ qe = qlen; te = tlen; mode = BSO_MODE_EXTEND; }
+		else { qe = aq[i] + ksz / 2; te = at[i] + ksz / 2; ml++; }
+		if(!(qb == qe && tb == te)){
+			uint32_t sq = qe - qb, st = te - tb, *seg = malloc(sizeof(uint32_t) * ((size_t)sq + st + 2));
+			if(ml){ bso_cv_push(&cv, 0, ml); rs[5] += ml; rs[9] += ml; ml = 0; }
+			if(mode == 3){ /* the stretch before the first anchor: EXTEND on the reversed prefixes, then everything so far is reversed (:1489-1499) */
+				uint8_t *rq = malloc(sq + 1), *rt = malloc(st + 1);
+				for(k=0;k<sq;k++) rq[k] = qseq[qe - 1 - k];
+				for(k=0;k<st;k++) rt[k] = tseq[te - 1 - k];
+				err |= bso_edit_pairwise(rq, sq, rt, st, BSO_MODE_EXTEND, 0, r2, seg, sq + st + 2, &nseg);
+				free(rq); free(rt);
+				for(k=0;k<nseg;k++) bso_cv_raw(&cv, seg[k]);
+				rs[1] = qe - r2[2]; rs[3] = te - r2[4]; rs[2] = qe; rs[4] = te;
+				if(cv.buf) for(k=0;k<cv.n/2&&cv.n<=cv.cap;k++){ uint32_t w = cv.buf[k]; cv.buf[k] = cv.buf[cv.n - 1 - k]; cv.buf[cv.n - 1 - k] = w; }
+			} else {
+				err |= bso_edit_pairwise(qseq + qb, sq, tseq + tb, st, (int)mode, 0, r2, seg, sq + st + 2, &nseg);
+				for(k=0;k<nseg;k++) bso_cv_raw(&cv, seg[k]);
+				rs[2] = qb + r2[2]; rs[4] = tb + r2[4];
+			}
+			free(seg);
+			rs[5] += r2[5]; rs[6] += r2[6]; rs[7] += r2[7]; rs[8] += r2[8]; rs[9] += r2[9]; rs[0] += r2[0];
+		}
+		qb = qe + 1; tb = te + 1;
+		mode = BSO_MODE_GLOBAL;
+	}
+	if(ncigar) *ncigar = cv.n;
+	if(cv.over) err |= BSO_ERR_CIGCAP;
+	free(aq); free(at);
+	return err;
 }

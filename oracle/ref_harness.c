@@ -10,6 +10,7 @@
  * Functions wrapped:
  *   banded_striped_epi8_seqalign_pairwise   bsalign.h:3854
  *   striped_seqedit_pairwise                bsalign.h:1046
+ *   kmer_striped_seqedit_pairwise           bsalign.h:1209
  * The reference is single-threaded; the *_batch entry points run a pthread pool over independent
  * pairs, one b1v mempool + u4v cigars per thread.
  */
@@ -57,9 +58,12 @@ static void* bsref_worker(void *arg){
 				if(job->kind == 0){
 					rs = banded_striped_epi8_seqalign_pairwise((u1i*)job->seqs + job->qoff[j], job->qlen[j], (u1i*)job->seqs + job->toff[j], job->tlen[j],
 						mempool, cigars, job->mode, job->bandwidth, mtx, job->go1, job->ge1, job->go2, job->ge2, 0);
-				} else {
+				} else if(job->kind == 1){
 					rs = striped_seqedit_pairwise((u1i*)job->seqs + job->qoff[j], job->qlen[j], (u1i*)job->seqs + job->toff[j], job->tlen[j],
 						job->mode, job->bandwidth, mempool, cigars, 0);
+				} else { // k-mer guided edit (bsalign.h:1209); it reverses a prefix of both sequences in place and restores it
+					rs = kmer_striped_seqedit_pairwise((u1i)job->bandwidth, (u1i*)job->seqs + job->qoff[j], job->qlen[j], (u1i*)job->seqs + job->toff[j], job->tlen[j],
+						mempool, cigars, 0);
 				}
 			}
 			bsref_store_result(job->results + j * 10, &rs);
@@ -112,6 +116,17 @@ int bsref_edit_batch(uint64_t n, const uint8_t *seqs, const uint64_t *qoff, cons
 	memset(&job, 0, sizeof(job));
 	job.kind = 1; job.n = n; job.seqs = seqs; job.qoff = qoff; job.qlen = qlen; job.toff = toff; job.tlen = tlen;
 	job.mode = mode; job.bandwidth = bandwidth;
+	job.results = results; job.cigars = cigars; job.cgoff = cgoff; job.ncigar = ncigar; job.repeat = repeat;
+	return bsref_run(&job, nthreads);
+}
+
+/* kmer_striped_seqedit_pairwise bsalign.h:1209 (main.c:196 `bsalign edit -m kmer -k ksz`); pairs must not share bytes (in-place reversal) */
+int bsref_kmer_edit_batch(uint64_t n, uint8_t *seqs, const uint64_t *qoff, const uint32_t *qlen, const uint64_t *toff, const uint32_t *tlen,
+		uint32_t ksz, int32_t *results, uint32_t *cigars, const uint64_t *cgoff, uint32_t *ncigar, int nthreads, int repeat){
+	bsref_job_t job;
+	memset(&job, 0, sizeof(job));
+	job.kind = 2; job.n = n; job.seqs = seqs; job.qoff = qoff; job.qlen = qlen; job.toff = toff; job.tlen = tlen;
+	job.mode = 0; job.bandwidth = ksz;
 	job.results = results; job.cigars = cigars; job.cgoff = cgoff; job.ncigar = ncigar; job.repeat = repeat;
 	return bsref_run(&job, nthreads);
 }

@@ -85,6 +85,36 @@ def run_batch(lib, prefix, kind, batch, mode, bandwidth, mtx=None, gaps=(0, 0, 0
     return res, cigs, rc
 
 
+def kmer_caps(batch):
+    cap = 2 * (batch.qlen.astype(np.uint64) + batch.tlen.astype(np.uint64)) + 8
+    off = np.zeros(batch.n + 1, dtype=np.uint64)
+    np.cumsum(cap, out=off[1:])
+    return off
+
+
+def kmer_batch(which, batch, ksz, nthreads=1, repeat=1, errs=None):
+    """kmer_striped_seqedit_pairwise (bsalign.h:1209) over a batch: which = 'ref' (the compiled reference; it reverses sequence prefixes in
+    place and restores them, so it gets its own copy of the arena) or 'oracle'.  Returns (results, cigars, rc)."""
+    n = batch.n
+    res = np.zeros((n, 10), dtype=np.int32)
+    off = kmer_caps(batch)
+    arena = np.zeros(int(off[-1]), dtype=np.uint32)
+    ncg = np.zeros(n, dtype=np.uint32)
+    seqs = batch.seqs.copy()
+    global last_call_seconds
+    import time as _time
+    _t0 = _time.perf_counter()
+    if which == "ref":
+        rc = ref().bsref_kmer_edit_batch(ctypes.c_uint64(n), _ptr(seqs), _ptr(batch.qoff), _ptr(batch.qlen), _ptr(batch.toff), _ptr(batch.tlen),
+                                         ctypes.c_uint32(ksz), _ptr(res), _ptr(arena), _ptr(off), _ptr(ncg), ctypes.c_int(nthreads), ctypes.c_int(repeat))
+    else:
+        rc = oracle().bso_kmer_edit_batch(ctypes.c_uint64(n), _ptr(seqs), _ptr(batch.qoff), _ptr(batch.qlen), _ptr(batch.toff), _ptr(batch.tlen),
+                                          ctypes.c_uint32(ksz), _ptr(res), _ptr(arena), _ptr(off), _ptr(ncg), ctypes.c_int(nthreads), ctypes.c_int(repeat),
+                                          _ptr(errs) if errs is not None else None)
+    last_call_seconds = _time.perf_counter() - _t0
+    return res, split_cigars(arena, off, ncg), rc
+
+
 def ref_batch(kind, batch, mode, bandwidth, mtx=None, gaps=(0, 0, 0, 0), **kw):
     return run_batch(ref(), "bsref", kind, batch, mode, bandwidth, mtx, gaps, **kw)
 
