@@ -375,6 +375,55 @@ def main_poa(args, w, njobs, ncores, rank, local_rank, world):
         dist.destroy_process_group()
 
 
+def run_kmer_edit(ctx, ncores, pairs=1000000, qlen=300, ksz=13, steps=2, warmup=2, cpu_seconds=5.0, check=256):
+    """the k-mer guided edit (kmer_striped_seqedit_pairwise, bsalign.h:1209; `bsalign edit -m kmer -k 13`) on the
+    configs[3] batch shape.  No band-cell count describes this path (the anchors replace most of the DP), so the unit is pairs per second:
+    kernel-only from the CUDA events of the call, end to end = wall time of ONE C-ABI call with pinned host buffers; the reference is the
+    unmodified kmer_striped_seqedit_pairwise on all host cores."""
+    import torch
+    import checkers as ck
+    from bsalign_b200 import api, synth
+    w = WORKLOADS["c4"]
+    batch = synth.make_pairs(pairs, qlen, 1000, *w["err"])
+    pin = lambda a: torch.from_numpy(a).pin_memory().numpy()
+    hb = synth.PairBatch.__new__(synth.PairBatch)
+    hb.seqs, hb.qoff, hb.qlen, hb.toff, hb.tlen = pin(batch.seqs), pin(batch.qoff), pin(batch.qlen), pin(batch.toff), pin(batch.tlen)
+    outbuf = tuple(pin(a) if a is not None else None for a in api._alloc_out(hb, True))
+    got = None
+    walls, kern, fb = [], [], []
+    for it in range(warmup + steps):
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        got = ctx.kmer_edit_batch(hb, ksz, dense=True, out=outbuf)
+        dt = time.perf_counter() - t0
+        tm = ctx.timing()
+        if it >= warmup:
+            walls.append(dt); kern.append(tm["forward_ms"] + tm["traceback_ms"]); fb.append(tm["waves"])
+    wall = sum(walls) / len(walls); kms = sum(kern) / len(kern)
+    out = {"workload": "c4k: configs[3] batch shape (1M pairs 300bp x 300bp) through the k-mer guided edit, k = %d" % ksz, "pairs": int(batch.n),
+           "unit": "Mpairs/s", "value": batch.n / (kms * 1e-3) / 1e6, "kernel_ms_per_step": kms, "e2e": batch.n / wall / 1e6, "e2e_ms_per_step": wall * 1e3,
+           "pairs_without_anchors": int(fb[-1]), "gpu_launches": int(tm["forward_launches"] + tm["other_launches"]),
+           "h2d_bytes_per_step": int(tm["h2d_bytes"]), "d2h_bytes_per_step": int(tm["d2h_bytes"]), "steps": steps, "warmup": warmup}
+    gc = got.cigars()
+    m = min(check, batch.n)
+    sub = synth.PairBatch(batch.seqs, batch.qoff[:m], batch.qlen[:m], batch.toff[:m], batch.tlen[:m])
+    exp, ecg, _ = ck.kmer_batch("oracle", sub, ksz, nthreads=ncores)
+    ok = bool(np.array_equal(exp, got.results[:m]) and all(np.array_equal(ecg[i], gc[i]) for i in range(m)))
+    out["parity"] = {"checked": {"pairs": m, "against": "oracle", "bit_exact": ok}}
+    if cpu_seconds and ck.have_ref():
+        m = min(batch.n, 20000)
+        sub = synth.PairBatch(batch.seqs, batch.qoff[:m], batch.qlen[:m], batch.toff[:m], batch.tlen[:m])
+        t0 = time.perf_counter()
+        r, c, _ = ck.kmer_batch("ref", sub, ksz, nthreads=ncores)
+        dt = time.perf_counter() - t0
+        rate = m / dt / 1e6
+        out["cpu"] = {"value": rate, "unit": "Mpairs/s", "cores": ncores, "kind": "reference", "sample": "first %d pairs, %d host threads, %.1f s" % (m, ncores, dt),
+                      "results_equal_gpu": bool(np.array_equal(r, got.results[:m]) and all(np.array_equal(c[i], gc[i]) for i in range(m)))}
+        out["speedup_vs_cpu"] = out["value"] / rate
+        out["e2e_speedup_vs_cpu"] = out["e2e"] / rate
+    return out
+
+
 def load_peaks():
     try:
         return json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
@@ -755,6 +804,11 @@ def main():
                                    "parity": so["parity"], "steps": sargs.steps, "warmup": sargs.warmup}
             except Exception as e:   # a secondary run must never take the headline line with it
                 secondary[name] = {"error": repr(e)}
+        try:
+            ctx.trim()
+            secondary["c4k"] = run_kmer_edit(ctx, ncores, cpu_seconds=0 if args.no_cpu_baseline else 5.0, check=min(args.check, 256))
+        except Exception as e:
+            secondary["c4k"] = {"error": repr(e)}
     if rank == 0:
         line = {"metric": "GCUPS", "value": main_out["value"], "unit": "GCUPS (1e9 band cells/s)", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
                 "ms_per_step": main_out["ms_per_step"], "higher_is_better": True, "scaling": "strong" if world > 1 else "weak", "vs_baseline": None,

@@ -72,6 +72,9 @@ def lib():
                                                  _I8, _I8, _I8, _I8, _P, _P, _P, _P, _P]
         L.bsb200_edit_pairwise_batch.argtypes = [_P, ctypes.c_uint64, _P, _P, _P, _P, _P, ctypes.c_int, ctypes.c_uint32,
                                                  _P, _P, _P, _P, _P]
+        L.bsb200_kmer_edit_batch.argtypes = [_P, ctypes.c_uint64, _P, _P, _P, _P, _P, ctypes.c_uint32, _P, _P, _P, _P, _P]
+        L.bsb200_kmer_edit_batch_dense.argtypes = [_P, ctypes.c_uint64, _P, _P, _P, _P, _P, ctypes.c_uint32, _P, _P, ctypes.c_uint64, _P, _P, _P]
+        L.bsb200_kmer_edit_pairwise.argtypes = [_P, ctypes.c_uint32, _P, ctypes.c_uint32, _P, ctypes.c_uint32, _P, _P, ctypes.c_uint32, _P, _P]
         L.bsb200_batch_upload_dev.restype = _P
         L.bsb200_batch_upload_dev.argtypes = L.bsb200_batch_upload.argtypes
         L.bsb200_pairwise_batch_dense.argtypes = [_P, ctypes.c_int, ctypes.c_uint64, _P, _P, _P, _P, _P, ctypes.c_int, ctypes.c_uint32, _P,
@@ -205,6 +208,24 @@ class Context:
                                                   int(mode), int(bandwidth), _ptr(res), _ptr(cg), _ptr(off), _ptr(ncg), _ptr(st))
         self._check(rc, "bsb200_edit_pairwise_batch")
         return BatchResult(res, cg, off, ncg, st)
+
+    def kmer_edit_batch(self, batch, ksz, dense=False, out=None):
+        """kmer_striped_seqedit_pairwise (bsalign.h:1209) over a batch; dense=True: cigars come back dense and in pair order."""
+        n = batch.n
+        if not dense:
+            res, cg, off, ncg, st = out if out is not None else _alloc_out(batch, True)
+            rc = self._lib.bsb200_kmer_edit_batch(self._h, n, _ptr(batch.seqs), _ptr(batch.qoff), _ptr(batch.qlen), _ptr(batch.toff), _ptr(batch.tlen),
+                                                  int(ksz), _ptr(res), _ptr(cg), _ptr(off), _ptr(ncg), _ptr(st))
+            self._check(rc, "bsb200_kmer_edit_batch")
+            return BatchResult(res, cg, off, ncg, st)
+        res, cg, _off, ncg, st = out if out is not None else _alloc_out(batch, True)
+        total = ctypes.c_uint64(0)
+        rc = self._lib.bsb200_kmer_edit_batch_dense(self._h, n, _ptr(batch.seqs), _ptr(batch.qoff), _ptr(batch.qlen), _ptr(batch.toff), _ptr(batch.tlen),
+                                                    int(ksz), _ptr(res), _ptr(cg), len(cg), ctypes.byref(total), _ptr(ncg), _ptr(st))
+        self._check(rc, "bsb200_kmer_edit_batch_dense")
+        doff = np.zeros(n + 1, dtype=np.uint64)
+        np.cumsum(ncg, out=doff[1:])
+        return BatchResult(res, cg, doff, ncg, st)
 
     # ---- staged form: inputs stay resident in HBM between runs -------------------------------------
     def upload(self, kind, batch, mode, bandwidth, matrix=None, gaps=(0, 0, 0, 0), want_cigar=True):

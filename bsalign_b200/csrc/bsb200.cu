@@ -10,6 +10,7 @@
 #include "epi8_wave.cuh"
 #include "epi8_backcal.cuh"
 #include "edit_kernels.cuh"
+#include "kmer_edit.cuh"
 
 #include <cub/device/device_scan.cuh>
 #include <cub/iterator/transform_input_iterator.cuh>
@@ -80,6 +81,7 @@ struct bsb200_ctx {
 	DevBuf dev_cache[18];
 	HostBuf host_cache[8];
 	DevBuf poa_cache[40];   // same, for POA sweep batches (poa_host.cuh)
+	DevBuf kmer_cache[8];   // k-mer guided edit: warp slots, gap-trace pool, counters, order list, fallback sub-batch results
 	HostBuf poa_hcache[2];
 };
 
@@ -152,6 +154,7 @@ extern "C" void bsb200_destroy(bsb200_ctx *ctx){
 	for(auto &d : ctx->dev_cache) d.release();
 	for(auto &h : ctx->host_cache) h.release();
 	for(auto &d : ctx->poa_cache) d.release();
+	for(auto &d : ctx->kmer_cache) d.release();
 	for(auto &h : ctx->poa_hcache) h.release();
 	for(auto &e : ctx->ev) cudaEventDestroy(e);
 	cudaStreamDestroy(ctx->stream);
@@ -168,6 +171,7 @@ extern "C" void bsb200_trim(bsb200_ctx *ctx){
 	for(auto &d : ctx->dev_cache) d.release();
 	for(auto &h : ctx->host_cache) h.release();
 	for(auto &d : ctx->poa_cache) d.release();
+	for(auto &d : ctx->kmer_cache) d.release();
 	for(auto &h : ctx->poa_hcache) h.release();
 	ctx->auto_budget = 0;
 }
@@ -1025,6 +1029,207 @@ extern "C" int bsb200_batch_fetch_dense_dev(bsb200_ctx *ctx, bsb200_batch *b, in
 	float ms = 0; cudaEventElapsedTime(&ms, ctx->ev[2], ctx->ev[3]);
 	ctx->timing.d2h_ms = ms; ctx->timing.d2h_bytes = 8;
 	return 0;
+}
+
+
+// ---- k-mer guided edit alignment: replaces kmer_striped_seqedit_pairwise (bsalign.h:1209) for batches ------------------------------
+// Anchors, chain, filter, the gap alignments and the stitching run in kmer_edit_kernel (kmer_edit.cuh), one warp per pair.  Pairs without
+// usable anchors come back flagged: the reference aligns those with the plain global edit (bsalign.h:1440), and so do we, as a sub-batch
+// of the edit kernel on the arena that is already on the device.  Output as in bsb200_batch_fetch (cgoff given) or bsb200_batch_fetch_dense.
+static int kmer_edit_impl(bsb200_ctx *ctx, uint64_t n, const uint8_t *seqs, const uint64_t *qoff, const uint32_t *qlen, const uint64_t *toff,
+		const uint32_t *tlen, uint32_t ksz, bsb200_result_t *results, uint32_t *cigars, const uint64_t *cgoff, uint64_t dense_cap, uint64_t *total_words,
+		uint32_t *ncigar, int32_t *status){
+	if(!ctx) return -1;
+	ctx->err.clear();
+	if(total_words) *total_words = 0;
+	if(ksz > 15) ksz = 15;   // bsalign.h:1217
+	if(ksz == 0 || n >= 0xFFFFFFF0ull || (n && (!seqs || !qoff || !qlen || !toff || !tlen))) return fail(ctx, "bsb200_kmer_edit_batch (k-mer size 1..15)", cudaSuccess);
+	if(n == 0) return 0;
+	cudaSetDevice(ctx->device);
+	cudaStream_t st = ctx->stream;
+	const bool hostprof = getenv("BSB200_HOSTPROF") != nullptr;
+	auto tp0 = std::chrono::steady_clock::now();
+	auto lap = [&](const char *what){ if(hostprof){ auto t1 = std::chrono::steady_clock::now(); fprintf(stderr, "[kmer] %-28s %8.3f ms\n", what, std::chrono::duration<double, std::milli>(t1 - tp0).count()); tp0 = t1; } };
+	bsb200_batch *b = new bsb200_batch();
+	{
+		DevBuf *ds[] = {&b->d_seqs, &b->d_qoff, &b->d_toff, &b->d_qlen, &b->d_tlen, &b->d_order, &b->d_trace_off, &b->d_results, &b->d_status,
+			&b->d_ncigar, &b->d_cig_raw, &b->d_cig_off, &b->d_cig_dense, &b->d_dense_off, &b->d_dense_total, &b->d_block_rows, &b->d_prefix, &b->d_bits};
+		for(int k=0;k<18;k++){ *ds[k] = ctx->dev_cache[k]; ctx->dev_cache[k] = DevBuf(); }
+		HostBuf *hs[] = {&b->h_results, &b->h_status, &b->h_ncigar, &b->h_dense_off, &b->h_dense, &b->h_total};
+		for(int k=0;k<6;k++){ *hs[k] = ctx->host_cache[k]; ctx->host_cache[k] = HostBuf(); }
+	}
+	b->kind = 1; b->n = n; b->mode = 0; b->bandwidth = 0; b->want_cigar = 1;
+	cudaEvent_t evk[2] = {nullptr, nullptr};
+	auto done = [&](int rc){ cudaStreamSynchronize(st); for(auto &e_ : evk) if(e_) cudaEventDestroy(e_); bsb200_batch_free(ctx, b); return rc; };
+	#define CKK(call) do { cudaError_t _e = (call); if(_e != cudaSuccess) return done(fail(ctx, #call, _e)); } while(0)
+	const int NT = plan_threads(n);
+	size_t seq_end = 0; uint32_t maxq = 0, maxt = 0; uint64_t cells = 0;
+	b->empty.assign(n, 0);
+	{
+		std::vector<uint64_t> pe(NT, 0), pc(NT, 0), px(NT, 0); std::vector<uint32_t> mq(NT, 0), mt(NT, 0);
+		par_slices(n, NT, [&](int w, uint64_t lo, uint64_t hi){
+			uint64_t se = 0, cc = 0, cx = 0; uint32_t q_ = 0, t_ = 0;   // locals: the per-thread slots share cache lines
+			for(uint64_t i=lo;i<hi;i++){
+				se = std::max<uint64_t>(se, std::max<uint64_t>(qoff[i] + qlen[i], toff[i] + tlen[i]));
+				if(qlen[i] && tlen[i]){ cc += (uint64_t)qlen[i] + tlen[i] + 2; cx += (uint64_t)qlen[i] * tlen[i]; q_ = std::max(q_, qlen[i]); t_ = std::max(t_, tlen[i]); }
+				else b->empty[i] = 1;
+			}
+			pe[w] = se; pc[w] = cc; px[w] = cx; mq[w] = q_; mt[w] = t_;
+		});
+		for(int w=0;w<NT;w++){ seq_end = std::max<size_t>(seq_end, pe[w]); b->cig_words += pc[w]; cells += px[w]; maxq = std::max(maxq, mq[w]); maxt = std::max(maxt, mt[w]); }
+	}
+	lap("scan of the lengths");
+	CKK(b->d_seqs.reserve(seq_end + 16));
+	CKK(b->d_qoff.reserve(n * 8 + 8)); CKK(b->d_toff.reserve(n * 8 + 8)); CKK(b->d_qlen.reserve(n * 4 + 4)); CKK(b->d_tlen.reserve(n * 4 + 4));
+	lap("input buffers");
+	CKK(b->d_results.reserve(n * 40 + 40)); CKK(b->d_status.reserve(n * 4 + 4)); CKK(b->d_ncigar.reserve(n * 4 + 4));
+	CKK(b->d_dense_off.reserve(n * 8 + 8)); CKK(b->d_dense_total.reserve(16));
+	CKK(b->d_cig_raw.reserve(b->cig_words * 4 + 16)); CKK(b->d_cig_dense.reserve(b->cig_words * 4 + 16));
+	CKK(cudaEventCreate(&evk[0])); CKK(cudaEventCreate(&evk[1]));
+	lap("output buffers + events");
+	cudaEventRecord(ctx->ev[0], st);
+	CKK(cudaMemcpyAsync(b->d_seqs.p, seqs, seq_end, cudaMemcpyHostToDevice, st));
+	CKK(cudaMemcpyAsync(b->d_qoff.p, qoff, n * 8, cudaMemcpyHostToDevice, st));
+	CKK(cudaMemcpyAsync(b->d_toff.p, toff, n * 8, cudaMemcpyHostToDevice, st));
+	CKK(cudaMemcpyAsync(b->d_qlen.p, qlen, n * 4, cudaMemcpyHostToDevice, st));
+	CKK(cudaMemcpyAsync(b->d_tlen.p, tlen, n * 4, cudaMemcpyHostToDevice, st));
+	cudaEventRecord(ctx->ev[1], st);
+	// ---- warp slots and the pool for large gap traces ------------------------------------------------------------------------
+	KmerArgs a;
+	memset(&a, 0, sizeof(a));
+	const uint64_t wb = kmer_warp_bytes(maxq, maxt, &a);
+	size_t freeb = 0, totalb = 0;
+	CKK(cudaMemGetInfo(&freeb, &totalb));
+	freeb += ctx->kmer_cache[0].cap + ctx->kmer_cache[1].cap;
+	int occ = 0;
+	CKK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kmer_edit_kernel, kKmWarps * 32, 0));
+	if(occ < 1) occ = 1;
+	uint64_t slots = std::min<uint64_t>((uint64_t)ctx->num_sms * occ * kKmWarps, (n + kKmWarps - 1) / kKmWarps * kKmWarps);
+	if(const char *e_ = getenv("BSB200_KMER_SLOTS")) slots = std::max<uint64_t>(kKmWarps, strtoull(e_, nullptr, 10) / kKmWarps * kKmWarps);
+	while(slots > kKmWarps && slots * wb > freeb / 2) slots = (slots / 2 + kKmWarps - 1) / kKmWarps * kKmWarps;
+	if(slots * wb > freeb / 2) return done(fail(ctx, "k-mer edit: a pair of this length does not fit the device scratch", cudaSuccess));
+	uint64_t pool_bytes = std::min<uint64_t>((freeb - slots * wb) / 2, 16ull << 30);
+	if(const char *e_ = getenv("BSB200_KMER_POOL")) pool_bytes = strtoull(e_, nullptr, 10);
+	pool_bytes = std::max<uint64_t>(pool_bytes, 4096) & ~15ull;
+	CKK(ctx->kmer_cache[0].reserve(slots * wb, true));
+	CKK(ctx->kmer_cache[1].reserve(pool_bytes, true));
+	CKK(ctx->kmer_cache[2].reserve(256));
+	a.seqs = b->d_seqs.as<uint8_t>(); a.qoff = b->d_qoff.as<uint64_t>(); a.toff = b->d_toff.as<uint64_t>();
+	a.qlen = b->d_qlen.as<uint32_t>(); a.tlen = b->d_tlen.as<uint32_t>();
+	a.ksz = ksz;
+	a.next = ctx->kmer_cache[2].as<unsigned int>();
+	a.pool_used = (unsigned long long*)((uint8_t*)ctx->kmer_cache[2].p + 16);
+	a.scratch = ctx->kmer_cache[0].as<uint8_t>();
+	a.pool = ctx->kmer_cache[1].as<uint8_t>(); a.pool_bytes = pool_bytes;
+	a.results = b->d_results.as<int32_t>(); a.status = b->d_status.as<int32_t>(); a.ncigar = b->d_ncigar.as<uint32_t>();
+	a.dense = b->d_cig_dense.as<uint32_t>(); a.dense_off = b->d_dense_off.as<uint64_t>(); a.dense_total = b->d_dense_total.as<unsigned long long>();
+	CKK(cudaMemsetAsync(b->d_dense_total.p, 0, 16, st));
+	CKK(b->h_status.reserve(n * 4));
+	lap("copies queued, scratch");
+	int32_t *hst = b->h_status.as<int32_t>();
+	std::vector<uint32_t> redo, fall;
+	uint32_t launches = 0;
+	cudaEventRecord(evk[0], st);
+	for(int round=0;;round++){
+		// round 0: every pair; later rounds: the pairs that found the pool empty, with fewer warps sharing it
+		const uint64_t np = round == 0 ? n : redo.size();
+		uint64_t warps = round == 0 ? slots : (round == 1 ? std::min<uint64_t>(slots, 2 * kKmWarps) : kKmWarps);
+		if(round > 0){
+			CKK(ctx->kmer_cache[3].reserve(redo.size() * 4 + 16));
+			CKK(cudaMemcpyAsync(ctx->kmer_cache[3].p, redo.data(), redo.size() * 4, cudaMemcpyHostToDevice, st));
+			a.order = ctx->kmer_cache[3].as<uint32_t>();
+		}
+		a.npairs = (uint32_t)np;
+		CKK(cudaMemsetAsync(ctx->kmer_cache[2].p, 0, 32, st));
+		const unsigned grid = (unsigned)(round < 3 ? (warps + kKmWarps - 1) / kKmWarps : 1);
+		kmer_edit_kernel<<<grid, round < 3 ? kKmWarps * 32 : 32, 0, st>>>(a);
+		CKK(cudaGetLastError());
+		launches++;
+		CKK(cudaMemcpyAsync(hst, b->d_status.p, n * 4, cudaMemcpyDeviceToHost, st));
+		CKK(cudaStreamSynchronize(st));
+		std::vector<uint32_t> again;
+		if(round == 0){ for(uint64_t i=0;i<n;i++){ if(hst[i] & kStPool) again.push_back((uint32_t)i); else if(hst[i] & kStFallback) fall.push_back((uint32_t)i); } }
+		else for(uint32_t i : redo){ if(hst[i] & kStPool) again.push_back(i); else if(hst[i] & kStFallback) fall.push_back(i); }
+		redo.swap(again);
+		if(redo.empty()) break;
+		if(round >= 3) return done(fail(ctx, "k-mer edit: the trace of one gap between anchors is larger than the device pool", cudaSuccess));
+	}
+	cudaEventRecord(evk[1], st);
+	lap("kernel rounds");
+	// ---- pairs without anchors: plain global edit (bsalign.h:1440) on the resident arena, results merged back -------------------------
+	float fb_ms = 0; uint32_t fb_launches = 0;
+	if(!fall.empty()){
+		const uint64_t m = fall.size();
+		std::sort(fall.begin(), fall.end());
+		std::vector<uint64_t> sq(m), so(m); std::vector<uint32_t> ql(m), tl(m);
+		for(uint64_t f=0;f<m;f++){ const uint32_t i = fall[f]; sq[f] = qoff[i]; so[f] = toff[i]; ql[f] = qlen[i]; tl[f] = tlen[i]; }
+		bsb200_batch *sb = upload_impl(ctx, 1, m, nullptr, b->d_seqs.as<uint8_t>(), nullptr, sq.data(), ql.data(), so.data(), tl.data(), 0, 0, nullptr, 0, 0, 0, 0, 1);
+		if(!sb) return done(-1);
+		int rc = bsb200_batch_run(ctx, sb);
+		fb_ms = ctx->timing.run_ms; fb_launches = ctx->timing.forward_launches + ctx->timing.traceback_launches + ctx->timing.other_launches;
+		cudaError_t e1 = cudaSuccess;
+		if(rc == 0){
+			e1 = ctx->kmer_cache[4].reserve(m * 40 + 40);
+			if(e1 == cudaSuccess) e1 = ctx->kmer_cache[5].reserve(m * 4 + 4);
+			if(e1 == cudaSuccess) e1 = ctx->kmer_cache[6].reserve(m * 4 + 4);
+			if(e1 == cudaSuccess) e1 = ctx->kmer_cache[7].reserve(sb->cig_words * 4 + 16);
+			if(e1 != cudaSuccess){ fail(ctx, "device allocation", e1); rc = -1; }
+		}
+		uint64_t tw = 0;
+		if(rc == 0) rc = bsb200_batch_fetch_dense_dev(ctx, sb, ctx->kmer_cache[4].as<int32_t>(), ctx->kmer_cache[7].as<uint32_t>(), sb->cig_words + 4, &tw,
+			ctx->kmer_cache[6].as<uint32_t>(), ctx->kmer_cache[5].as<int32_t>());
+		if(rc == 0){
+			CKK(ctx->kmer_cache[3].reserve(m * 4 + 16));
+			cudaError_t e2 = cudaMemcpyAsync(ctx->kmer_cache[3].p, fall.data(), m * 4, cudaMemcpyHostToDevice, st);
+			if(e2 == cudaSuccess){
+				kmer_merge_kernel<<<(unsigned)((m * 32 + 255) / 256), 256, 0, st>>>(ctx->kmer_cache[3].as<uint32_t>(), (uint32_t)m, ctx->kmer_cache[4].as<int32_t>(),
+					ctx->kmer_cache[5].as<int32_t>(), ctx->kmer_cache[6].as<uint32_t>(), ctx->kmer_cache[7].as<uint32_t>(), sb->d_prefix.as<uint64_t>(),
+					a.results, a.status, a.ncigar, a.dense, a.dense_off, a.dense_total);
+				e2 = cudaGetLastError();
+				fb_launches++;
+			}
+			if(e2 == cudaSuccess) e2 = cudaStreamSynchronize(st);
+			if(e2 != cudaSuccess){ fail(ctx, "k-mer edit: merge of the fallback pairs", e2); rc = -1; }
+		}
+		const std::string keep = ctx->err;
+		bsb200_batch_free(ctx, sb);
+		if(rc != 0){ ctx->err = keep; return done(rc); }
+	}
+	lap("fallback pairs");
+	float h2d_ms = 0, k_ms = 0;
+	CKK(cudaStreamSynchronize(st));
+	cudaEventElapsedTime(&h2d_ms, ctx->ev[0], ctx->ev[1]);
+	cudaEventElapsedTime(&k_ms, evk[0], evk[1]);
+	b->ran = true;
+	ctx->timing = bsb200_timing_t();
+	int rc = fetch_impl(ctx, b, results, cigars, cgoff, dense_cap, total_words, ncigar, status);
+	lap("fetch");
+	ctx->timing.h2d_ms = h2d_ms; ctx->timing.h2d_bytes = seq_end + n * 24;
+	ctx->timing.forward_ms = k_ms; ctx->timing.forward_launches = launches;
+	ctx->timing.traceback_ms = fb_ms; ctx->timing.other_launches = fb_launches;   // the fallback sub-batch (edit kernel) and the merge
+	ctx->timing.run_ms = k_ms + fb_ms; ctx->timing.cells = cells; ctx->timing.waves = (uint32_t)fall.size();   // waves: pairs that took the fallback
+	ctx->timing.total_ms = h2d_ms + k_ms + fb_ms + ctx->timing.d2h_ms;
+	#undef CKK
+	return done(rc);
+}
+
+extern "C" int bsb200_kmer_edit_batch(bsb200_ctx *ctx, uint64_t n, const uint8_t *seqs, const uint64_t *qoff, const uint32_t *qlen, const uint64_t *toff,
+		const uint32_t *tlen, uint32_t ksz, bsb200_result_t *results, uint32_t *cigars, const uint64_t *cgoff, uint32_t *ncigar, int32_t *status){
+	return kmer_edit_impl(ctx, n, seqs, qoff, qlen, toff, tlen, ksz, results, cigars, cgoff, 0, nullptr, ncigar, status);
+}
+
+extern "C" int bsb200_kmer_edit_batch_dense(bsb200_ctx *ctx, uint64_t n, const uint8_t *seqs, const uint64_t *qoff, const uint32_t *qlen, const uint64_t *toff,
+		const uint32_t *tlen, uint32_t ksz, bsb200_result_t *results, uint32_t *cigars, uint64_t cigar_cap_words, uint64_t *total_words, uint32_t *ncigar, int32_t *status){
+	return kmer_edit_impl(ctx, n, seqs, qoff, qlen, toff, tlen, ksz, results, cigars, nullptr, cigar_cap_words, total_words, ncigar, status);
+}
+
+extern "C" int bsb200_kmer_edit_pairwise(bsb200_ctx *ctx, uint32_t ksz, const uint8_t *qseq, uint32_t qlen, const uint8_t *tseq, uint32_t tlen,
+		bsb200_result_t *result, uint32_t *cigar, uint32_t cigar_cap, uint32_t *ncigar, int32_t *status){
+	std::vector<uint8_t> arena((size_t)qlen + tlen + 1);
+	if(qlen) memcpy(arena.data(), qseq, qlen);
+	if(tlen) memcpy(arena.data() + qlen, tseq, tlen);
+	const uint64_t qo = 0, to = qlen, cgo[2] = {0, cigar_cap};
+	return kmer_edit_impl(ctx, 1, arena.data(), &qo, &qlen, &to, &tlen, ksz, result, cigar, cigar ? cgo : nullptr, 0, nullptr, ncigar, status);
 }
 
 // ---- host helpers of the multi-GPU split (bsalign_b200/shard.py): compact arenas per shard, pair-ordered merge of the shards' cigars ----

@@ -156,7 +156,7 @@ static inline size_t bsb200_format_pair(std::string &out, const char *qname, uin
 }
 
 // Whole-file command: every two consecutive records of `path` are a pair (main.c:314); they are aligned in batches of `batch_pairs`
-// through bsb200_batch_upload_bits and the text of `bsalign align` (kind 0) / `bsalign edit` (kind 1) goes to `out` in input order.
+// through bsb200_batch_upload_bits and the text of `bsalign align` (kind 0) / `bsalign edit` (kind 1; kind 2 = `edit -m kmer`, bandwidth = k) goes to `out` in input order.
 // Returns the number of pairs, or -1 (message via bsb200_last_error).
 extern "C" int64_t bsb200_align_file(bsb200_ctx *ctx, int kind, const char *path, int mode, uint32_t bandwidth, const int8_t matrix[16],
 		int8_t go1, int8_t ge1, int8_t go2, int8_t ge2, void *out_, uint64_t batch_pairs){
@@ -171,6 +171,7 @@ extern "C" int64_t bsb200_align_file(bsb200_ctx *ctx, int kind, const char *path
 	std::vector<bsb200_result_t> res;
 	std::vector<uint32_t> cig;
 	std::vector<char> rows;
+	std::vector<uint8_t> bases;
 	std::string text;
 	int64_t rc = (int64_t)npairs;
 	for(uint64_t p0=0;p0<npairs&&rc>=0;p0+=batch_pairs){
@@ -183,11 +184,21 @@ extern "C" int64_t bsb200_align_file(bsb200_ctx *ctx, int kind, const char *path
 			cap += (uint64_t)qlen[k] + tlen[k] + 2;
 		}
 		cig.resize(cap);
-		bsb200_batch *b = bsb200_batch_upload_bits(ctx, kind, m, sf->bits.data(), qoff.data(), qlen.data(), toff.data(), tlen.data(), mode, bandwidth, matrix, go1, ge1, go2, ge2, 1);
-		if(!b){ rc = -1; break; }
 		uint64_t total = 0;
-		if(bsb200_batch_run(ctx, b) || bsb200_batch_fetch_dense(ctx, b, res.data(), cig.data(), cap, &total, ncg.data(), nullptr)){ bsb200_batch_free(ctx, b); rc = -1; break; }
-		bsb200_batch_free(ctx, b);
+		if(kind == 2){ // `edit -m kmer -k ksz` (main.c:196): the k-mer size travels in `bandwidth`; one base per byte for this entry point
+			const uint64_t lo = qoff[0], hi = toff[m - 1] + tlen[m - 1];
+			bases.resize(hi - lo + 1);
+			for(uint64_t i=lo;i<hi;i++) bases[i - lo] = (uint8_t)((sf->bits[i >> 5] >> (((~i) & 31) << 1)) & 3);
+			for(uint64_t k=0;k<m;k++){ qoff[k] -= lo; toff[k] -= lo; }
+			const int krc = bsb200_kmer_edit_batch_dense(ctx, m, bases.data(), qoff.data(), qlen.data(), toff.data(), tlen.data(), bandwidth, res.data(), cig.data(), cap, &total, ncg.data(), nullptr);
+			for(uint64_t k=0;k<m;k++){ qoff[k] += lo; toff[k] += lo; }
+			if(krc){ rc = -1; break; }
+		} else {
+			bsb200_batch *b = bsb200_batch_upload_bits(ctx, kind, m, sf->bits.data(), qoff.data(), qlen.data(), toff.data(), tlen.data(), mode, bandwidth, matrix, go1, ge1, go2, ge2, 1);
+			if(!b){ rc = -1; break; }
+			if(bsb200_batch_run(ctx, b) || bsb200_batch_fetch_dense(ctx, b, res.data(), cig.data(), cap, &total, ncg.data(), nullptr)){ bsb200_batch_free(ctx, b); rc = -1; break; }
+			bsb200_batch_free(ctx, b);
+		}
 		uint64_t cpos = 0;
 		text.clear();
 		for(uint64_t k=0;k<m;k++){

@@ -99,6 +99,23 @@ int bsb200_edit_pairwise(bsb200_ctx *ctx, const uint8_t *qseq, uint32_t qlen, co
 		int mode, uint32_t bandwidth,
 		bsb200_result_t *result, uint32_t *cigar, uint32_t cigar_cap, uint32_t *ncigar, int32_t *status);
 
+/* ---- k-mer guided edit alignment: replaces kmer_striped_seqedit_pairwise (bsalign.h:1209-1536; main.c:196 `bsalign edit -m kmer -k ksz`,
+ * bspoa.h:2089) ----
+ * ksz: k-mer size, 1..15 (larger values are clamped to 15 like bsalign.h:1217).  Unique shared canonical k-mers anchor the pair, the
+ * gaps between the anchors are aligned with the edit DP, a pair without usable anchors gets the plain global edit (bsalign.h:1440).
+ * Arguments as bsb200_edit_pairwise_batch; a pair needs room for qlen + tlen + 2 cigar words.  The *_dense form returns the cigars
+ * dense and in pair order like bsb200_pairwise_batch_dense.  Limit: a pair WITHOUT anchors must have qlen <= 16384 (the unbanded
+ * global edit of the fallback). */
+int bsb200_kmer_edit_batch(bsb200_ctx *ctx, uint64_t n, const uint8_t *seqs,
+		const uint64_t *qoff, const uint32_t *qlen, const uint64_t *toff, const uint32_t *tlen, uint32_t ksz,
+		bsb200_result_t *results, uint32_t *cigars, const uint64_t *cgoff, uint32_t *ncigar, int32_t *status);
+int bsb200_kmer_edit_batch_dense(bsb200_ctx *ctx, uint64_t n, const uint8_t *seqs,
+		const uint64_t *qoff, const uint32_t *qlen, const uint64_t *toff, const uint32_t *tlen, uint32_t ksz,
+		bsb200_result_t *results, uint32_t *cigars, uint64_t cigar_cap_words, uint64_t *total_words, uint32_t *ncigar, int32_t *status);
+/* the reference's argument list for ONE pair (bsalign.h:1209 minus mempool / verbose) */
+int bsb200_kmer_edit_pairwise(bsb200_ctx *ctx, uint32_t ksz, const uint8_t *qseq, uint32_t qlen, const uint8_t *tseq, uint32_t tlen,
+		bsb200_result_t *result, uint32_t *cigar, uint32_t cigar_cap, uint32_t *ncigar, int32_t *status);
+
 /* ---- more shapes of the same call (kind: 0 = epi8, 1 = edit; matrix / gaps ignored for kind 1) ------------------------------------ */
 /* one call, cigars DENSE and in pair order (pair i starts at word sum(ncigar[0..i-1]); see bsb200_batch_fetch_dense): the fast path */
 int bsb200_pairwise_batch_dense(bsb200_ctx *ctx, int kind, uint64_t n, const uint8_t *seqs,
@@ -186,7 +203,8 @@ uint32_t bsb200_cigar2alnstr(const uint64_t *bits, uint64_t qoff, uint64_t toff,
 uint64_t bsb200_format_pair_text(char *out, uint64_t cap, const char *qname, uint32_t qlen, const char *tname, uint32_t tlen, const bsb200_result_t *rs,
 		const uint64_t *bits, uint64_t qoff, uint64_t toff, const uint32_t *cigar, uint32_t ncigar);
 /* the whole command: consecutive records of `path` are pairs (main.c:314), aligned in batches through bsb200_batch_upload_bits; the
- * reference's text goes to `out` (a FILE*) in input order.  Returns the number of pairs, or -1. */
+ * reference's text goes to `out` (a FILE*) in input order.  kind 0 = align, 1 = edit, 2 = `edit -m kmer` (bandwidth carries the k-mer
+ * size).  Returns the number of pairs, or -1. */
 int64_t bsb200_align_file(bsb200_ctx *ctx, int kind, const char *path, int mode, uint32_t bandwidth, const int8_t matrix[16],
 		int8_t gapo1, int8_t gape1, int8_t gapo2, int8_t gape2, void *out /* FILE* */, uint64_t batch_pairs /* 0 = 1M */);
 

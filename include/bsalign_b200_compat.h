@@ -108,9 +108,33 @@ static inline seqalign_result_t b200_striped_seqedit_pairwise(u1i *qseq, u4i qle
 	return rs;
 }
 
+/* kmer_striped_seqedit_pairwise, bsalign.h:1209: the cigars are always cleared first (bsalign.h:1438), an empty sequence gives the all-zero result */
+static inline seqalign_result_t b200_kmer_striped_seqedit_pairwise(u1i ksz, u1i *qseq, u4i qlen, u1i *tseq, u4i tlen, b1v *mempool, u4v *cigars, int verbose){
+	seqalign_result_t rs;
+	bsb200_result_t r;
+	uint32_t *buf, n = 0;
+	int32_t st = 0;
+	UNUSED(mempool); UNUSED(verbose);
+	if(cigars) clear_u4v(cigars);
+	if(qlen == 0 || tlen == 0){ memset(&rs, 0, sizeof(seqalign_result_t)); return rs; }
+	buf = cigars? (uint32_t*)malloc(sizeof(uint32_t) * ((size_t)qlen + tlen + 2)) : NULL;
+	if(bsb200_kmer_edit_pairwise(bsalign_b200_default_ctx(), ksz, qseq, qlen, tseq, tlen, &r, buf, qlen + tlen + 2, &n, &st)){
+		fflush(stdout); fprintf(stderr, " -- bsalign_b200: %s in %s -- %s:%d --\n", bsb200_last_error(bsalign_b200_default_ctx()), __FUNCTION__, __FILE__, __LINE__); fflush(stderr);
+		abort();
+	}
+	bsalign_b200_last_status = st;
+	if(st & ~BSB200_ST_EMPTY) BSALIGN_B200_ON_STATUS(st, __FUNCTION__);
+	rs.score = r.score; rs.qb = r.qb; rs.qe = r.qe; rs.tb = r.tb; rs.te = r.te;
+	rs.mat = r.mat; rs.mis = r.mis; rs.ins = r.ins; rs.del = r.del; rs.aln = r.aln;
+	bsalign_b200_take_cigars(cigars, 0, buf, n);
+	if(buf) free(buf);
+	return rs;
+}
+
 #ifdef BSALIGN_B200_OVERRIDE
 #define banded_striped_epi8_seqalign_pairwise b200_banded_striped_epi8_seqalign_pairwise
 #define striped_seqedit_pairwise b200_striped_seqedit_pairwise
+#define kmer_striped_seqedit_pairwise b200_kmer_striped_seqedit_pairwise
 #endif
 
 #endif

@@ -3,8 +3,8 @@
  *
  * Drop-in check of include/bsalign_b200_compat.h against the UNMODIFIED reference headers (compiled from where they lie under
  * /root/reference, see oracle/Makefile): the README program of the reference (README.md:51-80) with every pair going through
- *   (a) banded_striped_epi8_seqalign_pairwise / striped_seqedit_pairwise of the reference (bsalign.h:3854, :1046), and
- *   (b) the same NAMES re-bodied on the GPU (b200_banded_striped_epi8_seqalign_pairwise / b200_striped_seqedit_pairwise),
+ *   (a) banded_striped_epi8_seqalign_pairwise / striped_seqedit_pairwise / kmer_striped_seqedit_pairwise of the reference (bsalign.h:3854, :1046, :1209), and
+ *   (b) the same NAMES re-bodied on the GPU (b200_banded_striped_epi8_seqalign_pairwise / b200_striped_seqedit_pairwise / b200_kmer_striped_seqedit_pairwise),
  * same mempool / cigars vectors, modes with and without SEQALIGN_MODE_CIGRESV; seqalign_result_t and every cigar word must be equal.
  * Also checks that a pair the library flags (the reference's traceback never terminates on it) does not come back looking valid:
  * the status hook is called.
@@ -65,6 +65,12 @@ int main(int argc, char **argv){
 		ra = striped_seqedit_pairwise(q, ql, t, tlen, mode, (mode == SEQALIGN_MODE_GLOBAL) ? 64 : 0, mempool, ca, 0);
 		rb = b200_striped_seqedit_pairwise(q, ql, t, tlen, mode, (mode == SEQALIGN_MODE_GLOBAL) ? 64 : 0, mempool, cb, 0);
 		if(!same_result(&ra, &rb) || !same_cigars(ca, cb)){ bad ++; fprintf(stderr, "pair %u edit mode %d: score %d vs %d, cigars %u vs %u\n", p, mode, ra.score, rb.score, (u4i)ca->size, (u4i)cb->size); }
+		done ++;
+		/* k-mer guided edit (bsalign.h:1209): it reverses a prefix of both sequences in place and restores it */
+		clear_u4v(ca); clear_u4v(cb); push_u4v(cb, 0x55);
+		ra = kmer_striped_seqedit_pairwise((p & 1) ? 13 : 7, q, ql, t, tlen, mempool, ca, 0);
+		rb = b200_kmer_striped_seqedit_pairwise((p & 1) ? 13 : 7, q, ql, t, tlen, mempool, cb, 0);
+		if(!same_result(&ra, &rb) || !same_cigars(ca, cb)){ bad ++; fprintf(stderr, "pair %u kmer edit: score %d vs %d, cigars %u vs %u\n", p, ra.score, rb.score, (u4i)ca->size, (u4i)cb->size); }
 		done ++;
 	}
 	/* the empty-input rule of the edit entry point (bsalign.h:1051-1054) */

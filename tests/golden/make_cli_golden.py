@@ -22,7 +22,8 @@ sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))
 REF = os.path.join(ROOT, "oracle", "_ref", "bsalign_ref")
 RUN_SH = {"NoBand": ["align", "-M", "2", "-X", "2", "-O", "4", "-E", "2", "-Q", "0", "-P", "0"],
           "Band64": ["align", "-W", "64", "-M", "2", "-X", "2", "-O", "4", "-E", "2", "-Q", "0", "-P", "0", "-m", "overlap"],
-          "Edit0": ["edit", "-W", "0"]}
+          "Edit0": ["edit", "-W", "0"],
+          "Kmer13": ["edit", "-m", "kmer", "-k", "13"]}   # not in run.sh: the k-mer guided edit (main.c:196) on the same file
 
 
 def write_real_fasta(path):
@@ -57,7 +58,7 @@ def main():
     with gzip.open(os.path.join(HERE, "cli_small.fq.gz"), "wt") as f:
         f.write(fq)
     for src in ("cli_small.fa", "cli_small.fq.gz"):
-        for name, args in (("align", ["align", "-m", "global"]), ("edit", ["edit"])):
+        for name, args in (("align", ["align", "-m", "global"]), ("edit", ["edit"]), ("kmer", ["edit", "-m", "kmer", "-k", "9"])):
             txt = subprocess.run([REF] + args + [os.path.join(HERE, src)], capture_output=True, check=True).stdout
             open(os.path.join(HERE, "%s.%s.txt" % (src.split(".")[0] + "_" + src.split(".")[1], name)), "wb").write(txt)
             print(src, name, len(txt))

@@ -311,7 +311,7 @@ def test_real_ont_example_all_pairs(ctx):
 
 def test_pairwise_compat_header_runs_against_reference():
     """include/bsalign_b200_compat.h EXECUTED: a C program built from the reference's own headers calls the reference functions and the
-    re-bodied ones on the same pairs (oracle/pairwise_dropin_test.c; built by oracle/Makefile where the reference tree exists, travels
+    re-bodied ones (epi8, edit, k-mer guided edit) on the same pairs (oracle/pairwise_dropin_test.c; built by oracle/Makefile where the reference tree exists, travels
     as a binary) - identical seqalign_result_t + cigar vectors, CIGRESV appends, empty edit input, and a flagged pair reaches the
     status hook instead of looking valid."""
     import subprocess
@@ -321,7 +321,7 @@ def test_pairwise_compat_header_runs_against_reference():
     for args in (["40", "500", "3"], ["12", "2300", "9"]):
         out = subprocess.run([exe] + args, capture_output=True, text=True, timeout=600)
         assert out.returncode == 0, out.stdout + out.stderr
-        n = 2 * int(args[0])
+        n = 3 * int(args[0])   # epi8, edit and the k-mer guided edit of every pair
         assert "identical=%d/%d" % (n, n) in out.stdout and "flagged_calls=0" not in out.stdout, out.stdout
 
 
@@ -382,3 +382,50 @@ def test_command_line_text_equals_reference_on_real_example(tmp_path):
         out = subprocess.run([exe] + g["args"] + [str(fa)], capture_output=True, timeout=600)
         assert out.returncode == 0, out.stderr.decode()
         assert len(out.stdout) == g["bytes"] and hashlib.md5(out.stdout).hexdigest() == g["md5"], name
+
+
+def test_kmer_edit_matches_golden_and_oracle(ctx, monkeypatch):
+    """The k-mer guided edit (bsb200_kmer_edit_batch, replaces kmer_striped_seqedit_pairwise bsalign.h:1209): the reference's golden answers,
+    then seeded batches against the oracle - short and long pairs, pairs without anchors (plain global edit), the dense output form, a
+    starved pool for large gap traces (retry rounds) and few warp slots."""
+    from test_oracle import kmer_golden
+    batch, cases = kmer_golden()
+    for k, res, cigs in cases:
+        got = ctx.kmer_edit_batch(batch, k, dense=(k == 9))
+        assert np.array_equal(got.results, res), k
+        assert all(np.array_equal(a, b) for a, b in zip(got.cigars(), cigs)), k
+        st = got.status.copy()
+        st[batch.qlen == 0] &= ~16
+        assert not st.any()
+    rng = np.random.default_rng(123)
+
+    def related(n, qlen, p):
+        q = rng.integers(0, 4, (n, qlen)).astype(np.uint8)
+        t, tl = synth.mutate_batch(rng, q, p, p, p)
+        out, o = [], 0
+        for i in range(n):
+            out.append((q[i].copy(), t[o + (i % 4) * 5:o + tl[i]].copy()))
+            o += tl[i]
+        return out
+
+    def check(b, k, **kw):
+        got = ctx.kmer_edit_batch(b, k, **kw)
+        exp, ecg, _ = ck.kmer_batch("oracle", b, k, nthreads=8)
+        assert np.array_equal(got.results, exp), k
+        assert all(np.array_equal(x, y) for x, y in zip(got.cigars(), ecg)), k
+        return got
+    pairs = related(3000, 300, .03) + related(300, 1000, .05) + related(500, 80, .1) + related(6, 15000, .03)
+    pairs += [(rng.integers(0, 4, 90).astype(np.uint8), rng.integers(0, 4, 70).astype(np.uint8)) for _ in range(40)]
+    b = synth.PairBatch.from_lists(pairs)
+    check(b, 13)
+    assert ctx.timing()["waves"] >= 40          # the unrelated pairs took the plain global edit
+    check(b, 13, dense=True)
+    check(b, 6)
+    core = rng.integers(0, 4, 1500).astype(np.uint8)
+    gap = np.concatenate([core[:200], rng.integers(0, 4, 900).astype(np.uint8), core[1200:]])
+    big = synth.PairBatch.from_lists([(core, gap), (gap, core)] * 6 + related(4, 15000, .04))
+    check(big, 13)
+    monkeypatch.setenv("BSB200_KMER_POOL", "2000000")   # a few 900 x 900 gaps at a time
+    check(big, 13)
+    monkeypatch.setenv("BSB200_KMER_SLOTS", "4")
+    check(b, 13)

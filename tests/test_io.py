@@ -35,6 +35,9 @@ def test_formatter_reproduces_reference_text():
             res, cigs, _ = ck.oracle_batch(kind, batch, mode, 0, mtx, (-3, -2, 0, 0))
             text = b"".join(api.format_pair_text(sf, k, res[k], cigs[k]) for k in range(npair))
             assert text == open(os.path.join(GOLD, "%s.%s.txt" % (tag, name)), "rb").read(), (src, name)
+        res, cigs, _ = ck.kmer_batch("oracle", batch, 9)   # `edit -m kmer -k 9` (main.c:196)
+        text = b"".join(api.format_pair_text(sf, k, res[k], cigs[k]) for k in range(npair))
+        assert text == open(os.path.join(GOLD, "%s.kmer.txt" % tag), "rb").read(), (src, "kmer")
 
 
 def test_binary_msa_round_trips_the_reference_bytes(tmp_path):

@@ -60,6 +60,46 @@ def test_oracle_edit_matches_golden():
     assert check_against(run, z, batch, "edit") > 400
 
 
+def kmer_golden():
+    z, batch = load_golden("kmer_golden.npz")
+    cases = []
+    for ci, k in enumerate(z["ks"]):
+        ncig = z["ncig%d" % ci]
+        off = np.concatenate([[0], np.cumsum(ncig.astype(np.int64))]).astype(np.int64)
+        cases.append((int(k), z["res%d" % ci], [z["cig%d" % ci][int(off[i]):int(off[i + 1])] for i in range(len(ncig))]))
+    return batch, cases
+
+
+def test_oracle_kmer_edit_matches_golden():
+    """kmer_striped_seqedit_pairwise (bsalign.h:1209): the oracle's restatement against the answers of the unmodified reference
+    (tests/golden/make_kmer_golden.py): 96 pairs x 4 k-mer sizes, anchored pairs, pairs without anchors, clipped ends, big gaps."""
+    batch, cases = kmer_golden()
+    for k, res, cigs in cases:
+        r, c, _ = ck.kmer_batch("oracle", batch, k, nthreads=4)
+        assert np.array_equal(r, res), k
+        assert all(np.array_equal(a, b) for a, b in zip(c, cigs)), k
+
+
+@pytest.mark.skipif(not ck.have_ref(), reason="oracle/_ref not built (no /root/reference on this box)")
+def test_oracle_kmer_edit_vs_compiled_reference():
+    rng = np.random.default_rng(77)
+    for k in (13, 6, 1, 15):
+        pairs = []
+        for n, qlen, ps in ((30, 250, .04), (10, 900, .06), (20, 70, .1), (10, 400, .25)):
+            q = rng.integers(0, 4, (n, qlen)).astype(np.uint8)
+            t, tl = synth.mutate_batch(rng, q, ps, ps, ps)
+            o = 0
+            for i in range(n):
+                pairs.append((q[i].copy(), t[o + (i % 3) * 4:o + tl[i]].copy()))
+                o += tl[i]
+        pairs += [(rng.integers(0, 4, 50).astype(np.uint8), rng.integers(0, 4, 61).astype(np.uint8)) for _ in range(4)]
+        batch = synth.PairBatch.from_lists(pairs)
+        r1, c1, _ = ck.kmer_batch("ref", batch, k, nthreads=4)
+        r2, c2, _ = ck.kmer_batch("oracle", batch, k, nthreads=4)
+        assert np.array_equal(r1, r2), k
+        assert all(np.array_equal(a, b) for a, b in zip(c1, c2)), k
+
+
 def test_readme_example():
     """README.md:36-42 of the reference: pair 29.1/29.2, score 128, 71 matches, 4 mismatches, one indel."""
     z = np.load(os.path.join(GOLD, "readme_pair.npz"))
