@@ -231,6 +231,9 @@ static inline int b200_align_rd_bspoacore(bsb200_ctx *ctx, BSPOA *g, BSPOAPar *p
 typedef struct {
 	bsb200_ctx *ctx; BSPOA **gs; u4i n, *nheads, *ntails, *slot; u2i rid; b200_poa_pack_t *p;
 	int phase; volatile u4i next;
+#ifdef BSALIGN_B200_POA_KMER_H
+	b200_poa_kmer_slot_t *kslot;   /* per object: the band-placement alignment of this round, computed as one GPU batch */
+#endif
 } b200_poa_round_t;
 
 static inline void b200_poa_round_object(b200_poa_round_t *r, u4i k){
@@ -248,7 +251,29 @@ static inline void b200_poa_round_object(b200_poa_round_t *r, u4i k){
 		r->ntails[k] = get_rdnode_bspoa(g, rid, rlen)->header;
 		if(g->par->nrec){ ridxbeg = num_max(0, Int(rid) - g->par->nrec - 1); ridxend = rid; } else { ridxbeg = 0; ridxend = MAX_U2; }
 		sel_nodes_bspoa(g, r->nheads[k], r->ntails[k], ridxbeg, ridxend);
+#ifdef BSALIGN_B200_POA_KMER_H
+		/* with bsalign_b200_poa_kmer.h the round stops here: does prepare_rd_align_bspoa align the read against the consensus with the
+		 * k-mer guided edit (the conditions of bspoa.h:2052-2088)?  Then the read is unpacked now (prepare does the same again) and the
+		 * alignment of all such objects is one GPU batch between phase 0 and phase 3 */
+		r->slot[k] = MAX_U4 - 3;
+		r->kslot[k].armed = 0;
+		if(g->par->bwtrigger && g->par->ksz && ref_bspoanodev(g->nodes, r->nheads[k])->header == g->HEAD && ref_bspoanodev(g->nodes, r->ntails[k])->header == g->TAIL
+				&& !(g->par->refmode && g->cges->buffer[rid] > g->cgbs->buffer[rid]) && g->cns->size && Int(roundup_times(rlen, WORDSIZE)) > g->par->bandwidth){
+			clear_and_encap_u1v(g->qseq, rlen);
+			bitseq_basebank(g->seqs->rdseqs, g->seqs->rdoffs->buffer[rid], rlen, g->qseq->buffer);
+			g->qseq->size = rlen;
+			r->kslot[k].armed = -1;   /* wanted */
+		}
+	} else if(r->phase == 3){   /* the rest of phase 0 once the batch of k-mer guided alignments is back */
+		u4i rlen;
+		if(r->slot[k] != MAX_U4 - 3) return;
+		rlen = g->seqs->rdlens->buffer[rid];
+		b200_poa_kmer_slot = r->kslot[k].armed == 1 ? &r->kslot[k] : NULL;
 		prepare_rd_align_bspoa(g, g->par, r->nheads[k], r->ntails[k], rid, 0, rlen);
+		b200_poa_kmer_slot = NULL;
+#else
+		prepare_rd_align_bspoa(g, g->par, r->nheads[k], r->ntails[k], rid, 0, rlen);
+#endif
 		if(g->sels->size == 0){ align_rd_bspoacore(g, g->par, rid, r->nheads[k], r->ntails[k]); r->slot[k] = MAX_U4 - 1; return; }
 		r->slot[k] = MAX_U4 - 2;   /* takes part in this round's batch */
 	} else if(r->phase == 1){   /* behind the sweep: the tail of align_rd_bspoa (bspoa.h:2652-2666) */
@@ -306,6 +331,66 @@ static inline void b200_poa_round_run(b200_poa_round_t *r, int phase){
 	for(t=1;t<nt;t++) pthread_join(th[t], NULL);
 }
 
+#ifdef BSALIGN_B200_POA_KMER_H
+/* kmer_striped_seqedit_pairwise(par->ksz, g->qseq, g->cns) of every object that asked for it in phase 0 as ONE bsb200_kmer_edit_batch call;
+ * the results wait in the objects' slots for the hook (bsalign_b200_poa_kmer.h).  All objects of a batch share par->ksz or are grouped by it. */
+static uint32_t *b200_poa_kmer_cig = NULL; static uint64_t b200_poa_kmer_cigcap = 0;
+static uint8_t *b200_poa_kmer_arena = NULL; static uint64_t b200_poa_kmer_arenacap = 0;
+static unsigned long b200_poa_kmer_batches = 0, b200_poa_kmer_pairs = 0;
+static inline void b200_poa_kmer_round(b200_poa_round_t *r){
+	u4i k, m = 0, ksz;
+	uint64_t *qoff, *toff, *cgoff, bytes = 0, words = 0;
+	uint32_t *qlen, *tlen, *ncg, *idx;
+	bsb200_result_t *res;
+	for(k=0;k<r->n;k++) if(r->slot[k] == MAX_U4 - 3 && r->kslot[k].armed == -1) m ++;
+	if(m == 0) return;
+	qoff = (uint64_t*)malloc(sizeof(uint64_t) * (3 * (size_t)m + 1)); toff = qoff + m; cgoff = toff + m;
+	qlen = (uint32_t*)malloc(sizeof(uint32_t) * 4 * (size_t)m); tlen = qlen + m; ncg = tlen + m; idx = ncg + m;
+	res = (bsb200_result_t*)malloc(sizeof(bsb200_result_t) * m);
+	while(1){   /* one batch per distinct k-mer size (normally one) */
+		u4i j = 0;
+		ksz = 0; bytes = 0; words = 0;
+		for(k=0;k<r->n;k++){
+			BSPOA *g = r->gs[k];
+			if(r->slot[k] != MAX_U4 - 3 || r->kslot[k].armed != -1) continue;
+			if(ksz == 0) ksz = g->par->ksz;
+			if((u4i)g->par->ksz != ksz) continue;
+			idx[j] = k; qlen[j] = g->qseq->size; tlen[j] = g->cns->size;
+			qoff[j] = bytes; toff[j] = bytes + qlen[j]; bytes += (uint64_t)qlen[j] + tlen[j];
+			cgoff[j] = words; words += (uint64_t)qlen[j] + tlen[j] + 2;
+			j ++;
+		}
+		if(j == 0) break;
+		cgoff[j] = words;
+		if(bytes > b200_poa_kmer_arenacap){ b200_poa_kmer_arenacap = bytes + bytes / 4; b200_poa_kmer_arena = (uint8_t*)realloc(b200_poa_kmer_arena, b200_poa_kmer_arenacap); }
+		if(words > b200_poa_kmer_cigcap){ b200_poa_kmer_cigcap = words + words / 4; b200_poa_kmer_cig = (uint32_t*)realloc(b200_poa_kmer_cig, sizeof(uint32_t) * b200_poa_kmer_cigcap); }
+		for(k=0;k<j;k++){
+			BSPOA *g = r->gs[idx[k]];
+			memcpy(b200_poa_kmer_arena + qoff[k], g->qseq->buffer, qlen[k]);
+			memcpy(b200_poa_kmer_arena + toff[k], g->cns->buffer, tlen[k]);
+		}
+		if(bsb200_kmer_edit_batch(r->ctx, j, b200_poa_kmer_arena, qoff, qlen, toff, tlen, ksz, res, b200_poa_kmer_cig, cgoff, ncg, NULL)){
+			fflush(stdout); fprintf(stderr, " -- bsalign_b200: %s in %s -- %s:%d --\n", bsb200_last_error(r->ctx), __FUNCTION__, __FILE__, __LINE__); fflush(stderr);
+			abort();
+		}
+		b200_poa_kmer_batches ++; b200_poa_kmer_pairs += j;
+		for(k=0;k<j;k++){
+			b200_poa_kmer_slot_t *s = r->kslot + idx[k];
+			s->qlen = qlen[k]; s->tlen = tlen[k];
+			s->rs.score = res[k].score; s->rs.qb = res[k].qb; s->rs.qe = res[k].qe; s->rs.tb = res[k].tb; s->rs.te = res[k].te;
+			s->rs.mat = res[k].mat; s->rs.mis = res[k].mis; s->rs.ins = res[k].ins; s->rs.del = res[k].del; s->rs.aln = res[k].aln;
+			s->cigar = b200_poa_kmer_cig + cgoff[k]; s->ncigar = ncg[k];
+			s->armed = 1;
+		}
+		if(j == m) break;
+		/* other k-mer sizes remain: their cigars would overwrite this batch's, so those objects fall back to the reference's CPU call */
+		for(k=0;k<r->n;k++) if(r->slot[k] == MAX_U4 - 3 && r->kslot[k].armed == -1) r->kslot[k].armed = 0;
+		break;
+	}
+	free(qoff); free(qlen); free(res);
+}
+#endif
+
 static inline void b200_end_bspoa_batch(bsb200_ctx *ctx, BSPOA **gs, u4i n){
 	b200_poa_pack_t *p = b200_poa_pack_init();
 	u4i k, maxr = 0, *nheads, *ntails, *slot;
@@ -330,10 +415,17 @@ static inline void b200_end_bspoa_batch(bsb200_ctx *ctx, BSPOA **gs, u4i n){
 	{
 		b200_poa_round_t rd;
 		rd.ctx = ctx; rd.gs = gs; rd.n = n; rd.nheads = nheads; rd.ntails = ntails; rd.slot = slot; rd.p = p;
+#ifdef BSALIGN_B200_POA_KMER_H
+		rd.kslot = (b200_poa_kmer_slot_t*)calloc(n + 1, sizeof(b200_poa_kmer_slot_t));
+#endif
 		for(rid=1;rid<maxr;rid++){   /* bspoa.h:4752-4763 with align_rd_bspoa (bspoa.h:2620-2667) split around the sweep */
 			b200_poa_pack_clear(p);
 			rd.rid = rid;
 			b200_poa_round_run(&rd, 0);
+#ifdef BSALIGN_B200_POA_KMER_H
+			b200_poa_kmer_round(&rd);
+			b200_poa_round_run(&rd, 3);
+#endif
 			for(k=0;k<n;k++){   /* the batch is packed in object order */
 				if(slot[k] != MAX_U4 - 2) continue;
 				slot[k] = p->njobs;
@@ -348,6 +440,9 @@ static inline void b200_end_bspoa_batch(bsb200_ctx *ctx, BSPOA **gs, u4i n){
 		}
 		rd.rid = 0;
 		b200_poa_round_run(&rd, 2);
+#ifdef BSALIGN_B200_POA_KMER_H
+		free(rd.kslot);
+#endif
 	}
 	free(nheads); free(ntails); free(slot);
 	b200_poa_pack_free(p);

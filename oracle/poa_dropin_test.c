@@ -8,6 +8,8 @@
  * and the consensus, its qualities, the alternative bases and the whole MSA matrix must be byte-identical.
  * Usage: poa_dropin <jobs> <reads per job> <template length> <seed> [realn] [host threads, 0 = all cores]
  */
+#include "bsalign.h"
+#include "bsalign_b200_poa_kmer.h"   /* the band-placement alignments of a round become one GPU batch; the reference arm keeps its own CPU call */
 #include "bspoa.h"
 #include "bsalign_b200_poa_compat.h"
 #include <time.h>
@@ -98,8 +100,9 @@ int main(int argc, char **argv){
 		if(!same){ bad ++; fprintf(stderr, "job %u: consensus / MSA differ (cns %u vs %u, msa %u vs %u)\n", j, (u4i)a->cns->size, (u4i)b->cns->size, (u4i)a->msacols->size, (u4i)b->msacols->size); }
 	}
 	{
-		printf("poa_dropin: jobs=%u reads=%u tlen=%u realn=%d  identical=%u/%u  cns_len[0]=%u msa_bytes[0]=%u  host_threads=%d  reference_s=%.3f  gpu_lockstep_s=%.3f  whole_job_speedup=%.2f\n",
-			njobs, nreads, tlen, par.realn, njobs - bad, njobs, (u4i)ga[0]->cns->size, (u4i)ga[0]->msacols->size, nthr, t_ref, t_gpu, t_ref / t_gpu);
+		printf("poa_dropin: jobs=%u reads=%u tlen=%u realn=%d  identical=%u/%u  cns_len[0]=%u msa_bytes[0]=%u  host_threads=%d  reference_s=%.3f  gpu_lockstep_s=%.3f  whole_job_speedup=%.2f  kmer_batches=%lu kmer_pairs=%lu\n",
+			njobs, nreads, tlen, par.realn, njobs - bad, njobs, (u4i)ga[0]->cns->size, (u4i)ga[0]->msacols->size, nthr, t_ref, t_gpu, t_ref / t_gpu,
+			b200_poa_kmer_batches, b200_poa_kmer_pairs);
 	}
 	for(j=0;j<njobs;j++){ free_bspoa(ga[j]); free_bspoa(gb[j]); }
 	bsb200_destroy(ctx);

@@ -123,6 +123,9 @@ def test_poa_dropin_end_bspoa_identical_msa():
             out = subprocess.run([os.path.join(ref_dir, name)] + args, capture_output=True, text=True, timeout=600)
             assert out.returncode == 0, out.stdout + out.stderr
             assert "identical=%s/%s" % (args[0], args[0]) in out.stdout, out.stdout
+            # the band placement of every round (kmer_striped_seqedit_pairwise inside prepare_rd_align_bspoa, bspoa.h:2089) went through
+            # bsb200_kmer_edit_batch: include/bsalign_b200_poa_kmer.h
+            assert "kmer_pairs=" in out.stdout and "kmer_pairs=0" not in out.stdout, out.stdout
 
 
 def _as_dump_like(job):
