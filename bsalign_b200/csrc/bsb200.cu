@@ -1097,15 +1097,21 @@ static int kmer_edit_impl(bsb200_ctx *ctx, uint64_t n, const uint8_t *seqs, cons
 	// ---- warp slots and the pool for large gap traces ------------------------------------------------------------------------
 	KmerArgs a;
 	memset(&a, 0, sizeof(a));
-	const uint64_t wb = kmer_warp_bytes(maxq, maxt, &a);
 	size_t freeb = 0, totalb = 0;
 	CKK(cudaMemGetInfo(&freeb, &totalb));
 	freeb += ctx->kmer_cache[0].cap + ctx->kmer_cache[1].cap;
 	int occ = 0;
 	CKK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kmer_edit_kernel, kKmWarps * 32, 0));
 	if(occ < 1) occ = 1;
-	uint64_t slots = std::min<uint64_t>((uint64_t)ctx->num_sms * occ * kKmWarps, (n + kKmWarps - 1) / kKmWarps * kKmWarps);
+	const uint64_t max_warps = (uint64_t)ctx->num_sms * occ * kKmWarps;
+	// pairs a warp works on at a time: as many as leave every warp of the GPU at least two groups (a group's serial phases use one lane per pair)
+	uint32_t group = 1;
+	while(group < 32 && n >= 2 * max_warps * (group * 2)) group *= 2;
+	if(const char *e_ = getenv("BSB200_KMER_GROUP")){ const long g_ = strtol(e_, nullptr, 10); group = (uint32_t)std::min<long>(32, std::max<long>(1, g_)); }
+	uint64_t slots = std::min<uint64_t>(max_warps, ((n + group - 1) / group + kKmWarps - 1) / kKmWarps * kKmWarps);
 	if(const char *e_ = getenv("BSB200_KMER_SLOTS")) slots = std::max<uint64_t>(kKmWarps, strtoull(e_, nullptr, 10) / kKmWarps * kKmWarps);
+	uint64_t wb = kmer_warp_bytes(maxq, maxt, group, &a);
+	while(group > 1 && slots * wb > freeb / 2){ group /= 2; wb = kmer_warp_bytes(maxq, maxt, group, &a); }
 	while(slots > kKmWarps && slots * wb > freeb / 2) slots = (slots / 2 + kKmWarps - 1) / kKmWarps * kKmWarps;
 	if(slots * wb > freeb / 2) return done(fail(ctx, "k-mer edit: a pair of this length does not fit the device scratch", cudaSuccess));
 	uint64_t pool_bytes = std::min<uint64_t>((freeb - slots * wb) / 2, 16ull << 30);
@@ -1131,20 +1137,24 @@ static int kmer_edit_impl(bsb200_ctx *ctx, uint64_t n, const uint8_t *seqs, cons
 	uint32_t launches = 0;
 	cudaEventRecord(evk[0], st);
 	for(int round=0;;round++){
-		// round 0: every pair; later rounds: the pairs that found the pool empty, with fewer warps sharing it
+		// round 0: every pair.  Round 1: the pairs that found the pool empty, with two CTAs sharing it.  Round 2: what is left, ONE pair
+		// per launch (the pool is handed out by a bump pointer and only the host resets it).
+		const bool single = round >= 2;
 		const uint64_t np = round == 0 ? n : redo.size();
-		uint64_t warps = round == 0 ? slots : (round == 1 ? std::min<uint64_t>(slots, 2 * kKmWarps) : kKmWarps);
 		if(round > 0){
 			CKK(ctx->kmer_cache[3].reserve(redo.size() * 4 + 16));
 			CKK(cudaMemcpyAsync(ctx->kmer_cache[3].p, redo.data(), redo.size() * 4, cudaMemcpyHostToDevice, st));
-			a.order = ctx->kmer_cache[3].as<uint32_t>();
 		}
-		a.npairs = (uint32_t)np;
-		CKK(cudaMemsetAsync(ctx->kmer_cache[2].p, 0, 32, st));
-		const unsigned grid = (unsigned)(round < 3 ? (warps + kKmWarps - 1) / kKmWarps : 1);
-		kmer_edit_kernel<<<grid, round < 3 ? kKmWarps * 32 : 32, 0, st>>>(a);
-		CKK(cudaGetLastError());
-		launches++;
+		for(uint64_t k=0;k<(single ? np : 1);k++){
+			a.order = round == 0 ? nullptr : ctx->kmer_cache[3].as<uint32_t>() + (single ? k : 0);
+			a.npairs = single ? 1u : (uint32_t)np;
+			if(single) a.group = 1;
+			CKK(cudaMemsetAsync(ctx->kmer_cache[2].p, 0, 32, st));
+			const uint64_t warps = round == 0 ? slots : std::min<uint64_t>(slots, 2 * kKmWarps);
+			kmer_edit_kernel<<<single ? 1u : (unsigned)((warps + kKmWarps - 1) / kKmWarps), single ? 32 : kKmWarps * 32, 0, st>>>(a);
+			CKK(cudaGetLastError());
+			launches++;
+		}
 		CKK(cudaMemcpyAsync(hst, b->d_status.p, n * 4, cudaMemcpyDeviceToHost, st));
 		CKK(cudaStreamSynchronize(st));
 		std::vector<uint32_t> again;
@@ -1152,7 +1162,7 @@ static int kmer_edit_impl(bsb200_ctx *ctx, uint64_t n, const uint8_t *seqs, cons
 		else for(uint32_t i : redo){ if(hst[i] & kStPool) again.push_back(i); else if(hst[i] & kStFallback) fall.push_back(i); }
 		redo.swap(again);
 		if(redo.empty()) break;
-		if(round >= 3) return done(fail(ctx, "k-mer edit: the trace of one gap between anchors is larger than the device pool", cudaSuccess));
+		if(single) return done(fail(ctx, "k-mer edit: the gap traces of one pair are larger than the device pool", cudaSuccess));
 	}
 	cudaEventRecord(evk[1], st);
 	lap("kernel rounds");

@@ -3,17 +3,19 @@
 //
 // The reference sorts the canonical k-mers of both sequences, keeps those seen exactly twice (once per sequence, same strand), sorts
 // them by query offset, chains them, filters the chain by diagonal and aligns the gaps between the anchors with the edit DP.  Here:
-//   * ONE WARP PER PAIR (persistent warps fetch pairs from a counter; every warp owns one scratch slot sized for the largest pair).
+//   * persistent warps fetch GROUPS of up to 32 pairs from a counter; every warp owns one scratch slot.  The warp-wide phases run pair
+//     after pair, the serial phases on one lane per pair (group = 1 when a batch has fewer pairs than the GPU has warps).
 //   * unique shared k-mers come from a hash table in the warp's slot instead of two sorts: every lane rolls over its own stretch of
 //     positions and inserts (atomicCAS on the key, the per-sequence value word goes NONE -> offset|strand -> MULTI), then the query
 //     positions are scanned IN ORDER and a ballot compacts
 //     the hits - which is the reference's list after its second sort (query offsets are distinct).
 //   * the chain (patience tails with the reference's own predecessor rule), the diagonal filter (mean / median / 3x rule) and the
-//     coverage tests are sequential per pair: lane 0.
-//   * the gaps between the anchors are independent edit alignments: lane l takes gaps l, l + 32, ... - a Myers/Hyyro bit-vector DP of
+//     coverage tests are sequential per pair: one lane.
+//   * the gaps between the anchors are independent edit alignments: the gaps of all pairs of a group form one work list that is
+//     spread over the lanes - a Myers/Hyyro bit-vector DP of
 //     (gap length / 64) words per row whose trace lives in the lane's own scratch (one-word gaps up to 127 rows) or in a pool
 //     (anything larger; a pair that finds the pool empty is flagged and run again by the host once the pool is free).
-//   * lane 0 stitches the gap cigars around the anchor matches with the reference's push order (bsalign.h:1461-1531) and the warp
+//   * one lane stitches the gap cigars around the anchor matches with the reference's push order (bsalign.h:1461-1531) and the warp
 //     copies the result into the dense cigar arena.
 // A pair without usable anchors is flagged kStFallback: the host runs those through the plain global edit kernel (bsalign.h:1440).
 #pragma once
@@ -34,30 +36,41 @@ struct KmerArgs {
 	const uint32_t *qlen, *tlen;
 	const uint32_t *order;           // pairs of this launch (nullptr: 0 .. npairs-1)
 	uint32_t npairs, ksz;
+	uint32_t group;                  // pairs a warp works on at a time (1..32)
 	unsigned int *next;              // pair counter
 	uint8_t *scratch; uint64_t warp_bytes;
-	uint64_t off_kq, off_hq, off_ht, off_tails, off_pred, off_seg, off_stage, off_out, off_lane;   // byte offsets inside a warp's slot
+	uint64_t off_kq, off_lane, off_glist, off_gmeta, off_pairs, pair_bytes;        // a warp's slot: hash table, query k-mers, lane scratch, gap work list, then `group` pair blocks
+	uint64_t off_hq, off_ht, off_tails, off_pred, off_seg, off_stage, off_out;     // byte offsets inside a pair block
 	uint8_t *pool; unsigned long long *pool_used; uint64_t pool_bytes;
 	int32_t *results, *status;
 	uint32_t *ncigar, *dense; uint64_t *dense_off; unsigned long long *dense_total;
 };
 
-// scratch a warp needs for pairs up to (maxq, maxt); fills the offsets of `a`
-__host__ inline uint64_t kmer_warp_bytes(uint32_t maxq, uint32_t maxt, KmerArgs *a){
+// scratch a warp needs for `group` pairs up to (maxq, maxt) at a time; fills the offsets of `a`
+__host__ inline uint64_t kmer_warp_bytes(uint32_t maxq, uint32_t maxt, uint32_t group, KmerArgs *a){
 	uint64_t H = 64; while(H < 2 * ((uint64_t)maxq + maxt)) H <<= 1;
 	const uint64_t mh = (uint64_t)(maxq < maxt ? maxq : maxt) + 2;
 	auto up = [](uint64_t x){ return (x + 127) / 128 * 128; };
 	uint64_t o = up(H * 12);
-	uint64_t off_kq = o; o += up(((uint64_t)maxq + 2) * 4);
-	uint64_t off_hq = o; o += up(mh * 4);
-	uint64_t off_ht = o; o += up(mh * 4);
-	uint64_t off_tails = o; o += up(mh * 4);
-	uint64_t off_pred = o; o += up(mh * 4);
-	uint64_t off_seg = o; o += up((mh + 1) * 32);
-	uint64_t off_stage = o; o += up(((uint64_t)maxq + maxt + 8) * 4);
-	uint64_t off_out = o; o += up(((uint64_t)maxq + maxt + 8) * 4);
-	uint64_t off_lane = o; o += (uint64_t)32 * 2 * kKmSmallRows * 8;
-	if(a){ a->off_kq = off_kq; a->off_hq = off_hq; a->off_ht = off_ht; a->off_tails = off_tails; a->off_pred = off_pred; a->off_seg = off_seg; a->off_stage = off_stage; a->off_out = off_out; a->off_lane = off_lane; a->warp_bytes = o; }
+	const uint64_t off_kq = o; o += up(((uint64_t)maxq + 2) * 4);
+	const uint64_t off_lane = o; o += (uint64_t)32 * 2 * kKmSmallRows * 8;
+	const uint64_t off_gmeta = o; o += 3 * 32 * 4 + 128;
+	const uint64_t off_glist = o; o += up((mh + 1) * 4 * group);
+	const uint64_t off_pairs = o;
+	uint64_t q = 0;
+	const uint64_t off_hq = q; q += up(mh * 4);
+	const uint64_t off_ht = q; q += up(mh * 4);
+	const uint64_t off_tails = q; q += up(mh * 4);
+	const uint64_t off_pred = q; q += up(mh * 4);
+	const uint64_t off_seg = q; q += up((mh + 1) * 32);
+	const uint64_t off_stage = q; q += up(((uint64_t)maxq + maxt + 8) * 4);
+	const uint64_t off_out = q; q += up(((uint64_t)maxq + maxt + 8) * 4);
+	o += q * group;
+	if(a){
+		a->off_kq = off_kq; a->off_lane = off_lane; a->off_glist = off_glist; a->off_gmeta = off_gmeta; a->off_pairs = off_pairs; a->pair_bytes = q; a->group = group;
+		a->off_hq = off_hq; a->off_ht = off_ht; a->off_tails = off_tails; a->off_pred = off_pred; a->off_seg = off_seg; a->off_stage = off_stage; a->off_out = off_out;
+		a->warp_bytes = o;
+	}
 	return o;
 }
 
@@ -134,7 +147,21 @@ __device__ inline int km_gap(const uint8_t *qp, int qd, uint32_t sq, const uint8
 		if(type == 2){ const int srow = sbeg + rowsum; if(srow < smin){ smin = srow; rx = (int)sq - 1; ry = (int)i; } }   // bsalign.h:1124-1139
 		else if(i + 1 == st) smin = sbeg + rowsum;
 	}
-	if(type == 2){ // arg-min over the last row in the reference's lane / chunk order (bsalign.h:813-963)
+	if(type == 2 && W == 1){ // arg-min over the last row, one word: bit-lane j is band position j (the general form is below)
+		int run = sbeg, best = sbeg; uint32_t pmin = 0;
+		for(uint32_t blk4=0;blk4<4;blk4++){
+			int sc = 0; uint32_t st_ = 0;
+			for(uint32_t l=0;l<16;l++){
+				const uint32_t j = blk4 * 16 + l;
+				const int u = (int)((pv1 >> j) & 1) - (int)((mv1 >> j) & 1);
+				const int c = run + (u < 0 ? u : 0); run += u;
+				if(l == 0 || sc > c){ sc = c; st_ = l; }
+			}
+			if(sc >= best) continue;
+			best = sc; pmin = blk4 * 16 + st_;
+		}
+		if(best < smin){ smin = best; rx = (int)pmin; ry = (int)st - 1; }
+	} else if(type == 2){ // arg-min over the last row in the reference's lane / chunk order (bsalign.h:813-963)
 		int sb = sbeg, best = sbeg; uint32_t pmin = 0;
 		uint32_t cw = W == 1 ? 0u : 0xffffffffu; uint64_t pw_ = pv1, mw_ = mv1;   // the word of the last row the scan is in
 		for(uint32_t blk4=0;blk4<4;blk4++){
@@ -204,22 +231,38 @@ __device__ inline int km_gap(const uint8_t *qp, int qd, uint32_t sq, const uint8
 	return err;
 }
 
-__device__ inline void kmer_pair(const KmerArgs &a, const uint32_t pair, uint8_t *ws, const uint32_t lane){
+// per-pair arrays inside a warp's slot (pair j of the group the warp is working on)
+struct KmView { uint32_t *hq, *ht, *tails, *pred; int32_t *seg; uint32_t *stage, *out; };
+__device__ __forceinline__ KmView km_view(const KmerArgs &a, uint8_t *ws, uint32_t j){
+	uint8_t *pb = ws + a.off_pairs + (uint64_t)j * a.pair_bytes;
+	KmView v;
+	v.hq = (uint32_t*)(pb + a.off_hq); v.ht = (uint32_t*)(pb + a.off_ht); v.tails = (uint32_t*)(pb + a.off_tails); v.pred = (uint32_t*)(pb + a.off_pred);
+	v.seg = (int32_t*)(pb + a.off_seg); v.stage = (uint32_t*)(pb + a.off_stage); v.out = (uint32_t*)(pb + a.off_out);
+	return v;
+}
+
+__device__ __forceinline__ uint32_t km_cmin(uint32_t qlen, uint32_t tlen, uint32_t ksz){   // bsalign.h:1221-1222, the reference's double arithmetic
+	const uint32_t mn = qlen < tlen ? qlen : tlen;
+	const uint32_t c = (uint32_t)__dadd_rn(__dmul_rn((double)mn, 0.05), 1.0);
+	return c > 2 * ksz ? 2 * ksz : c;
+}
+
+// no alignment from this kernel: all-zero result, status says why (one lane)
+__device__ __forceinline__ void km_leave(const KmerArgs &a, uint32_t pair, int st){
+	int32_t *rs = a.results + (size_t)pair * 10;
+	for(int k=0;k<10;k++) rs[k] = 0;
+	a.status[pair] = st; a.ncigar[pair] = 0; a.dense_off[pair] = 0;
+}
+
+// Phase A (whole warp): unique shared canonical k-mers of one pair (bsalign.h:1230-1276) into v.hq / v.ht in query order.
+// Returns the number of hits, or -1 when the pair is finished already (empty input, or no chance of anchors: flagged for the fallback).
+__device__ inline int km_hits(const KmerArgs &a, const uint32_t pair, uint8_t *ws, const KmView &v, const uint32_t lane){
 	const uint32_t FULL = 0xffffffffu;
 	const uint32_t qlen = a.qlen[pair], tlen = a.tlen[pair], ksz = a.ksz;
 	const uint8_t *qs = a.seqs + a.qoff[pair], *ts = a.seqs + a.toff[pair];
-	int32_t *rs = a.results + (size_t)pair * 10;
-	auto leave = [&](int st){ // no alignment from this kernel: all-zero result, status says why
-		if(lane < 10) rs[lane] = 0;
-		if(lane == 0){ a.status[pair] = st; a.ncigar[pair] = 0; a.dense_off[pair] = 0; }
-	};
-	if(qlen == 0 || tlen == 0){ leave(0); return; }
-	const uint32_t mn = qlen < tlen ? qlen : tlen;
-	uint32_t cmin = (uint32_t)__dadd_rn(__dmul_rn((double)mn, 0.05), 1.0);   // bsalign.h:1221-1222
-	if(cmin > 2 * ksz) cmin = 2 * ksz;
+	if(qlen == 0 || tlen == 0){ if(lane == 0) km_leave(a, pair, 0); return -1; }
 	const uint32_t nq = qlen >= ksz ? qlen - ksz + 1 : 0, nt = tlen >= ksz ? tlen - ksz + 1 : 0;
-	if(nq == 0 || nt == 0){ leave(kStFallback); return; }
-	// ---- unique shared canonical k-mers (bsalign.h:1230-1276) -----------------------------------------------------------------
+	if(nq == 0 || nt == 0){ if(lane == 0) km_leave(a, pair, kStFallback); return -1; }
 	uint32_t hbits = 6; while((1ull << hbits) < 2 * ((uint64_t)nq + nt)) hbits++;
 	const uint32_t H = 1u << hbits, hm = H - 1;
 	uint32_t *keys = (uint32_t*)ws, *qv = keys + H, *tv = qv + H;
@@ -244,7 +287,6 @@ __device__ inline void kmer_pair(const KmerArgs &a, const uint32_t pair, uint8_t
 		}
 	}
 	__syncwarp();
-	uint32_t *hq = (uint32_t*)(ws + a.off_hq), *ht = (uint32_t*)(ws + a.off_ht);
 	uint32_t nh = 0;
 	for(uint32_t base=0;base<nq;base+=32){
 		const uint32_t p = base + lane;
@@ -253,158 +295,213 @@ __device__ inline void kmer_pair(const KmerArgs &a, const uint32_t pair, uint8_t
 			const uint32_t km = kq[p] >> 1;
 			uint32_t h = km_slot(km, hbits);
 			while(keys[h] != km) h = (h + 1) & hm;
-			const uint32_t v = qv[h], w = tv[h];
-			hit = v != kKmMulti && w < kKmMulti && ((v ^ w) & 1u) == 0;
+			const uint32_t x = qv[h], w = tv[h];
+			hit = x != kKmMulti && w < kKmMulti && ((x ^ w) & 1u) == 0;
 			// the reference's scan ends on a zeroed sentinel, so a LAST group of k-mer value 0 is never looked at: only possible when it is the only one
 			if(km == 0 && nq == 1 && nt == 1) hit = false;
 			tt = w >> 1;
 		}
 		const uint32_t mask = __ballot_sync(FULL, hit);
-		if(hit){ const uint32_t r = nh + __popc(mask & ((1u << lane) - 1u)); hq[r] = p; ht[r] = tt; }
+		if(hit){ const uint32_t r = nh + __popc(mask & ((1u << lane) - 1u)); v.hq[r] = p; v.ht[r] = tt; }
 		nh += __popc(mask);
 	}
 	__syncwarp();
-	if(nh * ksz < cmin){ leave(kStFallback); return; }
-	// ---- chain, filter, coverage: lane 0 (bsalign.h:1277-1424) -----------------------------------------------------------------
-	uint32_t kmap = 0;
-	if(lane == 0){
-		uint32_t *tails = (uint32_t*)(ws + a.off_tails), *pred = (uint32_t*)(ws + a.off_pred);
-		uint32_t len = 1, b, e, m;
-		tails[0] = 0; pred[0] = kKmNone;
-		for(uint32_t i=1;i<nh;i++){
-			const uint32_t ti = ht[i];
-			if(ti > ht[tails[len - 1]]){ pred[i] = tails[len - 1]; tails[len++] = i; }
-			else if(ti <= ht[tails[0]]){ pred[i] = kKmNone; tails[0] = i; }
-			else {
-				b = 0; e = len;
-				while(b < e){
-					m = b + ((e - b) >> 1);
-					const uint32_t tm = ht[tails[m]];
-					if(ti > tm) b = m + 1; else if(ti < tm) e = m; else { b = m; break; }
-				}
-				pred[i] = pred[tails[b - 1]];   // the reference's rule: the predecessor of the tail before it
-				tails[b] = i;
-			}
-		}
-		b = 0; e = 0xFFFFFFFFu;
-		for(m=tails[len-1];m!=kKmNone;m=pred[m]){
-			hq[m] |= kKmOn;
-			if(ht[m] + ksz <= e) b += ksz; else b += e - ht[m];
-			e = ht[m];
-		}
-		bool ok = b >= cmin;
-		if(ok){
-			int *dl = (int*)tails;
-			for(;;){ // drop anchors whose diagonal is far from the mean (bsalign.h:1347-1394)
-				int tot = 0; uint32_t cnt = 0, drop = 0;
-				for(uint32_t i=0;i<nh;i++) if(hq[i] & kKmOn){ const int d = (int)(hq[i] & ~kKmOn) - (int)ht[i]; tot += d; dl[cnt++] = d; }
-				if(cnt * ksz < cmin) break;
-				const int mean = tot / (int)cnt;
-				const int median = km_select(dl, (int)cnt, (int)(cnt / 2));
-				int var = (median > mean ? median - mean : mean - median) * 3;
-				if(var < 50) var = 50;
-				for(uint32_t i=0;i<nh;i++) if(hq[i] & kKmOn){
-					int d = (int)(hq[i] & ~kKmOn) - (int)ht[i] - mean;
-					if(d < 0) d = -d;
-					if(d > var){ hq[i] &= ~kKmOn; drop++; }
-				}
-				if(drop == 0) break;
-			}
-			uint32_t kept = 0; m = 0; e = 0;
-			for(uint32_t i=0;i<nh;i++) if(hq[i] & kKmOn){
-				const uint32_t t_ = ht[i];
-				if(t_ >= e + ksz) m += ksz; else m += t_ + ksz - e;
-				e = t_ + ksz;
-				hq[kept] = hq[i] & ~kKmOn; ht[kept] = t_; kept++;
-			}
-			if(m >= cmin) kmap = kept;
-		}
-	}
-	kmap = __shfl_sync(FULL, kmap, 0);
-	if(kmap == 0){ leave(kStFallback); return; }
-	__syncwarp();
-	// ---- the gaps: lane l takes gaps l, l + 32, ... (bsalign.h:1461-1531) --------------------------------------------------------
-	int32_t *seg = (int32_t*)(ws + a.off_seg);
-	uint32_t *stage = (uint32_t*)(ws + a.off_stage);
-	const uint32_t kh = ksz / 2;
-	int gerr = 0;
-	for(uint32_t i=lane;i<=kmap;i+=32){
-		const uint32_t qb = i ? hq[i - 1] + kh + 1 : 0, tb = i ? ht[i - 1] + kh + 1 : 0;
-		const uint32_t qe = i < kmap ? hq[i] + kh : qlen, te = i < kmap ? ht[i] + kh : tlen;
-		int32_t *rec = seg + (size_t)i * 8;
-		if(qb == qe && tb == te){ rec[7] = -1; continue; }
-		const uint32_t sq = qe - qb, st = te - tb;
-		if(sq == 0 || st == 0){ for(int k=0;k<8;k++) rec[k] = 0; continue; }   // bsalign.h:1051-1054: all-zero result, cigars untouched
-		const uint32_t W = (sq + 63) / 64;
-		const uint64_t words = 2 * (uint64_t)W * ((uint64_t)st + 2);
-		uint64_t *scr; uint32_t sd;
-		if(W == 1 && st + 1 <= kKmSmallRows - 1){ scr = (uint64_t*)(ws + a.off_lane) + lane; sd = 32; }
-		else {
-			const unsigned long long bytes = (words * 8 + 15) & ~15ull;
-			const unsigned long long off = atomicAdd(a.pool_used, bytes);
-			if(off + bytes > a.pool_bytes){ gerr |= kStPool; rec[7] = -1; continue; }
-			scr = (uint64_t*)(a.pool + off); sd = 1;
-		}
-		uint32_t *cg = stage + qb + tb;
-		if(i == 0) gerr |= km_gap(qs + qe - 1, -1, sq, ts + te - 1, -1, st, 2, scr, sd, cg, sq + st, rec);
-		else gerr |= km_gap(qs + qb, 1, sq, ts + tb, 1, st, i == kmap ? 2 : 0, scr, sd, cg, sq + st, rec);
-	}
-	for(int o=16;o;o>>=1) gerr |= __shfl_xor_sync(FULL, gerr, o);
-	__syncwarp();
-	if(gerr & kStPool){ leave(kStPool); return; }
-	// ---- stitch (lane 0), then the warp moves the words into the dense arena -------------------------------------------------------
-	uint32_t *out = (uint32_t*)(ws + a.off_out);
-	const uint32_t outcap = qlen + tlen + 2;
-	uint32_t n = 0;
-	if(lane == 0){
-		int R[10] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
-		uint32_t ml = 0;
-		auto raw = [&](uint32_t w){ if(n < outcap) out[n] = w; else gerr |= 4; n++; };
-		for(uint32_t i=0;i<=kmap;i++){
-			const uint32_t qb = i ? hq[i - 1] + kh + 1 : 0, tb = i ? ht[i - 1] + kh + 1 : 0;
-			const uint32_t qe = i < kmap ? hq[i] + kh : qlen, te = i < kmap ? ht[i] + kh : tlen;
-			if(i < kmap) ml++;
-			if(qb == qe && tb == te) continue;
-			const int32_t *rec = seg + (size_t)i * 8;
-			const uint32_t *cg = stage + qb + tb;
-			const uint32_t nw = (uint32_t)rec[7];
-			if(i == 0){ // the reference pushes M, appends the gap's cigar and reverses everything (bsalign.h:1476-1499)
-				for(uint32_t k=0;k<nw;k++) raw(cg[k]);
-				raw(ml << 4);
-				R[5] += (int)ml; R[9] += (int)ml; ml = 0;
-				R[1] = (int)qe - rec[0]; R[3] = (int)te - rec[1]; R[2] = (int)qe; R[4] = (int)te;
-			} else {
-				if(ml){
-					if(n && n <= outcap && (out[n - 1] & 0xf) == 0) out[n - 1] += ml << 4; else raw(ml << 4);
-					R[5] += (int)ml; R[9] += (int)ml; ml = 0;
-				}
-				for(uint32_t k=0;k<nw;k++) raw(cg[nw - 1 - k]);
-				R[2] = (int)qb + rec[0]; R[4] = (int)tb + rec[1];
-			}
-			R[5] += rec[2]; R[6] += rec[3]; R[7] += rec[4]; R[8] += rec[5]; R[9] += rec[2] + rec[3] + rec[4] + rec[5]; R[0] += rec[6];
-		}
-		for(int k=0;k<10;k++) rs[k] = R[k];
-		if(n > outcap) n = outcap;
-		a.ncigar[pair] = n;
-		a.status[pair] = gerr & 7;
-	}
-	n = __shfl_sync(FULL, n, 0);
-	unsigned long long off = 0;
-	if(lane == 0){ off = atomicAdd(a.dense_total, (unsigned long long)n); a.dense_off[pair] = off; }
-	off = __shfl_sync(FULL, off, 0);
-	__syncwarp();
-	for(uint32_t k=lane;k<n;k+=32) a.dense[off + k] = out[k];
+	if(nh * ksz < km_cmin(qlen, tlen, ksz)){ if(lane == 0) km_leave(a, pair, kStFallback); return -1; }
+	return (int)nh;
 }
 
+// Phase B (ONE lane per pair): chain, diagonal filter, coverage (bsalign.h:1277-1424); the anchors are compacted in place.  Returns
+// their number, 0 = the pair takes the fallback.
+__device__ inline uint32_t km_chain(const KmView &v, const uint32_t nh, const uint32_t ksz, const uint32_t cmin){
+	uint32_t *hq = v.hq, *ht = v.ht, *tails = v.tails, *pred = v.pred;
+	uint32_t len = 1, b, e, m;
+	tails[0] = 0; pred[0] = kKmNone;
+	for(uint32_t i=1;i<nh;i++){
+		const uint32_t ti = ht[i];
+		if(ti > ht[tails[len - 1]]){ pred[i] = tails[len - 1]; tails[len++] = i; }
+		else if(ti <= ht[tails[0]]){ pred[i] = kKmNone; tails[0] = i; }
+		else {
+			b = 0; e = len;
+			while(b < e){
+				m = b + ((e - b) >> 1);
+				const uint32_t tm = ht[tails[m]];
+				if(ti > tm) b = m + 1; else if(ti < tm) e = m; else { b = m; break; }
+			}
+			pred[i] = pred[tails[b - 1]];   // the reference's rule: the predecessor of the tail before it
+			tails[b] = i;
+		}
+	}
+	b = 0; e = 0xFFFFFFFFu;
+	for(m=tails[len-1];m!=kKmNone;m=pred[m]){
+		hq[m] |= kKmOn;
+		if(ht[m] + ksz <= e) b += ksz; else b += e - ht[m];
+		e = ht[m];
+	}
+	if(b < cmin) return 0;
+	int *dl = (int*)tails;
+	for(;;){ // drop anchors whose diagonal is far from the mean (bsalign.h:1347-1394)
+		int tot = 0; uint32_t cnt = 0, drop = 0;
+		for(uint32_t i=0;i<nh;i++) if(hq[i] & kKmOn){ const int d = (int)(hq[i] & ~kKmOn) - (int)ht[i]; tot += d; dl[cnt++] = d; }
+		if(cnt * ksz < cmin) break;
+		const int mean = tot / (int)cnt;
+		const int median = km_select(dl, (int)cnt, (int)(cnt / 2));
+		int var = (median > mean ? median - mean : mean - median) * 3;
+		if(var < 50) var = 50;
+		for(uint32_t i=0;i<nh;i++) if(hq[i] & kKmOn){
+			int d = (int)(hq[i] & ~kKmOn) - (int)ht[i] - mean;
+			if(d < 0) d = -d;
+			if(d > var){ hq[i] &= ~kKmOn; drop++; }
+		}
+		if(drop == 0) break;
+	}
+	uint32_t kept = 0; m = 0; e = 0;
+	for(uint32_t i=0;i<nh;i++) if(hq[i] & kKmOn){
+		const uint32_t t_ = ht[i];
+		if(t_ >= e + ksz) m += ksz; else m += t_ + ksz - e;
+		e = t_ + ksz;
+		hq[kept] = hq[i] & ~kKmOn; ht[kept] = t_; kept++;
+	}
+	return m >= cmin ? kept : 0;
+}
+
+// Phase C1 (ONE lane per pair): the gaps of a pair that need a DP (bsalign.h:1461-1531) are appended to the warp's work list as
+// (pair block << 27 | gap index); adjacent anchors have none, a gap with one empty side gets the all-zero record of bsalign.h:1051-1054.
+// pass 0 counts, pass 1 writes from `at`.
+__device__ inline uint32_t km_gap_list(const KmerArgs &a, const uint32_t pair, const KmView &v, const uint32_t kmap, const uint32_t blk, uint32_t *list, uint32_t at, const int pass){
+	const uint32_t qlen = a.qlen[pair], tlen = a.tlen[pair], kh = a.ksz / 2;
+	const uint32_t *hq = v.hq, *ht = v.ht;
+	uint32_t c = 0;
+	for(uint32_t i=0;i<=kmap;i++){
+		const uint32_t qb = i ? hq[i - 1] + kh + 1 : 0, tb = i ? ht[i - 1] + kh + 1 : 0;
+		const uint32_t qe = i < kmap ? hq[i] + kh : qlen, te = i < kmap ? ht[i] + kh : tlen;
+		if(qb == qe && tb == te) continue;
+		if(qe == qb || te == tb){ if(pass){ int32_t *rec = v.seg + (size_t)i * 8; for(int k=0;k<8;k++) rec[k] = 0; } continue; }
+		if(pass) list[at + c] = (blk << 27) | i;
+		c++;
+	}
+	return c;
+}
+
+// Phase C2 (any lane): one entry of the work list
+__device__ inline int km_gap_run(const KmerArgs &a, const uint32_t pair, uint8_t *ws, const KmView &v, const uint32_t kmap, const uint32_t i, const uint32_t lane){
+	const uint32_t qlen = a.qlen[pair], tlen = a.tlen[pair], kh = a.ksz / 2;
+	const uint8_t *qs = a.seqs + a.qoff[pair], *ts = a.seqs + a.toff[pair];
+	const uint32_t *hq = v.hq, *ht = v.ht;
+	const uint32_t qb = i ? hq[i - 1] + kh + 1 : 0, tb = i ? ht[i - 1] + kh + 1 : 0;
+	const uint32_t qe = i < kmap ? hq[i] + kh : qlen, te = i < kmap ? ht[i] + kh : tlen;
+	int32_t *rec = v.seg + (size_t)i * 8;
+	const uint32_t sq = qe - qb, st = te - tb;
+	const uint32_t W = (sq + 63) / 64;
+	const uint64_t words = 2 * (uint64_t)W * ((uint64_t)st + 2);
+	uint64_t *scr; uint32_t sd;
+	if(W == 1 && st + 1 <= kKmSmallRows - 1){ scr = (uint64_t*)(ws + a.off_lane) + lane; sd = 32; }
+	else {
+		const unsigned long long bytes = (words * 8 + 15) & ~15ull;
+		const unsigned long long off = atomicAdd(a.pool_used, bytes);
+		if(off + bytes > a.pool_bytes){ rec[7] = 0; return kStPool; }
+		scr = (uint64_t*)(a.pool + off); sd = 1;
+	}
+	uint32_t *cg = v.stage + qb + tb;
+	if(i == 0) return km_gap(qs + qe - 1, -1, sq, ts + te - 1, -1, st, 2, scr, sd, cg, sq + st, rec);
+	return km_gap(qs + qb, 1, sq, ts + tb, 1, st, i == kmap ? 2 : 0, scr, sd, cg, sq + st, rec);
+}
+
+// Phase D (ONE lane per pair): stitch the gap cigars around the anchor matches with the reference's push order; result, status, count.
+__device__ inline uint32_t km_stitch(const KmerArgs &a, const uint32_t pair, const KmView &v, const uint32_t kmap, int gerr){
+	const uint32_t qlen = a.qlen[pair], tlen = a.tlen[pair], kh = a.ksz / 2;
+	const uint32_t *hq = v.hq, *ht = v.ht;
+	uint32_t *out = v.out;
+	const uint32_t outcap = qlen + tlen + 2;
+	uint32_t n = 0, ml = 0;
+	int R[10] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
+	auto raw = [&](uint32_t w){ if(n < outcap) out[n] = w; else gerr |= 4; n++; };
+	for(uint32_t i=0;i<=kmap;i++){
+		const uint32_t qb = i ? hq[i - 1] + kh + 1 : 0, tb = i ? ht[i - 1] + kh + 1 : 0;
+		const uint32_t qe = i < kmap ? hq[i] + kh : qlen, te = i < kmap ? ht[i] + kh : tlen;
+		if(i < kmap) ml++;
+		if(qb == qe && tb == te) continue;
+		const int32_t *rec = v.seg + (size_t)i * 8;
+		const uint32_t *cg = v.stage + qb + tb;
+		const uint32_t nw = (uint32_t)rec[7];
+		if(i == 0){ // the reference pushes M, appends the gap's cigar and reverses everything (bsalign.h:1476-1499)
+			for(uint32_t k=0;k<nw;k++) raw(cg[k]);
+			raw(ml << 4);
+			R[5] += (int)ml; R[9] += (int)ml; ml = 0;
+			R[1] = (int)qe - rec[0]; R[3] = (int)te - rec[1]; R[2] = (int)qe; R[4] = (int)te;
+		} else {
+			if(ml){
+				if(n && n <= outcap && (out[n - 1] & 0xf) == 0) out[n - 1] += ml << 4; else raw(ml << 4);
+				R[5] += (int)ml; R[9] += (int)ml; ml = 0;
+			}
+			for(uint32_t k=0;k<nw;k++) raw(cg[nw - 1 - k]);
+			R[2] = (int)qb + rec[0]; R[4] = (int)tb + rec[1];
+		}
+		R[5] += rec[2]; R[6] += rec[3]; R[7] += rec[4]; R[8] += rec[5]; R[9] += rec[2] + rec[3] + rec[4] + rec[5]; R[0] += rec[6];
+	}
+	int32_t *rs = a.results + (size_t)pair * 10;
+	for(int k=0;k<10;k++) rs[k] = R[k];
+	if(n > outcap) n = outcap;
+	a.ncigar[pair] = n;
+	a.status[pair] = gerr & 7;
+	a.dense_off[pair] = 0;
+	return n;
+}
+
+// A warp works on a.group pairs at a time: the warp-wide phases (A, C and the copy) run pair after pair, the serial phases (B, D) on
+// one lane per pair.  group = 1 (few long pairs: more warps than pairs) leaves the serial phases to lane 0.
 __global__ void __launch_bounds__(kKmWarps * 32, 8) kmer_edit_kernel(const KmerArgs a){
-	const uint32_t lane = threadIdx.x & 31;
+	const uint32_t FULL = 0xffffffffu;
+	const uint32_t lane = threadIdx.x & 31, G = a.group;
 	uint8_t *ws = a.scratch + (uint64_t)(blockIdx.x * kKmWarps + (threadIdx.x >> 5)) * a.warp_bytes;
 	for(;;){
-		uint32_t idx = 0;
-		if(lane == 0) idx = atomicAdd(a.next, 1u);
-		idx = __shfl_sync(0xffffffffu, idx, 0);
-		if(idx >= a.npairs) break;
-		kmer_pair(a, a.order ? a.order[idx] : idx, ws, lane);
+		uint32_t idx0 = 0;
+		if(lane == 0) idx0 = atomicAdd(a.next, G);
+		idx0 = __shfl_sync(FULL, idx0, 0);
+		if(idx0 >= a.npairs) break;
+		const uint32_t cnt = a.npairs - idx0 < G ? a.npairs - idx0 : G;
+		uint32_t my_pair = 0, my_kmap = 0, my_n = 0; int my_nh = -1, my_gerr = 0;
+		for(uint32_t j=0;j<cnt;j++){
+			const uint32_t pair = a.order ? a.order[idx0 + j] : idx0 + j;
+			const int nh = km_hits(a, pair, ws, km_view(a, ws, j), lane);
+			if(lane == j){ my_pair = pair; my_nh = nh; }
+			__syncwarp();
+		}
+		if(my_nh >= 0){
+			my_kmap = km_chain(km_view(a, ws, lane), (uint32_t)my_nh, a.ksz, km_cmin(a.qlen[my_pair], a.tlen[my_pair], a.ksz));
+			if(my_kmap == 0) km_leave(a, my_pair, kStFallback);
+		}
+		__syncwarp();
+		// the gaps of all pairs of the group form one work list, spread evenly over the lanes
+		uint32_t *glist = (uint32_t*)(ws + a.off_glist), *gmeta = (uint32_t*)(ws + a.off_gmeta);   // gmeta: [pair | kmap | flags] x 32
+		const KmView mine = km_view(a, ws, lane);
+		const uint32_t c = my_kmap ? km_gap_list(a, my_pair, mine, my_kmap, lane, glist, 0, 0) : 0;
+		uint32_t incl = c;
+		for(int o=1;o<32;o<<=1){ const uint32_t t_ = __shfl_up_sync(FULL, incl, o); if(lane >= (uint32_t)o) incl += t_; }
+		const uint32_t total = __shfl_sync(FULL, incl, 31);
+		if(my_kmap) km_gap_list(a, my_pair, mine, my_kmap, lane, glist, incl - c, 1);
+		gmeta[lane] = my_pair; gmeta[32 + lane] = my_kmap; gmeta[64 + lane] = 0;
+		__syncwarp();
+		for(uint32_t e=lane;e<total;e+=32){
+			const uint32_t w = glist[e], blk = w >> 27, gi = w & 0x7FFFFFFu;
+			const int g = km_gap_run(a, gmeta[blk], ws, km_view(a, ws, blk), gmeta[32 + blk], gi, lane);
+			if(g) atomicOr(&gmeta[64 + blk], (uint32_t)g);
+		}
+		__syncwarp();
+		my_gerr = (int)gmeta[64 + lane];
+		if(my_kmap){
+			if(my_gerr & kStPool) km_leave(a, my_pair, kStPool);
+			else my_n = km_stitch(a, my_pair, km_view(a, ws, lane), my_kmap, my_gerr);
+		}
+		__syncwarp();
+		for(uint32_t j=0;j<cnt;j++){
+			const uint32_t n = __shfl_sync(FULL, my_n, j), pair = __shfl_sync(FULL, my_pair, j);
+			if(n == 0) continue;
+			unsigned long long off = 0;
+			if(lane == 0){ off = atomicAdd(a.dense_total, (unsigned long long)n); a.dense_off[pair] = off; }
+			off = __shfl_sync(FULL, off, 0);
+			const uint32_t *out = km_view(a, ws, j).out;
+			for(uint32_t k=lane;k<n;k+=32) a.dense[off + k] = out[k];
+		}
 		__syncwarp();
 	}
 }

@@ -429,3 +429,12 @@ def test_kmer_edit_matches_golden_and_oracle(ctx, monkeypatch):
     check(big, 13)
     monkeypatch.setenv("BSB200_KMER_SLOTS", "4")
     check(b, 13)
+    monkeypatch.delenv("BSB200_KMER_SLOTS")
+    monkeypatch.delenv("BSB200_KMER_POOL")
+    for grp in ("32", "7", "1"):   # pairs a warp works on at a time (serial phases: one lane per pair)
+        monkeypatch.setenv("BSB200_KMER_GROUP", grp)
+        check(b, 13)
+        check(big, 13)
+    monkeypatch.setenv("BSB200_KMER_POOL", "2000000")
+    monkeypatch.setenv("BSB200_KMER_GROUP", "32")
+    check(big, 13)
