@@ -6,8 +6,8 @@
 //   * persistent warps fetch GROUPS of up to 32 pairs from a counter; every warp owns one scratch slot.  The warp-wide phases run pair
 //     after pair, the serial phases on one lane per pair (group = 1 when a batch has fewer pairs than the GPU has warps).
 //   * unique shared k-mers come from a hash table in the warp's slot instead of two sorts: every lane rolls over its own stretch of
-//     positions and inserts (atomicCAS on the key, the per-sequence value word goes NONE -> offset|strand -> MULTI), then the query
-//     positions are scanned IN ORDER and a ballot compacts
+//     positions and inserts (atomicCAS on the key; a per-sequence 64-bit word takes occurrences << 32 | offset|strand as a fire-and-forget
+//     add), then the query positions are scanned IN ORDER and a ballot compacts
 //     the hits - which is the reference's list after its second sort (query offsets are distinct).
 //   * the chain (patience tails with the reference's own predecessor rule), the diagonal filter (mean / median / 3x rule) and the
 //     coverage tests are sequential per pair: one lane.
@@ -28,7 +28,7 @@ constexpr int kKmWarps = 4;                    // warps per CTA
 constexpr uint32_t kKmSmallRows = 128;         // trace rows (incl. the init row) of a one-word gap that fit the lane's own scratch
 constexpr int kStFallback = 0x40000000;        // internal: no usable anchors, the pair takes the plain global edit
 constexpr int kStPool = 0x08000000;            // internal: the pool for large gap traces was exhausted, run the pair again
-constexpr uint32_t kKmNone = 0xFFFFFFFFu, kKmMulti = 0xFFFFFFFEu, kKmOn = 0x80000000u;
+constexpr uint32_t kKmNone = 0xFFFFFFFFu, kKmOn = 0x80000000u;
 
 struct KmerArgs {
 	const uint8_t *seqs;
@@ -48,10 +48,10 @@ struct KmerArgs {
 
 // scratch a warp needs for `group` pairs up to (maxq, maxt) at a time; fills the offsets of `a`
 __host__ inline uint64_t kmer_warp_bytes(uint32_t maxq, uint32_t maxt, uint32_t group, KmerArgs *a){
-	uint64_t H = 64; while(H < 2 * ((uint64_t)maxq + maxt)) H <<= 1;
+	uint64_t H = 64; while(2 * H < 3 * ((uint64_t)maxq + maxt)) H <<= 1;
 	const uint64_t mh = (uint64_t)(maxq < maxt ? maxq : maxt) + 2;
 	auto up = [](uint64_t x){ return (x + 127) / 128 * 128; };
-	uint64_t o = up(H * 12);
+	uint64_t o = up(H * 20);
 	const uint64_t off_kq = o; o += up(((uint64_t)maxq + 2) * 4);
 	const uint64_t off_lane = o; o += (uint64_t)32 * 2 * kKmSmallRows * 8;
 	const uint64_t off_gmeta = o; o += 3 * 32 * 4 + 128;
@@ -263,27 +263,47 @@ __device__ inline int km_hits(const KmerArgs &a, const uint32_t pair, uint8_t *w
 	if(qlen == 0 || tlen == 0){ if(lane == 0) km_leave(a, pair, 0); return -1; }
 	const uint32_t nq = qlen >= ksz ? qlen - ksz + 1 : 0, nt = tlen >= ksz ? tlen - ksz + 1 : 0;
 	if(nq == 0 || nt == 0){ if(lane == 0) km_leave(a, pair, kStFallback); return -1; }
-	uint32_t hbits = 6; while((1ull << hbits) < 2 * ((uint64_t)nq + nt)) hbits++;
+	uint32_t hbits = 6; while(2 * (1ull << hbits) < 3 * ((uint64_t)nq + nt)) hbits++;   // load <= 2/3
 	const uint32_t H = 1u << hbits, hm = H - 1;
-	uint32_t *keys = (uint32_t*)ws, *qv = keys + H, *tv = qv + H;
-	{ uint4 *z = (uint4*)ws; const uint4 f = make_uint4(kKmNone, kKmNone, kKmNone, kKmNone); for(uint32_t i=lane;i<3*(H/4);i+=32) z[i] = f; }
+	// table: keys[H] (all ones = empty), then per sequence one 64-bit word per slot: occurrences << 32 | sum of (offset << 1 | strand).
+	// Only the key needs an atomic with a result (probing); the occurrence words are fire-and-forget adds.
+	uint32_t *keys = (uint32_t*)ws;
+	unsigned long long *qv = (unsigned long long*)(keys + H), *tv = qv + H;
+	{
+		uint4 *z = (uint4*)ws; const uint4 f = make_uint4(kKmNone, kKmNone, kKmNone, kKmNone), o = make_uint4(0, 0, 0, 0);
+		for(uint32_t i=lane;i<H/4;i+=32) z[i] = f;
+		for(uint32_t i=H/4+lane;i<5*(H/4);i+=32) z[i] = o;
+	}
 	__syncwarp();
-	// every lane rolls over its own stretch of k-mer positions (one byte per position); the query's k-mers are kept for the scan below
+	// every lane rolls over its own stretch of k-mer positions of BOTH sequences (one byte per position and sequence; the two key
+	// atomics of an iteration are in flight together); the query's k-mers are kept for the scan below
 	uint32_t *kq = (uint32_t*)(ws + a.off_kq);
 	const uint32_t kmk = 0xFFFFFFFFu >> ((16 - ksz) << 1), sft = (ksz - 1) << 1;
-	for(int src=0;src<2;src++){
-		const uint8_t *s = src ? ts : qs; const uint32_t ns = src ? nt : nq; uint32_t *val = src ? tv : qv;
-		const uint32_t per = (ns + 31) / 32, p0 = lane * per, p1 = p0 + per < ns ? p0 + per : ns;
-		uint32_t fw = 0, rv = 0;
-		if(p0 < p1) for(uint32_t i=0;i+1<ksz;i++){ const uint32_t c = s[p0 + i] & 3u; fw = (fw << 2) | c; rv = (rv >> 2) | ((3u - c) << sft); }
-		for(uint32_t p=p0;p<p1;p++){
-			const uint32_t c = s[p + ksz - 1] & 3u;
-			fw = ((fw << 2) | c) & kmk; rv = (rv >> 2) | ((3u - c) << sft);
-			const uint32_t dir = rv < fw, km = dir ? rv : fw;
-			if(src == 0) kq[p] = (km << 1) | dir;
-			uint32_t h = km_slot(km, hbits);
-			for(;;){ const uint32_t old = atomicCAS(&keys[h], kKmNone, km); if(old == kKmNone || old == km) break; h = (h + 1) & hm; }
-			if(atomicCAS(&val[h], kKmNone, (p << 1) | dir) != kKmNone) val[h] = kKmMulti;
+	{
+		const uint32_t perq = (nq + 31) / 32, pert = (nt + 31) / 32;
+		uint32_t pq = lane * perq, pt = lane * pert;
+		const uint32_t eq = pq + perq < nq ? pq + perq : nq, et = pt + pert < nt ? pt + pert : nt;
+		uint32_t fq = 0, rq = 0, ft = 0, rt = 0;
+		if(pq < eq) for(uint32_t i=0;i+1<ksz;i++){ const uint32_t c = qs[pq + i] & 3u; fq = (fq << 2) | c; rq = (rq >> 2) | ((3u - c) << sft); }
+		if(pt < et) for(uint32_t i=0;i+1<ksz;i++){ const uint32_t c = ts[pt + i] & 3u; ft = (ft << 2) | c; rt = (rt >> 2) | ((3u - c) << sft); }
+		while(pq < eq || pt < et){
+			const bool vq = pq < eq, vt = pt < et;
+			uint32_t kmq = 0, kmt = 0, dq = 0, dt = 0, hq_ = 0, ht_ = 0, oq = 0, ot = 0;
+			if(vq){ const uint32_t c = qs[pq + ksz - 1] & 3u; fq = ((fq << 2) | c) & kmk; rq = (rq >> 2) | ((3u - c) << sft); dq = rq < fq; kmq = dq ? rq : fq; hq_ = km_slot(kmq, hbits); }
+			if(vt){ const uint32_t c = ts[pt + ksz - 1] & 3u; ft = ((ft << 2) | c) & kmk; rt = (rt >> 2) | ((3u - c) << sft); dt = rt < ft; kmt = dt ? rt : ft; ht_ = km_slot(kmt, hbits); }
+			if(vq) oq = atomicCAS(&keys[hq_], kKmNone, kmq);
+			if(vt) ot = atomicCAS(&keys[ht_], kKmNone, kmt);
+			if(vq){
+				while(!(oq == kKmNone || oq == kmq)){ hq_ = (hq_ + 1) & hm; oq = atomicCAS(&keys[hq_], kKmNone, kmq); }
+				atomicAdd(&qv[hq_], (1ull << 32) | ((pq << 1) | dq));
+				kq[pq] = (kmq << 1) | dq;
+				pq++;
+			}
+			if(vt){
+				while(!(ot == kKmNone || ot == kmt)){ ht_ = (ht_ + 1) & hm; ot = atomicCAS(&keys[ht_], kKmNone, kmt); }
+				atomicAdd(&tv[ht_], (1ull << 32) | ((pt << 1) | dt));
+				pt++;
+			}
 		}
 	}
 	__syncwarp();
@@ -295,11 +315,11 @@ __device__ inline int km_hits(const KmerArgs &a, const uint32_t pair, uint8_t *w
 			const uint32_t km = kq[p] >> 1;
 			uint32_t h = km_slot(km, hbits);
 			while(keys[h] != km) h = (h + 1) & hm;
-			const uint32_t x = qv[h], w = tv[h];
-			hit = x != kKmMulti && w < kKmMulti && ((x ^ w) & 1u) == 0;
+			const unsigned long long x = qv[h], w = tv[h];
+			hit = (x >> 32) == 1 && (w >> 32) == 1 && ((x ^ w) & 1u) == 0;
 			// the reference's scan ends on a zeroed sentinel, so a LAST group of k-mer value 0 is never looked at: only possible when it is the only one
 			if(km == 0 && nq == 1 && nt == 1) hit = false;
-			tt = w >> 1;
+			tt = (uint32_t)w >> 1;
 		}
 		const uint32_t mask = __ballot_sync(FULL, hit);
 		if(hit){ const uint32_t r = nh + __popc(mask & ((1u << lane) - 1u)); v.hq[r] = p; v.ht[r] = tt; }
