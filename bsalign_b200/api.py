@@ -79,6 +79,7 @@ def lib():
         L.bsb200_batch_upload_dev.argtypes = L.bsb200_batch_upload.argtypes
         L.bsb200_pairwise_batch_dense.argtypes = [_P, ctypes.c_int, ctypes.c_uint64, _P, _P, _P, _P, _P, ctypes.c_int, ctypes.c_uint32, _P,
                                                   _I8, _I8, _I8, _I8, _P, _P, ctypes.c_uint64, _P, _P, _P]
+        L.bsb200_pairwise_batch_dense_bits.argtypes = L.bsb200_pairwise_batch_dense.argtypes
         L.bsb200_pairwise_batch_ptrs.argtypes = [_P, ctypes.c_int, ctypes.c_uint64, _P, _P, _P, _P, ctypes.c_int, ctypes.c_uint32, _P,
                                                  _I8, _I8, _I8, _I8, _P, _P, _P, _P, ctypes.c_int]
         L.bsb200_pairwise_batch_multi.argtypes = [_P, ctypes.c_int, ctypes.c_int, ctypes.c_uint64, _P, _P, _P, _P, _P, ctypes.c_int, ctypes.c_uint32, _P,
@@ -195,9 +196,20 @@ class Context:
                                                    _ptr(res), _ptr(cg), 0 if cg is None else cg.size, ctypes.byref(total), _ptr(ncg), _ptr(st))
         self._check(rc, "bsb200_pairwise_batch_dense")
         self.last_timing = self.timing()
-        doff = np.zeros(len(ncg) + 1, dtype=np.uint64)
-        np.cumsum(ncg, out=doff[1:])
-        return BatchResult(res, cg, doff, ncg, st)
+        return BatchResult(res, cg, None, ncg, st)
+
+    def dense_bits(self, kind, bits, batch, mode, bandwidth, matrix=None, gaps=(0, 0, 0, 0), out=None):
+        """ONE C-ABI call (bsb200_pairwise_batch_dense_bits) with the sequences 2-bit packed in BaseBank words (pack_bits); batch.qoff / toff are
+        base offsets.  Results + dense pair-ordered cigars."""
+        m = np.ascontiguousarray(matrix if matrix is not None else np.zeros(16), dtype=np.int8)
+        res, cg, off, ncg, st = out if out is not None else _alloc_out(batch, True)
+        total = ctypes.c_uint64(0)
+        rc = self._lib.bsb200_pairwise_batch_dense_bits(self._h, 0 if kind == "epi8" else 1, batch.n, _ptr(bits), _ptr(batch.qoff), _ptr(batch.qlen),
+                                                        _ptr(batch.toff), _ptr(batch.tlen), int(mode), int(bandwidth), _ptr(m), gaps[0], gaps[1], gaps[2], gaps[3],
+                                                        _ptr(res), _ptr(cg), 0 if cg is None else cg.size, ctypes.byref(total), _ptr(ncg), _ptr(st))
+        self._check(rc, "bsb200_pairwise_batch_dense_bits")
+        self.last_timing = self.timing()
+        return BatchResult(res, cg, None, ncg, st)
 
     def edit_batch(self, batch, mode, bandwidth, want_cigar=True, out=None, dense=False):
         if dense:
@@ -223,9 +235,7 @@ class Context:
         rc = self._lib.bsb200_kmer_edit_batch_dense(self._h, n, _ptr(batch.seqs), _ptr(batch.qoff), _ptr(batch.qlen), _ptr(batch.toff), _ptr(batch.tlen),
                                                     int(ksz), _ptr(res), _ptr(cg), len(cg), ctypes.byref(total), _ptr(ncg), _ptr(st))
         self._check(rc, "bsb200_kmer_edit_batch_dense")
-        doff = np.zeros(n + 1, dtype=np.uint64)
-        np.cumsum(ncg, out=doff[1:])
-        return BatchResult(res, cg, doff, ncg, st)
+        return BatchResult(res, cg, None, ncg, st)
 
     # ---- staged form: inputs stay resident in HBM between runs -------------------------------------
     def upload(self, kind, batch, mode, bandwidth, matrix=None, gaps=(0, 0, 0, 0), want_cigar=True):
@@ -435,9 +445,16 @@ class BatchResult:
     def __init__(self, results, cigar_arena, cigar_off, ncigar, status):
         self.results = results      # (n, 10) int32, columns = RESULT_FIELDS
         self.cigar_arena = cigar_arena
-        self.cigar_off = cigar_off
+        self._off = cigar_off       # None: dense pair-ordered cigars, the offsets are the running sum of ncigar (computed on first use)
         self.ncigar = ncigar
         self.status = status
+
+    @property
+    def cigar_off(self):
+        if self._off is None:
+            self._off = np.zeros(len(self.ncigar) + 1, dtype=np.uint64)
+            np.cumsum(self.ncigar, out=self._off[1:])
+        return self._off
 
     def cigar(self, i):
         o = int(self.cigar_off[i])
@@ -466,9 +483,7 @@ class ResidentBatch:
         total = ctypes.c_uint64(0)
         rc = self.ctx._lib.bsb200_batch_fetch_dense(self.ctx._h, self._h, _ptr(res), _ptr(cg), 0 if cg is None else cg.size, ctypes.byref(total), _ptr(ncg), _ptr(st))
         self.ctx._check(rc, "bsb200_batch_fetch_dense")
-        doff = np.zeros(len(ncg) + 1, dtype=np.uint64)
-        np.cumsum(ncg, out=doff[1:])
-        return BatchResult(res, cg, doff, ncg, st)
+        return BatchResult(res, cg, None, ncg, st)
 
     def fetch_dense_dev(self, d_results, d_cigars, cigar_cap_words, d_ncigar, d_status):
         """Results into DEVICE buffers (int device pointers, any may be 0/None).  Returns the number of dense cigar words."""

@@ -23,6 +23,8 @@
 #include <numeric>
 #include <string>
 #include <thread>
+#include <mutex>
+#include <condition_variable>
 #include <atomic>
 #include <vector>
 
@@ -37,7 +39,7 @@ struct DevBuf {
 		if(n <= cap) return cudaSuccess;
 		if(p) cudaFree(p);
 		p = nullptr; cap = 0;
-		size_t want = exact ? n + 256 : n + n / 8 + 256;
+		size_t want = (exact && n > (4ull << 30)) ? n + 256 : n + n / 8 + 256;   // exact: only the large arenas are sized against the free memory
 		cudaError_t e = cudaMalloc(&p, want);
 		if(e == cudaSuccess) cap = want;
 		return e;
@@ -81,6 +83,7 @@ struct bsb200_ctx {
 	DevBuf dev_cache[18];
 	HostBuf host_cache[8];
 	DevBuf poa_cache[40];   // same, for POA sweep batches (poa_host.cuh)
+	bsb200_ctx *helper = nullptr;   // second context on the same device: the one-call entry points pipeline large edit batches over both
 	DevBuf kmer_cache[8];   // k-mer guided edit: warp slots, gap-trace pool, counters, order list, fallback sub-batch results
 	HostBuf poa_hcache[2];
 };
@@ -148,6 +151,7 @@ extern "C" bsb200_ctx *bsb200_create(int device, uint64_t trace_budget_bytes){
 
 extern "C" void bsb200_destroy(bsb200_ctx *ctx){
 	if(!ctx) return;
+	if(ctx->helper){ bsb200_destroy(ctx->helper); ctx->helper = nullptr; }
 	cudaSetDevice(ctx->device);
 	cudaStreamSynchronize(ctx->stream);
 	ctx->trace.release(); ctx->trace2.release(); ctx->counter.release();
@@ -165,6 +169,7 @@ extern "C" void bsb200_destroy(bsb200_ctx *ctx){
 // give the traceback arena and every cached buffer back to the device (the next batch allocates again)
 extern "C" void bsb200_trim(bsb200_ctx *ctx){
 	if(!ctx) return;
+	if(ctx->helper) bsb200_trim(ctx->helper);
 	cudaSetDevice(ctx->device);
 	cudaStreamSynchronize(ctx->stream);
 	ctx->trace.release(); ctx->trace2.release();
@@ -276,9 +281,13 @@ static int plan_wave(const bsb200_ctx *ctx, const bsb200_batch *b, uint32_t min_
 // d_seqs_ext: the sequence arena is already in this device's memory (it arrived over NVLink: bsalign_b200/shard.py); the batch
 // uses it in place and the caller keeps it alive until bsb200_batch_free.  Offsets and lengths are host arrays in both cases.
 // bits64: the sequences come 2-bit packed (bsb200_batch_upload_bits): a quarter of the bytes cross PCIe, a kernel unpacks them.
+// The sequences of a batch may come from TWO stretches of the caller's arena (all queries / all targets of a chunk of pairs): the
+// second stretch starts at base `at1` of the batch's own arena; lengths in bases (bits: whole words, at1 a multiple of 32).
+struct SeqSegs { uint64_t src1, len0, len1, at1; };
+
 static bsb200_batch *upload_impl(bsb200_ctx *ctx, int kind, uint64_t n, const uint8_t *seqs, const uint8_t *d_seqs_ext, const uint64_t *bits64,
 		const uint64_t *qoff, const uint32_t *qlen, const uint64_t *toff, const uint32_t *tlen,
-		int mode, uint32_t bandwidth, const int8_t matrix[16], int8_t go1, int8_t ge1, int8_t go2, int8_t ge2, int want_cigar){
+		int mode, uint32_t bandwidth, const int8_t matrix[16], int8_t go1, int8_t ge1, int8_t go2, int8_t ge2, int want_cigar, const SeqSegs *segs = nullptr){
 	if(!ctx) return nullptr;
 	ctx->err.clear();
 	if(n >= 0xFFFFFFF0ull || (n && ((!seqs && !d_seqs_ext && !bits64) || !qoff || !qlen || !toff || !tlen)) || (kind == 0 && !matrix) || kind < 0 || kind > 1){
@@ -338,10 +347,18 @@ static bsb200_batch *upload_impl(bsb200_ctx *ctx, int kind, uint64_t n, const ui
 				const uint64_t nw = (seq_end + 31) / 32;
 				R(b->d_bits.reserve(nw * 8 + 8));
 				if(e == cudaSuccess){
-					R(cudaMemcpyAsync(b->d_bits.p, bits64, nw * 8, cudaMemcpyHostToDevice, st));
+					if(segs){
+						R(cudaMemcpyAsync(b->d_bits.p, bits64, (segs->len0 + 31) / 32 * 8, cudaMemcpyHostToDevice, st));
+						R(cudaMemcpyAsync(b->d_bits.as<uint64_t>() + segs->at1 / 32, bits64 + segs->src1 / 32, (segs->len1 + 31) / 32 * 8, cudaMemcpyHostToDevice, st));
+					} else R(cudaMemcpyAsync(b->d_bits.p, bits64, nw * 8, cudaMemcpyHostToDevice, st));
 					unpack_bits_kernel<<<(unsigned)((nw + 255) / 256), 256, 0, st>>>(b->d_bits.as<uint64_t>(), b->d_seqs.as<uint8_t>(), nw, seq_end);
 				}
-			} else if(!d_seqs_ext) R(cudaMemcpyAsync(b->d_seqs.p, seqs, seq_end, cudaMemcpyHostToDevice, st));
+			} else if(!d_seqs_ext){
+				if(segs){
+					R(cudaMemcpyAsync(b->d_seqs.p, seqs, segs->len0, cudaMemcpyHostToDevice, st));
+					R(cudaMemcpyAsync(b->d_seqs.as<uint8_t>() + segs->at1, seqs + segs->src1, segs->len1, cudaMemcpyHostToDevice, st));
+				} else R(cudaMemcpyAsync(b->d_seqs.p, seqs, seq_end, cudaMemcpyHostToDevice, st));
+			}
 			R(cudaMemcpyAsync(b->d_qoff.p, qoff, n * 8, cudaMemcpyHostToDevice, st));
 			R(cudaMemcpyAsync(b->d_toff.p, toff, n * 8, cudaMemcpyHostToDevice, st));
 			R(cudaMemcpyAsync(b->d_qlen.p, qlen, n * 4, cudaMemcpyHostToDevice, st));
@@ -575,7 +592,10 @@ static bsb200_batch *upload_impl(bsb200_ctx *ctx, int kind, uint64_t n, const ui
 	float ms = 0; cudaEventElapsedTime(&ms, ctx->ev[0], ctx->ev[1]);
 	ctx->timing = bsb200_timing_t();
 	ctx->timing.h2d_ms = ms;
-	ctx->timing.h2d_bytes = (d_seqs_ext ? 0 : (bits64 ? (seq_end + 31) / 32 * 8 : seq_end)) + n * (8 + 8 + 4 + 4 + 4 + 8) + (want_cigar ? (n + 1) * 8 : 0);
+	{
+		const uint64_t sb = segs ? segs->len0 + segs->len1 : seq_end;
+		ctx->timing.h2d_bytes = (d_seqs_ext ? 0 : (bits64 ? (sb + 31) / 32 * 8 : sb)) + n * (8 + 8 + 4 + 4 + 4 + 8) + (want_cigar ? (n + 1) * 8 : 0);
+	}
 	ctx->timing.cells = b->cells;
 	ctx->timing.trace_bytes = b->trace_bytes;
 	ctx->timing.waves = (uint32_t)b->waves.size();
@@ -1329,12 +1349,155 @@ extern "C" int bsb200_edit_pairwise_batch(bsb200_ctx *ctx, uint64_t n, const uin
 }
 
 // ---- one call, dense pair-ordered cigars (the fast path of the staged form as ONE ABI function) ---------------------------------
+// Large EDIT batches are cut into chunks of consecutive pairs that two host threads push through two contexts of the same device
+// (ctx and ctx->helper, one stream each): the H2D copy of chunk c + 1 and the host plan of chunk c + 2 run while chunk c is in its
+// kernel and its results travel back.  A million 300 bp pairs are 600 MB in, 5 ms of kernel and 100 MB out: without the overlap the
+// call takes the sum, with it little more than the copy.  The chunks' dense cigars are fetched in chunk order, each behind the
+// words of its predecessors.  Either the byte arena (seqs) or the 2-bit words (bits; offsets are base offsets) is given.
+static int dense_pipelined(bsb200_ctx *ctx, int kind, uint64_t n, const uint8_t *seqs, const uint64_t *bits,
+		const uint64_t *qoff, const uint32_t *qlen, const uint64_t *toff, const uint32_t *tlen,
+		int mode, uint32_t bandwidth, const int8_t *matrix, int8_t go1, int8_t ge1, int8_t go2, int8_t ge2,
+		bsb200_result_t *results, uint32_t *cigars, uint64_t cigar_cap_words, uint64_t *total_words, uint32_t *ncigar, int32_t *status){
+	if(!ctx->helper){
+		ctx->helper = bsb200_create(ctx->device, ctx->trace_budget ? ctx->trace_budget / 2 : 0);
+		if(!ctx->helper) return fail(ctx, "second context for the pipelined call", cudaSuccess);
+	}
+	ctx->err.clear();
+	const auto call0 = std::chrono::steady_clock::now();
+	const uint64_t K = std::min<uint64_t>(8, std::max<uint64_t>(2, n / 131072));
+	struct { std::mutex m, upload; std::condition_variable cv; uint64_t next_fetch = 0, base = 0; int err = 0; std::string msg; } sy;
+	bsb200_timing_t acc[2] = {bsb200_timing_t(), bsb200_timing_t()};
+	auto worker = [&](int t){
+		bsb200_ctx *cx = t ? ctx->helper : ctx;
+		cudaSetDevice(cx->device);
+		// rebased offsets live in pinned memory: a copy from pageable memory would wait for the sequence copy queued before it
+		HostBuf &hq2 = cx->host_cache[6], &ht2 = cx->host_cache[7];
+		// the stretch of the arena a chunk's queries come from and the one its targets come from: one copy when they touch or overlap
+		// (pairs stored q, t, q, t ...), two when the arena holds all queries first and all targets behind them.  The chunk after next is
+		// prepared while this worker's chunk is still on the device.
+		SeqSegs sg; bool two = false; uint64_t lo = 0;
+		auto prep = [&](uint64_t c){
+			const uint64_t c0 = n * c / K, c1 = n * (c + 1) / K, m = c1 - c0;
+			uint64_t qlo = ~0ull, qhi = 0, tlo = ~0ull, thi = 0;
+			for(uint64_t i=c0;i<c1;i++){
+				qlo = std::min(qlo, qoff[i]); qhi = std::max(qhi, qoff[i] + qlen[i]);
+				tlo = std::min(tlo, toff[i]); thi = std::max(thi, toff[i] + tlen[i]);
+			}
+			if(bits){ qlo &= ~31ull; tlo &= ~31ull; }   // whole words
+			if(hq2.reserve(m * 8) != cudaSuccess || ht2.reserve(m * 8) != cudaSuccess){ cudaGetLastError(); std::lock_guard<std::mutex> g(sy.m); if(!sy.err){ sy.err = -1; sy.msg = "pinned host allocation"; } return; }
+			uint64_t *q2 = hq2.as<uint64_t>(), *t2 = ht2.as<uint64_t>();
+			lo = std::min(qlo, tlo);
+			const uint64_t gap = qlo < tlo ? (tlo > qhi ? tlo - qhi : 0) : (qlo > thi ? qlo - thi : 0);
+			two = gap > 4096;
+			if(two){
+				const bool qfirst = qlo < tlo;
+				const uint64_t len0 = qfirst ? qhi - qlo : thi - tlo, at1 = (len0 + 127) / 128 * 128;
+				sg.len0 = len0; sg.len1 = qfirst ? thi - tlo : qhi - qlo; sg.src1 = (qfirst ? tlo : qlo) - lo; sg.at1 = at1;
+				for(uint64_t i=0;i<m;i++){
+					q2[i] = qfirst ? qoff[c0 + i] - qlo : qoff[c0 + i] - qlo + at1;
+					t2[i] = qfirst ? toff[c0 + i] - tlo + at1 : toff[c0 + i] - tlo;
+				}
+			} else for(uint64_t i=0;i<m;i++){ q2[i] = qoff[c0 + i] - lo; t2[i] = toff[c0 + i] - lo; }
+		};
+		if((uint64_t)t < K) prep((uint64_t)t);
+		for(uint64_t c=(uint64_t)t;c<K;c+=2){
+			const uint64_t c0 = n * c / K, c1 = n * (c + 1) / K, m = c1 - c0;
+			const auto tstart = std::chrono::steady_clock::now();
+			uint64_t *q2 = hq2.as<uint64_t>(), *t2 = ht2.as<uint64_t>();
+			const SeqSegs sgc = sg; const SeqSegs *psg = two ? &sgc : nullptr;
+			int rc = 0;
+			{ std::lock_guard<std::mutex> g(sy.m); rc = sy.err; }
+			auto w0 = tstart;
+			auto wlap = [&](const char *what){ if(getenv("BSB200_HOSTPROF")){ auto w1 = std::chrono::steady_clock::now(); fprintf(stderr, "[pipe %d] chunk %llu %-8s %7.3f ms  (at %7.3f)\n", t, (unsigned long long)c, what, std::chrono::duration<double, std::milli>(w1 - w0).count(), std::chrono::duration<double, std::milli>(w1 - call0).count()); w0 = w1; } };
+			// one upload at a time: the link is shared anyway, and two workers that copy side by side fall into lock step (both copy, both
+			// compute, both fetch) instead of one copying while the other computes
+			bsb200_batch *b = nullptr;
+			{
+				std::lock_guard<std::mutex> up(sy.upload);
+				wlap("token");
+				b = rc ? nullptr : upload_impl(cx, kind, m, seqs ? seqs + lo : nullptr, nullptr, bits ? bits + (lo >> 5) : nullptr, q2, qlen + c0, t2, tlen + c0,
+					mode, bandwidth, matrix, go1, ge1, go2, ge2, cigars != nullptr, psg);
+			}
+			if(!b && !rc) rc = -1;
+			bsb200_timing_t tm = cx->timing;
+			wlap("upload");
+			if(rc == 0){ rc = bsb200_batch_run(cx, b); const float h = tm.h2d_ms; const uint64_t hb = tm.h2d_bytes; tm = cx->timing; tm.h2d_ms = h; tm.h2d_bytes = hb; }
+			wlap("run");
+			if(c + 2 < K) prep(c + 2);
+			wlap("prep+2");
+			std::unique_lock<std::mutex> lk(sy.m);
+			sy.cv.wait(lk, [&]{ return sy.next_fetch == c; });   // the dense cigars of the chunks go out in chunk order
+			wlap("wait");
+			if(rc == 0 && sy.err) rc = sy.err;
+			const uint64_t base = sy.base;
+			lk.unlock();
+			uint64_t tw = 0;
+			if(rc == 0){
+				rc = fetch_impl(cx, b, results + c0, cigars ? cigars + base : nullptr, nullptr, cigar_cap_words > base ? cigar_cap_words - base : 0, &tw, ncigar ? ncigar + c0 : nullptr, status ? status + c0 : nullptr);
+				tm.d2h_ms = cx->timing.d2h_ms; tm.d2h_bytes = cx->timing.d2h_bytes;
+			}
+			wlap("fetch");
+			lk.lock();
+			if(rc && !sy.err){ sy.err = rc; sy.msg = cx->err; }
+			sy.base = base + tw; sy.next_fetch = c + 1;
+			lk.unlock();
+			sy.cv.notify_all();
+			if(b) bsb200_batch_free(cx, b);
+			wlap("free");
+			bsb200_timing_t &A = acc[t];
+			A.h2d_ms += tm.h2d_ms; A.forward_ms += tm.forward_ms; A.traceback_ms += tm.traceback_ms; A.d2h_ms += tm.d2h_ms; A.run_ms += tm.run_ms;
+			A.forward_launches += tm.forward_launches; A.traceback_launches += tm.traceback_launches; A.other_launches += tm.other_launches;
+			A.cells += tm.cells; A.trace_bytes += tm.trace_bytes; A.h2d_bytes += tm.h2d_bytes; A.d2h_bytes += tm.d2h_bytes;
+		}
+	};
+	std::thread th(worker, 1);
+	worker(0);
+	th.join();
+	if(getenv("BSB200_HOSTPROF")) fprintf(stderr, "[pipe] all chunks done at %7.3f ms\n", std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - call0).count());
+	cudaSetDevice(ctx->device);
+	bsb200_timing_t T = acc[0];
+	T.h2d_ms += acc[1].h2d_ms; T.forward_ms += acc[1].forward_ms; T.traceback_ms += acc[1].traceback_ms; T.d2h_ms += acc[1].d2h_ms; T.run_ms += acc[1].run_ms;
+	T.forward_launches += acc[1].forward_launches; T.traceback_launches += acc[1].traceback_launches; T.other_launches += acc[1].other_launches;
+	T.cells += acc[1].cells; T.trace_bytes += acc[1].trace_bytes; T.h2d_bytes += acc[1].h2d_bytes; T.d2h_bytes += acc[1].d2h_bytes;
+	T.waves = (uint32_t)K; T.total_ms = T.h2d_ms + T.run_ms + T.d2h_ms;   // sums over the chunks: they overlap, the wall time is shorter
+	ctx->timing = T;
+	if(total_words) *total_words = sy.base;
+	if(sy.err){ ctx->err = sy.msg; return sy.err; }
+	return 0;
+}
+
+static bool pipeline_pays(int kind, uint64_t n){
+	if(getenv("BSB200_NOPIPE")) return false;
+	return kind == 1 && n >= 262144;
+}
+
 extern "C" int bsb200_pairwise_batch_dense(bsb200_ctx *ctx, int kind, uint64_t n, const uint8_t *seqs,
 		const uint64_t *qoff, const uint32_t *qlen, const uint64_t *toff, const uint32_t *tlen,
 		int mode, uint32_t bandwidth, const int8_t matrix[16], int8_t go1, int8_t ge1, int8_t go2, int8_t ge2,
 		bsb200_result_t *results, uint32_t *cigars, uint64_t cigar_cap_words, uint64_t *total_words, uint32_t *ncigar, int32_t *status){
 	if(!ctx) return -1;
+	if(pipeline_pays(kind, n) && seqs && qoff && qlen && toff && tlen && results)
+		return dense_pipelined(ctx, kind, n, seqs, nullptr, qoff, qlen, toff, tlen, mode, bandwidth, matrix, go1, ge1, go2, ge2, results, cigars, cigar_cap_words, total_words, ncigar, status);
 	bsb200_batch *b = bsb200_batch_upload(ctx, kind, n, seqs, qoff, qlen, toff, tlen, mode, bandwidth, matrix, go1, ge1, go2, ge2, cigars != nullptr);
+	if(!b) return -1;
+	int rc = bsb200_batch_run(ctx, b);
+	if(rc == 0) rc = bsb200_batch_fetch_dense(ctx, b, results, cigars, cigar_cap_words, total_words, ncigar, status);
+	bsb200_timing_t tm = ctx->timing;
+	bsb200_batch_free(ctx, b);
+	tm.total_ms = tm.h2d_ms + tm.run_ms + tm.d2h_ms;
+	ctx->timing = tm;
+	return rc;
+}
+
+// the same call with the sequences 2-bit packed (a BaseBank's words, see bsb200_batch_upload_bits; qoff / toff are base offsets)
+extern "C" int bsb200_pairwise_batch_dense_bits(bsb200_ctx *ctx, int kind, uint64_t n, const uint64_t *bits,
+		const uint64_t *qoff, const uint32_t *qlen, const uint64_t *toff, const uint32_t *tlen,
+		int mode, uint32_t bandwidth, const int8_t matrix[16], int8_t go1, int8_t ge1, int8_t go2, int8_t ge2,
+		bsb200_result_t *results, uint32_t *cigars, uint64_t cigar_cap_words, uint64_t *total_words, uint32_t *ncigar, int32_t *status){
+	if(!ctx) return -1;
+	if(pipeline_pays(kind, n) && bits && qoff && qlen && toff && tlen && results)
+		return dense_pipelined(ctx, kind, n, nullptr, bits, qoff, qlen, toff, tlen, mode, bandwidth, matrix, go1, ge1, go2, ge2, results, cigars, cigar_cap_words, total_words, ncigar, status);
+	bsb200_batch *b = bsb200_batch_upload_bits(ctx, kind, n, bits, qoff, qlen, toff, tlen, mode, bandwidth, matrix, go1, ge1, go2, ge2, cigars != nullptr);
 	if(!b) return -1;
 	int rc = bsb200_batch_run(ctx, b);
 	if(rc == 0) rc = bsb200_batch_fetch_dense(ctx, b, results, cigars, cigar_cap_words, total_words, ncigar, status);

@@ -122,6 +122,12 @@ int bsb200_pairwise_batch_dense(bsb200_ctx *ctx, int kind, uint64_t n, const uin
 		const uint64_t *qoff, const uint32_t *qlen, const uint64_t *toff, const uint32_t *tlen,
 		int mode, uint32_t bandwidth, const int8_t matrix[16], int8_t gapo1, int8_t gape1, int8_t gapo2, int8_t gape2,
 		bsb200_result_t *results, uint32_t *cigars, uint64_t cigar_cap_words, uint64_t *total_words, uint32_t *ncigar, int32_t *status);
+/* the same call with the sequences 2-BIT PACKED (a BaseBank's words as in bsb200_batch_upload_bits; qoff / toff are base offsets).  Both
+ * forms pipeline large edit batches internally: chunks of pairs go through two streams, so copies, host planning and kernels overlap. */
+int bsb200_pairwise_batch_dense_bits(bsb200_ctx *ctx, int kind, uint64_t n, const uint64_t *bits,
+		const uint64_t *qoff, const uint32_t *qlen, const uint64_t *toff, const uint32_t *tlen,
+		int mode, uint32_t bandwidth, const int8_t matrix[16], int8_t gapo1, int8_t gape1, int8_t gapo2, int8_t gape2,
+		bsb200_result_t *results, uint32_t *cigars, uint64_t cigar_cap_words, uint64_t *total_words, uint32_t *ncigar, int32_t *status);
 /* one POINTER per sequence, the way the reference's callers hold them (bsalign.h:399 takes u1i *qseq, u1i *tseq per call); gathered into
  * one pinned arena by `nthreads` host threads.  cigar_out (may be NULL) holds one pointer per pair (entries may be NULL) with room for
  * qlen[i] + tlen[i] + 2 words. */

@@ -438,3 +438,34 @@ def test_kmer_edit_matches_golden_and_oracle(ctx, monkeypatch):
     monkeypatch.setenv("BSB200_KMER_POOL", "2000000")
     monkeypatch.setenv("BSB200_KMER_GROUP", "32")
     check(big, 13)
+
+
+def test_pipelined_one_call_equals_plain_call(ctx, monkeypatch):
+    """bsb200_pairwise_batch_dense / _dense_bits cut large edit batches into chunks that two streams work on (copies, host planning and
+    kernels overlap): same results, same dense cigars as the unpipelined call, from bytes and from 2-bit words."""
+    rng = np.random.default_rng(9)
+    n = 300000
+    q = rng.integers(0, 4, (n, 48)).astype(np.uint8)
+    t, tl = synth.mutate_batch(rng, q, .03, .03, .03)
+    qoff = np.arange(n, dtype=np.uint64) * 48
+    toff = n * 48 + np.concatenate([[0], np.cumsum(tl[:-1].astype(np.uint64))]).astype(np.uint64)
+    qlen = np.full(n, 48, np.uint32)
+    qlen[[5, 37499, 37500, n - 1]] = 0          # empty pairs, also on chunk borders
+    b = synth.PairBatch(np.concatenate([q.ravel(), t]), qoff, qlen, toff, tl.astype(np.uint32))
+    monkeypatch.setenv("BSB200_NOPIPE", "1")
+    plain = ctx.edit_batch(b, 0, 64, dense=True)
+    assert ctx.last_timing["waves"] == 1
+    monkeypatch.delenv("BSB200_NOPIPE")
+    piped = ctx.edit_batch(b, 0, 64, dense=True)
+    assert ctx.last_timing["waves"] > 1
+    bits = api.pack_bits(b.seqs)
+    packed = ctx.dense_bits("edit", bits, b, 0, 64)
+    for got in (piped, packed):
+        assert np.array_equal(got.results, plain.results) and np.array_equal(got.ncigar, plain.ncigar) and np.array_equal(got.status, plain.status)
+        tot = int(plain.ncigar.sum())
+        assert np.array_equal(got.cigar_arena[:tot], plain.cigar_arena[:tot])
+    m = 2000
+    sub = synth.PairBatch(b.seqs, b.qoff[:m], b.qlen[:m], b.toff[:m], b.tlen[:m])
+    exp, ecg, _ = ck.oracle_batch("edit", sub, 0, 64)
+    gc = piped.cigars()
+    assert np.array_equal(piped.results[:m], exp) and all(np.array_equal(gc[i], ecg[i]) for i in range(m))
