@@ -391,14 +391,24 @@ def run_kmer_edit(ctx, ncores, pairs=1000000, qlen=300, ksz=13, steps=2, warmup=
     outbuf = tuple(pin(a) if a is not None else None for a in api._alloc_out(hb, True))
     got = None
     walls, kern, fb = [], [], []
-    for it in range(warmup + steps):
-        torch.cuda.synchronize()
-        t0 = time.perf_counter()
-        got = ctx.kmer_edit_batch(hb, ksz, dense=True, out=outbuf)
-        dt = time.perf_counter() - t0
-        tm = ctx.timing()
-        if it >= warmup:
-            walls.append(dt); kern.append(tm["forward_ms"] + tm["traceback_ms"]); fb.append(tm["waves"])
+    # kernel-only: the unpipelined call (one launch over the whole batch, CUDA events around it); end to end: the call as a user makes it
+    # (batches of this size are pipelined in chunks over two streams inside the call)
+    for pipe in (False, True):
+        if pipe:
+            os.environ.pop("BSB200_NOPIPE", None)
+        else:
+            os.environ["BSB200_NOPIPE"] = "1"
+        for it in range(warmup + steps):
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            got = ctx.kmer_edit_batch(hb, ksz, dense=True, out=outbuf)
+            dt = time.perf_counter() - t0
+            tm = ctx.timing()
+            if it >= warmup:
+                if pipe:
+                    walls.append(dt); fb.append(tm["waves"])
+                else:
+                    kern.append(tm["forward_ms"] + tm["traceback_ms"])
     wall = sum(walls) / len(walls); kms = sum(kern) / len(kern)
     out = {"workload": "c4k: configs[3] batch shape (1M pairs 300bp x 300bp) through the k-mer guided edit, k = %d" % ksz, "pairs": int(batch.n),
            "unit": "Mpairs/s", "value": batch.n / (kms * 1e-3) / 1e6, "kernel_ms_per_step": kms, "e2e": batch.n / wall / 1e6, "e2e_ms_per_step": wall * 1e3,

@@ -25,6 +25,7 @@
 #include <thread>
 #include <mutex>
 #include <condition_variable>
+#include <functional>
 #include <atomic>
 #include <vector>
 
@@ -1056,9 +1057,18 @@ extern "C" int bsb200_batch_fetch_dense_dev(bsb200_ctx *ctx, bsb200_batch *b, in
 // Anchors, chain, filter, the gap alignments and the stitching run in kmer_edit_kernel (kmer_edit.cuh), one warp per pair.  Pairs without
 // usable anchors come back flagged: the reference aligns those with the plain global edit (bsalign.h:1440), and so do we, as a sub-batch
 // of the edit kernel on the arena that is already on the device.  Output as in bsb200_batch_fetch (cgoff given) or bsb200_batch_fetch_dense.
+static int dense_pipelined(bsb200_ctx *ctx, int kind, uint64_t n, const uint8_t *seqs, const uint64_t *bits,
+		const uint64_t *qoff, const uint32_t *qlen, const uint64_t *toff, const uint32_t *tlen,
+		int mode, uint32_t bandwidth, const int8_t *matrix, int8_t go1, int8_t ge1, int8_t go2, int8_t ge2,
+		bsb200_result_t *results, uint32_t *cigars, uint64_t cigar_cap_words, uint64_t *total_words, uint32_t *ncigar, int32_t *status, uint32_t ksz);
+
+// a chunk of a pipelined call fetches its dense cigars behind those of the chunks before it: begin() waits for the turn and returns the
+// words already out, end() publishes this chunk's count
+struct FetchTurn { std::function<uint64_t()> begin; std::function<void(uint64_t)> end; bool taken = false; };
+
 static int kmer_edit_impl(bsb200_ctx *ctx, uint64_t n, const uint8_t *seqs, const uint64_t *qoff, const uint32_t *qlen, const uint64_t *toff,
 		const uint32_t *tlen, uint32_t ksz, bsb200_result_t *results, uint32_t *cigars, const uint64_t *cgoff, uint64_t dense_cap, uint64_t *total_words,
-		uint32_t *ncigar, int32_t *status){
+		uint32_t *ncigar, int32_t *status, const SeqSegs *segs = nullptr, FetchTurn *turn = nullptr, int share = 1){
 	if(!ctx) return -1;
 	ctx->err.clear();
 	if(total_words) *total_words = 0;
@@ -1108,7 +1118,10 @@ static int kmer_edit_impl(bsb200_ctx *ctx, uint64_t n, const uint8_t *seqs, cons
 	CKK(cudaEventCreate(&evk[0])); CKK(cudaEventCreate(&evk[1]));
 	lap("output buffers + events");
 	cudaEventRecord(ctx->ev[0], st);
-	CKK(cudaMemcpyAsync(b->d_seqs.p, seqs, seq_end, cudaMemcpyHostToDevice, st));
+	if(segs){
+		CKK(cudaMemcpyAsync(b->d_seqs.p, seqs, segs->len0, cudaMemcpyHostToDevice, st));
+		CKK(cudaMemcpyAsync(b->d_seqs.as<uint8_t>() + segs->at1, seqs + segs->src1, segs->len1, cudaMemcpyHostToDevice, st));
+	} else CKK(cudaMemcpyAsync(b->d_seqs.p, seqs, seq_end, cudaMemcpyHostToDevice, st));
 	CKK(cudaMemcpyAsync(b->d_qoff.p, qoff, n * 8, cudaMemcpyHostToDevice, st));
 	CKK(cudaMemcpyAsync(b->d_toff.p, toff, n * 8, cudaMemcpyHostToDevice, st));
 	CKK(cudaMemcpyAsync(b->d_qlen.p, qlen, n * 4, cudaMemcpyHostToDevice, st));
@@ -1123,7 +1136,7 @@ static int kmer_edit_impl(bsb200_ctx *ctx, uint64_t n, const uint8_t *seqs, cons
 	int occ = 0;
 	CKK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kmer_edit_kernel, kKmWarps * 32, 0));
 	if(occ < 1) occ = 1;
-	const uint64_t max_warps = (uint64_t)ctx->num_sms * occ * kKmWarps;
+	const uint64_t max_warps = std::max<uint64_t>(kKmWarps, (uint64_t)ctx->num_sms * occ * kKmWarps / (share > 1 ? share : 1));   // share: calls running side by side on this device
 	// pairs a warp works on at a time: as many as leave every warp of the GPU at least two groups (a group's serial phases use one lane per pair)
 	uint32_t group = 1;
 	while(group < 32 && n >= 2 * max_warps * (group * 2)) group *= 2;
@@ -1232,9 +1245,13 @@ static int kmer_edit_impl(bsb200_ctx *ctx, uint64_t n, const uint8_t *seqs, cons
 	cudaEventElapsedTime(&k_ms, evk[0], evk[1]);
 	b->ran = true;
 	ctx->timing = bsb200_timing_t();
-	int rc = fetch_impl(ctx, b, results, cigars, cgoff, dense_cap, total_words, ncigar, status);
+	uint64_t base = 0, tw = 0;
+	if(turn){ base = turn->begin(); turn->taken = true; }
+	int rc = fetch_impl(ctx, b, results, (cigars && !cgoff) ? cigars + base : cigars, cgoff, dense_cap > base ? dense_cap - base : 0, &tw, ncigar, status);
+	if(turn) turn->end(rc == 0 ? tw : 0);
+	if(total_words) *total_words = tw;
 	lap("fetch");
-	ctx->timing.h2d_ms = h2d_ms; ctx->timing.h2d_bytes = seq_end + n * 24;
+	ctx->timing.h2d_ms = h2d_ms; ctx->timing.h2d_bytes = (segs ? segs->len0 + segs->len1 : seq_end) + n * 24;
 	ctx->timing.forward_ms = k_ms; ctx->timing.forward_launches = launches;
 	ctx->timing.traceback_ms = fb_ms; ctx->timing.other_launches = fb_launches;   // the fallback sub-batch (edit kernel) and the merge
 	ctx->timing.run_ms = k_ms + fb_ms; ctx->timing.cells = cells; ctx->timing.waves = (uint32_t)fall.size();   // waves: pairs that took the fallback
@@ -1250,6 +1267,8 @@ extern "C" int bsb200_kmer_edit_batch(bsb200_ctx *ctx, uint64_t n, const uint8_t
 
 extern "C" int bsb200_kmer_edit_batch_dense(bsb200_ctx *ctx, uint64_t n, const uint8_t *seqs, const uint64_t *qoff, const uint32_t *qlen, const uint64_t *toff,
 		const uint32_t *tlen, uint32_t ksz, bsb200_result_t *results, uint32_t *cigars, uint64_t cigar_cap_words, uint64_t *total_words, uint32_t *ncigar, int32_t *status){
+	if(ctx && n >= 400000 && !getenv("BSB200_NOPIPE") && ksz && seqs && qoff && qlen && toff && tlen && results)   // see dense_pipelined
+		return dense_pipelined(ctx, 1, n, seqs, nullptr, qoff, qlen, toff, tlen, 0, 0, nullptr, 0, 0, 0, 0, results, cigars, cigar_cap_words, total_words, ncigar, status, ksz > 15 ? 15 : ksz);
 	return kmer_edit_impl(ctx, n, seqs, qoff, qlen, toff, tlen, ksz, results, cigars, nullptr, cigar_cap_words, total_words, ncigar, status);
 }
 
@@ -1357,14 +1376,15 @@ extern "C" int bsb200_edit_pairwise_batch(bsb200_ctx *ctx, uint64_t n, const uin
 static int dense_pipelined(bsb200_ctx *ctx, int kind, uint64_t n, const uint8_t *seqs, const uint64_t *bits,
 		const uint64_t *qoff, const uint32_t *qlen, const uint64_t *toff, const uint32_t *tlen,
 		int mode, uint32_t bandwidth, const int8_t *matrix, int8_t go1, int8_t ge1, int8_t go2, int8_t ge2,
-		bsb200_result_t *results, uint32_t *cigars, uint64_t cigar_cap_words, uint64_t *total_words, uint32_t *ncigar, int32_t *status){
+		bsb200_result_t *results, uint32_t *cigars, uint64_t cigar_cap_words, uint64_t *total_words, uint32_t *ncigar, int32_t *status, uint32_t ksz){
 	if(!ctx->helper){
 		ctx->helper = bsb200_create(ctx->device, ctx->trace_budget ? ctx->trace_budget / 2 : 0);
 		if(!ctx->helper) return fail(ctx, "second context for the pipelined call", cudaSuccess);
 	}
 	ctx->err.clear();
 	const auto call0 = std::chrono::steady_clock::now();
-	const uint64_t K = std::min<uint64_t>(8, std::max<uint64_t>(2, n / 131072));
+	// (the k-mer guided edit, ksz > 0, is kernel bound and its kernel likes many pairs per launch: fewer, larger chunks)
+	const uint64_t K = ksz ? std::min<uint64_t>(4, std::max<uint64_t>(2, n / 200000)) : std::min<uint64_t>(8, std::max<uint64_t>(2, n / 131072));
 	struct { std::mutex m, upload; std::condition_variable cv; uint64_t next_fetch = 0, base = 0; int err = 0; std::string msg; } sy;
 	bsb200_timing_t acc[2] = {bsb200_timing_t(), bsb200_timing_t()};
 	auto worker = [&](int t){
@@ -1409,6 +1429,22 @@ static int dense_pipelined(bsb200_ctx *ctx, int kind, uint64_t n, const uint8_t 
 			{ std::lock_guard<std::mutex> g(sy.m); rc = sy.err; }
 			auto w0 = tstart;
 			auto wlap = [&](const char *what){ if(getenv("BSB200_HOSTPROF")){ auto w1 = std::chrono::steady_clock::now(); fprintf(stderr, "[pipe %d] chunk %llu %-8s %7.3f ms  (at %7.3f)\n", t, (unsigned long long)c, what, std::chrono::duration<double, std::milli>(w1 - w0).count(), std::chrono::duration<double, std::milli>(w1 - call0).count()); w0 = w1; } };
+			if(ksz){   // the k-mer guided edit is one function: copies, kernel rounds, fallback pairs; it takes its fetch turn through the hook
+				FetchTurn turn;
+				turn.begin = [&]() -> uint64_t { std::unique_lock<std::mutex> lk(sy.m); sy.cv.wait(lk, [&]{ return sy.next_fetch == c; }); return sy.base; };
+				turn.end = [&](uint64_t tw){ { std::lock_guard<std::mutex> g(sy.m); sy.base += tw; sy.next_fetch = c + 1; } sy.cv.notify_all(); };
+				if(rc == 0) rc = kmer_edit_impl(cx, m, seqs + lo, q2, qlen + c0, t2, tlen + c0, ksz, results + c0, cigars, nullptr, cigar_cap_words, nullptr,
+					ncigar ? ncigar + c0 : nullptr, status ? status + c0 : nullptr, psg, &turn, 2);
+				if(!turn.taken){ turn.begin(); turn.end(0); }
+				if(rc){ std::lock_guard<std::mutex> g(sy.m); if(!sy.err){ sy.err = rc; sy.msg = cx->err; } }
+				const bsb200_timing_t tm = cx->timing;
+				bsb200_timing_t &A = acc[t];
+				A.h2d_ms += tm.h2d_ms; A.forward_ms += tm.forward_ms; A.traceback_ms += tm.traceback_ms; A.d2h_ms += tm.d2h_ms; A.run_ms += tm.run_ms;
+				A.forward_launches += tm.forward_launches; A.other_launches += tm.other_launches; A.cells += tm.cells; A.h2d_bytes += tm.h2d_bytes; A.d2h_bytes += tm.d2h_bytes;
+				A.reserved += tm.waves;   // pairs that took the fallback
+				if(c + 2 < K) prep(c + 2);
+				continue;
+			}
 			// one upload at a time: the link is shared anyway, and two workers that copy side by side fall into lock step (both copy, both
 			// compute, both fetch) instead of one copying while the other computes
 			bsb200_batch *b = nullptr;
@@ -1459,7 +1495,8 @@ static int dense_pipelined(bsb200_ctx *ctx, int kind, uint64_t n, const uint8_t 
 	T.h2d_ms += acc[1].h2d_ms; T.forward_ms += acc[1].forward_ms; T.traceback_ms += acc[1].traceback_ms; T.d2h_ms += acc[1].d2h_ms; T.run_ms += acc[1].run_ms;
 	T.forward_launches += acc[1].forward_launches; T.traceback_launches += acc[1].traceback_launches; T.other_launches += acc[1].other_launches;
 	T.cells += acc[1].cells; T.trace_bytes += acc[1].trace_bytes; T.h2d_bytes += acc[1].h2d_bytes; T.d2h_bytes += acc[1].d2h_bytes;
-	T.waves = (uint32_t)K; T.total_ms = T.h2d_ms + T.run_ms + T.d2h_ms;   // sums over the chunks: they overlap, the wall time is shorter
+	T.waves = ksz ? acc[0].reserved + acc[1].reserved : (uint32_t)K; T.reserved = 0;
+	T.total_ms = T.h2d_ms + T.run_ms + T.d2h_ms;   // sums over the chunks: they overlap, the wall time is shorter
 	ctx->timing = T;
 	if(total_words) *total_words = sy.base;
 	if(sy.err){ ctx->err = sy.msg; return sy.err; }
@@ -1477,7 +1514,7 @@ extern "C" int bsb200_pairwise_batch_dense(bsb200_ctx *ctx, int kind, uint64_t n
 		bsb200_result_t *results, uint32_t *cigars, uint64_t cigar_cap_words, uint64_t *total_words, uint32_t *ncigar, int32_t *status){
 	if(!ctx) return -1;
 	if(pipeline_pays(kind, n) && seqs && qoff && qlen && toff && tlen && results)
-		return dense_pipelined(ctx, kind, n, seqs, nullptr, qoff, qlen, toff, tlen, mode, bandwidth, matrix, go1, ge1, go2, ge2, results, cigars, cigar_cap_words, total_words, ncigar, status);
+		return dense_pipelined(ctx, kind, n, seqs, nullptr, qoff, qlen, toff, tlen, mode, bandwidth, matrix, go1, ge1, go2, ge2, results, cigars, cigar_cap_words, total_words, ncigar, status, 0);
 	bsb200_batch *b = bsb200_batch_upload(ctx, kind, n, seqs, qoff, qlen, toff, tlen, mode, bandwidth, matrix, go1, ge1, go2, ge2, cigars != nullptr);
 	if(!b) return -1;
 	int rc = bsb200_batch_run(ctx, b);
@@ -1496,7 +1533,7 @@ extern "C" int bsb200_pairwise_batch_dense_bits(bsb200_ctx *ctx, int kind, uint6
 		bsb200_result_t *results, uint32_t *cigars, uint64_t cigar_cap_words, uint64_t *total_words, uint32_t *ncigar, int32_t *status){
 	if(!ctx) return -1;
 	if(pipeline_pays(kind, n) && bits && qoff && qlen && toff && tlen && results)
-		return dense_pipelined(ctx, kind, n, nullptr, bits, qoff, qlen, toff, tlen, mode, bandwidth, matrix, go1, ge1, go2, ge2, results, cigars, cigar_cap_words, total_words, ncigar, status);
+		return dense_pipelined(ctx, kind, n, nullptr, bits, qoff, qlen, toff, tlen, mode, bandwidth, matrix, go1, ge1, go2, ge2, results, cigars, cigar_cap_words, total_words, ncigar, status, 0);
 	bsb200_batch *b = bsb200_batch_upload_bits(ctx, kind, n, bits, qoff, qlen, toff, tlen, mode, bandwidth, matrix, go1, ge1, go2, ge2, cigars != nullptr);
 	if(!b) return -1;
 	int rc = bsb200_batch_run(ctx, b);

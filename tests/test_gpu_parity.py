@@ -469,3 +469,17 @@ def test_pipelined_one_call_equals_plain_call(ctx, monkeypatch):
     exp, ecg, _ = ck.oracle_batch("edit", sub, 0, 64)
     gc = piped.cigars()
     assert np.array_equal(piped.results[:m], exp) and all(np.array_equal(gc[i], ecg[i]) for i in range(m))
+    # the k-mer guided edit pipelines its dense call the same way (from 400k pairs on)
+    n2 = 420000
+    idx = np.arange(n2) % n
+    b2 = synth.PairBatch(b.seqs, b.qoff[idx], b.qlen[idx], b.toff[idx], b.tlen[idx])
+    monkeypatch.setenv("BSB200_NOPIPE", "1")
+    kplain = ctx.kmer_edit_batch(b2, 7, dense=True)
+    monkeypatch.delenv("BSB200_NOPIPE")
+    kpiped = ctx.kmer_edit_batch(b2, 7, dense=True)
+    assert np.array_equal(kpiped.results, kplain.results) and np.array_equal(kpiped.ncigar, kplain.ncigar) and np.array_equal(kpiped.status, kplain.status)
+    tot = int(kplain.ncigar.sum())
+    assert np.array_equal(kpiped.cigar_arena[:tot], kplain.cigar_arena[:tot])
+    exp, ecg, _ = ck.kmer_batch("oracle", sub, 7)
+    gc = kpiped.cigars()
+    assert np.array_equal(kpiped.results[:m], exp) and all(np.array_equal(gc[i], ecg[i]) for i in range(m))
