@@ -630,7 +630,7 @@ def run_workload(ctx, name, w, pairs, args, ncores, rank, world, local_rank, dis
                 stage = {}
             pool_used = []
             timers = {}
-            res = shard.run_sharded_device(hb, kind, w["bandwidth"], al, dist, device=dev, pinned=pinned, nthreads=ncores, timers=timers)
+            res = shard.run_sharded_device(hb, kind, w["bandwidth"], al, dist, device=dev, pinned=pinned, nthreads=ncores, timers=timers, packer=shard.cuda_packer(ctx))
             for k in ("plan", "scatter_issued", "aligned", "gathered", "assembled"):
                 if k in timers:
                     stage[k] = stage.get(k, 0.0) + timers[k] / args.steps

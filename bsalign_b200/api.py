@@ -80,6 +80,7 @@ def lib():
         L.bsb200_pairwise_batch_dense.argtypes = [_P, ctypes.c_int, ctypes.c_uint64, _P, _P, _P, _P, _P, ctypes.c_int, ctypes.c_uint32, _P,
                                                   _I8, _I8, _I8, _I8, _P, _P, ctypes.c_uint64, _P, _P, _P]
         L.bsb200_pairwise_batch_dense_bits.argtypes = L.bsb200_pairwise_batch_dense.argtypes
+        L.bsb200_pack_pairs_dev.argtypes = [_P, _P, _P, _P, _P, _P, _P, ctypes.c_uint64, _P]
         L.bsb200_pairwise_batch_ptrs.argtypes = [_P, ctypes.c_int, ctypes.c_uint64, _P, _P, _P, _P, ctypes.c_int, ctypes.c_uint32, _P,
                                                  _I8, _I8, _I8, _I8, _P, _P, _P, _P, ctypes.c_int]
         L.bsb200_pairwise_batch_multi.argtypes = [_P, ctypes.c_int, ctypes.c_int, ctypes.c_uint64, _P, _P, _P, _P, _P, ctypes.c_int, ctypes.c_uint32, _P,
@@ -291,6 +292,15 @@ def pack_pairs(batch, idx, out_seqs=None, nthreads=8):
     pb = PairBatch.__new__(PairBatch)
     pb.seqs, pb.qoff, pb.qlen, pb.toff, pb.tlen = out_seqs[:max(nbytes, 1)], qoff, np.ascontiguousarray(batch.qlen[i64]), toff, np.ascontiguousarray(batch.tlen[i64])
     return pb, nbytes
+
+
+def pack_pairs_dev(ctx, d_src_ptr, batch, idx, d_dst_ptr):
+    """bsb200_pack_pairs_dev: the batch's whole arena is at device pointer d_src_ptr; the pairs idx (query then target of each pair, in idx order)
+    are gathered into the compact arena at d_dst_ptr by a kernel.  batch.qoff / qlen / toff / tlen are host arrays."""
+    idx = np.ascontiguousarray(idx, dtype=np.uint64)
+    rc = ctx._lib.bsb200_pack_pairs_dev(ctx._h, ctypes.c_void_p(int(d_src_ptr)), _ptr(batch.qoff), _ptr(batch.qlen), _ptr(batch.toff), _ptr(batch.tlen),
+                                        _ptr(idx), len(idx), ctypes.c_void_p(int(d_dst_ptr)))
+    ctx._check(rc, "bsb200_pack_pairs_dev")
 
 
 def pairwise_batch_ptrs(ctx, kind, queries, targets, mode, bandwidth, matrix=None, gaps=(0, 0, 0, 0), nthreads=4):

@@ -1309,6 +1309,50 @@ extern "C" uint64_t bsb200_pack_pairs(const uint8_t *seqs, const uint64_t *qoff,
 	return pos[m];
 }
 
+// The same packing ON THE DEVICE: the caller's arena is already in this device's memory as it is (one large copy instead of a host-side
+// gather); one warp per sequence moves it to its place in the compact arena (query then target of each pair, in idx order).
+__global__ void __launch_bounds__(256) pack_pairs_kernel(const uint8_t *src, uint8_t *dst, const uint64_t *soff, const uint64_t *doff, const uint32_t *len, uint64_t nseg){
+	const uint64_t sgm = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+	if(sgm >= nseg) return;
+	const uint32_t lane = threadIdx.x & 31, n = len[sgm];
+	const uint8_t *s_ = src + soff[sgm]; uint8_t *d_ = dst + doff[sgm];
+	// bytes up to the destination's 16-byte line, then 16 bytes per lane and step when the source is aligned the same way
+	const uint32_t head = (uint32_t)((16 - ((uintptr_t)d_ & 15)) & 15);
+	if((((uintptr_t)s_ ^ (uintptr_t)d_) & 15) == 0 && n >= 64){
+		const uint32_t h = head < n ? head : n;
+		if(lane < h) d_[lane] = s_[lane];
+		const uint32_t body = (n - h) / 16;
+		const uint4 *s4 = (const uint4*)(s_ + h); uint4 *d4 = (uint4*)(d_ + h);
+		for(uint32_t k=lane;k<body;k+=32) d4[k] = s4[k];
+		for(uint32_t k=h+body*16+lane;k<n;k+=32) d_[k] = s_[k];
+	} else for(uint32_t k=lane;k<n;k+=32) d_[k] = s_[k];
+}
+
+extern "C" int bsb200_pack_pairs_dev(bsb200_ctx *ctx, const uint8_t *d_src, const uint64_t *qoff, const uint32_t *qlen, const uint64_t *toff, const uint32_t *tlen,
+		const uint64_t *idx, uint64_t m, uint8_t *d_dst){
+	if(!ctx || (m && (!d_src || !d_dst || !qoff || !qlen || !toff || !tlen || !idx))) return fail(ctx, "bsb200_pack_pairs_dev", cudaSuccess);
+	ctx->err.clear();
+	if(m == 0) return 0;
+	cudaSetDevice(ctx->device);
+	HostBuf &hb = ctx->host_cache[6];
+	DevBuf &db = ctx->kmer_cache[3];
+	const uint64_t nseg = 2 * m;
+	CK(hb.reserve(nseg * 20)); CK(db.reserve(nseg * 20));
+	uint64_t *so = hb.as<uint64_t>(), *dof = so + nseg; uint32_t *ln = (uint32_t*)(dof + nseg);
+	uint64_t pos = 0;
+	for(uint64_t k=0;k<m;k++){
+		const uint64_t i = idx[k];
+		so[2 * k] = qoff[i]; dof[2 * k] = pos; ln[2 * k] = qlen[i]; pos += qlen[i];
+		so[2 * k + 1] = toff[i]; dof[2 * k + 1] = pos; ln[2 * k + 1] = tlen[i]; pos += tlen[i];
+	}
+	CK(cudaMemcpyAsync(db.p, hb.p, nseg * 20, cudaMemcpyHostToDevice, ctx->stream));
+	const uint64_t *dso = db.as<uint64_t>(), *ddo = dso + nseg; const uint32_t *dln = (const uint32_t*)(ddo + nseg);
+	pack_pairs_kernel<<<(unsigned)((nseg * 32 + 255) / 256), 256, 0, ctx->stream>>>(d_src, d_dst, dso, ddo, dln, nseg);
+	CK(cudaGetLastError());
+	CK(cudaStreamSynchronize(ctx->stream));
+	return 0;
+}
+
 // dst[dst_off[k] .. + len[k]) = src[src_off[k] .. + len[k]) for k in [0, m): 32-bit words
 extern "C" void bsb200_scatter_words(uint32_t *dst, const uint64_t *dst_off, const uint32_t *src, const uint64_t *src_off, const uint32_t *len, uint64_t m, int nthreads){
 	if(nthreads < 1) nthreads = 1;

@@ -101,12 +101,24 @@ def cuda_aligner(ctx, kind, mode, bandwidth, mtx=None, gaps=(0, 0, 0, 0)):
     return align
 
 
-def run_sharded_device(batch, kind, bandwidth, align_fn, dist, device="cpu", pinned=None, nthreads=8, timers=None):
+def cuda_packer(ctx):
+    """packer for run_sharded_device on GPUs: rank 0's whole arena goes to its GPU in ONE copy (issued before the plan, so it travels while
+    the lengths are broadcast and the shards planned) and a kernel gathers every shard's compact arena there (bsb200_pack_pairs_dev) -
+    instead of a gather by host threads followed by the same copy."""
+    from . import api
+
+    def pack(d_src_ptr, batch, idx_all, d_dst_ptr):
+        api.pack_pairs_dev(ctx, d_src_ptr, batch, idx_all, d_dst_ptr)
+    return pack
+
+
+def run_sharded_device(batch, kind, bandwidth, align_fn, dist, device="cpu", pinned=None, nthreads=8, timers=None, packer=None):
     """One batch on rank 0 (`batch` is None elsewhere) -> shards of equal DP cells -> every rank aligns its shard on its own device ->
     rank 0 gets (results[n,10] int32, status[n] int32, ncigar[n] uint32, dense pair-ordered cigar words uint32).  Other ranks return None.
 
     Collectives (NCCL over NVLink when device is a cuda device, gloo in the CPU tests): one broadcast of the pair lengths, one send per
-    rank of its compact sequence arena (rank 0 packs it in host memory and moves it to its own GPU first), one all_gather of the cigar
+    rank of its compact sequence arena (rank 0 packs it in host memory and moves it to its own GPU first - or, with `packer`, moves the
+    whole arena and packs on the GPU), one all_gather of the cigar
     word counts, and per rank one send of its fixed-size records and one of its cigar words.  Nothing is exchanged during the DP.
     align_fn(arena tensor on `device`, ShardView) -> (records int32 [n_r, 12] = 10 result ints, status, ncigar; cigar words as int32; timing dict)
     timers: optional dict that receives wall-clock milliseconds of the stages on this rank."""
@@ -121,6 +133,9 @@ def run_sharded_device(batch, kind, bandwidth, align_fn, dist, device="cpu", pin
         if str(device).startswith("cuda"):
             torch.cuda.synchronize()
         lap[name] = (time.perf_counter() - t0) * 1e3
+    src_d = None
+    if rank == 0 and packer is not None and batch.n:
+        src_d = torch.from_numpy(batch.seqs).to(device, non_blocking=True)   # the whole arena starts crossing PCIe now
     # ---- pair lengths to every rank -----------------------------------------------------------------------------------------
     hdr = torch.zeros(1, dtype=torch.int64, device=device)
     if rank == 0:
@@ -148,10 +163,16 @@ def run_sharded_device(batch, kind, bandwidth, align_fn, dist, device="cpu", pin
         # rank 0's GPU, and the shards of the other ranks are sent on from there
         idx_all = np.concatenate([p["idx"] for p in plans]).astype(np.uint64)
         total = int(sum(p["nbytes"] for p in plans))
-        host = pinned(max(total, 1)) if pinned is not None else None
-        pb, nb = api.pack_pairs(batch, idx_all, out_seqs=host, nthreads=nthreads)
-        whole = torch.from_numpy(pb.seqs[:max(nb, 1)]).to(device, non_blocking=True)
-        keep.append((pb, whole))
+        if src_d is not None:
+            whole = torch.empty(max(total, 1), dtype=torch.uint8, device=device)
+            torch.cuda.current_stream().synchronize()
+            packer(src_d.data_ptr(), batch, idx_all, whole.data_ptr())
+            keep.append((src_d, whole))
+        else:
+            host = pinned(max(total, 1)) if pinned is not None else None
+            pb, nb = api.pack_pairs(batch, idx_all, out_seqs=host, nthreads=nthreads)
+            whole = torch.from_numpy(pb.seqs[:max(nb, 1)]).to(device, non_blocking=True)
+            keep.append((pb, whole))
         off = 0
         for r in range(world):
             nbr = plans[r]["nbytes"]

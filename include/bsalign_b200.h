@@ -185,6 +185,10 @@ int bsb200_batch_fetch_dense_dev(bsb200_ctx *ctx, bsb200_batch *b, int32_t *d_re
  * out_toff; out_seqs NULL: only size it), and the pair-ordered merge of the shards' dense cigars */
 uint64_t bsb200_pack_pairs(const uint8_t *seqs, const uint64_t *qoff, const uint32_t *qlen, const uint64_t *toff, const uint32_t *tlen,
 		const uint64_t *idx, uint64_t m, uint8_t *out_seqs, uint64_t *out_qoff, uint64_t *out_toff, int nthreads);
+/* the same packing on the device: d_src is the caller's whole arena in this device's memory, d_dst receives the compact arena
+ * (bsb200_pack_pairs with out_seqs == NULL sizes it); all other pointers are host arrays */
+int bsb200_pack_pairs_dev(bsb200_ctx *ctx, const uint8_t *d_src, const uint64_t *qoff, const uint32_t *qlen, const uint64_t *toff, const uint32_t *tlen,
+		const uint64_t *idx, uint64_t m, uint8_t *d_dst);
 void bsb200_scatter_words(uint32_t *dst, const uint64_t *dst_off, const uint32_t *src, const uint64_t *src_off, const uint32_t *len, uint64_t m, int nthreads);
 
 /* ---- ingest / egress next to the path (host code): sequence files into BaseBank words, and the command line's text ------------------ */

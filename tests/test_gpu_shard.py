@@ -28,7 +28,9 @@ def _worker(rank, world, port, q):
     for kind, mode, bw, n, qlen in (("epi8", 0, 0, 301, 400), ("epi8", 1, 128, 200, 700), ("edit", 0, 64, 500, 300)):
         batch = synth.make_pairs(n, qlen, seed=n) if rank == 0 else None
         timers = {}
-        out = shard.run_sharded_device(batch, kind, bw, shard.cuda_aligner(ctx, kind, mode, bw, mtx, (-3, -2, 0, 0)), dist, device=dev, nthreads=4, timers=timers)
+        # (the edit case packs the shards on the GPU: bsb200_pack_pairs_dev; the others by host threads)
+        out = shard.run_sharded_device(batch, kind, bw, shard.cuda_aligner(ctx, kind, mode, bw, mtx, (-3, -2, 0, 0)), dist, device=dev, nthreads=4, timers=timers,
+                                       packer=shard.cuda_packer(ctx) if (kind == "edit" or mode == 1) else None)
         if rank == 0:
             res, st, ncg, dense, goff = out
             exp, ecg, _ = ck.oracle_batch(kind, batch, mode, bw, mtx, (-3, -2, 0, 0), nthreads=8)
