@@ -1547,9 +1547,20 @@ static int dense_pipelined(bsb200_ctx *ctx, int kind, uint64_t n, const uint8_t 
 	return 0;
 }
 
-static bool pipeline_pays(int kind, uint64_t n){
-	if(getenv("BSB200_NOPIPE")) return false;
-	return kind == 1 && n >= 262144;
+// Large edit batches of SHORT pairs: the two contexts each hold the traceback store of a chunk, so the whole batch's store must be a small
+// part of the device (long pairs go through the plain path, whose waves are planned against all of the free memory).
+static bool pipeline_pays(const bsb200_ctx *ctx, int kind, uint64_t n, const uint32_t *qlen, const uint32_t *tlen, int mode, uint32_t bandwidth){
+	if(getenv("BSB200_NOPIPE") || kind != 1 || n < 262144 || !qlen || !tlen) return false;
+	const int NT = plan_threads(n);
+	std::vector<uint64_t> part(NT, 0);
+	par_slices(n, NT, [&](int w, uint64_t lo, uint64_t hi){
+		uint64_t b = 0;
+		for(uint64_t i=lo;i<hi;i++) if(qlen[i] && tlen[i]) b += edit_trace_bytes(edit_bandwidth(qlen[i], tlen[i], mode & 3, bandwidth), tlen[i]);
+		part[w] = b;
+	});
+	uint64_t total = 0;
+	for(uint64_t b : part) total += b;
+	return total <= ctx->total_mem / 4;
 }
 
 extern "C" int bsb200_pairwise_batch_dense(bsb200_ctx *ctx, int kind, uint64_t n, const uint8_t *seqs,
@@ -1557,7 +1568,7 @@ extern "C" int bsb200_pairwise_batch_dense(bsb200_ctx *ctx, int kind, uint64_t n
 		int mode, uint32_t bandwidth, const int8_t matrix[16], int8_t go1, int8_t ge1, int8_t go2, int8_t ge2,
 		bsb200_result_t *results, uint32_t *cigars, uint64_t cigar_cap_words, uint64_t *total_words, uint32_t *ncigar, int32_t *status){
 	if(!ctx) return -1;
-	if(pipeline_pays(kind, n) && seqs && qoff && qlen && toff && tlen && results)
+	if(seqs && qoff && toff && results && pipeline_pays(ctx, kind, n, qlen, tlen, mode, bandwidth))
 		return dense_pipelined(ctx, kind, n, seqs, nullptr, qoff, qlen, toff, tlen, mode, bandwidth, matrix, go1, ge1, go2, ge2, results, cigars, cigar_cap_words, total_words, ncigar, status, 0);
 	bsb200_batch *b = bsb200_batch_upload(ctx, kind, n, seqs, qoff, qlen, toff, tlen, mode, bandwidth, matrix, go1, ge1, go2, ge2, cigars != nullptr);
 	if(!b) return -1;
@@ -1576,7 +1587,7 @@ extern "C" int bsb200_pairwise_batch_dense_bits(bsb200_ctx *ctx, int kind, uint6
 		int mode, uint32_t bandwidth, const int8_t matrix[16], int8_t go1, int8_t ge1, int8_t go2, int8_t ge2,
 		bsb200_result_t *results, uint32_t *cigars, uint64_t cigar_cap_words, uint64_t *total_words, uint32_t *ncigar, int32_t *status){
 	if(!ctx) return -1;
-	if(pipeline_pays(kind, n) && bits && qoff && qlen && toff && tlen && results)
+	if(bits && qoff && toff && results && pipeline_pays(ctx, kind, n, qlen, tlen, mode, bandwidth))
 		return dense_pipelined(ctx, kind, n, nullptr, bits, qoff, qlen, toff, tlen, mode, bandwidth, matrix, go1, ge1, go2, ge2, results, cigars, cigar_cap_words, total_words, ncigar, status, 0);
 	bsb200_batch *b = bsb200_batch_upload_bits(ctx, kind, n, bits, qoff, qlen, toff, tlen, mode, bandwidth, matrix, go1, ge1, go2, ge2, cigars != nullptr);
 	if(!b) return -1;
