@@ -1133,8 +1133,11 @@ static int kmer_edit_impl(bsb200_ctx *ctx, uint64_t n, const uint8_t *seqs, cons
 	size_t freeb = 0, totalb = 0;
 	CKK(cudaMemGetInfo(&freeb, &totalb));
 	freeb += ctx->kmer_cache[0].cap + ctx->kmer_cache[1].cap;
+	// hash-table keys of short pairs in shared memory: up to 2048 entries per warp (32 KB per CTA) keep seven of the eight CTAs of an SM resident
+	uint64_t Hmax = 64; while(2 * Hmax < 3 * ((uint64_t)maxq + maxt)) Hmax <<= 1;
+	const uint32_t smem_keys = (Hmax <= 2048 && !getenv("BSB200_KMER_NOSMEM")) ? (uint32_t)Hmax : 0;
 	int occ = 0;
-	CKK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kmer_edit_kernel, kKmWarps * 32, 0));
+	CKK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kmer_edit_kernel, kKmWarps * 32, (size_t)smem_keys * 4 * kKmWarps));
 	if(occ < 1) occ = 1;
 	const uint64_t max_warps = std::max<uint64_t>(kKmWarps, (uint64_t)ctx->num_sms * occ * kKmWarps / (share > 1 ? share : 1));   // share: calls running side by side on this device
 	// pairs a warp works on at a time: as many as leave every warp of the GPU at least two groups (a group's serial phases use one lane per pair)
@@ -1156,6 +1159,7 @@ static int kmer_edit_impl(bsb200_ctx *ctx, uint64_t n, const uint8_t *seqs, cons
 	a.seqs = b->d_seqs.as<uint8_t>(); a.qoff = b->d_qoff.as<uint64_t>(); a.toff = b->d_toff.as<uint64_t>();
 	a.qlen = b->d_qlen.as<uint32_t>(); a.tlen = b->d_tlen.as<uint32_t>();
 	a.ksz = ksz;
+	a.smem_keys = smem_keys;
 	a.next = ctx->kmer_cache[2].as<unsigned int>();
 	a.pool_used = (unsigned long long*)((uint8_t*)ctx->kmer_cache[2].p + 16);
 	a.scratch = ctx->kmer_cache[0].as<uint8_t>();
@@ -1184,7 +1188,7 @@ static int kmer_edit_impl(bsb200_ctx *ctx, uint64_t n, const uint8_t *seqs, cons
 			if(single) a.group = 1;
 			CKK(cudaMemsetAsync(ctx->kmer_cache[2].p, 0, 32, st));
 			const uint64_t warps = round == 0 ? slots : std::min<uint64_t>(slots, 2 * kKmWarps);
-			kmer_edit_kernel<<<single ? 1u : (unsigned)((warps + kKmWarps - 1) / kKmWarps), single ? 32 : kKmWarps * 32, 0, st>>>(a);
+			kmer_edit_kernel<<<single ? 1u : (unsigned)((warps + kKmWarps - 1) / kKmWarps), single ? 32 : kKmWarps * 32, (size_t)a.smem_keys * 4 * kKmWarps, st>>>(a);
 			CKK(cudaGetLastError());
 			launches++;
 		}

@@ -37,6 +37,7 @@ struct KmerArgs {
 	const uint32_t *order;           // pairs of this launch (nullptr: 0 .. npairs-1)
 	uint32_t npairs, ksz;
 	uint32_t group;                  // pairs a warp works on at a time (1..32)
+	uint32_t smem_keys;              // hash-table keys per warp kept in shared memory (0: the keys live in the warp's slot)
 	unsigned int *next;              // pair counter
 	uint8_t *scratch; uint64_t warp_bytes;
 	uint64_t off_kq, off_lane, off_glist, off_gmeta, off_pairs, pair_bytes;        // a warp's slot: hash table, query k-mers, lane scratch, gap work list, then `group` pair blocks
@@ -267,12 +268,16 @@ __device__ inline int km_hits(const KmerArgs &a, const uint32_t pair, uint8_t *w
 	const uint32_t H = 1u << hbits, hm = H - 1;
 	// table: keys[H] (all ones = empty), then per sequence one 64-bit word per slot: occurrences << 32 | sum of (offset << 1 | strand).
 	// Only the key needs an atomic with a result (probing); the occurrence words are fire-and-forget adds.
-	uint32_t *keys = (uint32_t*)ws;
-	unsigned long long *qv = (unsigned long long*)(keys + H), *tv = qv + H;
+	// The keys of short pairs sit in SHARED memory (a.smem_keys entries per warp: the key atomics and the probe loads are the
+	// dependent accesses of this phase); the occurrence words stay in the warp's slot.
+	extern __shared__ uint32_t km_smem[];
+	uint32_t *keys = a.smem_keys ? km_smem + (size_t)(threadIdx.x >> 5) * a.smem_keys : (uint32_t*)ws;
+	unsigned long long *qv = (unsigned long long*)((uint32_t*)ws + H), *tv = qv + H;
 	{
-		uint4 *z = (uint4*)ws; const uint4 f = make_uint4(kKmNone, kKmNone, kKmNone, kKmNone), o = make_uint4(0, 0, 0, 0);
-		for(uint32_t i=lane;i<H/4;i+=32) z[i] = f;
-		for(uint32_t i=H/4+lane;i<5*(H/4);i+=32) z[i] = o;
+		const uint4 f = make_uint4(kKmNone, kKmNone, kKmNone, kKmNone), o = make_uint4(0, 0, 0, 0);
+		uint4 *zk = (uint4*)keys, *zv = (uint4*)qv;
+		for(uint32_t i=lane;i<H/4;i+=32) zk[i] = f;
+		for(uint32_t i=lane;i<H;i+=32) zv[i] = o;
 	}
 	__syncwarp();
 	// every lane rolls over its own stretch of k-mer positions of BOTH sequences (one byte per position and sequence; the two key
