@@ -583,13 +583,14 @@ def run_workload(ctx, name, w, pairs, args, ncores, rank, world, local_rank, dis
             e2e_extra["device_parts_note"] = "sums over the chunks; copies, kernels and host planning of different chunks overlap, so the wall time is shorter than the sum"
         # the same call with PAGEABLE caller buffers (what a reference caller holds: plain u1i* arrays)
         pout = api._alloc_out(batch, True)
-        t0 = time.perf_counter()
-        if kind == "epi8":
-            ctx.epi8_batch(batch, w["mode"], w["bandwidth"], mtx, *GAPS, out=pout, dense=True)
-        else:
-            ctx.edit_batch(batch, w["mode"], w["bandwidth"], out=pout, dense=True)
-        torch.cuda.synchronize()
-        pg_ms = (time.perf_counter() - t0) * 1e3
+        for it in range(2):   # one warm-up call (the library allocates its pinned staging buffers on first use), one timed
+            t0 = time.perf_counter()
+            if kind == "epi8":
+                ctx.epi8_batch(batch, w["mode"], w["bandwidth"], mtx, *GAPS, out=pout, dense=True)
+            else:
+                ctx.edit_batch(batch, w["mode"], w["bandwidth"], out=pout, dense=True)
+            torch.cuda.synchronize()
+            pg_ms = (time.perf_counter() - t0) * 1e3
         e2e_extra["pageable"] = {"value": total_cells / (pg_ms * 1e-3) / 1e9, "ms_per_step": pg_ms}
         # ... and with the sequences 2-bit packed the way the reference keeps them (BaseBank words, dna.h:63; main.c unpacks a pair per call):
         # one call of bsb200_pairwise_batch_dense_bits, packed words in pinned memory

@@ -84,6 +84,7 @@ struct bsb200_ctx {
 	DevBuf dev_cache[18];
 	HostBuf host_cache[8];
 	DevBuf poa_cache[40];   // same, for POA sweep batches (poa_host.cuh)
+	HostBuf stage[2]; cudaEvent_t stage_ev[2] = {nullptr, nullptr};   // pinned staging for large copies from / to pageable caller memory
 	bsb200_ctx *helper = nullptr;   // second context on the same device: the one-call entry points pipeline large edit batches over both
 	DevBuf kmer_cache[8];   // k-mer guided edit: warp slots, gap-trace pool, counters, order list, fallback sub-batch results
 	HostBuf poa_hcache[2];
@@ -146,6 +147,7 @@ extern "C" bsb200_ctx *bsb200_create(int device, uint64_t trace_budget_bytes){
 	cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking);
 	{ int lo = 0, hi = 0; cudaDeviceGetStreamPriorityRange(&lo, &hi); cudaStreamCreateWithPriority(&ctx->stream_bt, cudaStreamNonBlocking, hi); }
 	for(auto &e : ctx->ev) cudaEventCreate(&e);
+	for(auto &e : ctx->stage_ev) cudaEventCreateWithFlags(&e, cudaEventDisableTiming);
 	ctx->trace_budget = trace_budget_bytes;
 	return ctx;
 }
@@ -162,6 +164,8 @@ extern "C" void bsb200_destroy(bsb200_ctx *ctx){
 	for(auto &d : ctx->kmer_cache) d.release();
 	for(auto &h : ctx->poa_hcache) h.release();
 	for(auto &e : ctx->ev) cudaEventDestroy(e);
+	for(auto &e : ctx->stage_ev) if(e) cudaEventDestroy(e);
+	for(auto &h : ctx->stage) h.release();
 	cudaStreamDestroy(ctx->stream);
 	cudaStreamDestroy(ctx->stream_bt);
 	delete ctx;
@@ -179,6 +183,7 @@ extern "C" void bsb200_trim(bsb200_ctx *ctx){
 	for(auto &d : ctx->poa_cache) d.release();
 	for(auto &d : ctx->kmer_cache) d.release();
 	for(auto &h : ctx->poa_hcache) h.release();
+	for(auto &h : ctx->stage) h.release();
 	ctx->auto_budget = 0;
 }
 
@@ -242,6 +247,60 @@ __global__ void __launch_bounds__(256) unpack_bits_kernel(const uint64_t *bits, 
 }
 
 // shared memory of one pair's group in the wavefront kernel: u, e and selector images + the scratch words of its stages
+// ---- large copies between PAGEABLE caller memory and the device ----------------------------------------------------------------------
+// cudaMemcpyAsync on pageable memory is staged by the driver on one thread (~8 GB/s here).  A reference caller holds plain malloc'ed
+// arrays, so large copies are staged by us: host threads copy 32 MB pieces into / out of two pinned buffers while the DMA engine moves
+// the other one.  Pinned or registered caller memory (and small copies) go straight to cudaMemcpyAsync.
+static bool is_pageable(const void *p){
+	cudaPointerAttributes at;
+	if(cudaPointerGetAttributes(&at, p) != cudaSuccess){ cudaGetLastError(); return true; }
+	return at.type == cudaMemoryTypeUnregistered;
+}
+constexpr size_t kStageChunk = 32ull << 20;
+static void par_memcpy(void *dst, const void *src, size_t bytes){
+	const int NT = bytes >= (8u << 20) ? 8 : 1;
+	par_slices((bytes + 4095) / 4096, NT, [&](int, uint64_t lo, uint64_t hi){
+		const size_t b0 = lo * 4096, b1 = std::min<size_t>(bytes, hi * 4096);
+		if(b1 > b0) memcpy((uint8_t*)dst + b0, (const uint8_t*)src + b0, b1 - b0);
+	});
+}
+static cudaError_t h2d_copy(bsb200_ctx *ctx, void *dst, const void *src, size_t bytes, cudaStream_t st){
+	if(bytes < (4u << 20) || getenv("BSB200_NOSTAGE") || !is_pageable(src)) return cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, st);
+	cudaError_t e = cudaSuccess;
+	for(int k=0;k<2;k++) if((e = ctx->stage[k].reserve(kStageChunk)) != cudaSuccess) return e;
+	int k = 0;
+	for(size_t off=0;off<bytes;off+=kStageChunk,k^=1){
+		const size_t len = std::min(kStageChunk, bytes - off);
+		if(off >= 2 * kStageChunk && (e = cudaEventSynchronize(ctx->stage_ev[k])) != cudaSuccess) return e;   // the DMA that last read this buffer
+		par_memcpy(ctx->stage[k].p, (const uint8_t*)src + off, len);
+		if((e = cudaMemcpyAsync((uint8_t*)dst + off, ctx->stage[k].p, len, cudaMemcpyHostToDevice, st)) != cudaSuccess) return e;
+		cudaEventRecord(ctx->stage_ev[k], st);
+	}
+	// the staging buffers are reused by the next call: wait until the engine has read them
+	for(int j=0;j<2;j++) if((e = cudaEventSynchronize(ctx->stage_ev[j])) != cudaSuccess) return e;
+	return cudaSuccess;
+}
+// device -> pageable host; returns when the data is in dst (the stream is synchronised up to the copy)
+static cudaError_t d2h_copy(bsb200_ctx *ctx, void *dst, const void *src, size_t bytes, cudaStream_t st){
+	if(bytes < (4u << 20) || getenv("BSB200_NOSTAGE") || !is_pageable(dst)) return cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, st);
+	cudaError_t e = cudaSuccess;
+	for(int k=0;k<2;k++) if((e = ctx->stage[k].reserve(kStageChunk)) != cudaSuccess) return e;
+	const size_t nchunk = (bytes + kStageChunk - 1) / kStageChunk;
+	for(size_t c=0;c<=nchunk;c++){
+		if(c < nchunk){
+			const size_t off = c * kStageChunk, len = std::min(kStageChunk, bytes - off);
+			if((e = cudaMemcpyAsync(ctx->stage[c & 1].p, (const uint8_t*)src + off, len, cudaMemcpyDeviceToHost, st)) != cudaSuccess) return e;
+			cudaEventRecord(ctx->stage_ev[c & 1], st);
+		}
+		if(c > 0){   // while chunk c is on the link, host threads move chunk c - 1 to its place
+			const size_t off = (c - 1) * kStageChunk, len = std::min(kStageChunk, bytes - off);
+			if((e = cudaEventSynchronize(ctx->stage_ev[(c - 1) & 1])) != cudaSuccess) return e;
+			par_memcpy((uint8_t*)dst + off, ctx->stage[(c - 1) & 1].p, len);
+		}
+	}
+	return cudaSuccess;
+}
+
 static size_t wave_group_smem(uint32_t max_bw, int split){
 	const size_t img = epi8_image_bytes(max_bw / 16);
 	const size_t scratch = std::max<size_t>(320, (size_t)(2 + 2 * kLanes * split) * 4);
@@ -351,19 +410,19 @@ static bsb200_batch *upload_impl(bsb200_ctx *ctx, int kind, uint64_t n, const ui
 					if(segs){
 						R(cudaMemcpyAsync(b->d_bits.p, bits64, (segs->len0 + 31) / 32 * 8, cudaMemcpyHostToDevice, st));
 						R(cudaMemcpyAsync(b->d_bits.as<uint64_t>() + segs->at1 / 32, bits64 + segs->src1 / 32, (segs->len1 + 31) / 32 * 8, cudaMemcpyHostToDevice, st));
-					} else R(cudaMemcpyAsync(b->d_bits.p, bits64, nw * 8, cudaMemcpyHostToDevice, st));
+					} else R(h2d_copy(ctx, b->d_bits.p, bits64, nw * 8, st));
 					unpack_bits_kernel<<<(unsigned)((nw + 255) / 256), 256, 0, st>>>(b->d_bits.as<uint64_t>(), b->d_seqs.as<uint8_t>(), nw, seq_end);
 				}
 			} else if(!d_seqs_ext){
 				if(segs){
-					R(cudaMemcpyAsync(b->d_seqs.p, seqs, segs->len0, cudaMemcpyHostToDevice, st));
-					R(cudaMemcpyAsync(b->d_seqs.as<uint8_t>() + segs->at1, seqs + segs->src1, segs->len1, cudaMemcpyHostToDevice, st));
-				} else R(cudaMemcpyAsync(b->d_seqs.p, seqs, seq_end, cudaMemcpyHostToDevice, st));
+					R(h2d_copy(ctx, b->d_seqs.p, seqs, segs->len0, st));
+					R(h2d_copy(ctx, b->d_seqs.as<uint8_t>() + segs->at1, seqs + segs->src1, segs->len1, st));
+				} else R(h2d_copy(ctx, b->d_seqs.p, seqs, seq_end, st));
 			}
-			R(cudaMemcpyAsync(b->d_qoff.p, qoff, n * 8, cudaMemcpyHostToDevice, st));
-			R(cudaMemcpyAsync(b->d_toff.p, toff, n * 8, cudaMemcpyHostToDevice, st));
-			R(cudaMemcpyAsync(b->d_qlen.p, qlen, n * 4, cudaMemcpyHostToDevice, st));
-			R(cudaMemcpyAsync(b->d_tlen.p, tlen, n * 4, cudaMemcpyHostToDevice, st));
+			R(h2d_copy(ctx, b->d_qoff.p, qoff, n * 8, st));
+			R(h2d_copy(ctx, b->d_toff.p, toff, n * 8, st));
+			R(h2d_copy(ctx, b->d_qlen.p, qlen, n * 4, st));
+			R(h2d_copy(ctx, b->d_tlen.p, tlen, n * 4, st));
 		}
 	};
 	if(early) copy_inputs();
@@ -948,7 +1007,7 @@ static int fetch_impl(bsb200_ctx *ctx, bsb200_batch *b, bsb200_result_t *results
 	if(total_out) *total_out = 0;
 	CK(b->h_results.reserve(n * 40)); CK(b->h_status.reserve(n * 4)); CK(b->h_ncigar.reserve(n * 4)); CK(b->h_total.reserve(16));
 	cudaEventRecord(ctx->ev[2], st);
-	CK(cudaMemcpyAsync(results ? (void*)results : b->h_results.p, b->d_results.p, n * 40, cudaMemcpyDeviceToHost, st));
+	CK(d2h_copy(ctx, results ? (void*)results : b->h_results.p, b->d_results.p, n * 40, st));
 	CK(cudaMemcpyAsync(b->h_status.p, b->d_status.p, n * 4, cudaMemcpyDeviceToHost, st));
 	CK(cudaMemcpyAsync(b->h_ncigar.p, b->d_ncigar.p, n * 4, cudaMemcpyDeviceToHost, st));
 	uint64_t d2h = n * 48;
@@ -981,7 +1040,7 @@ static int fetch_impl(bsb200_ctx *ctx, bsb200_batch *b, bsb200_result_t *results
 			cigar_order_kernel<<<(unsigned)((n * 32 + 255) / 256), 256, 0, st>>>(b->d_cig_dense.as<uint32_t>(), b->d_dense_off.as<uint64_t>(),
 				b->d_ncigar.as<uint32_t>(), b->d_prefix.as<uint64_t>(), ordered, n);
 			CK(cudaGetLastError());
-			CK(cudaMemcpyAsync(cigars, ordered, total * 4, cudaMemcpyDeviceToHost, st));
+			CK(d2h_copy(ctx, cigars, ordered, total * 4, st));
 		}
 		d2h += 8 + total * 4;
 	}
@@ -1119,9 +1178,9 @@ static int kmer_edit_impl(bsb200_ctx *ctx, uint64_t n, const uint8_t *seqs, cons
 	lap("output buffers + events");
 	cudaEventRecord(ctx->ev[0], st);
 	if(segs){
-		CKK(cudaMemcpyAsync(b->d_seqs.p, seqs, segs->len0, cudaMemcpyHostToDevice, st));
-		CKK(cudaMemcpyAsync(b->d_seqs.as<uint8_t>() + segs->at1, seqs + segs->src1, segs->len1, cudaMemcpyHostToDevice, st));
-	} else CKK(cudaMemcpyAsync(b->d_seqs.p, seqs, seq_end, cudaMemcpyHostToDevice, st));
+		CKK(h2d_copy(ctx, b->d_seqs.p, seqs, segs->len0, st));
+		CKK(h2d_copy(ctx, b->d_seqs.as<uint8_t>() + segs->at1, seqs + segs->src1, segs->len1, st));
+	} else CKK(h2d_copy(ctx, b->d_seqs.p, seqs, seq_end, st));
 	CKK(cudaMemcpyAsync(b->d_qoff.p, qoff, n * 8, cudaMemcpyHostToDevice, st));
 	CKK(cudaMemcpyAsync(b->d_toff.p, toff, n * 8, cudaMemcpyHostToDevice, st));
 	CKK(cudaMemcpyAsync(b->d_qlen.p, qlen, n * 4, cudaMemcpyHostToDevice, st));
