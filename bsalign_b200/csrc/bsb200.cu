@@ -100,7 +100,9 @@ struct bsb200_batch {
 	int pw = 0; int want_cigar = 1;
 	uint32_t max_bw = 16, max_q64 = 64, max_qlen = 0;
 	int wave_split = 0;   // > 0: the batch takes the wavefront forward kernel with that many sub-blocks per lane (epi8_wave.cuh)
-	std::vector<uint8_t> empty;
+	std::vector<uint8_t> empty;          // 1: qlen or tlen 0; 2: edit pair too long for edit_kernel (long_pairs); 3: such a pair with a moving band (unsupported)
+	std::vector<uint32_t> long_pairs;    // edit pairs that take edit_long_kernel, and their scratch offsets
+	std::vector<uint64_t> long_off; uint64_t long_bytes = 0;
 	uint64_t cells = 0, trace_bytes = 0, cig_words = 0, max_wave_bytes = 0;
 	std::vector<Wave> waves;
 	std::vector<uint32_t> order;
@@ -445,7 +447,7 @@ static bsb200_batch *upload_impl(bsb200_ctx *ctx, int kind, uint64_t n, const ui
 	}
 	b->empty.assign(n, 0);
 	{
-		struct Part { uint64_t cells = 0, trace = 0, nact = 0; uint32_t max_q64 = 0, max_bw = 0, max_qlen = 0; };
+		struct Part { uint64_t cells = 0, trace = 0, nact = 0, nlong = 0; uint32_t max_q64 = 0, max_bw = 0, max_qlen = 0; };
 		std::vector<Part> part(NT);
 		par_slices(n, NT, [&](int w, uint64_t lo, uint64_t hi){
 			Part p;
@@ -462,6 +464,10 @@ static bsb200_batch *upload_impl(bsb200_ctx *ctx, int kind, uint64_t n, const ui
 					work[i] = (uint64_t)bw * tlen[i];
 				} else {
 					bw = edit_bandwidth(qlen[i], tlen[i], mode, bandwidth);
+					{   // beyond edit_kernel: a band over 16384 cells, or query bit-planes that outgrow shared memory even for one warp per CTA
+						const uint32_t q64 = (qlen[i] + 63) / 64 * 64;
+						if(bw > 16384 || (uint64_t)(q64 / 64 + 2) * 16 * 32 > ctx->smem_optin){ b->empty[i] = bw == q64 ? 2 : 3; p.nlong++; continue; }
+					}
 					p.cells += (uint64_t)bw * tlen[i];
 					p.trace += ((uint64_t)bw / 4 + 4) * tlen[i];
 					p.max_q64 = std::max<uint32_t>(p.max_q64, (qlen[i] + 63) / 64 * 64);
@@ -472,7 +478,14 @@ static bsb200_batch *upload_impl(bsb200_ctx *ctx, int kind, uint64_t n, const ui
 			}
 			part[w] = p;
 		});
-		uint64_t nact_ = 0;
+		uint64_t nact_ = 0, nlong_ = 0;
+		for(auto &p : part) nlong_ += p.nlong;
+		if(nlong_) for(uint64_t i=0;i<n;i++) if(b->empty[i] == 2){   // scratch of edit_long_kernel: query planes + 2 planes x (tlen + 1) rows
+			b->long_pairs.push_back((uint32_t)i); b->long_off.push_back(b->long_bytes);
+			const uint64_t W = ((uint64_t)qlen[i] + 63) / 64;
+			b->long_bytes += (16 * W * ((uint64_t)tlen[i] + 2) + 127) / 128 * 128;
+			b->cells += W * 64 * tlen[i];
+		}
 		for(auto &p : part){
 			b->cells += p.cells; b->trace_bytes += p.trace; nact_ += p.nact;
 			b->max_q64 = std::max(b->max_q64, p.max_q64); b->max_bw = std::max(b->max_bw, p.max_bw); b->max_qlen = std::max(b->max_qlen, p.max_qlen);
@@ -839,7 +852,7 @@ extern "C" int bsb200_batch_run(bsb200_ctx *ctx, bsb200_batch *b){
 		cudaEvent_t &operator[](size_t i){ return v[i]; }
 	} evs;
 	evs.st = st;
-	if(b->n == 0 || b->waves.empty()){ if(b->n){ cudaMemsetAsync(b->d_results.p, 0, b->n * 40, st); cudaMemsetAsync(b->d_status.p, 0, b->n * 4, st); cudaMemsetAsync(b->d_ncigar.p, 0, b->n * 4, st); cudaMemsetAsync(b->d_dense_off.p, 0, b->n * 8, st); cudaMemsetAsync(b->d_dense_total.p, 0, 16, st); cudaStreamSynchronize(st);} b->ran = true; return 0; }
+	if(b->n == 0 || (b->waves.empty() && b->long_pairs.empty())){ if(b->n){ cudaMemsetAsync(b->d_results.p, 0, b->n * 40, st); cudaMemsetAsync(b->d_status.p, 0, b->n * 4, st); cudaMemsetAsync(b->d_ncigar.p, 0, b->n * 4, st); cudaMemsetAsync(b->d_dense_off.p, 0, b->n * 8, st); cudaMemsetAsync(b->d_dense_total.p, 0, 16, st); cudaStreamSynchronize(st);} b->ran = true; return 0; }
 	CK(cudaEventRecord(ctx->ev[4], st));
 	CK(cudaMemsetAsync(b->d_results.p, 0, b->n * 40, st));
 	CK(cudaMemsetAsync(b->d_status.p, 0, b->n * 4, st));
@@ -948,6 +961,37 @@ extern "C" int bsb200_batch_run(bsb200_ctx *ctx, bsb200_batch *b){
 			CK(cudaEventRecord(evs[wi * 4 + 3], st));
 		}
 	}
+	if(!b->long_pairs.empty()){
+		// edit pairs beyond edit_kernel's limits: one thread per pair on scratch in HBM (edit_long_kernel), as many pairs at a time as 16 GB hold
+		const uint64_t cap = 16ull << 30;
+		DevBuf &scr = ctx->kmer_cache[1], &ids = ctx->kmer_cache[3], &offs = ctx->kmer_cache[4];
+		for(size_t k0=0;k0<b->long_pairs.size();){
+			size_t k1 = k0 + 1;
+			const uint64_t base = b->long_off[k0];
+			auto end_of = [&](size_t k){ return k + 1 < b->long_pairs.size() ? b->long_off[k + 1] : b->long_bytes; };
+			while(k1 < b->long_pairs.size() && end_of(k1) - base <= cap) k1++;
+			const uint64_t bytes = end_of(k1 - 1) - base;
+			const size_t m = k1 - k0;
+			if(scr.reserve(bytes + 256, true) != cudaSuccess){ cudaGetLastError(); ctx->err = "edit: not enough device memory for the trace of a pair longer than the kernel's band limit"; return -1; }
+			CK(ids.reserve(m * 4 + 16)); CK(offs.reserve(m * 8 + 16));
+			std::vector<uint64_t> rel(m);
+			for(size_t k=0;k<m;k++) rel[k] = b->long_off[k0 + k] - base;
+			CK(cudaMemcpyAsync(ids.p, b->long_pairs.data() + k0, m * 4, cudaMemcpyHostToDevice, st));
+			CK(cudaMemcpyAsync(offs.p, rel.data(), m * 8, cudaMemcpyHostToDevice, st));
+			EditLongArgs a;
+			a.seqs = b->seqs_dev(); a.qoff = b->d_qoff.as<uint64_t>(); a.toff = b->d_toff.as<uint64_t>(); a.qlen = b->d_qlen.as<uint32_t>(); a.tlen = b->d_tlen.as<uint32_t>();
+			a.pairs = ids.as<uint32_t>(); a.scr_off = offs.as<uint64_t>(); a.npairs = (uint32_t)m; a.scratch = scr.as<uint8_t>(); a.mode = b->mode;
+			a.results = b->d_results.as<int32_t>(); a.status = b->d_status.as<int32_t>();
+			a.cigars = b->want_cigar ? b->d_cig_raw.as<uint32_t>() : nullptr; a.cig_off = b->d_cig_off.as<uint64_t>();
+			a.dense = b->want_cigar ? b->d_cig_dense.as<uint32_t>() : nullptr; a.dense_off = b->d_dense_off.as<uint64_t>();
+			a.dense_total = b->d_dense_total.as<unsigned long long>(); a.ncigar = b->d_ncigar.as<uint32_t>();
+			edit_long_kernel<<<(unsigned)m, 32, 0, st>>>(a);
+			CK(cudaGetLastError());
+			CK(cudaStreamSynchronize(st));   // rel is a local
+			ctx->timing.other_launches++;
+			k0 = k1;
+		}
+	}
 	CK(cudaEventRecord(ctx->ev[5], st));
 	CK(cudaStreamSynchronize(st));
 	{ float rm = 0; cudaEventElapsedTime(&rm, ctx->ev[4], ctx->ev[5]); ctx->timing.run_ms = rm; }
@@ -958,7 +1002,7 @@ extern "C" int bsb200_batch_run(bsb200_ctx *ctx, bsb200_batch *b){
 		fwd_ms += m1; bt_ms += m2;
 	}
 	ctx->timing.forward_ms = fwd_ms; ctx->timing.traceback_ms = bt_ms;
-	ctx->timing.other_launches = 5 + (uint32_t)b->waves.size();
+	ctx->timing.other_launches += 5 + (uint32_t)b->waves.size();
 	b->ran = true;
 	return 0;
 }
@@ -1048,7 +1092,7 @@ static int fetch_impl(bsb200_ctx *ctx, bsb200_batch *b, bsb200_result_t *results
 	CK(cudaStreamSynchronize(st));
 	float ms = 0; cudaEventElapsedTime(&ms, ctx->ev[2], ctx->ev[3]);
 	ctx->timing.d2h_ms = ms; ctx->timing.d2h_bytes = d2h;
-	{ int32_t *hs0 = b->h_status.as<int32_t>(); for(uint64_t i=0;i<n;i++) if(b->empty[i]) hs0[i] |= BSB200_ST_EMPTY; }
+	{ int32_t *hs0 = b->h_status.as<int32_t>(); for(uint64_t i=0;i<n;i++) if(b->empty[i] == 1) hs0[i] |= BSB200_ST_EMPTY; else if(b->empty[i] == 3) hs0[i] |= BSB200_ST_UNSUPPORTED; }
 	if(status) memcpy(status, b->h_status.p, n * 4);
 	const uint32_t *hn = b->h_ncigar.as<uint32_t>();
 	if(ncigar) memcpy(ncigar, hn, n * 4);

@@ -118,9 +118,9 @@ __device__ inline int km_gap(const uint8_t *qp, int qd, uint32_t sq, const uint8
 	for(uint32_t i=0;i<st;i++){
 		const uint32_t tb = tp[(int64_t)i * td];
 		const uint64_t TL = (tb & 1) ? ~0ull : 0ull, TH = (tb & 2) ? ~0ull : 0ull;
-		uint64_t carry = 0, phin = 1ull, mhin = 0;
+		uint64_t carry = 0, phin = type == 1 ? 0ull : 1ull, mhin = 0;   // OVERLAP (type 1, the long-pair kernel below): H(-1, y) = 0
 		int rowsum = 0;
-		sbeg++;
+		if(type != 1) sbeg++;
 		for(uint32_t w=0;w<W;w++){
 			const uint64_t ql = W == 1 ? ql1 : KS(w), qh = W == 1 ? qh1 : KS(W + w);
 			const uint64_t valid = km_lowmask(sq - 64 * w);
@@ -145,7 +145,7 @@ __device__ inline int km_gap(const uint8_t *qp, int qd, uint32_t sq, const uint8
 			KT(i + 1, w, 0) = mv; KT(i + 1, w, 1) = pv;
 			rowsum += __popcll(pv & valid) - __popcll(mv & valid);
 		}
-		if(type == 2){ const int srow = sbeg + rowsum; if(srow < smin){ smin = srow; rx = (int)sq - 1; ry = (int)i; } }   // bsalign.h:1124-1139
+		if(type != 0){ const int srow = sbeg + rowsum; if(srow < smin){ smin = srow; rx = (int)sq - 1; ry = (int)i; } }   // bsalign.h:1124-1139
 		else if(i + 1 == st) smin = sbeg + rowsum;
 	}
 	if(type == 2 && W == 1){ // arg-min over the last row, one word: bit-lane j is band position j (the general form is below)
@@ -221,7 +221,7 @@ __device__ inline int km_gap(const uint8_t *qp, int qd, uint32_t sq, const uint8
 		if(1u == (run & 0xf)) run += 0x10u * (uint32_t)qb; else { flush(); run = (0x10u * (uint32_t)qb) | 1u; }
 		ins += qb;
 	}
-	if(tb_){ // GLOBAL and EXTEND both pad the target (bsalign.h:1029)
+	if(tb_ && type != 1){ // GLOBAL and EXTEND both pad the target (bsalign.h:1029)
 		if(2u == (run & 0xf)) run += 0x10u * (uint32_t)tb_; else { flush(); run = (0x10u * (uint32_t)tb_) | 2u; }
 		del += tb_;
 	}
@@ -529,6 +529,41 @@ __global__ void __launch_bounds__(kKmWarps * 32, 8) kmer_edit_kernel(const KmerA
 		}
 		__syncwarp();
 	}
+}
+
+// ---- unbanded edit alignment of pairs too long for edit_kernel (band > 16384 cells, or a query whose bit-planes outgrow shared memory) ----
+// One thread per pair runs the general form of km_gap above on scratch in HBM: as slow as one CPU core, but striped_seqedit_pairwise
+// (bsalign.h:1046) has no length limit and a drop-in must not have one either.  Modes GLOBAL (whole query as the band), OVERLAP, EXTEND.
+struct EditLongArgs {
+	const uint8_t *seqs; const uint64_t *qoff, *toff; const uint32_t *qlen, *tlen;
+	const uint32_t *pairs; const uint64_t *scr_off; uint32_t npairs;
+	uint8_t *scratch; int mode;
+	int32_t *results, *status; uint32_t *cigars; const uint64_t *cig_off;
+	uint32_t *dense; uint64_t *dense_off; unsigned long long *dense_total; uint32_t *ncigar;
+};
+
+__global__ void __launch_bounds__(32) edit_long_kernel(const EditLongArgs a){
+	if(threadIdx.x || blockIdx.x >= a.npairs) return;
+	const uint32_t pair = a.pairs[blockIdx.x];
+	const uint32_t qlen = a.qlen[pair], tlen = a.tlen[pair];
+	const int type = a.mode & 3;
+	int32_t rec[8];
+	CigarSink cg;
+	cg.buf = a.cigars ? a.cigars + a.cig_off[pair] : nullptr;
+	cg.cap = a.cigars ? (uint32_t)(a.cig_off[pair + 1] - a.cig_off[pair]) : 0;
+	cg.n = 0; cg.run = 0; cg.err = 0;
+	uint32_t dummy = 0;
+	const int err = km_gap(a.seqs + a.qoff[pair], 1, qlen, a.seqs + a.toff[pair], 1, tlen, type, (uint64_t*)(a.scratch + a.scr_off[blockIdx.x]), 1,
+		cg.buf ? cg.buf : &dummy, cg.cap, rec);
+	cg.n = (uint32_t)rec[7];
+	const int qe = rec[0], te = rec[1], mat = rec[2], mis = rec[3], ins = rec[4], del = rec[5];
+	const int tb = type == 1 ? te - (mat + mis + del) : 0;   // GLOBAL / EXTEND pad the target down to 0
+	int32_t *rs = a.results + (size_t)pair * 10;
+	rs[0] = type == 1 ? rec[6] + te - tb : rec[6];
+	rs[1] = 0; rs[2] = qe; rs[3] = tb; rs[4] = te; rs[5] = mat; rs[6] = mis; rs[7] = ins; rs[8] = del; rs[9] = mat + mis + ins + del;
+	if(cg.buf && cg.n > cg.cap) cg.err |= 4;
+	emit_dense(cg, a.dense, a.dense_off, a.dense_total, a.ncigar, pair);
+	a.status[pair] = ((cg.buf ? err : (err & ~4)) | cg.err) & 7;
 }
 
 // results of the pairs that took the plain global edit (a sub-batch) go back into the batch's arrays; their cigar words are appended

@@ -38,6 +38,8 @@ extern "C" {
 #define BSB200_ST_CIGCAP  4  /* cigar capacity given by the caller was too small; cigar truncated, counts still exact */
 #define BSB200_ST_REFBUG  8  /* edit band shift hits the reference's scratch-corrupting path (bsalign.h:704-713); result follows the intended algorithm */
 #define BSB200_ST_EMPTY  16  /* qlen==0 or tlen==0: all-zero result (bsalign.h:1051-1054) */
+#define BSB200_ST_UNSUPPORTED 32  /* edit pair with a MOVING band wider than 16384 cells (or a query of more than ~29 kb under a moving band): not built; all-zero result.
+                                     Unbanded edit alignments (OVERLAP, EXTEND, GLOBAL with bandwidth 0 or >= qlen) have no length limit. */
 
 /* same field order as seqalign_result_t, bsalign.h:213-218 */
 typedef struct {
@@ -104,8 +106,7 @@ int bsb200_edit_pairwise(bsb200_ctx *ctx, const uint8_t *qseq, uint32_t qlen, co
  * ksz: k-mer size, 1..15 (larger values are clamped to 15 like bsalign.h:1217).  Unique shared canonical k-mers anchor the pair, the
  * gaps between the anchors are aligned with the edit DP, a pair without usable anchors gets the plain global edit (bsalign.h:1440).
  * Arguments as bsb200_edit_pairwise_batch; a pair needs room for qlen + tlen + 2 cigar words.  The *_dense form returns the cigars
- * dense and in pair order like bsb200_pairwise_batch_dense.  Limit: a pair WITHOUT anchors must have qlen <= 16384 (the unbanded
- * global edit of the fallback). */
+ * dense and in pair order like bsb200_pairwise_batch_dense. */
 int bsb200_kmer_edit_batch(bsb200_ctx *ctx, uint64_t n, const uint8_t *seqs,
 		const uint64_t *qoff, const uint32_t *qlen, const uint64_t *toff, const uint32_t *tlen, uint32_t ksz,
 		bsb200_result_t *results, uint32_t *cigars, const uint64_t *cgoff, uint32_t *ncigar, int32_t *status);

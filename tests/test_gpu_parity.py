@@ -483,3 +483,32 @@ def test_pipelined_one_call_equals_plain_call(ctx, monkeypatch):
     exp, ecg, _ = ck.kmer_batch("oracle", sub, 7)
     gc = kpiped.cigars()
     assert np.array_equal(kpiped.results[:m], exp) and all(np.array_equal(gc[i], ecg[i]) for i in range(m))
+
+
+def test_edit_pairs_beyond_the_kernel_band_limit(ctx):
+    """striped_seqedit_pairwise has no length limit: unbanded edit alignments whose band exceeds edit_kernel's 16384 cells take
+    edit_long_kernel (one thread per pair on scratch in HBM), next to ordinary pairs of the same batch; a moving band that wide is
+    reported as BSB200_ST_UNSUPPORTED instead of failing the batch."""
+    rng = np.random.default_rng(31)
+    q = rng.integers(0, 4, (1, 17000)).astype(np.uint8)
+    t, tl = synth.mutate_batch(rng, q, .03, .03, .03)
+    small = synth.make_pairs(40, 300, seed=8)
+    pairs = [(small.query(i), small.target(i)) for i in range(small.n)]
+    pairs.insert(7, (q[0], t[50:int(tl[0]) - 30]))
+    pairs.append((t[:int(tl[0])], q[0, 100:]))
+    b = synth.PairBatch.from_lists(pairs)
+    for mode in (0, 1, 2):
+        got = ctx.edit_batch(b, mode, 0)
+        exp, ecg, _ = ck.oracle_batch("edit", b, mode, 0, nthreads=4)
+        assert np.array_equal(got.results, exp), mode
+        assert all(np.array_equal(x, y) for x, y in zip(got.cigars(), ecg)), mode
+        assert not got.status.any()
+        dense = ctx.edit_batch(b, mode, 0, dense=True)
+        assert np.array_equal(dense.results, exp) and all(np.array_equal(x, y) for x, y in zip(dense.cigars(), ecg)), mode
+    # a band of 16448 cells that moves along a 40 kb query: not built, flagged, the rest of the batch is unaffected
+    big = rng.integers(0, 4, 40000).astype(np.uint8)
+    b2 = synth.PairBatch.from_lists(pairs[:5] + [(big, big[:39000].copy())])
+    got = ctx.edit_batch(b2, 0, 16400)
+    assert got.status[5] == 32 and not got.results[5].any() and not got.status[:5].any()
+    exp, _, _ = ck.oracle_batch("edit", synth.PairBatch.from_lists(pairs[:5]), 0, 16400)
+    assert np.array_equal(got.results[:5], exp)
