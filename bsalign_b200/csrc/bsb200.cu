@@ -258,6 +258,8 @@ static bool is_pageable(const void *p){
 	if(cudaPointerGetAttributes(&at, p) != cudaSuccess){ cudaGetLastError(); return true; }
 	return at.type == cudaMemoryTypeUnregistered;
 }
+// a call that cuts its work into chunks asks once per caller array and tells the copies of its chunks (-1: ask per copy)
+static thread_local int tl_src_pageable = -1, tl_dst_pageable = -1;
 constexpr size_t kStageChunk = 32ull << 20;
 static void par_memcpy(void *dst, const void *src, size_t bytes){
 	const int NT = bytes >= (8u << 20) ? 8 : 1;
@@ -267,7 +269,7 @@ static void par_memcpy(void *dst, const void *src, size_t bytes){
 	});
 }
 static cudaError_t h2d_copy(bsb200_ctx *ctx, void *dst, const void *src, size_t bytes, cudaStream_t st){
-	if(bytes < (4u << 20) || getenv("BSB200_NOSTAGE") || !is_pageable(src)) return cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, st);
+	if(bytes < (4u << 20) || getenv("BSB200_NOSTAGE") || !(tl_src_pageable >= 0 ? tl_src_pageable != 0 : is_pageable(src))) return cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, st);
 	cudaError_t e = cudaSuccess;
 	for(int k=0;k<2;k++) if((e = ctx->stage[k].reserve(kStageChunk)) != cudaSuccess) return e;
 	int k = 0;
@@ -284,7 +286,7 @@ static cudaError_t h2d_copy(bsb200_ctx *ctx, void *dst, const void *src, size_t 
 }
 // device -> pageable host; returns when the data is in dst (the stream is synchronised up to the copy)
 static cudaError_t d2h_copy(bsb200_ctx *ctx, void *dst, const void *src, size_t bytes, cudaStream_t st){
-	if(bytes < (4u << 20) || getenv("BSB200_NOSTAGE") || !is_pageable(dst)) return cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, st);
+	if(bytes < (4u << 20) || getenv("BSB200_NOSTAGE") || !(tl_dst_pageable >= 0 ? tl_dst_pageable != 0 : is_pageable(dst))) return cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, st);
 	cudaError_t e = cudaSuccess;
 	for(int k=0;k<2;k++) if((e = ctx->stage[k].reserve(kStageChunk)) != cudaSuccess) return e;
 	const size_t nchunk = (bytes + kStageChunk - 1) / kStageChunk;
@@ -1538,9 +1540,14 @@ static int dense_pipelined(bsb200_ctx *ctx, int kind, uint64_t n, const uint8_t 
 	const uint64_t K = ksz ? std::min<uint64_t>(4, std::max<uint64_t>(2, n / 200000)) : std::min<uint64_t>(8, std::max<uint64_t>(2, n / 131072));
 	struct { std::mutex m, upload; std::condition_variable cv; uint64_t next_fetch = 0, base = 0; int err = 0; std::string msg; } sy;
 	bsb200_timing_t acc[2] = {bsb200_timing_t(), bsb200_timing_t()};
+	// pinned or pageable caller arrays: asked once here, not once per chunk and copy (the query costs ~30 us)
+	const int src_pg = is_pageable(seqs ? (const void*)seqs : (const void*)bits) ? 1 : 0;
+	const int dst_pg = (is_pageable(results) || (cigars && is_pageable(cigars))) ? 1 : 0;
 	auto worker = [&](int t){
 		bsb200_ctx *cx = t ? ctx->helper : ctx;
 		cudaSetDevice(cx->device);
+		tl_src_pageable = src_pg; tl_dst_pageable = dst_pg;
+		struct Reset { ~Reset(){ tl_src_pageable = -1; tl_dst_pageable = -1; } } reset_;
 		// rebased offsets live in pinned memory: a copy from pageable memory would wait for the sequence copy queued before it
 		HostBuf &hq2 = cx->host_cache[6], &ht2 = cx->host_cache[7];
 		// the stretch of the arena a chunk's queries come from and the one its targets come from: one copy when they touch or overlap
