@@ -166,3 +166,45 @@ def forked(fn, *args, timeout_s=120, **kw):
     if status != 0 or not data:
         return None
     return pickle.loads(data)
+
+
+def repetitive_pairs(seed, n=60):
+    """Pairs that stress the k-mer anchoring (kmer_striped_seqedit_pairwise): homopolymers, tandem repeats, two-letter sequences, internal
+    duplications, reversed and reverse-complemented partners, lengths around the k-mer size, a few point differences."""
+    from bsalign_b200 import synth
+    rng = np.random.default_rng(seed)
+    out = []
+    for _ in range(n):
+        kind = int(rng.integers(0, 6))
+        L = int(rng.integers(5, 400))
+        if kind == 0:
+            a = np.zeros(L, np.uint8)
+        elif kind == 1:
+            a = np.full(L, 3, np.uint8)
+        elif kind == 2:
+            u = rng.integers(0, 4, int(rng.integers(1, 7))).astype(np.uint8)
+            a = np.tile(u, L // len(u) + 1)[:L]
+        elif kind == 3:
+            a = (rng.integers(0, 2, L) * 3).astype(np.uint8)
+        elif kind == 4:
+            a = rng.integers(0, 4, L).astype(np.uint8)
+            m = L // 3
+            a[m:2 * m] = a[:m]
+        else:
+            a = rng.integers(0, 4, L).astype(np.uint8)
+        b = a.copy()
+        for _ in range(int(rng.integers(0, 6))):
+            p = int(rng.integers(0, len(b)))
+            op = int(rng.integers(0, 3))
+            if op == 0:
+                b[p] = (b[p] + 1) & 3
+            elif op == 1:
+                b = np.insert(b, p, rng.integers(0, 4)).astype(np.uint8)
+            elif len(b) > 2:
+                b = np.delete(b, p)
+        if rng.integers(0, 4) == 0:
+            b = b[::-1].copy()
+        if rng.integers(0, 5) == 0:
+            b = (3 - b[::-1]).astype(np.uint8)
+        out.append((a, b))
+    return synth.PairBatch.from_lists(out)

@@ -397,6 +397,12 @@ def test_kmer_edit_matches_golden_and_oracle(ctx, monkeypatch):
         st = got.status.copy()
         st[batch.qlen == 0] &= ~16
         assert not st.any()
+    for seed, k in ((1, 13), (2, 3), (3, 15), (4, 2), (5, 7), (6, 1), (7, 9)):   # homopolymers, tandem repeats, reverse complements ...
+        rb = ck.repetitive_pairs(seed, n=120)
+        got = ctx.kmer_edit_batch(rb, k)
+        exp, ecg, _ = ck.kmer_batch("oracle", rb, k, nthreads=4)
+        assert np.array_equal(got.results, exp), (seed, k)
+        assert all(np.array_equal(x, y) for x, y in zip(got.cigars(), ecg)), (seed, k)
     rng = np.random.default_rng(123)
 
     def related(n, qlen, p):

@@ -100,6 +100,18 @@ def test_oracle_kmer_edit_vs_compiled_reference():
         assert all(np.array_equal(a, b) for a, b in zip(c1, c2)), k
 
 
+@pytest.mark.skipif(not ck.have_ref(), reason="oracle/_ref not built (no /root/reference on this box)")
+def test_oracle_kmer_edit_on_repetitive_sequences():
+    """homopolymers, tandem repeats, duplications, reverse complements: the multiplicity rules of the anchoring (a k-mer counts only when
+    it occurs once in each sequence on the same strand) and the sentinel quirk of the reference's scan."""
+    for seed, k in ((1, 13), (2, 3), (3, 15), (4, 2), (5, 7), (6, 1)):
+        batch = ck.repetitive_pairs(seed)
+        r1, c1, _ = ck.kmer_batch("ref", batch, k)
+        r2, c2, _ = ck.kmer_batch("oracle", batch, k)
+        assert np.array_equal(r1, r2), (seed, k)
+        assert all(np.array_equal(a, b) for a, b in zip(c1, c2)), (seed, k)
+
+
 def test_readme_example():
     """README.md:36-42 of the reference: pair 29.1/29.2, score 128, 71 matches, 4 mismatches, one indel."""
     z = np.load(os.path.join(GOLD, "readme_pair.npz"))
