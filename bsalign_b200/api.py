@@ -80,6 +80,7 @@ def lib():
         L.bsb200_pairwise_batch_dense.argtypes = [_P, ctypes.c_int, ctypes.c_uint64, _P, _P, _P, _P, _P, ctypes.c_int, ctypes.c_uint32, _P,
                                                   _I8, _I8, _I8, _I8, _P, _P, ctypes.c_uint64, _P, _P, _P]
         L.bsb200_pairwise_batch_dense_bits.argtypes = L.bsb200_pairwise_batch_dense.argtypes
+        L.bsb200_remsa_batch.argtypes = [_P, ctypes.c_uint32, _P, _P, _P, ctypes.c_uint64, _P, _P, ctypes.c_uint64, _P, _P, _P]
         L.bsb200_pack_pairs_dev.argtypes = [_P, _P, _P, _P, _P, _P, _P, ctypes.c_uint64, _P]
         L.bsb200_pairwise_batch_ptrs.argtypes = [_P, ctypes.c_int, ctypes.c_uint64, _P, _P, _P, _P, ctypes.c_int, ctypes.c_uint32, _P,
                                                  _I8, _I8, _I8, _I8, _P, _P, _P, _P, ctypes.c_int]
@@ -292,6 +293,41 @@ def pack_pairs(batch, idx, out_seqs=None, nthreads=8):
     pb = PairBatch.__new__(PairBatch)
     pb.seqs, pb.qoff, pb.qlen, pb.toff, pb.tlen = out_seqs[:max(nbytes, 1)], qoff, np.ascontiguousarray(batch.qlen[i64]), toff, np.ascontiguousarray(batch.tlen[i64])
     return pb, nbytes
+
+
+def remsa_batch(ctx, jobs, want_matrices=False):
+    """bsb200_remsa_batch: the DP + walk of remsa_pedit_rd_bspoacore (bspoa.h:3916) for a batch of jobs.  A job has mlen, bw, mbeg, mend,
+    rdlen and the reference's arrays seqs0, seqs1 (sz1 bytes each, bw / 2 bytes of padding in front) and mats (2, 4, sz1).
+    Returns (list of match arrays, out[n, 4] = score / status / matched / 0, list of (M0, M1) or None)."""
+    n = len(jobs)
+    hdr = np.zeros((n, 8), dtype=np.int32)
+    blocks, in_off, match_off, mat_off = [], np.zeros(n, np.uint64), np.zeros(n, np.uint64), np.zeros(n, np.uint64)
+    o = mo = xo = 0
+    for k, j in enumerate(jobs):
+        hdr[k, :5] = (j.mlen, j.bw, j.mbeg, j.mend, j.rdlen)
+        blk = np.concatenate([j.seqs0, j.seqs1, j.mats.reshape(-1)]).astype(np.uint8)
+        in_off[k] = o; o += (len(blk) + 15) // 16 * 16
+        blocks.append(blk)
+        match_off[k] = mo; mo += j.rdlen
+        mat_off[k] = xo; xo += 2 * (2 * j.mlen + 1) * (j.bw + 2)
+    arena = np.zeros(max(o, 1), dtype=np.uint8)
+    for k, blk in enumerate(blocks):
+        arena[int(in_off[k]):int(in_off[k]) + len(blk)] = blk
+    match = np.zeros(max(mo, 1), dtype=np.int32)
+    out = np.zeros((n, 4), dtype=np.int32)
+    mats = np.zeros(max(xo, 1), dtype=np.uint8) if want_matrices else None
+    rc = ctx._lib.bsb200_remsa_batch(ctx._h, n, _ptr(hdr), _ptr(arena), _ptr(in_off), int(o), _ptr(match), _ptr(match_off), int(mo), _ptr(out),
+                                     _ptr(mats), _ptr(mat_off) if want_matrices else None)
+    ctx._check(rc, "bsb200_remsa_batch")
+    ms = [match[int(match_off[k]):int(match_off[k]) + jobs[k].rdlen].copy() for k in range(n)]
+    mm = None
+    if want_matrices:
+        mm = []
+        for k, j in enumerate(jobs):
+            szm = (2 * j.mlen + 1) * (j.bw + 2)
+            b0 = int(mat_off[k])
+            mm.append((mats[b0:b0 + szm], mats[b0 + szm:b0 + 2 * szm]))
+    return ms, out, mm
 
 
 def pack_pairs_dev(ctx, d_src_ptr, batch, idx, d_dst_ptr):

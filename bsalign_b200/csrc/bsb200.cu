@@ -11,6 +11,7 @@
 #include "epi8_backcal.cuh"
 #include "edit_kernels.cuh"
 #include "kmer_edit.cuh"
+#include "remsa_kernels.cuh"
 
 #include <cub/device/device_scan.cuh>
 #include <cub/iterator/transform_input_iterator.cuh>
@@ -86,6 +87,7 @@ struct bsb200_ctx {
 	DevBuf poa_cache[40];   // same, for POA sweep batches (poa_host.cuh)
 	HostBuf stage[2]; cudaEvent_t stage_ev[2] = {nullptr, nullptr};   // pinned staging for large copies from / to pageable caller memory
 	bsb200_ctx *helper = nullptr;   // second context on the same device: the one-call entry points pipeline large edit batches over both
+	DevBuf remsa_cache[8];  // re-alignment batches (bsb200_remsa_batch)
 	DevBuf kmer_cache[8];   // k-mer guided edit: warp slots, gap-trace pool, counters, order list, fallback sub-batch results
 	HostBuf poa_hcache[2];
 };
@@ -164,6 +166,7 @@ extern "C" void bsb200_destroy(bsb200_ctx *ctx){
 	for(auto &h : ctx->host_cache) h.release();
 	for(auto &d : ctx->poa_cache) d.release();
 	for(auto &d : ctx->kmer_cache) d.release();
+	for(auto &d : ctx->remsa_cache) d.release();
 	for(auto &h : ctx->poa_hcache) h.release();
 	for(auto &e : ctx->ev) cudaEventDestroy(e);
 	for(auto &e : ctx->stage_ev) if(e) cudaEventDestroy(e);
@@ -184,6 +187,7 @@ extern "C" void bsb200_trim(bsb200_ctx *ctx){
 	for(auto &h : ctx->host_cache) h.release();
 	for(auto &d : ctx->poa_cache) d.release();
 	for(auto &d : ctx->kmer_cache) d.release();
+	for(auto &d : ctx->remsa_cache) d.release();
 	for(auto &h : ctx->poa_hcache) h.release();
 	for(auto &h : ctx->stage) h.release();
 	ctx->auto_budget = 0;
@@ -1388,6 +1392,61 @@ extern "C" int bsb200_kmer_edit_pairwise(bsb200_ctx *ctx, uint32_t ksz, const ui
 	if(tlen) memcpy(arena.data() + qlen, tseq, tlen);
 	const uint64_t qo = 0, to = qlen, cgo[2] = {0, cigar_cap};
 	return kmer_edit_impl(ctx, 1, arena.data(), &qo, &qlen, &to, &tlen, ksz, result, cigar, cigar ? cgo : nullptr, 0, nullptr, ncigar, status);
+}
+
+
+// ---- re-alignment of reads against the MSA profile: the DP + walk of remsa_pedit_rd_bspoacore (bspoa.h:3916-4045) for batches ----------
+// hdr: per job 8 ints {mlen, bw, mbeg, mend, rend, 0, 0, 0}; `in` holds per job the ten arrays of the reference's own layout (see
+// remsa_kernels.cuh) at in_off[job]; match receives rend ints per job at match_off[job] (the MSA column of every read position, -1 =
+// not matched), out 4 ints per job {score of the walk, status, matched positions, 0}.  matrices (may be NULL): the two DP matrices of
+// every job, (2 * mlen + 1) * (bw + 2) bytes each, at mat_off[job] - for checks against the reference's own matrices.
+extern "C" int bsb200_remsa_batch(bsb200_ctx *ctx, uint32_t njobs, const int32_t *hdr, const uint8_t *in, const uint64_t *in_off, uint64_t in_bytes,
+		int32_t *match, const uint64_t *match_off, uint64_t match_ints, int32_t *out, uint8_t *matrices, const uint64_t *mat_off_out){
+	if(!ctx || (njobs && (!hdr || !in || !in_off || !match || !match_off || !out))) return fail(ctx, "bsb200_remsa_batch", cudaSuccess);
+	ctx->err.clear();
+	if(njobs == 0) return 0;
+	cudaSetDevice(ctx->device);
+	cudaStream_t st = ctx->stream;
+	std::vector<uint64_t> moff(njobs + 1, 0);
+	for(uint32_t j=0;j<njobs;j++){
+		const int32_t *h = hdr + (size_t)j * 8;
+		if(h[0] <= 0 || h[1] <= 0 || h[4] < 0) return fail(ctx, "bsb200_remsa_batch: bad job header", cudaSuccess);
+		moff[j + 1] = moff[j] + ((2ull * ((uint64_t)(2 * h[0] + 1) * (uint64_t)(h[1] + 2)) + 127) / 128 * 128);
+	}
+	DevBuf *c = ctx->remsa_cache;
+	CK(c[0].reserve(in_bytes + 16)); CK(c[1].reserve((size_t)njobs * 32)); CK(c[2].reserve((size_t)njobs * 8 + 8)); CK(c[3].reserve(moff[njobs] + 256, true));
+	CK(c[4].reserve((size_t)njobs * 8 + 8)); CK(c[5].reserve(match_ints * 4 + 16)); CK(c[6].reserve((size_t)njobs * 8 + 8)); CK(c[7].reserve((size_t)njobs * 16));
+	cudaEventRecord(ctx->ev[0], st);
+	CK(h2d_copy(ctx, c[0].p, in, in_bytes, st));
+	CK(cudaMemcpyAsync(c[1].p, hdr, (size_t)njobs * 32, cudaMemcpyHostToDevice, st));
+	CK(cudaMemcpyAsync(c[2].p, in_off, (size_t)njobs * 8, cudaMemcpyHostToDevice, st));
+	CK(cudaMemcpyAsync(c[4].p, moff.data(), (size_t)njobs * 8, cudaMemcpyHostToDevice, st));
+	CK(cudaMemcpyAsync(c[6].p, match_off, (size_t)njobs * 8, cudaMemcpyHostToDevice, st));
+	cudaEventRecord(ctx->ev[1], st);
+	RemsaArgs a;
+	a.njobs = njobs; a.hdr = c[1].as<int32_t>(); a.in = c[0].as<uint8_t>(); a.in_off = c[2].as<uint64_t>();
+	a.mat = c[3].as<uint8_t>(); a.mat_off = c[4].as<uint64_t>(); a.match = c[5].as<int32_t>(); a.match_off = c[6].as<uint64_t>(); a.out = c[7].as<int32_t>();
+	remsa_kernel<<<(njobs + kRemsaWarps - 1) / kRemsaWarps, kRemsaWarps * 32, 0, st>>>(a);
+	CK(cudaGetLastError());
+	cudaEventRecord(ctx->ev[2], st);
+	CK(d2h_copy(ctx, match, c[5].p, match_ints * 4, st));
+	CK(cudaMemcpyAsync(out, c[7].p, (size_t)njobs * 16, cudaMemcpyDeviceToHost, st));
+	if(matrices && mat_off_out){
+		for(uint32_t j=0;j<njobs;j++){
+			const int32_t *h = hdr + (size_t)j * 8;
+			CK(cudaMemcpyAsync(matrices + mat_off_out[j], c[3].as<uint8_t>() + moff[j], 2ull * (uint64_t)(2 * h[0] + 1) * (uint64_t)(h[1] + 2), cudaMemcpyDeviceToHost, st));
+		}
+	}
+	cudaEventRecord(ctx->ev[3], st);
+	CK(cudaStreamSynchronize(st));
+	float m0 = 0, m1 = 0, m2 = 0;
+	cudaEventElapsedTime(&m0, ctx->ev[0], ctx->ev[1]); cudaEventElapsedTime(&m1, ctx->ev[1], ctx->ev[2]); cudaEventElapsedTime(&m2, ctx->ev[2], ctx->ev[3]);
+	ctx->timing = bsb200_timing_t();
+	ctx->timing.h2d_ms = m0; ctx->timing.forward_ms = m1; ctx->timing.run_ms = m1; ctx->timing.d2h_ms = m2; ctx->timing.total_ms = m0 + m1 + m2;
+	ctx->timing.forward_launches = 1; ctx->timing.h2d_bytes = in_bytes + (uint64_t)njobs * 56; ctx->timing.d2h_bytes = match_ints * 4 + (uint64_t)njobs * 16;
+	{ uint64_t cells = 0; for(uint32_t j=0;j<njobs;j++){ const int32_t *h = hdr + (size_t)j * 8; cells += (uint64_t)h[1] * (2ull * (uint64_t)(h[3] - h[2])); } ctx->timing.cells = cells; }
+	ctx->timing.trace_bytes = moff[njobs];
+	return 0;
 }
 
 // ---- host helpers of the multi-GPU split (bsalign_b200/shard.py): compact arenas per shard, pair-ordered merge of the shards' cigars ----

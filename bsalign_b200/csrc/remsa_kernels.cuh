@@ -1,0 +1,137 @@
+// remsa_kernels.cuh -- re-alignment of reads against the MSA profile on the device: the DP and the walk of
+// remsa_pedit_rd_bspoacore (bspoa.h:3916-4045; kernel maxmat_dp_diag_rowcal bspoa.h:3856-3896).
+//
+// One job = one read of one BSPOA object in MSA coordinates against the (reversed) consensus and the per-column profile scores, in the
+// byte layout remsa_pedits_bspoa carves out of g->memp (bspoa.h:4209-4229): ten arrays of sz1 = roundup(mlen + bw, 16) bytes, each with
+// bw / 2 bytes of padding in front: seqs0, seqs1, mats[0][0..3], mats[1][0..3].  The reference walks an anti-diagonal band of bw cells
+// down the main diagonal (one SSE word per 16 cells) and keeps the DP in difference form in two byte matrices; the walk back re-derives
+// every step from those differences.
+//
+// One WARP per job.  bw = 32 (the default: editbw / 2) is one cell per lane: the previous diagonal stays in registers, a cell's upper
+// and left neighbours are one shuffle each, and the read / consensus / profile bytes of a cell slide along the lanes (one new byte per
+// diagonal comes from memory, the other 31 from the neighbour lane).  Other widths keep two diagonals in shared memory.  Every diagonal
+// is stored once (the walk needs it), the walk is lane 0: a chain of dependent byte lookups.
+#pragma once
+#include "common.cuh"
+#include <stdint.h>
+
+namespace bsb200 {
+
+struct RemsaArgs {
+	uint32_t njobs;
+	const int32_t *hdr;        // per job 8 ints: mlen, bw, mbeg, mend, rend (read positions), 0, 0, 0
+	const uint8_t *in;         // input blocks
+	const uint64_t *in_off;    // per job byte offset of its block
+	uint8_t *mat;              // per job two matrices of (2 * mlen + 1) * (bw + 2) bytes, back to back
+	const uint64_t *mat_off;
+	int32_t *match;            // per job rend ints: the MSA column a read position is matched to, or -1
+	const uint64_t *match_off;
+	int32_t *out;              // per job 4 ints: score of the walk, status, matched positions, 0
+};
+
+__device__ __forceinline__ int remsa_score(const uint8_t *seqs0, const uint8_t *seqs1, const uint8_t *mats0, const uint8_t *mats1, uint32_t sz1, int mlen, int xi, int yi){
+	const int s1 = seqs1[mlen - 1 - yi], s0 = seqs0[xi];
+	int h = (s1 < 4 ? mats0[(size_t)s1 * sz1 + xi] : 0) + (s0 < 4 ? mats1[(size_t)s0 * sz1 + (mlen - 1 - yi)] : 0);
+	return h > 255 ? 255 : h;
+}
+
+constexpr int kRemsaWarps = 4;          // jobs per CTA
+constexpr int kRemsaMaxBw = 256;        // widest band of the shared-memory path
+
+__global__ void __launch_bounds__(kRemsaWarps * 32) remsa_kernel(const RemsaArgs a){
+	__shared__ uint8_t rowbuf[kRemsaWarps][2][2][kRemsaMaxBw + 2];   // [warp][matrix][parity][border + cells + border]
+	const uint32_t lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+	const uint32_t job = blockIdx.x * kRemsaWarps + wid;
+	if(job >= a.njobs) return;
+	const int32_t *hd = a.hdr + (size_t)job * 8;
+	const int mlen = hd[0], bw = hd[1], mbeg = hd[2], mend = hd[3], rend = hd[4];
+	const int half = bw / 2, rowlen = bw + 2;
+	const uint32_t sz1 = (uint32_t)((mlen + bw + 15) / 16 * 16);
+	const uint8_t *blk = a.in + a.in_off[job];
+	const uint8_t *seqs0 = blk + half, *seqs1 = blk + sz1 + half, *mats0 = blk + 2 * (size_t)sz1 + half, *mats1 = blk + 6 * (size_t)sz1 + half;
+	uint8_t *M0 = a.mat + a.mat_off[job], *M1 = M0 + (size_t)(2 * mlen + 1) * rowlen;
+	int32_t *match = a.match + a.match_off[job];
+	int32_t *out = a.out + (size_t)job * 4;
+	for(int c=lane;c<rend;c+=32) match[c] = -1;
+	if(bw > kRemsaMaxBw || bw < 2 || (bw & 1) || mend <= mbeg || mbeg < 0 || mend > mlen){ if(lane == 0){ out[0] = 0; out[1] = 1; out[2] = 0; out[3] = 0; } return; }
+	// ---- forward: diagonals 2 * mbeg .. 2 * mend - 2, row i + 1 of the matrices from row i (bspoa.h:3749-3758, 3856-3896, 3925-3934) ----
+	{
+		uint8_t *r0 = M0 + (size_t)rowlen * 2 * mbeg, *r1 = M1 + (size_t)rowlen * 2 * mbeg;
+		for(int c=lane;c<rowlen;c+=32){ r0[c] = (c == 1 + half - 1) ? 255 : 0; r1[c] = (c == 1 + half) ? 255 : 0; }
+	}
+	if(bw == 32){
+		// one cell per lane; u / v of the previous diagonal in registers (borders: the values the reference writes beside the row)
+		int pu = (lane == (uint32_t)half - 1) ? 255 : 0, pv = (lane == (uint32_t)half) ? 255 : 0;
+		int bl_u = 0, bl_v = 0, br_u = 0, br_v = 0;   // border bytes left (-1) and right (bw) of the previous diagonal
+		int x = mbeg, y = mbeg;
+		for(int i=2*mbeg;;i++){
+			const int dir = i & 1;
+			const int h0 = remsa_score(seqs0, seqs1, mats0, mats1, sz1, mlen, x - half + (int)lane, y + half - (int)lane);
+			int u, v;
+			if(dir){ u = __shfl_down_sync(0xffffffffu, pu, 1); if(lane == 31) u = br_u; v = pv; }
+			else { u = pu; v = __shfl_up_sync(0xffffffffu, pv, 1); if(lane == 0) v = bl_v; }
+			int h = h0 < u ? u : h0;
+			if(h < v) h = v;
+			pu = h - v; pv = h - u;
+			uint8_t *nu = M0 + (size_t)rowlen * (i + 1) + 1, *nv = M1 + (size_t)rowlen * (i + 1) + 1;
+			nu[lane] = (uint8_t)pu; nv[lane] = (uint8_t)pv;
+			if(dir){ bl_u = 255; bl_v = 0; br_u = 0; br_v = 0; } else { bl_u = 0; bl_v = 0; br_u = 0; br_v = 255; }
+			if(lane == 0){ nu[-1] = (uint8_t)bl_u; nv[-1] = (uint8_t)bl_v; nu[bw] = (uint8_t)br_u; nv[bw] = (uint8_t)br_v; }
+			if(dir) y++; else x++;
+			if(x >= mend) break;
+		}
+		(void)br_v; (void)bl_u;
+	} else {
+		uint8_t (*rb)[2][kRemsaMaxBw + 2] = rowbuf[wid];
+		for(int c=lane;c<rowlen;c+=32){ rb[0][0][c] = (c == 1 + half - 1) ? 255 : 0; rb[1][0][c] = (c == 1 + half) ? 255 : 0; }
+		__syncwarp();
+		int x = mbeg, y = mbeg, par = 0;
+		for(int i=2*mbeg;;i++,par^=1){
+			const int dir = i & 1;
+			const uint8_t *pu = rb[0][par] + 1, *pv = rb[1][par] + 1;
+			uint8_t *qu = rb[0][par ^ 1] + 1, *qv = rb[1][par ^ 1] + 1;
+			uint8_t *nu = M0 + (size_t)rowlen * (i + 1) + 1, *nv = M1 + (size_t)rowlen * (i + 1) + 1;
+			for(int c=lane;c<bw;c+=32){
+				int h = remsa_score(seqs0, seqs1, mats0, mats1, sz1, mlen, x - half + c, y + half - c);
+				const int u = dir ? pu[c + 1] : pu[c], v = dir ? pv[c] : pv[c - 1];
+				if(h < u) h = u;
+				if(h < v) h = v;
+				qu[c] = (uint8_t)(h - v); qv[c] = (uint8_t)(h - u);
+				nu[c] = (uint8_t)(h - v); nv[c] = (uint8_t)(h - u);
+			}
+			if(lane == 0){
+				const uint8_t lu = dir ? 255 : 0, rv = dir ? 0 : 255;
+				qu[-1] = lu; qv[-1] = 0; qu[bw] = 0; qv[bw] = rv;
+				nu[-1] = lu; nv[-1] = 0; nu[bw] = 0; nv[bw] = rv;
+			}
+			__syncwarp();
+			if(dir) y++; else x++;
+			if(x >= mend) break;
+		}
+	}
+	__threadfence_block();
+	__syncwarp();
+	if(lane) return;
+	// ---- the walk (bspoa.h:3962-4040): lane 0 ---------------------------------------------------------------------------------------
+	int xi = mend - 1, yi = mend - 1, roff = rend, scr = 0, err = 0, nmatch = 0;
+	while(xi >= 0 && yi >= 0){
+		const int i = xi + yi;
+		if(i < mbeg + mbeg) break;
+		const int dir = i & 1;
+		const int xx = (xi - yi - dir) / 2 + half;
+		if(xx < 0 || xx >= bw){ err |= 1; break; }
+		const uint8_t *pu = M0 + (size_t)rowlen * i + 1, *pv = M1 + (size_t)rowlen * i + 1, *nu = M0 + (size_t)rowlen * (i + 1) + 1;
+		const int h = remsa_score(seqs0, seqs1, mats0, mats1, sz1, mlen, xi, yi);
+		const int e = dir ? pu[xx + 1] : pu[xx], f = dir ? pv[xx] : pv[xx - 1];
+		const int s = f + nu[xx];
+		if(s == f && !(xx == 0 && dir == 0)){ if(seqs0[xi] < 4) roff--; xi--; }
+		else if(s == e){ yi--; }
+		else if(s == h){
+			if(seqs0[xi] < 4){ roff--; if(roff >= 0 && roff < rend){ match[roff] = yi; nmatch++; } else err |= 1; }
+			scr += s; xi--; yi--;
+		} else { err |= 2; break; }   // the reference aborts here ("something wrong"): never seen on its own inputs
+	}
+	out[0] = scr; out[1] = err; out[2] = nmatch; out[3] = 0;
+}
+
+} // namespace bsb200

@@ -117,6 +117,17 @@ int bsb200_kmer_edit_batch_dense(bsb200_ctx *ctx, uint64_t n, const uint8_t *seq
 int bsb200_kmer_edit_pairwise(bsb200_ctx *ctx, uint32_t ksz, const uint8_t *qseq, uint32_t qlen, const uint8_t *tseq, uint32_t tlen,
 		bsb200_result_t *result, uint32_t *cigar, uint32_t cigar_cap, uint32_t *ncigar, int32_t *status);
 
+/* ---- re-alignment of reads against the MSA profile: the DP and the walk of remsa_pedit_rd_bspoacore (bspoa.h:3916-4045, kernel
+ * maxmat_dp_diag_rowcal bspoa.h:3856) for batches of (object, read) jobs ----
+ * hdr: per job 8 ints {mlen, bw, mbeg, mend, rend, 0, 0, 0} (bw = the band in cells, a multiple of 16, <= 256; rend = the read positions).
+ * `in` holds, at in_off[job], the job's ten arrays exactly as remsa_pedits_bspoa lays them out in g->memp (bspoa.h:4209-4229): seqs[0],
+ * seqs[1], mats[0][0..3], mats[1][0..3], each roundup(mlen + bw, 16) bytes with bw / 2 bytes of padding in front of index 0.
+ * match: rend ints per job at match_off[job] - the MSA column every read position is matched to (the reference calls merge_nodes_bspoa
+ * for exactly those pairs, bspoa.h:4012-4023), -1 otherwise.  out: 4 ints per job {score of the walk, status (0 = fine), matched
+ * positions, 0}.  matrices / mat_off (may be NULL): the two DP matrices per job, (2 * mlen + 1) * (bw + 2) bytes each, for checks. */
+int bsb200_remsa_batch(bsb200_ctx *ctx, uint32_t njobs, const int32_t *hdr, const uint8_t *in, const uint64_t *in_off, uint64_t in_bytes,
+		int32_t *match, const uint64_t *match_off, uint64_t match_ints, int32_t *out, uint8_t *matrices, const uint64_t *mat_off);
+
 /* ---- more shapes of the same call (kind: 0 = epi8, 1 = edit; matrix / gaps ignored for kind 1) ------------------------------------ */
 /* one call, cigars DENSE and in pair order (pair i starts at word sum(ncigar[0..i-1]); see bsb200_batch_fetch_dense): the fast path */
 int bsb200_pairwise_batch_dense(bsb200_ctx *ctx, int kind, uint64_t n, const uint8_t *seqs,

@@ -1387,3 +1387,74 @@ int bso_kmer_edit_pairwise(uint32_t ksz, const uint8_t *qseq, uint32_t qlen, con
 	free(aq); free(at);
 	return err;
 }
+
+/* ------------------------------------------------------------------------------------------------
+ * Re-alignment of one read against the MSA profile: remsa_pedit_rd_bspoacore, bspoa.h:3916-4045, restated
+ * per cell.  An anti-diagonal band of bw cells runs down the main diagonal of the (read-in-MSA-coordinates) x (MSA columns) square from
+ * mbeg to mend; diagonal `moff` = x + y is row moff + 1 of two byte matrices of bw + 2 bytes per row (one border byte on each side) that hold
+ * the DP in difference form: U = H - (value from above), V = H - (value from the left), unsigned bytes with saturating arithmetic
+ * (maxmat_dp_diag_rowcal, bspoa.h:3856-3896).  The cell score is the profile count of the read's base in that column plus the read's
+ * homopolymer count for the consensus base (prepare: bspoa.h:3760-3784; seqs1 / mats1 are stored reversed so that a diagonal is
+ * contiguous).  The walk back (bspoa.h:3962-4040) re-derives every step from the differences and reports, per read position, the MSA
+ * column it is matched to (the reference merges the read's node into that column's node there).
+ * seqs0 / seqs1 / mats point at index 0 of arrays with bw / 2 readable bytes in front and behind.  M0 / M1: (2 * mlen + 1) * (bw + 2) bytes.
+ * ------------------------------------------------------------------------------------------------ */
+static inline int bso_remsa_score(const uint8_t *seqs0, const uint8_t *seqs1, const uint8_t *const mats0[4], const uint8_t *const mats1[4], int mlen, int xi, int yi){
+	const int s1 = seqs1[mlen - 1 - yi], s0 = seqs0[xi];
+	int h = (s1 < 4 ? mats0[s1][xi] : 0) + (s0 < 4 ? mats1[s0][mlen - 1 - yi] : 0);
+	return h > 255 ? 255 : h;
+}
+
+int bso_remsa_core(int mlen, int bw, int mbeg, int mend, int rend, const uint8_t *seqs0, const uint8_t *seqs1,
+		const uint8_t *m00, const uint8_t *m01, const uint8_t *m02, const uint8_t *m03, const uint8_t *m10, const uint8_t *m11, const uint8_t *m12, const uint8_t *m13,
+		uint8_t *M0, uint8_t *M1, int32_t *match, int32_t *scr_out){
+	const uint8_t *const mats0[4] = {m00, m01, m02, m03}, *const mats1[4] = {m10, m11, m12, m13};
+	const int rowlen = bw + 2, half = bw / 2;
+	int x, y, i, c, dir, xi, yi, roff, scr = 0, err = 0;
+	for(c=0;c<rend;c++) match[c] = -1;
+	/* init (bspoa.h:3749-3758) */
+	memset(M0 + (size_t)rowlen * 2 * mbeg, 0, rowlen); memset(M1 + (size_t)rowlen * 2 * mbeg, 0, rowlen);
+	M0[(size_t)rowlen * 2 * mbeg + 1 + half - 1] = 255; M1[(size_t)rowlen * 2 * mbeg + 1 + half] = 255;
+	x = y = mbeg;
+	for(i=x+y;;i++){
+		const uint8_t *pu = M0 + (size_t)rowlen * i + 1, *pv = M1 + (size_t)rowlen * i + 1;
+		uint8_t *nu = M0 + (size_t)rowlen * (i + 1) + 1, *nv = M1 + (size_t)rowlen * (i + 1) + 1;
+		dir = i & 1;
+		/* on this diagonal cell c is (x - half + c, y + half - c): both x and y of the band centre are the loop's (x, y) */
+		for(c=0;c<bw;c++){
+			int h = bso_remsa_score(seqs0, seqs1, mats0, mats1, mlen, x - half + c, y + half - c);
+			const int u = dir ? pu[c + 1] : pu[c], v = dir ? pv[c] : pv[c - 1];
+			if(h < u) h = u;
+			if(h < v) h = v;
+			nu[c] = (uint8_t)(h - v); nv[c] = (uint8_t)(h - u);   /* h >= u, v: the saturating subtraction never saturates */
+		}
+		if(dir){ nu[-1] = 255; nv[-1] = 0; nu[bw] = 0; nv[bw] = 0; }
+		else { nu[-1] = 0; nv[-1] = 0; nu[bw] = 0; nv[bw] = 255; }
+		if(dir) y++; else x++;
+		if(x >= mend) break;
+	}
+	/* the walk (bspoa.h:3962-4040) */
+	xi = yi = mend - 1; roff = rend;
+	while(xi >= 0 && yi >= 0){
+		int xx, h, e, f, s, mdir;
+		i = xi + yi;
+		if(i < mbeg + mbeg) break;
+		dir = mdir = i & 1;
+		xx = (xi - yi - mdir) / 2 + half;   /* C division, as in the reference */
+		if(xx < 0 || xx >= bw){ err |= BSO_ERR_RANGE; break; }
+		{
+			const uint8_t *pu = M0 + (size_t)rowlen * i + 1, *pv = M1 + (size_t)rowlen * i + 1, *nu = M0 + (size_t)rowlen * (i + 1) + 1;
+			h = bso_remsa_score(seqs0, seqs1, mats0, mats1, mlen, xi, yi);
+			if(dir){ e = pu[xx + 1]; f = pv[xx]; } else { e = pu[xx]; f = pv[xx - 1]; }
+			s = f + nu[xx];
+		}
+		if(s == f && !(xx == 0 && dir == 0)){ if(seqs0[xi] < 4) roff--; xi--; }
+		else if(s == e){ yi--; }
+		else if(s == h){
+			if(seqs0[xi] < 4){ roff--; if(roff >= 0 && roff < rend) match[roff] = yi; else err |= BSO_ERR_RANGE; }
+			scr += s; xi--; yi--;
+		} else { err |= BSO_ERR_LOOP; break; }
+	}
+	if(scr_out) *scr_out = scr;
+	return err;
+}
