@@ -434,6 +434,53 @@ def run_kmer_edit(ctx, ncores, pairs=1000000, qlen=300, ksz=13, steps=2, warmup=
     return out
 
 
+def run_remsa(ctx, ncores, njobs=1000, mlen=20000, bw=32, distinct=16, steps=2, warmup=2, cpu_seconds=5.0, check=4):
+    """SURVEY section 8 row f2 (first part): the DP + walk of remsa_pedit_rd_bspoacore (bspoa.h:3916-4045) for one re-alignment round of
+    `njobs` lock-step BSPOA objects (one read each; 15 kb reads give an MSA of ~20k columns; band editbw / 2 = 32 cells).  Synthetic inputs
+    in the reference's layout (bsalign_b200/synth_remsa.py; `distinct` different jobs, repeated).  Unit: GCUPS over the band cells of the
+    anti-diagonals.  CPU: the oracle's scalar port on all host cores (kind "port": the reference's SSE kernel cannot be called on its own)."""
+    import torch
+    import remsa_jobs as rj
+    from bsalign_b200 import api, synth_remsa
+    base = [synth_remsa.make_job(mlen, bw=bw, seed=7000 + k) for k in range(distinct)]
+    jobs = [base[k % distinct] for k in range(njobs)]
+    rb = api.RemsaBatch(jobs)
+    pin = lambda a: torch.from_numpy(a).pin_memory().numpy()
+    rb.arena = pin(rb.arena)
+    outbuf = (pin(np.zeros(max(rb.match_ints, 1), dtype=np.int32)), pin(np.zeros((njobs, 4), dtype=np.int32)))
+    walls, kern = [], []
+    for it in range(warmup + steps):
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        ms, res, _ = api.remsa_batch(ctx, rb, out=outbuf)
+        dt = time.perf_counter() - t0
+        tm = ctx.timing()
+        if it >= warmup:
+            walls.append(dt); kern.append(tm["forward_ms"])
+    cells = float(tm["cells"])
+    kms, wall = sum(kern) / len(kern), sum(walls) / len(walls)
+    out = {"workload": "c5r: one re-alignment round (remsa_pedit_rd_bspoacore) over %d lock-step MSA jobs, MSA of %d columns, band %d" % (njobs, mlen, bw),
+           "jobs": njobs, "unit": "GCUPS", "value": cells / (kms * 1e-3) / 1e9, "kernel_ms_per_step": kms, "e2e": cells / wall / 1e9, "e2e_ms_per_step": wall * 1e3,
+           "gpu_launches": 1, "h2d_bytes_per_step": int(tm["h2d_bytes"]), "d2h_bytes_per_step": int(tm["d2h_bytes"]), "matrix_bytes_per_step": int(tm["trace_bytes"]),
+           "steps": steps, "warmup": warmup}
+    ok = True
+    for k in range(min(check, distinct)):
+        _, _, omatch, oscr, oerr = rj.oracle_core(base[k])
+        ok = ok and oerr == 0 and np.array_equal(omatch, ms[k]) and int(res[k, 0]) == oscr and int(res[k, 1]) == 0
+    out["parity"] = {"checked": {"jobs": min(check, distinct), "against": "oracle (pinned to the instrumented reference)", "bit_exact": bool(ok)}}
+    if cpu_seconds:
+        import concurrent.futures as cf
+        m = 8 * max(ncores, 16)
+        t0 = time.perf_counter()
+        with cf.ThreadPoolExecutor(ncores) as ex:
+            list(ex.map(lambda k: rj.oracle_core(base[k % distinct])[3], range(m)))
+        dt = time.perf_counter() - t0
+        rate = cells / njobs * m / dt / 1e9
+        out["cpu"] = {"value": rate, "unit": "GCUPS", "cores": ncores, "kind": "port", "sample": "%d jobs, %d host threads, %.1f s (the oracle's scalar restatement)" % (m, ncores, dt)}
+        out["speedup_vs_cpu"] = out["value"] / rate
+    return out
+
+
 def load_peaks():
     try:
         return json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
@@ -821,6 +868,11 @@ def main():
             secondary["c4k"] = run_kmer_edit(ctx, ncores, cpu_seconds=0 if args.no_cpu_baseline else 5.0, check=min(args.check, 256))
         except Exception as e:
             secondary["c4k"] = {"error": repr(e)}
+        try:
+            ctx.trim()
+            secondary["c5r"] = run_remsa(ctx, ncores, cpu_seconds=0 if args.no_cpu_baseline else 5.0)
+        except Exception as e:
+            secondary["c5r"] = {"error": repr(e)}
     if rank == 0:
         line = {"metric": "GCUPS", "value": main_out["value"], "unit": "GCUPS (1e9 band cells/s)", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
                 "ms_per_step": main_out["ms_per_step"], "higher_is_better": True, "scaling": "strong" if world > 1 else "weak", "vs_baseline": None,

@@ -295,39 +295,49 @@ def pack_pairs(batch, idx, out_seqs=None, nthreads=8):
     return pb, nbytes
 
 
-def remsa_batch(ctx, jobs, want_matrices=False):
-    """bsb200_remsa_batch: the DP + walk of remsa_pedit_rd_bspoacore (bspoa.h:3916) for a batch of jobs.  A job has mlen, bw, mbeg, mend,
-    rdlen and the reference's arrays seqs0, seqs1 (sz1 bytes each, bw / 2 bytes of padding in front) and mats (2, 4, sz1).
-    Returns (list of match arrays, out[n, 4] = score / status / matched / 0, list of (M0, M1) or None)."""
-    n = len(jobs)
-    hdr = np.zeros((n, 8), dtype=np.int32)
-    blocks, in_off, match_off, mat_off = [], np.zeros(n, np.uint64), np.zeros(n, np.uint64), np.zeros(n, np.uint64)
-    o = mo = xo = 0
-    for k, j in enumerate(jobs):
-        hdr[k, :5] = (j.mlen, j.bw, j.mbeg, j.mend, j.rdlen)
-        blk = np.concatenate([j.seqs0, j.seqs1, j.mats.reshape(-1)]).astype(np.uint8)
-        in_off[k] = o; o += (len(blk) + 15) // 16 * 16
-        blocks.append(blk)
-        match_off[k] = mo; mo += j.rdlen
-        mat_off[k] = xo; xo += 2 * (2 * j.mlen + 1) * (j.bw + 2)
-    arena = np.zeros(max(o, 1), dtype=np.uint8)
-    for k, blk in enumerate(blocks):
-        arena[int(in_off[k]):int(in_off[k]) + len(blk)] = blk
-    match = np.zeros(max(mo, 1), dtype=np.int32)
-    out = np.zeros((n, 4), dtype=np.int32)
-    mats = np.zeros(max(xo, 1), dtype=np.uint8) if want_matrices else None
-    rc = ctx._lib.bsb200_remsa_batch(ctx._h, n, _ptr(hdr), _ptr(arena), _ptr(in_off), int(o), _ptr(match), _ptr(match_off), int(mo), _ptr(out),
-                                     _ptr(mats), _ptr(mat_off) if want_matrices else None)
+class RemsaBatch:
+    """The arenas of bsb200_remsa_batch for a list of jobs (mlen, bw, mbeg, mend, rdlen, seqs0, seqs1 of sz1 bytes with bw / 2 bytes of
+    padding in front, mats (2, 4, sz1)): the ten arrays of a job back to back, the reference's own layout (bspoa.h:4209-4229)."""
+
+    def __init__(self, jobs):
+        n = len(jobs)
+        self.jobs, self.n = jobs, n
+        self.hdr = np.zeros((n, 8), dtype=np.int32)
+        self.in_off, self.match_off, self.mat_off = np.zeros(n, np.uint64), np.zeros(n, np.uint64), np.zeros(n, np.uint64)
+        o = mo = xo = 0
+        for k, j in enumerate(jobs):
+            self.hdr[k, :5] = (j.mlen, j.bw, j.mbeg, j.mend, j.rdlen)
+            self.in_off[k] = o; o += (10 * len(j.seqs0) + 15) // 16 * 16
+            self.match_off[k] = mo; mo += j.rdlen
+            self.mat_off[k] = xo; xo += 2 * (2 * j.mlen + 1) * (j.bw + 2)
+        self.in_bytes, self.match_ints, self.mat_bytes = o, mo, xo
+        self.arena = np.zeros(max(o, 1), dtype=np.uint8)
+        for k, j in enumerate(jobs):
+            b0, sz1 = int(self.in_off[k]), len(j.seqs0)
+            self.arena[b0:b0 + sz1] = j.seqs0
+            self.arena[b0 + sz1:b0 + 2 * sz1] = j.seqs1
+            self.arena[b0 + 2 * sz1:b0 + 10 * sz1] = j.mats.reshape(-1)
+
+
+def remsa_batch(ctx, jobs, want_matrices=False, out=None):
+    """bsb200_remsa_batch: the DP + walk of remsa_pedit_rd_bspoacore (bspoa.h:3916) for a batch of jobs (a list, or a RemsaBatch).
+    Returns (list of match arrays, out[n, 4] = score / status / matched / 0, list of (M0, M1) or None).  out: optional (match, out) arrays."""
+    rb = jobs if isinstance(jobs, RemsaBatch) else RemsaBatch(jobs)
+    n = rb.n
+    match, res = out if out is not None else (np.zeros(max(rb.match_ints, 1), dtype=np.int32), np.zeros((n, 4), dtype=np.int32))
+    mats = np.zeros(max(rb.mat_bytes, 1), dtype=np.uint8) if want_matrices else None
+    rc = ctx._lib.bsb200_remsa_batch(ctx._h, n, _ptr(rb.hdr), _ptr(rb.arena), _ptr(rb.in_off), int(rb.in_bytes), _ptr(match), _ptr(rb.match_off),
+                                     int(rb.match_ints), _ptr(res), _ptr(mats), _ptr(rb.mat_off) if want_matrices else None)
     ctx._check(rc, "bsb200_remsa_batch")
-    ms = [match[int(match_off[k]):int(match_off[k]) + jobs[k].rdlen].copy() for k in range(n)]
+    ms = [match[int(rb.match_off[k]):int(rb.match_off[k]) + rb.jobs[k].rdlen] for k in range(n)]
     mm = None
     if want_matrices:
         mm = []
-        for k, j in enumerate(jobs):
+        for k, j in enumerate(rb.jobs):
             szm = (2 * j.mlen + 1) * (j.bw + 2)
-            b0 = int(mat_off[k])
+            b0 = int(rb.mat_off[k])
             mm.append((mats[b0:b0 + szm], mats[b0 + szm:b0 + 2 * szm]))
-    return ms, out, mm
+    return ms, res, mm
 
 
 def pack_pairs_dev(ctx, d_src_ptr, batch, idx, d_dst_ptr):

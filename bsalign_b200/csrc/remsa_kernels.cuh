@@ -10,7 +10,9 @@
 // One WARP per job.  bw = 32 (the default: editbw / 2) is one cell per lane: the previous diagonal stays in registers, a cell's upper
 // and left neighbours are one shuffle each, and the read / consensus / profile bytes of a cell slide along the lanes (one new byte per
 // diagonal comes from memory, the other 31 from the neighbour lane).  Other widths keep two diagonals in shared memory.  Every diagonal
-// is stored once (the walk needs it), the walk is lane 0: a chain of dependent byte lookups.
+// is stored once (the walk needs it), the forward sweep leaves the step the
+// walk takes from every cell as 2 bits (one 64-bit word per diagonal at bw = 32; the reference's two byte matrices are only written for
+// checks), the walk is lane 0: a chain of dependent lookups in that small array.
 #pragma once
 #include "common.cuh"
 #include <stdint.h>
@@ -22,8 +24,10 @@ struct RemsaArgs {
 	const int32_t *hdr;        // per job 8 ints: mlen, bw, mbeg, mend, rend (read positions), 0, 0, 0
 	const uint8_t *in;         // input blocks
 	const uint64_t *in_off;    // per job byte offset of its block
-	uint8_t *mat;              // per job two matrices of (2 * mlen + 1) * (bw + 2) bytes, back to back
+	uint8_t *mat;              // FULL only: per job two matrices of (2 * mlen + 1) * (bw + 2) bytes, back to back
 	const uint64_t *mat_off;
+	uint64_t *codes;           // per job (2 * mlen + 1) rows of ceil(bw / 32) words: the step the walk takes from every cell (2 bits per cell)
+	const uint64_t *code_off;  // in words
 	int32_t *match;            // per job rend ints: the MSA column a read position is matched to, or -1
 	const uint64_t *match_off;
 	int32_t *out;              // per job 4 ints: score of the walk, status, matched positions, 0
@@ -38,6 +42,11 @@ __device__ __forceinline__ int remsa_score(const uint8_t *seqs0, const uint8_t *
 constexpr int kRemsaWarps = 4;          // jobs per CTA
 constexpr int kRemsaMaxBw = 256;        // widest band of the shared-memory path
 
+// FULL: also store the two difference matrices of the reference (checks); the walk itself reads the 2-bit step codes the forward sweep
+// leaves per cell: 1 = the read position has no partner (x - 1), 2 = the column has none (y - 1), 3 = matched (x - 1, y - 1).  With
+// s = H(cell) the reference's tests are s == f (H came from the left), s == e (from above), s == h (the cell's own score), in that order
+// (bspoa.h:3998-4030); H = max(h, u, v), so one of them always holds.
+template<bool FULL>
 __global__ void __launch_bounds__(kRemsaWarps * 32) remsa_kernel(const RemsaArgs a){
 	__shared__ uint8_t rowbuf[kRemsaWarps][2][2][kRemsaMaxBw + 2];   // [warp][matrix][parity][border + cells + border]
 	const uint32_t lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
@@ -49,13 +58,15 @@ __global__ void __launch_bounds__(kRemsaWarps * 32) remsa_kernel(const RemsaArgs
 	const uint32_t sz1 = (uint32_t)((mlen + bw + 15) / 16 * 16);
 	const uint8_t *blk = a.in + a.in_off[job];
 	const uint8_t *seqs0 = blk + half, *seqs1 = blk + sz1 + half, *mats0 = blk + 2 * (size_t)sz1 + half, *mats1 = blk + 6 * (size_t)sz1 + half;
-	uint8_t *M0 = a.mat + a.mat_off[job], *M1 = M0 + (size_t)(2 * mlen + 1) * rowlen;
+	uint8_t *M0 = FULL ? a.mat + a.mat_off[job] : nullptr, *M1 = FULL ? M0 + (size_t)(2 * mlen + 1) * rowlen : nullptr;
+	const int CW = (bw + 31) / 32;
+	uint64_t *codes = a.codes + a.code_off[job];
 	int32_t *match = a.match + a.match_off[job];
 	int32_t *out = a.out + (size_t)job * 4;
 	for(int c=lane;c<rend;c+=32) match[c] = -1;
 	if(bw > kRemsaMaxBw || bw < 2 || (bw & 1) || mend <= mbeg || mbeg < 0 || mend > mlen){ if(lane == 0){ out[0] = 0; out[1] = 1; out[2] = 0; out[3] = 0; } return; }
 	// ---- forward: diagonals 2 * mbeg .. 2 * mend - 2, row i + 1 of the matrices from row i (bspoa.h:3749-3758, 3856-3896, 3925-3934) ----
-	{
+	if(FULL){
 		uint8_t *r0 = M0 + (size_t)rowlen * 2 * mbeg, *r1 = M1 + (size_t)rowlen * 2 * mbeg;
 		for(int c=lane;c<rowlen;c+=32){ r0[c] = (c == 1 + half - 1) ? 255 : 0; r1[c] = (c == 1 + half) ? 255 : 0; }
 	}
@@ -73,10 +84,17 @@ __global__ void __launch_bounds__(kRemsaWarps * 32) remsa_kernel(const RemsaArgs
 			int h = h0 < u ? u : h0;
 			if(h < v) h = v;
 			pu = h - v; pv = h - u;
-			uint8_t *nu = M0 + (size_t)rowlen * (i + 1) + 1, *nv = M1 + (size_t)rowlen * (i + 1) + 1;
-			nu[lane] = (uint8_t)pu; nv[lane] = (uint8_t)pv;
+			{
+				const int t = (h == v && !(lane == 0 && dir == 0)) ? 1 : (h == u ? 2 : 3);
+				const uint32_t lo = __ballot_sync(0xffffffffu, t & 1), hi = __ballot_sync(0xffffffffu, t & 2);
+				if(lane == 0) codes[(size_t)(i + 1)] = (uint64_t)lo | ((uint64_t)hi << 32);
+			}
 			if(dir){ bl_u = 255; bl_v = 0; br_u = 0; br_v = 0; } else { bl_u = 0; bl_v = 0; br_u = 0; br_v = 255; }
-			if(lane == 0){ nu[-1] = (uint8_t)bl_u; nv[-1] = (uint8_t)bl_v; nu[bw] = (uint8_t)br_u; nv[bw] = (uint8_t)br_v; }
+			if(FULL){
+				uint8_t *nu = M0 + (size_t)rowlen * (i + 1) + 1, *nv = M1 + (size_t)rowlen * (i + 1) + 1;
+				nu[lane] = (uint8_t)pu; nv[lane] = (uint8_t)pv;
+				if(lane == 0){ nu[-1] = (uint8_t)bl_u; nv[-1] = (uint8_t)bl_v; nu[bw] = (uint8_t)br_u; nv[bw] = (uint8_t)br_v; }
+			}
 			if(dir) y++; else x++;
 			if(x >= mend) break;
 		}
@@ -90,19 +108,26 @@ __global__ void __launch_bounds__(kRemsaWarps * 32) remsa_kernel(const RemsaArgs
 			const int dir = i & 1;
 			const uint8_t *pu = rb[0][par] + 1, *pv = rb[1][par] + 1;
 			uint8_t *qu = rb[0][par ^ 1] + 1, *qv = rb[1][par ^ 1] + 1;
-			uint8_t *nu = M0 + (size_t)rowlen * (i + 1) + 1, *nv = M1 + (size_t)rowlen * (i + 1) + 1;
-			for(int c=lane;c<bw;c+=32){
-				int h = remsa_score(seqs0, seqs1, mats0, mats1, sz1, mlen, x - half + c, y + half - c);
-				const int u = dir ? pu[c + 1] : pu[c], v = dir ? pv[c] : pv[c - 1];
-				if(h < u) h = u;
-				if(h < v) h = v;
-				qu[c] = (uint8_t)(h - v); qv[c] = (uint8_t)(h - u);
-				nu[c] = (uint8_t)(h - v); nv[c] = (uint8_t)(h - u);
+			uint8_t *nu = FULL ? M0 + (size_t)rowlen * (i + 1) + 1 : nullptr, *nv = FULL ? M1 + (size_t)rowlen * (i + 1) + 1 : nullptr;
+			for(int c0=0;c0<bw;c0+=32){
+				const int c = c0 + (int)lane;
+				int t = 0;
+				if(c < bw){
+					int h = remsa_score(seqs0, seqs1, mats0, mats1, sz1, mlen, x - half + c, y + half - c);
+					const int u = dir ? pu[c + 1] : pu[c], v = dir ? pv[c] : pv[c - 1];
+					if(h < u) h = u;
+					if(h < v) h = v;
+					qu[c] = (uint8_t)(h - v); qv[c] = (uint8_t)(h - u);
+					if(FULL){ nu[c] = (uint8_t)(h - v); nv[c] = (uint8_t)(h - u); }
+					t = (h == v && !(c == 0 && dir == 0)) ? 1 : (h == u ? 2 : 3);
+				}
+				const uint32_t lo = __ballot_sync(0xffffffffu, t & 1), hi = __ballot_sync(0xffffffffu, t & 2);
+				if(lane == 0) codes[(size_t)(i + 1) * CW + (c0 >> 5)] = (uint64_t)lo | ((uint64_t)hi << 32);
 			}
 			if(lane == 0){
 				const uint8_t lu = dir ? 255 : 0, rv = dir ? 0 : 255;
 				qu[-1] = lu; qv[-1] = 0; qu[bw] = 0; qv[bw] = rv;
-				nu[-1] = lu; nv[-1] = 0; nu[bw] = 0; nv[bw] = rv;
+				if(FULL){ nu[-1] = lu; nv[-1] = 0; nu[bw] = 0; nv[bw] = rv; }
 			}
 			__syncwarp();
 			if(dir) y++; else x++;
@@ -112,7 +137,7 @@ __global__ void __launch_bounds__(kRemsaWarps * 32) remsa_kernel(const RemsaArgs
 	__threadfence_block();
 	__syncwarp();
 	if(lane) return;
-	// ---- the walk (bspoa.h:3962-4040): lane 0 ---------------------------------------------------------------------------------------
+	// ---- the walk (bspoa.h:3962-4040): lane 0, on the step codes ----------------------------------------------------------------------
 	int xi = mend - 1, yi = mend - 1, roff = rend, scr = 0, err = 0, nmatch = 0;
 	while(xi >= 0 && yi >= 0){
 		const int i = xi + yi;
@@ -120,16 +145,16 @@ __global__ void __launch_bounds__(kRemsaWarps * 32) remsa_kernel(const RemsaArgs
 		const int dir = i & 1;
 		const int xx = (xi - yi - dir) / 2 + half;
 		if(xx < 0 || xx >= bw){ err |= 1; break; }
-		const uint8_t *pu = M0 + (size_t)rowlen * i + 1, *pv = M1 + (size_t)rowlen * i + 1, *nu = M0 + (size_t)rowlen * (i + 1) + 1;
-		const int h = remsa_score(seqs0, seqs1, mats0, mats1, sz1, mlen, xi, yi);
-		const int e = dir ? pu[xx + 1] : pu[xx], f = dir ? pv[xx] : pv[xx - 1];
-		const int s = f + nu[xx];
-		if(s == f && !(xx == 0 && dir == 0)){ if(seqs0[xi] < 4) roff--; xi--; }
-		else if(s == e){ yi--; }
-		else if(s == h){
-			if(seqs0[xi] < 4){ roff--; if(roff >= 0 && roff < rend){ match[roff] = yi; nmatch++; } else err |= 1; }
-			scr += s; xi--; yi--;
-		} else { err |= 2; break; }   // the reference aborts here ("something wrong"): never seen on its own inputs
+		const uint64_t wcode = codes[(size_t)(i + 1) * CW + (xx >> 5)];
+		const int t = (int)((wcode >> (xx & 31)) & 1) | ((int)((wcode >> (32 + (xx & 31))) & 1) << 1);
+		const int s0 = seqs0[xi];
+		if(t == 1){ if(s0 < 4) roff--; xi--; }
+		else if(t == 2){ yi--; }
+		else if(t == 3){
+			if(s0 < 4){ roff--; if(roff >= 0 && roff < rend){ match[roff] = yi; nmatch++; } else err |= 1; }
+			scr += remsa_score(seqs0, seqs1, mats0, mats1, sz1, mlen, xi, yi);   // H of a matched cell is its own score
+			xi--; yi--;
+		} else { err |= 2; break; }
 	}
 	out[0] = scr; out[1] = err; out[2] = nmatch; out[3] = 0;
 }

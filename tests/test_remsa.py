@@ -53,3 +53,24 @@ def test_gpu_remsa_matches_reference_records_and_oracle():
             assert np.array_equal(ms2[k], ms[k % len(jobs)]) and np.array_equal(out2[k], out[k % len(jobs)])
     finally:
         ctx.close()
+
+
+@pytest.mark.gpu
+def test_gpu_remsa_on_full_shape_synthetic_jobs():
+    """MSAs of 20k columns (15 kb reads, BASELINE configs[4]'s shape) and other bands: synthetic inputs in the reference's layout
+    (bsalign_b200/synth_remsa.py), CUDA against the oracle: matrices, matched columns, score."""
+    from bsalign_b200 import api, synth_remsa
+    ctx = api.Context(0)
+    try:
+        jobs = [synth_remsa.make_job(20000, bw=32, seed=1), synth_remsa.make_job(5000, bw=64, seed=2), synth_remsa.make_job(3000, bw=16, seed=3),
+                synth_remsa.make_job(777, bw=48, seed=4), synth_remsa.make_job(9000, bw=32, seed=5, p_err=0.2)]
+        ms, out, mm = api.remsa_batch(ctx, jobs, want_matrices=True)
+        for k, j in enumerate(jobs):
+            M0, M1, match, scr, err = rj.oracle_core(j)
+            rl = j.bw + 2
+            lo, hi = rl * 2 * j.mbeg, rl * 2 * j.mend
+            assert err == 0 and out[k, 1] == 0 and int(out[k, 0]) == scr, (k, out[k], scr)
+            assert np.array_equal(mm[k][0][lo:hi], M0[lo:hi]) and np.array_equal(mm[k][1][lo:hi], M1[lo:hi]), k
+            assert np.array_equal(ms[k], match), k
+    finally:
+        ctx.close()
