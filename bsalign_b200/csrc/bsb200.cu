@@ -1413,11 +1413,11 @@ extern "C" int bsb200_remsa_batch(bsb200_ctx *ctx, uint32_t njobs, const int32_t
 		const int32_t *h = hdr + (size_t)j * 8;
 		if(h[0] <= 0 || h[1] <= 0 || h[4] < 0) return fail(ctx, "bsb200_remsa_batch: bad job header", cudaSuccess);
 		moff[j + 1] = moff[j] + (full ? ((2ull * ((uint64_t)(2 * h[0] + 1) * (uint64_t)(h[1] + 2)) + 127) / 128 * 128) : 0);
-		coff[j + 1] = coff[j] + (((uint64_t)(2 * h[0] + 1) * (uint64_t)((h[1] + 31) / 32) + 15) / 16 * 16);   // words
+		coff[j + 1] = coff[j] + (((uint64_t)(2 * h[0] + 1) * (uint64_t)((h[1] + 31) / 32) + 7) / 8 * 8);   // 16-byte records
 	}
 	DevBuf *c = ctx->remsa_cache;
-	CK(c[0].reserve(in_bytes + 16)); CK(c[1].reserve((size_t)njobs * 32)); CK(c[2].reserve((size_t)njobs * 8 + 8)); CK(c[3].reserve(moff[njobs] + coff[njobs] * 8 + 256, true));
-	CK(c[5].reserve(match_ints * 4 + 16)); CK(c[6].reserve((size_t)njobs * 8 + 8)); CK(c[7].reserve((size_t)njobs * 16));
+	CK(c[0].reserve(in_bytes + 16)); CK(c[1].reserve((size_t)njobs * 32)); CK(c[2].reserve((size_t)njobs * 8 + 8)); CK(c[3].reserve(moff[njobs] + coff[njobs] * 16 + 256, true));
+	CK(c[5].reserve(match_ints * 8 + 32)); CK(c[6].reserve((size_t)njobs * 8 + 8)); CK(c[7].reserve((size_t)njobs * 16));
 	cudaEventRecord(ctx->ev[0], st);
 	CK(h2d_copy(ctx, c[0].p, in, in_bytes, st));
 	CK(cudaMemcpyAsync(c[1].p, hdr, (size_t)njobs * 32, cudaMemcpyHostToDevice, st));
@@ -1429,8 +1429,8 @@ extern "C" int bsb200_remsa_batch(bsb200_ctx *ctx, uint32_t njobs, const int32_t
 	cudaEventRecord(ctx->ev[1], st);
 	RemsaArgs a;
 	a.njobs = njobs; a.hdr = c[1].as<int32_t>(); a.in = c[0].as<uint8_t>(); a.in_off = c[2].as<uint64_t>();
-	a.mat = c[3].as<uint8_t>(); a.mat_off = c[4].as<uint64_t>(); a.codes = (uint64_t*)(c[3].as<uint8_t>() + (moff[njobs] + 127) / 128 * 128); a.code_off = c[4].as<uint64_t>() + njobs;
-	a.match = c[5].as<int32_t>(); a.match_off = c[6].as<uint64_t>(); a.out = c[7].as<int32_t>();
+	a.mat = c[3].as<uint8_t>(); a.mat_off = c[4].as<uint64_t>(); a.codes = (uint4*)(c[3].as<uint8_t>() + (moff[njobs] + 127) / 128 * 128); a.code_off = c[4].as<uint64_t>() + njobs;
+	a.match = c[5].as<int32_t>(); a.xs = c[5].as<int32_t>() + match_ints + 4; a.match_off = c[6].as<uint64_t>(); a.out = c[7].as<int32_t>();
 	if(full) remsa_kernel<true><<<(njobs + kRemsaWarps - 1) / kRemsaWarps, kRemsaWarps * 32, 0, st>>>(a);
 	else remsa_kernel<false><<<(njobs + kRemsaWarps - 1) / kRemsaWarps, kRemsaWarps * 32, 0, st>>>(a);
 	CK(cudaGetLastError());
@@ -1451,7 +1451,7 @@ extern "C" int bsb200_remsa_batch(bsb200_ctx *ctx, uint32_t njobs, const int32_t
 	ctx->timing.h2d_ms = m0; ctx->timing.forward_ms = m1; ctx->timing.run_ms = m1; ctx->timing.d2h_ms = m2; ctx->timing.total_ms = m0 + m1 + m2;
 	ctx->timing.forward_launches = 1; ctx->timing.h2d_bytes = in_bytes + (uint64_t)njobs * 56; ctx->timing.d2h_bytes = match_ints * 4 + (uint64_t)njobs * 16;
 	{ uint64_t cells = 0; for(uint32_t j=0;j<njobs;j++){ const int32_t *h = hdr + (size_t)j * 8; cells += (uint64_t)h[1] * (2ull * (uint64_t)(h[3] - h[2])); } ctx->timing.cells = cells; }
-	ctx->timing.trace_bytes = moff[njobs] + coff[njobs] * 8;
+	ctx->timing.trace_bytes = moff[njobs] + coff[njobs] * 16;
 	return 0;
 }
 

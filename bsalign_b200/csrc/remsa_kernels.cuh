@@ -26,8 +26,9 @@ struct RemsaArgs {
 	const uint64_t *in_off;    // per job byte offset of its block
 	uint8_t *mat;              // FULL only: per job two matrices of (2 * mlen + 1) * (bw + 2) bytes, back to back
 	const uint64_t *mat_off;
-	uint64_t *codes;           // per job (2 * mlen + 1) rows of ceil(bw / 32) words: the step the walk takes from every cell (2 bits per cell)
-	const uint64_t *code_off;  // in words
+	uint4 *codes;              // per job (2 * mlen + 1) rows of ceil(bw / 32) records: four bits per cell (see remsa_kernel)
+	const uint64_t *code_off;  // in records
+	int32_t *xs;               // scratch, laid out like match: the MSA position of every matched read position
 	int32_t *match;            // per job rend ints: the MSA column a read position is matched to, or -1
 	const uint64_t *match_off;
 	int32_t *out;              // per job 4 ints: score of the walk, status, matched positions, 0
@@ -42,8 +43,8 @@ __device__ __forceinline__ int remsa_score(const uint8_t *seqs0, const uint8_t *
 constexpr int kRemsaWarps = 4;          // jobs per CTA
 constexpr int kRemsaMaxBw = 256;        // widest band of the shared-memory path
 
-// FULL: also store the two difference matrices of the reference (checks); the walk itself reads the 2-bit step codes the forward sweep
-// leaves per cell: 1 = the read position has no partner (x - 1), 2 = the column has none (y - 1), 3 = matched (x - 1, y - 1).  With
+// FULL: also store the two difference matrices of the reference (checks); the walk itself reads the bits the forward sweep leaves per
+// cell, among them the step: 1 = the read position has no partner (x - 1), 2 = the column has none (y - 1), 3 = matched (x - 1, y - 1).  With
 // s = H(cell) the reference's tests are s == f (H came from the left), s == e (from above), s == h (the cell's own score), in that order
 // (bspoa.h:3998-4030); H = max(h, u, v), so one of them always holds.
 template<bool FULL>
@@ -60,7 +61,8 @@ __global__ void __launch_bounds__(kRemsaWarps * 32) remsa_kernel(const RemsaArgs
 	const uint8_t *seqs0 = blk + half, *seqs1 = blk + sz1 + half, *mats0 = blk + 2 * (size_t)sz1 + half, *mats1 = blk + 6 * (size_t)sz1 + half;
 	uint8_t *M0 = FULL ? a.mat + a.mat_off[job] : nullptr, *M1 = FULL ? M0 + (size_t)(2 * mlen + 1) * rowlen : nullptr;
 	const int CW = (bw + 31) / 32;
-	uint64_t *codes = a.codes + a.code_off[job];
+	uint4 *codes = a.codes + a.code_off[job];
+	int32_t *xs = a.xs + a.match_off[job];
 	int32_t *match = a.match + a.match_off[job];
 	int32_t *out = a.out + (size_t)job * 4;
 	for(int c=lane;c<rend;c+=32) match[c] = -1;
@@ -87,7 +89,8 @@ __global__ void __launch_bounds__(kRemsaWarps * 32) remsa_kernel(const RemsaArgs
 			{
 				const int t = (h == v && !(lane == 0 && dir == 0)) ? 1 : (h == u ? 2 : 3);
 				const uint32_t lo = __ballot_sync(0xffffffffu, t & 1), hi = __ballot_sync(0xffffffffu, t & 2);
-				if(lane == 0) codes[(size_t)(i + 1)] = (uint64_t)lo | ((uint64_t)hi << 32);
+				const uint32_t nz = __ballot_sync(0xffffffffu, seqs0[x - half + (int)lane] < 4), hn = __ballot_sync(0xffffffffu, h0 != 0);
+				if(lane == 0) codes[(size_t)(i + 1)] = make_uint4(lo, hi, nz, hn);
 			}
 			if(dir){ bl_u = 255; bl_v = 0; br_u = 0; br_v = 0; } else { bl_u = 0; bl_v = 0; br_u = 0; br_v = 255; }
 			if(FULL){
@@ -111,9 +114,10 @@ __global__ void __launch_bounds__(kRemsaWarps * 32) remsa_kernel(const RemsaArgs
 			uint8_t *nu = FULL ? M0 + (size_t)rowlen * (i + 1) + 1 : nullptr, *nv = FULL ? M1 + (size_t)rowlen * (i + 1) + 1 : nullptr;
 			for(int c0=0;c0<bw;c0+=32){
 				const int c = c0 + (int)lane;
-				int t = 0;
+				int t = 0; bool cnz = false, chn = false;
 				if(c < bw){
 					int h = remsa_score(seqs0, seqs1, mats0, mats1, sz1, mlen, x - half + c, y + half - c);
+					cnz = seqs0[x - half + c] < 4; chn = h != 0;
 					const int u = dir ? pu[c + 1] : pu[c], v = dir ? pv[c] : pv[c - 1];
 					if(h < u) h = u;
 					if(h < v) h = v;
@@ -122,7 +126,8 @@ __global__ void __launch_bounds__(kRemsaWarps * 32) remsa_kernel(const RemsaArgs
 					t = (h == v && !(c == 0 && dir == 0)) ? 1 : (h == u ? 2 : 3);
 				}
 				const uint32_t lo = __ballot_sync(0xffffffffu, t & 1), hi = __ballot_sync(0xffffffffu, t & 2);
-				if(lane == 0) codes[(size_t)(i + 1) * CW + (c0 >> 5)] = (uint64_t)lo | ((uint64_t)hi << 32);
+				const uint32_t nz = __ballot_sync(0xffffffffu, cnz), hn = __ballot_sync(0xffffffffu, chn);
+				if(lane == 0) codes[(size_t)(i + 1) * CW + (c0 >> 5)] = make_uint4(lo, hi, nz, hn);
 			}
 			if(lane == 0){
 				const uint8_t lu = dir ? 255 : 0, rv = dir ? 0 : 255;
@@ -136,27 +141,39 @@ __global__ void __launch_bounds__(kRemsaWarps * 32) remsa_kernel(const RemsaArgs
 	}
 	__threadfence_block();
 	__syncwarp();
-	if(lane) return;
-	// ---- the walk (bspoa.h:3962-4040): lane 0, on the step codes ----------------------------------------------------------------------
-	int xi = mend - 1, yi = mend - 1, roff = rend, scr = 0, err = 0, nmatch = 0;
-	while(xi >= 0 && yi >= 0){
-		const int i = xi + yi;
-		if(i < mbeg + mbeg) break;
-		const int dir = i & 1;
-		const int xx = (xi - yi - dir) / 2 + half;
-		if(xx < 0 || xx >= bw){ err |= 1; break; }
-		const uint64_t wcode = codes[(size_t)(i + 1) * CW + (xx >> 5)];
-		const int t = (int)((wcode >> (xx & 31)) & 1) | ((int)((wcode >> (32 + (xx & 31))) & 1) << 1);
-		const int s0 = seqs0[xi];
-		if(t == 1){ if(s0 < 4) roff--; xi--; }
-		else if(t == 2){ yi--; }
-		else if(t == 3){
-			if(s0 < 4){ roff--; if(roff >= 0 && roff < rend){ match[roff] = yi; nmatch++; } else err |= 1; }
-			scr += remsa_score(seqs0, seqs1, mats0, mats1, sz1, mlen, xi, yi);   // H of a matched cell is its own score
-			xi--; yi--;
-		} else { err |= 2; break; }
+	// ---- the walk (bspoa.h:3962-4040): lane 0, on the four bits the sweep left per cell: step (2 bits: 1 = x - 1, 2 = y - 1, 3 = both),
+	// "the read has a base in this column", "the cell's own score is not zero".  The score of the walk is the sum of the matched cells'
+	// scores: those of matched read positions are added up by the whole warp afterwards, the others (no read base there: zero on the
+	// reference's own inputs) on the spot.
+	int scr = 0, err = 0, nmatch = 0;
+	if(lane == 0 && !(hd[5] & 1)){   // (hdr[5] bit 0: skip the walk - a development aid for timing the sweep alone)
+		int xi = mend - 1, yi = mend - 1, roff = rend;
+		while(xi >= 0 && yi >= 0){
+			const int i = xi + yi;
+			if(i < mbeg + mbeg) break;
+			const int dir = i & 1;
+			const int xx = (xi - yi - dir) / 2 + half;
+			if(xx < 0 || xx >= bw){ err |= 1; break; }
+			const uint4 wc = codes[(size_t)(i + 1) * CW + (xx >> 5)];
+			// the walk only moves down the diagonals: ask for the records it reaches ~48 diagonals from now
+			if(i > mbeg + mbeg + 48) asm volatile("prefetch.global.L1 [%0];" :: "l"(codes + (size_t)(i + 1 - 48) * CW + (xx >> 5)));
+			const uint32_t bit = 1u << (xx & 31);
+			const int t = ((wc.x & bit) ? 1 : 0) | ((wc.y & bit) ? 2 : 0);
+			const bool nz = (wc.z & bit) != 0;
+			if(t == 1){ if(nz) roff--; xi--; }
+			else if(t == 2){ yi--; }
+			else if(t == 3){
+				if(nz){ roff--; if(roff >= 0 && roff < rend){ match[roff] = yi; xs[roff] = xi; nmatch++; } else err |= 1; }
+				else if(wc.w & bit) scr += remsa_score(seqs0, seqs1, mats0, mats1, sz1, mlen, xi, yi);
+				xi--; yi--;
+			} else { err |= 2; break; }
+		}
 	}
-	out[0] = scr; out[1] = err; out[2] = nmatch; out[3] = 0;
+	__threadfence_block();
+	__syncwarp();
+	for(int r=lane;r<rend;r+=32){ const int yj = match[r]; if(yj >= 0) scr += remsa_score(seqs0, seqs1, mats0, mats1, sz1, mlen, xs[r], yj); }
+	for(int o=16;o;o>>=1) scr += __shfl_xor_sync(0xffffffffu, scr, o);
+	if(lane == 0){ out[0] = scr; out[1] = err; out[2] = nmatch; out[3] = 0; }
 }
 
 } // namespace bsb200
