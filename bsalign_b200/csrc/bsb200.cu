@@ -1431,6 +1431,7 @@ extern "C" int bsb200_remsa_batch(bsb200_ctx *ctx, uint32_t njobs, const int32_t
 	a.njobs = njobs; a.hdr = c[1].as<int32_t>(); a.in = c[0].as<uint8_t>(); a.in_off = c[2].as<uint64_t>();
 	a.mat = c[3].as<uint8_t>(); a.mat_off = c[4].as<uint64_t>(); a.codes = (uint4*)(c[3].as<uint8_t>() + (moff[njobs] + 127) / 128 * 128); a.code_off = c[4].as<uint64_t>() + njobs;
 	a.match = c[5].as<int32_t>(); a.xs = c[5].as<int32_t>() + match_ints + 4; a.match_off = c[6].as<uint64_t>(); a.out = c[7].as<int32_t>();
+	if(full) CK(cudaMemsetAsync(c[3].p, 0, moff[njobs], st));   // rows outside a job's diagonals are never written (the reference's hold older calls' rows there)
 	if(full) remsa_kernel<true><<<(njobs + kRemsaWarps - 1) / kRemsaWarps, kRemsaWarps * 32, 0, st>>>(a);
 	else remsa_kernel<false><<<(njobs + kRemsaWarps - 1) / kRemsaWarps, kRemsaWarps * 32, 0, st>>>(a);
 	CK(cudaGetLastError());

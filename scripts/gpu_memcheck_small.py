@@ -1,5 +1,5 @@
 """Small inputs through the round-2 kernels, meant to run under `compute-sanitizer --tool memcheck` (development aid):
-k-mer guided edit (grouped and one pair per warp, with fallback pairs and a starved pool), device-side shard packing, the wavefront kernel."""
+k-mer guided edit (grouped and one pair per warp, with fallback pairs and a starved pool), device-side shard packing, the wavefront kernel, the re-alignment kernel."""
 import os
 import sys
 
@@ -61,5 +61,13 @@ for qlen, n in ((400, 64), (3000, 6)):
     ok = np.array_equal(got.results, e2) and all(np.array_equal(x, y) for x, y in zip(got.cigars(), c2))
     print("wave", qlen, "ok" if ok else "DIFFERS")
     bad += not ok
+# read re-alignment against the MSA profile: the reference's own records, with and without the byte matrices
+import remsa_jobs as rj  # noqa: E402
+jobs = rj.load_golden()[:12] + rj.load_golden()[-9:]
+ms, out, mm = api.remsa_batch(ctx, jobs, want_matrices=True)
+ms2, out2, _ = api.remsa_batch(ctx, jobs)
+ok = all(rj.compare(j, mm[k][0], mm[k][1], ms[k]) is None and np.array_equal(ms[k], ms2[k]) for k, j in enumerate(jobs)) and np.array_equal(out, out2) and not out[:, 1].any()
+print("remsa", "ok" if ok else "DIFFERS")
+bad += not ok
 ctx.close()
 sys.exit(1 if bad else 0)
