@@ -699,6 +699,15 @@ extern "C" bsb200_batch *bsb200_batch_upload_bits(bsb200_ctx *ctx, int kind, uin
 	return upload_impl(ctx, kind, n, nullptr, nullptr, bits, qoff, qlen, toff, tlen, mode, bandwidth, matrix, go1, ge1, go2, ge2, want_cigar);
 }
 
+// row store of the two-pass kernel: cp.async.bulk copies out of the shared-memory images (1) or the LDS.128 -> STG.128 loop (0).
+// Measured (profiles/ab_bulk_store_r2.txt): full bands (config 2 on this kernel, 1 KB images) 18.80 -> 17.33 ms with the bulk copies;
+// moving bands (config 3, 512-byte images, the copy has only the steering code to hide behind) 80.93 -> 81.14 ms.  Hence on for
+// full-band batches only; BSB200_BULK_STORE overrides (the A/B).
+static int bulk_store_default(bool full){
+	if(const char *ev = getenv("BSB200_BULK_STORE")) return atoi(ev) != 0;
+	return full ? 1 : 0;
+}
+
 template<int PW, bool FAST, bool ANCH>
 static int launch_epi8_forward(bsb200_ctx *ctx, Epi8Args a, uint32_t npairs, bool full){
 	// CTA shape: as many groups per SM as the shared memory allows.  Normally 128 threads = 4 warps x 4 groups; a wide band
@@ -915,6 +924,7 @@ extern "C" int bsb200_batch_run(bsb200_ctx *ctx, bsb200_batch *b){
 			}
 			// every band covers its whole query: bandwidth 0, or a bandwidth (rounded up to 16 by the kernel) no shorter than the longest query
 			const bool full = (b->bandwidth == 0 || (b->bandwidth + 15) / 16 * 16 >= b->max_qlen) && !getenv("BSB200_NOFULL");   // (BSB200_NOFULL: tests run the general instantiation on full bands too)
+			a.bulk_store = bulk_store_default(full);
 			if(fast) rc = anch ? launch_epi8_forward_pw<true, true>(ctx, a, np, b->pw, full) : launch_epi8_forward_pw<true, false>(ctx, a, np, b->pw, full);
 			else rc = anch ? launch_epi8_forward_pw<false, true>(ctx, a, np, b->pw, full) : launch_epi8_forward_pw<false, false>(ctx, a, np, b->pw, full);
 			if(rc) return rc;

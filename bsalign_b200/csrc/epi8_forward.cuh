@@ -46,7 +46,20 @@ struct Epi8Args {
 	uint32_t c256, c65536;       // 256 and 65536 at run time: byte packing / half-word shifts as IMAD on the FMA pipe (wavefront kernel)
 	int redo;                    // two-pass kernel: only take the pairs the wavefront kernel flagged (kStRedo)
 	int force_redo;              // wavefront kernel: flag every pair (test hook: exercises the redo path)
+	int bulk_store;              // two-pass kernel: finished row images leave shared memory as cp.async.bulk copies (BSB200_BULK_STORE)
 };
+
+// ---- bulk copy shared memory -> global memory (TMA unit, non-tensor form: SASS UBLKCP) ---------------------
+// Both addresses 16-byte aligned, bytes a multiple of 16.  The writes that filled the shared-memory image went through the generic
+// proxy: every writing thread issues bulk_fence() and the group synchronises before ONE thread issues the copy; that thread waits
+// with bulk_wait_read() (source read, not global visibility: the kernel boundary orders the traceback behind it) before anyone
+// overwrites the image.
+__device__ __forceinline__ void bulk_fence(){ asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void bulk_store_s2g(void *gdst, const void *ssrc, uint32_t bytes){
+	asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" :: "l"(gdst), "r"((uint32_t)__cvta_generic_to_shared(ssrc)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_commit(){ asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_read(){ asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
 
 // ---- saturating s16x2 arithmetic ------------------------------------------------------------------------
 constexpr uint32_t kLO = 0xff80ff80u, kHI = 0x007f007fu, kONE = 0x00010001u;
@@ -280,6 +293,11 @@ __global__ void __launch_bounds__(kFwdThreads, FULL ? 4 : 0) epi8_forward_kernel
 	#define QCODE(x) ((x) < qlen ? (uint32_t)qs[(x)] : 4u)
 
 	while(true){
+		if(a.bulk_store){
+			// the bulk copies of the previous row have read their images (they ran beside the steering and end-point code)
+			if(t <= PW) bulk_wait_read();
+			__syncwarp(gmask);
+		}
 		if(!have && !done){
 			uint32_t idx = 0;
 			if(t == 0) idx = atomicAdd(a.counter, 1u);
@@ -775,6 +793,12 @@ __global__ void __launch_bounds__(kFwdThreads, FULL ? 4 : 0) epi8_forward_kernel
 		if(have){
 			uint8_t *dst = tr + (size_t)RS * (row + 1);
 			const uint32_t nch = IB / 16; // 16-byte pieces per array image
+			if(a.bulk_store){
+				// one cp.async.bulk per array image (thread k: image k) instead of the LDS.128 -> STG.128 loop of the group
+				bulk_fence();
+				__syncwarp(gmask);
+				if(t <= PW){ bulk_store_s2g(dst + (size_t)IB * t, sU + (size_t)IMG * t, IB); bulk_commit(); }
+			} else
 			for(uint32_t c=t;c<nch;c+=kGroup){
 				*(uint4*)(dst + 16 * c) = *(const uint4*)(sU + 16 * c);
 				if(PW >= 1) *(uint4*)(dst + IB + 16 * c) = *(const uint4*)(sE + 16 * c);
