@@ -133,6 +133,44 @@ static inline void b200_poa_pack_job(b200_poa_pack_t *p, BSPOA *g, BSPOAPar *par
 	p->node_off[j + 1] = p->nnode; p->edge_off[j + 1] = p->nedge;
 }
 
+/* append the ONE job of q (packed by its object's host thread) to the batch p: plain copies, every index inside a job is local to it */
+static inline void b200_poa_pack_append(b200_poa_pack_t *p, const b200_poa_pack_t *q){
+	u4i j = p->njobs;
+	uint64_t nloc = q->nnode, ne = q->nedge, nre = q->nredge, dummy_cap;
+	if(j + 2 > p->cap_jobs){
+		uint32_t nc = (j + 2) * 2 + 14;
+		p->par = (int32_t*)realloc(p->par, sizeof(int32_t) * 10 * nc); p->qoff = (uint64_t*)realloc(p->qoff, 8 * (size_t)nc); p->slen = (uint32_t*)realloc(p->slen, 4 * (size_t)nc);
+		p->node_off = (uint64_t*)realloc(p->node_off, 8 * (size_t)nc); p->edge_off = (uint64_t*)realloc(p->edge_off, 8 * (size_t)nc);
+		p->head = (uint32_t*)realloc(p->head, 4 * (size_t)nc); p->tail = (uint32_t*)realloc(p->tail, 4 * (size_t)nc);
+		p->row_off = (uint64_t*)realloc(p->row_off, 8 * (size_t)nc); p->best = (int32_t*)realloc(p->best, 12 * (size_t)nc); p->status = (int32_t*)realloc(p->status, 4 * (size_t)nc);
+		p->redge_off = (uint64_t*)realloc(p->redge_off, 8 * (size_t)nc); p->trace = (int32_t*)realloc(p->trace, 32 * (size_t)nc);
+		p->cap_jobs = nc;
+	}
+	memcpy(p->par + 10 * (size_t)j, q->par, sizeof(int32_t) * 10);
+	p->qoff[j] = p->nq; p->slen[j] = q->slen[0]; p->head[j] = q->head[0]; p->tail[j] = q->tail[0];
+	B200_GROW(p->queries, p->cap_q, p->nq + q->nq + 16, uint8_t);
+	memcpy(p->queries + p->nq, q->queries, q->nq); p->nq += q->nq;
+	p->node_off[j] = p->nnode; p->edge_off[j] = p->nedge; p->redge_off[j] = p->nredge;
+	dummy_cap = p->cap_node; B200_GROW(p->base, dummy_cap, p->nnode + nloc, uint8_t);
+	dummy_cap = p->cap_node; B200_GROW(p->bonus, dummy_cap, p->nnode + nloc, uint8_t);
+	dummy_cap = p->cap_node; B200_GROW(p->rpos, dummy_cap, p->nnode + nloc, int32_t);
+	B200_GROW(p->nct, p->cap_node, p->nnode + nloc, int32_t);
+	memcpy(p->base + p->nnode, q->base, nloc); memcpy(p->bonus + p->nnode, q->bonus, nloc);
+	memcpy(p->rpos + p->nnode, q->rpos, sizeof(int32_t) * nloc); memcpy(p->nct + p->nnode, q->nct, sizeof(int32_t) * nloc);
+	B200_GROW(p->eoff, p->cap_eoff, p->neoff + nloc + 1, int32_t);
+	memcpy(p->eoff + p->neoff, q->eoff, sizeof(int32_t) * (nloc + 1));
+	B200_GROW(p->edst, p->cap_edge, p->nedge + ne + 1, int32_t);
+	memcpy(p->edst + p->nedge, q->edst, sizeof(int32_t) * ne);
+	B200_GROW(p->reoff, p->cap_reoff, p->nreoff + nloc + 1, int32_t);
+	memcpy(p->reoff + p->nreoff, q->reoff, sizeof(int32_t) * (nloc + 1));
+	dummy_cap = p->cap_redge; B200_GROW(p->resrc, dummy_cap, p->nredge + nre + 1, int32_t);
+	B200_GROW(p->recov, p->cap_redge, p->nredge + nre + 1, int32_t);
+	memcpy(p->resrc + p->nredge, q->resrc, sizeof(int32_t) * nre); memcpy(p->recov + p->nredge, q->recov, sizeof(int32_t) * nre);
+	p->nnode += nloc; p->neoff += nloc + 1; p->nreoff += nloc + 1; p->nedge += ne; p->nredge += nre;
+	p->njobs = j + 1;
+	p->node_off[j + 1] = p->nnode; p->edge_off[j + 1] = p->nedge; p->redge_off[j + 1] = p->nredge;
+}
+
 /* run every packed sweep on the GPU (one batch) */
 static inline void b200_poa_pack_run(bsb200_ctx *ctx, b200_poa_pack_t *p){
 	uint32_t j;
@@ -228,9 +266,11 @@ static inline int b200_align_rd_bspoacore(bsb200_ctx *ctx, BSPOA *g, BSPOAPar *p
  * b200_poa_host_threads sets how many host threads share it (one per in-flight object). */
 #include <pthread.h>
 #include <unistd.h>
+#include <time.h>
 typedef struct {
 	bsb200_ctx *ctx; BSPOA **gs; u4i n, *nheads, *ntails, *slot; u2i rid; b200_poa_pack_t *p;
 	int phase; volatile u4i next;
+	b200_poa_pack_t **mine;   /* per object: its sweep job of this round, packed by the object's own host thread */
 #ifdef BSALIGN_B200_POA_KMER_H
 	b200_poa_kmer_slot_t *kslot;   /* per object: the band-placement alignment of this round, computed as one GPU batch */
 #endif
@@ -239,6 +279,20 @@ typedef struct {
 static inline void b200_poa_round_object(b200_poa_round_t *r, u4i k){
 	BSPOA *g = r->gs[k];
 	u2i rid = r->rid;
+	if(r->phase == 4){   /* bspoa.h:4726-4751: the reads into the graph */
+		clear_u1v(g->cns); clear_u1v(g->qlt); clear_u1v(g->alt);
+		if(g->par->refmode){
+			resize_u1v(g->cns, g->seqs->rdlens->buffer[0]); resize_u1v(g->qlt, g->seqs->rdlens->buffer[0]); resize_u1v(g->alt, g->seqs->rdlens->buffer[0]);
+			bitseq_basebank(g->seqs->rdseqs, g->seqs->rdoffs->buffer[0], g->seqs->rdlens->buffer[0], g->cns->buffer);
+			memset(g->qlt->buffer, 0, g->seqs->rdlens->buffer[0]); memset(g->alt->buffer, 0, g->seqs->rdlens->buffer[0]);
+		}
+		if(g->seqs->nseq <= 1){ g->nmsa = 0; return; }
+		if(g->par->shuffle) shuffle_reads_by_kmers_bspoa(g);
+		g->nmsa = g->par->seqcore? num_min(g->seqs->nseq, g->par->seqcore) : g->seqs->nseq;
+		for(rid=0;rid<g->seqs->nseq;rid++) _add_read_bspoa_core(g, rid);
+		g->nrds = 1;
+		return;
+	}
 	if(r->phase == 0){   /* before the sweep: bspoa.h:4753-4755 and the head of align_rd_bspoa (bspoa.h:2620-2642) */
 		u4i rlen; u2i ridxbeg, ridxend;
 		r->slot[k] = MAX_U4;
@@ -276,6 +330,9 @@ static inline void b200_poa_round_object(b200_poa_round_t *r, u4i k){
 #endif
 		if(g->sels->size == 0){ align_rd_bspoacore(g, g->par, rid, r->nheads[k], r->ntails[k]); r->slot[k] = MAX_U4 - 1; return; }
 		r->slot[k] = MAX_U4 - 2;   /* takes part in this round's batch */
+		if(r->mine[k] == NULL) r->mine[k] = b200_poa_pack_init();
+		b200_poa_pack_clear(r->mine[k]);
+		b200_poa_pack_job(r->mine[k], g, g->par, r->nheads[k], r->ntails[k]);
 	} else if(r->phase == 1){   /* behind the sweep: the tail of align_rd_bspoa (bspoa.h:2652-2666) */
 		u4i t;
 		if(r->slot[k] == MAX_U4) return;
@@ -391,58 +448,219 @@ static inline void b200_poa_kmer_round(b200_poa_round_t *r){
 }
 #endif
 
+#ifdef BSALIGN_B200_POA_REMSA_H
+/* ---- remsa_pedits_bspoa (bspoa.h:4178-4457) of all in-flight objects with its DP on the GPU -------------------------------------------
+ * Phase 2 of every object (bspoa.h:4764-4777, the reference's own code) runs on its own host thread with the hook of
+ * bsalign_b200_poa_remsa.h installed.  Whenever an object reaches remsa_pedit_rd_bspoacore (once per read and round) its thread puts
+ * the call's inputs - the ten arrays as they lie in g->memp - into the shared arena and waits; when every object still inside phase 2
+ * waits, the last one to arrive runs them as ONE bsb200_remsa_batch (the rendezvous: one job per object) and wakes the others; every
+ * thread then replays the walk's merge_nodes_bspoa calls (bspoa.h:4012-4023) from the matched columns that came back, in the walk's
+ * order, and returns the walk's score to remsa_pedits_bspoa, which carries on (connect_rdnodes_bspoa, next read).  Objects that finish
+ * leave the rendezvous.  B200_REMSA_BATCH_FN: the batch entry point (tests substitute a CPU checker to exercise this driver without a GPU). */
+#ifndef B200_REMSA_BATCH_FN
+#define B200_REMSA_BATCH_FN bsb200_remsa_batch
+#endif
+#ifndef B200_REMSA_MAX_INFLIGHT
+#define B200_REMSA_MAX_INFLIGHT 1024
+#endif
+typedef struct { int32_t hdr[8], out[4]; uint64_t in_off, match_off; const u1i *src[2]; uint32_t sz1; int late; } b200_remsa_job_t;
+typedef struct {
+	pthread_mutex_t mu; pthread_cond_t cv;
+	bsb200_ctx *ctx;
+	u4i active, waiting, reserved, cap_jobs; unsigned long gen;
+	b200_remsa_job_t **jobs;
+	uint8_t *in; uint64_t in_bytes, cap_in;
+	int32_t *match; uint64_t match_ints, cap_match;
+	int32_t *hdr, *out; uint64_t *in_off, *match_off;
+} b200_remsa_rv_t;
+static b200_remsa_rv_t *b200_remsa_rv = NULL;
+static unsigned long b200_poa_remsa_batches = 0, b200_poa_remsa_jobs = 0;
+
+/* called with the lock held once every active object waits */
+static inline void b200_remsa_launch(b200_remsa_rv_t *rv){
+	u4i j, n = rv->waiting;
+	if(rv->in_bytes > rv->cap_in){   /* jobs that found no room (late) are copied here; the others' bytes move with realloc */
+		rv->cap_in = rv->in_bytes + rv->in_bytes / 4 + 4096;
+		rv->in = (uint8_t*)realloc(rv->in, rv->cap_in);
+	}
+	if(rv->match_ints > rv->cap_match){ rv->cap_match = rv->match_ints + rv->match_ints / 4 + 1024; free(rv->match); rv->match = (int32_t*)malloc(sizeof(int32_t) * rv->cap_match); }
+	if(rv->in == NULL || rv->match == NULL){ fflush(stdout); fprintf(stderr, " -- Out of memory in %s -- %s:%d --\n", __FUNCTION__, __FILE__, __LINE__); fflush(stderr); abort(); }
+	for(j=0;j<n;j++){
+		b200_remsa_job_t *jb = rv->jobs[j];
+		if(jb->late){
+			memcpy(rv->in + jb->in_off, jb->src[0], 2 * (size_t)jb->sz1);
+			memcpy(rv->in + jb->in_off + 2 * (size_t)jb->sz1, jb->src[1], 8 * (size_t)jb->sz1);
+		}
+		memcpy(rv->hdr + 8 * (size_t)j, jb->hdr, sizeof(jb->hdr));
+		rv->in_off[j] = jb->in_off; rv->match_off[j] = jb->match_off;
+	}
+	if(B200_REMSA_BATCH_FN(rv->ctx, n, rv->hdr, rv->in, rv->in_off, rv->in_bytes, rv->match, rv->match_off, rv->match_ints, rv->out, NULL, NULL)){
+		fflush(stdout); fprintf(stderr, " -- bsalign_b200: %s in %s -- %s:%d --\n", rv->ctx ? bsb200_last_error(rv->ctx) : "remsa batch failed", __FUNCTION__, __FILE__, __LINE__); fflush(stderr);
+		abort();
+	}
+	for(j=0;j<n;j++) memcpy(rv->jobs[j]->out, rv->out + 4 * (size_t)j, sizeof(rv->jobs[j]->out));
+	b200_poa_remsa_batches ++; b200_poa_remsa_jobs += n;
+	rv->waiting = 0; rv->reserved = 0; rv->in_bytes = 0; rv->match_ints = 0; rv->gen ++;
+	pthread_cond_broadcast(&rv->cv);
+}
+
+/* what B200_REMSA_CORE calls in an object thread: remsa_pedit_rd_bspoacore's contract (bspoa.h:3916-4045) - the read's nodes merged into
+ * the msa nodes of the columns the walk matched them to, the walk's score returned - minus the DP matrices, which nothing reads afterwards */
+static inline int b200_remsa_core_hook(void *gp, u2i rid, u4i rbeg, u4i rend, u1i **matrix, u1i **seqs, u1i *(*mats)[4], int mlen, int mbeg, int mend, int W){
+	BSPOA *g = (BSPOA*)gp;
+	b200_remsa_rv_t *rv = b200_remsa_rv;
+	b200_remsa_job_t job;
+	const u4i bw = W * WORDSIZE, HW = bw / 2;
+	const int32_t *m;
+	u4i roff;
+	UNUSED(rbeg); UNUSED(matrix);
+	memset(&job, 0, sizeof(job));
+	job.hdr[0] = mlen; job.hdr[1] = bw; job.hdr[2] = mbeg; job.hdr[3] = mend; job.hdr[4] = rend;
+	job.sz1 = roundup_times(mlen + bw, WORDSIZE);
+	job.src[0] = seqs[0] - HW;       /* seqs[0], seqs[1]: bspoa.h:4209-4210, :4228-4229 */
+	job.src[1] = mats[0][0] - HW;    /* mats[0][0..3], mats[1][0..3]: bspoa.h:4216-4223 */
+	pthread_mutex_lock(&rv->mu);
+	job.in_off = rv->in_bytes; job.match_off = rv->match_ints;
+	rv->in_bytes += 10 * (uint64_t)job.sz1; rv->match_ints += rend;
+	job.late = rv->in_bytes > rv->cap_in;
+	rv->jobs[rv->reserved ++] = &job;
+	pthread_mutex_unlock(&rv->mu);
+	if(!job.late){   /* the arena only moves inside b200_remsa_launch, which needs this thread to wait first */
+		memcpy(rv->in + job.in_off, job.src[0], 2 * (size_t)job.sz1);
+		memcpy(rv->in + job.in_off + 2 * (size_t)job.sz1, job.src[1], 8 * (size_t)job.sz1);
+	}
+	pthread_mutex_lock(&rv->mu);
+	rv->waiting ++;
+	if(rv->waiting == rv->active) b200_remsa_launch(rv);
+	else { unsigned long gen0 = rv->gen; while(rv->gen == gen0) pthread_cond_wait(&rv->cv, &rv->mu); }
+	pthread_mutex_unlock(&rv->mu);
+	if(job.out[1]){
+		fflush(stdout); fprintf(stderr, " -- bsalign_b200: re-alignment of read %u left its band (status %d) in %s -- %s:%d --\n", (unsigned)rid, job.out[1], __FUNCTION__, __FILE__, __LINE__); fflush(stderr);
+		abort();   /* the reference aborts here too (bspoa.h:3982-3985, :4027-4030) */
+	}
+	m = rv->match + job.match_off;
+	for(roff=rend;roff-->0;){
+		if(m[roff] >= 0){
+			bspoanode_t *v = get_rdnode_bspoa(g, rid, roff);
+			bspoanode_t *u = get_rdnode_bspoa(g, g->seqs->nseq + 1 + v->base, m[roff]);
+			merge_nodes_bspoa(g, u, v);
+		}
+	}
+	return job.out[0];
+}
+
+typedef struct { b200_poa_round_t *r; u4i k; } b200_remsa_thr_t;
+static void *b200_remsa_object_thread(void *arg){
+	b200_remsa_thr_t *t = (b200_remsa_thr_t*)arg;
+	b200_remsa_rv_t *rv = b200_remsa_rv;
+	b200_remsa_core_fn = b200_remsa_core_hook;
+	b200_poa_round_object(t->r, t->k);
+	b200_remsa_core_fn = NULL;
+	pthread_mutex_lock(&rv->mu);
+	rv->active --;
+	if(rv->waiting && rv->waiting == rv->active) b200_remsa_launch(rv);
+	pthread_mutex_unlock(&rv->mu);
+	return NULL;
+}
+
+/* phase 2 (bspoa.h:4764-4777) of all objects, up to B200_REMSA_MAX_INFLIGHT at a time, one host thread each */
+static inline void b200_poa_realign_run(b200_poa_round_t *r){
+	b200_remsa_rv_t rv;
+	pthread_t *th = (pthread_t*)malloc(sizeof(pthread_t) * B200_REMSA_MAX_INFLIGHT);
+	b200_remsa_thr_t *ta = (b200_remsa_thr_t*)malloc(sizeof(b200_remsa_thr_t) * B200_REMSA_MAX_INFLIGHT);
+	u4i beg, cnt, t;
+	memset(&rv, 0, sizeof(rv));
+	pthread_mutex_init(&rv.mu, NULL); pthread_cond_init(&rv.cv, NULL);
+	rv.ctx = r->ctx;
+	rv.cap_jobs = B200_REMSA_MAX_INFLIGHT;
+	rv.jobs = (b200_remsa_job_t**)malloc(sizeof(b200_remsa_job_t*) * rv.cap_jobs);
+	rv.hdr = (int32_t*)malloc(sizeof(int32_t) * 12 * (size_t)rv.cap_jobs); rv.out = rv.hdr + 8 * (size_t)rv.cap_jobs;
+	rv.in_off = (uint64_t*)malloc(sizeof(uint64_t) * 2 * (size_t)rv.cap_jobs); rv.match_off = rv.in_off + rv.cap_jobs;
+	b200_remsa_rv = &rv;
+	r->phase = 2; r->rid = 0;
+	for(beg=0;beg<r->n;beg+=cnt){
+		cnt = num_min(r->n - beg, (u4i)B200_REMSA_MAX_INFLIGHT);
+		rv.active = cnt; rv.waiting = 0; rv.reserved = 0; rv.in_bytes = 0; rv.match_ints = 0;
+		for(t=0;t<cnt;t++){
+			ta[t].r = r; ta[t].k = beg + t;
+			if(pthread_create(&th[t], NULL, b200_remsa_object_thread, ta + t)){
+				fflush(stdout); fprintf(stderr, " -- cannot start a host thread per in-flight object in %s -- %s:%d --\n", __FUNCTION__, __FILE__, __LINE__); fflush(stderr);
+				abort();
+			}
+		}
+		for(t=0;t<cnt;t++) pthread_join(th[t], NULL);
+	}
+	b200_remsa_rv = NULL;
+	free(rv.jobs); free(rv.hdr); free(rv.in_off); free(rv.in); free(rv.match); free(th); free(ta);
+	pthread_mutex_destroy(&rv.mu); pthread_cond_destroy(&rv.cv);
+}
+
+/* the realn rounds + final msa / cns (bspoa.h:4764-4777) of n objects whose reads are all in their graphs */
+static inline void b200_poa_realign_batch(bsb200_ctx *ctx, BSPOA **gs, u4i n){
+	b200_poa_round_t rd;
+	memset(&rd, 0, sizeof(rd));
+	rd.ctx = ctx; rd.gs = gs; rd.n = n;
+	b200_poa_realign_run(&rd);
+}
+#endif
+
 static inline void b200_end_bspoa_batch(bsb200_ctx *ctx, BSPOA **gs, u4i n){
 	b200_poa_pack_t *p = b200_poa_pack_init();
 	u4i k, maxr = 0, *nheads, *ntails, *slot;
 	u2i rid;
 	int i;
 	nheads = (u4i*)malloc(sizeof(u4i) * (n + 1)); ntails = (u4i*)malloc(sizeof(u4i) * (n + 1)); slot = (u4i*)malloc(sizeof(u4i) * (n + 1));
-	for(k=0;k<n;k++){   /* bspoa.h:4726-4751 */
-		BSPOA *g = gs[k];
-		clear_u1v(g->cns); clear_u1v(g->qlt); clear_u1v(g->alt);
-		if(g->par->refmode){
-			resize_u1v(g->cns, g->seqs->rdlens->buffer[0]); resize_u1v(g->qlt, g->seqs->rdlens->buffer[0]); resize_u1v(g->alt, g->seqs->rdlens->buffer[0]);
-			bitseq_basebank(g->seqs->rdseqs, g->seqs->rdoffs->buffer[0], g->seqs->rdlens->buffer[0], g->cns->buffer);
-			memset(g->qlt->buffer, 0, g->seqs->rdlens->buffer[0]); memset(g->alt->buffer, 0, g->seqs->rdlens->buffer[0]);
-		}
-		if(g->seqs->nseq <= 1){ g->nmsa = 0; continue; }
-		if(g->par->shuffle) shuffle_reads_by_kmers_bspoa(g);
-		g->nmsa = g->par->seqcore? num_min(g->seqs->nseq, g->par->seqcore) : g->seqs->nseq;
-		for(rid=0;rid<g->seqs->nseq;rid++) _add_read_bspoa_core(g, rid);
-		g->nrds = 1;
-		if(g->nmsa > maxr) maxr = g->nmsa;
-	}
 	{
 		b200_poa_round_t rd;
+		double lap[8] = {0, 0, 0, 0, 0, 0, 0, 0}, lap_t0, lap_t1;   /* where the wall time of a batch goes (printed with BSB200_HOSTPROF set) */
+		struct timespec lap_ts;
+#define B200_LAP(i) do { clock_gettime(CLOCK_MONOTONIC, &lap_ts); lap_t1 = lap_ts.tv_sec + 1e-9 * lap_ts.tv_nsec; lap[i] += lap_t1 - lap_t0; lap_t0 = lap_t1; } while(0)
+		clock_gettime(CLOCK_MONOTONIC, &lap_ts); lap_t0 = lap_ts.tv_sec + 1e-9 * lap_ts.tv_nsec;
 		rd.ctx = ctx; rd.gs = gs; rd.n = n; rd.nheads = nheads; rd.ntails = ntails; rd.slot = slot; rd.p = p;
+		rd.mine = (b200_poa_pack_t**)calloc(n + 1, sizeof(b200_poa_pack_t*));
+		rd.rid = 0;
+		b200_poa_round_run(&rd, 4);   /* objects are independent here too */
+		for(k=0;k<n;k++) if(gs[k]->seqs->nseq > 1 && gs[k]->nmsa > maxr) maxr = gs[k]->nmsa;
+		B200_LAP(7);
 #ifdef BSALIGN_B200_POA_KMER_H
 		rd.kslot = (b200_poa_kmer_slot_t*)calloc(n + 1, sizeof(b200_poa_kmer_slot_t));
 #endif
 		for(rid=1;rid<maxr;rid++){   /* bspoa.h:4752-4763 with align_rd_bspoa (bspoa.h:2620-2667) split around the sweep */
 			b200_poa_pack_clear(p);
 			rd.rid = rid;
-			b200_poa_round_run(&rd, 0);
+			b200_poa_round_run(&rd, 0); B200_LAP(0);
 #ifdef BSALIGN_B200_POA_KMER_H
-			b200_poa_kmer_round(&rd);
-			b200_poa_round_run(&rd, 3);
+			b200_poa_kmer_round(&rd); B200_LAP(1);
+			b200_poa_round_run(&rd, 3); B200_LAP(2);
 #endif
 			for(k=0;k<n;k++){   /* the batch is packed in object order */
 				if(slot[k] != MAX_U4 - 2) continue;
 				slot[k] = p->njobs;
-				b200_poa_pack_job(p, gs[k], gs[k]->par, nheads[k], ntails[k]);
+				b200_poa_pack_append(p, rd.mine[k]);
 			}
+			B200_LAP(3);
 #ifdef BSALIGN_B200_POA_HOST_TRACEBACK
 			b200_poa_pack_run(ctx, p);
 #else
 			b200_poa_pack_run_walk(ctx, p);
 #endif
-			b200_poa_round_run(&rd, 1);
+			B200_LAP(4);
+			b200_poa_round_run(&rd, 1); B200_LAP(5);
 		}
 		rd.rid = 0;
+#ifdef BSALIGN_B200_POA_REMSA_H
+		b200_poa_realign_run(&rd);   /* the re-alignment DPs of all objects as GPU batches (bsalign_b200_poa_remsa.h) */
+#else
 		b200_poa_round_run(&rd, 2);
+#endif
+		B200_LAP(6);
+		if(getenv("BSB200_HOSTPROF")) fprintf(stderr, "[end_bspoa_batch] %u objects, %u rounds: reads into the graphs %.3f s, before the sweep %.3f s, k-mer batches %.3f s, band placement %.3f s, packing %.3f s, "
+			"sweep + walk (GPU) %.3f s, graph surgery %.3f s, realn rounds + final msa / cns %.3f s\n", n, maxr, lap[7], lap[0], lap[1], lap[2], lap[3], lap[4], lap[5], lap[6]);
 #ifdef BSALIGN_B200_POA_KMER_H
 		free(rd.kslot);
 #endif
+		for(k=0;k<n;k++) if(rd.mine[k]) b200_poa_pack_free(rd.mine[k]);
+		free(rd.mine);
 	}
 	free(nheads); free(ntails); free(slot);
 	b200_poa_pack_free(p);

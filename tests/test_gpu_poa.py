@@ -128,6 +128,30 @@ def test_poa_dropin_end_bspoa_identical_msa():
             assert "kmer_pairs=" in out.stdout and "kmer_pairs=0" not in out.stdout, out.stdout
 
 
+def test_poa_dropin_realign_rounds_on_gpu_identical_msa():
+    """The re-alignment rounds (remsa_pedits_bspoa, bspoa.h:4178-4457) with the DP + walk of every read (remsa_pedit_rd_bspoacore,
+    bspoa.h:3916-4045) on the GPU: include/bsalign_b200_poa_remsa.h + b200_poa_realign_run, one bsb200_remsa_batch per rendezvous of the
+    in-flight objects.  Whole jobs through b200_end_bspoa_batch against the reference's end_bspoa: byte-identical consensus + MSA,
+    including objects with different read counts (they leave the rendezvous early) and one full-shape job (64 reads x 15 kb)."""
+    import os
+    import re
+    import subprocess
+    ref_dir = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "oracle", "_ref")
+    exe = os.path.join(ref_dir, "poa_remsa_dropin")
+    if not os.path.exists(exe):
+        pytest.skip("oracle/_ref/poa_remsa_dropin was not built (no reference tree at build time)")
+    for args, reads_min in ((["6", "12", "1500", "3"], 12), (["5", "10", "3000", "5", "2", "6"], 10), (["1", "64", "15000", "7"], 64)):
+        out = subprocess.run([exe] + args, capture_output=True, text=True, timeout=900)
+        assert out.returncode == 0, out.stdout + out.stderr
+        assert "identical=%s/%s" % (args[0], args[0]) in out.stdout, out.stdout
+        realn = int(args[4]) if len(args) > 4 else 3
+        m = re.search(r"remsa_batches=(\d+) remsa_jobs=(\d+)", out.stdout)
+        # every re-aligned read of every object and round went through bsb200_remsa_batch (beyond par.seqcore = 40 reads only the last
+        # round takes all reads, bspoa.h:4188 / :4346)
+        core = min(reads_min, 40)
+        assert m and int(m.group(2)) >= int(args[0]) * core * realn and int(m.group(1)) >= core * realn, out.stdout
+
+
 def _as_dump_like(job):
     """A bsalign_b200.poa.SweepJob viewed through the attribute names the checker helpers use."""
     w = pj.SweepJob()

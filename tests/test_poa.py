@@ -100,3 +100,20 @@ def test_oracle_walk_matches_live_reference():
         for j in pj.ref_dump(pj.make_reads(12, 1200, 17, *err), par):
             match, out = pj.oracle_backtrace(j, j.rows, j.ub, j.maxidx, j.maxoff)
             assert pj.compare_backtrace(j, match, out) is None
+
+
+def test_realign_driver_rendezvous_with_cpu_checker():
+    """The re-alignment driver of include/bsalign_b200_poa_compat.h (b200_poa_realign_run: one host thread per in-flight object, the
+    rendezvous, the hook of bsalign_b200_poa_remsa.h, the replay of merge_nodes_bspoa from the matched columns) with the batch entry point
+    replaced by the oracle's scalar core (oracle/poa_remsa_dropin_test.c, -DREMSA_CPU_CHECK: no GPU needed) against the reference's own
+    end_bspoa: byte-identical consensus + MSA, also when objects hold different numbers of reads and leave the rendezvous early.  The GPU
+    arm of the same program is tests/test_gpu_poa.py::test_poa_dropin_realign_rounds_on_gpu_identical_msa."""
+    import os
+    import subprocess
+    exe = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "oracle", "_ref", "poa_remsa_dropin_cpu")
+    if not os.path.exists(exe):
+        pytest.skip("oracle/_ref/poa_remsa_dropin_cpu was not built (no reference tree at build time)")
+    for args in (["4", "8", "1200", "3"], ["5", "6", "2000", "5", "2", "5"]):
+        out = subprocess.run([exe] + args, capture_output=True, text=True, timeout=300)
+        assert out.returncode == 0, out.stdout + out.stderr
+        assert "identical=%s/%s" % (args[0], args[0]) in out.stdout and "remsa_jobs=0" not in out.stdout, out.stdout
