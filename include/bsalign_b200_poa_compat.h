@@ -394,6 +394,9 @@ static inline void b200_poa_round_run(b200_poa_round_t *r, int phase){
 static uint32_t *b200_poa_kmer_cig = NULL; static uint64_t b200_poa_kmer_cigcap = 0;
 static uint8_t *b200_poa_kmer_arena = NULL; static uint64_t b200_poa_kmer_arenacap = 0;
 static unsigned long b200_poa_kmer_batches = 0, b200_poa_kmer_pairs = 0;
+/* a round with fewer alignments than this keeps the reference's CPU call on the objects' host threads (a batch of 15 kb reads costs the
+ * GPU ~150 ms however few pairs it holds; 64 of them cost 16 cores ~20 ms: the batch pays from a few hundred objects on).  1 = always GPU. */
+static int b200_poa_kmer_min_pairs = 1;
 static inline void b200_poa_kmer_round(b200_poa_round_t *r){
 	u4i k, m = 0, ksz;
 	uint64_t *qoff, *toff, *cgoff, bytes = 0, words = 0;
@@ -401,6 +404,10 @@ static inline void b200_poa_kmer_round(b200_poa_round_t *r){
 	bsb200_result_t *res;
 	for(k=0;k<r->n;k++) if(r->slot[k] == MAX_U4 - 3 && r->kslot[k].armed == -1) m ++;
 	if(m == 0) return;
+	if((int)m < b200_poa_kmer_min_pairs){
+		for(k=0;k<r->n;k++) if(r->slot[k] == MAX_U4 - 3 && r->kslot[k].armed == -1) r->kslot[k].armed = 0;
+		return;
+	}
 	qoff = (uint64_t*)malloc(sizeof(uint64_t) * (3 * (size_t)m + 1)); toff = qoff + m; cgoff = toff + m;
 	qlen = (uint32_t*)malloc(sizeof(uint32_t) * 4 * (size_t)m); tlen = qlen + m; ncg = tlen + m; idx = ncg + m;
 	res = (bsb200_result_t*)malloc(sizeof(bsb200_result_t) * m);
@@ -475,6 +482,9 @@ typedef struct {
 } b200_remsa_rv_t;
 static b200_remsa_rv_t *b200_remsa_rv = NULL;
 static unsigned long b200_poa_remsa_batches = 0, b200_poa_remsa_jobs = 0;
+/* with fewer objects than this the realn rounds keep the reference's CPU core on b200_poa_host_threads threads (a rendezvous of 20k-column
+ * jobs costs ~30 ms however few objects take part; 64 such jobs cost 16 cores ~6 ms).  1 = always GPU. */
+static int b200_poa_remsa_min_objects = 1;
 
 /* called with the lock held once every active object waits */
 static inline void b200_remsa_launch(b200_remsa_rv_t *rv){
@@ -569,6 +579,7 @@ static inline void b200_poa_realign_run(b200_poa_round_t *r){
 	pthread_t *th = (pthread_t*)malloc(sizeof(pthread_t) * B200_REMSA_MAX_INFLIGHT);
 	b200_remsa_thr_t *ta = (b200_remsa_thr_t*)malloc(sizeof(b200_remsa_thr_t) * B200_REMSA_MAX_INFLIGHT);
 	u4i beg, cnt, t;
+	if((int)r->n < b200_poa_remsa_min_objects){ free(th); free(ta); b200_poa_round_run(r, 2); return; }
 	memset(&rv, 0, sizeof(rv));
 	pthread_mutex_init(&rv.mu, NULL); pthread_cond_init(&rv.cv, NULL);
 	rv.ctx = r->ctx;

@@ -12,7 +12,7 @@
  *          rounds with the batch entry point replaced by the oracle's scalar core: exercises the rendezvous, the hook and the merge
  *          replay on a box without a GPU (tests/test_poa.py).
  * Consensus, qualities, alternative bases and the whole MSA matrix must be byte-identical.
- * Usage: poa_remsa_dropin <jobs> <reads per job> <template length> <seed> [realn] [reads per job vary by up to this many]
+ * Usage: poa_remsa_dropin <jobs> <reads per job> <template length> <seed> [realn] [reads per job vary by up to this many] [b200_poa_remsa_min_objects]
  */
 #include "bsalign.h"
 #include "bsalign_b200_poa_kmer.h"
@@ -88,6 +88,7 @@ int main(int argc, char **argv){
 	rng_state = (argc > 4 ? strtoull(argv[4], NULL, 10) : 1) * 0x9E3779B97F4A7C15ULL + 88172645463325252ULL;
 	if(argc > 5) par.realn = atoi(argv[5]);
 	realn = par.realn;
+	if(argc > 7){ b200_poa_remsa_min_objects = atoi(argv[7]); b200_poa_host_threads = 0; }
 #ifdef REMSA_CPU_CHECK
 	par.shuffle = 0;   /* arm B runs the tail of end_bspoa twice (realn = 0, then the rounds): the read order must not be restored twice */
 #endif

@@ -117,3 +117,6 @@ def test_realign_driver_rendezvous_with_cpu_checker():
         out = subprocess.run([exe] + args, capture_output=True, text=True, timeout=300)
         assert out.returncode == 0, out.stdout + out.stderr
         assert "identical=%s/%s" % (args[0], args[0]) in out.stdout and "remsa_jobs=0" not in out.stdout, out.stdout
+    # below b200_poa_remsa_min_objects the rounds keep the reference's core on the worker threads: same result, no batch
+    out = subprocess.run([exe, "3", "6", "1000", "9", "2", "0", "100"], capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0 and "identical=3/3" in out.stdout and "remsa_jobs=0 " in out.stdout, out.stdout + out.stderr
