@@ -9,8 +9,10 @@
 //
 // Mapping: one THREAD per pair (a 300x300 pair at band 64 is one machine word per row), 32 pairs of similar
 // length per warp, rows of the 32 pairs interleaved in the HBM trace so that every warp-wide row store is
-// one contiguous 256-byte line per plane.  Forward sweep and backtrace are fused in one kernel: the
-// trace of a pair is still L2-resident when its own thread walks it back.
+// one contiguous 256-byte line per plane.  Forward sweep and backtrace are fused in one kernel, which saves a launch and the
+// per-pair state, not the traffic: at configs[3]'s size the interleaved trace of all resident warps (> 1 GB per 200k pairs) does not
+// stay in the 126 MB L2, so the walk reads it back from HBM once (ncu: 1.05 GB written + 1.08 GB read per 200k pairs, DRAM / algorithmic
+// bytes 1.76; profiles/ncu_full_edit_c4_200kpairs_r2.txt).
 #pragma once
 #include "common.cuh"
 #include <stdint.h>
